@@ -1,0 +1,95 @@
+"""ctypes binding of ``libdeluca_b200.so`` (the C ABI declared in ``include/deluca_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing, or the device is not a
+Blackwell (sm_100) part, every entry point raises.  Nothing here imports ``oracle/``.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeluca_b200.so")
+
+c_f32p = ctypes.c_void_p  # device pointers travel as integers
+_lock = threading.Lock()
+_lib = None
+
+
+class DlcError(RuntimeError):
+    """Raised when an ABI call returns non-zero (message from ``dlc_last_error``)."""
+
+
+class DlcLdsParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int64),
+        ("env_offset", ctypes.c_int64),
+        ("T", ctypes.c_int32),
+        ("d", ctypes.c_int32),
+        ("m", ctypes.c_int32),
+        ("H", ctypes.c_int32),
+        ("HH", ctypes.c_int32),
+        ("policy", ctypes.c_int32),
+        ("t0", ctypes.c_int32),
+        ("decay", ctypes.c_int32),
+        ("noise_uses_prev_action", ctypes.c_int32),
+        ("shared_dynamics", ctypes.c_int32),
+        ("traj_stride", ctypes.c_int32),
+        ("lr_scale", ctypes.c_float),
+        ("w_std", ctypes.c_float),
+        ("bpc_delta", ctypes.c_float),
+        ("kernel_variant", ctypes.c_int32),
+        ("seed", ctypes.c_uint64),
+    ]
+
+
+POLICY = {"lqr": 0, "gpc": 1, "bpc": 2}
+
+# every symbol include/deluca_b200.h declares: name -> (restype, argtypes)
+_P = ctypes.c_void_p
+SYMBOLS = {
+    "dlc_abi_version": (ctypes.c_int32, []),
+    "dlc_last_error": (ctypes.c_char_p, []),
+    "dlc_check_device": (ctypes.c_int32, []),
+    "dlc_gaussian_disturbance_f32": (ctypes.c_int32, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                      ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32,
+                                                      ctypes.c_float, _P]),
+    "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),
+    "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
+    "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 17
+                            + [_P, ctypes.c_size_t, _P]),
+}
+
+
+def lib():
+    """Load the shared library once.  Raises if it has not been built (``make -C deluca_b200/csrc``
+    or ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise ImportError(
+                    f"{LIB_PATH} not found: build it with `make -C deluca_b200/csrc` "
+                    "(there is no CPU fallback)")
+            L = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dlc_last_error().decode("utf-8", "replace")
+        raise DlcError(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,24 @@
+// ABI plumbing shared by every entry point of libdeluca_b200.so.
+#include "common.cuh"
+
+namespace dlc {
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+}  // namespace dlc
+
+extern "C" int32_t dlc_abi_version(void) { return DLC_ABI_VERSION; }
+
+extern "C" const char* dlc_last_error(void) { return dlc::last_error_buf(); }
+
+extern "C" int32_t dlc_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return dlc::cuda_status(e, "cudaGetDevice");
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return dlc::cuda_status(e, "cudaDeviceGetAttribute");
+  if (major != 10) return dlc::fail(DLC_ERR_DEVICE, "libdeluca_b200 is built for sm_100a only");
+  return DLC_OK;
+}

@@ -1,0 +1,788 @@
+// Fused LDS + {LQR, GPC, BPC} rollout kernels.  See include/deluca_b200.h for
+// the reference lines each piece stands for; DESIGN.md section 3 for the layout/roofline.
+//
+// Two kernels:
+//   lds_tpe_kernel<D,M,H,HH,POLICY>  "thread per env", dims compile-time.  A and GPC's M live in
+//       registers, B, K and the disturbance-history ring live in shared memory laid out
+//       [element][thread] (bank = thread, so every access is conflict-free); the T-step loop is
+//       fused, only costs / sampled trajectories / final state go back to HBM.
+//   lds_generic_kernel               any (d,m,H,HH,policy incl. BPC), runtime dims, per-env state in
+//       a global-memory workspace laid out [element][env] (coalesced).  Correct for every shape
+//       the reference accepts (including the dynamic_slice clamping of HH < H-1); not tuned.
+#include "common.cuh"
+
+namespace dlc {
+
+struct LdsArgs {
+  DlcLdsParams p;
+  const float *A, *B, *K, *W;
+  float *x_io, *M_io, *hist_io, *xprev_io, *uprev_io, *eps_io;
+  const float* eps_new;
+  float* cost_out;
+  double* cost_sum_out;
+  float *x_out, *u_out;
+  int32_t* status_out;
+  float* ws;
+};
+
+// ------------------------------------------------------------------------------------------
+// lane-split kernel: L adjacent lanes of a warp own one env.
+//
+// Lane q of a group owns the state coordinates S_q = [q*DL, q*DL+DL) (DL = ceil(D/L); coordinates
+// >= D are zero padding) and keeps, in REGISTERS, everything indexed by them:
+//     rows S_q of A and B, columns S_q of K and of every M[i], and x/y/lambda restricted to S_q.
+// The disturbance-history ring (columns S_q only) is the one structure indexed dynamically; it
+// lives in shared memory as [slot][k][thread] (bank = thread: conflict-free).
+// Vectors that a lane needs in full are exchanged with xor-shuffles and kept in LANE-RELATIVE
+// order: chunk c of a gathered vector holds the coordinates of lane q^c, so every register index
+// is a compile-time constant.  A's rows are stored with their columns permuted the same way.
+//     A y      : all-gather y, then own rows            ((L-1)*DL shuffles)
+//     A' lam   : partial sums over own rows, reduce-scatter ((L-1)*DL shuffles)
+//     K y, B' lam, M-window products: partial sums over own coordinates, all-reduce (m*log2 L)
+//     K' du, B v, rank-1 updates of M: local.
+// ------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ float group_allreduce(float v) {
+#pragma unroll
+  for (int o = 1; o < L; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int D, int M, int H, int HH, int POLICY, int L, int TPB>
+struct SplitLayout {
+  static constexpr int DL = (D + L - 1) / L;
+  static constexpr int P = H + HH;
+  static constexpr int kFloats = POLICY == DLC_POLICY_GPC ? P * DL : 0;  // per thread
+  static constexpr size_t kSmemBytes = (size_t)kFloats * TPB * sizeof(float);
+};
+
+template <int D, int M, int H, int HH, int POLICY, int L, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
+  using Lay = SplitLayout<D, M, H, HH, POLICY, L, TPB>;
+  constexpr int DL = Lay::DL, DF = DL * L, P = Lay::P;
+  constexpr bool GPC = POLICY == DLC_POLICY_GPC;
+  static_assert(!GPC || HH >= H - 1, "templated path needs HH >= H-1 (no index clamping)");
+  static_assert(L == 1 || L == 2 || L == 4, "group size");
+  extern __shared__ float sm[];
+  const DlcLdsParams& p = a.p;
+  const int tid = threadIdx.x;
+  const int q = tid % L;  // lane within the group
+  const int64_t n_raw = ((int64_t)blockIdx.x * TPB + tid) / L;
+  const bool live = n_raw < p.N;
+  const int64_t n = live ? n_raw : p.N - 1;  // idle groups shadow the last env (keeps shuffles whole)
+  float* const sH = sm + tid;                // ring element (slot, k): sH[(slot*DL + k) * TPB]
+
+  // ---- parameters -> registers
+  const int64_t np = p.shared_dynamics ? 0 : n;
+  float Ar[DL][DF], Br[DL][M], Kc[M][DL];
+#pragma unroll
+  for (int i = 0; i < DL; ++i) {
+    const int gi = q * DL + i;
+#pragma unroll
+    for (int c = 0; c < L; ++c)
+#pragma unroll
+      for (int k = 0; k < DL; ++k) {
+        const int gj = (q ^ c) * DL + k;
+        Ar[i][c * DL + k] = (gi < D && gj < D) ? __ldg(a.A + np * (D * D) + gi * D + gj) : 0.f;
+      }
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      Br[i][c] = gi < D ? __ldg(a.B + np * (D * M) + gi * M + c) : 0.f;
+      Kc[c][i] = gi < D ? __ldg(a.K + np * (M * D) + c * D + gi) : 0.f;
+    }
+  }
+  float x[DL], ax[DL], uprev[M];
+#pragma unroll
+  for (int k = 0; k < DL; ++k) x[k] = (q * DL + k < D) ? a.x_io[n * D + q * DL + k] : 0.f;
+  float Mr[GPC ? H : 1][M][DL];
+  int head = 0;
+  if (GPC) {
+#pragma unroll
+    for (int i = 0; i < H; ++i)
+#pragma unroll
+      for (int c = 0; c < M; ++c)
+#pragma unroll
+        for (int k = 0; k < DL; ++k)
+          Mr[i][c][k] = (q * DL + k < D) ? a.M_io[n * (H * M * D) + (i * M + c) * D + q * DL + k] : 0.f;
+#pragma unroll
+    for (int s = 0; s < P; ++s)
+#pragma unroll
+      for (int k = 0; k < DL; ++k)
+        sH[(s * DL + k) * TPB] = (q * DL + k < D) ? a.hist_io[n * (P * D) + s * D + q * DL + k] : 0.f;
+    // ax = A * (previous observed state).  The reference recomputes it every step (_gpc.py:155);
+    // here the env step, which forms the same product, hands it to the next step.
+    float xf[DF];
+#pragma unroll
+    for (int k = 0; k < DL; ++k) xf[k] = (q * DL + k < D) ? a.xprev_io[n * D + q * DL + k] : 0.f;
+#pragma unroll
+    for (int c = 1; c < L; ++c)
+#pragma unroll
+      for (int k = 0; k < DL; ++k) xf[c * DL + k] = __shfl_xor_sync(0xffffffffu, xf[k], c);
+#pragma unroll
+    for (int i = 0; i < DL; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < DF; ++r) s = fmaf(Ar[i][r], xf[r], s);
+      ax[i] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < M; ++c) uprev[c] = a.uprev_io ? a.uprev_io[n * M + c] : 0.f;
+  }
+
+  const bool sampled = live && (a.x_out || a.u_out) && (n % p.traj_stride == 0);
+  const int64_t ns = n / p.traj_stride;
+  const int64_t Ns = (p.N + p.traj_stride - 1) / p.traj_stride;
+  const uint32_t env_id = (uint32_t)(p.env_offset + n);
+  double csum = 0.0;
+
+  // disturbance for own coordinates at step t
+  auto load_w = [&](int t, float w[DL]) {
+    if (a.W) {
+      const float* gw = a.W + ((int64_t)t * p.N + n) * D + q * DL;
+#pragma unroll
+      for (int k = 0; k < DL; ++k) w[k] = (q * DL + k < D) ? __ldg(gw + k) : 0.f;
+    } else {
+      // own coordinates span at most (DL+6)/4 Philox groups
+      constexpr int NG = L == 1 ? (DL + 3) / 4 : (DL + 6) / 4;
+      const int g0 = (q * DL) / 4;
+      float z[NG * 4];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g0 + g, 0u, z + 4 * g);
+      const int off = q * DL - g0 * 4;  // 0..3
+#pragma unroll
+      for (int k = 0; k < DL; ++k) {
+        float zz = z[k];
+#pragma unroll
+        for (int o = 1; o < 4; ++o)
+          if (k + o < NG * 4) zz = (off == o) ? z[k + o] : zz;
+        w[k] = (q * DL + k < D) ? p.w_std * zz : 0.f;
+      }
+    }
+  };
+  float wnext[DL];
+  if (p.T > 0) load_w(0, wnext);
+
+  auto slot = [&](int k) {  // physical base of logical (post-shift) ring index k
+    int s = head + k;
+    s -= (s >= P) ? P : 0;
+    return sH + s * (DL * TPB);
+  };
+
+  for (int t = 0; t < p.T; ++t) {
+    float w_t[DL];
+#pragma unroll
+    for (int k = 0; k < DL; ++k) w_t[k] = wnext[k];
+    if (t + 1 < p.T) load_w(t + 1, wnext);  // issued early: HBM latency / MUFU work overlaps the step
+
+    // ---- partial sums over own coordinates, reduced together:
+    //      red[0..M)            K x                                   _lqr.py:72
+    //      red[M..2M)           mw  = sum_i M[i] hist[HH+i]           _gpc.py:171-183
+    //      red[2M + h*M + c]    v_h = sum_i M[i] w[h+i], h < H-1      _gpc.py:112-116
+    constexpr int NR = GPC ? M * (H + 1) : M;
+    float red[NR];
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < DL; ++k) s = fmaf(Kc[c][k], x[k], s);
+      red[c] = s;
+    }
+    if (GPC) {
+      // After this step's ring shift every stored noise drops one logical index, so the action
+      // window hist[HH..HH+H) of the old ring is window [HH-1..HH+H-1) of the new one -- the final
+      // window of policy_loss: mw serves both.  No M-window product depends on the simulated state
+      // y nor on the noise appended below (their indices are <= P-2), so all are formed up front.
+      head = (head + 1 == P) ? 0 : head + 1;  // roll(-1)               _gpc.py:156-157
+#pragma unroll
+      for (int hh = 0; hh < H; ++hh) {        // hh = 0: final/action window; hh >= 1: v_{hh-1}
+        const int base = hh == 0 ? HH - 1 : hh - 1;
+        float acc[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const float* w = slot(base + i);
+#pragma unroll
+          for (int k = 0; k < DL; ++k) {
+            const float wk = w[k * TPB];
+#pragma unroll
+            for (int c = 0; c < M; ++c) acc[c] = fmaf(Mr[i][c][k], wk, acc[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < M; ++c) red[M + hh * M + c] = acc[c];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) red[r] = group_allreduce<L>(red[r]);
+    float u[M];
+#pragma unroll
+    for (int c = 0; c < M; ++c) u[c] = GPC ? red[M + c] - red[c] : -red[c];
+
+    if (GPC) {
+      // ---- noise = x - A x_prev - B u ; append                   _gpc.py:155-157
+      {
+        float* wn = slot(P - 1);
+#pragma unroll
+        for (int i = 0; i < DL; ++i) {
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < M; ++c)
+            s = fmaf(Br[i][c], p.noise_uses_prev_action ? uprev[c] : u[c], s);
+          wn[i * TPB] = (x[i] - ax[i]) - s;
+        }
+      }
+      // ---- policy_loss forward: y <- A y + B(-K y + v_h) + w[h+H]      _gpc.py:118-124
+      float y[DL];
+#pragma unroll
+      for (int k = 0; k < DL; ++k) y[k] = 0.f;
+#pragma unroll
+      for (int h = 0; h < H - 1; ++h) {
+        const float* wh = slot(h + H);
+        float v[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) v[c] = red[2 * M + h * M + c];
+        float yn[DL];
+        if (h == 0) {  // y == 0: A y and K y vanish
+#pragma unroll
+          for (int i = 0; i < DL; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < M; ++c) s = fmaf(Br[i][c], v[c], s);
+            yn[i] = s + wh[i * TPB];
+          }
+        } else {
+          float yf[DF], ky[M];
+#pragma unroll
+          for (int k = 0; k < DL; ++k) yf[k] = y[k];
+#pragma unroll
+          for (int c = 1; c < L; ++c)
+#pragma unroll
+            for (int k = 0; k < DL; ++k) yf[c * DL + k] = __shfl_xor_sync(0xffffffffu, y[k], c);
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < DL; ++k) s = fmaf(Kc[c][k], y[k], s);
+            ky[c] = s;
+          }
+#pragma unroll
+          for (int c = 0; c < M; ++c) v[c] -= group_allreduce<L>(ky[c]);
+#pragma unroll
+          for (int i = 0; i < DL; ++i) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < DF; ++r) s = fmaf(Ar[i][r], yf[r], s);
+#pragma unroll
+            for (int c = 0; c < M; ++c) s = fmaf(Br[i][c], v[c], s);
+            yn[i] = s + wh[i * TPB];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < DL; ++k) y[k] = yn[k];
+      }
+      // ---- u_f = -K y + mw ; adjoint seeds (SURVEY A-3.5): du = 2 u_f, lam = 2 y - K' du
+      const float lr = p.decay ? p.lr_scale * (1.0f / (float)(p.t0 + t + 1)) : p.lr_scale;
+      float du[M];
+#pragma unroll
+      for (int c = 0; c < M; ++c) {
+        float s = 0.f;
+        if (H > 1) {
+#pragma unroll
+          for (int k = 0; k < DL; ++k) s = fmaf(Kc[c][k], y[k], s);
+          s = group_allreduce<L>(s);
+        }
+        du[c] = 2.0f * (red[M + c] - s);
+      }
+      float lam[DL];
+#pragma unroll
+      for (int k = 0; k < DL; ++k) {
+        float s = 2.0f * y[k];
+#pragma unroll
+        for (int c = 0; c < M; ++c) s = fmaf(-Kc[c][k], du[c], s);
+        lam[k] = s;
+      }
+      // ---- M[i] -= lr * (dL/du_h) (x) w[.]   (rank-1, in place; the adjoint never reads M)  _gpc.py:163
+      {
+        float sc[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) sc[c] = -lr * du[c];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const float* w = slot(HH - 1 + i);
+#pragma unroll
+          for (int k = 0; k < DL; ++k) {
+            const float wk = w[k * TPB];
+#pragma unroll
+            for (int c = 0; c < M; ++c) Mr[i][c][k] = fmaf(sc[c], wk, Mr[i][c][k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = H - 2; h >= 0; --h) {
+        float sc[M];  // -lr * B' lam
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < DL; ++i) s = fmaf(Br[i][c], lam[i], s);
+          sc[c] = group_allreduce<L>(s);
+        }
+        if (h > 0) {  // lam <- A' lam - K' lam_u  (before sc is scaled)
+          float part[DF];
+#pragma unroll
+          for (int r = 0; r < DF; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < DL; ++i) s = fmaf(Ar[i][r], lam[i], s);
+            part[r] = s;
+          }
+#pragma unroll
+          for (int k = 0; k < DL; ++k) {
+            float s = part[k];
+#pragma unroll
+            for (int c = 1; c < L; ++c) s += __shfl_xor_sync(0xffffffffu, part[c * DL + k], c);
+#pragma unroll
+            for (int c = 0; c < M; ++c) s = fmaf(-Kc[c][k], sc[c], s);
+            lam[k] = s;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < M; ++c) sc[c] *= -lr;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const float* w = slot(h + i);
+#pragma unroll
+          for (int k = 0; k < DL; ++k) {
+            const float wk = w[k * TPB];
+#pragma unroll
+            for (int c = 0; c < M; ++c) Mr[i][c][k] = fmaf(sc[c], wk, Mr[i][c][k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < M; ++c) uprev[c] = u[c];
+    }
+
+    // ---- realised cost  x'x + u'u                                   _gpc.py:29-40
+    float cost;
+    {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < DL; ++k) s = fmaf(x[k], x[k], s);
+      cost = group_allreduce<L>(s);
+      float cu = 0.f;
+#pragma unroll
+      for (int c = 0; c < M; ++c) cu = fmaf(u[c], u[c], cu);
+      cost += cu;
+    }
+    csum += (double)cost;
+    if (live && q == 0 && a.cost_out) a.cost_out[(int64_t)t * p.N + n] = cost;
+    if (GPC && live && t == p.T - 1) {  // the agent's copy of the last state it saw (_gpc.py:167)
+#pragma unroll
+      for (int k = 0; k < DL; ++k)
+        if (q * DL + k < D) a.xprev_io[n * D + q * DL + k] = x[k];
+    }
+    if (sampled) {
+      if (a.x_out) {
+#pragma unroll
+        for (int k = 0; k < DL; ++k)
+          if (q * DL + k < D) a.x_out[((int64_t)t * Ns + ns) * D + q * DL + k] = x[k];
+      }
+      if (a.u_out && q == 0) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) a.u_out[((int64_t)t * Ns + ns) * M + c] = u[c];
+      }
+    }
+
+    // ---- env: x <- (A x + B u) + w_t                                _lds.py:102-111
+    {
+      float xf[DF];
+#pragma unroll
+      for (int k = 0; k < DL; ++k) xf[k] = x[k];
+#pragma unroll
+      for (int c = 1; c < L; ++c)
+#pragma unroll
+        for (int k = 0; k < DL; ++k) xf[c * DL + k] = __shfl_xor_sync(0xffffffffu, x[k], c);
+#pragma unroll
+      for (int i = 0; i < DL; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < DF; ++r) s = fmaf(Ar[i][r], xf[r], s);
+        ax[i] = s;
+#pragma unroll
+        for (int c = 0; c < M; ++c) s = fmaf(Br[i][c], u[c], s);
+        x[i] = s + w_t[i];
+      }
+    }
+  }
+
+  // ---- write back
+  if (!live) return;
+#pragma unroll
+  for (int k = 0; k < DL; ++k)
+    if (q * DL + k < D) a.x_io[n * D + q * DL + k] = x[k];
+  if (q == 0) {
+    if (a.cost_sum_out) a.cost_sum_out[n] = csum;
+    if (a.status_out) a.status_out[n] = isfinite(csum) ? 0 : DLC_STATUS_NONFINITE;
+  }
+  if (GPC) {
+#pragma unroll
+    for (int i = 0; i < H; ++i)
+#pragma unroll
+      for (int c = 0; c < M; ++c)
+#pragma unroll
+        for (int k = 0; k < DL; ++k)
+          if (q * DL + k < D) a.M_io[n * (H * M * D) + (i * M + c) * D + q * DL + k] = Mr[i][c][k];
+#pragma unroll
+    for (int s = 0; s < P; ++s)
+#pragma unroll
+      for (int k = 0; k < DL; ++k)
+        if (q * DL + k < D) a.hist_io[n * (P * D) + s * D + q * DL + k] = slot(s)[k * TPB];
+    if (a.uprev_io && q == 0) {
+#pragma unroll
+      for (int c = 0; c < M; ++c) a.uprev_io[n * M + c] = uprev[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// runtime-dims kernel: one thread per env, state updated in place in the caller's env-major
+// buffers, small vectors in a [element][env] workspace.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline int generic_ws_floats_per_env(int d, int m) { return 6 * d + 6 * m; }
+
+__global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
+  const DlcLdsParams& p = a.p;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int d = p.d, m = p.m, H = p.H;
+  const bool gpc = p.policy == DLC_POLICY_GPC, bpc = p.policy == DLC_POLICY_BPC;
+  const int P = gpc ? p.H + p.HH : p.H;  // history length (_gpc.py:98 / _bpc.py:82)
+  const int64_t np = p.shared_dynamics ? 0 : n;
+  const float* A = a.A + np * d * d;
+  const float* B = a.B + np * d * m;
+  const float* K = a.K + np * m * d;
+  float* x = a.x_io + n * d;
+  float* Mv = (gpc || bpc) ? a.M_io + n * (int64_t)H * m * d : nullptr;
+  float* hist = (gpc || bpc) ? a.hist_io + n * (int64_t)P * d : nullptr;
+  float* xprev = (gpc || bpc) ? a.xprev_io + n * d : nullptr;
+  float* eps = bpc ? a.eps_io + n * (int64_t)H * H * m * d : nullptr;
+  const int HMD = H * m * d;
+  // workspace vectors, element e at ws[(off + e) * N + n]
+  const int64_t N = p.N;
+  float* ws = a.ws + n;
+  auto V = [&](int off, int e) -> float& { return ws[(int64_t)(off + e) * N]; };
+  const int oU = 0, oUN = m, oV = 2 * m, oMW = 3 * m, oLU = 4 * m, oDU = 5 * m;
+  const int oY = 6 * m, oYN = oY + d, oLAM = oYN + d, oLN = oLAM + d, oW = oLN + d, oNZ = oW + d;
+  for (int c = 0; c < m; ++c) V(oUN, c) = a.uprev_io ? a.uprev_io[n * m + c] : 0.f;
+
+  const bool sampled = (a.x_out || a.u_out) && (n % p.traj_stride == 0);
+  const int64_t ns = n / p.traj_stride;
+  const int64_t Ns = (p.N + p.traj_stride - 1) / p.traj_stride;
+  const uint32_t env_id = (uint32_t)(p.env_offset + n);
+  double csum = 0.0;
+  float prev_cost = bpc ? V(oNZ, 0) : 0.f;  // staged by bpc_cost_stage_kernel (see below)
+
+  auto win_dot = [&](int start, int off_out) {  // out[c] = sum_i sum_j M[i][c][j] hist[start+i][j]
+    for (int c = 0; c < m; ++c) {
+      float s = 0.f;
+      for (int i = 0; i < H; ++i)
+        for (int j = 0; j < d; ++j) s = fmaf(Mv[(i * m + c) * d + j], hist[(start + i) * d + j], s);
+      V(off_out, c) = s;
+    }
+  };
+  auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+
+  for (int t = 0; t < p.T; ++t) {
+    // ---- action
+    if (gpc || bpc) win_dot(P - H, oMW);
+    for (int c = 0; c < m; ++c) {
+      float s = 0.f;
+      for (int j = 0; j < d; ++j) s = fmaf(K[c * d + j], x[j], s);
+      V(oU, c) = (gpc || bpc) ? V(oMW, c) - s : -s;
+    }
+    if (gpc || bpc) {
+      // ---- noise, ring shift                                    _gpc.py:155-157 / _bpc.py:124-126
+      for (int i = 0; i < d; ++i) {
+        float s = 0.f, sb = 0.f;
+        for (int j = 0; j < d; ++j) s = fmaf(A[i * d + j], xprev[j], s);
+        for (int c = 0; c < m; ++c)
+          sb = fmaf(B[i * m + c], p.noise_uses_prev_action ? V(oUN, c) : V(oU, c), sb);
+        V(oW, i) = (x[i] - s) - sb;
+      }
+      for (int k = 0; k < (P - 1) * d; ++k) hist[k] = hist[k + d];
+      for (int i = 0; i < d; ++i) hist[(P - 1) * d + i] = V(oW, i);
+    }
+    if (gpc) {
+      const int HH = p.HH;
+      // ---- policy_loss forward (windows clamp like lax.dynamic_slice)   _gpc.py:109-125
+      for (int i = 0; i < d; ++i) V(oY, i) = 0.f;
+      for (int h = 0; h < H - 1; ++h) {
+        win_dot(clampi(h, 0, P - H), oV);
+        for (int c = 0; c < m; ++c) {
+          float s = 0.f;
+          for (int j = 0; j < d; ++j) s = fmaf(K[c * d + j], V(oY, j), s);
+          V(oV, c) -= s;
+        }
+        const int idx = (h + H < P - 1) ? h + H : P - 1;
+        for (int i = 0; i < d; ++i) {
+          float s = 0.f;
+          for (int j = 0; j < d; ++j) s = fmaf(A[i * d + j], V(oY, j), s);
+          for (int c = 0; c < m; ++c) s = fmaf(B[i * m + c], V(oV, c), s);
+          V(oYN, i) = s + hist[idx * d + i];
+        }
+        for (int i = 0; i < d; ++i) V(oY, i) = V(oYN, i);
+      }
+      const int fstart = clampi(HH - 1, 0, P - H);
+      win_dot(fstart, oV);
+      const float lr = p.decay ? p.lr_scale * (1.0f / (float)(p.t0 + t + 1)) : p.lr_scale;
+      for (int c = 0; c < m; ++c) {
+        float s = 0.f;
+        for (int j = 0; j < d; ++j) s = fmaf(K[c * d + j], V(oY, j), s);
+        V(oDU, c) = 2.0f * (V(oV, c) - s);  // dL/du_f
+      }
+      for (int i = 0; i < d; ++i) {
+        float s = 2.0f * V(oY, i);
+        for (int c = 0; c < m; ++c) s = fmaf(-K[c * d + i], V(oDU, c), s);
+        V(oLAM, i) = s;
+      }
+      // adjoint, M updated in place (the backward pass never reads M)
+      for (int i = 0; i < H; ++i)
+        for (int c = 0; c < m; ++c)
+          for (int j = 0; j < d; ++j)
+            Mv[(i * m + c) * d + j] =
+                fmaf(-lr * V(oDU, c), hist[(fstart + i) * d + j], Mv[(i * m + c) * d + j]);
+      for (int h = H - 2; h >= 0; --h) {
+        for (int c = 0; c < m; ++c) {
+          float s = 0.f;
+          for (int i = 0; i < d; ++i) s = fmaf(B[i * m + c], V(oLAM, i), s);
+          V(oLU, c) = s;
+        }
+        const int st = clampi(h, 0, P - H);
+        for (int i = 0; i < H; ++i)
+          for (int c = 0; c < m; ++c)
+            for (int j = 0; j < d; ++j)
+              Mv[(i * m + c) * d + j] =
+                  fmaf(-lr * V(oLU, c), hist[(st + i) * d + j], Mv[(i * m + c) * d + j]);
+        for (int j = 0; j < d; ++j) {
+          float s = 0.f;
+          for (int i = 0; i < d; ++i) s = fmaf(A[i * d + j], V(oLAM, i), s);
+          for (int c = 0; c < m; ++c) s = fmaf(-K[c * d + j], V(oLU, c), s);
+          V(oLN, j) = s;
+        }
+        for (int j = 0; j < d; ++j) V(oLAM, j) = V(oLN, j);
+      }
+    }
+    if (bpc) {
+      // ---- bandit update                                        _bpc.py:128-139
+      float lr = p.lr_scale;
+      if (p.decay) lr = p.lr_scale * (1.0f / (powf((float)(p.t0 + t), 0.75f) + 1.0f));
+      for (int k = 0; k < HMD; ++k) {
+        float s = 0.f;
+        for (int q = 0; q < H; ++q) s += eps[q * HMD + k];
+        Mv[k] -= lr * (prev_cost * s);
+      }
+      for (int k = 0; k < (H - 1) * HMD; ++k) eps[k] = eps[k + HMD];
+      float* en = eps + (H - 1) * HMD;
+      if (a.eps_new) {
+        const float* src = a.eps_new + ((int64_t)t * p.N + n) * HMD;
+        for (int k = 0; k < HMD; ++k) en[k] = src[k];
+      } else {  // unit-norm Gaussian direction from the Philox stream 1 (_bpc.py:26-30)
+        float ss = 0.f;
+        for (int g = 0; g < (HMD + 3) / 4; ++g) {
+          float z[4];
+          normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g, 1u, z);
+          for (int k = 0; k < 4 && g * 4 + k < HMD; ++k) {
+            en[g * 4 + k] = z[k];
+            ss = fmaf(z[k], z[k], ss);
+          }
+        }
+        const float inv = 1.0f / sqrtf(ss);
+        for (int k = 0; k < HMD; ++k) en[k] *= inv;
+      }
+      for (int k = 0; k < HMD; ++k) Mv[k] = fmaf(p.bpc_delta, en[k], Mv[k]);
+    }
+    if (gpc || bpc) {
+      for (int i = 0; i < d; ++i) xprev[i] = x[i];
+      for (int c = 0; c < m; ++c) V(oUN, c) = V(oU, c);
+    }
+    // ---- realised cost
+    float cost = 0.f, cu = 0.f;
+    for (int i = 0; i < d; ++i) cost = fmaf(x[i], x[i], cost);
+    for (int c = 0; c < m; ++c) cu = fmaf(V(oU, c), V(oU, c), cu);
+    cost += cu;
+    prev_cost = cost;
+    csum += (double)cost;
+    if (a.cost_out) a.cost_out[(int64_t)t * p.N + n] = cost;
+    if (sampled) {
+      if (a.x_out)
+        for (int i = 0; i < d; ++i) a.x_out[((int64_t)t * Ns + ns) * d + i] = x[i];
+      if (a.u_out)
+        for (int c = 0; c < m; ++c) a.u_out[((int64_t)t * Ns + ns) * m + c] = V(oU, c);
+    }
+    // ---- env step
+    if (a.W) {
+      const float* gw = a.W + ((int64_t)t * p.N + n) * d;
+      for (int i = 0; i < d; ++i) V(oW, i) = gw[i];
+    } else {
+      for (int g = 0; g < (d + 3) / 4; ++g) {
+        float z[4];
+        normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g, 0u, z);
+        for (int k = 0; k < 4 && g * 4 + k < d; ++k) V(oW, g * 4 + k) = p.w_std * z[k];
+      }
+    }
+    for (int i = 0; i < d; ++i) {
+      float s = 0.f;
+      for (int j = 0; j < d; ++j) s = fmaf(A[i * d + j], x[j], s);
+      for (int c = 0; c < m; ++c) s = fmaf(B[i * m + c], V(oU, c), s);
+      V(oYN, i) = s + V(oW, i);
+    }
+    for (int i = 0; i < d; ++i) x[i] = V(oYN, i);
+  }
+  if (a.uprev_io && (gpc || bpc))
+    for (int c = 0; c < m; ++c) a.uprev_io[n * m + c] = V(oUN, c);
+  if (bpc) V(oNZ, 0) = prev_cost;
+  if (a.cost_sum_out) a.cost_sum_out[n] = csum;
+  if (a.status_out) a.status_out[n] = isfinite(csum) ? 0 : DLC_STATUS_NONFINITE;
+}
+
+// stage / unstage the BPC carried cost through workspace slot oNZ (keeps LdsArgs small)
+__global__ void bpc_cost_stage_kernel(float* ws, float* cost_io, int64_t N, int off, int to_ws) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (to_ws) ws[(int64_t)off * N + n] = cost_io ? cost_io[n] : 0.f;
+  else if (cost_io) cost_io[n] = ws[(int64_t)off * N + n];
+}
+
+__global__ void gaussian_disturbance_kernel(float* W, int64_t N, int T, int d, uint64_t seed,
+                                            int64_t env_offset, int t0, float std) {
+  const int G = (d + 3) / 4;
+  const int64_t total = (int64_t)T * N * G;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    const int64_t n = (idx / G) % N;
+    const int t = (int)(idx / (G * N));
+    float z[4];
+    normal4(seed, (uint32_t)(env_offset + n), (uint32_t)(t0 + t), g, 0u, z);
+    float* dst = W + ((int64_t)t * N + n) * d + g * 4;
+    for (int k = 0; k < 4 && g * 4 + k < d; ++k) dst[k] = std * z[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <int D, int M, int H, int HH, int POLICY, int L, int MINB>
+static int32_t launch_split(const LdsArgs& a, cudaStream_t st) {
+  constexpr int TPB = 128;
+  using Lay = SplitLayout<D, M, H, HH, POLICY, L, TPB>;
+  auto kern = lds_split_kernel<D, M, H, HH, POLICY, L, TPB, MINB>;
+  static_assert(Lay::kSmemBytes * MINB <= 227 * 1024, "ring does not fit shared memory");
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Lay::kSmemBytes);
+  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_split)");
+  const int64_t threads = a.p.N * L;
+  const unsigned grid = (unsigned)((threads + TPB - 1) / TPB);
+  kern<<<grid, TPB, Lay::kSmemBytes, st>>>(a);
+  return cuda_status(cudaGetLastError(), "lds_split_kernel launch");
+}
+
+// (d, m, H, HH, lanes per env, min blocks per SM for GPC)
+#define DLC_SPLIT_SHAPES(X) \
+  X(10, 3, 3, 10, 2, 3)     \
+  X(10, 3, 3, 2, 2, 3)      \
+  X(10, 3, 10, 10, 4, 3)    \
+  X(4, 1, 3, 2, 1, 4)       \
+  X(4, 2, 5, 7, 1, 3)
+
+static bool try_split(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
+  const DlcLdsParams& p = a.p;
+  if (p.kernel_variant == 1 || p.policy == DLC_POLICY_BPC) return false;
+#define X(D_, M_, H_, HH_, L_, MINB_)                                                 \
+  if (p.d == D_ && p.m == M_) {                                                       \
+    if (p.policy == DLC_POLICY_LQR) {                                                 \
+      *rc = launch_split<D_, M_, 1, 1, DLC_POLICY_LQR, L_, 4>(a, st);                 \
+      return true;                                                                    \
+    }                                                                                 \
+    if (p.H == H_ && p.HH == HH_) {                                                   \
+      *rc = launch_split<D_, M_, H_, HH_, DLC_POLICY_GPC, L_, MINB_>(a, st);          \
+      return true;                                                                    \
+    }                                                                                 \
+  }
+  DLC_SPLIT_SHAPES(X)
+#undef X
+  return false;
+}
+
+}  // namespace dlc
+
+using namespace dlc;
+
+extern "C" size_t dlc_lds_workspace_bytes(const DlcLdsParams* p) {
+  if (!p || p->N <= 0 || p->d <= 0 || p->m <= 0) return 0;
+  return (size_t)(generic_ws_floats_per_env(p->d, p->m) + 1) * (size_t)p->N * sizeof(float);
+}
+
+extern "C" int32_t dlc_gaussian_disturbance_f32(float* W, int64_t N, int32_t T, int32_t d,
+                                                uint64_t seed, int64_t env_offset, int32_t t0,
+                                                float std, void* stream) {
+  if (!W || N < 0 || T < 0 || d <= 0) return fail(DLC_ERR_ARG, "dlc_gaussian_disturbance_f32: bad argument");
+  if (N == 0 || T == 0) return DLC_OK;
+  const int64_t total = (int64_t)T * N * ((d + 3) / 4);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  gaussian_disturbance_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, N, T, d, seed, env_offset, t0, std);
+  return cuda_status(cudaGetLastError(), "gaussian_disturbance_kernel launch");
+}
+
+extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, const float* B,
+                                       const float* K, const float* W, float* x_io, float* M_io,
+                                       float* hist_io, float* xprev_io, float* uprev_io,
+                                       float* bpc_eps_io, const float* bpc_eps_new,
+                                       float* bpc_cost_io, float* cost_out, double* cost_sum_out,
+                                       float* x_out, float* u_out, int32_t* status_out,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: params is NULL");
+  if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: negative N or T");
+  if (p->d <= 0 || p->m <= 0) return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: d and m must be positive");
+  if (p->policy < DLC_POLICY_LQR || p->policy > DLC_POLICY_BPC)
+    return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: unknown policy");
+  if (p->traj_stride < 1) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: traj_stride must be >= 1");
+  if (p->N == 0) return DLC_OK;  // empty batch: nothing to do
+  if (!A || !B || !K || !x_io) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: A, B, K and x_io are required");
+  const bool learn = p->policy != DLC_POLICY_LQR;
+  if (learn) {
+    if (p->H < 1 || (p->policy == DLC_POLICY_GPC && p->HH < 1))
+      return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: H >= 1 and HH >= 1 required");
+    if (!M_io || !hist_io || !xprev_io)
+      return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: M_io, hist_io and xprev_io are required for GPC/BPC");
+    if (p->noise_uses_prev_action && !uprev_io)
+      return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: uprev_io is required when noise_uses_prev_action is set");
+    if (p->policy == DLC_POLICY_BPC && !bpc_eps_io)
+      return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: bpc_eps_io is required for BPC");
+  }
+  if ((uint64_t)(p->env_offset + p->N) > 0xFFFFFFFFull)
+    return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: env_offset + N exceeds the 32-bit stream counter");
+  LdsArgs a;
+  a.p = *p;
+  a.A = A; a.B = B; a.K = K; a.W = W;
+  a.x_io = x_io; a.M_io = M_io; a.hist_io = hist_io; a.xprev_io = xprev_io; a.uprev_io = uprev_io;
+  a.eps_io = bpc_eps_io; a.eps_new = bpc_eps_new;
+  a.cost_out = cost_out; a.cost_sum_out = cost_sum_out; a.x_out = x_out; a.u_out = u_out;
+  a.status_out = status_out; a.ws = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t rc = DLC_OK;
+  if (try_split(a, st, &rc)) return rc;
+  if (!workspace || workspace_bytes < dlc_lds_workspace_bytes(p))
+    return fail(DLC_ERR_WORKSPACE, "dlc_lds_rollout_f32: this shape runs the runtime-dims kernel and needs "
+                                   "dlc_lds_workspace_bytes() of workspace");
+  const unsigned grid = (unsigned)((p->N + 127) / 128);
+  const int oNZ = 6 * p->m + 5 * p->d;
+  if (p->policy == DLC_POLICY_BPC)
+    bpc_cost_stage_kernel<<<grid, 128, 0, st>>>(a.ws, bpc_cost_io, p->N, oNZ, 1);
+  lds_generic_kernel<<<grid, 128, 0, st>>>(a);
+  if (p->policy == DLC_POLICY_BPC)
+    bpc_cost_stage_kernel<<<grid, 128, 0, st>>>(a.ws, bpc_cost_io, p->N, oNZ, 0);
+  return cuda_status(cudaGetLastError(), "lds_generic_kernel launch");
+}

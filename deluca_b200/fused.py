@@ -1,0 +1,110 @@
+"""Fused-rollout entry points: thin, allocation-only wrappers over the C ABI.
+
+These are what the scan x vmap drivers (``deluca_b200.training.apg`` etc.) dispatch to.  All
+tensors are torch CUDA tensors used purely as device-memory handles; every number is produced
+by ``libdeluca_b200.so``.
+"""
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _abi
+
+
+def _f32(t, name, shape=None):
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError(f"{name} must be a CUDA tensor (no CPU path exists)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t
+
+
+def gaussian_disturbance(N, T, d, seed, env_offset=0, t0=0, std=0.5, device="cuda", out=None):
+    """W[T,N,d] of the counter-based stream the kernels draw in-register (include/deluca_b200.h)."""
+    W = out if out is not None else torch.empty((T, N, d), dtype=torch.float32, device=device)
+    _f32(W, "out", (T, N, d))
+    with torch.cuda.device(W.device):
+        rc = _abi.lib().dlc_gaussian_disturbance_f32(_abi.ptr(W), N, T, d, seed, env_offset, t0, std,
+                                                    _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_gaussian_disturbance_f32")
+    return W
+
+
+class LdsRolloutResult(dict):
+    __getattr__ = dict.__getitem__
+
+
+def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=None, xprev=None,
+                uprev=None, eps=None, eps_new=None, bpc_cost=None, t0=0, lr_scale=0.005, decay=True,
+                noise_uses_prev_action=False, w_std=0.5, seed=0, env_offset=0, bpc_delta=0.01,
+                keep_costs=True, traj_stride=0, kernel_variant=0, donate=False):
+    """T fused steps of LDS + LQR/GPC/BPC for N envs (``dlc_lds_rollout_f32``).
+
+    A[N,d,d] B[N,d,m] K[N,m,d] (or unbatched = shared by all envs), x[N,d].  State tensors
+    (``M, hist, xprev, uprev, eps, bpc_cost``) default to the agents' initial values
+    (_gpc.py:82-101, _bpc.py:79-90 with explicit M/eps).  Unless ``donate`` the inputs are left
+    untouched and updated copies are returned (the reference's functional convention).
+    Returns costs[T,N], cost_sum[N] (fp64), x (final), the new agent state, status[N] and, when
+    ``traj_stride`` > 0, sampled trajectories X[T,Ns,d], U[T,Ns,m] of every ``traj_stride``-th env.
+    """
+    lib = _abi.lib()
+    _f32(x, "x")
+    N, d = x.shape
+    shared = A.dim() == 2
+    m = B.shape[-1]
+    _f32(A, "A", (d, d) if shared else (N, d, d))
+    _f32(B, "B", (d, m) if shared else (N, d, m))
+    _f32(K, "K", (m, d) if shared else (N, m, d))
+    dev = x.device
+    pol = _abi.POLICY[policy]
+    learn = pol != 0
+    P = (H + HH) if policy == "gpc" else H
+    cl = (lambda t: t) if donate else (lambda t: None if t is None else t.clone())
+    x_io = cl(x)
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+    M_io = hist_io = xprev_io = uprev_io = eps_io = cost_io = None
+    if learn:
+        M_io = cl(_f32(M, "M", (N, H, m, d))) if M is not None else z(N, H, m, d)
+        hist_io = cl(_f32(hist, "hist", (N, P, d))) if hist is not None else z(N, P, d)
+        xprev_io = cl(_f32(xprev, "xprev", (N, d))) if xprev is not None else z(N, d)
+        uprev_io = cl(_f32(uprev, "uprev", (N, m))) if uprev is not None else z(N, m)
+    if policy == "bpc":
+        if M is None or eps is None:
+            raise ValueError("BPC needs explicit M and eps (the reference draws them from an unseeded RNG)")
+        eps_io = cl(_f32(eps, "eps", (N, H, H, m, d)))
+        cost_io = cl(_f32(bpc_cost, "bpc_cost", (N,))) if bpc_cost is not None else z(N)
+        _f32(eps_new, "eps_new", (T, N, H, m, d))
+    _f32(W, "W", (T, N, d))
+    costs = torch.empty((T, N), dtype=torch.float32, device=dev) if keep_costs else None
+    cost_sum = torch.empty((N,), dtype=torch.float64, device=dev)
+    status = torch.empty((N,), dtype=torch.int32, device=dev)
+    X = U = None
+    if traj_stride and traj_stride > 0:
+        Ns = (N + traj_stride - 1) // traj_stride
+        X = torch.empty((T, Ns, d), dtype=torch.float32, device=dev)
+        U = torch.empty((T, Ns, m), dtype=torch.float32, device=dev)
+    p = _abi.DlcLdsParams(N=N, env_offset=env_offset, T=T, d=d, m=m, H=H, HH=HH, policy=pol, t0=t0,
+                          decay=int(bool(decay)), noise_uses_prev_action=int(bool(noise_uses_prev_action)),
+                          shared_dynamics=int(shared), traj_stride=max(1, int(traj_stride or 1)),
+                          lr_scale=lr_scale, w_std=w_std, bpc_delta=bpc_delta,
+                          kernel_variant=kernel_variant, seed=seed)
+    ws_bytes = lib.dlc_lds_workspace_bytes(ctypes.byref(p))
+    ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.dlc_lds_rollout_f32(ctypes.byref(p), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K), _abi.ptr(W),
+                                     _abi.ptr(x_io), _abi.ptr(M_io), _abi.ptr(hist_io), _abi.ptr(xprev_io),
+                                     _abi.ptr(uprev_io), _abi.ptr(eps_io), _abi.ptr(eps_new),
+                                     _abi.ptr(cost_io), _abi.ptr(costs), _abi.ptr(cost_sum), _abi.ptr(X),
+                                     _abi.ptr(U), _abi.ptr(status), _abi.ptr(ws), ws.numel() * 4,
+                                     _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lds_rollout_f32")
+    return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, M=M_io, hist=hist_io, xprev=xprev_io,
+                            uprev=uprev_io, eps=eps_io, bpc_cost=cost_io, status=status, X=X, U=U,
+                            t=t0 + T)

@@ -1,0 +1,220 @@
+"""Parity of the fused LDS + LQR/GPC/BPC CUDA rollout against the CPU oracle (B200 only).
+
+Tolerance (BASELINE.json north_star): <= 1e-4 relative on costs and states for stable systems,
+checked against the float64 oracle; the float32 oracle's own deviation is asserted to be of the
+same order so the bound is meaningful.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lds as O
+from oracle import philox as P
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def _problem(N, d, m, T, seed=0, dense=False):
+    rng = np.random.default_rng(seed)
+    A, B, x0 = O.lds_default_params(rng, N, d, m)
+    if dense:  # general (non-diagonal) stable A
+        Q = np.linalg.qr(rng.standard_normal((N, d, d)))[0]
+        A = (Q @ A @ np.swapaxes(Q, 1, 2)).astype(np.float32)
+    K = O.lqr_gain(A, B)
+    W = (0.5 * rng.standard_normal((T, N, d))).astype(np.float32)
+    x0 = (0.1 * rng.standard_normal((N, d))).astype(np.float32)
+    return A, B, K, x0, W
+
+
+def _rel(a, b, floor):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+def _check(res, ref, T):
+    costs = res.costs.cpu().numpy()
+    assert np.isfinite(costs).all()
+    assert _rel(costs, ref["costs"], 1e-2 * np.abs(ref["costs"]).mean()).max() < RTOL
+    xs = np.abs(ref["x_final"]).mean()
+    assert _rel(res.x.cpu().numpy(), ref["x_final"], xs).max() < RTOL
+    np.testing.assert_allclose(res.cost_sum.cpu().numpy(), ref["costs"].astype(np.float64).sum(0), rtol=RTOL)
+    assert (res.status.cpu().numpy() == 0).all()
+
+
+@pytest.mark.parametrize("d,m,H,HH,variant", [
+    (10, 3, 3, 10, 0), (10, 3, 3, 10, 1), (10, 3, 3, 2, 0), (10, 3, 10, 10, 0), (4, 1, 3, 2, 0),
+    (4, 2, 5, 7, 0), (4, 2, 5, 7, 1), (6, 2, 4, 5, 0), (3, 1, 1, 1, 0), (5, 2, 4, 2, 0)])
+@pytest.mark.parametrize("dense", [False, True])
+def test_gpc_matches_oracle(d, m, H, HH, variant, dense):
+    from deluca_b200.fused import lds_rollout
+    N, T = 70, 300   # N not a multiple of the block / group size
+    A, B, K, x0, W = _problem(N, d, m, T, seed=d * 100 + H, dense=dense)
+    kw = dict(H=H, HH=HH, lr_scale=5e-4)
+    ref64 = O.rollout_lds(A, B, K, x0, W, "gpc", dtype=np.float64, **kw)
+    ref32 = O.rollout_lds(A, B, K, x0, W, "gpc", dtype=np.float32, **kw)
+    res = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W), traj_stride=1,
+                      kernel_variant=variant, **kw)
+    _check(res, ref64, T)
+    # the fp32 restatement is no closer to fp64 than the kernel is (same order of magnitude)
+    e_k = np.abs(res.costs.cpu().numpy() - ref64["costs"]).max()
+    e_o = np.abs(ref32["costs"] - ref64["costs"]).max()
+    assert e_k < 20 * e_o + 1e-6
+    # agent state and sampled trajectories
+    st = ref64["state"]
+    np.testing.assert_allclose(res.M.cpu().numpy(), st["M"], rtol=1e-3, atol=1e-5 * np.abs(st["M"]).max() + 1e-9)
+    np.testing.assert_allclose(res.hist.cpu().numpy(), st["hist"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(res.xprev.cpu().numpy(), st["xprev"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(res.X.cpu().numpy(), ref64["X"][:T], rtol=1e-3, atol=1e-4)
+
+
+def test_gpc_reference_default_lr_short_horizon():
+    """Reference defaults (lr_scale=0.005, decay) on a horizon short enough to stay finite."""
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 33, 60, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=11)
+    ref = O.rollout_lds(A, B, K, x0, W, "gpc", H=3, HH=10, dtype=np.float64)
+    res = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W), H=3, HH=10)
+    c = res.costs.cpu().numpy()
+    ok = np.isfinite(ref["costs"]).all(axis=0) & (np.abs(ref["costs"]).max(axis=0) < 1e4)
+    assert ok.sum() > N // 2
+    assert _rel(c[:, ok], ref["costs"][:, ok], 1e-2 * np.abs(ref["costs"][:, ok]).mean()).max() < 1e-3
+
+
+def test_gpc_intended_noise_variant():
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 40, 400, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=5)
+    kw = dict(H=3, HH=10, noise_uses_prev_action=True)
+    ref = O.rollout_lds(A, B, K, x0, W, "gpc", dtype=np.float64, **kw)
+    for variant in (0, 1):
+        res = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W),
+                          kernel_variant=variant, **kw)
+        _check(res, ref, T)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_lqr_matches_oracle_and_zero_lr_gpc(variant):
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 129, 200, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=2, dense=True)
+    ref = O.rollout_lds(A, B, K, x0, W, "lqr", dtype=np.float64)
+    a = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="lqr", W=_dev(W), kernel_variant=variant)
+    _check(a, ref, T)
+    b = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W), H=3, HH=10,
+                    lr_scale=0.0, kernel_variant=variant)
+    # M == 0 and lr == 0 reduce GPC to LQR (SURVEY A-3.6): same arithmetic, same bits
+    assert torch.equal(a.costs, b.costs) and torch.equal(a.x, b.x)
+
+
+def test_resume_is_identical_and_inputs_untouched():
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 64, 90, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=3)
+    dA, dB, dK, dx, dW = map(_dev, (A, B, K, x0, W))
+    kw = dict(policy="gpc", H=3, HH=10, lr_scale=5e-4)
+    full = lds_rollout(dA, dB, dK, dx, T, W=dW, **kw)
+    assert torch.equal(dx, _dev(x0))
+    h1 = lds_rollout(dA, dB, dK, dx, 40, W=dW[:40].contiguous(), **kw)
+    h2 = lds_rollout(dA, dB, dK, h1.x, T - 40, W=dW[40:].contiguous(), M=h1.M, hist=h1.hist,
+                     xprev=h1.xprev, uprev=h1.uprev, t0=h1.t, **kw)
+    assert torch.equal(full.costs[40:], h2.costs)
+    assert torch.equal(full.x, h2.x) and torch.equal(full.M, h2.M) and torch.equal(full.hist, h2.hist)
+
+
+def test_shared_dynamics_equals_per_env_copy():
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 50, 100, 10, 3
+    A, B, K, x0, W = _problem(1, d, m, T, seed=4)
+    rng = np.random.default_rng(0)
+    x0 = rng.standard_normal((N, d)).astype(np.float32)
+    W = (0.5 * rng.standard_normal((T, N, d))).astype(np.float32)
+    kw = dict(policy="gpc", H=3, HH=10, lr_scale=5e-4)
+    a = lds_rollout(_dev(A[0]), _dev(B[0]), _dev(K[0]), _dev(x0), T, W=_dev(W), **kw)
+    b = lds_rollout(_dev(np.repeat(A, N, 0)), _dev(np.repeat(B, N, 0)), _dev(np.repeat(K, N, 0)), _dev(x0), T,
+                    W=_dev(W), **kw)
+    assert torch.equal(a.costs, b.costs)
+
+
+def test_in_kernel_disturbance_equals_materialised_stream_and_oracle():
+    from deluca_b200.fused import gaussian_disturbance, lds_rollout
+    N, T, d, m = 100, 64, 10, 3
+    A, B, K, x0, _ = _problem(N, d, m, T, seed=6)
+    W = gaussian_disturbance(N, T, d, seed=1234, env_offset=7, t0=0, std=0.5)
+    Wo = P.gaussian_disturbance(1234, np.arange(7, 7 + N), 0, T, d, 0.5)
+    np.testing.assert_allclose(W.cpu().numpy(), Wo, atol=5e-6, rtol=0)
+    kw = dict(policy="gpc", H=3, HH=10, lr_scale=5e-4)
+    for variant in (0, 1):
+        a = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, W=None, seed=1234, env_offset=7, w_std=0.5,
+                        kernel_variant=variant, **kw)
+        b = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, W=W, kernel_variant=variant, **kw)
+        assert torch.equal(a.costs, b.costs)
+    # sharding invariance: envs [32, 64) on their own draw the same stream
+    s = slice(32, 64)
+    c = lds_rollout(_dev(A[s]), _dev(B[s]), _dev(K[s]), _dev(x0[s]), T, W=None, seed=1234, env_offset=7 + 32, **kw)
+    assert torch.equal(a.costs[:, s], c.costs)
+
+
+def test_bpc_matches_oracle():
+    from deluca_b200.fused import lds_rollout
+    rng = np.random.default_rng(6)
+    N, d, m, H, T = 20, 10, 3, 5, 120
+    A, B, K, x0, W = _problem(N, d, m, T, seed=8)
+    M0 = O.unit_norm(rng.standard_normal((N, H, m, d)).astype(np.float32))
+    eps0 = O.unit_norm(rng.standard_normal((N, H, H, m, d)).astype(np.float32))
+    eps = O.unit_norm(rng.standard_normal((T * N, H, m, d)).astype(np.float32)).reshape(T, N, H, m, d)
+    for decay in (False, True):
+        st = O.bpc_init(N, d, m, H, M0, eps0, dtype=np.float64)
+        ref = O.rollout_lds(A, B, K, x0, W, "bpc", H=H, state=st, bpc_eps=eps, decay=decay, lr_scale=1e-5,
+                            dtype=np.float64)
+        res = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="bpc", W=_dev(W), H=H,
+                          M=_dev(0.01 * M0), eps=_dev(eps0), eps_new=_dev(eps), decay=decay, lr_scale=1e-5)
+        _check(res, ref, T)
+        np.testing.assert_allclose(res.M.cpu().numpy(), ref["state"]["M"], rtol=1e-3, atol=1e-6)
+
+
+def test_empty_batch_and_argument_errors():
+    from deluca_b200 import _abi
+    from deluca_b200.fused import lds_rollout
+    z = lambda *s: torch.zeros(s, device="cuda")
+    r = lds_rollout(z(0, 10, 10), z(0, 10, 3), z(0, 3, 10), z(0, 10), 5, policy="lqr", W=z(5, 0, 10))
+    assert r.costs.shape == (5, 0)
+    with pytest.raises(TypeError):
+        lds_rollout(torch.zeros(1, 2, 2), z(1, 2, 1), z(1, 1, 2), z(1, 2), 1, policy="lqr")
+    with pytest.raises(_abi.DlcError):  # HH = 0 is rejected by the ABI
+        lds_rollout(z(1, 2, 2), z(1, 2, 1), z(1, 1, 2), z(1, 2), 1, policy="gpc", H=2, HH=0)
+
+
+def test_nonfinite_status_flag():
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 8, 50, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=9)
+    A[3] *= 40.0  # wildly unstable env
+    r = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W), H=3, HH=10)
+    s = r.status.cpu().numpy()
+    assert s[3] == 1 and (np.delete(s, 3) == 0).all()
+
+
+def test_large_batch_properties():
+    """BASELINE-sized batch, short horizon: linearity of the LQR rollout in (x0, W) and the
+    cost_sum == sum(costs) checksum hold for every env."""
+    from deluca_b200.fused import gaussian_disturbance, lds_rollout
+    N, T, d, m = 65536, 64, 10, 3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.diag_embed(0.9 + 0.05 * torch.rand(N, d, device="cuda", generator=g))
+    B = torch.randn(N, d, m, device="cuda", generator=g)
+    K = 0.05 * torch.randn(N, m, d, device="cuda", generator=g)
+    x0 = torch.randn(N, d, device="cuda", generator=g)
+    W = gaussian_disturbance(N, T, d, seed=3)
+    a = lds_rollout(A, B, K, x0, T, policy="lqr", W=W, traj_stride=64)
+    b = lds_rollout(A, B, K, 2 * x0, T, policy="lqr", W=2 * W, traj_stride=64)
+    assert torch.allclose(b.X, 2 * a.X, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(b.costs, 4 * a.costs, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(a.costs.double().sum(0), a.cost_sum, rtol=1e-6)
+    gp = lds_rollout(A, B, K, x0, T, policy="gpc", W=W, H=3, HH=10, lr_scale=1e-4)
+    assert torch.allclose(gp.costs.double().sum(0), gp.cost_sum, rtol=1e-6)
+    assert int(gp.status.sum()) == 0

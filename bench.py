@@ -235,6 +235,7 @@ def main():
     sync()
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_all0.record()
+    torch.cuda.nvtx.range_push("dlc_timed")
     for i in range(args.steps):
         kev[i][0].record()
         r = lds_rollout(A, B, K, x0, T, W=W, **kw)
@@ -245,6 +246,7 @@ def main():
         if world > 1:
             dist.all_reduce(s)
         stats.copy_(s)
+    torch.cuda.nvtx.range_pop()
     t_all1.record()
     sync()
     clocks = sampler.stop() if rank == 0 else None

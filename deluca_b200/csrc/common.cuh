@@ -36,15 +36,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   return c;
 }
 
-// two uint32 -> two standard normals (Box-Muller on 24-bit uniforms; u1 in (0,1], u2 in [0,1))
+// two uint32 -> two standard normals: Box-Muller on 24-bit uniforms, u1 in (0,1], u2 in [0,1).
+//   rad = sqrt(max(-2 ln2 * lg2(u1), 0)),  ang = 2 pi (u2 - 1/2) in [-pi, pi)  (u2 - 1/2 is exact)
+// Every step is a single pinned PTX instruction so that the in-register stream of the rollout
+// kernels and the materialised stream of dlc_gaussian_disturbance_f32 agree bit for bit
+// (the compiler may reassociate around __logf/__sincosf differently from one kernel to the next).
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& z0, float& z1) {
-  const float u1 = (float)((ra >> 8) + 1u) * 5.9604644775390625e-08f;  // 2^-24
-  const float u2 = (float)(rb >> 8) * 5.9604644775390625e-08f;
-  const float rad = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.2831853071795864769f * u2, &s, &c);
-  z0 = rad * c;
-  z1 = rad * s;
+  const float u1 = __fmul_rn((float)((ra >> 8) + 1u), 5.9604644775390625e-08f);  // 2^-24
+  const float u2 = __fmul_rn((float)(rb >> 8), 5.9604644775390625e-08f);
+  float l2, rad, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+  const float r2 = fmaxf(__fmul_rn(l2, -1.3862943611198906f), 0.0f);  // lg2.approx may round lg2(1-eps) above 0
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(r2));
+  const float ang = __fmul_rn(u2 - 0.5f, 6.2831853071795864769f);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
+  z0 = __fmul_rn(rad, c);
+  z1 = __fmul_rn(rad, s);
 }
 
 // four standard normals for (env, t, group j, stream s)

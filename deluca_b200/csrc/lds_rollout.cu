@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
 #pragma unroll
         for (int o = 1; o < 4; ++o)
           if (k + o < NG * 4) zz = (off == o) ? z[k + o] : zz;
-        w[k] = (q * DL + k < D) ? p.w_std * zz : 0.f;
+        w[k] = (q * DL + k < D) ? __fmul_rn(p.w_std, zz) : 0.f;  // never contracted into the add below
       }
     }
   };
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
       for (int g = 0; g < (d + 3) / 4; ++g) {
         float z[4];
         normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g, 0u, z);
-        for (int k = 0; k < 4 && g * 4 + k < d; ++k) V(oW, g * 4 + k) = p.w_std * z[k];
+        for (int k = 0; k < 4 && g * 4 + k < d; ++k) V(oW, g * 4 + k) = __fmul_rn(p.w_std, z[k]);
       }
     }
     for (int i = 0; i < d; ++i) {
@@ -667,7 +667,7 @@ __global__ void gaussian_disturbance_kernel(float* W, int64_t N, int T, int d, u
     float z[4];
     normal4(seed, (uint32_t)(env_offset + n), (uint32_t)(t0 + t), g, 0u, z);
     float* dst = W + ((int64_t)t * N + n) * d + g * 4;
-    for (int k = 0; k < 4 && g * 4 + k < d; ++k) dst[k] = std * z[k];
+    for (int k = 0; k < 4 && g * 4 + k < d; ++k) dst[k] = __fmul_rn(std, z[k]);
   }
 }
 

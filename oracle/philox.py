@@ -10,7 +10,8 @@ counter-based stream and this module restates it on the CPU:
   counter = (env, t, j, 0)          j = b // 4 selects the group of four coordinates
   four 32-bit outputs (r0..r3) -> two Box-Muller pairs:
       u1 = ((r >> 8) + 1) * 2^-24  in (0, 1]     u2 = (r' >> 8) * 2^-24  in [0, 1)
-      z0 = sqrt(-2 ln u1) cos(2 pi u2),  z1 = sqrt(-2 ln u1) sin(2 pi u2)
+      ang = 2 pi (u2 - 1/2) in [-pi, pi)
+      z0 = sqrt(-2 ln u1) cos(ang),  z1 = sqrt(-2 ln u1) sin(ang)
   w[t, env, b] = std * z[b % 4]
 
 The integer part is bit-exact against the kernel; the float transform uses libm here and
@@ -50,7 +51,7 @@ def box_muller_f32(r_a, r_b):
     u1 = ((r_a >> np.uint32(8)).astype(np.uint32) + np.uint32(1)).astype(f32) * f32(2.0 ** -24)
     u2 = (r_b >> np.uint32(8)).astype(f32) * f32(2.0 ** -24)
     rad = np.sqrt(f32(-2.0) * np.log(u1)).astype(f32)
-    ang = (f32(2.0 * np.pi) * u2).astype(f32)
+    ang = (f32(2.0 * np.pi) * (u2 - f32(0.5))).astype(f32)
     return (rad * np.cos(ang)).astype(f32), (rad * np.sin(ang)).astype(f32)
 
 

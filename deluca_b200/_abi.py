@@ -38,11 +38,39 @@ class DlcLdsParams(ctypes.Structure):
         ("w_std", ctypes.c_float),
         ("bpc_delta", ctypes.c_float),
         ("kernel_variant", ctypes.c_int32),
+        ("mode", ctypes.c_int32),
         ("seed", ctypes.c_uint64),
     ]
 
 
-POLICY = {"lqr": 0, "gpc": 1, "bpc": 2}
+class DlcLungParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int64), ("T", ctypes.c_int32), ("sim", ctypes.c_int32), ("nk", ctypes.c_int32),
+        ("kf_per_env", ctypes.c_int32), ("kx", ctypes.c_float * 16), ("period", ctypes.c_float),
+        ("xp_in", ctypes.c_float), ("pid_decay", ctypes.c_float), ("default_dt", ctypes.c_float),
+        ("run_dt", ctypes.c_float), ("env_flow", ctypes.c_float),
+        ("leak", ctypes.c_int32), ("peep_valve", ctypes.c_float), ("PC", ctypes.c_float), ("P0", ctypes.c_float),
+        ("R", ctypes.c_float), ("dt", ctypes.c_float), ("min_volume", ctypes.c_float), ("r0", ctypes.c_float),
+        ("r0_sq", ctypes.c_float), ("leak_coef", ctypes.c_float),
+        ("delay", ctypes.c_int32), ("d_R", ctypes.c_float), ("d_C", ctypes.c_float), ("inertia", ctypes.c_float),
+        ("control_gain", ctypes.c_float), ("mode", ctypes.c_int32),
+    ]
+
+
+LUNG_BUFFER_FIELDS = [
+    "K", "kf", "u_in_in", "u_out_in", "steps_io", "time_io", "volume_io", "pressure_io", "target_io",
+    "pipe_pressure_io", "in_history_io", "out_history_io", "obs_pressure_io", "obs_time_io",
+    "pid_p_io", "pid_i_io", "pid_d_io", "pid_time_io", "pid_dt_io", "pid_steps_io",
+    "exp_time_io", "exp_dt_io", "exp_steps_io",
+    "timestamp_out", "u_in_out", "u_out_out", "pressure_out", "flow_out", "target_out", "status_out",
+]
+
+
+class DlcLungBuffers(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in LUNG_BUFFER_FIELDS]
+
+
+POLICY = {"lqr": 0, "gpc": 1, "bpc": 2, "open": 3}
 
 # every symbol include/deluca_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
@@ -53,9 +81,12 @@ SYMBOLS = {
     "dlc_gaussian_disturbance_f32": (ctypes.c_int32, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                                       ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32,
                                                       ctypes.c_float, _P]),
+    "dlc_sizeof": (ctypes.c_size_t, [ctypes.c_int32]),
+    "dlc_lung_pid_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLungParams), ctypes.POINTER(DlcLungBuffers), _P]),
+    "dlc_pid_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_float] + [_P] * 9),
     "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),
     "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
-    "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 17
+    "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 18
                             + [_P, ctypes.c_size_t, _P]),
 }
 
@@ -75,6 +106,10 @@ def lib():
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args
+            for which, struct in enumerate((DlcLdsParams, DlcLungParams, DlcLungBuffers)):
+                if L.dlc_sizeof(which) != ctypes.sizeof(struct):
+                    raise ImportError(f"{struct.__name__}: ctypes layout ({ctypes.sizeof(struct)} B) does not match "
+                                      f"the library ({L.dlc_sizeof(which)} B); rebuild libdeluca_b200.so")
             _lib = L
     return _lib
 

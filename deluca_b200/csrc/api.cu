@@ -22,3 +22,12 @@ extern "C" int32_t dlc_check_device(void) {
   if (major != 10) return dlc::fail(DLC_ERR_DEVICE, "libdeluca_b200 is built for sm_100a only");
   return DLC_OK;
 }
+
+extern "C" size_t dlc_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(DlcLdsParams);
+    case 1: return sizeof(DlcLungParams);
+    case 2: return sizeof(DlcLungBuffers);
+    default: return 0;
+  }
+}

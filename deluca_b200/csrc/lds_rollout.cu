@@ -15,7 +15,7 @@ namespace dlc {
 
 struct LdsArgs {
   DlcLdsParams p;
-  const float *A, *B, *K, *W;
+  const float *A, *B, *K, *W, *U_in;
   float *x_io, *M_io, *hist_io, *xprev_io, *uprev_io, *eps_io;
   const float* eps_new;
   float* cost_out;
@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
   if (n >= p.N) return;
   const int d = p.d, m = p.m, H = p.H;
   const bool gpc = p.policy == DLC_POLICY_GPC, bpc = p.policy == DLC_POLICY_BPC;
+  const bool open_loop = p.policy == DLC_POLICY_OPEN, agent_only = p.mode == DLC_MODE_AGENT_ONLY;
   const int P = gpc ? p.H + p.HH : p.H;  // history length (_gpc.py:98 / _bpc.py:82)
   const int64_t np = p.shared_dynamics ? 0 : n;
   const float* A = a.A + np * d * d;
@@ -499,6 +500,10 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
     if (gpc || bpc) win_dot(P - H, oMW);
     for (int c = 0; c < m; ++c) {
       float s = 0.f;
+      if (open_loop) {
+        V(oU, c) = a.U_in[((int64_t)t * p.N + n) * m + c];
+        continue;
+      }
       for (int j = 0; j < d; ++j) s = fmaf(K[c * d + j], x[j], s);
       V(oU, c) = (gpc || bpc) ? V(oMW, c) - s : -s;
     }
@@ -622,6 +627,7 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
         for (int c = 0; c < m; ++c) a.u_out[((int64_t)t * Ns + ns) * m + c] = V(oU, c);
     }
     // ---- env step
+    if (agent_only) continue;
     if (a.W) {
       const float* gw = a.W + ((int64_t)t * p.N + n) * d;
       for (int i = 0; i < d; ++i) V(oW, i) = gw[i];
@@ -699,7 +705,9 @@ static int32_t launch_split(const LdsArgs& a, cudaStream_t st) {
 
 static bool try_split(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
-  if (p.kernel_variant == 1 || p.policy == DLC_POLICY_BPC) return false;
+  if (p.kernel_variant == 1 || p.policy == DLC_POLICY_BPC || p.policy == DLC_POLICY_OPEN ||
+      p.mode != DLC_MODE_CLOSED_LOOP)
+    return false;
 #define X(D_, M_, H_, HH_, L_, MINB_)                                                 \
   if (p.d == D_ && p.m == M_) {                                                       \
     if (p.policy == DLC_POLICY_LQR) {                                                 \
@@ -737,7 +745,8 @@ extern "C" int32_t dlc_gaussian_disturbance_f32(float* W, int64_t N, int32_t T, 
 }
 
 extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, const float* B,
-                                       const float* K, const float* W, float* x_io, float* M_io,
+                                       const float* K, const float* W, const float* u_in, float* x_io,
+                                       float* M_io,
                                        float* hist_io, float* xprev_io, float* uprev_io,
                                        float* bpc_eps_io, const float* bpc_eps_new,
                                        float* bpc_cost_io, float* cost_out, double* cost_sum_out,
@@ -746,12 +755,17 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
   if (!p) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: params is NULL");
   if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: negative N or T");
   if (p->d <= 0 || p->m <= 0) return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: d and m must be positive");
-  if (p->policy < DLC_POLICY_LQR || p->policy > DLC_POLICY_BPC)
+  if (p->policy < DLC_POLICY_LQR || p->policy > DLC_POLICY_OPEN)
     return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: unknown policy");
+  if (p->mode != DLC_MODE_CLOSED_LOOP && p->mode != DLC_MODE_AGENT_ONLY)
+    return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: unknown mode");
+  if (p->policy == DLC_POLICY_OPEN && (!u_in || p->mode != DLC_MODE_CLOSED_LOOP))
+    return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: DLC_POLICY_OPEN needs u_in and closed-loop mode");
   if (p->traj_stride < 1) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: traj_stride must be >= 1");
   if (p->N == 0) return DLC_OK;  // empty batch: nothing to do
-  if (!A || !B || !K || !x_io) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: A, B, K and x_io are required");
-  const bool learn = p->policy != DLC_POLICY_LQR;
+  if (!A || !B || !x_io || (!K && p->policy != DLC_POLICY_OPEN))
+    return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: A, B, K and x_io are required");
+  const bool learn = p->policy == DLC_POLICY_GPC || p->policy == DLC_POLICY_BPC;
   if (learn) {
     if (p->H < 1 || (p->policy == DLC_POLICY_GPC && p->HH < 1))
       return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: H >= 1 and HH >= 1 required");
@@ -766,7 +780,7 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
     return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: env_offset + N exceeds the 32-bit stream counter");
   LdsArgs a;
   a.p = *p;
-  a.A = A; a.B = B; a.K = K; a.W = W;
+  a.A = A; a.B = B; a.K = K; a.W = W; a.U_in = u_in;
   a.x_io = x_io; a.M_io = M_io; a.hist_io = hist_io; a.xprev_io = xprev_io; a.uprev_io = uprev_io;
   a.eps_io = bpc_eps_io; a.eps_new = bpc_eps_new;
   a.cost_out = cost_out; a.cost_sum_out = cost_sum_out; a.x_out = x_out; a.u_out = u_out;

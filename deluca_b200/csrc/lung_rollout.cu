@@ -1,0 +1,215 @@
+// Fused ventilator episode: PID + Expiratory + BalloonLung / DelayLung.
+// One thread per breath; all state in registers (DelayLung's two valve histories in a local
+// ring); per step five/six coalesced 4-byte stores per thread ([T,N] time-major series), which is
+// what bounds the kernel (HBM writes).
+#include "common.cuh"
+
+namespace dlc {
+
+struct LungArgs {
+  DlcLungParams p;
+  DlcLungBuffers b;
+};
+
+// BreathWaveform.at: jnp.interp(t, xp, fp, period) on the host-built table (lung/core.py:54-60)
+__device__ __forceinline__ float waveform_at(const DlcLungParams& p, const float* kf, float t) {
+  const float x = fmodf(t, p.period);  // t >= 0 on this path, so fmod == jnp.mod
+  int i = 1;
+#pragma unroll 1
+  for (int k = 1; k < p.nk - 1; ++k) i += (p.kx[k] <= x) ? 1 : 0;  // searchsorted(side='right'), clipped
+  const float x0 = p.kx[i - 1], dx = p.kx[i] - x0;
+  const float f0 = kf[i - 1], df = kf[i] - f0;
+  return dx == 0.f ? f0 : f0 + __fdiv_rn(x - x0, dx) * df;
+}
+
+template <int SIM>
+__global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
+  const DlcLungParams& p = a.p;
+  const DlcLungBuffers& b = a.b;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  float kf[DLC_MAX_KNOTS];
+  {
+    const float* g = b.kf + (p.kf_per_env ? n * p.nk : 0);
+#pragma unroll
+    for (int k = 0; k < DLC_MAX_KNOTS; ++k) kf[k] = k < p.nk ? g[k] : 0.f;
+  }
+  const float k0 = b.K[n * 3 + 0], k1 = b.K[n * 3 + 1], k2 = b.K[n * 3 + 2];
+  float time = b.time_io[n], volume = b.volume_io[n], pressure = b.pressure_io[n];
+  float steps = b.steps_io[n], target = b.target_io[n];
+  float pipe = SIM == DLC_SIM_DELAY ? b.pipe_pressure_io[n] : 0.f;
+  float obs_p = b.obs_pressure_io[n], obs_t = b.obs_time_io[n];
+  float cp = b.pid_p_io[n], ci = b.pid_i_io[n], cd = b.pid_d_io[n], ctime = b.pid_time_io[n], cdt = b.pid_dt_io[n];
+  int csteps = b.pid_steps_io[n];
+  float etime = b.exp_time_io[n], edt = b.exp_dt_io[n];
+  int esteps = b.exp_steps_io[n];
+  float hin[SIM == DLC_SIM_DELAY ? DLC_MAX_DELAY : 1], hout[SIM == DLC_SIM_DELAY ? DLC_MAX_DELAY : 1];
+  int pos = 0;  // ring slot of logical index 0 (the newest entry)
+  if (SIM == DLC_SIM_DELAY) {
+    for (int k = 0; k < p.delay; ++k) {
+      hin[k] = b.in_history_io[n * p.delay + k];
+      hout[k] = b.out_history_io[n * p.delay + k];
+    }
+  }
+  bool bad = false;
+  const bool run_ctrl = p.mode != DLC_LUNG_MODE_ENV_ONLY, run_env = p.mode != DLC_LUNG_MODE_CTRL_ONLY;
+
+  for (int t = 0; t < p.T; ++t) {
+    const float pr_emit = obs_p;                                   // run_controller.py:118
+    float u_in, u_out;
+    if (run_ctrl) {
+    // ---- PID                                                     controllers/_pid.py:77-102
+    const float tgt = waveform_at(p, kf, obs_t);
+    const float err = tgt - obs_p;
+    const float np_ = err;
+    const float ni = ci + p.pid_decay * (err - ci);
+    const float nd = cd + p.pid_decay * ((err - cp) - cd);
+    cp = np_; ci = ni; cd = nd;
+    u_in = (np_ * k0 + ni * k1) + nd * k2;                          // Dense(1, use_bias=False)
+    u_in = fminf(fmaxf(u_in, 0.f), 100.f);                          // lax.clamp(0, u, 100)
+    cdt = fmaxf(p.default_dt, obs_t - (isinf(ctime) ? 0.f : ctime));
+    ctime = obs_t;
+    ++csteps;
+    // ---- Expiratory                                              controllers/_expiratory.py:35-45
+    u_out = (fmodf(obs_t, p.period) <= p.xp_in) ? 0.f : 1.f;
+    edt = fmaxf(p.default_dt, obs_t - (isinf(etime) ? 0.f : etime));
+    etime = obs_t;
+    ++esteps;
+    } else {
+      u_in = b.u_in_in[(int64_t)t * p.N + n];
+      u_out = b.u_out_in[(int64_t)t * p.N + n];
+    }
+    // ---- simulator
+    if (!run_env) {
+    } else if (SIM == DLC_SIM_BALLOON) {                                   // envs/_balloon_lung.py:100-146
+      float valve = 1.0f * (tanhf(0.03f * (3.0f * u_in - 130.f)) + 1.0f);
+      valve = fminf(fmaxf(valve, 0.f), 1.72f);
+      float flow = fminf(fmaxf(valve * p.R, 0.f), 2.0f);
+      if (pressure > p.peep_valve) flow -= (u_out > 0.f ? 1.0f : 0.0f) * 0.05f * pressure;
+      volume += flow * p.dt;
+      if (p.leak) volume += p.leak_coef * (p.min_volume - volume);
+      const float r = powf(__fdiv_rn(3.0f * volume, 12.566370614359172f), 0.33333333333333333f);
+      const float q = __fdiv_rn(p.r0, r);
+      const float q2 = q * q;
+      pressure = p.P0 + __fdiv_rn(p.PC * (1.0f - q2 * q2 * q2), p.r0_sq * r);
+      steps = time + 1.0f;                                          // sic (:135)
+      time = time + p.dt;
+      target = waveform_at(p, kf, time);
+      obs_p = pressure;
+      obs_t = time;
+    } else {                                                        // envs/_delay_lung.py:75-133
+      const float uin_pos = u_in > 0.f ? u_in : 0.f;
+      pos = pos == 0 ? p.delay - 1 : pos - 1;                       // roll(+1); [0] <- u
+      hin[pos] = uin_pos;
+      hout[pos] = u_out;
+      obs_p = pressure;                                             // observation of the pre-dynamics state
+      obs_t = time;
+      const float flow = __fdiv_rn(pressure, p.d_R);
+      volume = fmaxf(volume + flow * p.dt, p.min_volume);
+      const float r = powf(__fdiv_rn(3.0f * volume, 12.566370614359172f), 0.33333333333333333f);
+      const float q = __fdiv_rn(p.r0, r);
+      const float q2 = q * q;
+      const float lung_p = __fdiv_rn(p.d_C * (1.0f - q2 * q2 * q2), p.r0_sq * r);
+      const bool early = time < (float)p.delay;                     // seconds vs steps, sic (:88-96)
+      const float impulse = early ? 0.f : p.control_gain * uin_pos;
+      const float peep = early ? 0.f : u_out;
+      pipe = p.inertia * pipe + impulse;
+      pressure = fmaxf(0.f, pipe - lung_p);
+      if (peep != 0.f) pipe *= 0.995f;
+      steps = time + 1.0f;
+      time = time + p.dt;
+      target = waveform_at(p, kf, time);
+    }
+    // ---- emitted series                                          run_controller.py:128-141
+    const float ts = p.dt * steps - p.run_dt;
+    const int64_t o = (int64_t)t * p.N + n;
+    if (b.timestamp_out) b.timestamp_out[o] = ts;
+    if (b.u_in_out) b.u_in_out[o] = u_in;
+    if (b.u_out_out) b.u_out_out[o] = u_out;
+    if (b.pressure_out) b.pressure_out[o] = pr_emit;
+    if (b.flow_out) b.flow_out[o] = p.env_flow;
+    if (b.target_out) b.target_out[o] = waveform_at(p, kf, ts);     // waveform.at(timestamps), :207
+    bad |= !isfinite(pressure);
+  }
+
+  b.steps_io[n] = steps; b.time_io[n] = time; b.volume_io[n] = volume; b.pressure_io[n] = pressure;
+  b.target_io[n] = target;
+  b.obs_pressure_io[n] = obs_p; b.obs_time_io[n] = obs_t;
+  b.pid_p_io[n] = cp; b.pid_i_io[n] = ci; b.pid_d_io[n] = cd; b.pid_time_io[n] = ctime; b.pid_dt_io[n] = cdt;
+  b.pid_steps_io[n] = csteps;
+  b.exp_time_io[n] = etime; b.exp_dt_io[n] = edt; b.exp_steps_io[n] = esteps;
+  if (SIM == DLC_SIM_DELAY) {
+    b.pipe_pressure_io[n] = pipe;
+    for (int k = 0; k < p.delay; ++k) {
+      int s = pos + k;
+      s -= s >= p.delay ? p.delay : 0;
+      b.in_history_io[n * p.delay + k] = hin[s];
+      b.out_history_io[n * p.delay + k] = hout[s];
+    }
+  }
+  if (b.status_out) b.status_out[n] = bad ? DLC_STATUS_NONFINITE : 0;
+}
+
+}  // namespace dlc
+
+extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLungBuffers* b, void* stream) {
+  using namespace dlc;
+  if (!p || !b) return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: NULL params/buffers");
+  if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: negative N or T");
+  if (p->sim != DLC_SIM_BALLOON && p->sim != DLC_SIM_DELAY)
+    return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: unknown simulator");
+  if (p->nk < 2 || p->nk > DLC_MAX_KNOTS) return fail(DLC_ERR_SHAPE, "dlc_lung_pid_rollout_f32: 2 <= nk <= 16 knots");
+  if (p->sim == DLC_SIM_DELAY && (p->delay < 1 || p->delay > DLC_MAX_DELAY))
+    return fail(DLC_ERR_SHAPE, "dlc_lung_pid_rollout_f32: 1 <= delay <= 64");
+  if (p->N == 0) return DLC_OK;
+  const bool need = b->K && b->kf && b->steps_io && b->time_io && b->volume_io && b->pressure_io && b->target_io &&
+                    b->obs_pressure_io && b->obs_time_io && b->pid_p_io && b->pid_i_io && b->pid_d_io &&
+                    b->pid_time_io && b->pid_dt_io && b->pid_steps_io && b->exp_time_io && b->exp_dt_io &&
+                    b->exp_steps_io;
+  if (!need) return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: a required state buffer is NULL");
+  if (p->mode < 0 || p->mode > DLC_LUNG_MODE_ENV_ONLY) return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: unknown mode");
+  if (p->mode == DLC_LUNG_MODE_ENV_ONLY && !(b->u_in_in && b->u_out_in))
+    return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: env-only mode needs u_in_in and u_out_in");
+  if (p->sim == DLC_SIM_DELAY && !(b->pipe_pressure_io && b->in_history_io && b->out_history_io))
+    return fail(DLC_ERR_ARG, "dlc_lung_pid_rollout_f32: DelayLung needs pipe_pressure/in_history/out_history");
+  LungArgs a;
+  a.p = *p;
+  a.b = *b;
+  const unsigned grid = (unsigned)((p->N + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->sim == DLC_SIM_BALLOON) lung_pid_kernel<DLC_SIM_BALLOON><<<grid, 128, 0, st>>>(a);
+  else lung_pid_kernel<DLC_SIM_DELAY><<<grid, 128, 0, st>>>(a);
+  return cuda_status(cudaGetLastError(), "lung_pid_kernel launch");
+}
+
+namespace dlc {
+__global__ void __launch_bounds__(256) pid_kernel(int64_t N, int T, float decay, const float* KP, const float* KI,
+                                                  const float* KD, const float* err, float* P_io, float* I_io,
+                                                  float* D_io, float* u_out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float kp = KP[n], ki = KI[n], kd = KD[n];
+  float P = P_io[n], I = I_io[n], D = D_io[n];
+  for (int t = 0; t < T; ++t) {
+    const float e = err[(int64_t)t * N + n];
+    I = I + decay * (e - I);
+    D = D + decay * ((e - P) - D);
+    P = e;
+    u_out[(int64_t)t * N + n] = (kp * P + ki * I) + kd * D;
+  }
+  P_io[n] = P; I_io[n] = I; D_io[n] = D;
+}
+}  // namespace dlc
+
+extern "C" int32_t dlc_pid_f32(int64_t N, int32_t T, float decay, const float* K_P, const float* K_I,
+                               const float* K_D, const float* err, float* P_io, float* I_io, float* D_io,
+                               float* u_out, void* stream) {
+  using namespace dlc;
+  if (N < 0 || T < 0) return fail(DLC_ERR_ARG, "dlc_pid_f32: negative N or T");
+  if (N == 0 || T == 0) return DLC_OK;
+  if (!K_P || !K_I || !K_D || !err || !P_io || !I_io || !D_io || !u_out)
+    return fail(DLC_ERR_ARG, "dlc_pid_f32: NULL buffer");
+  pid_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, T, decay, K_P, K_I, K_D, err, P_io,
+                                                                            I_io, D_io, u_out);
+  return cuda_status(cudaGetLastError(), "pid_kernel launch");
+}

@@ -1,0 +1,130 @@
+"""LDS environment (``deluca/envs/_lds.py``) on the fused CUDA path.
+
+Two faces, as in the reference:
+  * stateful, the reference's own:  ``env = LDS(); env.init(d_in, d_hidden, d_out, ...)``,
+    ``y = env(u)`` mutates ``env.x`` / ``env.t`` (``_lds.py:58-111``);
+  * functional pytree, what ``apg_rollout`` x ``vmap`` needs: ``state = env.reset(N)``,
+    ``state, obs = env.step(state, u)`` with ``LDSState(x[N,d], t)`` (SURVEY A-1).
+Every state update is computed by ``dlc_lds_rollout_f32`` (open-loop policy, T = 1).  Disturbances
+come from the library's counter-based Gaussian stream (Threefry is not reproducible without JAX,
+SURVEY a3); ``key`` is the integer stream seed.
+"""
+import math
+
+import torch
+
+from ..core import Disturbance, Env, Obj, field
+from .. import fused
+
+
+class ZeroDisturbance(Disturbance):
+    """``_lds.py:24-32``."""
+
+    def init(self, d):
+        self.d = d
+
+    def std(self):
+        return 0.0
+
+    def __call__(self, t, key, N=1, device="cuda"):
+        return torch.zeros(N, self.d, device=device)
+
+
+class GaussianDisturbance(Disturbance):
+    """``_lds.py:35-41``: N(0, 1) * std, std = 0.5."""
+
+    def init(self, d, std=0.5):
+        self.d = d
+        self._std = std
+
+    def std(self):
+        return self._std
+
+    def __call__(self, t, key, N=1, device="cuda", env_offset=0):
+        return fused.gaussian_disturbance(N, 1, self.d, seed=int(key), env_offset=env_offset, t0=int(t),
+                                          std=self._std, device=device)[0]
+
+
+class SinusDisturbance(Disturbance):
+    """``_lds.py:44-52``: sin(t * phases) * amplitude; phases ~ N(0,1) from stream seed 0."""
+
+    def init(self, d, amplitude=0.5, device="cuda"):
+        self.d = d
+        self.amplitude = amplitude
+        self.phases = fused.gaussian_disturbance(1, 1, d, seed=0, std=1.0, device=device)[0, 0]
+
+    def std(self):
+        return None
+
+    def __call__(self, t, key, N=1, device="cuda"):
+        return (torch.sin(float(t) * self.phases) * self.amplitude).expand(N, self.d).contiguous()
+
+
+class LDSState(Obj):
+    """Functional state of an LDS batch: x[N,d] and the step counter (SURVEY A-1)."""
+    x: torch.Tensor = field(None, jaxed=True)
+    t: int = field(0, jaxed=False)
+
+
+class LDS(Env):
+    """``deluca.envs.LDS`` (``_lds.py:55-111``).  A[d,d] / B[d,n] / C[p,d] may also be given with a
+    leading env axis [N,...] (per-env systems, the vmapped case)."""
+
+    def init(self, d_in=1, d_hidden=25, d_out=1, A=None, B=None, C=None, key=0, x0=None, disturbance=None,
+             device="cuda"):
+        g = torch.Generator(device=device).manual_seed(int(key))
+        dev = torch.device(device)
+        as_t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=dev).contiguous()
+        self.A = as_t(A) if A is not None else torch.diag(
+            0.9 + 0.05 * torch.rand(d_hidden, device=dev, generator=g))            # _lds.py:71-77
+        self.B = as_t(B) if B is not None else torch.randn(d_hidden, d_in, device=dev, generator=g)
+        self.C = as_t(C) if C is not None else torch.randn(d_out, d_hidden, device=dev, generator=g)
+        self.d, self.n, self.p = self.A.shape[-1], self.B.shape[-1], self.C.shape[-2]
+        self.x = torch.zeros(self.d, 1, device=dev) if x0 is None else as_t(x0).reshape(self.d, 1)
+        self.t = 0
+        self.disturbance = disturbance if disturbance is not None else GaussianDisturbance()
+        self.disturbance.init(self.d)
+        self.key = int(key)
+        return self.x
+
+    # ---- functional face
+    def reset(self, N=1, x0=None):
+        dev = self.A.device
+        x = torch.zeros(N, self.d, device=dev) if x0 is None else torch.as_tensor(
+            x0, dtype=torch.float32, device=dev).reshape(N, self.d).contiguous()
+        st = LDSState(x=x, t=0)
+        st.freeze()
+        return st, self.observe(st)
+
+    def observe(self, state):
+        """y = C x (``_lds.py:108``)."""
+        if self.C.dim() == 2:
+            return state.x @ self.C.T
+        return torch.einsum("npd,nd->np", self.C, state.x)
+
+    def step(self, state, u, key=None, env_offset=0):
+        """``Env.__call__(state, action)``: x <- A x + B u + w_t, t <- t + 1 (``_lds.py:102-111``)."""
+        N = state.x.shape[0]
+        u = torch.as_tensor(u, dtype=torch.float32, device=state.x.device).reshape(N, self.n).contiguous()
+        key = self.key if key is None else int(key)
+        std = self.disturbance.std()
+        W = None
+        if std is None or std == 0.0:   # not the Gaussian stream: materialise this step's w_t
+            W = self.disturbance(state.t, key, N=N, device=state.x.device).reshape(1, N, self.d).contiguous()
+        r = fused.lds_rollout(self.A, self.B, None, state.x, 1, policy="open", u_in=u.reshape(1, N, self.n), W=W,
+                              w_std=std or 0.0, seed=key, t0=state.t, env_offset=env_offset, keep_costs=False)
+        st = LDSState(x=r.x, t=state.t + 1)
+        st.freeze()
+        return st, self.observe(st)
+
+    # ---- stateful face (the reference's)
+    def __call__(self, u, key=None):
+        st = LDSState(x=self.x.reshape(1, self.d).contiguous(), t=self.t)
+        st, y = self.step(st, torch.as_tensor(u, dtype=torch.float32).reshape(1, self.n), key=key)
+        self.x = st.x.reshape(self.d, 1)
+        self.t += 1
+        return y.reshape(self.p, 1)
+
+    @property
+    def action_size(self) -> int:
+        return self.n

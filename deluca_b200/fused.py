@@ -44,7 +44,7 @@ class LdsRolloutResult(dict):
 def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=None, xprev=None,
                 uprev=None, eps=None, eps_new=None, bpc_cost=None, t0=0, lr_scale=0.005, decay=True,
                 noise_uses_prev_action=False, w_std=0.5, seed=0, env_offset=0, bpc_delta=0.01,
-                keep_costs=True, traj_stride=0, kernel_variant=0, donate=False):
+                keep_costs=True, traj_stride=0, kernel_variant=0, donate=False, u_in=None, agent_only=False):
     """T fused steps of LDS + LQR/GPC/BPC for N envs (``dlc_lds_rollout_f32``).
 
     A[N,d,d] B[N,d,m] K[N,m,d] (or unbatched = shared by all envs), x[N,d].  State tensors
@@ -82,6 +82,8 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
         cost_io = cl(_f32(bpc_cost, "bpc_cost", (N,))) if bpc_cost is not None else z(N)
         _f32(eps_new, "eps_new", (T, N, H, m, d))
     _f32(W, "W", (T, N, d))
+    if policy == "open":
+        _f32(u_in, "u_in", (T, N, m))
     costs = torch.empty((T, N), dtype=torch.float32, device=dev) if keep_costs else None
     cost_sum = torch.empty((N,), dtype=torch.float64, device=dev)
     status = torch.empty((N,), dtype=torch.int32, device=dev)
@@ -94,11 +96,11 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
                           decay=int(bool(decay)), noise_uses_prev_action=int(bool(noise_uses_prev_action)),
                           shared_dynamics=int(shared), traj_stride=max(1, int(traj_stride or 1)),
                           lr_scale=lr_scale, w_std=w_std, bpc_delta=bpc_delta,
-                          kernel_variant=kernel_variant, seed=seed)
+                          kernel_variant=kernel_variant, mode=int(bool(agent_only)), seed=seed)
     ws_bytes = lib.dlc_lds_workspace_bytes(ctypes.byref(p))
     ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        rc = lib.dlc_lds_rollout_f32(ctypes.byref(p), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K), _abi.ptr(W),
+        rc = lib.dlc_lds_rollout_f32(ctypes.byref(p), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K), _abi.ptr(W), _abi.ptr(u_in),
                                      _abi.ptr(x_io), _abi.ptr(M_io), _abi.ptr(hist_io), _abi.ptr(xprev_io),
                                      _abi.ptr(uprev_io), _abi.ptr(eps_io), _abi.ptr(eps_new),
                                      _abi.ptr(cost_io), _abi.ptr(costs), _abi.ptr(cost_sum), _abi.ptr(X),
@@ -108,3 +110,28 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
     return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, M=M_io, hist=hist_io, xprev=xprev_io,
                             uprev=uprev_io, eps=eps_io, bpc_cost=cost_io, status=status, X=X, U=U,
                             t=t0 + T)
+
+
+# ------------------------------------------------------------------------------------------ lung
+def lung_rollout(params, bufs):
+    """``dlc_lung_pid_rollout_f32`` on already-prepared ctypes structs (see deluca_b200.lung)."""
+    any_t = next(v for v in bufs.values() if v is not None)
+    b = _abi.DlcLungBuffers(**{k: (None if v is None else v.data_ptr()) for k, v in bufs.items()})
+    with torch.cuda.device(any_t.device):
+        rc = _abi.lib().dlc_lung_pid_rollout_f32(ctypes.byref(params), ctypes.byref(b), _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lung_pid_rollout_f32")
+
+
+def pid_rollout(K_P, K_I, K_D, err, P, I, D, decay):
+    """``dlc_pid_f32``: generic PID over err[T,N]; returns u[T,N] and the new (P, I, D)."""
+    T, N = err.shape
+    for name, t in (("K_P", K_P), ("K_I", K_I), ("K_D", K_D), ("P", P), ("I", I), ("D", D)):
+        _f32(t, name, (N,))
+    _f32(err, "err")
+    P, I, D = P.clone(), I.clone(), D.clone()
+    u = torch.empty_like(err)
+    with torch.cuda.device(err.device):
+        rc = _abi.lib().dlc_pid_f32(N, T, decay, _abi.ptr(K_P), _abi.ptr(K_I), _abi.ptr(K_D), _abi.ptr(err),
+                                    _abi.ptr(P), _abi.ptr(I), _abi.ptr(D), _abi.ptr(u), _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_pid_f32")
+    return u, P, I, D

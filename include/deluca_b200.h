@@ -46,6 +46,9 @@ extern "C" {
 #define DLC_STATUS_NOT_PD 2      /* Q_uu not positive definite in the Riccati backward pass */
 
 int32_t dlc_abi_version(void);
+/* sizeof() of the parameter structs as compiled, so a binding can verify its own layout:
+ * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers (more below); 0 for unknown */
+size_t dlc_sizeof(int32_t which);
 const char* dlc_last_error(void);
 /* 0 if the current CUDA device can run this library (compute capability 10.x) */
 int32_t dlc_check_device(void);
@@ -77,6 +80,10 @@ int32_t dlc_gaussian_disturbance_f32(float* W /*[T,N,d]*/, int64_t N, int32_t T,
 #define DLC_POLICY_LQR 0
 #define DLC_POLICY_GPC 1
 #define DLC_POLICY_BPC 2
+#define DLC_POLICY_OPEN 3  /* u_t read from u_in[T,N,m]: LDS.__call__(u) on its own (_lds.py:102-111) */
+
+#define DLC_MODE_CLOSED_LOOP 0 /* agent then env, T steps */
+#define DLC_MODE_AGENT_ONLY 1  /* Agent.__call__ only: x_io is the observed state and is not advanced */
 
 typedef struct DlcLdsParams {
   int64_t N;           /* envs in this call (this rank's shard) */
@@ -94,6 +101,7 @@ typedef struct DlcLdsParams {
   float w_std;         /* std of the in-kernel Gaussian disturbance, used when W == NULL */
   float bpc_delta;     /* _bpc.py:53 */
   int32_t kernel_variant; /* 0 = auto; 1 = force the runtime-dims kernel (testing) */
+  int32_t mode;        /* DLC_MODE_*: which half of the loop runs (single-step Env/Agent calls use 1 and 2) */
   uint64_t seed;       /* disturbance / perturbation stream seed */
 } DlcLdsParams;
 
@@ -105,6 +113,7 @@ int32_t dlc_lds_rollout_f32(
     const float* B,       /* [N,d,m] or [d,m] */
     const float* K,       /* [N,m,d] or [m,d] */
     const float* W,       /* [T,N,d] disturbances, or NULL: generate in-kernel (Philox, w_std) */
+    const float* u_in,    /* [T,N,m] actions for DLC_POLICY_OPEN (NULL otherwise) */
     float* x_io,          /* [N,d]   env state: x_t0 in, x_t0+T out */
     float* M_io,          /* [N,H,m,d]     GPC/BPC M        (NULL for LQR) */
     float* hist_io,       /* [N,H+HH,d]    noise_history, oldest -> newest (BPC: [N,H,d]) (NULL for LQR) */
@@ -120,6 +129,83 @@ int32_t dlc_lds_rollout_f32(
     float* u_out,         /* [T,Ns,m] sampled u_t, or NULL */
     int32_t* status_out,  /* [N]     DLC_STATUS_* bit flags, or NULL */
     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Ventilator episode: lung PID + Expiratory controllers driving BalloonLung / DelayLung, fused.
+ *
+ * Replaces lax.scan(loop_over_tt) of run_controller_scan
+ * (deluca/lung/utils/scripts/run_controller.py:111-141,144-220) batched over N breaths, i.e. per step
+ *     u_in  = PID(c_state, obs)          deluca/lung/controllers/_pid.py:77-102
+ *     u_out = Expiratory(e_state, obs)   deluca/lung/controllers/_expiratory.py:35-45
+ *     state, obs = env(state,(u_in,u_out))   deluca/lung/envs/_balloon_lung.py:100-146
+ *                                            deluca/lung/envs/_delay_lung.py:75-133
+ * with BreathWaveform.at / is_in (deluca/lung/core.py:54-66) evaluated from a host-built knot table
+ * (the sorted, period-padded table jnp.interp(..., period=) builds; float32 knots reproduce the
+ * reference's 3 - 1e-8 == 3 collapse, SURVEY A-9).  All reference quirks are kept: steps = time + 1,
+ * timestamp = dt*steps - dt, DelayLung's `time < delay` and pre-dynamics observation, flow = env.flow.
+ * ------------------------------------------------------------------------------------ */
+#define DLC_SIM_BALLOON 0
+#define DLC_SIM_DELAY 1
+#define DLC_LUNG_MODE_CLOSED_LOOP 0 /* PID + Expiratory + simulator (run_controller_scan) */
+#define DLC_LUNG_MODE_CTRL_ONLY 1   /* Controller.__call__ only: obs_*_io is the observation, simulator untouched */
+#define DLC_LUNG_MODE_ENV_ONLY 2    /* LungEnv.__call__ only: actions read from u_in_in/u_out_in [T,N] */
+#define DLC_MAX_KNOTS 16
+#define DLC_MAX_DELAY 64
+
+typedef struct DlcLungParams {
+  int64_t N;                 /* breaths (envs) */
+  int32_t T;                 /* steps */
+  int32_t sim;               /* DLC_SIM_* */
+  int32_t nk;                /* knots in kx / per-env kf rows (<= DLC_MAX_KNOTS) */
+  int32_t kf_per_env;        /* 1: kf is [N,nk]; 0: kf is [nk], shared */
+  float kx[DLC_MAX_KNOTS];   /* knot abscissae, ascending, period-padded */
+  float period;              /* 60 / bpm */
+  float xp_in;               /* xp[in_bounds[1]]: is_in(t) = (t mod period) <= xp_in */
+  float pid_decay;           /* dt / (dt + RC), _pid.py:83 */
+  float default_dt;          /* DEFAULT_DT floor of the controllers' dt bookkeeping */
+  float run_dt;              /* run_controller_scan's dt (timestamp = env.time(state) - dt) */
+  float env_flow;            /* the env's static `flow` field, emitted as the flow series */
+  /* BalloonLung statics (_balloon_lung.py:61-73); r0 = (3 min_volume / 4 pi)^(1/3) from the host */
+  int32_t leak;
+  float peep_valve, PC, P0, R, dt, min_volume, r0, r0_sq, leak_coef /* dt/(5+dt) */;
+  /* DelayLung statics (_delay_lung.py:41-50) */
+  int32_t delay;
+  float d_R, d_C, inertia, control_gain;
+  int32_t mode;              /* DLC_LUNG_MODE_* */
+} DlcLungParams;
+
+typedef struct DlcLungBuffers {
+  const float* K;            /* [N,3] PID gains (the Dense(1, no bias) kernel) */
+  const float* kf;           /* [N,nk] or [nk] knot ordinates */
+  const float *u_in_in, *u_out_in; /* [T,N] actions, DLC_LUNG_MODE_ENV_ONLY only */
+  /* simulator state, one array per pytree leaf (SimulatorState), all [N] */
+  float *steps_io, *time_io, *volume_io, *pressure_io, *target_io;
+  float *pipe_pressure_io;   /* DelayLung only */
+  float *in_history_io, *out_history_io; /* DelayLung only, [N,delay], index 0 = newest */
+  float *obs_pressure_io, *obs_time_io;  /* Observation */
+  /* PIDControllerState / ControllerState leaves, [N] */
+  float *pid_p_io, *pid_i_io, *pid_d_io, *pid_time_io, *pid_dt_io;
+  int32_t* pid_steps_io;
+  float *exp_time_io, *exp_dt_io;
+  int32_t* exp_steps_io;
+  /* per-step series, each [T,N] or NULL */
+  float *timestamp_out, *u_in_out, *u_out_out, *pressure_out, *flow_out, *target_out;
+  int32_t* status_out;       /* [N] DLC_STATUS_* or NULL */
+} DlcLungBuffers;
+
+int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLungBuffers* b, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Generic leaky PID agent (deluca/agents/_pid.py:20-48), T steps over a given error series:
+ *     P = e; I += decay (e - I); D += decay (e - P_prev - D); u = K_P P + K_I I + K_D D,
+ *     decay = dt / (dt + RC) (:30-32).
+ * ------------------------------------------------------------------------------------ */
+int32_t dlc_pid_f32(int64_t N, int32_t T, float decay,
+                    const float* K_P, const float* K_I, const float* K_D, /* [N] gains (pytree leaves) */
+                    const float* err,                                   /* [T,N] observations (= errors) */
+                    float* P_io, float* I_io, float* D_io,              /* [N] PIDState */
+                    float* u_out,                                       /* [T,N] actions */
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC

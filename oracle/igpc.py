@@ -1,0 +1,341 @@
+"""deluca/igpc (rollout, compute_ders, LQR backward pass, iLQR, GPC_rollout, iGPC_closed, iLC_closed)
+and the classic envs it plans on, restated on the CPU (test infrastructure; see oracle/__init__.py).
+
+Parity unpinned: the reference has no test for any of this.  Analytic Jacobians replace
+``jax.jacfwd`` / ``jax.grad`` and are cross-checked against ``torch.autograd`` on a literal
+restatement of the env step (tests/test_oracle_igpc.py).
+
+Batched over a leading trajectory axis N; all trajectories advance in lockstep and the
+reference's data-dependent Python control flow (``if cC <= c: ... break``) becomes per-trajectory
+masks with the same accept order.
+
+Rulings:
+  A-6  Pendulum is reproduced as written: thdot' = th + accel (no dt, old thdot ignored).
+  A-7  Cartpole: the stray commas at _cartpole.py:83-88 make the literal code a TypeError; the
+       evident intent arr' = A arr + B (u + offset) is implemented (a waiver).
+  A-10 iLQR passes ``alpha`` instead of ``alphaC`` to the candidate rollout (ilqr.py:58-67);
+       ``fix_backtracking=False`` reproduces that, ``True`` uses alphaC.
+  Cost: the reference ships no cost function for this path; c(x,u) = sum q (x-goal)^2 + sum r u^2
+       with q = 1, r = 0.1 is this repo's stated choice.
+"""
+import numpy as np
+
+
+# ----------------------------------------------------------------------------- envs
+class Pendulum:
+    """``deluca/envs/classic/_pendulum.py:35-77``."""
+    d, m = 3, 1
+
+    def __init__(self, m=1.0, l=1.0, g=9.81, max_torque=1.0, dt=0.02, H=300, goal_state=(0.0, -1.0, 0.0)):
+        self.mass, self.l, self.g, self.max_torque, self.dt, self.H = m, l, g, max_torque, dt, H
+        self.goal_state = np.asarray(goal_state)
+
+    def init(self, N, dtype):
+        x = np.zeros((N, 3), dtype=dtype)
+        x[:, 1] = 1.0                                                     # :47
+        return x
+
+    def step(self, x, u):
+        """x[N,3], u[N,1] -> x'[N,3]   (:54-73, verbatim incl. thdot' = th + accel)."""
+        c = x.dtype.type
+        th = np.arctan2(x[:, 0], x[:, 1])
+        a = c(self.max_torque) * np.tanh(u[:, 0])
+        newthdot = th + (c(-3.0 * self.g / (2.0 * self.l)) * np.sin(th + c(np.pi))
+                         + c(3.0 / (self.mass * self.l ** 2)) * a)
+        newth = th + newthdot * c(self.dt)
+        return np.stack([np.sin(newth), np.cos(newth), newthdot], axis=1).astype(x.dtype)
+
+    def jac(self, x, u):
+        """Analytic d step / d x [N,3,3] and d step / d u [N,3,1]."""
+        c = x.dtype.type
+        s, co = x[:, 0], x[:, 1]
+        r2 = s * s + co * co
+        th = np.arctan2(s, co)
+        dth = np.stack([co / r2, -s / r2, np.zeros_like(s)], axis=1)      # d th / d arr
+        tu = np.tanh(u[:, 0])
+        a = c(self.max_torque) * tu
+        k1, k2 = c(-3.0 * self.g / (2.0 * self.l)), c(3.0 / (self.mass * self.l ** 2))
+        newthdot = th + (k1 * np.sin(th + c(np.pi)) + k2 * a)
+        newth = th + newthdot * c(self.dt)
+        dthd_dth = c(1) + k1 * np.cos(th + c(np.pi))
+        dnth_dth = c(1) + c(self.dt) * dthd_dth
+        sn, cn = np.sin(newth), np.cos(newth)
+        Fx = np.stack([(cn * dnth_dth)[:, None] * dth, (-sn * dnth_dth)[:, None] * dth,
+                       dthd_dth[:, None] * dth], axis=1)
+        dthd_du = k2 * c(self.max_torque) * (c(1) - tu * tu)
+        Fu = np.stack([cn * c(self.dt) * dthd_du, -sn * c(self.dt) * dthd_du, dthd_du], axis=1)[:, :, None]
+        return Fx.astype(x.dtype), Fu.astype(x.dtype)
+
+
+class Cartpole:
+    """``deluca/envs/classic/_cartpole.py:36-93`` with the A-7 waiver (intent-fixed)."""
+    d, m = 4, 1
+
+    def __init__(self, m=0.1, M=1.0, l=1.0, g=9.81, dt=0.02, H=10, goal_state=(0.0, 0.0, 0.0, 0.0), offset=0.0):
+        self.mass, self.M, self.l, self.g, self.dt, self.H, self.offset = m, M, l, g, dt, H, offset
+        self.goal_state = np.asarray(goal_state)
+
+    def init(self, N, dtype):
+        return np.zeros((N, 4), dtype=dtype)
+
+    def AB(self, dtype):
+        dt, m, M, l, g = self.dt, self.mass, self.M, self.l, self.g
+        A = np.array([[1.0, 0.0, dt, 0.0], [0.0, 1.0, 0.0, dt], [0.0, dt * m * g / M, 1.0, 0.0],
+                      [0.0, dt * (m + M) * g / (M * l), 0.0, 1.0]], dtype=dtype)       # :70-82
+        B = np.array([[0.0], [0.0], [dt / M], [dt / (M * l)]], dtype=dtype)           # :83-87
+        return A, B
+
+    def step(self, x, u):
+        A, B = self.AB(x.dtype)
+        return (x @ A.T + (u + x.dtype.type(self.offset)) @ B.T).astype(x.dtype)
+
+    def jac(self, x, u):
+        A, B = self.AB(x.dtype)
+        N = x.shape[0]
+        return np.broadcast_to(A, (N, 4, 4)).copy(), np.broadcast_to(B, (N, 4, 1)).copy()
+
+
+class QuadCost:
+    """c(x,u) = sum_i q_i (x_i - goal_i)^2 + sum_j r_j u_j^2  (this repo's stated choice)."""
+
+    def __init__(self, goal, q=1.0, r=0.1):
+        self.goal, self.q, self.r = np.asarray(goal, dtype=np.float64), q, r
+
+    def __call__(self, x, u):
+        c = x.dtype.type
+        dx = x - self.goal.astype(x.dtype)
+        return c(self.q) * (dx * dx).sum(1) + c(self.r) * (u * u).sum(1)
+
+    def ders(self, x, u):
+        c = x.dtype.type
+        N, d = x.shape
+        m = u.shape[1]
+        c_x = c(2 * self.q) * (x - self.goal.astype(x.dtype))
+        c_u = c(2 * self.r) * u
+        c_xx = np.broadcast_to(c(2 * self.q) * np.eye(d, dtype=x.dtype), (N, d, d))
+        c_uu = np.broadcast_to(c(2 * self.r) * np.eye(m, dtype=x.dtype), (N, m, m))
+        return c_x, c_u, c_xx, c_uu
+
+
+# ----------------------------------------------------------------------------- rollout / ders / LQR
+def rollout(env, cost, U_old, k=None, K=None, X_old=None, alpha=1.0, x0=None):
+    """``igpc.rollout`` (``rollout.py:22-65``).  U_old[N,H,m], k[N,H,m], K[N,H,m,d], X_old[N,H+1,d],
+    alpha scalar or [N].  Returns X[N,H+1,d], U[N,H,m], cost[N] (terminal state not costed)."""
+    N, H, m = U_old.shape
+    dtype = U_old.dtype
+    alpha = np.broadcast_to(np.asarray(alpha, dtype=dtype), (N,))
+    X = np.zeros((N, H + 1, env.d), dtype=dtype)
+    U = np.zeros((N, H, m), dtype=dtype)
+    X[:, 0] = env.init(N, dtype) if x0 is None else x0
+    c = np.zeros(N, dtype=dtype)
+    for h in range(H):
+        if k is None:
+            U[:, h] = U_old[:, h]                                           # :52-53
+        else:
+            U[:, h] = (U_old[:, h] + alpha[:, None] * k[:, h]) + np.einsum(
+                "nij,nj->ni", K[:, h], X[:, h] - X_old[:, h])               # :55-57
+        X[:, h + 1] = env.step(X[:, h], U[:, h])                            # :59
+        c = c + cost(X[:, h], U[:, h])                                      # :60
+    return X, U, c
+
+
+def compute_ders(env, cost, X, U):
+    """``compute_ders`` (``rollout.py:68-99``): D[N,H,d], (F_x[N,H,d,d], F_u[N,H,d,m]),
+    (c_x, c_u, c_xx, c_uu) per step."""
+    N, H, m = U.shape
+    d = env.d
+    x0 = X[:, :-1].reshape(N * H, d)
+    u = U.reshape(N * H, m)
+    D = (X[:, 1:].reshape(N * H, d) - env.step(x0, u)).reshape(N, H, d)
+    Fx, Fu = env.jac(x0, u)
+    c_x, c_u, c_xx, c_uu = cost.ders(x0, u)
+    r = lambda a: a.reshape((N, H) + a.shape[1:])
+    return D, (r(Fx), r(Fu)), (r(c_x), r(c_u), r(c_xx), r(c_uu))
+
+
+def lqr_backward(F, C):
+    """``LQR`` (``lqr_solver.py:40-86``): Riccati backward pass.  Returns k[N,H,m], K[N,H,m,d]."""
+    Fx, Fu = F
+    c_x, c_u, c_xx, c_uu = C
+    N, H, d, m = Fu.shape
+    dtype = Fx.dtype
+    k = np.zeros((N, H, m), dtype=dtype)
+    K = np.zeros((N, H, m, d), dtype=dtype)
+    V_x = np.zeros((N, d), dtype=dtype)
+    V_xx = np.zeros((N, d, d), dtype=dtype)
+    T = lambda a: np.swapaxes(a, 1, 2)
+    for h in range(H - 1, -1, -1):
+        fx, fu = Fx[:, h], Fu[:, h]
+        Q_x = c_x[:, h] + np.einsum("nji,nj->ni", fx, V_x)
+        Q_u = c_u[:, h] + np.einsum("nji,nj->ni", fu, V_x)
+        Q_xx = c_xx[:, h] + T(fx) @ V_xx @ fx
+        Q_ux = T(fu) @ V_xx @ fx
+        Q_uu = c_uu[:, h] + T(fu) @ V_xx @ fu
+        Qi = np.linalg.inv(Q_uu)
+        K[:, h] = -Qi @ Q_ux
+        k[:, h] = -np.einsum("nij,nj->ni", Qi, Q_u)
+        V_x = Q_x - np.einsum("nji,nj->ni", K[:, h], np.einsum("nij,nj->ni", Q_uu, k[:, h]))
+        V_xx = Q_xx - T(K[:, h]) @ Q_uu @ K[:, h]
+        V_xx = (V_xx + T(V_xx)) / dtype.type(2)
+    return k, K
+
+
+# ----------------------------------------------------------------------------- iLQR
+def ilqr(env, cost, U, T, x0=None, alpha=0.5, backtracking=True, fix_backtracking=False, n_alpha=10):
+    """``iLQR`` (``ilqr.py:27-93``).  Returns X, U, k, K, c, alpha[N]."""
+    N = U.shape[0]
+    dtype = U.dtype
+    X, U, c = rollout(env, cost, U, x0=x0)
+    alpha = np.full(N, alpha, dtype=dtype)
+    k = K = None
+    for _ in range(T):
+        _, F, C = compute_ders(env, cost, X, U)
+        k, K = lqr_backward(F, C)
+        if backtracking:
+            done = np.zeros(N, dtype=bool)
+            Xn, Un, cn, an = X.copy(), U.copy(), c.copy(), alpha.copy()
+            # as written every candidate rollout uses `alpha` (A-10), so all ten are identical and only
+            # j = 0 can ever be accepted; with the fix each candidate uses its own alphaC
+            for j in range(n_alpha if fix_backtracking else 1):
+                alphaC = (alpha * dtype.type(1.1)) * dtype.type(1.1) ** dtype.type(-(j ** 2))     # :55
+                XC, UC, cC = rollout(env, cost, U, k, K, X, alphaC if fix_backtracking else alpha, x0=x0)
+                acc = (~done) & (cC <= c)                                   # :73
+                Xn[acc], Un[acc], cn[acc], an[acc] = XC[acc], UC[acc], cC[acc], alphaC[acc]
+                done |= acc
+                if done.all():
+                    break
+            X, U, c, alpha = Xn, Un, cn, an
+        else:
+            X, U, c = rollout(env, cost, U, k, K, X, alpha, x0=x0)          # :78-90
+    return X, U, k, K, c, alpha
+
+
+# ----------------------------------------------------------------------------- iGPC
+def igpc_counterfact_grad(env, cost, E, off, W, x, U_old, k, K, X_old, alpha, Cc=1.0, H=3, M=3):
+    """grad of ``counterfact_loss`` wrt (E, off) (``igpc.py:22-60``) by a hand adjoint.
+
+    Only the LAST step's cost is returned by the reference (``cost =``, ``:41``), so the loss is
+    c(y_{H-1}, u_{H-1}) with y advanced H-1 times by env_sim + W[h+M].
+    E[N,H,m,d], off[N,m], W[N,H+M,d], x[N,d]; U_old/k/K/X_old are the H-step windows."""
+    N, d = x.shape
+    m = off.shape[1]
+    dtype = x.dtype
+    ys, us, Fxs, Fus = [], [], [], []
+    y = x
+    for h in range(H):
+        ud = np.einsum("nhij,nhj->ni", E, W[:, h:h + M]) + off              # :27-34
+        u = ((U_old[:, h] + alpha[:, None] * k[:, h]) + np.einsum("nij,nj->ni", K[:, h], y - X_old[:, h])) \
+            + dtype.type(Cc) * ud                                           # :35-40
+        ys.append(y)
+        us.append(u)
+        if h < H - 1:
+            Fx, Fu = env.jac(y, u)
+            Fxs.append(Fx)
+            Fus.append(Fu)
+            y = env.step(y, u) + W[:, h + M]                                # :43-44
+    c_x, c_u, _, _ = cost.ders(ys[-1], us[-1])
+    gE = np.zeros_like(E)
+    goff = np.zeros_like(off)
+    lam_y, lam_u = c_x, c_u
+    for h in range(H - 1, -1, -1):
+        # u_h depends on y_h through K[h] and on (E, off) through C * u_delta
+        gE += dtype.type(Cc) * np.einsum("ni,nhj->nhij", lam_u, W[:, h:h + M])
+        goff += dtype.type(Cc) * lam_u
+        lam_y = lam_y + np.einsum("nij,ni->nj", K[:, h], lam_u)
+        if h > 0:
+            Fx, Fu = Fxs[h - 1], Fus[h - 1]
+            lam_u = np.einsum("nij,ni->nj", Fu, lam_y)
+            lam_y = np.einsum("nij,ni->nj", Fx, lam_y)
+    return gE, goff
+
+
+def gpc_rollout(env_true, env_sim, cost, U_old, k, K, X_old, D, F, alpha, w_is="de", ref_lr=0.1, x0=None):
+    """``GPC_rollout`` (``igpc.py:63-126``).  Returns X, U, cost[N]."""
+    H_, M_, lr, Cc = 3, 3, ref_lr, 1.0                                      # :67
+    N, Hh, m = U_old.shape
+    d = env_sim.d
+    dtype = U_old.dtype
+    alpha = np.broadcast_to(np.asarray(alpha, dtype=dtype), (N,))
+    X = np.zeros((N, Hh + 1, d), dtype=dtype)
+    U = np.zeros((N, Hh, m), dtype=dtype)
+    W = np.zeros((N, H_ + M_, d), dtype=dtype)
+    E = np.zeros((N, H_, m, d), dtype=dtype)
+    off = np.zeros((N, m), dtype=dtype)
+    X[:, 0] = env_true.init(N, dtype) if x0 is None else x0
+    c = np.zeros(N, dtype=dtype)
+    for h in range(Hh):
+        ud = np.einsum("nhij,nhj->ni", E, W[:, -M_:]) + off                 # :80
+        U[:, h] = ((U_old[:, h] + alpha[:, None] * k[:, h]) + np.einsum(
+            "nij,nj->ni", K[:, h], X[:, h] - X_old[:, h])) + dtype.type(Cc) * ud          # :81-86
+        X[:, h + 1] = env_true.step(X[:, h], U[:, h])                       # :87
+        c = c + cost(X[:, h], U[:, h])                                      # :88
+        new_state = env_sim.step(X[:, h], U[:, h])                          # :91
+        if w_is == "de":
+            w = X[:, h + 1] - new_state
+        elif w_is == "dede":
+            w = (X[:, h + 1] - new_state) - D[:, h]
+        else:
+            w = X[:, h + 1] - (X_old[:, h + 1] + np.einsum("nij,nj->ni", F[0][:, h], X[:, h] - X_old[:, h])
+                               + np.einsum("nij,nj->ni", F[1][:, h], U[:, h] - U_old[:, h]))
+        W = np.concatenate([W[:, 1:], w[:, None]], axis=1)                  # :103-104
+        if h >= H_:
+            s = slice(h - H_, h)                                            # the first H entries of [h-H:]
+            gE, goff = igpc_counterfact_grad(env_sim, cost, E, off, W, X[:, h - H_], U_old[:, s], k[:, s],
+                                             K[:, s], X_old[:, s], alpha, Cc, H_, M_)
+            E = E - dtype.type(lr / h) * gE                                 # :124-125
+            off = off - dtype.type(lr / h) * goff
+    return X, U, c
+
+
+def igpc_closed(env_true, env_sim, cost, U, T, w_is="de", lr=0.1, ref_alpha=1.0, backtracking=True,
+                x0=None, n_alpha=6):
+    """``iGPC_closed`` (``igpc.py:129-179``) with ``verbose=False`` (no LR annealing, ``:153-156``)."""
+    N = U.shape[0]
+    dtype = U.dtype
+    alpha = np.full(N, ref_alpha, dtype=dtype)
+    X, U, c = rollout(env_true, cost, U, x0=x0)
+    k = K = None
+    for _ in range(T):
+        D, F, C = compute_ders(env_sim, cost, X, U)
+        k, K = lqr_backward(F, C)
+        if backtracking:
+            done = np.zeros(N, dtype=bool)
+            Xn, Un, cn, an = X.copy(), U.copy(), c.copy(), alpha.copy()
+            for j in range(n_alpha):
+                alphaC = (alpha * dtype.type(1.1)) * dtype.type(1.1) ** dtype.type(-(j ** 2))     # :159
+                XC, UC, cC = gpc_rollout(env_true, env_sim, cost, U, k, K, X, D, F, alphaC, w_is, lr, x0=x0)
+                acc = (~done) & (cC < c)                                    # strict, :164
+                Xn[acc], Un[acc], cn[acc], an[acc] = XC[acc], UC[acc], cC[acc], alphaC[acc]
+                done |= acc
+                if done.all():
+                    break
+            X, U, c, alpha = Xn, Un, cn, an
+        else:
+            X, U, c = gpc_rollout(env_true, env_sim, cost, U, k, K, X, D, F, alpha, w_is, lr, x0=x0)
+    return X, U, k, K, c, alpha
+
+
+def ilc_closed(env_true, env_sim, cost, U, T, ref_alpha=1.0, x0=None, n_alpha=10):
+    """``iLC_closed`` (``ilc.py:23-69``) with backtracking and ``verbose=False``: derivatives from
+    env_sim, candidate rollouts on env_true with alphaC, accept the first cC <= c.  (With
+    ``verbose=False`` ``prev_loop_fail`` is never cleared but also never acted on, ``:44-47,58``.)"""
+    N = U.shape[0]
+    dtype = U.dtype
+    alpha = np.full(N, ref_alpha, dtype=dtype)
+    X, U, c = rollout(env_true, cost, U, x0=x0)
+    k = K = None
+    for _ in range(T):
+        _, F, C = compute_ders(env_sim, cost, X, U)
+        k, K = lqr_backward(F, C)
+        done = np.zeros(N, dtype=bool)
+        Xn, Un, cn, an = X.copy(), U.copy(), c.copy(), alpha.copy()
+        for j in range(n_alpha):
+            alphaC = (alpha * dtype.type(1.1)) * dtype.type(1.1) ** dtype.type(-(j ** 2))
+            XC, UC, cC = rollout(env_true, cost, U, k, K, X, alphaC, x0=x0)
+            acc = (~done) & (cC <= c)
+            Xn[acc], Un[acc], cn[acc], an[acc] = XC[acc], UC[acc], cC[acc], alphaC[acc]
+            done |= acc
+            if done.all():
+                break
+        X, U, c, alpha = Xn, Un, cn, an
+    return X, U, k, K, c, alpha

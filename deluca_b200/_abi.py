@@ -70,6 +70,20 @@ class DlcLungBuffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in LUNG_BUFFER_FIELDS]
 
 
+class DlcEnvSpec(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("p", ctypes.c_float * 7)]
+
+
+class DlcPlanParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int64), ("H", ctypes.c_int32), ("T", ctypes.c_int32),
+        ("env_true", DlcEnvSpec), ("env_sim", DlcEnvSpec),
+        ("q", ctypes.c_float * 8), ("goal", ctypes.c_float * 8), ("r", ctypes.c_float * 4),
+        ("algo", ctypes.c_int32), ("backtracking", ctypes.c_int32), ("fix_backtracking", ctypes.c_int32),
+        ("n_alpha", ctypes.c_int32), ("w_is", ctypes.c_int32), ("alpha0", ctypes.c_float), ("lr", ctypes.c_float),
+    ]
+
+
 POLICY = {"lqr": 0, "gpc": 1, "bpc": 2, "open": 3}
 
 # every symbol include/deluca_b200.h declares: name -> (restype, argtypes)
@@ -84,6 +98,13 @@ SYMBOLS = {
     "dlc_sizeof": (ctypes.c_size_t, [ctypes.c_int32]),
     "dlc_lung_pid_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLungParams), ctypes.POINTER(DlcLungBuffers), _P]),
     "dlc_pid_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_float] + [_P] * 9),
+    "dlc_env_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams), ctypes.c_int32] + [_P] * 10),
+    "dlc_linearize_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams), ctypes.c_int32] + [_P] * 10),
+    "dlc_riccati_backward_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+                                 + [_P] * 10),
+    "dlc_igpc_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 10),
+    "dlc_plan_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcPlanParams)]),
+    "dlc_plan_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 9 + [ctypes.c_size_t, _P]),
     "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),
     "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
     "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 18
@@ -106,7 +127,7 @@ def lib():
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args
-            for which, struct in enumerate((DlcLdsParams, DlcLungParams, DlcLungBuffers)):
+            for which, struct in enumerate((DlcLdsParams, DlcLungParams, DlcLungBuffers, DlcPlanParams)):
                 if L.dlc_sizeof(which) != ctypes.sizeof(struct):
                     raise ImportError(f"{struct.__name__}: ctypes layout ({ctypes.sizeof(struct)} B) does not match "
                                       f"the library ({L.dlc_sizeof(which)} B); rebuild libdeluca_b200.so")

@@ -28,6 +28,7 @@ extern "C" size_t dlc_sizeof(int32_t which) {
     case 0: return sizeof(DlcLdsParams);
     case 1: return sizeof(DlcLungParams);
     case 2: return sizeof(DlcLungBuffers);
+    case 3: return sizeof(DlcPlanParams);
     default: return 0;
   }
 }

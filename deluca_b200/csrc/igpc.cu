@@ -1,0 +1,770 @@
+// deluca/igpc on the device: trajectory rollouts of the classic envs, closed-form
+// linearisation, the Riccati backward pass, GPC_rollout with a hand adjoint of counterfact_loss, and
+// the iLQR / iGPC_closed / iLC_closed outer loops with their backtracking, all batched over N
+// independent trajectories, one thread per trajectory.  Per-trajectory data (X, U, k, K: 6.4 KB at
+// d=3, H=200) stays in the caller's env-major arrays, which are L2-resident for the configured sizes;
+// the time axis is a serial dependency chain, so these kernels are latency- not bandwidth-bound.
+#include "common.cuh"
+
+namespace dlc {
+
+// ----------------------------------------------------------------------------------- env models
+template <int KIND>
+struct Model;
+
+template <>
+struct Model<DLC_ENV_PENDULUM> {  // deluca/envs/classic/_pendulum.py:54-73 (as written, SURVEY A-6)
+  static constexpr int D = 3, M = 1;
+  float k1, k2, max_torque, dt;
+  __device__ explicit Model(const DlcEnvSpec& s) {
+    const float m = s.p[0], l = s.p[1], g = s.p[2];
+    max_torque = s.p[3];
+    dt = s.p[4];
+    k1 = -3.0f * g / (2.0f * l);
+    k2 = 3.0f / (m * l * l);
+  }
+  __device__ void step(const float* x, const float* u, float* xn) const {
+    const float th = atan2f(x[0], x[1]);
+    const float a = max_torque * tanhf(u[0]);
+    const float nthd = th + (k1 * sinf(th + 3.14159265358979323846f) + k2 * a);
+    const float nth = th + nthd * dt;
+    float s, c;
+    sincosf(nth, &s, &c);
+    xn[0] = s; xn[1] = c; xn[2] = nthd;
+  }
+  // Fx[i*D+j] = d xn_i / d x_j, Fu[i*M+c] = d xn_i / d u_c
+  __device__ void jac(const float* x, const float* u, float* Fx, float* Fu) const {
+    const float s = x[0], co = x[1];
+    const float r2 = s * s + co * co;
+    const float th = atan2f(s, co);
+    const float dth0 = co / r2, dth1 = -s / r2;
+    const float tu = tanhf(u[0]);
+    const float a = max_torque * tu;
+    float sp, cp;
+    sincosf(th + 3.14159265358979323846f, &sp, &cp);
+    const float nthd = th + (k1 * sp + k2 * a);
+    const float nth = th + nthd * dt;
+    const float dthd_dth = 1.0f + k1 * cp;
+    const float dnth_dth = 1.0f + dt * dthd_dth;
+    float sn, cn;
+    sincosf(nth, &sn, &cn);
+    Fx[0] = cn * dnth_dth * dth0;  Fx[1] = cn * dnth_dth * dth1;  Fx[2] = 0.f;
+    Fx[3] = -sn * dnth_dth * dth0; Fx[4] = -sn * dnth_dth * dth1; Fx[5] = 0.f;
+    Fx[6] = dthd_dth * dth0;       Fx[7] = dthd_dth * dth1;       Fx[8] = 0.f;
+    const float dthd_du = k2 * max_torque * (1.0f - tu * tu);
+    Fu[0] = cn * dt * dthd_du; Fu[1] = -sn * dt * dthd_du; Fu[2] = dthd_du;
+  }
+};
+
+template <>
+struct Model<DLC_ENV_CARTPOLE> {  // _cartpole.py:60-89, intent-fixed (SURVEY A-7)
+  static constexpr int D = 4, M = 1;
+  float a21, a31, b2, b3, dt, offset;
+  __device__ explicit Model(const DlcEnvSpec& s) {
+    const float m = s.p[0], Mc = s.p[1], l = s.p[2], g = s.p[3];
+    dt = s.p[4];
+    offset = s.p[5];
+    a21 = dt * m * g / Mc;
+    a31 = dt * (m + Mc) * g / (Mc * l);
+    b2 = dt / Mc;
+    b3 = dt / (Mc * l);
+  }
+  __device__ void step(const float* x, const float* u, float* xn) const {
+    const float v = u[0] + offset;
+    xn[0] = x[0] + dt * x[2];
+    xn[1] = x[1] + dt * x[3];
+    xn[2] = (a21 * x[1] + x[2]) + b2 * v;
+    xn[3] = (a31 * x[1] + x[3]) + b3 * v;
+  }
+  __device__ void jac(const float*, const float*, float* Fx, float* Fu) const {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Fx[i] = 0.f;
+    Fx[0] = 1.f; Fx[2] = dt; Fx[5] = 1.f; Fx[7] = dt; Fx[9] = a21; Fx[10] = 1.f; Fx[13] = a31; Fx[15] = 1.f;
+    Fu[0] = 0.f; Fu[1] = 0.f; Fu[2] = b2; Fu[3] = b3;
+  }
+};
+
+template <int D, int M>
+__device__ __forceinline__ float quad_cost(const DlcPlanParams& p, const float* x, const float* u) {
+  float cx = 0.f, cu = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const float e = x[i] - p.goal[i];
+    cx = fmaf(p.q[i] * e, e, cx);
+  }
+#pragma unroll
+  for (int c = 0; c < M; ++c) cu = fmaf(p.r[c] * u[c], u[c], cu);
+  return cx + cu;
+}
+
+// u = U_old[h] + alpha k[h] + K[h] (x - X_old[h])                        rollout.py:55-57
+template <int D, int M>
+__device__ __forceinline__ void feedback_u(const float* Uo, const float* kk, const float* KK, const float* Xo,
+                                           float alpha, const float* x, float* u) {
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) s = fmaf(KK[c * D + j], x[j] - Xo[j], s);
+    u[c] = (Uo[c] + alpha * kk[c]) + s;
+  }
+}
+
+// igpc.rollout for one trajectory.  Returns the cost; X/U written to Xw/Uw.
+template <class Mdl>
+__device__ float rollout_one(const Mdl& env, const DlcPlanParams& p, const float* Uo, const float* kk,
+                             const float* KK, const float* Xo, float alpha, const float* x0, float* Xw, float* Uw) {
+  constexpr int D = Mdl::D, M = Mdl::M;
+  float x[D], u[M], xn[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) { x[i] = x0[i]; Xw[i] = x[i]; }
+  float cost = 0.f;
+  for (int h = 0; h < p.H; ++h) {
+    if (kk == nullptr) {
+#pragma unroll
+      for (int c = 0; c < M; ++c) u[c] = Uo[h * M + c];
+    } else {
+      feedback_u<D, M>(Uo + h * M, kk + h * M, KK + h * M * D, Xo + h * D, alpha, x, u);
+    }
+    env.step(x, u, xn);
+    cost += quad_cost<D, M>(p, x, u);
+#pragma unroll
+    for (int c = 0; c < M; ++c) Uw[h * M + c] = u[c];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { x[i] = xn[i]; Xw[(h + 1) * D + i] = xn[i]; }
+  }
+  return cost;
+}
+
+// small dense inverse (Gauss-Jordan, partial pivoting); returns false if singular / non-finite
+template <int M>
+__device__ bool inv_small(const float* A, float* Ai) {
+  if (M == 1) {
+    Ai[0] = 1.0f / A[0];
+    return A[0] != 0.f && isfinite(Ai[0]);
+  }
+  float a[M][2 * M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) { a[i][j] = A[i * M + j]; a[i][M + j] = i == j ? 1.f : 0.f; }
+  for (int c = 0; c < M; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < M; ++r) if (fabsf(a[r][c]) > fabsf(a[piv][c])) piv = r;
+    if (a[piv][c] == 0.f) return false;
+    for (int j = 0; j < 2 * M; ++j) { const float t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+    const float inv = 1.0f / a[c][c];
+    for (int j = 0; j < 2 * M; ++j) a[c][j] *= inv;
+    for (int r = 0; r < M; ++r) {
+      if (r == c) continue;
+      const float f = a[r][c];
+      for (int j = 0; j < 2 * M; ++j) a[r][j] -= f * a[c][j];
+    }
+  }
+  bool ok = true;
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < M; ++j) { Ai[i * M + j] = a[i][M + j]; ok &= isfinite(a[i][M + j]); }
+  return ok;
+}
+
+// One Riccati step (lqr_solver.py:68-85); updates V_x, V_xx, writes k[h], K[h].  Returns Q_uu status.
+template <int D, int M>
+__device__ int riccati_step(const float* fx, const float* fu, const float* cx, const float* cu, const float* cxx,
+                            const float* cuu, float* Vx, float* Vxx, float* kh, float* Kh) {
+  float Qx[D], Qu[M], Qxx[D * D], Qux[M * D], Quu[M * M], VF[D * D], VFu[D * M];
+  // VF = V_xx f_x, VFu = V_xx f_u
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int l = 0; l < D; ++l) s = fmaf(Vxx[i * D + l], fx[l * D + j], s);
+      VF[i * D + j] = s;
+    }
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int l = 0; l < D; ++l) s = fmaf(Vxx[i * D + l], fu[l * M + c], s);
+      VFu[i * M + c] = s;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < D; ++l) s = fmaf(fx[l * D + i], Vx[l], s);
+    Qx[i] = cx[i] + s;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < D; ++l) t = fmaf(fx[l * D + i], VF[l * D + j], t);
+      Qxx[i * D + j] = cxx[i * D + j] + t;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int l = 0; l < D; ++l) s = fmaf(fu[l * M + c], Vx[l], s);
+    Qu[c] = cu[c] + s;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < D; ++l) t = fmaf(fu[l * M + c], VF[l * D + j], t);
+      Qux[c * D + j] = t;
+    }
+#pragma unroll
+    for (int e = 0; e < M; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < D; ++l) t = fmaf(fu[l * M + c], VFu[l * M + e], t);
+      Quu[c * M + e] = cuu[c * M + e] + t;
+    }
+  }
+  float Qi[M * M];
+  int status = 0;
+  if (!inv_small<M>(Quu, Qi)) status |= DLC_STATUS_NOT_PD;
+  if (M == 1 && !(Quu[0] > 0.f)) status |= DLC_STATUS_NOT_PD;
+  float Kl[M * D], kl[M];
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < M; ++e) s = fmaf(Qi[c * M + e], Qu[e], s);
+    kl[c] = -s;
+    kh[c] = -s;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < M; ++e) t = fmaf(Qi[c * M + e], Qux[e * D + j], t);
+      Kl[c * D + j] = -t;
+      Kh[c * D + j] = -t;
+    }
+  }
+  // V_x = Q_x - K' Q_uu k ; V_xx = Q_xx - K' Q_uu K ; symmetrise
+  float Qk[M], QK[M * D];
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < M; ++e) s = fmaf(Quu[c * M + e], kl[e], s);
+    Qk[c] = s;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < M; ++e) t = fmaf(Quu[c * M + e], Kl[e * D + j], t);
+      QK[c * D + j] = t;
+    }
+  }
+  float Vn[D * D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < M; ++c) s = fmaf(Kl[c * D + i], Qk[c], s);
+    Vx[i] = Qx[i] - s;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int c = 0; c < M; ++c) t = fmaf(Kl[c * D + i], QK[c * D + j], t);
+      Vn[i * D + j] = Qxx[i * D + j] - t;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) Vxx[i * D + j] = (Vn[i * D + j] + Vn[j * D + i]) * 0.5f;
+  return status;
+}
+
+template <int D, int M>
+__device__ __forceinline__ void cost_ders(const DlcPlanParams& p, const float* x, const float* u, float* cx, float* cu,
+                                          float* cxx, float* cuu) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    cx[i] = (2.0f * p.q[i]) * (x[i] - p.goal[i]);
+#pragma unroll
+    for (int j = 0; j < D; ++j) cxx[i * D + j] = i == j ? 2.0f * p.q[i] : 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < M; ++c) {
+    cu[c] = (2.0f * p.r[c]) * u[c];
+#pragma unroll
+    for (int e = 0; e < M; ++e) cuu[c * M + e] = c == e ? 2.0f * p.r[c] : 0.f;
+  }
+}
+
+// compute_ders + LQR fused: linearise env_sim along (X, U) on the fly, going backwards.
+template <class Mdl>
+__device__ int backward_pass(const Mdl& sim, const DlcPlanParams& p, const float* X, const float* U, float* kk,
+                             float* KK) {
+  constexpr int D = Mdl::D, M = Mdl::M;
+  float Vx[D], Vxx[D * D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) Vx[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) Vxx[i] = 0.f;
+  int status = 0;
+  for (int h = p.H - 1; h >= 0; --h) {
+    float x[D], u[M], fx[D * D], fu[D * M], cx[D], cu[M], cxx[D * D], cuu[M * M];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = X[h * D + i];
+#pragma unroll
+    for (int c = 0; c < M; ++c) u[c] = U[h * M + c];
+    sim.jac(x, u, fx, fu);
+    cost_ders<D, M>(p, x, u, cx, cu, cxx, cuu);
+    status |= riccati_step<D, M>(fx, fu, cx, cu, cxx, cuu, Vx, Vxx, kk + h * M, KK + h * M * D);
+  }
+  return status;
+}
+
+// GPC_rollout (igpc.py:63-126) for one trajectory; counterfact_loss gradient by hand adjoint
+// (only the last step's cost survives in the reference, igpc.py:41).
+template <class Mdl>
+__device__ float igpc_rollout_one(const Mdl& tru, const Mdl& sim, const DlcPlanParams& p, const float* Uo,
+                                  const float* kk, const float* KK, const float* Xo, float alpha, const float* x0,
+                                  float* Xw, float* Uw) {
+  constexpr int D = Mdl::D, M = Mdl::M, HG = 3, MG = 3;  // H, M of GPC_rollout (:67)
+  const float Cc = 1.0f;
+  float W[HG + MG][D], E[HG][M][D], off[M];
+#pragma unroll
+  for (int i = 0; i < HG + MG; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) W[i][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < HG; ++i)
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int j = 0; j < D; ++j) E[i][c][j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < M; ++c) off[c] = 0.f;
+  float x[D], u[M], xn[D], xs[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) { x[i] = x0[i]; Xw[i] = x[i]; }
+  float cost = 0.f;
+  for (int h = 0; h < p.H; ++h) {
+    // U_delta = tensordot(E, W[-M:]) + off                                :80
+    feedback_u<D, M>(Uo + h * M, kk + h * M, KK + h * M * D, Xo + h * D, alpha, x, u);
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < HG; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(E[i][c][j], W[HG + i][j], s);
+      u[c] += Cc * (s + off[c]);
+    }
+    tru.step(x, u, xn);                                                    // :87
+    cost += quad_cost<D, M>(p, x, u);                                      // :88
+    sim.step(x, u, xs);                                                    // :91
+    float w[D];
+    if (p.w_is == DLC_W_DE) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = xn[i] - xs[i];
+    } else if (p.w_is == DLC_W_DEDE) {   // D[h] = X_old[h+1] - sim(X_old[h], U_old[h])  (compute_ders)
+      float xo[D], uo[M], so[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xo[i] = Xo[h * D + i];
+#pragma unroll
+      for (int c = 0; c < M; ++c) uo[c] = Uo[h * M + c];
+      sim.step(xo, uo, so);
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = (xn[i] - xs[i]) - (Xo[(h + 1) * D + i] - so[i]);
+    } else {                             // F[h] = jac of sim at (X_old[h], U_old[h])
+      float xo[D], uo[M], fx[D * D], fu[D * M];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xo[i] = Xo[h * D + i];
+#pragma unroll
+      for (int c = 0; c < M; ++c) uo[c] = Uo[h * M + c];
+      sim.jac(xo, uo, fx, fu);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float s = 0.f, t = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(fx[i * D + j], x[j] - xo[j], s);
+#pragma unroll
+        for (int c = 0; c < M; ++c) t = fmaf(fu[i * M + c], u[c] - uo[c], t);
+        w[i] = xn[i] - ((Xo[(h + 1) * D + i] + s) + t);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HG + MG - 1; ++i)                                  // W[0] = w; roll(-1)   :103-104
+#pragma unroll
+      for (int j = 0; j < D; ++j) W[i][j] = W[i + 1][j];
+#pragma unroll
+    for (int j = 0; j < D; ++j) W[HG + MG - 1][j] = w[j];
+#pragma unroll
+    for (int c = 0; c < M; ++c) Uw[h * M + c] = u[c];
+#pragma unroll
+    for (int i = 0; i < D; ++i) Xw[(h + 1) * D + i] = xn[i];
+
+    if (h >= HG) {                                                         // :105-125
+      // forward: y_0 = X[h-H]; y_{j+1} = sim(y_j, u_j) + W[j+M]
+      const int b = h - HG;
+      float y[HG][D], uu[HG][M], Fx[HG - 1][D * D], Fu[HG - 1][D * M];
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[0][i] = Xw[b * D + i];
+#pragma unroll
+      for (int j = 0; j < HG; ++j) {
+        feedback_u<D, M>(Uo + (b + j) * M, kk + (b + j) * M, KK + (b + j) * M * D, Xo + (b + j) * D, alpha, y[j],
+                         uu[j]);
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < HG; ++i)
+#pragma unroll
+            for (int l = 0; l < D; ++l) s = fmaf(E[i][c][l], W[j + i][l], s);
+          uu[j][c] += Cc * (s + off[c]);
+        }
+        if (j < HG - 1) {
+          float yn[D];
+          sim.jac(y[j], uu[j], Fx[j], Fu[j]);
+          sim.step(y[j], uu[j], yn);
+#pragma unroll
+          for (int i = 0; i < D; ++i) y[j + 1][i] = yn[i] + W[j + MG][i];
+        }
+      }
+      // adjoint of c(y_{H-1}, u_{H-1})
+      float ly[D], lu[M], cxx[D * D], cuu[M * M];
+      cost_ders<D, M>(p, y[HG - 1], uu[HG - 1], ly, lu, cxx, cuu);
+      const float sc = p.lr / (float)h;
+#pragma unroll
+      for (int j = HG - 1; j >= 0; --j) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const float g = Cc * lu[c];
+          off[c] -= sc * g;
+#pragma unroll
+          for (int i = 0; i < HG; ++i)
+#pragma unroll
+            for (int l = 0; l < D; ++l) E[i][c][l] -= sc * (g * W[j + i][l]);
+        }
+        // note: E/off of this very update must not feed the remaining adjoint steps -- they do not:
+        // the adjoint only reads W, K, Fx, Fu.
+        const float* Kj = KK + (b + j) * M * D;
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+          float s = ly[l];
+#pragma unroll
+          for (int c = 0; c < M; ++c) s = fmaf(Kj[c * D + l], lu[c], s);
+          ly[l] = s;
+        }
+        if (j > 0) {
+          float nu[M], ny[D];
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s = fmaf(Fu[j - 1][i * M + c], ly[i], s);
+            nu[c] = s;
+          }
+#pragma unroll
+          for (int l = 0; l < D; ++l) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s = fmaf(Fx[j - 1][i * D + l], ly[i], s);
+            ny[l] = s;
+          }
+#pragma unroll
+          for (int c = 0; c < M; ++c) lu[c] = nu[c];
+#pragma unroll
+          for (int l = 0; l < D; ++l) ly[l] = ny[l];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = xn[i];
+  }
+  return cost;
+}
+
+// ----------------------------------------------------------------------------------- kernels
+struct PlanArgs {
+  DlcPlanParams p;
+  const float *U_old, *k, *K, *X_old, *alpha, *x0;
+  float *X_out, *U_out, *cost_out, *k_out, *K_out, *alpha_out;
+  int32_t* status_out;
+  float* ws;
+  int use_sim;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) env_rollout_kernel(const PlanArgs a) {
+  using Mdl = Model<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.p.N) return;
+  const int H = a.p.H;
+  const Mdl env(a.use_sim ? a.p.env_sim : a.p.env_true);
+  const float c = rollout_one(env, a.p, a.U_old + n * H * M, a.k ? a.k + n * H * M : nullptr,
+                              a.K ? a.K + n * H * M * D : nullptr, a.X_old ? a.X_old + n * (H + 1) * D : nullptr,
+                              a.alpha ? a.alpha[n] : 1.0f, a.x0 + n * D, a.X_out + n * (H + 1) * D,
+                              a.U_out + n * H * M);
+  a.cost_out[n] = c;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) igpc_rollout_kernel(const PlanArgs a) {
+  using Mdl = Model<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= a.p.N) return;
+  const int H = a.p.H;
+  const Mdl tru(a.p.env_true), sim(a.p.env_sim);
+  a.cost_out[n] = igpc_rollout_one(tru, sim, a.p, a.U_old + n * H * M, a.k + n * H * M, a.K + n * H * M * D,
+                                   a.X_old + n * (H + 1) * D, a.alpha ? a.alpha[n] : 1.0f, a.x0 + n * D,
+                                   a.X_out + n * (H + 1) * D, a.U_out + n * H * M);
+}
+
+struct LinArgs {
+  DlcPlanParams p;
+  const float *X, *U;
+  float *D_out, *Fx, *Fu, *cx, *cu, *cxx, *cuu;
+  int use_sim;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) linearize_kernel(const LinArgs a) {
+  using Mdl = Model<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (n, h)
+  const int H = a.p.H;
+  if (idx >= a.p.N * H) return;
+  const int64_t n = idx / H;
+  const int h = (int)(idx % H);
+  const Mdl env(a.use_sim ? a.p.env_sim : a.p.env_true);
+  float x[D], u[M], xn[D], fx[D * D], fu[D * M], cx[D], cu[M], cxx[D * D], cuu[M * M];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = a.X[(n * (H + 1) + h) * D + i];
+#pragma unroll
+  for (int c = 0; c < M; ++c) u[c] = a.U[(n * H + h) * M + c];
+  env.step(x, u, xn);
+  env.jac(x, u, fx, fu);
+  cost_ders<D, M>(a.p, x, u, cx, cu, cxx, cuu);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if (a.D_out) a.D_out[idx * D + i] = a.X[(n * (H + 1) + h + 1) * D + i] - xn[i];
+    a.cx[idx * D + i] = cx[i];
+  }
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) { a.Fx[idx * D * D + i] = fx[i]; a.cxx[idx * D * D + i] = cxx[i]; }
+#pragma unroll
+  for (int i = 0; i < D * M; ++i) a.Fu[idx * D * M + i] = fu[i];
+#pragma unroll
+  for (int c = 0; c < M; ++c) a.cu[idx * M + c] = cu[c];
+#pragma unroll
+  for (int i = 0; i < M * M; ++i) a.cuu[idx * M * M + i] = cuu[i];
+}
+
+template <int D, int M>
+__global__ void __launch_bounds__(128) riccati_kernel(int64_t N, int H, const float* Fx, const float* Fu,
+                                                      const float* cx, const float* cu, const float* cxx,
+                                                      const float* cuu, float* k_out, float* K_out,
+                                                      int32_t* status_out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float Vx[D], Vxx[D * D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) Vx[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) Vxx[i] = 0.f;
+  int status = 0;
+  for (int h = H - 1; h >= 0; --h) {
+    const int64_t o = n * H + h;
+    float fx[D * D], fu[D * M], lcx[D], lcu[M], lcxx[D * D], lcuu[M * M];
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) { fx[i] = Fx[o * D * D + i]; lcxx[i] = cxx[o * D * D + i]; }
+#pragma unroll
+    for (int i = 0; i < D * M; ++i) fu[i] = Fu[o * D * M + i];
+#pragma unroll
+    for (int i = 0; i < D; ++i) lcx[i] = cx[o * D + i];
+#pragma unroll
+    for (int c = 0; c < M; ++c) lcu[c] = cu[o * M + c];
+#pragma unroll
+    for (int i = 0; i < M * M; ++i) lcuu[i] = cuu[o * M * M + i];
+    status |= riccati_step<D, M>(fx, fu, lcx, lcu, lcxx, lcuu, Vx, Vxx, k_out + o * M, K_out + o * M * D);
+  }
+  if (status_out) status_out[n] = status;
+}
+
+// iLQR / iGPC_closed / iLC_closed, whole outer loop per trajectory (ilqr.py:27-93, igpc.py:129-179,
+// ilc.py:23-69).  Nominal (X, U) live in X_out / U_io, the candidate in the workspace.
+template <int KIND>
+__global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
+  using Mdl = Model<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M;
+  const DlcPlanParams& p = a.p;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const int H = p.H;
+  const Mdl tru(p.env_true), sim(p.env_sim);
+  float* X = a.X_out + n * (H + 1) * D;
+  float* U = a.U_out + n * H * M;
+  float* kk = a.k_out + n * H * M;
+  float* KK = a.K_out + n * H * M * D;
+  float* XC = a.ws + n * ((H + 1) * D + H * M);
+  float* UC = XC + (H + 1) * D;
+  const float* x0 = a.x0 + n * D;
+  // initial open-loop rollout into the candidate buffers, then adopt it (U may alias U_old)
+  float c = rollout_one(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
+  float alpha = p.alpha0;
+  int status = 0;
+  for (int t = 0; t < p.T; ++t) {
+    status |= backward_pass(sim, p, X, U, kk, KK);   // compute_ders(env_sim) + LQR
+    const bool ilqr = p.algo == DLC_ALGO_ILQR;
+    if (p.backtracking) {
+      // iLQR as written passes `alpha` (not alphaC) to every candidate: they are identical, so only
+      // the first can be accepted (SURVEY A-10)
+      const int ncand = (ilqr && !p.fix_backtracking) ? 1 : p.n_alpha;
+      for (int j = 0; j < ncand; ++j) {
+        const float alphaC = (alpha * 1.1f) * powf(1.1f, -(float)(j * j));
+        const float a_use = (ilqr && !p.fix_backtracking) ? alpha : alphaC;
+        float cC;
+        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, a_use, x0, XC, UC);
+        else cC = rollout_one(tru, p, U, kk, KK, X, a_use, x0, XC, UC);
+        const bool accept = p.algo == DLC_ALGO_IGPC ? (cC < c) : (cC <= c);
+        if (accept) {
+          for (int i = 0; i < (H + 1) * D; ++i) X[i] = XC[i];
+          for (int i = 0; i < H * M; ++i) U[i] = UC[i];
+          c = cC;
+          alpha = alphaC;
+          break;
+        }
+      }
+    } else {
+      if (p.algo == DLC_ALGO_IGPC) c = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alpha, x0, XC, UC);
+      else c = rollout_one(tru, p, U, kk, KK, X, alpha, x0, XC, UC);
+      for (int i = 0; i < (H + 1) * D; ++i) X[i] = XC[i];
+      for (int i = 0; i < H * M; ++i) U[i] = UC[i];
+    }
+  }
+  a.cost_out[n] = c;
+  if (a.alpha_out) a.alpha_out[n] = alpha;
+  if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
+  if (a.status_out) a.status_out[n] = status;
+}
+
+static int32_t check_plan(const DlcPlanParams* p, const char* who) {
+  if (!p) return fail(DLC_ERR_ARG, "NULL params");
+  if (p->N < 0 || p->H < 1 || p->T < 0) return fail(DLC_ERR_ARG, "bad N / H / T");
+  if (p->env_true.kind != p->env_sim.kind) return fail(DLC_ERR_SHAPE, "env_true and env_sim must be the same kind of env");
+  if (p->env_true.kind != DLC_ENV_PENDULUM && p->env_true.kind != DLC_ENV_CARTPOLE)
+    return fail(DLC_ERR_SHAPE, "unknown env kind");
+  (void)who;
+  return DLC_OK;
+}
+
+}  // namespace dlc
+
+using namespace dlc;
+
+#define DLC_DISPATCH_ENV(kind, KERNEL, grid, st, args)                                   \
+  do {                                                                                    \
+    if ((kind) == DLC_ENV_PENDULUM) KERNEL<DLC_ENV_PENDULUM><<<grid, 128, 0, st>>>(args); \
+    else KERNEL<DLC_ENV_CARTPOLE><<<grid, 128, 0, st>>>(args);                            \
+  } while (0)
+
+extern "C" int32_t dlc_env_rollout_f32(const DlcPlanParams* p, int32_t use_sim_env, const float* U_old,
+                                       const float* k, const float* K, const float* X_old, const float* alpha,
+                                       const float* x0, float* X_out, float* U_out, float* cost_out, void* stream) {
+  int32_t rc = check_plan(p, "dlc_env_rollout_f32");
+  if (rc) return rc;
+  if (p->N == 0) return DLC_OK;
+  if (!U_old || !x0 || !X_out || !U_out || !cost_out) return fail(DLC_ERR_ARG, "dlc_env_rollout_f32: NULL buffer");
+  if (k && (!K || !X_old)) return fail(DLC_ERR_ARG, "dlc_env_rollout_f32: k needs K and X_old");
+  PlanArgs a{};
+  a.p = *p; a.U_old = U_old; a.k = k; a.K = K; a.X_old = X_old; a.alpha = alpha; a.x0 = x0;
+  a.X_out = X_out; a.U_out = U_out; a.cost_out = cost_out; a.use_sim = use_sim_env;
+  const unsigned grid = (unsigned)((p->N + 127) / 128);
+  DLC_DISPATCH_ENV(p->env_true.kind, env_rollout_kernel, grid, (cudaStream_t)stream, a);
+  return cuda_status(cudaGetLastError(), "env_rollout_kernel launch");
+}
+
+extern "C" int32_t dlc_igpc_rollout_f32(const DlcPlanParams* p, const float* U_old, const float* k, const float* K,
+                                        const float* X_old, const float* alpha, const float* x0, float* X_out,
+                                        float* U_out, float* cost_out, void* stream) {
+  int32_t rc = check_plan(p, "dlc_igpc_rollout_f32");
+  if (rc) return rc;
+  if (p->N == 0) return DLC_OK;
+  if (!U_old || !k || !K || !X_old || !x0 || !X_out || !U_out || !cost_out)
+    return fail(DLC_ERR_ARG, "dlc_igpc_rollout_f32: NULL buffer");
+  if (p->w_is < DLC_W_DE || p->w_is > DLC_W_DELIN) return fail(DLC_ERR_ARG, "dlc_igpc_rollout_f32: bad w_is");
+  PlanArgs a{};
+  a.p = *p; a.U_old = U_old; a.k = k; a.K = K; a.X_old = X_old; a.alpha = alpha; a.x0 = x0;
+  a.X_out = X_out; a.U_out = U_out; a.cost_out = cost_out;
+  const unsigned grid = (unsigned)((p->N + 127) / 128);
+  DLC_DISPATCH_ENV(p->env_true.kind, igpc_rollout_kernel, grid, (cudaStream_t)stream, a);
+  return cuda_status(cudaGetLastError(), "igpc_rollout_kernel launch");
+}
+
+extern "C" int32_t dlc_linearize_f32(const DlcPlanParams* p, int32_t use_sim_env, const float* X, const float* U,
+                                     float* D_out, float* Fx_out, float* Fu_out, float* cx_out, float* cu_out,
+                                     float* cxx_out, float* cuu_out, void* stream) {
+  int32_t rc = check_plan(p, "dlc_linearize_f32");
+  if (rc) return rc;
+  if (p->N == 0) return DLC_OK;
+  if (!X || !U || !Fx_out || !Fu_out || !cx_out || !cu_out || !cxx_out || !cuu_out)
+    return fail(DLC_ERR_ARG, "dlc_linearize_f32: NULL buffer");
+  LinArgs a{};
+  a.p = *p; a.X = X; a.U = U; a.D_out = D_out; a.Fx = Fx_out; a.Fu = Fu_out; a.cx = cx_out; a.cu = cu_out;
+  a.cxx = cxx_out; a.cuu = cuu_out; a.use_sim = use_sim_env;
+  const unsigned grid = (unsigned)((p->N * p->H + 127) / 128);
+  DLC_DISPATCH_ENV(p->env_true.kind, linearize_kernel, grid, (cudaStream_t)stream, a);
+  return cuda_status(cudaGetLastError(), "linearize_kernel launch");
+}
+
+extern "C" int32_t dlc_riccati_backward_f32(int64_t N, int32_t H, int32_t d, int32_t m, const float* Fx,
+                                            const float* Fu, const float* cx, const float* cu, const float* cxx,
+                                            const float* cuu, float* k_out, float* K_out, int32_t* status_out,
+                                            void* stream) {
+  if (N < 0 || H < 1) return fail(DLC_ERR_ARG, "dlc_riccati_backward_f32: bad N / H");
+  if (N == 0) return DLC_OK;
+  if (!Fx || !Fu || !cx || !cu || !cxx || !cuu || !k_out || !K_out)
+    return fail(DLC_ERR_ARG, "dlc_riccati_backward_f32: NULL buffer");
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RIC(D_, M_)                                                                                         \
+  if (d == D_ && m == M_) {                                                                                 \
+    riccati_kernel<D_, M_><<<grid, 128, 0, st>>>(N, H, Fx, Fu, cx, cu, cxx, cuu, k_out, K_out, status_out); \
+    return cuda_status(cudaGetLastError(), "riccati_kernel launch");                                        \
+  }
+  RIC(3, 1) RIC(4, 1) RIC(2, 1) RIC(4, 2) RIC(6, 2) RIC(6, 3) RIC(8, 2)
+#undef RIC
+  return fail(DLC_ERR_SHAPE, "dlc_riccati_backward_f32: (d, m) not instantiated: (2,1) (3,1) (4,1) (4,2) (6,2) (6,3) (8,2)");
+}
+
+extern "C" size_t dlc_plan_workspace_bytes(const DlcPlanParams* p) {
+  if (!p || p->N <= 0 || p->H < 1) return 0;
+  const int d = p->env_true.kind == DLC_ENV_PENDULUM ? 3 : 4, m = 1;
+  return (size_t)p->N * ((size_t)(p->H + 1) * d + (size_t)p->H * m) * sizeof(float);
+}
+
+extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float* x0, float* X_out, float* k_out,
+                                float* K_out, float* cost_out, float* alpha_out, int32_t* status_out,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  int32_t rc = check_plan(p, "dlc_plan_f32");
+  if (rc) return rc;
+  if (p->algo < DLC_ALGO_ILQR || p->algo > DLC_ALGO_ILC) return fail(DLC_ERR_ARG, "dlc_plan_f32: unknown algo");
+  if (p->w_is < DLC_W_DE || p->w_is > DLC_W_DELIN) return fail(DLC_ERR_ARG, "dlc_plan_f32: bad w_is");
+  if (p->backtracking && p->n_alpha < 1) return fail(DLC_ERR_ARG, "dlc_plan_f32: n_alpha must be >= 1");
+  if (p->N == 0) return DLC_OK;
+  if (!U_io || !x0 || !X_out || !k_out || !K_out || !cost_out)
+    return fail(DLC_ERR_ARG, "dlc_plan_f32: NULL buffer");
+  if (!workspace || workspace_bytes < dlc_plan_workspace_bytes(p))
+    return fail(DLC_ERR_WORKSPACE, "dlc_plan_f32: workspace smaller than dlc_plan_workspace_bytes()");
+  PlanArgs a{};
+  a.p = *p; a.U_out = U_io; a.x0 = x0; a.X_out = X_out; a.k_out = k_out; a.K_out = K_out; a.cost_out = cost_out;
+  a.alpha_out = alpha_out; a.status_out = status_out; a.ws = (float*)workspace;
+  const unsigned grid = (unsigned)((p->N + 127) / 128);
+  DLC_DISPATCH_ENV(p->env_true.kind, plan_kernel, grid, (cudaStream_t)stream, a);
+  return cuda_status(cudaGetLastError(), "plan_kernel launch");
+}

@@ -1,0 +1,2 @@
+from ._cartpole import Cartpole, CartpoleState  # noqa: F401
+from ._pendulum import Pendulum, PendulumState, QuadCost  # noqa: F401

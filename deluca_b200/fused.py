@@ -135,3 +135,108 @@ def pid_rollout(K_P, K_I, K_D, err, P, I, D, decay):
                                     _abi.ptr(P), _abi.ptr(I), _abi.ptr(D), _abi.ptr(u), _abi.current_stream_ptr())
     _abi.check(rc, "dlc_pid_f32")
     return u, P, I, D
+
+
+# ------------------------------------------------------------------------------------------ igpc
+def plan_params(env_true, env_sim, cost, N, H, T=0, algo=0, backtracking=True, fix_backtracking=False,
+                n_alpha=10, w_is=0, alpha0=1.0, lr=0.1):
+    """``DlcPlanParams`` from env/cost mirror objects (``env.spec()`` -> (kind, [static fields]))."""
+    p = _abi.DlcPlanParams()
+    p.N, p.H, p.T = N, H, T
+    for dst, env in ((p.env_true, env_true), (p.env_sim, env_sim)):
+        kind, vals = env.spec()
+        dst.kind = kind
+        for i, v in enumerate(vals):
+            dst.p[i] = v
+    d, m = env_true.state_dim, env_true.action_dim
+    q, r, goal = cost.vectors(d, m)
+    for i in range(d):
+        p.q[i], p.goal[i] = q[i], goal[i]
+    for i in range(m):
+        p.r[i] = r[i]
+    p.algo, p.backtracking, p.fix_backtracking, p.n_alpha = algo, int(backtracking), int(fix_backtracking), n_alpha
+    p.w_is, p.alpha0, p.lr = w_is, alpha0, lr
+    return p
+
+
+def _launch_on(t, fn, *args):
+    with torch.cuda.device(t.device):
+        return fn(*args, _abi.current_stream_ptr())
+
+
+def env_rollout(p, U_old, x0, k=None, K=None, X_old=None, alpha=None, use_sim=False):
+    N, H, m = U_old.shape
+    d = x0.shape[1]
+    for name, t in (("U_old", U_old), ("x0", x0), ("k", k), ("K", K), ("X_old", X_old), ("alpha", alpha)):
+        _f32(t, name)
+    X = torch.empty(N, H + 1, d, device=x0.device)
+    U = torch.empty(N, H, m, device=x0.device)
+    c = torch.empty(N, device=x0.device)
+    rc = _launch_on(x0, _abi.lib().dlc_env_rollout_f32, ctypes.byref(p), int(use_sim), _abi.ptr(U_old), _abi.ptr(k),
+                    _abi.ptr(K), _abi.ptr(X_old), _abi.ptr(alpha), _abi.ptr(x0), _abi.ptr(X), _abi.ptr(U), _abi.ptr(c))
+    _abi.check(rc, "dlc_env_rollout_f32")
+    return X, U, c
+
+
+def igpc_rollout(p, U_old, k, K, X_old, alpha, x0):
+    N, H, m = U_old.shape
+    d = x0.shape[1]
+    for name, t in (("U_old", U_old), ("x0", x0), ("k", k), ("K", K), ("X_old", X_old), ("alpha", alpha)):
+        _f32(t, name)
+    X = torch.empty(N, H + 1, d, device=x0.device)
+    U = torch.empty(N, H, m, device=x0.device)
+    c = torch.empty(N, device=x0.device)
+    rc = _launch_on(x0, _abi.lib().dlc_igpc_rollout_f32, ctypes.byref(p), _abi.ptr(U_old), _abi.ptr(k), _abi.ptr(K),
+                    _abi.ptr(X_old), _abi.ptr(alpha), _abi.ptr(x0), _abi.ptr(X), _abi.ptr(U), _abi.ptr(c))
+    _abi.check(rc, "dlc_igpc_rollout_f32")
+    return X, U, c
+
+
+def linearize(p, X, U, use_sim=True):
+    N, H, m = U.shape
+    d = X.shape[2]
+    _f32(X, "X", (N, H + 1, d)); _f32(U, "U")
+    e = lambda *s: torch.empty(N, H, *s, device=X.device)
+    D, Fx, Fu, cx, cu, cxx, cuu = e(d), e(d, d), e(d, m), e(d), e(m), e(d, d), e(m, m)
+    rc = _launch_on(X, _abi.lib().dlc_linearize_f32, ctypes.byref(p), int(use_sim), _abi.ptr(X), _abi.ptr(U),
+                    _abi.ptr(D), _abi.ptr(Fx), _abi.ptr(Fu), _abi.ptr(cx), _abi.ptr(cu), _abi.ptr(cxx), _abi.ptr(cuu))
+    _abi.check(rc, "dlc_linearize_f32")
+    return D, (Fx, Fu), (cx, cu, cxx, cuu)
+
+
+def riccati_backward(F, C):
+    Fx, Fu = F
+    cx, cu, cxx, cuu = C
+    N, H, d, m = Fu.shape
+    for t in (Fx, Fu, cx, cu, cxx, cuu):
+        _f32(t, "F/C leaf")
+    k = torch.empty(N, H, m, device=Fx.device)
+    K = torch.empty(N, H, m, d, device=Fx.device)
+    status = torch.empty(N, dtype=torch.int32, device=Fx.device)
+    rc = _launch_on(Fx, _abi.lib().dlc_riccati_backward_f32, N, H, d, m, _abi.ptr(Fx), _abi.ptr(Fu), _abi.ptr(cx),
+                    _abi.ptr(cu), _abi.ptr(cxx), _abi.ptr(cuu), _abi.ptr(k), _abi.ptr(K), _abi.ptr(status))
+    _abi.check(rc, "dlc_riccati_backward_f32")
+    return k, K, status
+
+
+def plan(p, U, x0):
+    """``dlc_plan_f32``: the whole iLQR / iGPC / iLC loop.  Returns X, U, k, K, cost, alpha, status."""
+    N, H, m = U.shape
+    d = x0.shape[1]
+    _f32(U, "U"); _f32(x0, "x0", (N, d))
+    dev = x0.device
+    U_io = U.clone()
+    X = torch.empty(N, H + 1, d, device=dev)
+    k = torch.zeros(N, H, m, device=dev)
+    K = torch.zeros(N, H, m, d, device=dev)
+    c = torch.empty(N, device=dev)
+    alpha = torch.empty(N, device=dev)
+    status = torch.empty(N, dtype=torch.int32, device=dev)
+    nbytes = _abi.lib().dlc_plan_workspace_bytes(ctypes.byref(p))
+    ws = torch.empty(max(nbytes, 4) // 4, device=dev)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().dlc_plan_f32(ctypes.byref(p), _abi.ptr(U_io), _abi.ptr(x0), _abi.ptr(X), _abi.ptr(k),
+                                     _abi.ptr(K), _abi.ptr(c), _abi.ptr(alpha), _abi.ptr(status), _abi.ptr(ws),
+                                     ws.numel() * 4, _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_plan_f32")
+    return X, U_io, k, K, c, alpha, status

@@ -47,7 +47,7 @@ extern "C" {
 
 int32_t dlc_abi_version(void);
 /* sizeof() of the parameter structs as compiled, so a binding can verify its own layout:
- * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers (more below); 0 for unknown */
+ * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers, 3 DlcPlanParams; 0 for unknown */
 size_t dlc_sizeof(int32_t which);
 const char* dlc_last_error(void);
 /* 0 if the current CUDA device can run this library (compute capability 10.x) */
@@ -206,6 +206,89 @@ int32_t dlc_pid_f32(int64_t N, int32_t T, float decay,
                     float* P_io, float* I_io, float* D_io,              /* [N] PIDState */
                     float* u_out,                                       /* [T,N] actions */
                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * deluca/igpc: trajectory rollout, linearisation, Riccati backward pass and the iLQR / iGPC / iLC
+ * outer loops on the classic envs, batched over N independent trajectories.
+ *
+ *   dlc_env_rollout_f32        igpc.rollout           deluca/igpc/rollout.py:22-65
+ *   dlc_linearize_f32          compute_ders           deluca/igpc/rollout.py:68-99   (closed-form Jacobians
+ *                                                     of the env step instead of jax.jacfwd / jax.grad)
+ *   dlc_riccati_backward_f32   LQR                    deluca/igpc/lqr_solver.py:40-86 (host NumPy there)
+ *   dlc_igpc_rollout_f32       GPC_rollout            deluca/igpc/igpc.py:63-126 (+ counterfact_loss :22-60,
+ *                                                     hand adjoint instead of jit(grad))
+ *   dlc_plan_f32               iLQR / iGPC_closed / iLC_closed   ilqr.py:27-93, igpc.py:129-179, ilc.py:23-69
+ *                              the whole outer loop incl. backtracking stays on the device; the accept
+ *                              order of the reference's sequential `if cC <= c: break` is preserved.
+ * Envs: Pendulum (deluca/envs/classic/_pendulum.py:54-73, as written) and Cartpole
+ * (_cartpole.py:60-89 with the intent-fixing waiver SURVEY A-7).  Cost: c(x,u) = sum q_i (x_i-goal_i)^2
+ * + sum r_j u_j^2 (the reference ships no cost for this path).
+ * Layouts are the vmapped reference shapes: X[N,H+1,d], U[N,H,m], k[N,H,m], K[N,H,m,d].
+ * ------------------------------------------------------------------------------------ */
+#define DLC_ENV_PENDULUM 0 /* d = 3, m = 1; params: m, l, g, max_torque, dt */
+#define DLC_ENV_CARTPOLE 1 /* d = 4, m = 1; params: m, M, l, g, dt, offset */
+#define DLC_PLAN_MAXD 8
+#define DLC_PLAN_MAXM 4
+#define DLC_ALGO_ILQR 0
+#define DLC_ALGO_IGPC 1
+#define DLC_ALGO_ILC 2
+#define DLC_W_DE 0
+#define DLC_W_DEDE 1
+#define DLC_W_DELIN 2
+
+typedef struct DlcEnvSpec {
+  int32_t kind;        /* DLC_ENV_* */
+  float p[7];          /* static fields in the order listed above */
+} DlcEnvSpec;
+
+typedef struct DlcPlanParams {
+  int64_t N;           /* trajectories */
+  int32_t H;           /* env.H: steps per trajectory */
+  int32_t T;           /* outer iterations (dlc_plan_f32) */
+  DlcEnvSpec env_true; /* the env rolled out */
+  DlcEnvSpec env_sim;  /* the model that is linearised (== env_true for iLQR) */
+  float q[DLC_PLAN_MAXD], goal[DLC_PLAN_MAXD], r[DLC_PLAN_MAXM]; /* quadratic cost */
+  int32_t algo;        /* DLC_ALGO_* */
+  int32_t backtracking;
+  int32_t fix_backtracking; /* iLQR only: 0 = as written (candidates use alpha, ilqr.py:58-67), 1 = alphaC */
+  int32_t n_alpha;     /* candidates per iteration: 10 (iLQR, iLC), 6 (iGPC) */
+  int32_t w_is;        /* DLC_W_* (iGPC) */
+  float alpha0;        /* iLQR alpha = 0.5; iGPC / iLC ref_alpha = 1.0 */
+  float lr;            /* iGPC ref_lr */
+} DlcPlanParams;
+
+int32_t dlc_env_rollout_f32(const DlcPlanParams* p, int32_t use_sim_env,
+                            const float* U_old,  /* [N,H,m] */
+                            const float* k,      /* [N,H,m] or NULL: open loop (U = U_old) */
+                            const float* K,      /* [N,H,m,d] */
+                            const float* X_old,  /* [N,H+1,d] */
+                            const float* alpha,  /* [N] or NULL (= 1.0) */
+                            const float* x0,     /* [N,d] start states */
+                            float* X_out, float* U_out, float* cost_out /* [N] */, void* stream);
+
+int32_t dlc_linearize_f32(const DlcPlanParams* p, int32_t use_sim_env, const float* X, const float* U,
+                          float* D_out /*[N,H,d]*/, float* Fx_out /*[N,H,d,d]*/, float* Fu_out /*[N,H,d,m]*/,
+                          float* cx_out /*[N,H,d]*/, float* cu_out /*[N,H,m]*/, float* cxx_out /*[N,H,d,d]*/,
+                          float* cuu_out /*[N,H,m,m]*/, void* stream);
+
+int32_t dlc_riccati_backward_f32(int64_t N, int32_t H, int32_t d, int32_t m, const float* Fx, const float* Fu,
+                                 const float* cx, const float* cu, const float* cxx, const float* cuu,
+                                 float* k_out, float* K_out, int32_t* status_out /*[N] or NULL*/, void* stream);
+
+int32_t dlc_igpc_rollout_f32(const DlcPlanParams* p, const float* U_old, const float* k, const float* K,
+                             const float* X_old, const float* alpha /*[N]*/, const float* x0,
+                             float* X_out, float* U_out, float* cost_out, void* stream);
+
+size_t dlc_plan_workspace_bytes(const DlcPlanParams* p);
+int32_t dlc_plan_f32(const DlcPlanParams* p,
+                     float* U_io,        /* [N,H,m] initial controls in, final controls out */
+                     const float* x0,    /* [N,d] */
+                     float* X_out,       /* [N,H+1,d] */
+                     float* k_out, float* K_out, /* last gains ([N,H,m], [N,H,m,d]) */
+                     float* cost_out,    /* [N] */
+                     float* alpha_out,   /* [N] */
+                     int32_t* status_out,/* [N] or NULL */
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC

@@ -1,0 +1,161 @@
+"""Parity of the igpc kernels (rollout, linearise, Riccati, GPC_rollout, iLQR/iGPC/iLC loops) against
+the CPU oracle (B200 only).  The pendulum map is expansive, so closed-loop quantities are compared
+on short horizons (BASELINE.json: "short horizons for chaotic envs")."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import igpc as OG
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _envs(kind, H):
+    from deluca_b200.envs.classic import Cartpole, Pendulum, QuadCost
+    if kind == "pendulum":
+        o_true, o_sim = OG.Pendulum(H=H, m=1.1), OG.Pendulum(H=H)
+        d_true, d_sim = Pendulum.create(H=H, m=1.1), Pendulum.create(H=H)
+    else:
+        o_true, o_sim = OG.Cartpole(H=H, m=0.12), OG.Cartpole(H=H)
+        d_true, d_sim = Cartpole.create(H=H, m=0.12), Cartpole.create(H=H)
+    oc = OG.QuadCost(o_sim.goal_state, 1.0, 0.1)
+    dc = QuadCost(list(o_sim.goal_state), 1.0, 0.1)
+    return o_true, o_sim, oc, d_true, d_sim, dc
+
+
+def _start(o_env, N, seed=0):
+    rng = np.random.default_rng(seed)
+    return (o_env.init(N, np.float32) + 0.05 * rng.standard_normal((N, o_env.d))).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["pendulum", "cartpole"])
+def test_rollout_linearize_riccati(kind):
+    from deluca_b200.envs.classic import PendulumState
+    from deluca_b200.igpc.lqr_solver import LQR
+    from deluca_b200.igpc.rollout import compute_ders, rollout
+    H, N = 30, 70
+    o_true, o_sim, oc, d_true, d_sim, dc = _envs(kind, H)
+    rng = np.random.default_rng(1)
+    x0 = _start(o_sim, N)
+    U0 = (0.3 * rng.standard_normal((N, H, 1))).astype(np.float32)
+    Xo, Uo, co = OG.rollout(o_sim, oc, U0.astype(np.float64), x0=x0.astype(np.float64))
+    X, U, c = rollout(d_sim, dc, _t(U0), start_state=PendulumState(arr=_t(x0)))
+    np.testing.assert_allclose(_np(X), Xo, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(_np(c), co, rtol=1e-4)
+    # derivatives at the oracle's trajectory
+    D, F, C = compute_ders(d_sim, dc, _t(Xo), _t(Uo))
+    Do, Fo, Co = OG.compute_ders(o_sim, oc, Xo, Uo)
+    for got, want in zip(list(F) + list(C), list(Fo) + list(Co)):
+        np.testing.assert_allclose(_np(got), want, rtol=1e-4, atol=1e-5)
+    assert np.abs(_np(D)).max() < 1e-5
+    # Riccati backward pass on the oracle's (float32-rounded) derivatives
+    Fo32 = tuple(a.astype(np.float32) for a in Fo)
+    Co32 = tuple(a.astype(np.float32) for a in Co)
+    k, K = LQR(tuple(_t(a) for a in Fo32), tuple(_t(a) for a in Co32))
+    ko, Ko = OG.lqr_backward(tuple(a.astype(np.float64) for a in Fo32), tuple(a.astype(np.float64) for a in Co32))
+    np.testing.assert_allclose(_np(K), Ko, rtol=2e-3, atol=2e-4 * np.abs(Ko).max())
+    np.testing.assert_allclose(_np(k), ko, rtol=2e-3, atol=2e-4 * np.abs(ko).max())
+    # closed-loop rollout with those gains
+    Xc, Uc, cc = rollout(d_sim, dc, _t(Uo), _t(ko), _t(Ko), _t(Xo), alpha=0.5, start_state=PendulumState(arr=_t(x0)))
+    Xco, Uco, cco = OG.rollout(o_sim, oc, Uo, ko, Ko, Xo, 0.5, x0=x0.astype(np.float64))
+    np.testing.assert_allclose(_np(cc), cco, rtol=1e-3)
+
+
+@pytest.mark.parametrize("w_is", ["de", "dede", "delin"])
+def test_gpc_rollout_matches_oracle(w_is):
+    from deluca_b200.envs.classic import PendulumState
+    from deluca_b200.igpc.igpc import GPC_rollout
+    H, N = 25, 40
+    o_true, o_sim, oc, d_true, d_sim, dc = _envs("pendulum", H)
+    x0 = _start(o_true, N, 2)
+    U0 = np.zeros((N, H, 1))
+    X, U, c = OG.rollout(o_true, oc, U0, x0=x0.astype(np.float64))
+    D, F, C = OG.compute_ders(o_sim, oc, X, U)
+    k, K = OG.lqr_backward(F, C)
+    alpha = np.full(N, 0.3)
+    Xo, Uo, co = OG.gpc_rollout(o_true, o_sim, oc, U, k, K, X, D, F, alpha, w_is, 0.05, x0=x0.astype(np.float64))
+    Xg, Ug, cg = GPC_rollout(d_true, d_sim, dc, _t(U), _t(k), _t(K), _t(X), None, None, _t(alpha), w_is, 0.05,
+                             start_state=PendulumState(arr=_t(x0)))
+    np.testing.assert_allclose(_np(cg), co, rtol=2e-3)
+    np.testing.assert_allclose(_np(Ug), Uo, rtol=1e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("kind,fix", [("pendulum", False), ("pendulum", True), ("cartpole", True)])
+def test_ilqr_loop_matches_oracle(kind, fix):
+    from deluca_b200.envs.classic import PendulumState
+    from deluca_b200.igpc.ilqr import iLQR
+    H, N, T = 20, 64, 4
+    o_true, o_sim, oc, d_true, d_sim, dc = _envs(kind, H)
+    x0 = _start(o_sim, N, 3)
+    U0 = np.zeros((N, H, 1), np.float32)
+    Xo, Uo, ko, Ko, co, ao = OG.ilqr(o_sim, oc, U0.astype(np.float64), T, x0=x0.astype(np.float64),
+                                     fix_backtracking=fix)
+    X, U, k, K, c = iLQR(d_sim, dc, _t(U0), T, start_state=PendulumState(arr=_t(x0)), fix_backtracking=fix)
+    _, _, c0 = OG.rollout(o_sim, oc, U0.astype(np.float64), x0=x0.astype(np.float64))
+    c = _np(c)
+    assert np.isfinite(c).all() and (c <= c0 * (1 + 1e-5)).all()
+    # accept/reject decisions can flip on ties; require agreement on the bulk of the batch
+    rel = np.abs(c - co) / np.maximum(np.abs(co), 1e-6)
+    assert np.median(rel) < 1e-3 and (rel < 2e-2).mean() > 0.9
+
+
+@pytest.mark.parametrize("algo", ["igpc", "ilc"])
+def test_igpc_and_ilc_loops(algo):
+    from deluca_b200.envs.classic import PendulumState
+    from deluca_b200.igpc.igpc import iGPC_closed
+    from deluca_b200.igpc.ilc import iLC_closed
+    H, N, T = 20, 64, 3
+    o_true, o_sim, oc, d_true, d_sim, dc = _envs("pendulum", H)
+    x0 = _start(o_true, N, 4)
+    U0 = np.zeros((N, H, 1), np.float32)
+    st = PendulumState(arr=_t(x0))
+    if algo == "igpc":
+        co = OG.igpc_closed(o_true, o_sim, oc, U0.astype(np.float64), T, lr=0.01, x0=x0.astype(np.float64))[4]
+        c = iGPC_closed(d_true, d_sim, dc, _t(U0), T, lr=0.01, start_state=st)[4]
+    else:
+        co = OG.ilc_closed(o_true, o_sim, oc, U0.astype(np.float64), T, x0=x0.astype(np.float64))[4]
+        c = iLC_closed(d_true, d_sim, dc, _t(U0), T, start_state=st)[4]
+    c = _np(c)
+    _, _, c0 = OG.rollout(o_true, oc, U0.astype(np.float64), x0=x0.astype(np.float64))
+    assert np.isfinite(c).all() and (c <= c0 * (1 + 1e-5)).all()
+    rel = np.abs(c - co) / np.maximum(np.abs(co), 1e-6)
+    assert np.median(rel) < 1e-3 and (rel < 2e-2).mean() > 0.9
+
+
+def test_single_step_env_calls():
+    from deluca_b200.envs.classic import Cartpole, Pendulum
+    for Env, O in ((Pendulum, OG.Pendulum), (Cartpole, OG.Cartpole)):
+        env, o = Env.create(), O()
+        state, _ = env.init()
+        x = o.init(1, np.float64)
+        for t in range(5):
+            u = np.array([[0.3 * (t - 2)]])
+            state, obs = env(state, _t(u[0]))
+            x = o.step(x, u)
+            np.testing.assert_allclose(_np(obs), x[0], rtol=1e-5, atol=1e-6)
+        assert state.h == 5
+
+
+def test_config3_size_runs():
+    """BASELINE config 3: 4096 trajectories x T=200 x 20 iterations (pendulum): finite, monotone."""
+    from deluca_b200.envs.classic import Pendulum, PendulumState, QuadCost
+    from deluca_b200.igpc.ilqr import iLQR
+    from deluca_b200.igpc.rollout import rollout
+    N, H = 4096, 200
+    env = Pendulum.create(H=H)
+    cost = QuadCost([0.0, -1.0, 0.0], 1.0, 0.1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x0 = torch.tensor([0.0, 1.0, 0.0], device="cuda") + 0.05 * torch.randn(N, 3, device="cuda", generator=g)
+    U0 = torch.zeros(N, H, 1, device="cuda")
+    st = PendulumState(arr=x0)
+    c0 = rollout(env, cost, U0, start_state=st)[2]
+    c = iLQR(env, cost, U0, 20, start_state=st, fix_backtracking=True)[4]
+    assert bool(torch.isfinite(c).all()) and bool((c <= c0 * (1 + 1e-5)).all()) and bool((c < c0).any())

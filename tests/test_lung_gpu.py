@@ -1,0 +1,126 @@
+"""Parity of the fused ventilator episode kernel (PID + Expiratory + Balloon/DelayLung) and the lung
+mirrors against the CPU oracle (B200 only).  Tolerance: 1e-4 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lung as OL
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _close(a, b, scale=None):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    scale = scale if scale is not None else max(np.abs(b).mean(), 1e-3)
+    assert np.abs(a - b).max() <= RTOL * np.maximum(np.abs(b), scale).max(), np.abs(a - b).max()
+    assert (np.abs(a - b) <= RTOL * np.maximum(np.abs(b), scale)).all()
+
+
+@pytest.mark.parametrize("sim,T", [("balloon", 29), ("balloon", 400), ("delay", 29), ("delay", 1000)])
+def test_run_controller_scan_matches_oracle(sim, T):
+    from deluca_b200.lung.controllers import PID
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung, DelayLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    rng = np.random.default_rng(0)
+    N = 300
+    K = rng.uniform(0, 5, (N, 3)).astype(np.float32)
+    pip = rng.choice([10, 15, 20, 25, 30, 35], N).astype(np.float32)
+    ref = OL.run_controller_scan(K, pip, 5.0, T=T, sim=sim, dtype=np.float32)
+    env = (BalloonLung if sim == "balloon" else DelayLung).create()
+    wave = BreathWaveform.create(pip=torch.tensor(pip), peep=5.0)
+    res = run_controller_scan(PID.create(params=torch.tensor(K)), T=T, env=env, waveform=wave, init_controller=True)
+    for k in ("timestamp", "pressure", "flow", "u_in", "u_out", "target"):
+        got = res["timeseries"][k]
+        assert got.shape == (N, T)
+        _close(got.T, ref["timeseries"][k])
+    b = res["final"]["buffers"]
+    _close(b["volume_io"], ref["env_state"]["volume"])
+    _close(b["pressure_io"], ref["env_state"]["pressure"])
+    _close(b["time_io"], ref["env_state"]["time"])
+    _close(b["pid_i_io"], ref["controller_state"]["i"])
+    assert (b["pid_steps_io"].cpu().numpy() == T).all()
+    if sim == "delay":
+        _close(b["in_history_io"], ref["env_state"]["in_history"], 1.0)
+        _close(b["out_history_io"], ref["env_state"]["out_history"], 1.0)
+    assert int(res["status"].sum()) == 0
+
+
+def test_waveform_known_answers_on_device():
+    """deluca/tests/lung/core_test.py:55-62 through the kernel's interpolator (ctrl-only step:
+    p = target - pressure with pressure = 0)."""
+    from deluca_b200.lung import _launch
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung
+    ts = [0.0, 0.5, 1.0, 1.25, 1.5, 3.0, 2.0, 2.5]
+    want = [35.0, 35.0, 35.0, 20.0, 5.0, 35.0, 15.0, 25.0]   # last two: the fp32 ramp (SURVEY A-9)
+    b, out = _launch.launch(BalloonLung.create(), BreathWaveform.create(), len(ts), 1, "ctrl_only", "cuda",
+                            obs=dict(predicted_pressure=0.0, time=torch.tensor(ts)))
+    assert b["pid_p_io"].cpu().tolist() == want
+    # is_in at 0.5 / 1.0 / 1.5 (core_test.py:43-47): u_out = 0 while inhaling
+    assert out["u_out"][0, [1, 2, 4]].cpu().tolist() == [0.0, 0.0, 1.0]
+    w = BreathWaveform.create()
+    assert [w.at(t) for t in ts] == want and w.is_in(1.0) and not w.is_in(1.5)
+
+
+def test_single_step_env_and_controller_calls_compose_to_the_fused_episode():
+    """Env.__call__ / Controller.__call__ one step at a time == the fused scan."""
+    from deluca_b200.lung.controllers import PID, Expiratory
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    N, T = 5, 12
+    K = torch.tensor([[3.0, 4.0, 0.0]]).expand(N, 3).contiguous()
+    wave = BreathWaveform.create(pip=torch.tensor([10.0, 15.0, 20.0, 25.0, 35.0]), peep=5.0)
+    env = BalloonLung.create(waveform=wave)
+    pid, exp = PID.create(params=K), Expiratory.create(waveform=wave)
+    fusedr = run_controller_scan(pid, T=T, env=env, waveform=wave, init_controller=True)
+    state, obs = env.reset(N)
+    cs, es = pid.init(wave), exp.init()
+    us, ps = [], []
+    for _ in range(T):
+        ps.append(obs.predicted_pressure)
+        cs, u_in = pid(cs, obs)
+        es, u_out = exp(es, obs)
+        state, obs = env(state, (u_in, u_out))
+        us.append(u_in)
+    assert torch.equal(torch.stack(us, 1), fusedr["timeseries"]["u_in"])
+    assert torch.equal(torch.stack(ps, 1), fusedr["timeseries"]["pressure"])
+
+
+def test_generic_pid_agent_matches_oracle():
+    from deluca_b200.agents import PID
+    rng = np.random.default_rng(1)
+    N, T = 64, 50
+    kp, ki, kd = (rng.uniform(0, 3, N).astype(np.float32) for _ in range(3))
+    err = rng.standard_normal((T, N)).astype(np.float32)
+    agent = PID.create(K_P=torch.tensor(kp).cuda(), K_I=torch.tensor(ki).cuda(), K_D=torch.tensor(kd).cuda())
+    st = agent.init()
+    ost = dict(P=np.zeros(N, np.float32), I=np.zeros(N, np.float32), D=np.zeros(N, np.float32))
+    for t in range(T):
+        st, u = agent(st, torch.tensor(err[t]).cuda())
+        uo = OL.generic_pid_call(ost, kp, ki, kd, err[t])
+        _close(u, uo, 1.0)
+
+
+def test_million_breaths_properties():
+    """BASELINE config 4 size (2^20 breaths, T = 29): identical breaths give identical series, u_in
+    stays inside the clamp, u_out follows is_in, and the emitted pressure is the previous step's state."""
+    from deluca_b200.lung.controllers import PID
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    N, T = 1 << 20, 29
+    g = torch.Generator().manual_seed(0)
+    K = (5 * torch.rand(N // 2, 3, generator=g)).repeat(2, 1)
+    pip = torch.tensor([10.0, 15, 20, 25, 30, 35])[torch.randint(0, 6, (N // 2,), generator=g)].repeat(2)
+    res = run_controller_scan(PID.create(params=K), T=T, env=BalloonLung.create(),
+                              waveform=BreathWaveform.create(pip=pip, peep=5.0), init_controller=True)
+    ts = res["timeseries"]
+    assert ts["u_in"].shape == (N, T)
+    assert torch.equal(ts["u_in"][: N // 2], ts["u_in"][N // 2:])
+    assert float(ts["u_in"].min()) >= 0.0 and float(ts["u_in"].max()) <= 100.0
+    assert float(ts["u_out"].abs().max()) == 0.0           # 29 steps of 0.03 s stay inside the inhale
+    assert float(ts["pressure"][:, 0].abs().max()) == 0.0
+    assert int(res["status"].sum()) == 0

@@ -1,0 +1,84 @@
+"""The reference-shaped Python interface (Obj/Env/Agent mirrors, apg drivers) on the CUDA path (B200)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lds as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def test_stateful_lds_gpc_loop_matches_oracle():
+    """The colab-style loop of SURVEY S2 (config 1: single env, d=10, m=3, H=3, HH=10)."""
+    from deluca_b200.agents import GPC
+    from deluca_b200.envs import LDS
+    from deluca_b200.fused import gaussian_disturbance
+    rng = np.random.default_rng(0)
+    d, m, T = 10, 3, 1000
+    A, B, _ = O.lds_default_params(rng, 1, d, m)
+    env = LDS()
+    env.init(d_in=m, d_hidden=d, d_out=d, A=A[0], B=B[0], C=np.eye(d), key=5)
+    agent = GPC(env.A, env.B, H=3, HH=10, lr_scale=1e-4)
+    K = agent.K.cpu().numpy()[None]
+    np.testing.assert_allclose(K, O.lqr_gain(A, B), rtol=1e-4, atol=1e-6)
+    W = gaussian_disturbance(1, T, d, seed=5).cpu().numpy()
+    ref = O.rollout_lds(A, B, K, np.zeros((1, d), np.float32), W, "gpc", H=3, HH=10, lr_scale=1e-4, dtype=np.float64)
+    x = env.x
+    costs = []
+    for t in range(T):
+        u = agent(x)
+        costs.append(float((x * x).sum() + (u * u).sum()))
+        x = env(u)
+    rel = np.abs(np.array(costs) - ref["costs"][:, 0]) / np.maximum(ref["costs"][:, 0], 1e-2 * ref["costs"].mean())
+    assert rel.max() < 1e-4
+    assert agent.t == T and env.t == T
+
+
+def test_apg_parallel_rollouts_equals_stepping_and_oracle():
+    from deluca_b200.agents import GPC, LQR
+    from deluca_b200.agents._gpc import quad_loss
+    from deluca_b200.envs import LDS
+    from deluca_b200.fused import gaussian_disturbance
+    from deluca_b200.training.apg import apg_parallel_rollouts
+    rng = np.random.default_rng(1)
+    N, d, m, T = 48, 10, 3, 60
+    A, B, _ = O.lds_default_params(rng, N, d, m)
+    env = LDS()
+    env.init(d_in=m, d_hidden=d, d_out=d, A=A, B=B, C=np.eye(d), key=9)
+    agent = GPC(env.A, env.B, H=3, HH=10, lr_scale=1e-4)
+    st, obs = env.reset(N)
+    ro, env_final = apg_parallel_rollouts(env, st, obs, agent, agent.init(N), T, quad_loss)
+    assert ro.losses.shape == (N, T) and ro.actions.shape == (N, T, m)
+    W = gaussian_disturbance(N, T, d, seed=9).cpu().numpy()
+    ref = O.rollout_lds(A, B, agent.K.cpu().numpy(), np.zeros((N, d), np.float32), W, "gpc", H=3, HH=10,
+                        lr_scale=1e-4, dtype=np.float64)
+    rel = np.abs(ro.losses.T.cpu().numpy() - ref["costs"]) / np.maximum(ref["costs"], 1e-2 * ref["costs"].mean())
+    assert rel.max() < 1e-4
+    # step-by-step through Env.step / Agent.step reproduces the fused rollout
+    s, a = env.reset(N)[0], agent.init(N)
+    for t in range(T):
+        a, u = agent.step(a, s.x)
+        s, _ = env.step(s, u)
+    assert torch.allclose(s.x, env_final.x, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(a.M, ro.agent_states.M, rtol=1e-4, atol=1e-7)
+    lq = LQR(env.A, env.B)
+    ro2, _ = apg_parallel_rollouts(env, st, obs, lq, None, T, quad_loss)
+    assert float(ro2.losses.mean()) > 0
+
+
+def test_obj_contract_and_errors():
+    import dataclasses
+    from deluca_b200.agents._gpc import GPCState
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.training.apg import apg_parallel_rollouts
+    w = BreathWaveform.create()
+    with pytest.raises(dataclasses.FrozenInstanceError):
+        w.pip = 3
+    s = GPCState(M=torch.zeros(1), noise_history=torch.zeros(2), state=torch.zeros(3), action=torch.zeros(4))
+    assert [t.numel() for t in s.flatten()] == [1, 2, 3, 4]
+    with pytest.raises(NotImplementedError):
+        apg_parallel_rollouts(object(), None, None, None, None, 1, None)

@@ -126,29 +126,33 @@ def measure_fp32_peak(torch, dev):
 
 
 def cpu_baseline(wl, seconds_target=12.0):
-    """The oracle's multi-threaded torch-CPU restatement on a bounded sample of the workload."""
+    """The oracle's C restatement (oracle/lds_c.c, OpenMP over envs, every host thread) timed on a
+    bounded sample of the workload: same step, same distributions, fewer envs and steps."""
     import numpy as np
-    import torch
-    from oracle.lds_torch import gpc_rollout_torch
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    Nc, Tc = 8192, 16
+    from oracle.lds_c import gpc_rollout_c, max_threads
+    cores = max_threads()
     d, m = wl["d"], wl["m"]
+    Nc = 2048 * cores
     rng = np.random.default_rng(0)
-    A = torch.diag_embed(torch.tensor(rng.uniform(0.9, 0.95, (Nc, d)), dtype=torch.float32))
-    B = torch.tensor(rng.standard_normal((Nc, d, m)), dtype=torch.float32)
-    K = torch.tensor(0.05 * rng.standard_normal((Nc, m, d)), dtype=torch.float32)
-    x0 = torch.zeros(Nc, d)
-    run = lambda T: gpc_rollout_torch(A, B, K, x0, torch.tensor(0.5 * rng.standard_normal((T, Nc, d)),
-                                                                dtype=torch.float32),
-                                      H=wl["H"], HH=wl["HH"], lr_scale=LR_SCALE)
-    run(4)
-    t0 = time.perf_counter(); run(Tc); dt = time.perf_counter() - t0
-    Tc2 = int(max(Tc, min(2000, Tc * seconds_target / max(dt, 1e-3))))
-    t0 = time.perf_counter(); run(Tc2); dt = time.perf_counter() - t0
-    return {"value": Nc * Tc2 / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{Nc} envs x {Tc2} steps of the same LDS+GPC step (oracle/lds_torch.py, torch CPU fp32, "
-                      f"{cores} threads), {dt:.1f} s"}
+    A = np.zeros((Nc, d, d), np.float32)
+    A[:, np.arange(d), np.arange(d)] = rng.uniform(0.9, 0.95, (Nc, d))
+    B = rng.standard_normal((Nc, d, m)).astype(np.float32)
+    K = (0.05 * rng.standard_normal((Nc, m, d))).astype(np.float32)
+    x0 = np.zeros((Nc, d), np.float32)
+
+    def run(T):
+        W = (0.5 * rng.standard_normal((T, Nc, d))).astype(np.float32)
+        t0 = time.perf_counter()
+        gpc_rollout_c(A, B, K, x0, W, wl["H"], wl["HH"], LR_SCALE, True, np.float32, cores)
+        return time.perf_counter() - t0
+
+    run(8)
+    dt = run(32)
+    Tc = int(max(32, min(1000, 32 * seconds_target / max(dt, 1e-3))))
+    dt = run(Tc)
+    return {"value": Nc * Tc / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{Nc} envs x {Tc} steps of the same LDS+GPC step (oracle/lds_c.c: scalar C, OpenMP over envs, "
+                      f"fp32, {cores} threads), {dt:.1f} s"}
 
 
 def run_reference(args, wl, rank, world):
@@ -178,6 +182,7 @@ def main():
     ap.add_argument("--disturbance", default="hbm", choices=["hbm", "kernel"],
                     help="hbm: W[T,N,d] resident in HBM before timing; kernel: Philox drawn in-register")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="DlcLdsParams.kernel_variant (0 = auto)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
@@ -206,7 +211,8 @@ def main():
     A, B, K, x0 = make_problem(torch, wl, dev, rank)
     use_hbm_w = args.disturbance == "hbm"
     W = gaussian_disturbance(N, T, d, seed=SEED, env_offset=env_offset, std=W_STD, device=dev) if use_hbm_w else None
-    kw = dict(policy="gpc", H=H, HH=HH, lr_scale=LR_SCALE, decay=True, seed=SEED, env_offset=env_offset, w_std=W_STD)
+    kw = dict(policy="gpc", H=H, HH=HH, lr_scale=LR_SCALE, decay=True, seed=SEED, env_offset=env_offset, w_std=W_STD,
+              kernel_variant=args.variant)
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
 
     from deluca_b200.sharding import local_stats, reduce_stats, summarize
@@ -223,12 +229,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 0)):
-        step()
-    # ---- timed region: K steps; kernel time on the launch stream via CUDA events
+    # the clock sampler (nvidia-smi -lms) is started BEFORE the warm-up: its first query on a fresh box
+    # takes long enough to stall a kernel, which must not land inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 0)):
+        step()
+    # ---- timed region: K steps; kernel time on the launch stream via CUDA events
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync()
     t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -244,7 +252,8 @@ def main():
     sync()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_all0.elapsed_time(t_all1)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / max(args.steps, 1)
+    kern_each = [a.elapsed_time(b) for a, b in kev]
+    kern_ms = sum(kern_each) / max(args.steps, 1)
     tm = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -300,6 +309,7 @@ def main():
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak if fp32_peak else None, "traffic": None,
                          "kernel": "lds_split_kernel", "kernel_ms": kern_ms,
+                         "kernel_ms_each": [round(v, 3) for v in kern_each],
                          "flops_per_env_step": F, "bytes_per_env_step": Bts,
                          "peak_source": "measured live: dlc_microbench_f32 (FFMA %.1f, FFMA2 %.1f TFLOP/s); "
                                         "MEASURED_PEAKS.json has no FP32 non-tensor peak" % (fp32["ffma"], fp32["ffma2"]),

@@ -32,7 +32,9 @@ struct LdsArgs {
 // >= D are zero padding) and keeps, in REGISTERS, everything indexed by them:
 //     rows S_q of A and B, columns S_q of K and of every M[i], and x/y/lambda restricted to S_q.
 // The disturbance-history ring (columns S_q only) is the one structure indexed dynamically; it
-// lives in shared memory as [slot][k][thread] (bank = thread: conflict-free).
+// lives in shared memory as [slot][k][thread] (bank = thread: conflict-free) and is MIRRORED: every
+// entry is stored at physical slots i and i + P (2P - 1 slots), so logical index k is always at head + k with no
+// wrap test and every access of a step is base-register + immediate.
 // Vectors that a lane needs in full are exchanged with xor-shuffles and kept in LANE-RELATIVE
 // order: chunk c of a gathered vector holds the coordinates of lane q^c, so every register index
 // is a compile-time constant.  A's rows are stored with their columns permuted the same way.
@@ -52,12 +54,13 @@ template <int D, int M, int H, int HH, int POLICY, int L, int TPB>
 struct SplitLayout {
   static constexpr int DL = (D + L - 1) / L;
   static constexpr int P = H + HH;
-  static constexpr int kFloats = POLICY == DLC_POLICY_GPC ? P * DL : 0;  // per thread
+  static constexpr int kFloats = POLICY == DLC_POLICY_GPC ? (2 * P - 1) * DL : 0;  // per thread (mirrored ring)
   static constexpr size_t kSmemBytes = (size_t)kFloats * TPB * sizeof(float);
 };
 
 template <int D, int M, int H, int HH, int POLICY, int L, int TPB, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
+__global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 8 > 255 ? 255 : (65536 / (TPB * MINB)) / 8 * 8)
+    lds_split_kernel(const LdsArgs a) {
   using Lay = SplitLayout<D, M, H, HH, POLICY, L, TPB>;
   constexpr int DL = Lay::DL, DF = DL * L, P = Lay::P;
   constexpr bool GPC = POLICY == DLC_POLICY_GPC;
@@ -108,7 +111,11 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
     for (int s = 0; s < P; ++s)
 #pragma unroll
       for (int k = 0; k < DL; ++k)
-        sH[(s * DL + k) * TPB] = (q * DL + k < D) ? a.hist_io[n * (P * D) + s * D + q * DL + k] : 0.f;
+      {
+        const float v = (q * DL + k < D) ? a.hist_io[n * (P * D) + s * D + q * DL + k] : 0.f;
+        sH[(s * DL + k) * TPB] = v;
+        if (s + P < 2 * P - 1) sH[((s + P) * DL + k) * TPB] = v;
+      }
     // ax = A * (previous observed state).  The reference recomputes it every step (_gpc.py:155);
     // here the env step, which forms the same product, hands it to the next step.
     float xf[DF];
@@ -162,11 +169,8 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
   float wnext[DL];
   if (p.T > 0) load_w(0, wnext);
 
-  auto slot = [&](int k) {  // physical base of logical (post-shift) ring index k
-    int s = head + k;
-    s -= (s >= P) ? P : 0;
-    return sH + s * (DL * TPB);
-  };
+  const float* ring = sH;   // = sH + head * DL * TPB: logical index k lives at ring + k * DL * TPB
+  auto slot = [&](int k) { return ring + k * (DL * TPB); };
 
   for (int t = 0; t < p.T; ++t) {
     float w_t[DL];
@@ -178,7 +182,11 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
     //      red[0..M)            K x                                   _lqr.py:72
     //      red[M..2M)           mw  = sum_i M[i] hist[HH+i]           _gpc.py:171-183
     //      red[2M + h*M + c]    v_h = sum_i M[i] w[h+i], h < H-1      _gpc.py:112-116
-    constexpr int NR = GPC ? M * (H + 1) : M;
+    // For short histories all M-window products are formed up front and share one batched
+    // reduction; for long ones (H > 4) that would keep M*(H+1) partial sums live, so v_h is formed
+    // inside the recursion instead (BATCH_V = false) and only K x and mw are reduced here.
+    constexpr bool BATCH_V = H <= 4;
+    constexpr int NR = GPC ? (BATCH_V ? M * (H + 1) : 2 * M) : M;
     float red[NR];
 #pragma unroll
     for (int c = 0; c < M; ++c) {
@@ -187,28 +195,31 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
       for (int k = 0; k < DL; ++k) s = fmaf(Kc[c][k], x[k], s);
       red[c] = s;
     }
+    auto window_dot = [&](int base, float acc[M]) {   // partial sum_i M[i] w[base+i] over own coordinates
+#pragma unroll
+      for (int c = 0; c < M; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float* w = slot(base + i);
+#pragma unroll
+        for (int k = 0; k < DL; ++k) {
+          const float wk = w[k * TPB];
+#pragma unroll
+          for (int c = 0; c < M; ++c) acc[c] = fmaf(Mr[i][c][k], wk, acc[c]);
+        }
+      }
+    };
     if (GPC) {
       // After this step's ring shift every stored noise drops one logical index, so the action
       // window hist[HH..HH+H) of the old ring is window [HH-1..HH+H-1) of the new one -- the final
       // window of policy_loss: mw serves both.  No M-window product depends on the simulated state
-      // y nor on the noise appended below (their indices are <= P-2), so all are formed up front.
+      // y nor on the noise appended below (their indices are <= P-2).
       head = (head + 1 == P) ? 0 : head + 1;  // roll(-1)               _gpc.py:156-157
+      ring = sH + head * (DL * TPB);
 #pragma unroll
-      for (int hh = 0; hh < H; ++hh) {        // hh = 0: final/action window; hh >= 1: v_{hh-1}
-        const int base = hh == 0 ? HH - 1 : hh - 1;
+      for (int hh = 0; hh < (BATCH_V ? H : 1); ++hh) {   // hh = 0: final/action window; hh >= 1: v_{hh-1}
         float acc[M];
-#pragma unroll
-        for (int c = 0; c < M; ++c) acc[c] = 0.f;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-          const float* w = slot(base + i);
-#pragma unroll
-          for (int k = 0; k < DL; ++k) {
-            const float wk = w[k * TPB];
-#pragma unroll
-            for (int c = 0; c < M; ++c) acc[c] = fmaf(Mr[i][c][k], wk, acc[c]);
-          }
-        }
+        window_dot(hh == 0 ? HH - 1 : hh - 1, acc);
 #pragma unroll
         for (int c = 0; c < M; ++c) red[M + hh * M + c] = acc[c];
       }
@@ -222,14 +233,19 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
     if (GPC) {
       // ---- noise = x - A x_prev - B u ; append                   _gpc.py:155-157
       {
-        float* wn = slot(P - 1);
+        // newest entry: physical slot head + P - 1 and its mirror head - 1 (the copy at 2P - 1 that
+        // head == 0 would need is never read: that entry stays reachable at slot P - 1 until it expires)
+        float* wn = sH + (head + P - 1) * (DL * TPB);
+        float* wm = wn - P * (DL * TPB);
 #pragma unroll
         for (int i = 0; i < DL; ++i) {
           float s = 0.f;
 #pragma unroll
           for (int c = 0; c < M; ++c)
             s = fmaf(Br[i][c], p.noise_uses_prev_action ? uprev[c] : u[c], s);
-          wn[i * TPB] = (x[i] - ax[i]) - s;
+          const float nz = (x[i] - ax[i]) - s;
+          wn[i * TPB] = nz;
+          if (head != 0) wm[i * TPB] = nz;
         }
       }
       // ---- policy_loss forward: y <- A y + B(-K y + v_h) + w[h+H]      _gpc.py:118-124
@@ -240,8 +256,14 @@ __global__ void __launch_bounds__(TPB, MINB) lds_split_kernel(const LdsArgs a) {
       for (int h = 0; h < H - 1; ++h) {
         const float* wh = slot(h + H);
         float v[M];
+        if (BATCH_V) {
 #pragma unroll
-        for (int c = 0; c < M; ++c) v[c] = red[2 * M + h * M + c];
+          for (int c = 0; c < M; ++c) v[c] = red[(BATCH_V ? 2 * M + h * M : 0) + c];
+        } else {
+          window_dot(h, v);
+#pragma unroll
+          for (int c = 0; c < M; ++c) v[c] = group_allreduce<L>(v[c]);
+        }
         float yn[DL];
         if (h == 0) {  // y == 0: A y and K y vanish
 #pragma unroll
@@ -680,12 +702,11 @@ __global__ void gaussian_disturbance_kernel(float* W, int64_t N, int T, int d, u
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int D, int M, int H, int HH, int POLICY, int L, int MINB>
+template <int D, int M, int H, int HH, int POLICY, int L, int TPB, int MINB>
 static int32_t launch_split(const LdsArgs& a, cudaStream_t st) {
-  constexpr int TPB = 128;
   using Lay = SplitLayout<D, M, H, HH, POLICY, L, TPB>;
   auto kern = lds_split_kernel<D, M, H, HH, POLICY, L, TPB, MINB>;
-  static_assert(Lay::kSmemBytes * MINB <= 227 * 1024, "ring does not fit shared memory");
+  static_assert((Lay::kSmemBytes + 1024) * MINB <= 228 * 1024, "ring does not fit shared memory");
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Lay::kSmemBytes);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_split)");
@@ -695,27 +716,75 @@ static int32_t launch_split(const LdsArgs& a, cudaStream_t st) {
   return cuda_status(cudaGetLastError(), "lds_split_kernel launch");
 }
 
-// (d, m, H, HH, lanes per env, min blocks per SM for GPC)
+// Launch shapes of the GPC kernel: (threads per CTA, CTAs per SM) -> warps per SM.  Rollouts are
+// equal-length jobs, so the grid runs in ceil(warps / (SMs * warps_per_SM)) rounds and a partially
+// filled last round is pure loss (65,536 envs at L = 2 are 27.7 warps per SM: 12 warps/SM leaves the
+// third round 31 % full, 10 warps/SM fills three rounds to 92 %, 14 warps/SM two rounds to 99 %).
+// The launcher picks the shape with the best round efficiency x measured per-shape throughput.
+struct LaunchShape { int tpb, minb; float rel_throughput; };
+// rel_throughput: steady-state throughput relative to shape 3, measured on B200 (profiles/r01_*):
+// register spills cost far more than occupancy buys, so the no-spill shapes win.
+static constexpr LaunchShape kShapes[] = {
+    {128, 3, 0.48f},  // kernel_variant 2: 12 warps/SM, 168 regs (spills)
+    {64, 5, 0.82f},   // kernel_variant 3: 10 warps/SM, 200 regs (few spills)
+    {64, 7, 0.35f},   // kernel_variant 4: 14 warps/SM, 144 regs (spills)
+    {128, 2, 1.00f},  // kernel_variant 5:  8 warps/SM, 255 regs (no spills)
+    {32, 7, 0.93f},   // kernel_variant 6:  7 warps/SM, 255 regs, one-warp CTAs
+    {32, 8, 1.00f},   // kernel_variant 7:  8 warps/SM, 255 regs, one-warp CTAs
+};
+static constexpr int kNumShapes = sizeof(kShapes) / sizeof(kShapes[0]);
+
+static int pick_shape(const LdsArgs& a, int L, int sms) {
+  const int v = a.p.kernel_variant;
+  if (v >= 2 && v < 2 + kNumShapes) return v - 2;
+  const double warps = (double)((a.p.N * L + 31) / 32);
+  int best = 3;
+  double best_score = -1.0;
+  for (int i = 0; i < kNumShapes; ++i) {
+    const double cap = (double)sms * (kShapes[i].tpb / 32) * kShapes[i].minb;
+    const double rounds = ceil(warps / cap);
+    const double score = warps / (rounds * cap) * kShapes[i].rel_throughput;
+    if (score > best_score + 1e-9) { best_score = score; best = i; }
+  }
+  return best;
+}
+
+template <int D, int M, int H, int HH, int L>
+static int32_t launch_gpc(const LdsArgs& a, cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  switch (pick_shape(a, L, sms)) {
+    case 0: return launch_split<D, M, H, HH, DLC_POLICY_GPC, L, 128, 3>(a, st);
+    case 1: return launch_split<D, M, H, HH, DLC_POLICY_GPC, L, 64, 5>(a, st);
+    case 2: return launch_split<D, M, H, HH, DLC_POLICY_GPC, L, 64, 7>(a, st);
+    case 4: return launch_split<D, M, H, HH, DLC_POLICY_GPC, L, 32, 7>(a, st);
+    case 5: return launch_split<D, M, H, HH, DLC_POLICY_GPC, L, 32, 8>(a, st);
+    default: return launch_split<D, M, H, HH, DLC_POLICY_GPC, L, 128, 2>(a, st);
+  }
+}
+
+// (d, m, H, HH, lanes per env)
 #define DLC_SPLIT_SHAPES(X) \
-  X(10, 3, 3, 10, 2, 3)     \
-  X(10, 3, 3, 2, 2, 3)      \
-  X(10, 3, 10, 10, 4, 3)    \
-  X(4, 1, 3, 2, 1, 4)       \
-  X(4, 2, 5, 7, 1, 3)
+  X(10, 3, 3, 10, 2)        \
+  X(10, 3, 3, 2, 2)         \
+  X(10, 3, 10, 10, 4)       \
+  X(4, 1, 3, 2, 1)          \
+  X(4, 2, 5, 7, 1)
 
 static bool try_split(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
   if (p.kernel_variant == 1 || p.policy == DLC_POLICY_BPC || p.policy == DLC_POLICY_OPEN ||
       p.mode != DLC_MODE_CLOSED_LOOP)
     return false;
-#define X(D_, M_, H_, HH_, L_, MINB_)                                                 \
+#define X(D_, M_, H_, HH_, L_)                                                        \
   if (p.d == D_ && p.m == M_) {                                                       \
     if (p.policy == DLC_POLICY_LQR) {                                                 \
-      *rc = launch_split<D_, M_, 1, 1, DLC_POLICY_LQR, L_, 4>(a, st);                 \
+      *rc = launch_split<D_, M_, 1, 1, DLC_POLICY_LQR, L_, 128, 4>(a, st);            \
       return true;                                                                    \
     }                                                                                 \
     if (p.H == H_ && p.HH == HH_) {                                                   \
-      *rc = launch_split<D_, M_, H_, HH_, DLC_POLICY_GPC, L_, MINB_>(a, st);          \
+      *rc = launch_gpc<D_, M_, H_, HH_, L_>(a, st);                                   \
       return true;                                                                    \
     }                                                                                 \
   }

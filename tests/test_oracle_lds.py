@@ -163,3 +163,20 @@ def test_gaussian_disturbance_moments_and_sharding():
     # a shard of envs / a later start draws the same numbers
     W2 = P.gaussian_disturbance(7, np.arange(100, 164), 10, 20, 10, 0.5)
     np.testing.assert_array_equal(W[10:30, 100:164], W2)
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/lds_c.c (the CPU-baseline port) against the line-by-line NumPy restatement."""
+    from oracle.lds_c import gpc_rollout_c
+    rng = np.random.default_rng(7)
+    for (d, m, H, HH) in ((10, 3, 3, 10), (10, 3, 10, 10), (4, 2, 5, 7)):
+        N, T = 12, 80
+        A, B, _ = O.lds_default_params(rng, N, d, m)
+        K = O.lqr_gain(A, B)
+        x0 = (0.1 * rng.standard_normal((N, d))).astype(np.float32)
+        W = (0.5 * rng.standard_normal((T, N, d))).astype(np.float32)
+        for dt, tol in ((np.float64, 1e-12), (np.float32, 2e-5)):
+            r = O.rollout_lds(A, B, K, x0, W, "gpc", H=H, HH=HH, lr_scale=1e-4, dtype=dt)
+            c, x = gpc_rollout_c(A, B, K, x0, W, H, HH, 1e-4, True, dt)
+            np.testing.assert_allclose(c, r["costs"], rtol=tol, atol=tol)
+            np.testing.assert_allclose(x, r["x_final"], rtol=tol, atol=tol)

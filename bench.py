@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -147,20 +147,23 @@ def cpu_baseline(wl, seconds_target=12.0):
         return time.perf_counter() - t0
 
     run(8)
-    dt = run(32)
-    Tc = int(max(32, min(1000, 32 * seconds_target / max(dt, 1e-3))))
-    dt = run(Tc)
-    return {"value": Nc * Tc / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{Nc} envs x {Tc} steps of the same LDS+GPC step (oracle/lds_c.c: scalar C, OpenMP over envs, "
-                      f"fp32, {cores} threads), {dt:.1f} s"}
+    Tc = 500
+    dt1 = run(Tc)
+    reps = int(max(1, min(40, round(seconds_target / max(dt1, 1e-3)))))
+    dt = sum(run(Tc) for _ in range(reps))
+    return {"value": Nc * Tc * reps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "seconds": dt, "reps": reps,
+            "sample": f"{reps} x ({Nc} envs x {Tc} steps) of the same LDS+GPC step (oracle/lds_c.c: scalar C, OpenMP "
+                      f"over envs, fp32, {cores} threads), {dt:.1f} s"}
 
 
 def run_reference(args, wl, rank, world):
     if rank != 0:
         return
-    cb = cpu_baseline(wl, seconds_target=10.0 * max(1, args.steps))
+    cb = cpu_baseline(wl, seconds_target=min(60.0, 8.0 * max(1, args.steps)))
     line = {"impl": "reference", "metric": "LDS+GPC env-steps/sec", "value": cb["value"], "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * cb["seconds"] / cb["reps"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "note": "reference semantics restated on the CPU (JAX is not "
                        "installable in this image, SURVEY F2); bounded sample, see cpu_baseline.sample"},
@@ -308,7 +311,7 @@ def main():
                        "parallelism": f"env-sharded x{world}"},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak if fp32_peak else None, "traffic": None,
-                         "kernel": "lds_split_kernel", "kernel_ms": kern_ms,
+                         "kernel": "lds_f2_kernel" if (H <= 4 and args.variant in (0, 8, 9)) else "lds_split_kernel", "kernel_ms": kern_ms,
                          "kernel_ms_each": [round(v, 3) for v in kern_each],
                          "flops_per_env_step": F, "bytes_per_env_step": Bts,
                          "peak_source": "measured live: dlc_microbench_f32 (FFMA %.1f, FFMA2 %.1f TFLOP/s); "

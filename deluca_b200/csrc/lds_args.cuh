@@ -1,0 +1,22 @@
+// Argument block shared by the LDS rollout kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dlc {
+
+struct LdsArgs {
+  DlcLdsParams p;
+  const float *A, *B, *K, *W, *U_in;
+  float *x_io, *M_io, *hist_io, *xprev_io, *uprev_io, *eps_io;
+  const float* eps_new;
+  float* cost_out;
+  double* cost_sum_out;
+  float *x_out, *u_out;
+  int32_t* status_out;
+  float* ws;
+};
+
+// packed-FFMA2 lane-split GPC kernel (lds_rollout_f2.cu).  Returns false if (d,m,H,HH) has no instantiation.
+bool launch_gpc_f2(const LdsArgs& a, cudaStream_t st, int32_t* rc);
+
+}  // namespace dlc

@@ -10,20 +10,11 @@
 //       a global-memory workspace laid out [element][env] (coalesced).  Correct for every shape
 //       the reference accepts (including the dynamic_slice clamping of HH < H-1); not tuned.
 #include "common.cuh"
+#include "lds_args.cuh"
 
 namespace dlc {
 
-struct LdsArgs {
-  DlcLdsParams p;
-  const float *A, *B, *K, *W, *U_in;
-  float *x_io, *M_io, *hist_io, *xprev_io, *uprev_io, *eps_io;
-  const float* eps_new;
-  float* cost_out;
-  double* cost_sum_out;
-  float *x_out, *u_out;
-  int32_t* status_out;
-  float* ws;
-};
+// LdsArgs lives in lds_args.cuh (shared with lds_rollout_f2.cu)
 
 // ------------------------------------------------------------------------------------------
 // lane-split kernel: L adjacent lanes of a warp own one env.
@@ -784,6 +775,10 @@ static bool try_split(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
       return true;                                                                    \
     }                                                                                 \
     if (p.H == H_ && p.HH == HH_) {                                                   \
+      /* packed-FFMA2 kernel: default for short histories (6-10 % faster on B200), forced by 8 / 9 */ \
+      if (((p.kernel_variant == 0 && H_ <= 4) || p.kernel_variant == 8 || p.kernel_variant == 9) && \
+          launch_gpc_f2(a, st, rc))                                                   \
+        return true;                                                                  \
       *rc = launch_gpc<D_, M_, H_, HH_, L_>(a, st);                                   \
       return true;                                                                    \
     }                                                                                 \

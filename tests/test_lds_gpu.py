@@ -48,6 +48,7 @@ def _check(res, ref, T):
 
 @pytest.mark.parametrize("d,m,H,HH,variant", [
     (10, 3, 3, 10, 0), (10, 3, 3, 10, 1), (10, 3, 3, 2, 0), (10, 3, 10, 10, 0), (4, 1, 3, 2, 0),
+    (10, 3, 3, 10, 5), (10, 3, 3, 10, 8), (10, 3, 3, 10, 9), (10, 3, 3, 2, 8), (10, 3, 10, 10, 8), (10, 3, 10, 10, 9),
     (4, 2, 5, 7, 0), (4, 2, 5, 7, 1), (6, 2, 4, 5, 0), (3, 1, 1, 1, 0), (5, 2, 4, 2, 0)])
 @pytest.mark.parametrize("dense", [False, True])
 def test_gpc_matches_oracle(d, m, H, HH, variant, dense):

@@ -41,11 +41,18 @@ def sim_params(env, p):
     p.env_flow = float(env.flow)
 
 
-def launch(env, waveform, N, T, mode, dev, *, K=None, env_state=None, obs=None, pid_state=None, exp_state=None,
+def launch(env, waveform, N, T, mode, dev, **kw):
+    """prepare() + one kernel call.  Returns (dict of updated leaves, dict of [T,N] series)."""
+    p, b, out = prepare(env, waveform, N, T, mode, dev, **kw)
+    fused.lung_rollout(p, b)
+    return b, out
+
+
+def prepare(env, waveform, N, T, mode, dev, *, K=None, env_state=None, obs=None, pid_state=None, exp_state=None,
            actions=None, pid_decay=DEFAULT_DT / (DEFAULT_DT + 0.5), run_dt=DEFAULT_DT, series=True):
-    """One kernel call.  ``env_state`` / ``obs`` / ``pid_state`` / ``exp_state`` are dicts of leaves
-    (scalars or [N] tensors); missing pieces get neutral values.  Returns (dict of updated leaves,
-    dict of [T,N] series)."""
+    """Pack one kernel call.  ``env_state`` / ``obs`` / ``pid_state`` / ``exp_state`` are dicts of
+    leaves (scalars or [N] tensors); missing pieces get neutral values.  Returns (params, buffers,
+    dict of [T,N] series tensors)."""
     p = _abi.DlcLungParams()
     p.N, p.T, p.mode = N, T, MODE[mode]
     waveform = waveform or BreathWaveform.create()
@@ -94,5 +101,4 @@ def launch(env, waveform, N, T, mode, dev, *, K=None, env_state=None, obs=None, 
             out[k] = torch.empty(T, N, device=dev)
             b[k + "_out"] = out[k]
     b["status_out"] = torch.empty(N, dtype=torch.int32, device=dev)
-    fused.lung_rollout(p, b)
-    return b, out
+    return p, b, out

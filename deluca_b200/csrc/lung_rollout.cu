@@ -11,18 +11,46 @@ struct LungArgs {
   DlcLungBuffers b;
 };
 
-// BreathWaveform.at: jnp.interp(t, xp, fp, period) on the host-built table (lung/core.py:54-60)
-__device__ __forceinline__ float waveform_at(const DlcLungParams& p, const float* kf, float t) {
-  const float x = fmodf(t, p.period);  // t >= 0 on this path, so fmod == jnp.mod
+// t mod period for t >= 0, bit-identical to fmodf (IEEE remainders are exactly representable):
+// q = floor(t / period) with a correctly rounded divide can only be one too large (when t / period
+// rounds up to an integer); the FMA residual t - q*period is then exact (a small negative multiple of
+// the operands' common granularity) and adding the period back is exact as well.
+__device__ __forceinline__ float fmod_pos(float t, float period) {
+  if (!(t >= 0.f) || !(t < 1e30f)) return fmodf(t, period);
+  const float q = floorf(__fdiv_rn(t, period));
+  float r = fmaf(-q, period, t);
+  if (r < 0.f) r += period;
+  return r;
+}
+
+// BreathWaveform.at: jnp.interp(t, xp, fp, period) on the host-built table (lung/core.py:54-60).
+// `x` is t mod period (fmodf: exact, and t >= 0 on this path, so it equals jnp.mod).  NK > 0 is the
+// compile-time knot count (7 for the default 5-knot waveform): the search is unrolled and the
+// per-env ordinates stay in registers; NK == 0 reads the count from the parameter block.
+template <int NK>
+__device__ __forceinline__ float interp_knots(const DlcLungParams& p, const float* kf, float x) {
+  if (NK > 0) {
+    float x0 = p.kx[0], x1 = p.kx[1], f0 = kf[0], f1 = kf[1];
+#pragma unroll
+    for (int k = 1; k < NK - 1; ++k) {  // searchsorted(side='right'), clipped to [1, NK-1]
+      const bool adv = p.kx[k] <= x;
+      x0 = adv ? p.kx[k] : x0;
+      x1 = adv ? p.kx[k + 1] : x1;
+      f0 = adv ? kf[k] : f0;
+      f1 = adv ? kf[k + 1] : f1;
+    }
+    const float dx = x1 - x0;
+    return dx == 0.f ? f0 : f0 + __fdiv_rn(x - x0, dx) * (f1 - f0);
+  }
   int i = 1;
 #pragma unroll 1
-  for (int k = 1; k < p.nk - 1; ++k) i += (p.kx[k] <= x) ? 1 : 0;  // searchsorted(side='right'), clipped
+  for (int k = 1; k < p.nk - 1; ++k) i += (p.kx[k] <= x) ? 1 : 0;
   const float x0 = p.kx[i - 1], dx = p.kx[i] - x0;
   const float f0 = kf[i - 1], df = kf[i] - f0;
   return dx == 0.f ? f0 : f0 + __fdiv_rn(x - x0, dx) * df;
 }
 
-template <int SIM>
+template <int SIM, int NK>
 __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   const DlcLungParams& p = a.p;
   const DlcLungBuffers& b = a.b;
@@ -51,7 +79,7 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
       hout[k] = b.out_history_io[n * p.delay + k];
     }
   }
-  bool bad = false;
+  bool bad = false, ran_env = false;
   const bool run_ctrl = p.mode != DLC_LUNG_MODE_ENV_ONLY, run_env = p.mode != DLC_LUNG_MODE_CTRL_ONLY;
 
   for (int t = 0; t < p.T; ++t) {
@@ -59,7 +87,8 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
     float u_in, u_out;
     if (run_ctrl) {
     // ---- PID                                                     controllers/_pid.py:77-102
-    const float tgt = waveform_at(p, kf, obs_t);
+    const float xo = fmod_pos(obs_t, p.period);                      // shared by PID (at) and Expiratory (is_in)
+    const float tgt = interp_knots<NK>(p, kf, xo);
     const float err = tgt - obs_p;
     const float np_ = err;
     const float ni = ci + p.pid_decay * (err - ci);
@@ -71,7 +100,7 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
     ctime = obs_t;
     ++csteps;
     // ---- Expiratory                                              controllers/_expiratory.py:35-45
-    u_out = (fmodf(obs_t, p.period) <= p.xp_in) ? 0.f : 1.f;
+    u_out = (xo <= p.xp_in) ? 0.f : 1.f;
     edt = fmaxf(p.default_dt, obs_t - (isinf(etime) ? 0.f : etime));
     etime = obs_t;
     ++esteps;
@@ -88,13 +117,14 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
       if (pressure > p.peep_valve) flow -= (u_out > 0.f ? 1.0f : 0.0f) * 0.05f * pressure;
       volume += flow * p.dt;
       if (p.leak) volume += p.leak_coef * (p.min_volume - volume);
-      const float r = powf(__fdiv_rn(3.0f * volume, 12.566370614359172f), 0.33333333333333333f);
+      // (3V/4pi)^(1/3): cbrtf differs from the reference's pow(x, float32(1/3)) by < 1 ulp
+      const float r = cbrtf(__fdiv_rn(3.0f * volume, 12.566370614359172f));
       const float q = __fdiv_rn(p.r0, r);
       const float q2 = q * q;
       pressure = p.P0 + __fdiv_rn(p.PC * (1.0f - q2 * q2 * q2), p.r0_sq * r);
       steps = time + 1.0f;                                          // sic (:135)
-      time = time + p.dt;
-      target = waveform_at(p, kf, time);
+      time = time + p.dt;                                           // target = waveform.at(time): only the
+      ran_env = true;                                               // last one survives, formed after the loop
       obs_p = pressure;
       obs_t = time;
     } else {                                                        // envs/_delay_lung.py:75-133
@@ -106,7 +136,7 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
       obs_t = time;
       const float flow = __fdiv_rn(pressure, p.d_R);
       volume = fmaxf(volume + flow * p.dt, p.min_volume);
-      const float r = powf(__fdiv_rn(3.0f * volume, 12.566370614359172f), 0.33333333333333333f);
+      const float r = cbrtf(__fdiv_rn(3.0f * volume, 12.566370614359172f));
       const float q = __fdiv_rn(p.r0, r);
       const float q2 = q * q;
       const float lung_p = __fdiv_rn(p.d_C * (1.0f - q2 * q2 * q2), p.r0_sq * r);
@@ -118,7 +148,7 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
       if (peep != 0.f) pipe *= 0.995f;
       steps = time + 1.0f;
       time = time + p.dt;
-      target = waveform_at(p, kf, time);
+      ran_env = true;
     }
     // ---- emitted series                                          run_controller.py:128-141
     const float ts = p.dt * steps - p.run_dt;
@@ -128,10 +158,11 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
     if (b.u_out_out) b.u_out_out[o] = u_out;
     if (b.pressure_out) b.pressure_out[o] = pr_emit;
     if (b.flow_out) b.flow_out[o] = p.env_flow;
-    if (b.target_out) b.target_out[o] = waveform_at(p, kf, ts);     // waveform.at(timestamps), :207
+    if (b.target_out) b.target_out[o] = interp_knots<NK>(p, kf, fmod_pos(ts, p.period));   // waveform.at(timestamps), :207
     bad |= !isfinite(pressure);
   }
 
+  if (ran_env) target = interp_knots<NK>(p, kf, fmod_pos(time, p.period));   // state.target (:140)
   b.steps_io[n] = steps; b.time_io[n] = time; b.volume_io[n] = volume; b.pressure_io[n] = pressure;
   b.target_io[n] = target;
   b.obs_pressure_io[n] = obs_p; b.obs_time_io[n] = obs_t;
@@ -177,8 +208,13 @@ extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLun
   a.b = *b;
   const unsigned grid = (unsigned)((p->N + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->sim == DLC_SIM_BALLOON) lung_pid_kernel<DLC_SIM_BALLOON><<<grid, 128, 0, st>>>(a);
-  else lung_pid_kernel<DLC_SIM_DELAY><<<grid, 128, 0, st>>>(a);
+  if (p->sim == DLC_SIM_BALLOON) {
+    if (p->nk == 7) lung_pid_kernel<DLC_SIM_BALLOON, 7><<<grid, 128, 0, st>>>(a);
+    else lung_pid_kernel<DLC_SIM_BALLOON, 0><<<grid, 128, 0, st>>>(a);
+  } else {
+    if (p->nk == 7) lung_pid_kernel<DLC_SIM_DELAY, 7><<<grid, 128, 0, st>>>(a);
+    else lung_pid_kernel<DLC_SIM_DELAY, 0><<<grid, 128, 0, st>>>(a);
+  }
   return cuda_status(cudaGetLastError(), "lung_pid_kernel launch");
 }
 

@@ -240,3 +240,37 @@ def plan(p, U, x0):
                                      ws.numel() * 4, _abi.current_stream_ptr())
     _abi.check(rc, "dlc_plan_f32")
     return X, U_io, k, K, c, alpha, status
+
+
+# ------------------------------------------------------------------------------------------ shared dynamics
+def lds_shared_pack(A, B, K):
+    """``dlc_lds_shared_pack_f32``: [A - B K ; -K] as TF32 hi/lo in the tensor-core staging layout."""
+    d, m = B.shape
+    _f32(A, "A", (d, d)); _f32(B, "B", (d, m)); _f32(K, "K", (m, d))
+    n = _abi.lib().dlc_lds_shared_packed_floats(d, m)
+    if n == 0:
+        raise ValueError("shared-dynamics tensor-core path needs d % 16 == 0, 16 <= d <= 256, d + m <= 384")
+    G = torch.empty(n, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = _abi.lib().dlc_lds_shared_pack_f32(_abi.ptr(A), _abi.ptr(B), _abi.ptr(K), d, m, _abi.ptr(G),
+                                                _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lds_shared_pack_f32")
+    return G
+
+
+def lds_shared_lqr_rollout(G_packed, x, T, m, W=None, keep_costs=True):
+    """``dlc_lds_shared_lqr_rollout_f32``: T steps of shared-dynamics LDS + LQR for N envs on tcgen05.
+    Returns costs[T,N] (or None), cost_sum[N] (fp64), x_final[N,d], status[N]."""
+    _f32(x, "x")
+    N, d = x.shape
+    _f32(W, "W", (T, N, d))
+    x_io = x.clone()
+    costs = torch.empty(T, N, device=x.device) if keep_costs else None
+    cost_sum = torch.empty(N, dtype=torch.float64, device=x.device)
+    status = torch.empty(N, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _abi.lib().dlc_lds_shared_lqr_rollout_f32(N, T, d, m, _abi.ptr(G_packed), _abi.ptr(W), _abi.ptr(x_io),
+                                                       _abi.ptr(costs), _abi.ptr(cost_sum), _abi.ptr(status),
+                                                       _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lds_shared_lqr_rollout_f32")
+    return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, status=status)

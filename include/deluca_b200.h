@@ -293,6 +293,25 @@ int32_t dlc_plan_f32(const DlcPlanParams* p,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Shared-dynamics LDS + LQR rollout on the tensor cores (tcgen05, TF32 x3 split, fp32 accumulate in TMEM).
+ * When A, B, K are shared by all envs (jax.vmap in_axes=None) the batch is the N dimension of a GEMM:
+ *     [x_{t+1} - w_t ; u_t] = [A - B K ; -K] X_t,   cost_t = x_t'x_t + u_t'u_t
+ * Replaces LDS.__call__ (deluca/envs/_lds.py:102-111) + LQR.__call__ (deluca/agents/_lqr.py:62-72) +
+ * quad_loss (deluca/agents/_gpc.py:29-40) under lax.scan x vmap.  Shapes: d % 16 == 0, 16 <= d <= 256,
+ * d + m <= 384.  dlc_lds_shared_pack_f32 forms [A - B K ; -K] (fp64 accumulate), splits it into TF32
+ * hi + lo and lays it out in the kernel's staging order; G_packed holds dlc_lds_shared_packed_floats(d, m)
+ * floats and can be reused across rollouts.
+ * ------------------------------------------------------------------------------------ */
+size_t dlc_lds_shared_packed_floats(int32_t d, int32_t m);
+int32_t dlc_lds_shared_pack_f32(const float* A /*[d,d]*/, const float* B /*[d,m]*/, const float* K /*[m,d]*/,
+                                int32_t d, int32_t m, float* G_packed, void* stream);
+int32_t dlc_lds_shared_lqr_rollout_f32(int64_t N, int32_t T, int32_t d, int32_t m, const float* G_packed,
+                                       const float* W /*[T,N,d] or NULL (no disturbance)*/,
+                                       float* x_io /*[N,d]*/, float* cost_out /*[T,N] or NULL*/,
+                                       double* cost_sum_out /*[N] or NULL*/, int32_t* status_out /*[N] or NULL*/,
+                                       void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC
  * kernels is not in MEASURED_PEAKS.json, so bench.py measures it with these.
  *   which: 0 FFMA (72 FMA/thread/iter)   1 packed fma.f32x2 (72 FMA/thread/iter)

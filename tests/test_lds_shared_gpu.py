@@ -1,0 +1,67 @@
+"""Parity of the shared-dynamics tcgen05 (3xTF32) LDS + LQR rollout against the float64 oracle (B200)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lds as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(d, m, seed=0):
+    rng = np.random.default_rng(seed)
+    Q = np.linalg.qr(rng.standard_normal((d, d)))[0]
+    A = (Q * rng.uniform(0.7, 0.95, d)) @ Q.T                      # spectral radius < 1
+    B = rng.standard_normal((d, m)) / np.sqrt(d)
+    K = O.lqr_gain(A[None], B[None], dtype=np.float64)[0]
+    return A.astype(np.float32), B.astype(np.float32), K.astype(np.float32)
+
+
+@pytest.mark.parametrize("d,m,N,T", [(256, 64, 130, 12), (64, 16, 64, 30), (128, 32, 200, 20), (48, 8, 70, 25),
+                                     (256, 64, 1, 3)])
+def test_shared_lqr_rollout_matches_oracle(d, m, N, T):
+    from deluca_b200.fused import lds_shared_lqr_rollout, lds_shared_pack
+    A, B, K = _system(d, m, seed=d + m)
+    rng = np.random.default_rng(1)
+    x0 = rng.standard_normal((N, d)).astype(np.float32)
+    W = (0.5 * rng.standard_normal((T, N, d))).astype(np.float32)
+    rep = lambda a: np.broadcast_to(a, (N,) + a.shape)
+    ref = O.rollout_lds(rep(A), rep(B), rep(K), x0, W, "lqr", dtype=np.float64, keep_x=False)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+    G = lds_shared_pack(t(A), t(B), t(K))
+    res = lds_shared_lqr_rollout(G, t(x0), T, m, W=t(W))
+    costs = res.costs.cpu().numpy()
+    rel = np.abs(costs - ref["costs"]) / np.maximum(np.abs(ref["costs"]), 1e-2 * np.abs(ref["costs"]).mean())
+    assert np.isfinite(costs).all() and rel.max() < 1e-4, rel.max()
+    xs = np.abs(ref["x_final"]).mean()
+    relx = np.abs(res.x.cpu().numpy() - ref["x_final"]) / np.maximum(np.abs(ref["x_final"]), xs)
+    assert relx.max() < 1e-4, relx.max()
+    np.testing.assert_allclose(res.cost_sum.cpu().numpy(), ref["costs"].sum(0), rtol=1e-4)
+    assert int(res.status.sum()) == 0
+
+
+def test_shared_path_agrees_with_the_per_env_cuda_core_kernel():
+    """Same rollout through dlc_lds_rollout_f32 (fp32 CUDA cores, runtime-dims kernel) and through
+    the tensor-core path: two independent implementations of the same reference lines."""
+    from deluca_b200.fused import lds_rollout, lds_shared_lqr_rollout, lds_shared_pack
+    d, m, N, T = 64, 16, 96, 40
+    A, B, K = _system(d, m, seed=3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x0 = torch.randn(N, d, device="cuda", generator=g)
+    W = 0.5 * torch.randn(T, N, d, device="cuda", generator=g)
+    t = lambda a: torch.as_tensor(a).cuda()
+    a = lds_rollout(t(A), t(B), t(K), x0, T, policy="lqr", W=W)
+    b = lds_shared_lqr_rollout(lds_shared_pack(t(A), t(B), t(K)), x0, T, m, W=W)
+    assert torch.allclose(a.costs, b.costs, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(a.x, b.x, rtol=1e-4, atol=1e-4)
+
+
+def test_shared_rejects_unsupported_shapes():
+    from deluca_b200 import _abi
+    from deluca_b200.fused import lds_shared_pack
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    with pytest.raises(ValueError):
+        lds_shared_pack(z(10, 10), z(10, 3), z(3, 10))      # d % 16 != 0
+    assert _abi.lib().dlc_lds_shared_packed_floats(512, 64) > 0   # size helper does not validate the range
+    with pytest.raises(_abi.DlcError):
+        lds_shared_pack(z(512, 512), z(512, 64), z(64, 512))

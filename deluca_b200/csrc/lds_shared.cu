@@ -5,7 +5,8 @@
 //     [     u_t       ] = [   -K    ]  X_t          G = [(d+m) x d],  X_t = [d x N_envs]
 //
 // One CTA owns NT = 64 envs for all T steps.  X_t lives in shared memory as the B operand (K-major,
-// no swizzle) split into TF32 hi + lo parts; G is streamed from L2 in k-chunks (pre-packed by
+// no swizzle; each 4-coordinate block is padded by 16 bytes so that the epilogue's stores -- one
+// coordinate per lane -- hit 32 distinct banks) split into TF32 hi + lo parts; G is streamed from L2 in k-chunks (pre-packed by
 // dlc_lds_shared_pack_f32 in exactly the shared-memory layout, also hi + lo); three tcgen05.mma passes
 // (hi*hi + hi*lo + lo*hi, "3xTF32") give fp32-level accuracy with fp32 accumulation in TMEM.  The
 // epilogue reads the accumulators back with tcgen05.ld, adds the disturbance, forms the per-env cost
@@ -14,18 +15,25 @@
 //
 // Replaces LDS.__call__ (deluca/envs/_lds.py:102-111) + LQR.__call__ (deluca/agents/_lqr.py:62-72) +
 // quad_loss (deluca/agents/_gpc.py:29-40) under lax.scan x vmap for shared (in_axes=None) dynamics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dlc {
 
 constexpr int kNT = 64;    // envs per CTA = MMA N
-constexpr int kKC = 16;    // k-chunk of G staged per pipeline stage (two K=8 MMA steps)
+constexpr int kKC = 8;     // k-chunk of G staged per pipeline stage (one K=8 MMA step)
+constexpr int kNS = 4;     // pipeline stages (bulk copies in flight)
 constexpr int kThreads = 128;
 
 struct SharedArgs {
   int64_t N;
   int T, d, m, MB;           // MB = 128-row blocks of G (rows padded with zeros)
-  const float* Gp;           // packed G: [d/kKC chunks][2 (hi, lo)][kKC/4][MB*128][4]
+  int RP;                    // rows of G actually packed: d + m rounded up to 8 (the last 128-row MMA block reads past
+                             // them; those accumulator rows are never used)
+  int dbg;                   // profiling switches (DLC_SHARED_DBG): 1 = hi*hi pass only, 2 = never refill G stages, 4 = skip epilogue stores
+  int C;                     // CTAs per cluster sharing each G chunk through TMA multicast (1, 2 or 4)
+  const float* Gp;           // packed G: [d/kKC chunks][2 (hi, lo)][kKC/4][RP][4]
   const float* W;            // [T,N,d] or NULL
   float* x_io;               // [N,d]
   float* cost_out;           // [T,N] or NULL
@@ -51,6 +59,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+// X operand (K-major, no swizzle): [k/4 blocks][kNT envs][4 coordinates], each block padded by 4 floats
+constexpr uint32_t kXBlock = kNT * 4 + 4;   // floats per 4-coordinate block (LBO = 1040 B: banks rotate by 4 per block)
+__device__ __forceinline__ uint32_t xoff(int n, int k) {
+  return (uint32_t)(k >> 2) * kXBlock + (uint32_t)n * 4u + (uint32_t)(k & 3);
+}
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -63,12 +81,23 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
                :: "r"(smem_u32(bar)) : "memory");
 }
+// the same arrival on the barrier at this offset in every CTA of `mask` (stage reuse is cluster-wide)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
 // bounded wait: a lost arrival traps (kernel error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     uint32_t ok;
     asm volatile(
@@ -88,9 +117,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // ------------------------------------------------------------------------------------ packing
 // G = [A - B K ; -K ; 0] -> TF32 hi/lo, laid out per k-chunk exactly as the kernel's stage buffer.
-__global__ void shared_pack_kernel(const float* A, const float* B, const float* K, int d, int m, int MB,
+__global__ void shared_pack_kernel(const float* A, const float* B, const float* K, int d, int m, int rows,
                                    float* Gp) {
-  const int rows = MB * 128;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * d) return;
   const int r = idx / d, k = idx % d;
@@ -112,156 +140,258 @@ __global__ void shared_pack_kernel(const float* A, const float* B, const float* 
 }
 
 // ------------------------------------------------------------------------------------ rollout
+// tcgen05.ld of one accumulator row (this thread's TMEM lane), 64 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_row64(uint32_t taddr, uint32_t (&v)[kNT]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+        "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+        "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+        "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// Column sums over the 32 lanes of a warp of a per-lane 64-vector (transposed butterfly: 62 shuffles).
+// On return lane L holds the sums of columns 2L and 2L+1 in q[0], q[1].
+__device__ __forceinline__ void warp_colsum64(float (&q)[kNT], int lane) {
+#pragma unroll
+  for (int off = 16, len = 32; off >= 1; off >>= 1, len >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < len; ++i) {
+      const float lo = q[i], hi = q[i + len];
+      const float keep = up ? hi : lo, send = up ? lo : hi;
+      q[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+template <int MB>
 __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const SharedArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int d = a.d, MB = a.MB, rows = MB * 128;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rows = a.RP;
+  const uint32_t part_floats = (uint32_t)(kKC / 4) * rows * 4;          // one hi (or lo) part of a stage
+  const uint32_t part_bytes = part_floats * 4, stage_bytes = 2 * part_bytes;
+  const int d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t env0 = (int64_t)blockIdx.x * kNT;
+  const int nvalid = (int)((a.N - env0) < kNT ? (a.N - env0 > 0 ? a.N - env0 : 0) : kNT);
   // shared-memory carve-up
-  float* sXhi = reinterpret_cast<float*>(smem);                         // [d/4][kNT][4]
-  float* sXlo = sXhi + (size_t)kNT * d;
-  const size_t part_floats = (size_t)(kKC / 4) * rows * 4;              // one hi (or lo) part of a stage
-  float* sG0 = sXlo + (size_t)kNT * d;                                  // stage s: sG0 + s * 2 * part_floats
-  const size_t stage_area = 4 * part_floats > (size_t)kNT * 129 + 31 ? 4 * part_floats : ((size_t)kNT * 129 + 31) / 32 * 32;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG0 + stage_area);       // [0,1] stage free, [2] accumulators ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* scratch = sG0;                                                  // epilogue reduction scratch (stage 0)
+  float* sXhi = reinterpret_cast<float*>(smem);                         // [d/4][kNT (+1 pad)][4]
+  float* sXlo = sXhi + (size_t)(d / 4) * kXBlock;
+  float* sG0 = sXlo + (size_t)(d / 4) * kXBlock;                                  // stage s at sG0 + s * 2 * part_floats
+  float* sSum = sG0 + 2 * kNS * part_floats;                            // [2 (x, u)][4 warps][kNT] column sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 2 * 4 * kNT);     // full[kNS], empty[kNS], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 1);
+  uint64_t *bar_full = bars, *bar_empty = bars + kNS, *bar_accum = bars + 2 * kNS;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
                  :: "r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
+  const int C = a.C;
+  uint32_t crank = 0;
+  if (C > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
+    for (int i = 0; i < kNS; ++i) mbar_init(&bars[i], 1);                // full: own producer's arrive.expect_tx
+    for (int i = 0; i < kNS; ++i) mbar_init(&bars[kNS + i], C);          // empty: one commit per CTA of the cluster
+    mbar_init(&bars[2 * kNS], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // X_0 -> operand buffer (hi/lo split), thread = (env n = tid / 2, half of the coordinates)
-  for (int idx = tid; idx < kNT * d; idx += kThreads) {
-    const int n = idx / d, k = idx % d;
-    const int64_t e = env0 + n;
-    const float x = e < a.N ? a.x_io[e * d + k] : 0.f;
-    float hi, lo;
-    split_tf32(x, hi, lo);
-    const size_t o = ((size_t)(k / 4) * kNT + n) * 4 + (k % 4);
-    sXhi[o] = hi;
-    sXlo[o] = lo;
-  }
+  // X_0 -> operand buffer (hi/lo split); |x_0|^2 per env through the column-sum scratch
   float xsq = 0.f;  // thread n < kNT: |x_t|^2 of env n
-  if (tid < kNT) {
-    const int64_t e = env0 + tid;
-    if (e < a.N)
-      for (int k = 0; k < d; ++k) { const float x = a.x_io[e * d + k]; xsq = fmaf(x, x, xsq); }
+  {
+    float part = 0.f;  // this thread's share of env (tid / 2): coordinates [ (tid&1)*d/2, ... )
+    const int n = tid >> 1, k0 = (tid & 1) * (d / 2);
+    const bool ok = n < nvalid;
+    const float* gx = a.x_io + (env0 + n) * d;
+    for (int k = k0; k < k0 + d / 2; ++k) {
+      const float x = ok ? gx[k] : 0.f;
+      float hi, lo;
+      split_tf32(x, hi, lo);
+      const uint32_t o = xoff(n, k);
+      sXhi[o] = hi;
+      sXlo[o] = lo;
+      part = fmaf(x, x, part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    if ((tid & 1) == 0) sSum[n] = part;
   }
   double csum = 0.0;
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (tid < kNT) xsq = sSum[tid];
+  if (C > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast at them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t idesc = umma_idesc_tf32(128, kNT);
   const int nchunk = d / kKC;
-  const uint32_t lboA = (uint32_t)rows * 16u, lboB = (uint32_t)kNT * 16u;
-  const int chunk_vec4 = (int)(2 * part_floats / 4);                    // uint4 loads per chunk
-  uint32_t uses[2] = {0, 0};                                             // completed fills per stage
+  const int64_t total = (int64_t)a.T * nchunk;                           // G chunks consumed over the rollout
+  const uint32_t lboA = (uint32_t)rows * 16u;
+  constexpr uint32_t lboB = kXBlock * 4;      // bytes between the two 4-coordinate halves of one K = 8 MMA step
+
+  // TMA producer (thread 0): one bulk copy per chunk; G is packed so that a chunk is contiguous
+  auto issue_load = [&](int s, int c) {
+    const uint32_t bar = smem_u32(&bar_full[s]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(stage_bytes) : "memory");
+    if (C == 1) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+          :: "r"(smem_u32(sG0) + (uint32_t)s * stage_bytes), "l"(a.Gp + (size_t)c * 2 * part_floats),
+             "r"(stage_bytes), "r"(bar) : "memory");
+    } else {
+      // this CTA fetches its 1/C slice of the chunk and multicasts it into every CTA of the cluster; each
+      // destination's full barrier (same offset) receives the bytes
+      const uint32_t slice = stage_bytes / C;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
+          :: "r"(smem_u32(sG0) + (uint32_t)s * stage_bytes + crank * slice),
+             "l"(reinterpret_cast<const char*>(a.Gp) + (size_t)c * stage_bytes + crank * slice), "r"(slice), "r"(bar),
+             "h"(cmask) : "memory");
+    }
+  };
+  if (tid == 0) {
+    for (int g = 0; g < kNS && g < total; ++g) issue_load(g, g % nchunk);
+  }
+  // descriptor bases: per-MMA descriptors differ from these only in the 14-bit start-address field
+  const uint64_t a_desc0 = umma_desc(smem_u32(sG0), lboA, 128);
+  const uint64_t bhi_desc0 = umma_desc(smem_u32(sXhi), lboB, 128);
+  const uint64_t blo_desc0 = umma_desc(smem_u32(sXlo), lboB, 128);
+  // per-thread epilogue constants
+  const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  int fill = 0, fphase = 0;      // pipeline cursor of this thread's role (stage index, phase parity)
+  int cnext = kNS % nchunk;      // producer: chunk index of the next refill
+  int64_t gnext = kNS;
 
   for (int t = 0; t < a.T; ++t) {
-    for (int c = 0; c < nchunk; ++c) {
-      const int s = c & 1;
-      if (uses[s] > 0) mbar_wait(&bars[s], (uses[s] - 1) & 1);          // MMAs of the previous fill retired
-      float* stage = sG0 + (size_t)s * 2 * part_floats;
-      const uint4* src = reinterpret_cast<const uint4*>(a.Gp + (size_t)c * 2 * part_floats);
-      uint4* dst = reinterpret_cast<uint4*>(stage);
-      for (int i = tid; i < chunk_vec4; i += kThreads) dst[i] = __ldg(src + i);
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t ghi = smem_u32(stage), glo = smem_u32(stage + part_floats);
+    float wv[kNT];
+    auto load_w = [&](int b) {   // disturbance of this thread's row of block b for the CTA's 64 envs
+      const int row = b * 128 + tid;
+      if (a.W != nullptr && row < d) {
+        const float* wrow = a.W + ((int64_t)t * a.N + env0) * d + row;
+        if (nvalid == kNT) {
 #pragma unroll
-        for (int ks = 0; ks < kKC / 8; ++ks) {
-          const uint32_t koffA = (uint32_t)ks * 2u * lboA;
-          const uint32_t koffB = (uint32_t)(c * (kKC / 4) + ks * 2) * lboB;
-          const uint64_t bhi = umma_desc(smem_u32(sXhi) + koffB, lboB, 128);
-          const uint64_t blo = umma_desc(smem_u32(sXlo) + koffB, lboB, 128);
-          for (int b = 0; b < MB; ++b) {
-            const uint32_t roff = (uint32_t)b * 128u * 16u;
-            const uint64_t ahi = umma_desc(ghi + koffA + roff, lboA, 128);
-            const uint64_t alo = umma_desc(glo + koffA + roff, lboA, 128);
-            const uint32_t td = tmem_base + (uint32_t)b * kNT;
-            umma_tf32(td, ahi, bhi, idesc, (c | ks) != 0);
-            umma_tf32(td, ahi, blo, idesc, 1);
-            umma_tf32(td, alo, bhi, idesc, 1);
-          }
+          for (int n = 0; n < kNT; ++n) wv[n] = __ldg(wrow + (uint32_t)n * (uint32_t)d);
+        } else {
+#pragma unroll
+          for (int n = 0; n < kNT; ++n) wv[n] = n < nvalid ? __ldg(wrow + (uint32_t)n * (uint32_t)d) : 0.f;
         }
-        umma_commit(&bars[s]);
-        if (c == nchunk - 1) umma_commit(&bars[2]);
+      } else {
+#pragma unroll
+        for (int n = 0; n < kNT; ++n) wv[n] = 0.f;
       }
-      ++uses[s];
+    };
+    if (warp == 0) {
+      // ---- producer warp: refill each stage as soon as the MMAs that read it have retired
+      for (int c = 0; c < nchunk; ++c) {
+        if (a.dbg & 2) break;
+        mbar_wait(&bar_empty[fill], (uint32_t)fphase);
+        if (lane == 0 && gnext < total) issue_load(fill, cnext);
+        ++gnext;
+        cnext = cnext + 1 == nchunk ? 0 : cnext + 1;
+        if (++fill == kNS) { fill = 0; fphase ^= 1; }
+      }
+    } else if (warp == 1) {
+      // ---- MMA warp: every lane tracks the pipeline (warp-uniform descriptors), one elected lane issues
+      uint64_t bhi = bhi_desc0, blo = blo_desc0;
+      for (int c = 0; c < nchunk; ++c) {
+        if (!(a.dbg & 2) || (t == 0 && c < kNS)) mbar_wait(&bar_full[fill], (uint32_t)fphase);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint64_t ahi = a_desc0 + (uint64_t)((uint32_t)fill * (stage_bytes >> 4));
+        const uint64_t alo = ahi + (part_bytes >> 4);
+        const uint32_t acc = c != 0;
+        if (elect_one()) {
+#pragma unroll
+          for (int b = 0; b < MB; ++b) {
+            const uint32_t td = tmem_base + (uint32_t)b * kNT;
+            umma_tf32(td, ahi + (uint64_t)(b * 128), bhi, idesc, acc);     // 128 rows x 16 B = 2048 B >> 4
+            if (!(a.dbg & 1)) {
+              umma_tf32(td, ahi + (uint64_t)(b * 128), blo, idesc, 1);
+              umma_tf32(td, alo + (uint64_t)(b * 128), bhi, idesc, 1);
+            }
+          }
+          if (C == 1) umma_commit(&bar_empty[fill]); else umma_commit_mc(&bar_empty[fill], cmask);
+          if (c == nchunk - 1) umma_commit(bar_accum);
+        }
+        __syncwarp();
+        bhi += (2 * lboB) >> 4;
+        blo += (2 * lboB) >> 4;
+        if (++fill == kNS) { fill = 0; fphase ^= 1; }
+      }
     }
-    // ---- epilogue: accumulators -> registers
-    mbar_wait(&bars[2], t & 1);
+    load_w(0);
+    // ---- epilogue: accumulators -> registers, x_{t+1} -> operand buffer, costs
+    mbar_wait(bar_accum, (uint32_t)(t & 1));
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     float xs_new = 0.f, us = 0.f;
+#pragma unroll
     for (int b = 0; b < MB; ++b) {
       const int row = b * 128 + tid;                                     // output row of G owned by this thread
       uint32_t v[kNT];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)b * kNT;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-          "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-          "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
-            "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
-            "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
-            "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
-            "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      tmem_ld_row64(lane_taddr + (uint32_t)b * kNT, v);
       const bool is_x = row < d, is_u = row >= d && row < d + a.m;
+      float* xh = sXhi + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3);   // lane = coordinate: 32 banks
+      float* xl = sXlo + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3);
+      float qx[kNT];
+      if (is_x) {
 #pragma unroll
-      for (int n = 0; n < kNT; ++n) {
-        float val = __uint_as_float(v[n]);
-        const int64_t e = env0 + n;
-        if (is_x) {
-          if (a.W && e < a.N) val += __ldg(a.W + ((int64_t)t * a.N + e) * d + row);   // x' = (A x + B u) + w_t
+        for (int n = 0; n < kNT; ++n) {
+          const float val = __uint_as_float(v[n]) + wv[n];               // x' = (A x + B u) + w_t
           float hi, lo;
           split_tf32(val, hi, lo);
-          const size_t o = ((size_t)(row / 4) * kNT + n) * 4 + (row % 4);
-          sXhi[o] = hi;
-          sXlo[o] = lo;
-          if (t == a.T - 1 && e < a.N) a.x_io[e * d + row] = val;
+          if (!(a.dbg & 4)) { xh[n * 4] = hi; xl[n * 4] = lo; }
+          qx[n] = val * val;
         }
-        scratch[n * 129 + tid] = (is_x || is_u) ? val * val : 0.f;
+      } else {
+#pragma unroll
+        for (int n = 0; n < kNT; ++n) {
+          const float val = __uint_as_float(v[n]);
+          qx[n] = is_u ? val * val : 0.f;
+        }
       }
+      if (b + 1 < MB) load_w(b + 1);                                     // next block's disturbance in flight
+      // a 128-row block holds state rows, action rows, or both (when d % 128 != 0): reduce x and u parts
+      const bool mixed = b * 128 < d && (b + 1) * 128 > d;
+      if (mixed) {
+        float qu[kNT];
+#pragma unroll
+        for (int n = 0; n < kNT; ++n) { qu[n] = is_u ? qx[n] : 0.f; qx[n] = is_x ? qx[n] : 0.f; }
+        warp_colsum64(qu, lane);
+        sSum[(4 + warp) * kNT + 2 * lane] = qu[0];
+        sSum[(4 + warp) * kNT + 2 * lane + 1] = qu[1];
+      }
+      warp_colsum64(qx, lane);
+      const int which = (b * 128 >= d) ? 1 : 0;                          // 0: state block (or mixed: x part), 1: action block
+      sSum[(which * 4 + warp) * kNT + 2 * lane] = qx[0];
+      sSum[(which * 4 + warp) * kNT + 2 * lane + 1] = qx[1];
       __syncthreads();
       if (tid < kNT) {
-        float sum = 0.f;
-        for (int j = 0; j < kThreads; ++j) sum += scratch[tid * 129 + j];
-        // rows [b*128, b*128+128) are all state rows, all action rows, or straddle d (d % 128 != 0)
-        if ((b + 1) * 128 <= d) xs_new += sum;
-        else if (b * 128 >= d) us += sum;
-        else {  // straddling block: split the sum at row d
-          float sx = 0.f;
-          for (int j = 0; j < d - b * 128; ++j) sx += scratch[tid * 129 + j];
-          xs_new += sx;
-          us += sum - sx;
-        }
+        const float s4 = (sSum[(which * 4 + 0) * kNT + tid] + sSum[(which * 4 + 1) * kNT + tid]) +
+                         (sSum[(which * 4 + 2) * kNT + tid] + sSum[(which * 4 + 3) * kNT + tid]);
+        if (which == 0) xs_new += s4; else us += s4;
+        if (mixed)
+          us += (sSum[(4 + 0) * kNT + tid] + sSum[(4 + 1) * kNT + tid]) +
+                (sSum[(4 + 2) * kNT + tid] + sSum[(4 + 3) * kNT + tid]);
       }
       __syncthreads();
     }
     if (tid < kNT) {
-      const int64_t e = env0 + tid;
       const float cost = xsq + us;                                       // x_t'x_t + u_t'u_t
-      if (e < a.N) {
-        if (a.cost_out) a.cost_out[(int64_t)t * a.N + e] = cost;
+      if (tid < nvalid) {
+        if (a.cost_out) a.cost_out[(int64_t)t * a.N + env0 + tid] = cost;
         csum += (double)cost;
       }
       xsq = xs_new;
@@ -271,14 +401,23 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   }
-  if (tid < kNT) {
-    const int64_t e = env0 + tid;
-    if (e < a.N) {
-      if (a.cost_sum_out) a.cost_sum_out[e] = csum;
-      if (a.status_out) a.status_out[e] = isfinite(csum) ? 0 : DLC_STATUS_NONFINITE;
+  // x_T back to global: hi + lo reconstructs the fp32 state exactly (lo = x - hi is exact)
+  {
+    const int n = tid >> 1, k0 = (tid & 1) * (d / 2);
+    if (n < nvalid) {
+      float* gx = a.x_io + (env0 + n) * d;
+      for (int k = k0; k < k0 + d / 2; ++k) {
+        const uint32_t o = xoff(n, k);
+        gx[k] = sXhi[o] + sXlo[o];
+      }
     }
   }
+  if (tid < nvalid) {
+    if (a.cost_sum_out) a.cost_sum_out[env0 + tid] = csum;
+    if (a.status_out) a.status_out[env0 + tid] = isfinite(csum) ? 0 : DLC_STATUS_NONFINITE;
+  }
   __syncthreads();
+  if (C > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(tmem_base) : "memory");
   }
@@ -289,10 +428,11 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
 using namespace dlc;
 
 static int shared_blocks(int d, int m) { return (d + m + 127) / 128; }
+static int shared_rows(int d, int m) { return (d + m + 7) / 8 * 8; }
 
 extern "C" size_t dlc_lds_shared_packed_floats(int32_t d, int32_t m) {
   if (d <= 0 || m <= 0 || d % kKC) return 0;
-  return (size_t)2 * shared_blocks(d, m) * 128 * d;
+  return (size_t)2 * shared_rows(d, m) * d;
 }
 
 extern "C" int32_t dlc_lds_shared_pack_f32(const float* A, const float* B, const float* K, int32_t d, int32_t m,
@@ -300,8 +440,8 @@ extern "C" int32_t dlc_lds_shared_pack_f32(const float* A, const float* B, const
   if (!A || !B || !K || !G_packed) return fail(DLC_ERR_ARG, "dlc_lds_shared_pack_f32: NULL buffer");
   if (d < kKC || d % kKC || d > 256 || m < 1 || shared_blocks(d, m) > 3)
     return fail(DLC_ERR_SHAPE, "dlc_lds_shared_pack_f32: need d % 16 == 0, 16 <= d <= 256, d + m <= 384");
-  const int MB = shared_blocks(d, m), total = MB * 128 * d;
-  shared_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, B, K, d, m, MB, G_packed);
+  const int RP = shared_rows(d, m), total = RP * d;
+  shared_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, B, K, d, m, RP, G_packed);
   return cuda_status(cudaGetLastError(), "shared_pack_kernel launch");
 }
 
@@ -314,15 +454,38 @@ extern "C" int32_t dlc_lds_shared_lqr_rollout_f32(int64_t N, int32_t T, int32_t 
   if (N == 0 || T == 0) return DLC_OK;
   if (!G_packed || !x_io) return fail(DLC_ERR_ARG, "dlc_lds_shared_lqr_rollout_f32: NULL buffer");
   SharedArgs a{};
-  a.N = N; a.T = T; a.d = d; a.m = m; a.MB = shared_blocks(d, m);
+  a.N = N; a.T = T; a.d = d; a.m = m; a.MB = shared_blocks(d, m); a.RP = shared_rows(d, m);
   a.Gp = G_packed; a.W = W; a.x_io = x_io; a.cost_out = cost_out; a.cost_sum_out = cost_sum_out;
   a.status_out = status_out;
-  const size_t part = (size_t)(kKC / 4) * a.MB * 128 * 4;
-  const size_t stage_area = 4 * part > (size_t)kNT * 129 + 31 ? 4 * part : ((size_t)kNT * 129 + 31) / 32 * 32;
-  const size_t smem = ((size_t)2 * kNT * d + stage_area) * sizeof(float) + 64;
-  cudaError_t e = cudaFuncSetAttribute(lds_shared_lqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t part = (size_t)(kKC / 4) * a.RP * 4;
+  const size_t smem = ((size_t)2 * (d / 4) * kXBlock + 2 * kNS * part + 2 * 4 * kNT) * sizeof(float) + 128;
+  void (*kern)(SharedArgs) = a.MB == 1 ? lds_shared_lqr_kernel<1> : a.MB == 2 ? lds_shared_lqr_kernel<2>
+                                                                               : lds_shared_lqr_kernel<3>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_shared_lqr)");
-  const unsigned grid = (unsigned)((N + kNT - 1) / kNT);
-  lds_shared_lqr_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(a);
-  return cuda_status(cudaGetLastError(), "lds_shared_lqr_kernel launch");
+  unsigned grid = (unsigned)((N + kNT - 1) / kNT);
+  // clusters of up to 4 CTAs share every G chunk through TMA multicast (L2 traffic / C); idle CTAs of a
+  // partially filled last cluster run on zeros and store nothing
+  const char* denv = getenv("DLC_SHARED_DBG");
+  a.dbg = denv ? atoi(denv) : 0;
+  const char* cenv = getenv("DLC_SHARED_CLUSTER");
+  int C = cenv ? atoi(cenv) : 4;
+  if (C != 1 && C != 2 && C != 4) C = 4;
+  while (C > 1 && grid < (unsigned)C) C >>= 1;
+  a.C = C;
+  grid = (grid + C - 1) / C * C;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, a);
+  return cuda_status(e, "lds_shared_lqr_kernel launch");
 }

@@ -80,6 +80,32 @@ for name, Env in (("pendulum", Pendulum), ("cartpole", Cartpole)):
                                   "mean_final_cost": float(c.mean()), "finite": bool(torch.isfinite(c).all()),
                                   "bound": "instruction latency (serial T x H dependency chain per trajectory)"}
 
+# ---- config 5 (dense part): shared-dynamics LDS d=256, m=64 + LQR on tcgen05 (3xTF32)
+from deluca_b200.riccati import dare_gain
+d5, m5 = 256, 64
+gg = torch.Generator(device=dev).manual_seed(0)
+Qm = torch.linalg.qr(torch.randn(d5, d5, device=dev, generator=gg, dtype=torch.float64))[0]
+A5 = ((Qm * (0.7 + 0.25 * torch.rand(d5, device=dev, generator=gg, dtype=torch.float64))) @ Qm.T).float().contiguous()
+B5 = (torch.randn(d5, m5, device=dev, generator=gg) / d5 ** 0.5).contiguous()
+K5 = dare_gain(A5, B5)[0].contiguous()
+G5 = fused.lds_shared_pack(A5, B5, K5)
+F5 = 2 * d5 * d5 + 2 * d5 * m5 + d5 + 2 * m5 * d5 + 2 * d5 + 2 * m5      # env + action + cost FLOPs per env-step
+tens_peak = peaks.get("bf16_tflops", 1590.0) / 2.0                        # dense TF32 = half the bf16 rate
+for N5, T5, with_w in ((148 * 64 * 8, 50, True), (1 << 20, 20, False)):
+    x5 = torch.randn(N5, d5, device=dev, generator=gg)
+    W5 = (0.5 * torch.randn(T5, N5, d5, device=dev, generator=gg)) if with_w else None
+    ms = timeit(lambda: fused.lds_shared_lqr_rollout(G5, x5, T5, m5, W=W5, keep_costs=True), reps=3, warm=2)
+    r5 = fused.lds_shared_lqr_rollout(G5, x5, T5, m5, W=W5)
+    ach = F5 * N5 * T5 / (ms * 1e-3) / 1e12
+    exe = 3 * 2 * 384 * d5 * N5 * T5 / (ms * 1e-3) / 1e12                 # executed tensor FLOPs: 3 passes, 384 padded rows
+    out[f"shared_lqr_d256_m64_N{N5}_{'W' if with_w else 'noW'}"] = {
+        "envs": N5, "T": T5, "kernel_ms": ms, "env_steps_per_s": N5 * T5 / (ms * 1e-3), "finite": int(r5.status.sum()) == 0,
+        "roofline": {"bound": "tensor", "achieved": ach, "executed_tensor_tflops": exe, "peak": tens_peak,
+                     "unit": "TFLOP/s", "frac": exe / tens_peak, "flops_per_env_step": F5,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (dense TF32 rate; not measured directly)"}}
+    del x5, W5, r5
+    torch.cuda.empty_cache()
+
 # ---- CPU oracle on bounded samples
 from oracle import igpc as OG
 from oracle import lung as OL

@@ -24,7 +24,8 @@ namespace dlc {
 constexpr int kNT = 64;    // envs per CTA = MMA N
 constexpr int kKC = 8;     // k-chunk of G staged per pipeline stage (one K=8 MMA step)
 constexpr int kNS = 4;     // pipeline stages (bulk copies in flight)
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;  // 8 warps: warp w and w + 4 share TMEM lane quadrant w % 4 and split the 64 envs
+constexpr int kHalf = kNT / 2; // envs (accumulator columns) handled by one thread in the epilogue
 
 struct SharedArgs {
   int64_t N;
@@ -140,31 +141,25 @@ __global__ void shared_pack_kernel(const float* A, const float* B, const float* 
 }
 
 // ------------------------------------------------------------------------------------ rollout
-// tcgen05.ld of one accumulator row (this thread's TMEM lane), 64 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld_row64(uint32_t taddr, uint32_t (&v)[kNT]) {
+// tcgen05.ld of one accumulator row (this thread's TMEM lane), 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_row32(uint32_t taddr, uint32_t (&v)[kHalf]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
-        "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
-        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
-        "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
-        "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// Column sums over the 32 lanes of a warp of a per-lane 64-vector (transposed butterfly: 62 shuffles).
-// On return lane L holds the sums of columns 2L and 2L+1 in q[0], q[1].
-__device__ __forceinline__ void warp_colsum64(float (&q)[kNT], int lane) {
+// Column sums over the 32 lanes of a warp of a per-lane 32-vector (transposed butterfly: 31 shuffles).
+// On return lane L holds the sum of column L in q[0].
+__device__ __forceinline__ void warp_colsum32(float (&q)[kHalf], int lane) {
 #pragma unroll
-  for (int off = 16, len = 32; off >= 1; off >>= 1, len >>= 1) {
+  for (int off = 16, len = 16; off >= 1; off >>= 1, len >>= 1) {
     const bool up = (lane & off) != 0;
 #pragma unroll
     for (int i = 0; i < len; ++i) {
@@ -212,11 +207,11 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   // X_0 -> operand buffer (hi/lo split); |x_0|^2 per env through the column-sum scratch
   float xsq = 0.f;  // thread n < kNT: |x_t|^2 of env n
   {
-    float part = 0.f;  // this thread's share of env (tid / 2): coordinates [ (tid&1)*d/2, ... )
-    const int n = tid >> 1, k0 = (tid & 1) * (d / 2);
+    float part = 0.f;  // this thread's share of env (tid / 4): a quarter of the coordinates
+    const int n = tid >> 2, k0 = (tid & 3) * (d / 4);
     const bool ok = n < nvalid;
     const float* gx = a.x_io + (env0 + n) * d;
-    for (int k = k0; k < k0 + d / 2; ++k) {
+    for (int k = k0; k < k0 + d / 4; ++k) {
       const float x = ok ? gx[k] : 0.f;
       float hi, lo;
       split_tf32(x, hi, lo);
@@ -226,7 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
       part = fmaf(x, x, part);
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
-    if ((tid & 1) == 0) sSum[n] = part;
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if ((tid & 3) == 0) sSum[n] = part;
   }
   double csum = 0.0;
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -271,27 +267,29 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   const uint64_t bhi_desc0 = umma_desc(smem_u32(sXhi), lboB, 128);
   const uint64_t blo_desc0 = umma_desc(smem_u32(sXlo), lboB, 128);
   // per-thread epilogue constants
-  const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int quad = warp & 3, half = warp >> 2;   // TMEM lane quadrant / which 32 of the 64 envs
+  const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * kHalf;
+  const int nbase = half * kHalf;
   int fill = 0, fphase = 0;      // pipeline cursor of this thread's role (stage index, phase parity)
   int cnext = kNS % nchunk;      // producer: chunk index of the next refill
   int64_t gnext = kNS;
 
   for (int t = 0; t < a.T; ++t) {
-    float wv[kNT];
-    auto load_w = [&](int b) {   // disturbance of this thread's row of block b for the CTA's 64 envs
-      const int row = b * 128 + tid;
+    float wv[kHalf];
+    auto load_w = [&](int b) {   // disturbance of this thread's row of block b for its 32 envs
+      const int row = b * 128 + quad * 32 + lane;
       if (a.W != nullptr && row < d) {
-        const float* wrow = a.W + ((int64_t)t * a.N + env0) * d + row;
+        const float* wrow = a.W + ((int64_t)t * a.N + env0 + nbase) * d + row;
         if (nvalid == kNT) {
 #pragma unroll
-          for (int n = 0; n < kNT; ++n) wv[n] = __ldg(wrow + (uint32_t)n * (uint32_t)d);
+          for (int n = 0; n < kHalf; ++n) wv[n] = __ldg(wrow + (uint32_t)n * (uint32_t)d);
         } else {
 #pragma unroll
-          for (int n = 0; n < kNT; ++n) wv[n] = n < nvalid ? __ldg(wrow + (uint32_t)n * (uint32_t)d) : 0.f;
+          for (int n = 0; n < kHalf; ++n) wv[n] = nbase + n < nvalid ? __ldg(wrow + (uint32_t)n * (uint32_t)d) : 0.f;
         }
       } else {
 #pragma unroll
-        for (int n = 0; n < kNT; ++n) wv[n] = 0.f;
+        for (int n = 0; n < kHalf; ++n) wv[n] = 0.f;
       }
     };
     if (warp == 0) {
@@ -339,16 +337,16 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
     float xs_new = 0.f, us = 0.f;
 #pragma unroll
     for (int b = 0; b < MB; ++b) {
-      const int row = b * 128 + tid;                                     // output row of G owned by this thread
-      uint32_t v[kNT];
-      tmem_ld_row64(lane_taddr + (uint32_t)b * kNT, v);
+      const int row = b * 128 + quad * 32 + lane;                        // output row of G owned by this thread
+      uint32_t v[kHalf];
+      tmem_ld_row32(lane_taddr + (uint32_t)b * kNT, v);
       const bool is_x = row < d, is_u = row >= d && row < d + a.m;
-      float* xh = sXhi + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3);   // lane = coordinate: 32 banks
-      float* xl = sXlo + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3);
-      float qx[kNT];
+      float* xh = sXhi + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3) + (uint32_t)nbase * 4u;   // lane = coordinate: 32 banks
+      float* xl = sXlo + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3) + (uint32_t)nbase * 4u;
+      float qx[kHalf];
       if (is_x) {
 #pragma unroll
-        for (int n = 0; n < kNT; ++n) {
+        for (int n = 0; n < kHalf; ++n) {
           const float val = __uint_as_float(v[n]) + wv[n];               // x' = (A x + B u) + w_t
           float hi, lo;
           split_tf32(val, hi, lo);
@@ -357,34 +355,35 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
         }
       } else {
 #pragma unroll
-        for (int n = 0; n < kNT; ++n) {
+        for (int n = 0; n < kHalf; ++n) {
           const float val = __uint_as_float(v[n]);
           qx[n] = is_u ? val * val : 0.f;
         }
       }
       if (b + 1 < MB) load_w(b + 1);                                     // next block's disturbance in flight
-      // a 128-row block holds state rows, action rows, or both (when d % 128 != 0): reduce x and u parts
+      // a 128-row block holds state rows, action rows, or both (when d % 128 != 0): reduce x and u parts;
+      // sSum[part][warp][32]: the column sums of warp (quad, half) for its 32 envs
       const bool mixed = b * 128 < d && (b + 1) * 128 > d;
       if (mixed) {
-        float qu[kNT];
+        float qu[kHalf];
 #pragma unroll
-        for (int n = 0; n < kNT; ++n) { qu[n] = is_u ? qx[n] : 0.f; qx[n] = is_x ? qx[n] : 0.f; }
-        warp_colsum64(qu, lane);
-        sSum[(4 + warp) * kNT + 2 * lane] = qu[0];
-        sSum[(4 + warp) * kNT + 2 * lane + 1] = qu[1];
+        for (int n = 0; n < kHalf; ++n) { qu[n] = is_u ? qx[n] : 0.f; qx[n] = is_x ? qx[n] : 0.f; }
+        warp_colsum32(qu, lane);
+        sSum[(8 + warp) * kHalf + lane] = qu[0];
       }
-      warp_colsum64(qx, lane);
+      warp_colsum32(qx, lane);
       const int which = (b * 128 >= d) ? 1 : 0;                          // 0: state block (or mixed: x part), 1: action block
-      sSum[(which * 4 + warp) * kNT + 2 * lane] = qx[0];
-      sSum[(which * 4 + warp) * kNT + 2 * lane + 1] = qx[1];
+      sSum[(which * 8 + warp) * kHalf + lane] = qx[0];
       __syncthreads();
-      if (tid < kNT) {
-        const float s4 = (sSum[(which * 4 + 0) * kNT + tid] + sSum[(which * 4 + 1) * kNT + tid]) +
-                         (sSum[(which * 4 + 2) * kNT + tid] + sSum[(which * 4 + 3) * kNT + tid]);
+      if (tid < kNT) {                                                   // thread = env: add the four quadrants of its half
+        const int hw = (tid >> 5) * 4, col = tid & 31;
+        const float* ps = sSum + (which * 8 + hw) * kHalf + col;
+        const float s4 = (ps[0] + ps[kHalf]) + (ps[2 * kHalf] + ps[3 * kHalf]);
         if (which == 0) xs_new += s4; else us += s4;
-        if (mixed)
-          us += (sSum[(4 + 0) * kNT + tid] + sSum[(4 + 1) * kNT + tid]) +
-                (sSum[(4 + 2) * kNT + tid] + sSum[(4 + 3) * kNT + tid]);
+        if (mixed) {
+          const float* pu = sSum + (8 + hw) * kHalf + col;
+          us += (pu[0] + pu[kHalf]) + (pu[2 * kHalf] + pu[3 * kHalf]);
+        }
       }
       __syncthreads();
     }
@@ -403,10 +402,10 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   }
   // x_T back to global: hi + lo reconstructs the fp32 state exactly (lo = x - hi is exact)
   {
-    const int n = tid >> 1, k0 = (tid & 1) * (d / 2);
+    const int n = tid >> 2, k0 = (tid & 3) * (d / 4);
     if (n < nvalid) {
       float* gx = a.x_io + (env0 + n) * d;
-      for (int k = k0; k < k0 + d / 2; ++k) {
+      for (int k = k0; k < k0 + d / 4; ++k) {
         const uint32_t o = xoff(n, k);
         gx[k] = sXhi[o] + sXlo[o];
       }

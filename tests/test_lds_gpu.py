@@ -108,8 +108,12 @@ def test_lqr_matches_oracle_and_zero_lr_gpc(variant):
     _check(a, ref, T)
     b = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W), H=3, HH=10,
                     lr_scale=0.0, kernel_variant=variant)
-    # M == 0 and lr == 0 reduce GPC to LQR (SURVEY A-3.6): same arithmetic, same bits
-    assert torch.equal(a.costs, b.costs) and torch.equal(a.x, b.x)
+    # M == 0 and lr == 0 reduce GPC to LQR (SURVEY A-3.6).  The runtime-dims kernel runs the same
+    # arithmetic for both (same bits); the templated GPC kernel packs its FMAs (other rounding order).
+    if variant == 1:
+        assert torch.equal(a.costs, b.costs) and torch.equal(a.x, b.x)
+    else:
+        assert torch.allclose(a.costs, b.costs, rtol=1e-5, atol=1e-5) and torch.allclose(a.x, b.x, rtol=1e-5, atol=1e-5)
 
 
 def test_resume_is_identical_and_inputs_untouched():

@@ -85,6 +85,26 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
       Kc[c][i] = gi < D ? __ldg(a.K + np * (M * D) + c * D + gi) : 0.f;
     }
   }
+  if (POLICY == DLC_POLICY_GPC) {
+    // GPC keeps the closed-loop matrix A - B K instead of A: the counterfactual recursion
+    // y <- A y + B(-K y + v) + w is (A - BK) y + B v + w and its adjoint lam <- A'lam - K'B'lam is
+    // (A - BK)' lam, which removes one K mat-vec and its cross-lane reduction per recursion step;
+    // the env step recovers A x = (A - BK) x + B (K x) from the K x it needs for the action anyway.
+#pragma unroll
+    for (int i = 0; i < DL; ++i) {
+#pragma unroll
+      for (int c = 0; c < L; ++c)
+#pragma unroll
+        for (int k = 0; k < DL; ++k) {
+          const int gj = (q ^ c) * DL + k;
+          float s = Ar[i][c * DL + k];
+#pragma unroll
+          for (int cc = 0; cc < M; ++cc)
+            s = fmaf(-Br[i][cc], gj < D ? __ldg(a.K + np * (M * D) + cc * D + gj) : 0.f, s);
+          Ar[i][c * DL + k] = s;
+        }
+    }
+  }
   float x[DL], ax[DL], uprev[M];
 #pragma unroll
   for (int k = 0; k < DL; ++k) x[k] = (q * DL + k < D) ? a.x_io[n * D + q * DL + k] : 0.f;
@@ -116,11 +136,21 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
     for (int c = 1; c < L; ++c)
 #pragma unroll
       for (int k = 0; k < DL; ++k) xf[c * DL + k] = __shfl_xor_sync(0xffffffffu, xf[k], c);
+    float kxp[M];
 #pragma unroll
-    for (int i = 0; i < DL; ++i) {
+    for (int c = 0; c < M; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < DL; ++k) s = fmaf(Kc[c][k], xf[k], s);
+      kxp[c] = group_allreduce<L>(s);
+    }
+#pragma unroll
+    for (int i = 0; i < DL; ++i) {   // A x_prev = (A - BK) x_prev + B (K x_prev)
       float s = 0.f;
 #pragma unroll
       for (int r = 0; r < DF; ++r) s = fmaf(Ar[i][r], xf[r], s);
+#pragma unroll
+      for (int c = 0; c < M; ++c) s = fmaf(Br[i][c], kxp[c], s);
       ax[i] = s;
     }
 #pragma unroll
@@ -265,22 +295,14 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
             yn[i] = s + wh[i * TPB];
           }
         } else {
-          float yf[DF], ky[M];
+          float yf[DF];
 #pragma unroll
           for (int k = 0; k < DL; ++k) yf[k] = y[k];
 #pragma unroll
           for (int c = 1; c < L; ++c)
 #pragma unroll
             for (int k = 0; k < DL; ++k) yf[c * DL + k] = __shfl_xor_sync(0xffffffffu, y[k], c);
-#pragma unroll
-          for (int c = 0; c < M; ++c) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < DL; ++k) s = fmaf(Kc[c][k], y[k], s);
-            ky[c] = s;
-          }
-#pragma unroll
-          for (int c = 0; c < M; ++c) v[c] -= group_allreduce<L>(ky[c]);
+          // (A - BK) y + B v_h: the -K y term lives in the closed-loop matrix
 #pragma unroll
           for (int i = 0; i < DL; ++i) {
             float s = 0.f;
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
           for (int i = 0; i < DL; ++i) s = fmaf(Br[i][c], lam[i], s);
           sc[c] = group_allreduce<L>(s);
         }
-        if (h > 0) {  // lam <- A' lam - K' lam_u  (before sc is scaled)
+        if (h > 0) {  // lam <- A' lam - K' lam_u = (A - BK)' lam
           float part[DF];
 #pragma unroll
           for (int r = 0; r < DF; ++r) {
@@ -355,9 +377,8 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
             float s = part[k];
 #pragma unroll
             for (int c = 1; c < L; ++c) s += __shfl_xor_sync(0xffffffffu, part[c * DL + k], c);
-#pragma unroll
-            for (int c = 0; c < M; ++c) s = fmaf(-Kc[c][k], sc[c], s);
-            lam[k] = s;
+            lam[k] = s;   // (A - BK)' lam
+
           }
         }
 #pragma unroll
@@ -422,9 +443,21 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < DF; ++r) s = fmaf(Ar[i][r], xf[r], s);
-        ax[i] = s;
+        if (GPC) {
+          // Ar holds A - BK: x' = (A - BK) x + B mw + w (u = mw - K x), and A x for the next step's
+          // noise estimate is (A - BK) x + B (K x)
+          float sa = s;
 #pragma unroll
-        for (int c = 0; c < M; ++c) s = fmaf(Br[i][c], u[c], s);
+          for (int c = 0; c < M; ++c) {
+            sa = fmaf(Br[i][c], red[c], sa);
+            s = fmaf(Br[i][c], red[GPC ? M + c : c], s);
+          }
+          ax[i] = sa;
+        } else {
+          ax[i] = s;
+#pragma unroll
+          for (int c = 0; c < M; ++c) s = fmaf(Br[i][c], u[c], s);
+        }
         x[i] = s + w_t[i];
       }
     }

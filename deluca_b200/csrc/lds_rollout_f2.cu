@@ -99,9 +99,16 @@ __global__ void __launch_bounds__(TPB)
   const float* gK = a.K + np * (M * D);
   f2 Ar2[NPA][DF], Br2[NPA][M], Kc2[M][NPA];
   float Art[DF], Brt[M], Kct[M];
+  // The kernel keeps the closed-loop matrix A - B K instead of A: the counterfactual recursion
+  // y <- A y + B(-K y + v) + w is (A - BK) y + B v + w and its adjoint is (A - BK)' lam, which removes one K
+  // mat-vec and its cross-lane reduction per recursion step; the env step recovers A x = (A - BK) x + B (K x).
   auto Aelem = [&](int k, int r) {  // row = own coordinate k, column = lane-relative index r
     const int gi = coord(k), gj = (q ^ (r / DL)) * DL + (r % DL);
-    return (gi < D && gj < D) ? __ldg(gA + gi * D + gj) : 0.f;
+    if (!(gi < D && gj < D)) return 0.f;
+    float s = __ldg(gA + gi * D + gj);
+#pragma unroll
+    for (int c = 0; c < M; ++c) s = fmaf(-__ldg(gB + gi * M + c), __ldg(gK + c * D + gj), s);
+    return s;
   };
 #pragma unroll
   for (int kk = 0; kk < NP; ++kk) {
@@ -235,9 +242,13 @@ __global__ void __launch_bounds__(TPB)
 #pragma unroll
     for (int kk = 0; kk < NP; ++kk) xp.p[kk] = pk(ld(a.xprev_io + n * D, 2 * kk), ld(a.xprev_io + n * D, 2 * kk + 1));
     xp.t = TAIL ? ld(a.xprev_io + n * D, DL - 1) : 0.f;
-    float xf[DF];
+    float xf[DF], kxp[M];
     gather(xp, xf);
-    Amul(xf, ax);
+    Amul(xf, ax);                                              // (A - BK) x_prev ...
+    Kdot(xp, kxp);
+#pragma unroll
+    for (int c = 0; c < M; ++c) kxp[c] = group_allreduce2<L>(kxp[c]);
+    Bacc(kxp, ax);                                             // ... + B (K x_prev) = A x_prev
 #pragma unroll
     for (int c = 0; c < M; ++c) uprev[c] = a.uprev_io ? a.uprev_io[n * M + c] : 0.f;
   }
@@ -392,12 +403,9 @@ __global__ void __launch_bounds__(TPB)
         for (int kk = 0; kk < NP; ++kk) yn.p[kk] = pk(0.f, 0.f);
         yn.t = 0.f;
       } else {
-        float yf[DF], ky[M];
+        float yf[DF];
         gather(y, yf);
-        Kdot(y, ky);
-#pragma unroll
-        for (int c = 0; c < M; ++c) v[c] -= group_allreduce2<L>(ky[c]);
-        Amul(yf, yn);
+        Amul(yf, yn);                                            // (A - BK) y: the -K y term is in the matrix
       }
       Bacc(v, yn);
 #pragma unroll
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(TPB)
       BTdot(lam, lu);
 #pragma unroll
       for (int c = 0; c < M; ++c) lu[c] = group_allreduce2<L>(lu[c]);
-      if (h > 0) {  // lam <- A' lam - K' lam_u
+      if (h > 0) {  // lam <- A' lam - K' lam_u = (A - BK)' lam
         float part[DF];
 #pragma unroll
         for (int r = 0; r < DF; ++r) {
@@ -459,8 +467,7 @@ __global__ void __launch_bounds__(TPB)
         }
 #pragma unroll
         for (int kk = 0; kk < NP; ++kk) lam.p[kk] = pk(own[2 * kk], own[2 * kk + 1]);
-        if (TAIL) lam.t = own[DL - 1];
-        KTsub(lu, lam);
+        if (TAIL) lam.t = own[DL - 1];                           // (A - BK)' lam
       }
       float sc[M];
 #pragma unroll
@@ -511,11 +518,13 @@ __global__ void __launch_bounds__(TPB)
 
     // ---- env: x <- (A x + B u) + w_t                                        _lds.py:102-111
     {
+      // x' = (A - BK) x + B mw + w (u = mw - K x); A x for the next noise estimate = (A - BK) x + B (K x)
       float xf[DF];
       gather(x, xf);
       Amul(xf, ax);
       Vk s = ax;
-      Bacc(u, s);
+      Bacc(red + M, s);
+      Bacc(red, ax);
 #pragma unroll
       for (int kk = 0; kk < NP; ++kk) x.p[kk] = add2(s.p[kk], w_t.p[kk]);
       if (TAIL) x.t = s.t + w_t.t;

@@ -208,6 +208,9 @@ def main():
     dev = torch.device("cuda", local)
     _abi.check(_abi.lib().dlc_check_device(), "dlc_check_device")
     if world > 1:
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout ahead of the JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     N, T, d, m, H, HH = (wl[k] for k in ("N", "T", "d", "m", "H", "HH"))
     env_offset = rank * N  # weak scaling: every rank owns N envs of a world*N-env job

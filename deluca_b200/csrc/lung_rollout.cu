@@ -249,3 +249,156 @@ extern "C" int32_t dlc_pid_f32(int64_t N, int32_t T, float decay, const float* K
                                                                             I_io, D_io, u_out);
   return cuda_status(cudaGetLastError(), "pid_kernel launch");
 }
+
+// ------------------------------------------------------------------------------------------
+// value + gradient of train_controller.rollout w.r.t. the PID gains (BalloonLung)
+// ------------------------------------------------------------------------------------------
+namespace dlc {
+
+struct LungGradArgs {
+  DlcLungParams p;
+  const float *K, *kf, *tt;
+  int loss_kind;
+  float noise, reset_pressure;
+  float *loss_out, *grad_out;
+  double* sums_out;
+  float* ws;   // [T][6][N]: P (after noise), V, p, i, d, time at the start of each step
+};
+
+template <int NK>
+__global__ void __launch_bounds__(128) lung_pid_grad_kernel(const LungGradArgs a) {
+  const DlcLungParams& p = a.p;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = n < p.N;
+  const int64_t nn = live ? n : p.N - 1;
+  float kf[DLC_MAX_KNOTS];
+  {
+    const float* g = a.kf + (p.kf_per_env ? nn * p.nk : 0);
+#pragma unroll
+    for (int k = 0; k < DLC_MAX_KNOTS; ++k) kf[k] = k < p.nk ? g[k] : 0.f;
+  }
+  const float k0 = a.K[nn * 3 + 0], k1 = a.K[nn * 3 + 1], k2 = a.K[nn * 3 + 2];
+  const float dec = p.pid_decay;
+  const float c4pi = 12.566370614359172f;
+  float* ws = a.ws + nn;
+  const int64_t N = p.N;
+  // ---- forward (train_controller.py:44-67), checkpointing the state at the start of every step
+  float P = a.reset_pressure, V = p.min_volume, cp = 0.f, ci = 0.f, cd = 0.f, time = 0.f, total = 0.f;
+  for (int t = 0; t < p.T; ++t) {
+    P += a.noise;                                                  // :51-53 (the noise also enters the state)
+    float* w = ws + (int64_t)t * 6 * N;
+    w[0] = P; w[N] = V; w[2 * N] = cp; w[3 * N] = ci; w[4 * N] = cd; w[5 * N] = time;
+    const float xo = fmod_pos(time, p.period);
+    const float err = interp_knots<NK>(p, kf, xo) - P;
+    const float np_ = err, ni = ci + dec * (err - ci), nd = cd + dec * ((err - cp) - cd);
+    cp = np_; ci = ni; cd = nd;
+    const float u_raw = (np_ * k0 + ni * k1) + nd * k2;
+    const float u = fminf(fmaxf(u_raw, 0.f), 100.f);
+    const bool inhale = xo <= p.xp_in;                             // u_out == 0
+    const float vraw = tanhf(0.03f * (3.0f * u - 130.f)) + 1.0f;
+    const float valve = fminf(fmaxf(vraw, 0.f), 1.72f);
+    float flow = fminf(fmaxf(valve * p.R, 0.f), 2.0f);
+    if (P > p.peep_valve) flow -= (inhale ? 0.0f : 1.0f) * 0.05f * P;
+    const float diff = interp_knots<NK>(p, kf, fmod_pos(a.tt[t], p.period)) - P;
+    if (inhale) total += a.loss_kind == DLC_LOSS_L1 ? fabsf(diff) : diff * diff;
+    V += flow * p.dt;
+    if (p.leak) V += p.leak_coef * (p.min_volume - V);
+    const float r = cbrtf(__fdiv_rn(3.0f * V, c4pi));
+    const float q = __fdiv_rn(p.r0, r), q2 = q * q;
+    P = p.P0 + __fdiv_rn(p.PC * (1.0f - q2 * q2 * q2), p.r0_sq * r);
+    time += p.dt;
+  }
+  // ---- backward: adjoints of (P, V, p, i, d) after step t, walked down to t = 0
+  float lP = 0.f, lV = 0.f, lp = 0.f, li = 0.f, ld = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  for (int t = p.T - 1; t >= 0; --t) {
+    const float* w = ws + (int64_t)t * 6 * N;
+    const float Pi = w[0], Vi = w[N], pi_ = w[2 * N], ii = w[3 * N], di = w[4 * N], ti = w[5 * N];
+    // recompute the step's intermediates
+    const float xo = fmod_pos(ti, p.period);
+    const float err = interp_knots<NK>(p, kf, xo) - Pi;
+    const float np_ = err, ni = ii + dec * (err - ii), nd = di + dec * ((err - pi_) - di);
+    const float u_raw = (np_ * k0 + ni * k1) + nd * k2;
+    const float u = fminf(fmaxf(u_raw, 0.f), 100.f);
+    const bool inhale = xo <= p.xp_in;
+    const float th = tanhf(0.03f * (3.0f * u - 130.f));
+    const float vraw = th + 1.0f;
+    const float vr = fminf(fmaxf(vraw, 0.f), 1.72f) * p.R;
+    float flow = fminf(fmaxf(vr, 0.f), 2.0f);
+    const bool valve_open = Pi > p.peep_valve;
+    if (valve_open) flow -= (inhale ? 0.0f : 1.0f) * 0.05f * Pi;
+    float Vn = Vi + flow * p.dt;
+    if (p.leak) Vn += p.leak_coef * (p.min_volume - Vn);
+    const float r = cbrtf(__fdiv_rn(3.0f * Vn, c4pi));
+    // P' = P0 + (PC / r0^2) (1/r - r0^6 / r^7)
+    const float ir = __fdiv_rn(1.0f, r), ir2 = ir * ir, q = p.r0 * ir, q2 = q * q, q6 = q2 * q2 * q2;
+    const float dPdr = __fdiv_rn(p.PC, p.r0_sq) * (-ir2 + 7.0f * q6 * ir2);
+    const float drdV = __fdiv_rn(r, 3.0f * Vn);
+    float gV = lV + lP * dPdr * drdV;
+    if (p.leak) gV *= (1.0f - p.leak_coef);
+    const float gflow = p.dt * gV;
+    float nlP = 0.f;
+    if (valve_open) nlP -= (inhale ? 0.0f : 1.0f) * 0.05f * gflow;
+    const float gvr = (vr >= 0.f && vr <= 2.0f) ? gflow : 0.f;        // clamp: gradient passes inside the range
+    const float gvraw = (vraw >= 0.f && vraw <= 1.72f) ? gvr * p.R : 0.f;
+    const float gu = 0.09f * (gvraw * (1.0f - th * th));               // d tanh(0.03 (3u - 130)) / du
+    const float guraw = (u_raw >= 0.f && u_raw <= 100.f) ? gu : 0.f;
+    g0 = fmaf(guraw, np_, g0); g1 = fmaf(guraw, ni, g1); g2 = fmaf(guraw, nd, g2);
+    const float gp = lp + k0 * guraw, gi = li + k1 * guraw, gd = ld + k2 * guraw;
+    const float gerr = gp + dec * gi + dec * gd;
+    nlP -= gerr;                                                       // err = target - P
+    if (inhale) {
+      const float diff = interp_knots<NK>(p, kf, fmod_pos(a.tt[t], p.period)) - Pi;
+      nlP -= a.loss_kind == DLC_LOSS_L1 ? (diff > 0.f ? 1.0f : (diff < 0.f ? -1.0f : 0.f)) : 2.0f * diff;
+    }
+    lP = nlP; lV = gV; lp = -dec * gd; li = (1.0f - dec) * gi; ld = (1.0f - dec) * gd;
+  }
+  if (live) {
+    a.loss_out[n] = total;
+    a.grad_out[n * 3 + 0] = g0; a.grad_out[n * 3 + 1] = g1; a.grad_out[n * 3 + 2] = g2;
+  }
+  if (a.sums_out) {   // block reduction, one atomic per block and component
+    __shared__ double red[4][4];
+    double v[4] = {live ? (double)total : 0.0, live ? (double)g0 : 0.0, live ? (double)g1 : 0.0,
+                   live ? (double)g2 : 0.0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    if ((threadIdx.x & 31) == 0)
+      for (int c = 0; c < 4; ++c) red[c][threadIdx.x >> 5] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 4) atomicAdd(&a.sums_out[threadIdx.x], (red[threadIdx.x][0] + red[threadIdx.x][1]) +
+                                                                  (red[threadIdx.x][2] + red[threadIdx.x][3]));
+  }
+}
+
+}  // namespace dlc
+
+extern "C" size_t dlc_lung_pid_grad_workspace_bytes(const DlcLungParams* p) {
+  if (!p || p->N <= 0 || p->T <= 0) return 0;
+  return (size_t)p->T * 6 * (size_t)p->N * sizeof(float);
+}
+
+extern "C" int32_t dlc_lung_pid_grad_f32(const DlcLungParams* p, const float* K, const float* kf, const float* tt,
+                                         int32_t loss_kind, float noise, float reset_pressure, float* loss_out,
+                                         float* gradK_out, double* sums_out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  using namespace dlc;
+  if (!p) return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: NULL params");
+  if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: negative N or T");
+  if (p->sim != DLC_SIM_BALLOON) return fail(DLC_ERR_SHAPE, "dlc_lung_pid_grad_f32: BalloonLung only");
+  if (p->nk < 2 || p->nk > DLC_MAX_KNOTS) return fail(DLC_ERR_SHAPE, "dlc_lung_pid_grad_f32: 2 <= nk <= 16 knots");
+  if (loss_kind != DLC_LOSS_L1 && loss_kind != DLC_LOSS_L2) return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: bad loss");
+  if (p->N == 0) return DLC_OK;
+  if (!K || !kf || (!tt && p->T > 0) || !loss_out || !gradK_out)
+    return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: NULL buffer");
+  if (p->T > 0 && (!workspace || workspace_bytes < dlc_lung_pid_grad_workspace_bytes(p)))
+    return fail(DLC_ERR_WORKSPACE, "dlc_lung_pid_grad_f32: workspace smaller than dlc_lung_pid_grad_workspace_bytes()");
+  LungGradArgs a;
+  a.p = *p; a.K = K; a.kf = kf; a.tt = tt; a.loss_kind = loss_kind; a.noise = noise; a.reset_pressure = reset_pressure;
+  a.loss_out = loss_out; a.grad_out = gradK_out; a.sums_out = sums_out; a.ws = (float*)workspace;
+  const unsigned grid = (unsigned)((p->N + 127) / 128);
+  if (p->nk == 7) lung_pid_grad_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  else lung_pid_grad_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return cuda_status(cudaGetLastError(), "lung_pid_grad_kernel launch");
+}

@@ -274,3 +274,22 @@ def lds_shared_lqr_rollout(G_packed, x, T, m, W=None, keep_costs=True):
                                                        _abi.current_stream_ptr())
     _abi.check(rc, "dlc_lds_shared_lqr_rollout_f32")
     return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, status=status)
+
+
+def lung_pid_value_and_grad(params, K, kf, tt, loss_kind=0, noise=0.0, reset_pressure=0.0, want_sums=True):
+    """``dlc_lung_pid_grad_f32``: per-breath loss[N], dloss/dK[N,3] and their batch sums [4] (fp64)."""
+    N, T = params.N, params.T
+    dev = K.device
+    _f32(K, "K", (N, 3)); _f32(kf, "kf"); _f32(tt, "tt", (T,))
+    loss = torch.empty(N, device=dev)
+    grad = torch.empty(N, 3, device=dev)
+    sums = torch.zeros(4, dtype=torch.float64, device=dev) if want_sums else None
+    nbytes = _abi.lib().dlc_lung_pid_grad_workspace_bytes(ctypes.byref(params))
+    ws = torch.empty(max(nbytes, 4) // 4, device=dev)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().dlc_lung_pid_grad_f32(ctypes.byref(params), _abi.ptr(K), _abi.ptr(kf), _abi.ptr(tt),
+                                              int(loss_kind), float(noise), float(reset_pressure), _abi.ptr(loss),
+                                              _abi.ptr(grad), _abi.ptr(sums), _abi.ptr(ws), ws.numel() * 4,
+                                              _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lung_pid_grad_f32")
+    return loss, grad, sums

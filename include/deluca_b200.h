@@ -198,6 +198,30 @@ typedef struct DlcLungBuffers {
 int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLungBuffers* b, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Reverse mode through the ventilator episode: value and gradient of
+ * train_controller.rollout (deluca/lung/utils/scripts/train_controller.py:33-67) with respect to the PID
+ * gains, i.e. what jax.value_and_grad(rollout_parallel) (:151-153) computes for the lung PID controller on
+ * BalloonLung.  Every breath starts from sim.reset() / controller.init(waveform) as in the reference;
+ *     loss_n = sum_i [u_out_i == 0] * loss_fn(waveform.at(tt[i]), pressure_i),  loss_fn = |x - y| or (x - y)^2.
+ * Forward pass stores six floats per step in the workspace, the backward pass is a hand-derived adjoint
+ * (checked against torch.autograd in tests).  p->sim must be DLC_SIM_BALLOON; p->T = len(tt).
+ * ------------------------------------------------------------------------------------ */
+#define DLC_LOSS_L1 0
+#define DLC_LOSS_L2 1
+size_t dlc_lung_pid_grad_workspace_bytes(const DlcLungParams* p);
+int32_t dlc_lung_pid_grad_f32(const DlcLungParams* p,
+                              const float* K,        /* [N,3] PID gains */
+                              const float* kf,       /* [N,nk] or [nk] knot ordinates (p->kf_per_env) */
+                              const float* tt,       /* [T] loss time stamps (jnp.linspace(0, duration, T)) */
+                              int32_t loss_kind,     /* DLC_LOSS_* */
+                              float noise,           /* use_noise * (mean + std * z): added to the pressure each step */
+                              float reset_pressure,  /* sim.reset_normalized_peep */
+                              float* loss_out,       /* [N] */
+                              float* gradK_out,      /* [N,3] d loss_n / d K_n */
+                              double* sums_out,      /* [4] += (sum loss, sum dK0, sum dK1, sum dK2) or NULL; caller zeroes */
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Generic leaky PID agent (deluca/agents/_pid.py:20-48), T steps over a given error series:
  *     P = e; I += decay (e - I); D += decay (e - P_prev - D); u = K_P P + K_I I + K_D D,
  *     decay = dt / (dt + RC) (:30-32).

@@ -61,6 +61,31 @@ for name, Env in (("balloon", BalloonLung), ("delay", DelayLung)):
         del p, b, series
         torch.cuda.empty_cache()
 
+# ---- 8(f) rank 1: value + gradient of train_controller.rollout w.r.t. the PID gains, 2^20 breaths x T=29
+from deluca_b200 import _abi
+from deluca_b200.lung.core import DEFAULT_DT
+import ctypes
+env = BalloonLung.create()
+pg = _abi.DlcLungParams()
+pg.N, pg.T, pg.mode = N, 29, 0
+kx, kf, period, xp_in = wave.knots(N=N, device=dev)
+pg.nk = len(kx)
+for i, v in enumerate(kx):
+    pg.kx[i] = v
+pg.kf_per_env = int(kf.dim() == 2)
+pg.period, pg.xp_in, pg.default_dt, pg.pid_decay = period, xp_in, DEFAULT_DT, 0.03 / 0.53
+_launch.sim_params(env, pg)
+Kd = K.to(dev).contiguous()
+ttd = torch.linspace(0, 0.87, 29, device=dev)
+ms = timeit(lambda: fused.lung_pid_value_and_grad(pg, Kd, kf, ttd))
+byts = 2 * 6 * 4.0 * N * 29   # checkpoint written by the forward pass and read by the backward pass
+out["lung_balloon_pid_value_and_grad_T29"] = {
+    "envs": N, "T": 29, "kernel_ms": ms, "env_steps_per_s": N * 29 / (ms * 1e-3),
+    "roofline": {"bound": "hbm", "achieved": byts / (ms * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s",
+                 "frac": byts / (ms * 1e-3) / 1e9 / HBM, "bytes_per_env_step": 48}}
+del Kd, kf
+torch.cuda.empty_cache()
+
 # ---- config 3: Pendulum / Cartpole + iLQR, IGPC: 4096 trajectories x H=200 x 20 iterations
 N, H, T = 4096, 200, 20
 for name, Env in (("pendulum", Pendulum), ("cartpole", Cartpole)):

@@ -1,0 +1,66 @@
+"""Committed fixtures (tests/golden/): the reference's own known answers pin the oracle; the frozen oracle
+vectors pin both the oracle (CPU) and the CUDA kernels (GPU)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lds as O
+from oracle import lung as OL
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_reproduces_reference_known_answers():
+    k = json.load(open(os.path.join(G, "reference_known_answers.json")))
+    kx, kf, period = OL.waveform_knots(35.0, 5.0)
+    for t, v in zip(k["waveform_at"]["t"], k["waveform_at"]["value"]):
+        assert float(OL.waveform_at(np.array([t], np.float32), kx, kf, period)[0]) == v
+    for t, v in zip(k["waveform_is_in"]["t"], k["waveform_is_in"]["value"]):
+        assert bool(OL.waveform_is_in(np.float32(t), 3.0)) == v
+    assert OL.lung_env_time(k["lung_env_time"]["steps"]) == np.float32(k["lung_env_time"]["value"])
+    assert OL.proper_time(np.float32(np.inf)) == 0.0 and OL.proper_time(np.float32(10.0)) == 10.0
+    assert OL.controller_decay(0.5) == math.inf and OL.controller_decay(1.0) == 0.0
+    assert OL.controller_decay(1.5) == np.float32(5) * (1 - np.exp(np.float32(5) * (np.float32(1.5) - np.float32(1.5))))
+
+
+def test_oracle_matches_its_frozen_vectors():
+    z = np.load(os.path.join(G, "oracle_lds_gpc_small.npz"))
+    r = O.rollout_lds(z["A"], z["B"], z["K"], z["x0"], z["W"], "gpc", H=3, HH=10, lr_scale=1e-4, dtype=np.float64)
+    np.testing.assert_allclose(r["costs"], z["costs"], rtol=1e-12)
+    np.testing.assert_allclose(r["state"]["M"], z["M"], rtol=1e-10, atol=1e-15)
+    z = np.load(os.path.join(G, "oracle_lung_small.npz"))
+    for sim in ("balloon", "delay"):
+        rr = OL.run_controller_scan(z["K"], z["pip"], 5.0, T=29, sim=sim, dtype=np.float32)
+        for k, v in rr["timeseries"].items():
+            np.testing.assert_allclose(v, z[f"{sim}_{k}"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_kernels_match_the_frozen_vectors():
+    from deluca_b200.fused import lds_rollout
+    from deluca_b200.lung.controllers import PID
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung, DelayLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    z = np.load(os.path.join(G, "oracle_lds_gpc_small.npz"))
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+    T = z["W"].shape[0]
+    for variant in (0, 1, 5):
+        r = lds_rollout(t(z["A"]), t(z["B"]), t(z["K"]), t(z["x0"]), T, policy="gpc", W=t(z["W"]), H=3, HH=10,
+                        lr_scale=1e-4, kernel_variant=variant)
+        c = r.costs.cpu().numpy()
+        assert (np.abs(c - z["costs"]) <= 1e-4 * np.maximum(np.abs(z["costs"]), 1e-2 * z["costs"].mean())).all()
+        np.testing.assert_allclose(r.M.cpu().numpy(), z["M"], rtol=1e-3, atol=1e-5 * np.abs(z["M"]).max())
+    z = np.load(os.path.join(G, "oracle_lung_small.npz"))
+    for sim, Env in (("balloon", BalloonLung), ("delay", DelayLung)):
+        res = run_controller_scan(PID.create(params=torch.tensor(z["K"])), T=29, env=Env.create(),
+                                  waveform=BreathWaveform.create(pip=torch.tensor(z["pip"]), peep=5.0),
+                                  init_controller=True)
+        for k in ("u_in", "pressure", "target", "timestamp", "u_out"):
+            want = z[f"{sim}_{k}"].T
+            got = res["timeseries"][k].cpu().numpy()
+            assert (np.abs(got - want) <= 1e-4 * np.maximum(np.abs(want), max(np.abs(want).mean(), 1e-3))).all(), (sim, k)

@@ -79,6 +79,7 @@ class DlcPlanParams(ctypes.Structure):
         ("N", ctypes.c_int64), ("H", ctypes.c_int32), ("T", ctypes.c_int32),
         ("env_true", DlcEnvSpec), ("env_sim", DlcEnvSpec),
         ("q", ctypes.c_float * 8), ("goal", ctypes.c_float * 8), ("r", ctypes.c_float * 4),
+        ("goal_u", ctypes.c_float * 4),
         ("algo", ctypes.c_int32), ("backtracking", ctypes.c_int32), ("fix_backtracking", ctypes.c_int32),
         ("n_alpha", ctypes.c_int32), ("w_is", ctypes.c_int32), ("alpha0", ctypes.c_float), ("lr", ctypes.c_float),
     ]

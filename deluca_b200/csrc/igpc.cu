@@ -84,6 +84,54 @@ struct Model<DLC_ENV_CARTPOLE> {  // _cartpole.py:60-89, intent-fixed (SURVEY A-
   }
 };
 
+template <>
+struct Model<DLC_ENV_QUADROTOR> {  // deluca/envs/classic/_planar_quadrotor.py:92-104 (explicit Euler, wind field)
+  static constexpr int D = 6, M = 2;
+  float im, g, dt, wind, kth;
+  int wind_kind;
+  __device__ explicit Model(const DlcEnvSpec& s) {
+    const float m = s.p[0], l = s.p[1];
+    im = 1.0f / m;
+    g = s.p[2];
+    dt = s.p[3];
+    wind = s.p[4];
+    wind_kind = (int)s.p[5];
+    kth = l / (m * l * l);
+  }
+  __device__ void step(const float* x, const float* u, float* xn) const {
+    float sn, cs;
+    sincosf(x[2], &sn, &cs);
+    const float wx = wind_kind == 0 ? wind * x[0] : wind * 0.70710678118654752f;
+    const float wy = wind_kind == 0 ? wind * x[1] : wind * 0.70710678118654752f;
+    const float tu = u[0] + u[1];
+    const float xdd = -tu * sn * im + wx * im;
+    const float ydd = tu * cs * im - g + wy * im;
+    const float tdd = kth * (u[1] - u[0]);
+    xn[0] = x[0] + x[3] * dt; xn[1] = x[1] + x[4] * dt; xn[2] = x[2] + x[5] * dt;
+    xn[3] = x[3] + xdd * dt;  xn[4] = x[4] + ydd * dt;  xn[5] = x[5] + tdd * dt;
+  }
+  __device__ void jac(const float* x, const float* u, float* Fx, float* Fu) const {
+    float sn, cs;
+    sincosf(x[2], &sn, &cs);
+    const float tu = u[0] + u[1];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Fx[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Fx[i * 6 + i] = 1.f;
+    Fx[0 * 6 + 3] = dt; Fx[1 * 6 + 4] = dt; Fx[2 * 6 + 5] = dt;
+    const float dw = wind_kind == 0 ? wind * im * dt : 0.f;
+    Fx[3 * 6 + 0] = dw;
+    Fx[3 * 6 + 2] = -tu * cs * im * dt;
+    Fx[4 * 6 + 1] = dw;
+    Fx[4 * 6 + 2] = -tu * sn * im * dt;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Fu[i] = 0.f;
+    Fu[3 * 2 + 0] = -sn * im * dt; Fu[3 * 2 + 1] = -sn * im * dt;
+    Fu[4 * 2 + 0] = cs * im * dt;  Fu[4 * 2 + 1] = cs * im * dt;
+    Fu[5 * 2 + 0] = -kth * dt;     Fu[5 * 2 + 1] = kth * dt;
+  }
+};
+
 template <int D, int M>
 __device__ __forceinline__ float quad_cost(const DlcPlanParams& p, const float* x, const float* u) {
   float cx = 0.f, cu = 0.f;
@@ -93,7 +141,10 @@ __device__ __forceinline__ float quad_cost(const DlcPlanParams& p, const float* 
     cx = fmaf(p.q[i] * e, e, cx);
   }
 #pragma unroll
-  for (int c = 0; c < M; ++c) cu = fmaf(p.r[c] * u[c], u[c], cu);
+  for (int c = 0; c < M; ++c) {
+    const float e = u[c] - p.goal_u[c];
+    cu = fmaf(p.r[c] * e, e, cu);
+  }
   return cx + cu;
 }
 
@@ -295,7 +346,7 @@ __device__ __forceinline__ void cost_ders(const DlcPlanParams& p, const float* x
   }
 #pragma unroll
   for (int c = 0; c < M; ++c) {
-    cu[c] = (2.0f * p.r[c]) * u[c];
+    cu[c] = (2.0f * p.r[c]) * (u[c] - p.goal_u[c]);
 #pragma unroll
     for (int e = 0; e < M; ++e) cuu[c * M + e] = c == e ? 2.0f * p.r[c] : 0.f;
   }
@@ -657,7 +708,7 @@ static int32_t check_plan(const DlcPlanParams* p, const char* who) {
   if (!p) return fail(DLC_ERR_ARG, "NULL params");
   if (p->N < 0 || p->H < 1 || p->T < 0) return fail(DLC_ERR_ARG, "bad N / H / T");
   if (p->env_true.kind != p->env_sim.kind) return fail(DLC_ERR_SHAPE, "env_true and env_sim must be the same kind of env");
-  if (p->env_true.kind != DLC_ENV_PENDULUM && p->env_true.kind != DLC_ENV_CARTPOLE)
+  if (p->env_true.kind < DLC_ENV_PENDULUM || p->env_true.kind > DLC_ENV_QUADROTOR)
     return fail(DLC_ERR_SHAPE, "unknown env kind");
   (void)who;
   return DLC_OK;
@@ -670,7 +721,8 @@ using namespace dlc;
 #define DLC_DISPATCH_ENV(kind, KERNEL, grid, st, args)                                   \
   do {                                                                                    \
     if ((kind) == DLC_ENV_PENDULUM) KERNEL<DLC_ENV_PENDULUM><<<grid, 128, 0, st>>>(args); \
-    else KERNEL<DLC_ENV_CARTPOLE><<<grid, 128, 0, st>>>(args);                            \
+    else if ((kind) == DLC_ENV_CARTPOLE) KERNEL<DLC_ENV_CARTPOLE><<<grid, 128, 0, st>>>(args); \
+    else KERNEL<DLC_ENV_QUADROTOR><<<grid, 128, 0, st>>>(args);                           \
   } while (0)
 
 extern "C" int32_t dlc_env_rollout_f32(const DlcPlanParams* p, int32_t use_sim_env, const float* U_old,
@@ -744,7 +796,8 @@ extern "C" int32_t dlc_riccati_backward_f32(int64_t N, int32_t H, int32_t d, int
 
 extern "C" size_t dlc_plan_workspace_bytes(const DlcPlanParams* p) {
   if (!p || p->N <= 0 || p->H < 1) return 0;
-  const int d = p->env_true.kind == DLC_ENV_PENDULUM ? 3 : 4, m = 1;
+  const int d = p->env_true.kind == DLC_ENV_PENDULUM ? 3 : (p->env_true.kind == DLC_ENV_CARTPOLE ? 4 : 6);
+  const int m = p->env_true.kind == DLC_ENV_QUADROTOR ? 2 : 1;
   return (size_t)p->N * ((size_t)(p->H + 1) * d + (size_t)p->H * m) * sizeof(float);
 }
 

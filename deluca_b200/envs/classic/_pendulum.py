@@ -21,8 +21,11 @@ class QuadCost:
     """c(x, u, env) = sum q (x - goal)^2 + sum r u^2: the cost the fused igpc kernels implement
     (the reference ships none for this path; q = 1, r = 0.1 is this repo's stated choice)."""
 
-    def __init__(self, goal, q=1.0, r=0.1):
-        self.goal, self.q, self.r = goal, q, r
+    def __init__(self, goal, q=1.0, r=0.1, goal_action=None):
+        self.goal, self.q, self.r, self.goal_action = goal, q, r, goal_action
+
+    def action_goal(self, m):
+        return [0.0] * m if self.goal_action is None else [float(x) for x in self.goal_action]
 
     def vectors(self, d, m):
         ex = lambda v, n: [float(x) for x in (v if hasattr(v, "__len__") else [v] * n)]
@@ -32,8 +35,9 @@ class QuadCost:
         x = state.arr if hasattr(state, "arr") else state
         q, r, goal = self.vectors(x.shape[-1], u.shape[-1])
         g = torch.tensor(goal, device=x.device)
+        gu = torch.tensor(self.action_goal(u.shape[-1]), device=x.device)
         return ((x - g) ** 2 * torch.tensor(q, device=x.device)).sum(-1) + (
-            u ** 2 * torch.tensor(r, device=x.device)).sum(-1)
+            (u - gu) ** 2 * torch.tensor(r, device=x.device)).sum(-1)
 
 
 class _ClassicEnv(Env):
@@ -44,6 +48,8 @@ class _ClassicEnv(Env):
         single = arr.dim() == 1
         x = arr.reshape(-1, self.state_dim).contiguous()
         u = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(-1, 1, self.action_dim)
+        if u.shape[0] not in (1, x.shape[0]):
+            raise ValueError("action batch does not match the state batch")
         u = u.expand(x.shape[0], 1, self.action_dim).contiguous()
         p = fused.plan_params(self, self, QuadCost([0.0] * self.state_dim, 0.0, 0.0), x.shape[0], 1)
         X, _, _ = fused.env_rollout(p, u, x)

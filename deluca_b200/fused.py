@@ -150,10 +150,11 @@ def plan_params(env_true, env_sim, cost, N, H, T=0, algo=0, backtracking=True, f
             dst.p[i] = v
     d, m = env_true.state_dim, env_true.action_dim
     q, r, goal = cost.vectors(d, m)
+    goal_u = cost.action_goal(m)
     for i in range(d):
         p.q[i], p.goal[i] = q[i], goal[i]
     for i in range(m):
-        p.r[i] = r[i]
+        p.r[i], p.goal_u[i] = r[i], goal_u[i]
     p.algo, p.backtracking, p.fix_backtracking, p.n_alpha = algo, int(backtracking), int(fix_backtracking), n_alpha
     p.w_is, p.alpha0, p.lr = w_is, alpha0, lr
     return p

@@ -247,12 +247,14 @@ int32_t dlc_pid_f32(int64_t N, int32_t T, float decay,
  *                              the whole outer loop incl. backtracking stays on the device; the accept
  *                              order of the reference's sequential `if cC <= c: break` is preserved.
  * Envs: Pendulum (deluca/envs/classic/_pendulum.py:54-73, as written) and Cartpole
- * (_cartpole.py:60-89 with the intent-fixing waiver SURVEY A-7).  Cost: c(x,u) = sum q_i (x_i-goal_i)^2
- * + sum r_j u_j^2 (the reference ships no cost for this path).
+ * (_cartpole.py:60-89 with the intent-fixing waiver SURVEY A-7) and PlanarQuadrotor (8(f) rank 2).
+ * Cost: c(x,u) = sum q_i (x_i-goal_i)^2 + sum r_j (u_j-goal_u_j)^2 (the reference ships no cost for this path).
  * Layouts are the vmapped reference shapes: X[N,H+1,d], U[N,H,m], k[N,H,m], K[N,H,m,d].
  * ------------------------------------------------------------------------------------ */
 #define DLC_ENV_PENDULUM 0 /* d = 3, m = 1; params: m, l, g, max_torque, dt */
 #define DLC_ENV_CARTPOLE 1 /* d = 4, m = 1; params: m, M, l, g, dt, offset */
+#define DLC_ENV_QUADROTOR 2 /* PlanarQuadrotor (deluca/envs/classic/_planar_quadrotor.py:51-104): d = 6, m = 2;
+                               params: m, l, g, dt, wind, wind_kind (0 = dissipative, 1 = constant) */
 #define DLC_PLAN_MAXD 8
 #define DLC_PLAN_MAXM 4
 #define DLC_ALGO_ILQR 0
@@ -274,6 +276,7 @@ typedef struct DlcPlanParams {
   DlcEnvSpec env_true; /* the env rolled out */
   DlcEnvSpec env_sim;  /* the model that is linearised (== env_true for iLQR) */
   float q[DLC_PLAN_MAXD], goal[DLC_PLAN_MAXD], r[DLC_PLAN_MAXM]; /* quadratic cost */
+  float goal_u[DLC_PLAN_MAXM]; /* action target of the cost (e.g. PlanarQuadrotor.goal_action = hover thrust) */
   int32_t algo;        /* DLC_ALGO_* */
   int32_t backtracking;
   int32_t fix_backtracking; /* iLQR only: 0 = as written (candidates use alpha, ilqr.py:58-67), 1 = alphaC */

@@ -95,23 +95,77 @@ class Cartpole:
         return np.broadcast_to(A, (N, 4, 4)).copy(), np.broadcast_to(B, (N, 4, 1)).copy()
 
 
-class QuadCost:
-    """c(x,u) = sum_i q_i (x_i - goal_i)^2 + sum_j r_j u_j^2  (this repo's stated choice)."""
+class PlanarQuadrotor:
+    """``deluca/envs/classic/_planar_quadrotor.py:51-104``: explicit Euler, wind field
+    ``dissipative`` (wind * x, wind * y) or ``constant`` (wind * cos(pi/4), wind * sin(pi/4))."""
+    d, m = 6, 2
 
-    def __init__(self, goal, q=1.0, r=0.1):
+    def __init__(self, m=0.1, l=0.2, g=9.81, dt=0.05, H=100, wind=0.0, wind_kind="dissipative",
+                 goal_state=(0.0,) * 6):
+        self.mass, self.l, self.g, self.dt, self.H, self.wind, self.wind_kind = m, l, g, dt, H, wind, wind_kind
+        self.goal_state = np.asarray(goal_state)
+        self.goal_action = np.array([m * g / 2.0, m * g / 2.0])            # :73
+
+    def init(self, N, dtype):
+        x = np.zeros((N, 6), dtype=dtype)
+        x[:, 0] = x[:, 1] = 1.0                                            # :87
+        return x
+
+    def step(self, x, u):
+        c = x.dtype.type
+        m, g, l, dt = c(self.mass), c(self.g), c(self.l), c(self.dt)
+        if self.wind_kind == "dissipative":
+            wx, wy = c(self.wind) * x[:, 0], c(self.wind) * x[:, 1]
+        else:
+            wx = wy = np.full(x.shape[0], c(self.wind * np.cos(np.pi / 4.0)))
+        th = x[:, 2]
+        tu = u[:, 0] + u[:, 1]
+        xdd = -tu * np.sin(th) / m + wx / m                                # :97
+        ydd = tu * np.cos(th) / m - g + wy / m                             # :98
+        tdd = l * (u[:, 1] - u[:, 0]) / (m * l ** 2)                       # :99
+        dot = np.stack([x[:, 3], x[:, 4], x[:, 5], xdd, ydd, tdd], axis=1)
+        return (x + dot * dt).astype(x.dtype)                              # :101
+
+    def jac(self, x, u):
+        c = x.dtype.type
+        N = x.shape[0]
+        m, l, dt = c(self.mass), c(self.l), c(self.dt)
+        th, tu = x[:, 2], u[:, 0] + u[:, 1]
+        Fx = np.broadcast_to(np.eye(6, dtype=x.dtype), (N, 6, 6)).copy()
+        Fx[:, 0, 3] = Fx[:, 1, 4] = Fx[:, 2, 5] = dt
+        if self.wind_kind == "dissipative":
+            Fx[:, 3, 0] = Fx[:, 4, 1] = c(self.wind) / m * dt
+        Fx[:, 3, 2] = -tu * np.cos(th) / m * dt
+        Fx[:, 4, 2] = -tu * np.sin(th) / m * dt
+        Fu = np.zeros((N, 6, 2), dtype=x.dtype)
+        Fu[:, 3, 0] = Fu[:, 3, 1] = -np.sin(th) / m * dt
+        Fu[:, 4, 0] = Fu[:, 4, 1] = np.cos(th) / m * dt
+        Fu[:, 5, 0], Fu[:, 5, 1] = -l / (m * l ** 2) * dt, l / (m * l ** 2) * dt
+        return Fx, Fu
+
+
+class QuadCost:
+    """c(x,u) = sum_i q_i (x_i - goal_i)^2 + sum_j r_j (u_j - goal_u_j)^2  (this repo's stated choice)."""
+
+    def __init__(self, goal, q=1.0, r=0.1, goal_action=None):
         self.goal, self.q, self.r = np.asarray(goal, dtype=np.float64), q, r
+        self.goal_action = None if goal_action is None else np.asarray(goal_action, dtype=np.float64)
+
+    def _du(self, u):
+        return u if self.goal_action is None else u - self.goal_action.astype(u.dtype)
 
     def __call__(self, x, u):
         c = x.dtype.type
         dx = x - self.goal.astype(x.dtype)
-        return c(self.q) * (dx * dx).sum(1) + c(self.r) * (u * u).sum(1)
+        du = self._du(u)
+        return c(self.q) * (dx * dx).sum(1) + c(self.r) * (du * du).sum(1)
 
     def ders(self, x, u):
         c = x.dtype.type
         N, d = x.shape
         m = u.shape[1]
         c_x = c(2 * self.q) * (x - self.goal.astype(x.dtype))
-        c_u = c(2 * self.r) * u
+        c_u = c(2 * self.r) * self._du(u)
         c_xx = np.broadcast_to(c(2 * self.q) * np.eye(d, dtype=x.dtype), (N, d, d))
         c_uu = np.broadcast_to(c(2 * self.r) * np.eye(m, dtype=x.dtype), (N, m, m))
         return c_x, c_u, c_xx, c_uu

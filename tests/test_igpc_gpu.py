@@ -19,7 +19,13 @@ def _np(t):
 
 
 def _envs(kind, H):
-    from deluca_b200.envs.classic import Cartpole, Pendulum, QuadCost
+    from deluca_b200.envs.classic import Cartpole, Pendulum, PlanarQuadrotor, QuadCost
+    if kind == "quadrotor":
+        o_true, o_sim = OG.PlanarQuadrotor(H=H, wind=0.1), OG.PlanarQuadrotor(H=H)
+        d_true, d_sim = PlanarQuadrotor.create(H=H, wind=0.1), PlanarQuadrotor.create(H=H)
+        oc = OG.QuadCost(o_sim.goal_state, 1.0, 0.1, goal_action=o_sim.goal_action)
+        dc = QuadCost(list(o_sim.goal_state), 1.0, 0.1, goal_action=list(o_sim.goal_action))
+        return o_true, o_sim, oc, d_true, d_sim, dc
     if kind == "pendulum":
         o_true, o_sim = OG.Pendulum(H=H, m=1.1), OG.Pendulum(H=H)
         d_true, d_sim = Pendulum.create(H=H, m=1.1), Pendulum.create(H=H)
@@ -36,7 +42,7 @@ def _start(o_env, N, seed=0):
     return (o_env.init(N, np.float32) + 0.05 * rng.standard_normal((N, o_env.d))).astype(np.float32)
 
 
-@pytest.mark.parametrize("kind", ["pendulum", "cartpole"])
+@pytest.mark.parametrize("kind", ["pendulum", "cartpole", "quadrotor"])
 def test_rollout_linearize_riccati(kind):
     from deluca_b200.envs.classic import PendulumState
     from deluca_b200.igpc.lqr_solver import LQR
@@ -45,7 +51,9 @@ def test_rollout_linearize_riccati(kind):
     o_true, o_sim, oc, d_true, d_sim, dc = _envs(kind, H)
     rng = np.random.default_rng(1)
     x0 = _start(o_sim, N)
-    U0 = (0.3 * rng.standard_normal((N, H, 1))).astype(np.float32)
+    U0 = (0.3 * rng.standard_normal((N, H, o_sim.m))).astype(np.float32)
+    if kind == "quadrotor":
+        U0 = (U0 * 0.1 + o_sim.goal_action).astype(np.float32)
     Xo, Uo, co = OG.rollout(o_sim, oc, U0.astype(np.float64), x0=x0.astype(np.float64))
     X, U, c = rollout(d_sim, dc, _t(U0), start_state=PendulumState(arr=_t(x0)))
     # 1e-4 on a short horizon; over the full horizon the (expansive) pendulum map amplifies float32
@@ -100,14 +108,16 @@ def test_gpc_rollout_matches_oracle(w_is):
         np.testing.assert_allclose(_np(Ug)[ok], Uo[ok], rtol=1e-2, atol=2e-3)
 
 
-@pytest.mark.parametrize("kind,fix", [("pendulum", False), ("pendulum", True), ("cartpole", True)])
+@pytest.mark.parametrize("kind,fix", [("pendulum", False), ("pendulum", True), ("cartpole", True), ("quadrotor", True)])
 def test_ilqr_loop_matches_oracle(kind, fix):
     from deluca_b200.envs.classic import PendulumState
     from deluca_b200.igpc.ilqr import iLQR
     H, N, T = 20, 64, 4
     o_true, o_sim, oc, d_true, d_sim, dc = _envs(kind, H)
     x0 = _start(o_sim, N, 3)
-    U0 = np.zeros((N, H, 1), np.float32)
+    U0 = np.zeros((N, H, o_sim.m), np.float32)
+    if kind == "quadrotor":
+        U0 = U0 + o_sim.goal_action.astype(np.float32)
     Xo, Uo, ko, Ko, co, ao = OG.ilqr(o_sim, oc, U0.astype(np.float64), T, x0=x0.astype(np.float64),
                                      fix_backtracking=fix)
     X, U, k, K, c = iLQR(d_sim, dc, _t(U0), T, start_state=PendulumState(arr=_t(x0)), fix_backtracking=fix)

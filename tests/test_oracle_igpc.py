@@ -127,3 +127,40 @@ def test_igpc_and_ilc_run_and_never_increase_cost():
         assert np.isfinite(c).all() and (c <= c0 + 1e-12).all()
     c = G.ilc_closed(env_true, env_sim, cost, U0, 3, x0=x0)[4]
     assert (c <= c0 + 1e-12).all()
+
+
+def test_planar_quadrotor_jacobians_match_autograd():
+    """deluca/envs/classic/_planar_quadrotor.py:92-104 restated literally in torch."""
+    for kind in ("dissipative", "constant"):
+        env = G.PlanarQuadrotor(wind=0.3, wind_kind=kind)
+        rng = np.random.default_rng(5)
+        x = rng.standard_normal((6, 6))
+        u = 0.5 + 0.2 * rng.standard_normal((6, 2))
+
+        def step_t(xt, ut):
+            xx, yy, th, xd, yd, thd = xt
+            wind = [env.wind * xx, env.wind * yy] if kind == "dissipative" else [
+                env.wind * np.cos(np.pi / 4.0) + 0 * xx, env.wind * np.sin(np.pi / 4.0) + 0 * xx]
+            xdd = -(ut[0] + ut[1]) * torch.sin(th) / env.mass + wind[0] / env.mass
+            ydd = (ut[0] + ut[1]) * torch.cos(th) / env.mass - env.g + wind[1] / env.mass
+            tdd = env.l * (ut[1] - ut[0]) / (env.mass * env.l ** 2)
+            return xt + torch.stack([xd, yd, thd, xdd, ydd, tdd]) * env.dt
+
+        Fx, Fu = env.jac(x, u)
+        for n in range(6):
+            J = torch.autograd.functional.jacobian(step_t, (torch.tensor(x[n]), torch.tensor(u[n])))
+            np.testing.assert_allclose(Fx[n], J[0].numpy(), rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(Fu[n], J[1].numpy(), rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(env.step(x[n:n + 1], u[n:n + 1])[0],
+                                       step_t(torch.tensor(x[n]), torch.tensor(u[n])).numpy(), rtol=1e-12)
+
+
+def test_ilqr_stabilises_the_quadrotor():
+    env = G.PlanarQuadrotor(H=60)
+    cost = G.QuadCost(env.goal_state, 1.0, 0.1, goal_action=env.goal_action)
+    N = 4
+    x0 = env.init(N, np.float64) + 0.05 * np.random.default_rng(0).standard_normal((N, 6))
+    U0 = np.tile(env.goal_action, (N, env.H, 1))
+    _, _, c0 = G.rollout(env, cost, U0, x0=x0)
+    c = G.ilqr(env, cost, U0, 8, x0=x0, fix_backtracking=True)[4]
+    assert (c < 0.5 * c0).all()

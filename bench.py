@@ -30,6 +30,10 @@ WORKLOADS = {
 # The reference default lr_scale=0.005 makes GPC-as-written diverge on the default LDS
 # (tests/test_oracle_lds.py::test_reference_noise_quirk...); 1e-4 keeps every env finite so that
 # the rollout that is timed is also the rollout whose parity is tested.
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
+# `ncu --set full` capture of this same command (profiles/r01_lds_f2_final_full.txt): 26.33 + 2.68 GB
+# against 28.9 GB of algorithmic bytes.  Other workloads / modes have no capture -> null.
+NCU_TRAFFIC_BYTES = {("c2", "hbm"): 26.328579e9 + 2.675452e9}
 LR_SCALE = 1e-4
 W_STD = 0.5
 SEED = 20240
@@ -317,7 +321,11 @@ def main():
                        "l2": "per-step inputs exceed L2" if use_hbm_w else "state is on-chip; costs written once",
                        "parallelism": f"env-sharded x{world}"},
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": ach / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": ach / fp32_peak if fp32_peak else None,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.disturbance))
+                         if not (args.envs or args.horizon) else None,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_lds_f2_final_full.txt)",
+                         "algorithmic_bytes": Bts * N * T,
                          "kernel": "lds_f2_kernel" if (H <= 4 and args.variant in (0, 8, 9)) else "lds_split_kernel", "kernel_ms": kern_ms,
                          "kernel_ms_each": [round(v, 3) for v in kern_each],
                          "flops_per_env_step": F, "bytes_per_env_step": Bts,

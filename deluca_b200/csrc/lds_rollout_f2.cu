@@ -587,11 +587,17 @@ static int32_t launch_f2(const LdsArgs& a, cudaStream_t st) {
 
 bool launch_gpc_f2(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
-  const bool three_ctas = p.kernel_variant == 9;  // 12 warps/SM at 168 regs (for measurement)
+  // Launch shape (measured on B200, config 2): one-warp CTAs x 9 per SM at 217 registers run 39.7 ms, 128 x 2
+  // at 243 registers 42.5 ms, 64 x 5 at 200 registers 57 ms (ptxas trades ILP for registers), 128 x 3 at 168
+  // registers 62 ms (spills).  Default = 32 x 9; kernel_variant 8: 128 x 2, 9: 128 x 3, 10: 64 x 5, 11: 32 x 9.
 #define F2(D_, M_, H_, HH_, L_)                                                          \
   if (p.d == D_ && p.m == M_ && p.H == H_ && p.HH == HH_) {                              \
-    *rc = three_ctas ? launch_f2<D_, M_, H_, HH_, L_, 128, 3>(a, st)                     \
-                     : launch_f2<D_, M_, H_, HH_, L_, 128, 2>(a, st);                    \
+    switch (p.kernel_variant) {                                                          \
+      case 9: *rc = launch_f2<D_, M_, H_, HH_, L_, 128, 3>(a, st); break;                \
+      case 10: *rc = launch_f2<D_, M_, H_, HH_, L_, 64, 5>(a, st); break;                \
+      case 8: *rc = launch_f2<D_, M_, H_, HH_, L_, 128, 2>(a, st); break;                \
+      default: *rc = launch_f2<D_, M_, H_, HH_, L_, 32, 9>(a, st); break;                \
+    }                                                                                    \
     return true;                                                                         \
   }
   F2(10, 3, 3, 10, 2)

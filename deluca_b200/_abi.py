@@ -101,6 +101,11 @@ SYMBOLS = {
     "dlc_lung_pid_grad_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLungParams)]),
     "dlc_lung_pid_grad_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLungParams), _P, _P, _P, ctypes.c_int32,
                                                ctypes.c_float, ctypes.c_float, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    "dlc_lds_lqr_grad_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
+    "dlc_lds_lqr_grad_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int32, _P, _P, _P, _P, _P, ctypes.c_uint64, ctypes.c_int64,
+                                              ctypes.c_int32, ctypes.c_float, _P, _P, _P, _P, _P, ctypes.c_size_t,
+                                              _P]),
     "dlc_pid_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_float] + [_P] * 9),
     "dlc_env_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams), ctypes.c_int32] + [_P] * 10),
     "dlc_linearize_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams), ctypes.c_int32] + [_P] * 10),

@@ -294,3 +294,28 @@ def lung_pid_value_and_grad(params, K, kf, tt, loss_kind=0, noise=0.0, reset_pre
                                               _abi.current_stream_ptr())
     _abi.check(rc, "dlc_lung_pid_grad_f32")
     return loss, grad, sums
+
+
+def lds_lqr_value_and_grad(A, B, K, x0, T, W=None, seed=0, env_offset=0, t0=0, w_std=0.5, want_x0_grad=False):
+    """``dlc_lds_lqr_grad_f32``: loss[N] = sum_t quad_loss(x_t, -K x_t), dloss/dK[N,m,d] (per env), optional
+    dloss/dx0[N,d], and the batch sums [1 + m*d] (fp64)."""
+    _f32(x0, "x0")
+    N, d = x0.shape
+    shared = A.dim() == 2
+    m = B.shape[-1]
+    _f32(A, "A", (d, d) if shared else (N, d, d)); _f32(B, "B", (d, m) if shared else (N, d, m))
+    _f32(K, "K", (m, d) if shared else (N, m, d)); _f32(W, "W", (T, N, d))
+    dev = x0.device
+    loss = torch.empty(N, device=dev)
+    gK = torch.empty(N, m, d, device=dev)
+    gx = torch.empty(N, d, device=dev) if want_x0_grad else None
+    sums = torch.zeros(1 + m * d, dtype=torch.float64, device=dev)
+    nbytes = _abi.lib().dlc_lds_lqr_grad_workspace_bytes(N, T, d)
+    ws = torch.empty(max(nbytes, 4) // 4, device=dev)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().dlc_lds_lqr_grad_f32(N, T, d, m, int(shared), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K),
+                                             _abi.ptr(x0), _abi.ptr(W), seed, env_offset, t0, w_std, _abi.ptr(loss),
+                                             _abi.ptr(gK), _abi.ptr(gx), _abi.ptr(sums), _abi.ptr(ws), ws.numel() * 4,
+                                             _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lds_lqr_grad_f32")
+    return loss, gK, gx, sums

@@ -75,6 +75,38 @@ def apg_rollout(env, env_start_state, env_init_obs, agent, agent_start_state, un
                                  loss_func, **kw)
 
 
+def value_and_grad_apg_loss(agent, env, env_start_states, env_init_obs, agent_init_states, unroll_length, loss_func,
+                            env_offset=0, disturbances=None):
+    """``jax.value_and_grad(apg_loss)`` (``apg.py:103-122,152-167``) for a linear state-feedback agent (LQR: the
+    leaf is ``agent.K``) on LDS with ``quad_loss``: returns (mean loss over batch and horizon, d mean-loss / dK)
+    with the gradient shaped like ``agent.K`` ([m,d] for a shared gain = summed over envs, [N,m,d] per env).
+    Forward and reverse pass run in ``dlc_lds_lqr_grad_f32`` (hand adjoint)."""
+    if not isinstance(env, LDS) or not isinstance(agent, LQR) or loss_func is not quad_loss:
+        raise NotImplementedError("the fused reverse-mode kernel covers LDS x linear state feedback (LQR.K) x quad_loss")
+    T = int(unroll_length)
+    x = env_start_states.x
+    N = x.shape[0]
+    std = env.disturbance.std()
+    W = disturbances
+    if W is None and (std is None or std == 0.0):
+        W = torch.stack([env.disturbance(env_start_states.t + t, env.key, N=N, device=x.device)
+                         for t in range(T)]).contiguous()
+    K = agent.K.to(x.device)
+    per_env_dyn = env.A.dim() == 3
+    if per_env_dyn and K.dim() == 2:
+        K = K.expand(N, *K.shape).contiguous()
+    A, B = env.A, env.B
+    if K.dim() == 3 and not per_env_dyn:
+        A, B = A.expand(N, *A.shape).contiguous(), B.expand(N, *B.shape).contiguous()
+    loss, gK, _, sums = fused.lds_lqr_value_and_grad(A, B, K, x, T, W=W, seed=env.key, env_offset=env_offset,
+                                                     t0=env_start_states.t, w_std=std or 0.0)
+    denom = float(N * T)
+    value = sums[0] / denom
+    if agent.K.dim() == 2:
+        return value, (sums[1:] / denom).float().reshape(agent.K.shape)
+    return value, gK / denom
+
+
 def apg_loss(env, env_start_states, env_init_obs, agent, agent_start_states, unroll_length, loss_func):
     """Mean loss over the batch and horizon, the forward value of ``apg_loss`` (``apg.py:103-122``)."""
     ro, _ = apg_parallel_rollouts(env, env_start_states, env_init_obs, agent, agent_start_states, unroll_length,

@@ -133,6 +133,28 @@ int32_t dlc_lds_rollout_f32(
     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Reverse mode through the LDS rollout: value and gradient of
+ *     loss_n = sum_{t<T} quad_loss(x_t, u_t),  u_t = -K x_t,  x_{t+1} = A x_t + B u_t + w_t
+ * with respect to the linear policy K (and optionally x_0) -- what jax.value_and_grad(apg_loss)
+ * (deluca/training/apg.py:103-122,152-167) computes for a linear state-feedback agent on LDS
+ * (deluca/envs/_lds.py:102-111, deluca/agents/_lqr.py:62-72, quad_loss deluca/agents/_gpc.py:29-40).
+ * The forward pass checkpoints x_t in the workspace ([T][d][N] floats); the backward pass is the hand adjoint
+ *     g_u = 2 u_t + B' lam_{t+1};  dK -= g_u x_t';  lam_t = 2 x_t + A' lam_{t+1} - K' g_u.
+ * d <= 16, m <= 8.  Disturbances: W[T,N,d] or the library's Philox stream (W == NULL), as in dlc_lds_rollout_f32.
+ * ------------------------------------------------------------------------------------ */
+size_t dlc_lds_lqr_grad_workspace_bytes(int64_t N, int32_t T, int32_t d);
+int32_t dlc_lds_lqr_grad_f32(int64_t N, int32_t T, int32_t d, int32_t m, int32_t shared_dynamics,
+                             const float* A, const float* B, const float* K, /* [N,...] or unbatched */
+                             const float* x0,      /* [N,d] */
+                             const float* W,       /* [T,N,d] or NULL */
+                             uint64_t seed, int64_t env_offset, int32_t t0, float w_std,
+                             float* loss_out,      /* [N] */
+                             float* gradK_out,     /* [N,m,d] d loss_n / d K (per env, also when K is shared) */
+                             float* gradx0_out,    /* [N,d] or NULL */
+                             double* sums_out,     /* [1 + m*d] += (sum loss, sum dK) or NULL; caller zeroes */
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Ventilator episode: lung PID + Expiratory controllers driving BalloonLung / DelayLung, fused.
  *
  * Replaces lax.scan(loop_over_tt) of run_controller_scan

@@ -82,3 +82,54 @@ def test_obj_contract_and_errors():
     assert [t.numel() for t in s.flatten()] == [1, 2, 3, 4]
     with pytest.raises(NotImplementedError):
         apg_parallel_rollouts(object(), None, None, None, None, 1, None)
+
+
+def test_value_and_grad_apg_loss_matches_autograd():
+    """Reverse mode through the LDS rollout (apg.py:103-122,152-167): dlc_lds_lqr_grad_f32 against torch.autograd
+    on a float64 restatement of the same scan."""
+    from deluca_b200.agents import LQR
+    from deluca_b200.agents._gpc import quad_loss
+    from deluca_b200.envs import LDS
+    from deluca_b200.fused import gaussian_disturbance, lds_lqr_value_and_grad
+    from deluca_b200.training.apg import value_and_grad_apg_loss
+    rng = np.random.default_rng(2)
+    N, d, m, T = 37, 10, 3, 80
+    A, B, _ = O.lds_default_params(rng, N, d, m)
+    K = O.lqr_gain(A, B) + 0.05 * rng.standard_normal((N, m, d)).astype(np.float32)
+    x0 = rng.standard_normal((N, d)).astype(np.float32)
+    W = gaussian_disturbance(N, T, d, seed=4).cpu().numpy()
+
+    def torch_loss(Kt, x0t):
+        At, Bt, Wt = (torch.tensor(a, dtype=torch.float64) for a in (A, B, W))
+        x, tot = x0t, 0
+        for t in range(T):
+            u = -torch.einsum("nij,nj->ni", Kt, x)
+            tot = tot + (x * x).sum(1) + (u * u).sum(1)
+            x = torch.einsum("nij,nj->ni", At, x) + torch.einsum("nij,nj->ni", Bt, u) + Wt[t]
+        return tot
+
+    Kt = torch.tensor(K, dtype=torch.float64, requires_grad=True)
+    xt = torch.tensor(x0, dtype=torch.float64, requires_grad=True)
+    lt = torch_loss(Kt, xt)
+    lt.sum().backward()
+    loss, gK, gx, sums = lds_lqr_value_and_grad(_dev(A), _dev(B), _dev(K), _dev(x0), T, W=_dev(W), want_x0_grad=True)
+    np.testing.assert_allclose(loss.cpu().numpy(), lt.detach().numpy(), rtol=1e-4)
+    gref = Kt.grad.numpy()
+    assert np.abs(gK.cpu().numpy() - gref).max() <= 1e-3 * np.abs(gref).max()
+    assert np.abs(gx.cpu().numpy() - xt.grad.numpy()).max() <= 1e-3 * np.abs(xt.grad.numpy()).max()
+    np.testing.assert_allclose(sums[1:].cpu().numpy().reshape(m, d), gref.sum(0), rtol=1e-3, atol=1e-3 * np.abs(gref.sum(0)).max())
+    # in-kernel disturbances == materialised stream
+    l2 = lds_lqr_value_and_grad(_dev(A), _dev(B), _dev(K), _dev(x0), T, W=None, seed=4)[0]
+    assert torch.equal(l2, loss)
+    # mirror: shared dynamics + shared K through the Env/Agent objects
+    env = LDS()
+    env.init(d_in=m, d_hidden=d, d_out=d, A=A[0], B=B[0], C=np.eye(d), key=4)
+    agent = LQR(env.A, env.B)
+    st, obs = env.reset(N, x0=x0)
+    value, grad = value_and_grad_apg_loss(agent, env, st, obs, None, T, quad_loss)
+    Ks = torch.tensor(agent.K.cpu().numpy(), dtype=torch.float64, requires_grad=True)
+    A, B = np.repeat(A[:1], N, 0), np.repeat(B[:1], N, 0)
+    ls = torch_loss(Ks.expand(N, m, d), torch.tensor(x0, dtype=torch.float64)).sum() / (N * T)
+    ls.backward()
+    assert abs(float(value) - float(ls)) <= 1e-4 * float(ls)
+    assert np.abs(grad.cpu().numpy() - Ks.grad.numpy()).max() <= 2e-3 * np.abs(Ks.grad.numpy()).max() + 1e-5

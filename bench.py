@@ -31,9 +31,9 @@ WORKLOADS = {
 # (tests/test_oracle_lds.py::test_reference_noise_quirk...); 1e-4 keeps every env finite so that
 # the rollout that is timed is also the rollout whose parity is tested.
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
-# `ncu --set full` capture of this same command (profiles/r01_lds_f2_final_full.txt): 26.33 + 2.68 GB
+# `ncu --set full` capture of this same command (profiles/r01_lds_f2_32x9_full.txt): 26.33 + 2.68 GB
 # against 28.9 GB of algorithmic bytes.  Other workloads / modes have no capture -> null.
-NCU_TRAFFIC_BYTES = {("c2", "hbm"): 26.328579e9 + 2.675452e9}
+NCU_TRAFFIC_BYTES = {("c2", "hbm"): 26.330129e9 + 2.676375e9}
 LR_SCALE = 1e-4
 W_STD = 0.5
 SEED = 20240
@@ -324,7 +324,7 @@ def main():
                          "frac": ach / fp32_peak if fp32_peak else None,
                          "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.disturbance))
                          if not (args.envs or args.horizon) else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_lds_f2_final_full.txt)",
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_lds_f2_32x9_full.txt)",
                          "algorithmic_bytes": Bts * N * T,
                          "kernel": "lds_f2_kernel" if (H <= 4 and args.variant in (0, 8, 9)) else "lds_split_kernel", "kernel_ms": kern_ms,
                          "kernel_ms_each": [round(v, 3) for v in kern_each],

@@ -326,7 +326,7 @@ def main():
                          if not (args.envs or args.horizon) else None,
                          "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_lds_f2_32x9_full.txt)",
                          "algorithmic_bytes": Bts * N * T,
-                         "kernel": "lds_f2_kernel" if (H <= 4 and args.variant in (0, 8, 9)) else "lds_split_kernel", "kernel_ms": kern_ms,
+                         "kernel": "lds_f2_kernel" if args.variant in (0, 8, 9, 10, 11, 12) else "lds_split_kernel", "kernel_ms": kern_ms,
                          "kernel_ms_each": [round(v, 3) for v in kern_each],
                          "flops_per_env_step": F, "bytes_per_env_step": Bts,
                          "peak_source": "measured live: dlc_microbench_f32 (FFMA %.1f, FFMA2 %.1f TFLOP/s); "

@@ -809,7 +809,7 @@ static bool try_split(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
     }                                                                                 \
     if (p.H == H_ && p.HH == HH_) {                                                   \
       /* packed-FFMA2 kernel: default for short histories (6-10 % faster on B200), forced by 8 / 9 */ \
-      if (((p.kernel_variant == 0 && H_ <= 4) || (p.kernel_variant >= 8 && p.kernel_variant <= 11)) && \
+      if (((p.kernel_variant == 0 && (H_ <= 4 || (H_ % 2 == 0 && HH_ == H_))) || (p.kernel_variant >= 8 && p.kernel_variant <= 12)) && \
           launch_gpc_f2(a, st, rc))                                                   \
         return true;                                                                  \
       *rc = launch_gpc<D_, M_, H_, HH_, L_>(a, st);                                   \

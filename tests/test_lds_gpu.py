@@ -48,7 +48,7 @@ def _check(res, ref, T):
 
 @pytest.mark.parametrize("d,m,H,HH,variant", [
     (10, 3, 3, 10, 0), (10, 3, 3, 10, 1), (10, 3, 3, 2, 0), (10, 3, 10, 10, 0), (4, 1, 3, 2, 0),
-    (10, 3, 3, 10, 5), (10, 3, 3, 10, 8), (10, 3, 3, 10, 9), (10, 3, 3, 2, 8), (10, 3, 10, 10, 8), (10, 3, 10, 10, 9),
+    (10, 3, 3, 10, 5), (10, 3, 3, 10, 8), (10, 3, 3, 10, 9), (10, 3, 3, 2, 8), (10, 3, 10, 10, 8), (10, 3, 10, 10, 12), (10, 3, 10, 10, 11), (10, 3, 10, 10, 5),
     (4, 2, 5, 7, 0), (4, 2, 5, 7, 1), (6, 2, 4, 5, 0), (3, 1, 1, 1, 0), (5, 2, 4, 2, 0)])
 @pytest.mark.parametrize("dense", [False, True])
 def test_gpc_matches_oracle(d, m, H, HH, variant, dense):
@@ -128,6 +128,22 @@ def test_resume_is_identical_and_inputs_untouched():
     h2 = lds_rollout(dA, dB, dK, h1.x, T - 40, W=dW[40:].contiguous(), M=h1.M, hist=h1.hist,
                      xprev=h1.xprev, uprev=h1.uprev, t0=h1.t, **kw)
     assert torch.equal(full.costs[40:], h2.costs)
+    assert torch.equal(full.x, h2.x) and torch.equal(full.M, h2.M) and torch.equal(full.hist, h2.hist)
+
+
+@pytest.mark.parametrize("variant", [0, 8, 11])
+def test_resume_long_history(variant):
+    """H = HH = 10 (slot-paired noise ring in the packed kernel): split rollouts continue bit-identically."""
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 45, 70, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=5)
+    dA, dB, dK, dx, dW = map(_dev, (A, B, K, x0, W))
+    kw = dict(policy="gpc", H=10, HH=10, lr_scale=1e-4, kernel_variant=variant)
+    full = lds_rollout(dA, dB, dK, dx, T, W=dW, **kw)
+    h1 = lds_rollout(dA, dB, dK, dx, 27, W=dW[:27].contiguous(), **kw)
+    h2 = lds_rollout(dA, dB, dK, h1.x, T - 27, W=dW[27:].contiguous(), M=h1.M, hist=h1.hist,
+                     xprev=h1.xprev, uprev=h1.uprev, t0=h1.t, **kw)
+    assert torch.equal(full.costs[27:], h2.costs)
     assert torch.equal(full.x, h2.x) and torch.equal(full.M, h2.M) and torch.equal(full.hist, h2.hist)
 
 

@@ -71,7 +71,7 @@ class DlcLungBuffers(ctypes.Structure):
 
 
 class DlcEnvSpec(ctypes.Structure):
-    _fields_ = [("kind", ctypes.c_int32), ("p", ctypes.c_float * 7)]
+    _fields_ = [("kind", ctypes.c_int32), ("p", ctypes.c_float * 8)]
 
 
 class DlcPlanParams(ctypes.Structure):
@@ -111,6 +111,8 @@ SYMBOLS = {
     "dlc_linearize_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams), ctypes.c_int32] + [_P] * 10),
     "dlc_riccati_backward_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
                                  + [_P] * 10),
+    "dlc_lqg_backward_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+                             + [_P] * 9 + [ctypes.c_float, ctypes.c_float, ctypes.c_int32] + [_P] * 5),
     "dlc_igpc_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 10),
     "dlc_plan_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcPlanParams)]),
     "dlc_plan_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 9 + [ctypes.c_size_t, _P]),

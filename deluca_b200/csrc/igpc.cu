@@ -132,6 +132,134 @@ struct Model<DLC_ENV_QUADROTOR> {  // deluca/envs/classic/_planar_quadrotor.py:9
   }
 };
 
+
+// Forward-mode scalar (value + NV partials): what jax.jacfwd does to Reacher's step (rollout.py:79-80)
+template <int NV>
+struct Dual {
+  float v, d[NV];
+};
+template <int NV>
+__device__ __forceinline__ Dual<NV> dconst(float c) {
+  Dual<NV> r;
+  r.v = c;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r.d[i] = 0.f;
+  return r;
+}
+template <int NV>
+__device__ __forceinline__ Dual<NV> dvar(float c, int idx) {
+  Dual<NV> r = dconst<NV>(c);
+  r.d[idx] = 1.f;
+  return r;
+}
+__device__ __forceinline__ float dconst_like(float, float c) { return c; }
+template <int NV>
+__device__ __forceinline__ Dual<NV> dconst_like(const Dual<NV>&, float c) { return dconst<NV>(c); }
+template <int NV>
+__device__ __forceinline__ Dual<NV> operator+(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r;
+  r.v = a.v + b.v;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r.d[i] = a.d[i] + b.d[i];
+  return r;
+}
+template <int NV>
+__device__ __forceinline__ Dual<NV> operator-(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r;
+  r.v = a.v - b.v;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r.d[i] = a.d[i] - b.d[i];
+  return r;
+}
+template <int NV>
+__device__ __forceinline__ Dual<NV> operator*(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r;
+  r.v = a.v * b.v;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r.d[i] = fmaf(a.v, b.d[i], a.d[i] * b.v);
+  return r;
+}
+template <int NV>
+__device__ __forceinline__ Dual<NV> operator*(float a, const Dual<NV>& b) {
+  Dual<NV> r;
+  r.v = a * b.v;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r.d[i] = a * b.d[i];
+  return r;
+}
+template <int NV>
+__device__ __forceinline__ Dual<NV> operator/(const Dual<NV>& a, const Dual<NV>& b) {
+  Dual<NV> r;
+  const float ib = 1.0f / b.v;
+  r.v = a.v * ib;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+  return r;
+}
+__device__ __forceinline__ void dsincos(float a, float* s, float* c) { sincosf(a, s, c); }
+template <int NV>
+__device__ __forceinline__ void dsincos(const Dual<NV>& a, Dual<NV>* s, Dual<NV>* c) {
+  float sv, cv;
+  sincosf(a.v, &sv, &cv);
+  s->v = sv;
+  c->v = cv;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { s->d[i] = cv * a.d[i]; c->d[i] = -sv * a.d[i]; }
+}
+
+template <>
+struct Model<DLC_ENV_REACHER> {  // deluca/envs/classic/_reacher.py:98-141 (two-link arm, state carries the tip offset)
+  static constexpr int D = 6, M = 2;
+  float m1, m2, l1, l2, g, dt, gx, gy;
+  __device__ explicit Model(const DlcEnvSpec& s) {
+    m1 = s.p[0]; m2 = s.p[1]; l1 = s.p[2]; l2 = s.p[3]; g = s.p[4]; dt = s.p[5]; gx = s.p[6]; gy = s.p[7];
+  }
+  template <class T>
+  __device__ void step_t(const T* x, const T* u, T* xn) const {
+    const T th1 = x[0], th2 = x[1], dth1 = x[2], dth2 = x[3];
+    T s2, c2, s1, c1, s12, c12;
+    dsincos(th2, &s2, &c2);
+    dsincos(th1, &s1, &c1);
+    dsincos(th1 + th2, &s12, &c12);
+    const float mll = m2 * l1 * l2;
+    const T a11 = dconst_like(th1, (m1 + m2) * l1 * l1 + m2 * l2 * l2) + (2.0f * mll) * c2;
+    const T a12 = dconst_like(th1, m2 * l2 * l2) + mll * c2;
+    const float a22 = m2 * l2 * l2;
+    const T b1 = ((u[0] + mll * ((2.0f * dth1 + dth2) * dth2 * s2)) - (m2 * l2 * g) * s12) - ((m1 + m2) * l1 * g) * s1;
+    const T b2 = (u[1] - mll * (dth1 * dth1 * s2)) - (m2 * l2 * g) * s12;
+    const T det = a22 * a11 - a12 * a12;                          // inv([[a11,a12],[a12,a22]]) @ b   :128-129
+    const T dd1 = (a22 * b1 - a12 * b2) / det;
+    const T dd2 = (a11 * b2 - a12 * b1) / det;
+    const T nth1 = th1 + dt * dth1, nth2 = th2 + dt * dth2;
+    T sn1, cn1, sn12, cn12;
+    dsincos(nth1, &sn1, &cn1);
+    dsincos(nth1 + nth2, &sn12, &cn12);
+    xn[0] = nth1;
+    xn[1] = nth2;
+    xn[2] = dth1 + dt * dd1;
+    xn[3] = dth2 + dt * dd2;
+    xn[4] = (l1 * cn1 + l2 * cn12) - dconst_like(th1, gx);
+    xn[5] = (l1 * sn1 + l2 * sn12) - dconst_like(th1, gy);
+  }
+  __device__ void step(const float* x, const float* u, float* xn) const { step_t<float>(x, u, xn); }
+  __device__ void jac(const float* x, const float* u, float* Fx, float* Fu) const {
+    typedef Dual<8> T;
+    T xd[D], ud[M], xo[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) xd[i] = dvar<8>(x[i], i);
+#pragma unroll
+    for (int c = 0; c < M; ++c) ud[c] = dvar<8>(u[c], D + c);
+    step_t<T>(xd, ud, xo);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) Fx[i * D + j] = xo[i].d[j];
+#pragma unroll
+      for (int c = 0; c < M; ++c) Fu[i * M + c] = xo[i].d[D + c];
+    }
+  }
+};
+
 template <int D, int M>
 __device__ __forceinline__ float quad_cost(const DlcPlanParams& p, const float* x, const float* u) {
   float cx = 0.f, cu = 0.f;
@@ -647,6 +775,178 @@ __global__ void __launch_bounds__(128) riccati_kernel(int64_t N, int H, const fl
   if (status_out) status_out[n] = status;
 }
 
+// Cholesky PD test + inverse of a small SPD matrix (lqr_solver.py:157-163 isPD_and_invert: inv = L^-T L^-1).
+// A non-positive or non-finite pivot reports "not PD" (NumPy raises / yields NaN there; both mean "raise lambda").
+template <int M>
+__device__ bool chol_inv(const float* A, float* Ai) {
+  float L[M][M], Li[M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) { L[i][j] = 0.f; Li[i][j] = 0.f; }
+  for (int j = 0; j < M; ++j) {
+    float s = A[j * M + j];
+    for (int l = 0; l < j; ++l) s -= L[j][l] * L[j][l];
+    if (!(s > 0.f) || !isfinite(s)) return false;
+    L[j][j] = sqrtf(s);
+    for (int i = j + 1; i < M; ++i) {
+      float t = A[i * M + j];
+      for (int l = 0; l < j; ++l) t -= L[i][l] * L[j][l];
+      L[i][j] = t / L[j][j];
+    }
+  }
+  for (int c = 0; c < M; ++c)          // forward substitution L Li = I
+    for (int i = c; i < M; ++i) {
+      float t = i == c ? 1.f : 0.f;
+      for (int l = c; l < i; ++l) t -= L[i][l] * Li[l][c];
+      Li[i][c] = t / L[i][i];
+    }
+  bool ok = true;
+  for (int i = 0; i < M; ++i)
+    for (int j = 0; j < M; ++j) {
+      float t = 0.f;
+      for (int l = 0; l < M; ++l) t = fmaf(Li[l][i], Li[l][j], t);
+      Ai[i * M + j] = t;
+      ok &= isfinite(t);
+    }
+  return ok;
+}
+
+// LQG (lqr_solver.py:89-154): regularised backward pass with c_ux, Cholesky PD test and the lambda schedule.
+template <int D, int M>
+__global__ void __launch_bounds__(128) lqg_kernel(int64_t N, int H, const float* Fx, const float* Fu, const float* cx,
+                                                  const float* cu, const float* cxx, const float* cuu,
+                                                  const float* cux, float* lambda_io, float* mult_io, float factor,
+                                                  float lambda_min, int reg_type, float* k_out, float* K_out,
+                                                  float* gains_out, int32_t* status_out) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float lam = lambda_io[n], mult = mult_io[n];
+  float gl = 0.f, gq = 0.f;
+  bool ok = false;
+  for (int attempt = 1; attempt < 10 && !ok; ++attempt) {          // `counter >= 10` gives up            :100-105
+    float Vx[D], Vxx[D * D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) Vx[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < D * D; ++i) Vxx[i] = 0.f;
+    gl = 0.f;
+    gq = 0.f;
+    ok = true;
+    for (int h = H - 1; h >= 0 && ok; --h) {
+      const int64_t o = n * H + h;
+      const float* fx = Fx + o * D * D;
+      const float* fu = Fu + o * D * M;
+      float VF[D * D], VFu[D * M], Qx[D], Qu[M], Qxx[D * D], Qux[M * D], Quu[M * M], Qur[M * M], Qxr[M * D];
+      for (int i = 0; i < D; ++i) {
+        for (int j = 0; j < D; ++j) {
+          float t = 0.f;
+          for (int l = 0; l < D; ++l) t = fmaf(Vxx[i * D + l], fx[l * D + j], t);
+          VF[i * D + j] = t;
+        }
+        for (int c = 0; c < M; ++c) {
+          float t = 0.f;
+          for (int l = 0; l < D; ++l) t = fmaf(Vxx[i * D + l], fu[l * M + c], t);
+          VFu[i * M + c] = t;
+        }
+      }
+      for (int i = 0; i < D; ++i) {
+        float t = 0.f;
+        for (int l = 0; l < D; ++l) t = fmaf(fx[l * D + i], Vx[l], t);
+        Qx[i] = cx[o * D + i] + t;
+        for (int j = 0; j < D; ++j) {
+          float v = 0.f;
+          for (int l = 0; l < D; ++l) v = fmaf(fx[l * D + i], VF[l * D + j], v);
+          Qxx[i * D + j] = cxx[o * D * D + i * D + j] + v;
+        }
+      }
+      for (int c = 0; c < M; ++c) {
+        float t = 0.f;
+        for (int l = 0; l < D; ++l) t = fmaf(fu[l * M + c], Vx[l], t);
+        Qu[c] = cu[o * M + c] + t;
+        for (int j = 0; j < D; ++j) {
+          float v = 0.f, r = 0.f;
+          for (int l = 0; l < D; ++l) { v = fmaf(fu[l * M + c], VF[l * D + j], v); r = fmaf(fu[l * M + c], fx[l * D + j], r); }
+          Qux[c * D + j] = cux[o * M * D + c * D + j] + v;
+          Qxr[c * D + j] = reg_type == 1 ? Qux[c * D + j] + lam * r : Qux[c * D + j];   // type V   :127-129
+        }
+        for (int e = 0; e < M; ++e) {
+          float v = 0.f, r = 0.f;
+          for (int l = 0; l < D; ++l) { v = fmaf(fu[l * M + c], VFu[l * M + e], v); r = fmaf(fu[l * M + c], fu[l * M + e], r); }
+          Quu[c * M + e] = cuu[o * M * M + c * M + e] + v;
+          Qur[c * M + e] = reg_type == 1 ? Quu[c * M + e] + lam * r                      // type V
+                                         : Quu[c * M + e] + (c == e ? lam : 0.f);        // type Q   :122-125
+        }
+      }
+      float Qi[M * M];
+      if (!chol_inv<M>(Qur, Qi)) { ok = false; break; }
+      float Kl[M * D], kl[M];
+      for (int c = 0; c < M; ++c) {
+        float t = 0.f;
+        for (int e = 0; e < M; ++e) t = fmaf(Qi[c * M + e], Qu[e], t);
+        kl[c] = -t;
+        k_out[o * M + c] = -t;
+        for (int j = 0; j < D; ++j) {
+          float v = 0.f;
+          for (int e = 0; e < M; ++e) v = fmaf(Qi[c * M + e], Qxr[e * D + j], v);
+          Kl[c * D + j] = -v;
+          K_out[o * M * D + c * D + j] = -v;
+        }
+      }
+      // V_x = Q_x + K'Q_uu k + K'Q_u + Q_ux'k ; V_xx = Q_xx + K'Q_uu K + K'Q_ux + Q_ux'K (unregularised Q)  :134-137
+      float Qk[M], QK[M * D];
+      for (int c = 0; c < M; ++c) {
+        float t = 0.f;
+        for (int e = 0; e < M; ++e) t = fmaf(Quu[c * M + e], kl[e], t);
+        Qk[c] = t;
+        for (int j = 0; j < D; ++j) {
+          float v = 0.f;
+          for (int e = 0; e < M; ++e) v = fmaf(Quu[c * M + e], Kl[e * D + j], v);
+          QK[c * D + j] = v;
+        }
+      }
+      float Vn[D * D];
+      for (int i = 0; i < D; ++i) {
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = 0; c < M; ++c) {
+          a1 = fmaf(Kl[c * D + i], Qk[c], a1);
+          a2 = fmaf(Kl[c * D + i], Qu[c], a2);
+          a3 = fmaf(Qux[c * D + i], kl[c], a3);
+        }
+        Vx[i] = ((Qx[i] + a1) + a2) + a3;
+        for (int j = 0; j < D; ++j) {
+          float b1 = 0.f, b2 = 0.f, b3 = 0.f;
+          for (int c = 0; c < M; ++c) {
+            b1 = fmaf(Kl[c * D + i], QK[c * D + j], b1);
+            b2 = fmaf(Kl[c * D + i], Qux[c * D + j], b2);
+            b3 = fmaf(Qux[c * D + i], Kl[c * D + j], b3);
+          }
+          Vn[i * D + j] = ((Qxx[i * D + j] + b1) + b2) + b3;
+        }
+      }
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) Vxx[i * D + j] = (Vn[i * D + j] + Vn[j * D + i]) * 0.5f;
+      for (int c = 0; c < M; ++c) {
+        gl = fmaf(kl[c], Qu[c], gl);                                // gains_lin  += k'Q_u       :143
+        gq = fmaf(kl[c], Qk[c], gq);                                // gains_quad += k'Q_uu k    :144
+      }
+    }
+    if (!ok) {                                                      // lambda_adjust(..., increase=True)  :21-37
+      mult = fmaxf(mult * factor, factor);
+      lam = fmaxf(lam * mult, lambda_min);
+      lam = fmaxf(lam, lambda_min);
+      if (lam > 1e10f) lam = 1e10f;
+    }
+  }
+  lambda_io[n] = lam;
+  mult_io[n] = mult;
+  if (gains_out) {
+    gains_out[2 * n] = ok ? gl : nanf("");
+    gains_out[2 * n + 1] = ok ? gq : nanf("");
+  }
+  if (status_out) status_out[n] = ok ? 0 : DLC_STATUS_NOT_PD;
+}
+
 // iLQR / iGPC_closed / iLC_closed, whole outer loop per trajectory (ilqr.py:27-93, igpc.py:129-179,
 // ilc.py:23-69).  Nominal (X, U) live in X_out / U_io, the candidate in the workspace.
 template <int KIND>
@@ -708,7 +1008,7 @@ static int32_t check_plan(const DlcPlanParams* p, const char* who) {
   if (!p) return fail(DLC_ERR_ARG, "NULL params");
   if (p->N < 0 || p->H < 1 || p->T < 0) return fail(DLC_ERR_ARG, "bad N / H / T");
   if (p->env_true.kind != p->env_sim.kind) return fail(DLC_ERR_SHAPE, "env_true and env_sim must be the same kind of env");
-  if (p->env_true.kind < DLC_ENV_PENDULUM || p->env_true.kind > DLC_ENV_QUADROTOR)
+  if (p->env_true.kind < DLC_ENV_PENDULUM || p->env_true.kind > DLC_ENV_REACHER)
     return fail(DLC_ERR_SHAPE, "unknown env kind");
   (void)who;
   return DLC_OK;
@@ -722,7 +1022,8 @@ using namespace dlc;
   do {                                                                                    \
     if ((kind) == DLC_ENV_PENDULUM) KERNEL<DLC_ENV_PENDULUM><<<grid, 128, 0, st>>>(args); \
     else if ((kind) == DLC_ENV_CARTPOLE) KERNEL<DLC_ENV_CARTPOLE><<<grid, 128, 0, st>>>(args); \
-    else KERNEL<DLC_ENV_QUADROTOR><<<grid, 128, 0, st>>>(args);                           \
+    else if ((kind) == DLC_ENV_QUADROTOR) KERNEL<DLC_ENV_QUADROTOR><<<grid, 128, 0, st>>>(args); \
+    else KERNEL<DLC_ENV_REACHER><<<grid, 128, 0, st>>>(args);                             \
   } while (0)
 
 extern "C" int32_t dlc_env_rollout_f32(const DlcPlanParams* p, int32_t use_sim_env, const float* U_old,
@@ -794,10 +1095,33 @@ extern "C" int32_t dlc_riccati_backward_f32(int64_t N, int32_t H, int32_t d, int
   return fail(DLC_ERR_SHAPE, "dlc_riccati_backward_f32: (d, m) not instantiated: (2,1) (3,1) (4,1) (4,2) (6,2) (6,3) (8,2)");
 }
 
+extern "C" int32_t dlc_lqg_backward_f32(int64_t N, int32_t H, int32_t d, int32_t m, const float* Fx, const float* Fu,
+                                        const float* cx, const float* cu, const float* cxx, const float* cuu,
+                                        const float* cux, float* lambda_io, float* multiplier_io, float factor,
+                                        float lambda_min, int32_t reg_type, float* k_out, float* K_out,
+                                        float* gains_out, int32_t* status_out, void* stream) {
+  if (N < 0 || H < 1) return fail(DLC_ERR_ARG, "dlc_lqg_backward_f32: bad N / H");
+  if (reg_type != 0 && reg_type != 1) return fail(DLC_ERR_ARG, "dlc_lqg_backward_f32: reg_type must be 0 (Q) or 1 (V)");
+  if (N == 0) return DLC_OK;
+  if (!Fx || !Fu || !cx || !cu || !cxx || !cuu || !cux || !lambda_io || !multiplier_io || !k_out || !K_out)
+    return fail(DLC_ERR_ARG, "dlc_lqg_backward_f32: NULL buffer");
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LQGK(D_, M_)                                                                                           \
+  if (d == D_ && m == M_) {                                                                                    \
+    lqg_kernel<D_, M_><<<grid, 128, 0, st>>>(N, H, Fx, Fu, cx, cu, cxx, cuu, cux, lambda_io, multiplier_io,    \
+                                             factor, lambda_min, reg_type, k_out, K_out, gains_out, status_out); \
+    return cuda_status(cudaGetLastError(), "lqg_kernel launch");                                               \
+  }
+  LQGK(3, 1) LQGK(4, 1) LQGK(2, 1) LQGK(4, 2) LQGK(6, 2) LQGK(6, 3) LQGK(8, 2)
+#undef LQGK
+  return fail(DLC_ERR_SHAPE, "dlc_lqg_backward_f32: (d, m) not instantiated: (2,1) (3,1) (4,1) (4,2) (6,2) (6,3) (8,2)");
+}
+
 extern "C" size_t dlc_plan_workspace_bytes(const DlcPlanParams* p) {
   if (!p || p->N <= 0 || p->H < 1) return 0;
   const int d = p->env_true.kind == DLC_ENV_PENDULUM ? 3 : (p->env_true.kind == DLC_ENV_CARTPOLE ? 4 : 6);
-  const int m = p->env_true.kind == DLC_ENV_QUADROTOR ? 2 : 1;
+  const int m = p->env_true.kind >= DLC_ENV_QUADROTOR ? 2 : 1;
   return (size_t)p->N * ((size_t)(p->H + 1) * d + (size_t)p->H * m) * sizeof(float);
 }
 

@@ -220,6 +220,28 @@ def riccati_backward(F, C):
     return k, K, status
 
 
+def lqg_backward(F, C, reg_lambda, multiplier, factor, lambda_min, reg_type):
+    """``dlc_lqg_backward_f32``: regularised Riccati pass with the lambda schedule on the device.
+    reg_lambda / multiplier are [N] tensors updated in place.  Returns k, K, gains[N,2], status[N]."""
+    Fx, Fu = F
+    cx, cu, cxx, cuu, cux = C
+    N, H, d, m = Fu.shape
+    for t in (Fx, Fu, cx, cu, cxx, cuu, cux, reg_lambda, multiplier):
+        _f32(t, "F/C leaf")
+    k = torch.zeros(N, H, m, device=Fx.device)
+    K = torch.zeros(N, H, m, d, device=Fx.device)
+    gains = torch.empty(N, 2, device=Fx.device)
+    status = torch.empty(N, dtype=torch.int32, device=Fx.device)
+    with torch.cuda.device(Fx.device):
+        rc = _abi.lib().dlc_lqg_backward_f32(N, H, d, m, _abi.ptr(Fx), _abi.ptr(Fu), _abi.ptr(cx), _abi.ptr(cu),
+                                             _abi.ptr(cxx), _abi.ptr(cuu), _abi.ptr(cux), _abi.ptr(reg_lambda),
+                                             _abi.ptr(multiplier), float(factor), float(lambda_min), int(reg_type),
+                                             _abi.ptr(k), _abi.ptr(K), _abi.ptr(gains), _abi.ptr(status),
+                                             _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lqg_backward_f32")
+    return k, K, gains, status
+
+
 def plan(p, U, x0):
     """``dlc_plan_f32``: the whole iLQR / iGPC / iLC loop.  Returns X, U, k, K, cost, alpha, status."""
     N, H, m = U.shape

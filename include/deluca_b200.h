@@ -277,6 +277,8 @@ int32_t dlc_pid_f32(int64_t N, int32_t T, float decay,
 #define DLC_ENV_CARTPOLE 1 /* d = 4, m = 1; params: m, M, l, g, dt, offset */
 #define DLC_ENV_QUADROTOR 2 /* PlanarQuadrotor (deluca/envs/classic/_planar_quadrotor.py:51-104): d = 6, m = 2;
                                params: m, l, g, dt, wind, wind_kind (0 = dissipative, 1 = constant) */
+#define DLC_ENV_REACHER 3 /* Reacher (deluca/envs/classic/_reacher.py:56-141): d = 6, m = 2;
+                             params: m1, m2, l1, l2, g, dt, goal_coord[0], goal_coord[1] */
 #define DLC_PLAN_MAXD 8
 #define DLC_PLAN_MAXM 4
 #define DLC_ALGO_ILQR 0
@@ -288,7 +290,7 @@ int32_t dlc_pid_f32(int64_t N, int32_t T, float decay,
 
 typedef struct DlcEnvSpec {
   int32_t kind;        /* DLC_ENV_* */
-  float p[7];          /* static fields in the order listed above */
+  float p[8];          /* static fields in the order listed above */
 } DlcEnvSpec;
 
 typedef struct DlcPlanParams {
@@ -325,6 +327,18 @@ int32_t dlc_linearize_f32(const DlcPlanParams* p, int32_t use_sim_env, const flo
 int32_t dlc_riccati_backward_f32(int64_t N, int32_t H, int32_t d, int32_t m, const float* Fx, const float* Fu,
                                  const float* cx, const float* cu, const float* cxx, const float* cuu,
                                  float* k_out, float* K_out, int32_t* status_out /*[N] or NULL*/, void* stream);
+
+/* LQG (deluca/igpc/lqr_solver.py:89-154) with isPD_and_invert (:157-163) and the increasing branch of
+ * lambda_adjust (:21-37) on the device: regularised Riccati pass (reg_type 0 = "Q": Q_uu + lambda I; 1 = "V":
+ * Q_uu + lambda f_u'f_u and Q_ux + lambda f_u'f_x), Cholesky PD test per step, up to 9 attempts with lambda raised
+ * after each failure.  lambda_io / multiplier_io [N] carry reg_lambda and multiplier in and the values the
+ * reference would return out; gains_out [N,2] = (gains_lin, gains_quad) or NaN when no lambda was found
+ * (reference: None, None); status_out DLC_STATUS_NOT_PD in that case.  cux [N,H,m,d]. */
+int32_t dlc_lqg_backward_f32(int64_t N, int32_t H, int32_t d, int32_t m, const float* Fx, const float* Fu,
+                             const float* cx, const float* cu, const float* cxx, const float* cuu,
+                             const float* cux, float* lambda_io, float* multiplier_io, float factor,
+                             float lambda_min, int32_t reg_type, float* k_out, float* K_out,
+                             float* gains_out /*[N,2] or NULL*/, int32_t* status_out /*[N] or NULL*/, void* stream);
 
 int32_t dlc_igpc_rollout_f32(const DlcPlanParams* p, const float* U_old, const float* k, const float* K,
                              const float* X_old, const float* alpha /*[N]*/, const float* x0,

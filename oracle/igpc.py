@@ -1,4 +1,4 @@
-"""deluca/igpc (rollout, compute_ders, LQR backward pass, iLQR, GPC_rollout, iGPC_closed, iLC_closed)
+"""deluca/igpc (rollout, compute_ders, LQR / LQG backward passes, iLQR, GPC_rollout, iGPC_closed, iLC_closed)
 and the classic envs it plans on, restated on the CPU (test infrastructure; see oracle/__init__.py).
 
 Parity unpinned: the reference has no test for any of this.  Analytic Jacobians replace
@@ -144,6 +144,101 @@ class PlanarQuadrotor:
         return Fx, Fu
 
 
+class _Fwd:
+    """Forward-mode value + tangent pair over a batch (what ``jax.jacfwd`` propagates): v[N], t[N,P]."""
+
+    def __init__(self, v, t):
+        self.v, self.t = v, t
+
+    @staticmethod
+    def lift(o, like):
+        return o if isinstance(o, _Fwd) else _Fwd(np.full_like(like.v, o), np.zeros_like(like.t))
+
+    def __add__(self, o):
+        o = _Fwd.lift(o, self)
+        return _Fwd(self.v + o.v, self.t + o.t)
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return _Fwd(-self.v, -self.t)
+
+    def __sub__(self, o):
+        return self + (-_Fwd.lift(o, self))
+
+    def __rsub__(self, o):
+        return _Fwd.lift(o, self) - self
+
+    def __mul__(self, o):
+        o = _Fwd.lift(o, self)
+        return _Fwd(self.v * o.v, self.v[:, None] * o.t + o.v[:, None] * self.t)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        o = _Fwd.lift(o, self)
+        q = self.v / o.v
+        return _Fwd(q, (self.t - q[:, None] * o.t) / o.v[:, None])
+
+    def sin(self):
+        return _Fwd(np.sin(self.v), np.cos(self.v)[:, None] * self.t)
+
+    def cos(self):
+        return _Fwd(np.cos(self.v), -np.sin(self.v)[:, None] * self.t)
+
+
+class Reacher:
+    """``deluca/envs/classic/_reacher.py:56-141``: two-link arm, explicit Euler on the joint
+    accelerations ``inv([[a11,a12],[a12,a22]]) @ b``, tip offset from ``goal_coord`` carried in the state.
+    ``max_torque`` is a declared field the step never uses."""
+    d, m = 6, 2
+
+    def __init__(self, m1=1.0, m2=1.0, l1=1.0, l2=1.0, g=0.0, dt=0.01, H=200, goal_coord=(0.0, 1.8)):
+        self.m1, self.m2, self.l1, self.l2, self.g, self.dt, self.H = m1, m2, l1, l2, g, dt, H
+        self.goal_coord = np.asarray(goal_coord, dtype=np.float64)
+        self.goal_state = np.zeros(6)
+
+    def init(self, N, dtype):
+        th1, th2 = np.pi / 4, np.pi / 2                                     # :75
+        arr = np.array([th1, th2, 0.0, 0.0,
+                        self.l1 * np.cos(th1) + self.l2 * np.cos(th1 + th2) - self.goal_coord[0],
+                        self.l1 * np.sin(th1) + self.l2 * np.sin(th1 + th2) - self.goal_coord[1]])
+        return np.broadcast_to(arr.astype(dtype), (N, 6)).copy()
+
+    def _f(self, th1, th2, dth1, dth2, t1, t2, sin, cos, c):
+        m1, m2, l1, l2, g, dt = (c(v) for v in (self.m1, self.m2, self.l1, self.l2, self.g, self.dt))
+        a11 = ((m1 + m2) * l1 ** 2 + m2 * l2 ** 2) + (c(2) * m2 * l1 * l2) * cos(th2)            # :113
+        a12 = m2 * l2 ** 2 + (m2 * l1 * l2) * cos(th2)                                            # :114
+        a22 = m2 * l2 ** 2                                                                        # :115
+        b1 = ((t1 + (m2 * l1 * l2) * ((c(2) * dth1 + dth2) * dth2 * sin(th2)))
+              - (m2 * l2 * g) * sin(th1 + th2)) - ((m1 + m2) * l1 * g) * sin(th1)                 # :116-121
+        b2 = (t2 - (m2 * l1 * l2) * (dth1 * dth1 * sin(th2))) - (m2 * l2 * g) * sin(th1 + th2)    # :122-126
+        det = a22 * a11 - a12 * a12                                                               # :127-128
+        dd1 = (a22 * b1 - a12 * b2) / det
+        dd2 = (a11 * b2 - a12 * b1) / det
+        nth1, nth2 = th1 + dth1 * dt, th2 + dth2 * dt                                             # :130
+        ndth1, ndth2 = dth1 + dd1 * dt, dth2 + dd2 * dt                                           # :131
+        Dx = (l1 * cos(nth1) + l2 * cos(nth1 + nth2)) - c(self.goal_coord[0])                     # :132-135
+        Dy = (l1 * sin(nth1) + l2 * sin(nth1 + nth2)) - c(self.goal_coord[1])
+        return [nth1, nth2, ndth1, ndth2, Dx, Dy]
+
+    def step(self, x, u):
+        c = x.dtype.type
+        out = self._f(x[:, 0], x[:, 1], x[:, 2], x[:, 3], u[:, 0], u[:, 1], np.sin, np.cos, c)
+        return np.stack(out, axis=1).astype(x.dtype)
+
+    def jac(self, x, u):
+        """Forward-mode Jacobians (the old tip offset x[4:6] has no influence: zero columns)."""
+        c = x.dtype.type
+        N = x.shape[0]
+        seeds = np.eye(8, dtype=x.dtype)
+        var = lambda v, i: _Fwd(v, np.broadcast_to(seeds[i], (N, 8)).copy())
+        out = self._f(var(x[:, 0], 0), var(x[:, 1], 1), var(x[:, 2], 2), var(x[:, 3], 3), var(u[:, 0], 6),
+                      var(u[:, 1], 7), lambda a: a.sin(), lambda a: a.cos(), c)
+        J = np.stack([o.t for o in out], axis=1)                           # [N,6,8]
+        return J[:, :, :6].astype(x.dtype), J[:, :, 6:].astype(x.dtype)
+
+
 class QuadCost:
     """c(x,u) = sum_i q_i (x_i - goal_i)^2 + sum_j r_j (u_j - goal_u_j)^2  (this repo's stated choice)."""
 
@@ -155,19 +250,20 @@ class QuadCost:
         return u if self.goal_action is None else u - self.goal_action.astype(u.dtype)
 
     def __call__(self, x, u):
-        c = x.dtype.type
         dx = x - self.goal.astype(x.dtype)
         du = self._du(u)
-        return c(self.q) * (dx * dx).sum(1) + c(self.r) * (du * du).sum(1)
+        q, r = np.asarray(self.q, dtype=x.dtype), np.asarray(self.r, dtype=x.dtype)     # scalars or per-coordinate
+        return (q * (dx * dx)).sum(1) + (r * (du * du)).sum(1)
 
     def ders(self, x, u):
-        c = x.dtype.type
         N, d = x.shape
         m = u.shape[1]
-        c_x = c(2 * self.q) * (x - self.goal.astype(x.dtype))
-        c_u = c(2 * self.r) * self._du(u)
-        c_xx = np.broadcast_to(c(2 * self.q) * np.eye(d, dtype=x.dtype), (N, d, d))
-        c_uu = np.broadcast_to(c(2 * self.r) * np.eye(m, dtype=x.dtype), (N, m, m))
+        q = np.broadcast_to(np.asarray(self.q, dtype=x.dtype), (d,))
+        r = np.broadcast_to(np.asarray(self.r, dtype=x.dtype), (m,))
+        c_x = x.dtype.type(2) * q * (x - self.goal.astype(x.dtype))
+        c_u = x.dtype.type(2) * r * self._du(u)
+        c_xx = np.broadcast_to(np.diag(x.dtype.type(2) * q), (N, d, d))
+        c_uu = np.broadcast_to(np.diag(x.dtype.type(2) * r), (N, m, m))
         return c_x, c_u, c_xx, c_uu
 
 
@@ -232,6 +328,87 @@ def lqr_backward(F, C):
         V_xx = Q_xx - T(K[:, h]) @ Q_uu @ K[:, h]
         V_xx = (V_xx + T(V_xx)) / dtype.type(2)
     return k, K
+
+
+def lambda_adjust(reg_lambda, multiplier, consts, increase):
+    """``lambda_adjust`` (``lqr_solver.py:21-37``) on scalars."""
+    factor, lambda_min = consts
+    if increase:
+        multiplier = max(multiplier * factor, factor)
+        reg_lambda = max(reg_lambda * multiplier, lambda_min)
+    else:
+        multiplier = min(1 / factor, multiplier / factor)
+        reg_lambda = reg_lambda * multiplier if reg_lambda * multiplier >= lambda_min else 0
+    reg_lambda = max(reg_lambda, lambda_min)
+    if reg_lambda > 1e10:
+        reg_lambda = 1e10
+    return reg_lambda, multiplier
+
+
+def _is_pd_and_invert(Mx):
+    """``isPD_and_invert`` (``lqr_solver.py:157-163``): Cholesky test, inverse as L^-T L^-1.  NumPy raises where
+    jnp would return NaN; both mean "not positive definite"."""
+    try:
+        L = np.linalg.cholesky(Mx)
+    except np.linalg.LinAlgError:
+        return False, None
+    if np.isnan(np.sum(L)):
+        return False, None
+    Li = np.linalg.inv(L)
+    return True, Li.T @ Li
+
+
+def lqg_backward(F, C, reg_lambda, multiplier, damping_consts, reg_type="V"):
+    """``LQG`` (``lqr_solver.py:89-154``) per trajectory.  C = (c_x, c_u, c_xx, c_uu, c_ux[N,H,m,d]).
+    reg_lambda / multiplier: scalars or [N].  Returns k, K (zero rows where no lambda was found), lam[N], mult[N],
+    gains_lin[N], gains_quad[N] (NaN there), ok[N]."""
+    Fx, Fu = F
+    c_x, c_u, c_xx, c_uu, c_ux = C
+    N, H, d, m = Fu.shape
+    dtype = Fx.dtype
+    lam = np.broadcast_to(np.asarray(reg_lambda, dtype=np.float64), (N,)).copy()
+    mult = np.broadcast_to(np.asarray(multiplier, dtype=np.float64), (N,)).copy()
+    k = np.zeros((N, H, m), dtype=dtype)
+    K = np.zeros((N, H, m, d), dtype=dtype)
+    gl = np.full(N, np.nan)
+    gq = np.full(N, np.nan)
+    ok = np.zeros(N, dtype=bool)
+    for n in range(N):
+        counter = 0
+        while True:
+            counter += 1
+            if counter >= 10:                                               # :100-103
+                k[n], K[n] = 0, 0
+                break
+            V_x, V_xx = np.zeros(d, dtype=dtype), np.zeros((d, d), dtype=dtype)
+            g_lin, g_quad = 0.0, 0.0
+            success = True
+            rl = dtype.type(lam[n])
+            for h in range(H - 1, -1, -1):
+                fx, fu = Fx[n, h], Fu[n, h]
+                Q_x, Q_u = c_x[n, h] + fx.T @ V_x, c_u[n, h] + fu.T @ V_x
+                Q_xx = c_xx[n, h] + fx.T @ V_xx @ fx
+                Q_ux = c_ux[n, h] + fu.T @ V_xx @ fx
+                Q_uu = c_uu[n, h] + fu.T @ V_xx @ fu
+                if reg_type == "Q":                                         # :121-125
+                    Q_uu_reg, Q_ux_reg = Q_uu + rl * np.eye(m, dtype=dtype), Q_ux
+                else:                                                       # :126-129
+                    Q_uu_reg, Q_ux_reg = Q_uu + rl * fu.T @ fu, Q_ux + rl * fu.T @ fx
+                pd, Qi = _is_pd_and_invert(Q_uu_reg)
+                if not pd:
+                    success = False
+                    break
+                K[n, h], k[n, h] = -Qi @ Q_ux_reg, -Qi @ Q_u
+                V_x = Q_x + K[n, h].T @ Q_uu @ k[n, h] + K[n, h].T @ Q_u + Q_ux.T @ k[n, h]      # :134
+                V_xx = Q_xx + K[n, h].T @ Q_uu @ K[n, h] + K[n, h].T @ Q_ux + Q_ux.T @ K[n, h]   # :135
+                V_xx = (V_xx + V_xx.T) / dtype.type(2)
+                g_lin += k[n, h] @ Q_u                                      # :143
+                g_quad += k[n, h] @ Q_uu @ k[n, h]                          # :144
+            if success:
+                ok[n], gl[n], gq[n] = True, g_lin, g_quad
+                break
+            lam[n], mult[n] = lambda_adjust(lam[n], mult[n], damping_consts, True)
+    return k, K, lam, mult, gl, gq, ok
 
 
 # ----------------------------------------------------------------------------- iLQR

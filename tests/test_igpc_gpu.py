@@ -19,7 +19,13 @@ def _np(t):
 
 
 def _envs(kind, H):
-    from deluca_b200.envs.classic import Cartpole, Pendulum, PlanarQuadrotor, QuadCost
+    from deluca_b200.envs.classic import Cartpole, Pendulum, PlanarQuadrotor, QuadCost, Reacher
+    if kind == "reacher":
+        kw = dict(H=H, dt=0.05, g=9.81)
+        o_true, o_sim = OG.Reacher(m2=1.1, **kw), OG.Reacher(**kw)
+        d_true, d_sim = Reacher.create(m2=1.1, **kw), Reacher.create(**kw)
+        q = [0.0, 0.0, 0.1, 0.1, 10.0, 10.0]
+        return o_true, o_sim, OG.QuadCost(o_sim.goal_state, q, 0.01), d_true, d_sim, QuadCost([0.0] * 6, q, 0.01)
     if kind == "quadrotor":
         o_true, o_sim = OG.PlanarQuadrotor(H=H, wind=0.1), OG.PlanarQuadrotor(H=H)
         d_true, d_sim = PlanarQuadrotor.create(H=H, wind=0.1), PlanarQuadrotor.create(H=H)
@@ -42,7 +48,7 @@ def _start(o_env, N, seed=0):
     return (o_env.init(N, np.float32) + 0.05 * rng.standard_normal((N, o_env.d))).astype(np.float32)
 
 
-@pytest.mark.parametrize("kind", ["pendulum", "cartpole", "quadrotor"])
+@pytest.mark.parametrize("kind", ["pendulum", "cartpole", "quadrotor", "reacher"])
 def test_rollout_linearize_riccati(kind):
     from deluca_b200.envs.classic import PendulumState
     from deluca_b200.igpc.lqr_solver import LQR
@@ -108,7 +114,8 @@ def test_gpc_rollout_matches_oracle(w_is):
         np.testing.assert_allclose(_np(Ug)[ok], Uo[ok], rtol=1e-2, atol=2e-3)
 
 
-@pytest.mark.parametrize("kind,fix", [("pendulum", False), ("pendulum", True), ("cartpole", True), ("quadrotor", True)])
+@pytest.mark.parametrize("kind,fix", [("pendulum", False), ("pendulum", True), ("cartpole", True), ("quadrotor", True),
+                                      ("reacher", True)])
 def test_ilqr_loop_matches_oracle(kind, fix):
     from deluca_b200.envs.classic import PendulumState
     from deluca_b200.igpc.ilqr import iLQR
@@ -153,13 +160,14 @@ def test_igpc_and_ilc_loops(algo):
 
 
 def test_single_step_env_calls():
-    from deluca_b200.envs.classic import Cartpole, Pendulum
-    for Env, O in ((Pendulum, OG.Pendulum), (Cartpole, OG.Cartpole)):
+    from deluca_b200.envs.classic import Cartpole, Pendulum, Reacher
+    for Env, O in ((Pendulum, OG.Pendulum), (Cartpole, OG.Cartpole), (Reacher, OG.Reacher)):
         env, o = Env.create(), O()
         state, _ = env.init()
         x = o.init(1, np.float64)
+        np.testing.assert_allclose(_np(state.arr), x[0], rtol=1e-6, atol=1e-6)
         for t in range(5):
-            u = np.array([[0.3 * (t - 2)]])
+            u = np.full((1, o.m), 0.3 * (t - 2))
             state, obs = env(state, _t(u[0]))
             x = o.step(x, u)
             np.testing.assert_allclose(_np(obs), x[0], rtol=1e-5, atol=1e-6)
@@ -181,3 +189,50 @@ def test_config3_size_runs():
     c0 = rollout(env, cost, U0, start_state=st)[2]
     c = iLQR(env, cost, U0, 20, start_state=st, fix_backtracking=True)[4]
     assert bool(torch.isfinite(c).all()) and bool((c <= c0 * (1 + 1e-5)).all()) and bool((c < c0).any())
+
+
+@pytest.mark.parametrize("reg_type", ["Q", "V"])
+def test_lqg_backward_matches_oracle(reg_type):
+    """deluca/igpc/lqr_solver.py:89-163 on the device: gains, value-gain estimates and the lambda schedule."""
+    from deluca_b200.igpc.lqr_solver import LQG, LQR
+    rng = np.random.default_rng(21)
+    N, H, d, m = 200, 25, 6, 2
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    Fx = f32(np.eye(d) + 0.1 * rng.standard_normal((N, H, d, d)))
+    Fu = f32(0.3 * rng.standard_normal((N, H, d, m)))
+    S, R = rng.standard_normal((N, H, d, d)), rng.standard_normal((N, H, m, m))
+    c_xx = f32(np.einsum("nhij,nhkj->nhik", S, S) / d + 0.1 * np.eye(d))
+    c_uu = np.einsum("nhij,nhkj->nhik", R, R) / m + 0.2 * np.eye(m)
+    c_uu[1::4] = -0.5 * np.eye(m)                    # needs lambda > 0.5 (type Q)
+    c_uu[2::40] = -1e12 * np.eye(m)                  # nothing helps: the reference returns None, None
+    c_uu = f32(c_uu)
+    c_x, c_u = f32(rng.standard_normal((N, H, d))), f32(rng.standard_normal((N, H, m)))
+    c_ux = f32(0.05 * rng.standard_normal((N, H, m, d)))
+    F, C = (Fx, Fu), (c_x, c_u, c_xx, c_uu, c_ux)
+    lam0 = np.where(np.arange(N) % 3 == 0, 0.0, 0.01)
+    consts = (10.0, 1e-3)
+    ko, Ko, lamo, multo, glo, gqo, oko = OG.lqg_backward(tuple(a.astype(np.float64) for a in F),
+                                                       tuple(a.astype(np.float64) for a in C), lam0, 1.0, consts, reg_type)
+    k, K, (lam, mult, gl, gq) = LQG(tuple(_t(a) for a in F), tuple(_t(a) for a in C), _t(lam0), 1.0, consts, reg_type)
+    ok = np.isfinite(_np(gl))
+    # the PD decision is discrete: allow a handful of borderline trajectories to take one more / one fewer attempt
+    same = (ok == oko) & np.isclose(_np(lam), lamo, rtol=1e-5)
+    assert same.mean() > 0.97 and (~oko).sum() >= 5 and (lamo[oko] > 0.5).sum() >= 20
+    np.testing.assert_allclose(_np(mult)[same], multo[same], rtol=1e-5)
+    g = same & oko
+    np.testing.assert_allclose(_np(K)[g], Ko[g], rtol=2e-3, atol=2e-4 * np.abs(Ko[g]).max())
+    np.testing.assert_allclose(_np(k)[g], ko[g], rtol=2e-3, atol=2e-4 * np.abs(ko[g]).max())
+    np.testing.assert_allclose(_np(gl)[g], glo[g], rtol=2e-3, atol=1e-3 * np.abs(glo[g]).max())
+    np.testing.assert_allclose(_np(gq)[g], gqo[g], rtol=2e-3, atol=1e-3 * np.abs(gqo[g]).max())
+    assert (_np(K)[same & ~oko] == 0).all()
+    # lambda = 0, c_ux = 0 on the well-posed trajectories: LQG == LQR (same device arithmetic up to rounding)
+    sel = np.arange(N)[(np.arange(N) % 4 != 1) & (np.arange(N) % 40 != 2)]
+    Fs, Cs = tuple(_t(a[sel]) for a in F), tuple(_t(a[sel]) for a in C[:4])
+    k0, K0 = LQR(Fs, Cs)
+    k1, K1, _ = LQG(Fs, Cs + (torch.zeros(len(sel), H, m, d, device="cuda"),), 0.0, 1.0, consts, reg_type)
+    np.testing.assert_allclose(_np(K1), _np(K0), rtol=1e-3, atol=1e-4 * float(K0.abs().max()))
+    # unbatched call returns the reference's scalars / None
+    n_bad = int(np.arange(N)[~oko][0])
+    kb, Kb, info = LQG(tuple(_t(a[n_bad]) for a in F), tuple(_t(a[n_bad]) for a in C), float(lam0[n_bad]), 1.0, consts,
+                       reg_type)
+    assert kb is None and Kb is None and info[2] is None and info[0] == 1e10

@@ -2,9 +2,28 @@
 // One thread per breath; all state in registers (DelayLung's two valve histories in a local
 // ring); per step five/six coalesced 4-byte stores per thread ([T,N] time-major series), which is
 // what bounds the kernel (HBM writes).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace dlc {
+
+// single-instruction special functions (MUFU.EX2 / LG2 / RCP); the wrappers pin the PTX so no slow path is emitted
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2f_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct LungArgs {
   DlcLungParams p;
@@ -50,8 +69,78 @@ __device__ __forceinline__ float interp_knots(const DlcLungParams& p, const floa
   return dx == 0.f ? f0 : f0 + __fdiv_rn(x - x0, dx) * df;
 }
 
-template <int SIM, int NK>
+// t mod period for 0 <= t < 2^20 * period, bit-identical to fmodf without a divide: q = floor(t * (1/period)) is
+// within one of the true quotient; the FMA residual t - q*period is then the correctly rounded value of a number
+// that is exactly representable whenever it lies in [-period, period), so its sign / size tells which way q was
+// off, and the residual recomputed with the corrected quotient is exact.
+__device__ __forceinline__ float fmod_fast(float t, float period, float inv_period, float t_max) {
+  // one unsigned compare: negative t (sign bit), NaN and t >= t_max all take the library path
+  if (__builtin_expect(__float_as_uint(t) >= __float_as_uint(t_max), 0)) return fmodf(t, period);
+  const float q = floorf(t * inv_period);
+  float r = fmaf(-q, period, t);
+  if (__builtin_expect(r < 0.f || r >= period, 0)) r = fmaf(-(r < 0.f ? q - 1.0f : q + 1.0f), period, t);
+  return r;
+}
+
+// One segment of the waveform table: the interpolant on [x0, x1) is f0 + (x - x0) * sl.  Episodes dwell ~30 steps
+// in a segment, so the knot search (searchsorted(side='right') clipped to [1, NK-1], as jnp.interp) only runs when
+// x leaves the cached segment; the values are the same either way.
+struct Seg {
+  float x0, x1, f0, sl;
+};
+
+template <int NK>
+__device__ __forceinline__ void seg_search(const DlcLungParams& p, const float* kf, float x, Seg& s) {
+  float x0, x1, f0, f1;
+  if (NK > 0) {
+    x0 = p.kx[0]; x1 = p.kx[1]; f0 = kf[0]; f1 = kf[1];
+#pragma unroll
+    for (int k = 1; k < NK - 1; ++k) {
+      const bool adv = p.kx[k] <= x;
+      x0 = adv ? p.kx[k] : x0;
+      x1 = adv ? p.kx[k + 1] : x1;
+      f0 = adv ? kf[k] : f0;
+      f1 = adv ? kf[k + 1] : f1;
+    }
+  } else {
+    int i = 1;
+#pragma unroll 1
+    for (int k = 1; k < p.nk - 1; ++k) i += (p.kx[k] <= x) ? 1 : 0;
+    x0 = p.kx[i - 1]; x1 = p.kx[i]; f0 = kf[i - 1]; f1 = kf[i];
+  }
+  const float dx = x1 - x0;
+  s.x0 = x0; s.x1 = x1; s.f0 = f0;
+  s.sl = dx == 0.f ? 0.f : __fdiv_rn(f1 - f0, dx);
+}
+
+template <int NK>
+__device__ __forceinline__ float interp_seg(const DlcLungParams& p, const float* kf, float x, Seg& s) {
+  if (__builtin_expect(!(s.x0 <= x && x < s.x1), 0)) seg_search<NK>(p, kf, x, s);
+  return fmaf(x - s.x0, s.sl, s.f0);
+}
+
+// tanh(z) + 1 = 2 e / (1 + e), e = exp(2z): relative accuracy ~3e-7 everywhere (tanhf(z) + 1 loses it for z << 0);
+// z is capped at 10, where the float32 value is already 2.
+__device__ __forceinline__ float tanh_plus_one(float z) {
+  const float e = exp2f_approx(fminf(z, 10.f) * 2.8853900817779268f);
+  return __fdividef(e + e, 1.0f + e);
+}
+
+// x^(1/3) for x > 0 (NaN for x < 0, like the reference's pow): ex2(lg2(x)/3) refined by one Newton step (<= 1 ulp).
+__device__ __forceinline__ float cbrt_pos(float x) {
+  float r = exp2f_approx(lg2f_approx(x) * 0.3333333333333333f);
+  const float r2 = r * r;
+  const float res = fmaf(r2, r, -x);
+  const float rc = rcpf_approx(3.0f * r2);
+  if (x > 0.f && x < 3.0e38f) r = fmaf(-res, rc, r);
+  return r;
+}
+
+// MODE >= 0 fixes p.mode at compile time (the closed-loop episode is the hot instance), MODE < 0 reads it; ALLOUT
+// promises that all six series pointers are non-NULL.
+template <int SIM, int NK, int MODE, bool ALLOUT>
 __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
+  extern __shared__ float ring[];                                  // DelayLung valve histories [2][delay][blockDim]
   const DlcLungParams& p = a.p;
   const DlcLungBuffers& b = a.b;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,98 +156,127 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   float steps = b.steps_io[n], target = b.target_io[n];
   float pipe = SIM == DLC_SIM_DELAY ? b.pipe_pressure_io[n] : 0.f;
   float obs_p = b.obs_pressure_io[n], obs_t = b.obs_time_io[n];
-  float cp = b.pid_p_io[n], ci = b.pid_i_io[n], cd = b.pid_d_io[n], ctime = b.pid_time_io[n], cdt = b.pid_dt_io[n];
-  int csteps = b.pid_steps_io[n];
-  float etime = b.exp_time_io[n], edt = b.exp_dt_io[n];
-  int esteps = b.exp_steps_io[n];
-  float hin[SIM == DLC_SIM_DELAY ? DLC_MAX_DELAY : 1], hout[SIM == DLC_SIM_DELAY ? DLC_MAX_DELAY : 1];
+  float cp = b.pid_p_io[n], ci = b.pid_i_io[n], cd = b.pid_d_io[n];
+  // controller bookkeeping (dt = max(default_dt, t - proper_time(time)); time = t; steps += 1) only depends on the
+  // last two observation times: carried as (previous, current) and formed once after the loop
+  float ctime = b.pid_time_io[n], etime = b.exp_time_io[n], prev_ctime = ctime, prev_etime = etime;
+  // ring layout [slot][thread] with a row stride of blockDim + 1 words: the per-step access (slot fixed, thread
+  // varies) and the transposing copies below (thread fixed, slot varies) are both bank-conflict-free
+  const int rs = blockDim.x + 1;
+  float* hin = ring + threadIdx.x;
+  float* hout = ring + (size_t)p.delay * rs + threadIdx.x;
   int pos = 0;  // ring slot of logical index 0 (the newest entry)
+  // the caller's histories are [N, delay]: a full CTA owns one contiguous chunk and copies it with coalesced
+  // accesses (the per-thread rows are 4 * delay bytes apart); the last, partial CTA copies row by row
+  const bool full_cta = (int64_t)(blockIdx.x + 1) * blockDim.x <= p.N;
   if (SIM == DLC_SIM_DELAY) {
-    for (int k = 0; k < p.delay; ++k) {
-      hin[k] = b.in_history_io[n * p.delay + k];
-      hout[k] = b.out_history_io[n * p.delay + k];
+    if (full_cta) {
+      const int64_t base = (int64_t)blockIdx.x * blockDim.x * p.delay;
+      const int count = blockDim.x * p.delay;
+      for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const int e = i / p.delay, k = i - e * p.delay;
+        ring[k * rs + e] = b.in_history_io[base + i];
+        ring[(p.delay + k) * rs + e] = b.out_history_io[base + i];
+      }
+      __syncthreads();
+    } else {
+      for (int k = 0; k < p.delay; ++k) {
+        hin[k * rs] = b.in_history_io[n * p.delay + k];
+        hout[k * rs] = b.out_history_io[n * p.delay + k];
+      }
     }
   }
   bool bad = false, ran_env = false;
-  const bool run_ctrl = p.mode != DLC_LUNG_MODE_ENV_ONLY, run_env = p.mode != DLC_LUNG_MODE_CTRL_ONLY;
+  const int mode = MODE >= 0 ? MODE : p.mode;
+  const bool run_ctrl = mode != DLC_LUNG_MODE_ENV_ONLY, run_env = mode != DLC_LUNG_MODE_CTRL_ONLY;
+  // running output pointers: one add per series and step instead of re-forming t * N + n
+  const int64_t N = p.N;
+  float* o_ts = b.timestamp_out ? b.timestamp_out + n : nullptr;
+  float* o_uin = b.u_in_out ? b.u_in_out + n : nullptr;
+  float* o_uout = b.u_out_out ? b.u_out_out + n : nullptr;
+  float* o_pr = b.pressure_out ? b.pressure_out + n : nullptr;
+  float* o_flow = b.flow_out ? b.flow_out + n : nullptr;
+  float* o_tgt = b.target_out ? b.target_out + n : nullptr;
+  const float* i_uin = b.u_in_in ? b.u_in_in + n : nullptr;
+  const float* i_uout = b.u_out_in ? b.u_out_in + n : nullptr;
+  const float period = p.period, xp_in = p.xp_in, dec = p.pid_decay, dt = p.dt, run_dt = p.run_dt;
+  const float inv_period = __fdiv_rn(1.0f, p.period), t_max = 1048576.0f * p.period;
+  const float pc_r0sq = __fdiv_rn(SIM == DLC_SIM_BALLOON ? p.PC : p.d_C, p.r0_sq), inv_dR = __fdiv_rn(1.0f, p.d_R);
+  const float early_end = (float)p.delay;
+  Seg seg_pid = {1.f, 0.f, 0.f, 0.f}, seg_out = {1.f, 0.f, 0.f, 0.f};   // empty segments: first use searches
 
   for (int t = 0; t < p.T; ++t) {
     const float pr_emit = obs_p;                                   // run_controller.py:118
     float u_in, u_out;
     if (run_ctrl) {
-    // ---- PID                                                     controllers/_pid.py:77-102
-    const float xo = fmod_pos(obs_t, p.period);                      // shared by PID (at) and Expiratory (is_in)
-    const float tgt = interp_knots<NK>(p, kf, xo);
-    const float err = tgt - obs_p;
-    const float np_ = err;
-    const float ni = ci + p.pid_decay * (err - ci);
-    const float nd = cd + p.pid_decay * ((err - cp) - cd);
-    cp = np_; ci = ni; cd = nd;
-    u_in = (np_ * k0 + ni * k1) + nd * k2;                          // Dense(1, use_bias=False)
-    u_in = fminf(fmaxf(u_in, 0.f), 100.f);                          // lax.clamp(0, u, 100)
-    cdt = fmaxf(p.default_dt, obs_t - (isinf(ctime) ? 0.f : ctime));
-    ctime = obs_t;
-    ++csteps;
-    // ---- Expiratory                                              controllers/_expiratory.py:35-45
-    u_out = (xo <= p.xp_in) ? 0.f : 1.f;
-    edt = fmaxf(p.default_dt, obs_t - (isinf(etime) ? 0.f : etime));
-    etime = obs_t;
-    ++esteps;
+      // ---- PID                                                   controllers/_pid.py:77-102
+      const float xo = fmod_fast(obs_t, period, inv_period, t_max);   // shared by PID (at) and Expiratory (is_in)
+      const float err = interp_seg<NK>(p, kf, xo, seg_pid) - obs_p;
+      const float ni = ci + dec * (err - ci);
+      const float nd = cd + dec * ((err - cp) - cd);
+      cp = err; ci = ni; cd = nd;
+      u_in = (err * k0 + ni * k1) + nd * k2;                        // Dense(1, use_bias=False)
+      u_in = fminf(fmaxf(u_in, 0.f), 100.f);                        // lax.clamp(0, u, 100)
+      // ---- Expiratory                                            controllers/_expiratory.py:35-45
+      u_out = (xo <= xp_in) ? 0.f : 1.f;
+      prev_ctime = ctime; prev_etime = etime;
+      ctime = obs_t; etime = obs_t;
     } else {
-      u_in = b.u_in_in[(int64_t)t * p.N + n];
-      u_out = b.u_out_in[(int64_t)t * p.N + n];
+      u_in = *i_uin; i_uin += N;
+      u_out = *i_uout; i_uout += N;
     }
     // ---- simulator
     if (!run_env) {
-    } else if (SIM == DLC_SIM_BALLOON) {                                   // envs/_balloon_lung.py:100-146
-      float valve = 1.0f * (tanhf(0.03f * (3.0f * u_in - 130.f)) + 1.0f);
+    } else if (SIM == DLC_SIM_BALLOON) {                            // envs/_balloon_lung.py:100-146
+      float valve = tanh_plus_one(0.03f * (3.0f * u_in - 130.f));
       valve = fminf(fmaxf(valve, 0.f), 1.72f);
       float flow = fminf(fmaxf(valve * p.R, 0.f), 2.0f);
       if (pressure > p.peep_valve) flow -= (u_out > 0.f ? 1.0f : 0.0f) * 0.05f * pressure;
-      volume += flow * p.dt;
+      volume += flow * dt;
       if (p.leak) volume += p.leak_coef * (p.min_volume - volume);
-      // (3V/4pi)^(1/3): cbrtf differs from the reference's pow(x, float32(1/3)) by < 1 ulp
-      const float r = cbrtf(__fdiv_rn(3.0f * volume, 12.566370614359172f));
-      const float q = __fdiv_rn(p.r0, r);
-      const float q2 = q * q;
-      pressure = p.P0 + __fdiv_rn(p.PC * (1.0f - q2 * q2 * q2), p.r0_sq * r);
+      const float r = cbrt_pos(volume * 0.238732414637843f);       // (3V / 4pi)^(1/3)
+      const float ir = rcpf_approx(r);
+      const float q = p.r0 * ir, q2 = q * q;
+      pressure = fmaf(pc_r0sq * fmaf(-q2 * q2, q2, 1.0f), ir, p.P0);   // P0 + PC (1 - (r0/r)^6) / (r0^2 r)
       steps = time + 1.0f;                                          // sic (:135)
-      time = time + p.dt;                                           // target = waveform.at(time): only the
+      time = time + dt;                                             // target = waveform.at(time): only the
       ran_env = true;                                               // last one survives, formed after the loop
       obs_p = pressure;
       obs_t = time;
     } else {                                                        // envs/_delay_lung.py:75-133
       const float uin_pos = u_in > 0.f ? u_in : 0.f;
       pos = pos == 0 ? p.delay - 1 : pos - 1;                       // roll(+1); [0] <- u
-      hin[pos] = uin_pos;
-      hout[pos] = u_out;
+      hin[pos * rs] = uin_pos;
+      hout[pos * rs] = u_out;
       obs_p = pressure;                                             // observation of the pre-dynamics state
       obs_t = time;
-      const float flow = __fdiv_rn(pressure, p.d_R);
-      volume = fmaxf(volume + flow * p.dt, p.min_volume);
-      const float r = cbrtf(__fdiv_rn(3.0f * volume, 12.566370614359172f));
-      const float q = __fdiv_rn(p.r0, r);
-      const float q2 = q * q;
-      const float lung_p = __fdiv_rn(p.d_C * (1.0f - q2 * q2 * q2), p.r0_sq * r);
-      const bool early = time < (float)p.delay;                     // seconds vs steps, sic (:88-96)
+      const float flow = pressure * inv_dR;
+      volume = fmaxf(volume + flow * dt, p.min_volume);
+      const float r = cbrt_pos(volume * 0.238732414637843f);
+      const float ir = rcpf_approx(r);
+      const float q = p.r0 * ir, q2 = q * q;
+      const float lung_p = pc_r0sq * fmaf(-q2 * q2, q2, 1.0f) * ir;
+      const bool early = time < early_end;                          // seconds vs steps, sic (:88-96)
       const float impulse = early ? 0.f : p.control_gain * uin_pos;
       const float peep = early ? 0.f : u_out;
       pipe = p.inertia * pipe + impulse;
       pressure = fmaxf(0.f, pipe - lung_p);
       if (peep != 0.f) pipe *= 0.995f;
       steps = time + 1.0f;
-      time = time + p.dt;
+      time = time + dt;
       ran_env = true;
     }
     // ---- emitted series                                          run_controller.py:128-141
-    const float ts = p.dt * steps - p.run_dt;
-    const int64_t o = (int64_t)t * p.N + n;
-    if (b.timestamp_out) b.timestamp_out[o] = ts;
-    if (b.u_in_out) b.u_in_out[o] = u_in;
-    if (b.u_out_out) b.u_out_out[o] = u_out;
-    if (b.pressure_out) b.pressure_out[o] = pr_emit;
-    if (b.flow_out) b.flow_out[o] = p.env_flow;
-    if (b.target_out) b.target_out[o] = interp_knots<NK>(p, kf, fmod_pos(ts, p.period));   // waveform.at(timestamps), :207
+    const float ts = dt * steps - run_dt;
+    if (ALLOUT || o_ts) { *o_ts = ts; o_ts += N; }
+    if (ALLOUT || o_uin) { *o_uin = u_in; o_uin += N; }
+    if (ALLOUT || o_uout) { *o_uout = u_out; o_uout += N; }
+    if (ALLOUT || o_pr) { *o_pr = pr_emit; o_pr += N; }
+    if (ALLOUT || o_flow) { *o_flow = p.env_flow; o_flow += N; }
+    if (ALLOUT || o_tgt) {                                          // waveform.at(timestamps), :207
+      *o_tgt = interp_seg<NK>(p, kf, fmod_fast(ts, period, inv_period, t_max), seg_out);
+      o_tgt += N;
+    }
     bad |= !isfinite(pressure);
   }
 
@@ -166,16 +284,35 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   b.steps_io[n] = steps; b.time_io[n] = time; b.volume_io[n] = volume; b.pressure_io[n] = pressure;
   b.target_io[n] = target;
   b.obs_pressure_io[n] = obs_p; b.obs_time_io[n] = obs_t;
-  b.pid_p_io[n] = cp; b.pid_i_io[n] = ci; b.pid_d_io[n] = cd; b.pid_time_io[n] = ctime; b.pid_dt_io[n] = cdt;
-  b.pid_steps_io[n] = csteps;
-  b.exp_time_io[n] = etime; b.exp_dt_io[n] = edt; b.exp_steps_io[n] = esteps;
+  b.pid_p_io[n] = cp; b.pid_i_io[n] = ci; b.pid_d_io[n] = cd;
+  if (run_ctrl && p.T > 0) {
+    b.pid_time_io[n] = ctime;
+    b.pid_dt_io[n] = fmaxf(p.default_dt, ctime - (isinf(prev_ctime) ? 0.f : prev_ctime));
+    b.pid_steps_io[n] += p.T;
+    b.exp_time_io[n] = etime;
+    b.exp_dt_io[n] = fmaxf(p.default_dt, etime - (isinf(prev_etime) ? 0.f : prev_etime));
+    b.exp_steps_io[n] += p.T;
+  }
   if (SIM == DLC_SIM_DELAY) {
     b.pipe_pressure_io[n] = pipe;
-    for (int k = 0; k < p.delay; ++k) {
-      int s = pos + k;
-      s -= s >= p.delay ? p.delay : 0;
-      b.in_history_io[n * p.delay + k] = hin[s];
-      b.out_history_io[n * p.delay + k] = hout[s];
+    if (full_cta) {                                                 // pos is the same in every thread (T steps each)
+      __syncthreads();
+      const int64_t base = (int64_t)blockIdx.x * blockDim.x * p.delay;
+      const int count = blockDim.x * p.delay;
+      for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const int e = i / p.delay, k = i - e * p.delay;
+        int s = pos + k;
+        s -= s >= p.delay ? p.delay : 0;
+        b.in_history_io[base + i] = ring[s * rs + e];
+        b.out_history_io[base + i] = ring[(p.delay + s) * rs + e];
+      }
+    } else {
+      for (int k = 0; k < p.delay; ++k) {
+        int s = pos + k;
+        s -= s >= p.delay ? p.delay : 0;
+        b.in_history_io[n * p.delay + k] = hin[s * rs];
+        b.out_history_io[n * p.delay + k] = hout[s * rs];
+      }
     }
   }
   if (b.status_out) b.status_out[n] = bad ? DLC_STATUS_NONFINITE : 0;
@@ -208,12 +345,33 @@ extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLun
   a.b = *b;
   const unsigned grid = (unsigned)((p->N + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
+  // hot instance: default 7-knot waveform table, closed loop, all six series requested
+  const bool hot = p->nk == 7 && p->mode == DLC_LUNG_MODE_CLOSED_LOOP && b->timestamp_out && b->u_in_out &&
+                   b->u_out_out && b->pressure_out && b->flow_out && b->target_out;
   if (p->sim == DLC_SIM_BALLOON) {
-    if (p->nk == 7) lung_pid_kernel<DLC_SIM_BALLOON, 7><<<grid, 128, 0, st>>>(a);
-    else lung_pid_kernel<DLC_SIM_BALLOON, 0><<<grid, 128, 0, st>>>(a);
+    if (hot) lung_pid_kernel<DLC_SIM_BALLOON, 7, DLC_LUNG_MODE_CLOSED_LOOP, true><<<grid, 128, 0, st>>>(a);
+    else if (p->nk == 7) lung_pid_kernel<DLC_SIM_BALLOON, 7, -1, false><<<grid, 128, 0, st>>>(a);
+    else lung_pid_kernel<DLC_SIM_BALLOON, 0, -1, false><<<grid, 128, 0, st>>>(a);
   } else {
-    if (p->nk == 7) lung_pid_kernel<DLC_SIM_DELAY, 7><<<grid, 128, 0, st>>>(a);
-    else lung_pid_kernel<DLC_SIM_DELAY, 0><<<grid, 128, 0, st>>>(a);
+    const size_t smem = 2 * (size_t)p->delay * 129 * sizeof(float);   // 64.5 KB at the maximum delay of 64
+    if (smem > 48 * 1024) {
+      static std::once_flag once;
+      static cudaError_t attr_rc[3];
+      std::call_once(once, [] {
+        const int cap = 2 * DLC_MAX_DELAY * 129 * 4;
+        attr_rc[0] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        attr_rc[1] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, -1, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        attr_rc[2] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 0, -1, false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      });
+      for (int i = 0; i < 3; ++i)
+        if (attr_rc[i] != cudaSuccess) return cuda_status(attr_rc[i], "lung_pid_kernel shared-memory attribute");
+    }
+    if (hot) lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, true><<<grid, 128, smem, st>>>(a);
+    else if (p->nk == 7) lung_pid_kernel<DLC_SIM_DELAY, 7, -1, false><<<grid, 128, smem, st>>>(a);
+    else lung_pid_kernel<DLC_SIM_DELAY, 0, -1, false><<<grid, 128, smem, st>>>(a);
   }
   return cuda_status(cudaGetLastError(), "lung_pid_kernel launch");
 }

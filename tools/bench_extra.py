@@ -60,6 +60,9 @@ for name, Env in (("balloon", BalloonLung), ("delay", DelayLung)):
                                                  "bytes_per_env_step": 24}}
         del p, b, series
         torch.cuda.empty_cache()
+if os.environ.get("DLC_EXTRA_ONLY") == "lung":
+    print(json.dumps(out, indent=1))
+    sys.exit(0)
 
 # ---- 8(f) rank 1: value + gradient of train_controller.rollout w.r.t. the PID gains, 2^20 breaths x T=29
 from deluca_b200 import _abi

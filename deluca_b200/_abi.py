@@ -57,6 +57,14 @@ class DlcLungParams(ctypes.Structure):
     ]
 
 
+class DlcSharedGpcParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int64), ("T", ctypes.c_int32), ("d", ctypes.c_int32), ("m", ctypes.c_int32),
+        ("H", ctypes.c_int32), ("HH", ctypes.c_int32), ("t0", ctypes.c_int32), ("decay", ctypes.c_int32),
+        ("lr_scale", ctypes.c_float), ("reserved", ctypes.c_int32),
+    ]
+
+
 LUNG_BUFFER_FIELDS = [
     "K", "kf", "u_in_in", "u_out_in", "steps_io", "time_io", "volume_io", "pressure_io", "target_io",
     "pipe_pressure_io", "in_history_io", "out_history_io", "obs_pressure_io", "obs_time_io",
@@ -120,6 +128,9 @@ SYMBOLS = {
     "dlc_lds_shared_pack_f32": (ctypes.c_int32, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "dlc_lds_shared_lqr_rollout_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                                         ctypes.c_int32] + [_P] * 7),
+    "dlc_lds_shared_gpc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcSharedGpcParams)]),
+    "dlc_lds_shared_gpc_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcSharedGpcParams)] + [_P] * 12
+                                       + [ctypes.c_size_t, _P]),
     "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),
     "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
     "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 18
@@ -142,7 +153,8 @@ def lib():
                 fn = getattr(L, name)
                 fn.restype = res
                 fn.argtypes = args
-            for which, struct in enumerate((DlcLdsParams, DlcLungParams, DlcLungBuffers, DlcPlanParams)):
+            for which, struct in enumerate((DlcLdsParams, DlcLungParams, DlcLungBuffers, DlcPlanParams,
+                                            DlcSharedGpcParams)):
                 if L.dlc_sizeof(which) != ctypes.sizeof(struct):
                     raise ImportError(f"{struct.__name__}: ctypes layout ({ctypes.sizeof(struct)} B) does not match "
                                       f"the library ({L.dlc_sizeof(which)} B); rebuild libdeluca_b200.so")

@@ -29,6 +29,7 @@ extern "C" size_t dlc_sizeof(int32_t which) {
     case 1: return sizeof(DlcLungParams);
     case 2: return sizeof(DlcLungBuffers);
     case 3: return sizeof(DlcPlanParams);
+    case 4: return sizeof(DlcSharedGpcParams);
     default: return 0;
   }
 }

@@ -1,0 +1,710 @@
+// Shared-dynamics LDS + GPC rollout with a per-env policy tensor M (BASELINE config 5:
+// d = 256, m = 64, H = HH = 16; M[H,m,d] = 1 MiB per env).
+//
+// Reference lines (google/deluca): GPC.get_action / update / policy_loss  deluca/agents/_gpc.py:109-183,
+// LDS.__call__ deluca/envs/_lds.py:102-111, quad_loss _gpc.py:29-40, under vmap with in_axes=None for A, B, K.
+//
+// With HH == H the H window products of policy_loss at step t and the action's own window product read only
+// noises that were known before step t (the newest noise never enters a window until one step later), so a step
+// splits into two kernels that alternate:
+//
+//   gpc_m_stream_kernel  (HBM-bound; one CTA per env, a thread owns two adjacent state coordinates)
+//       M_t      = M_{t-1} + sum_h (-lr_{t-1} g_h) (x) hist_t[h+i]          rank-H update, in place
+//       V_t[h]   = sum_i M_t[i] hist_t[1+h+i],  h = 0..H-1                  H window products
+//     M is read once and written once per env-step (2 MiB at config 5: the algorithmic minimum); both
+//     contractions run on the row while it is in registers (packed fma.rn.f32x2, pairs = the two coordinates).
+//     Rows are prefetched four n-slices ahead with per-thread cp.async (every thread copies exactly the 8 bytes
+//     per row it later consumes, so the pipeline needs no barrier).
+//
+//   gpc_shared_chain_kernel  (FP32-bound; one CTA per 64 envs, batch as the N dimension of dense GEMMs with the
+//   shared operators, register-tiled 8 envs x RT rows per thread, operands k-major in shared memory)
+//       u_t = -K x_t + V_t[H-1];  cost_t;  noise_t = x_t - A x_{t-1} - B u_t;  x_{t+1} = A x_t + B u_t + w_t
+//       y_{h+1} = [A-BK | B][y_h ; V_t[h]] + hist_t[h+H+1]   (h = 0..H-2, y_0 = 0)
+//       du = 2(-K y + V_t[H-1]);  lam = 2y - K'du;  [lam ; g_h] = [A-BK | B]' lam   (h = H-2..0)
+//     and writes -lr_t g_h for the next gpc_m_stream_kernel.
+//
+// Internal workspaces are env-minor ([...][Npad]) so the 8 envs a thread owns are 32 contiguous bytes.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+#pragma nv_diag_suppress 550
+
+namespace dlc {
+namespace sgpc {
+
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2 dup(float a) { return pk(a, a); }
+__device__ __forceinline__ void unpk(f2 p, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+constexpr int kE = 64;        // envs per CTA of the chain kernel
+// a thread of the chain kernel owns envs 4 tx .. 4 tx + 3 and 32 + 4 tx .. 32 + 4 tx + 3 (pairs j = 0..3), so the 8 tx of
+// a warp read 128 contiguous bytes of a Z row per LDS.128 (conflict-free)
+#define EO(j) (((j) < 2) ? (4 * tx + 2 * (j)) : (32 + 4 * tx + 2 * ((j) - 2)))
+constexpr int kKC = 16;       // k-chunk of the staged operator
+constexpr int kThreadsA = 256;
+constexpr int kWS = 3;       // operator chunks in flight (cp.async stages) in the chain kernel
+constexpr int kStages = 4;    // n-slices of M in flight per thread in the stream kernel
+
+// ------------------------------------------------------------------------------------------------ pack
+// FT  [d+m][d]   FT[c][r]  = (A - B K)[r][c] (c < d),  B[r][c-d]      forward chain, k = c
+// Fr  [d][d+m]   Fr[r][c]  = the same matrix, row-major                  adjoint chain, k = r
+// F2T [d+m][d]   F2T[c][r] = A[r][c] (c < d), B[r][c-d]                  env step on [x ; u]
+// nKT [d][m]     nKT[c][n] = -K[n][c]                                    u = -K x
+// nK  [m][d]     nK[n][c]  = -K[n][c]                                    -K' du
+__global__ void pack_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ K,
+                            int d, int m, float* FT, float* Fr, float* F2T, float* nKT, float* nK) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dm = d + m;
+  if (idx < d * dm) {
+    const int r = idx / dm, c = idx % dm;
+    float f, f2v;
+    if (c < d) {
+      double s = (double)A[r * d + c];
+      for (int j = 0; j < m; ++j) s -= (double)B[r * m + j] * (double)K[j * d + c];
+      f = (float)s;
+      f2v = A[r * d + c];
+    } else {
+      f = f2v = B[r * m + (c - d)];
+    }
+    FT[(size_t)c * d + r] = f;
+    Fr[(size_t)r * dm + c] = f;
+    F2T[(size_t)c * d + r] = f2v;
+  }
+  if (idx < m * d) {
+    const int n = idx / d, c = idx % d;
+    const float v = -K[n * d + c];
+    nKT[(size_t)c * m + n] = v;
+    nK[(size_t)n * d + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ state in / out
+struct StateArgs {
+  int64_t N, Npad;
+  int d, P, base;
+  const float* A;
+  float *x_io, *hist_io, *xprev_io;
+  float *Xw, *AXw, *Hw, *Hring;
+};
+
+// one thread per (env, coordinate)
+__global__ void state_in_kernel(StateArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.N * a.d) return;
+  const int64_t env = idx / a.d;
+  const int r = (int)(idx % a.d);
+  a.Xw[(size_t)r * a.Npad + env] = a.x_io[idx];
+  float ax = 0.f;
+  if (a.xprev_io) {
+    const float* xp = a.xprev_io + env * a.d;
+    const float* Ar = a.A + (size_t)r * a.d;
+    for (int c = 0; c < a.d; ++c) ax = fmaf(Ar[c], xp[c], ax);
+  }
+  a.AXw[(size_t)r * a.Npad + env] = ax;
+  for (int j = 0; j < a.P; ++j) {
+    const float h = a.hist_io ? a.hist_io[((size_t)env * a.P + j) * a.d + r] : 0.f;
+    a.Hring[((size_t)env * a.P + j) * a.d + r] = h;
+    a.Hw[((size_t)j * a.d + r) * a.Npad + env] = h;
+  }
+}
+
+__global__ void state_out_kernel(StateArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.N * a.d) return;
+  const int64_t env = idx / a.d;
+  const int r = (int)(idx % a.d);
+  a.x_io[idx] = a.Xw[(size_t)r * a.Npad + env];
+  if (a.hist_io)
+    for (int j = 0; j < a.P; ++j)
+      a.hist_io[((size_t)env * a.P + j) * a.d + r] = a.Hring[((size_t)env * a.P + (a.base + j) % a.P) * a.d + r];
+}
+
+// ------------------------------------------------------------------------------------------------ M stream
+struct StreamArgs {
+  int64_t N, Npad;
+  int base;            // ring slot of hist_t[0]
+  float* M;            // [N][H][MM][D]
+  const float* Hring;  // [Npad][2H][D]
+  const float* Gw;     // [H][MM][Npad], already scaled by -lr
+  float* Vw;           // [H][MM][Npad]
+};
+
+template <int D, int MM, int H, bool UPD, bool FWD>
+__global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
+  constexpr int P = 2 * H, NT = D / 2, NW = NT / 32;
+  static_assert(D % 64 == 0 && (H & (H - 1)) == 0 && H >= 2 && H <= 32, "shape");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  f2* sM = reinterpret_cast<f2*>(smem_raw);                              // [kStages][H][NT]
+  float* sG = reinterpret_cast<float*>(sM + (size_t)kStages * H * NT);   // [MM][H]
+  float* sV = sG + MM * H;                                               // [NW][H][MM]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t env = blockIdx.x;
+  const int k0 = 2 * tid;
+
+  float* Mp = a.M + (size_t)env * H * MM * D + k0;
+  auto issue = [&](int n) {
+    if (n < MM) {
+      f2* dst = sM + (size_t)(n % kStages) * H * NT + tid;
+#pragma unroll
+      for (int i = 0; i < H; ++i) cp_async8(dst + i * NT, Mp + ((size_t)i * MM + n) * D);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) issue(s);
+
+  f2 hp[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j)
+    hp[j] = *reinterpret_cast<const f2*>(a.Hring + ((size_t)env * P + ((a.base + j) % P)) * D + k0);
+  if (UPD) {
+    for (int idx = tid; idx < MM * H; idx += NT) {
+      const int n = idx % MM, h = idx / MM;
+      sG[n * H + h] = a.Gw[((size_t)h * MM + n) * a.Npad + env];
+    }
+    __syncthreads();
+  }
+
+  for (int n = 0; n < MM; ++n) {
+    issue(n + kStages - 1);
+    cp_async_wait<kStages - 1>();
+    const f2* src = sM + (size_t)(n % kStages) * H * NT + tid;
+    float g[H];
+    if (UPD) {
+#pragma unroll
+      for (int h = 0; h < H; h += 2) {
+        const float2 t = *reinterpret_cast<const float2*>(sG + n * H + h);
+        g[h] = t.x;
+        g[h + 1] = t.y;
+      }
+    }
+    f2 acc[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) acc[h] = 0ull;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      f2 mp = src[i * NT];
+      if (UPD) {
+        f2 p1 = 0ull;
+#pragma unroll
+        for (int h = 0; h < H; h += 2) {
+          mp = fma2(dup(g[h]), hp[h + i], mp);
+          p1 = fma2(dup(g[h + 1]), hp[h + 1 + i], p1);
+        }
+        mp = add2(mp, p1);
+        *reinterpret_cast<f2*>(Mp + ((size_t)i * MM + n) * D) = mp;
+      }
+      if (FWD) {
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          acc[h] = fma2(mp, hp[1 + h + i], acc[h]);
+      }
+    }
+    if (FWD) {
+      float v[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float x, y;
+        unpk(acc[h], x, y);
+        v[h] = x + y;
+      }
+      // transposed butterfly: H values over 32 lanes, afterwards lane l holds the warp sum of v[l >> S]
+      int cnt = H, off = 16;
+#pragma unroll
+      for (; cnt > 1; cnt >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < cnt / 2; ++j) {
+          const float send = up ? v[j] : v[j + cnt / 2];
+          const float keep = up ? v[j + cnt / 2] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+#pragma unroll
+      for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+      constexpr int per = 32 / H;  // lanes holding the same h
+      if ((lane % per) == 0) sV[(warp * H + lane / per) * MM + n] = v[0];
+    }
+  }
+  if (FWD) {
+    __syncthreads();
+    for (int idx = tid; idx < MM * H; idx += NT) {  // idx = h * MM + n
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += sV[w * H * MM + idx];
+      a.Vw[(size_t)idx * a.Npad + env] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ shared chain
+struct ChainArgs {
+  int64_t N, Npad;
+  int base;        // ring slot of hist_t[0]
+  int first;       // first step of this call: cost_sum / status are initialised
+  float nlr;       // -lr_t
+  const float *FT, *Fr, *F2T, *nKT, *nK;
+  const float* W;  // [N][d] disturbance of this step, or NULL
+  float *Xw, *AXw, *Hw, *Hring;
+  const float* Vw;
+  float* Gw;
+  float* cost_out;     // [N] of this step, or NULL
+  double* cost_sum;    // [N] or NULL
+  int32_t* status;     // [N] or NULL
+  float* xprev_out;    // [N][d]: x_t as the agent saw it (written on the last step), or NULL
+};
+
+// acc[r][j] (+)= sum_k Wg[k][RT*ty + r] * Z[zoff + k][EO(j) (+1)],  k in [kbeg, kend)
+template <int RT>
+__device__ __forceinline__ void gemm_acc(f2 (&acc)[RT][4], const float* __restrict__ Wg, int kbeg, int kend,
+                                         const float* Z, int zoff, float* sW, int swbuf, int tid) {
+  constexpr int ROWS = 32 * RT, CH = kKC * ROWS, NV = CH / 4;
+  const int nch = (kend - kbeg) / kKC;
+  const float* src = Wg + (size_t)kbeg * ROWS;
+  const int ty = tid >> 3, tx = tid & 7;
+  auto issue = [&](int c) {
+    if (c < nch) {
+      const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)c * CH);
+      float* dst = sW + (c % kWS) * swbuf;
+      for (int i = tid; i < NV; i += kThreadsA) cp_async16(dst + 4 * i, s4 + i);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int c = 0; c < kWS - 1; ++c) issue(c);
+  for (int c = 0; c < nch; ++c) {
+    cp_async_wait<kWS - 2>();
+    __syncthreads();         // chunk c has landed for every thread, and every thread is done with chunk c - 1
+    issue(c + kWS - 1);      // ... whose buffer is refilled now
+    const float* wb = sW + (c % kWS) * swbuf + RT * ty;
+    const float* zb = Z + (size_t)(zoff + kbeg + c * kKC) * kE + 4 * tx;
+#pragma unroll
+    for (int kk = 0; kk < kKC; ++kk) {
+      float w[RT];
+      if constexpr (RT % 4 == 0) {
+#pragma unroll
+        for (int r = 0; r < RT; r += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(wb + kk * ROWS + r);
+          w[r] = t.x; w[r + 1] = t.y; w[r + 2] = t.z; w[r + 3] = t.w;
+        }
+      } else if constexpr (RT % 2 == 0) {
+#pragma unroll
+        for (int r = 0; r < RT; r += 2) {
+          const float2 t = *reinterpret_cast<const float2*>(wb + kk * ROWS + r);
+          w[r] = t.x; w[r + 1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < RT; ++r) w[r] = wb[kk * ROWS + r];
+      }
+      const float4 z0 = *reinterpret_cast<const float4*>(zb + kk * kE);
+      const float4 z1 = *reinterpret_cast<const float4*>(zb + kk * kE + 32);
+      const f2 zp[4] = {pk(z0.x, z0.y), pk(z0.z, z0.w), pk(z1.x, z1.y), pk(z1.z, z1.w)};
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const f2 wr = dup(w[r]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fma2(wr, zp[j], acc[r][j]);
+      }
+    }
+  }
+  __syncthreads();  // the operator buffers and Z may be rewritten by the caller
+}
+
+template <int RT>
+__device__ __forceinline__ void zero_acc(f2 (&acc)[RT][4]) {
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[r][j] = 0ull;
+}
+
+// rows [row0, row0 + nrows) of Z  <-  src[row][env0 + e]   (src env-minor with leading dimension Npad)
+__device__ __forceinline__ void load_rows(float* Z, int row0, int nrows, const float* src, int64_t Npad, int64_t env0,
+                                          int tid) {
+  for (int idx = tid; idx < nrows * (kE / 4); idx += kThreadsA) {
+    const int r = idx / (kE / 4), e4 = idx % (kE / 4);
+    *reinterpret_cast<float4*>(Z + (size_t)(row0 + r) * kE + 4 * e4) =
+        *reinterpret_cast<const float4*>(src + (size_t)r * Npad + env0 + 4 * e4);
+  }
+}
+
+template <int D, int MM, int H>
+__global__ void __launch_bounds__(kThreadsA, 1) gpc_shared_chain_kernel(ChainArgs a) {
+  constexpr int DM = D + MM, P = 2 * H;
+  constexpr int RTD = D / 32, RTM = MM / 32, RTDM = DM / 32;
+  static_assert(D % 32 == 0 && MM % 32 == 0 && D % kKC == 0 && MM % kKC == 0, "shape");
+  constexpr int SWBUF = kKC * DM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sW = reinterpret_cast<float*>(smem_raw);  // [kWS][kKC][<= DM]
+  float* ZA = sW + kWS * SWBUF;                      // [DM][kE]
+  float* ZB = ZA + (size_t)DM * kE;
+  const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
+  const int64_t env0 = (int64_t)blockIdx.x * kE;
+  const int nvalid = (int)min((int64_t)kE, a.N - env0);
+  auto slot = [&](int j) { return (a.base + j) % P; };
+
+  // ---- S0: x_t and v_{H-1} (the action's window product)
+  load_rows(ZA, 0, D, a.Xw, a.Npad, env0, tid);
+  load_rows(ZA, D, MM, a.Vw + (size_t)(H - 1) * MM * a.Npad, a.Npad, env0, tid);
+  __syncthreads();
+  if (a.xprev_out) {
+    for (int idx = tid; idx < kE * D; idx += kThreadsA) {
+      const int e = idx / D, r = idx % D;
+      if (e < nvalid) a.xprev_out[(size_t)(env0 + e) * D + r] = ZA[(size_t)r * kE + e];
+    }
+  }
+  float csum[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) csum[e] = 0.f;
+
+  // ---- S1: u_t = -K x_t + v
+  {
+    f2 acc[RTM][4];
+    zero_acc<RTM>(acc);
+    gemm_acc<RTM>(acc, a.nKT, 0, D, ZA, 0, sW, SWBUF, tid);
+#pragma unroll
+    for (int r = 0; r < RTM; ++r) {
+      const int row = D + RTM * ty + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float u0, u1;
+        unpk(acc[r][j], u0, u1);
+        const float2 v = *reinterpret_cast<const float2*>(ZA + (size_t)row * kE + EO(j));
+        u0 += v.x;
+        u1 += v.y;
+        csum[2 * j] = fmaf(u0, u0, csum[2 * j]);
+        csum[2 * j + 1] = fmaf(u1, u1, csum[2 * j + 1]);
+        *reinterpret_cast<float2*>(ZB + (size_t)row * kE + EO(j)) = make_float2(u0, u1);
+      }
+    }
+  }
+  // ---- S2: A x_t, then + B u_t
+  {
+    f2 acc[RTD][4];
+    zero_acc<RTD>(acc);
+    gemm_acc<RTD>(acc, a.F2T, 0, D, ZA, 0, sW, SWBUF, tid);
+#pragma unroll
+    for (int r = 0; r < RTD; ++r) {
+      const int row = RTD * ty + r;
+      float* axp = a.AXw + (size_t)row * a.Npad + env0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float p0, p1;
+        unpk(acc[r][j], p0, p1);
+        const float2 x = *reinterpret_cast<const float2*>(ZA + (size_t)row * kE + EO(j));
+        const float2 old = *reinterpret_cast<const float2*>(axp + EO(j));
+        csum[2 * j] = fmaf(x.x, x.x, csum[2 * j]);
+        csum[2 * j + 1] = fmaf(x.y, x.y, csum[2 * j + 1]);
+        // x_t - A x_{t-1} + A x_t: the final epilogue subtracts (A x_t + B u_t)
+        *reinterpret_cast<float2*>(ZB + (size_t)row * kE + EO(j)) =
+            make_float2((x.x - old.x) + p0, (x.y - old.y) + p1);
+        *reinterpret_cast<float2*>(axp + EO(j)) = make_float2(p0, p1);
+      }
+    }
+    __syncthreads();  // u rows of ZB (S1 epilogue) visible to every thread
+    gemm_acc<RTD>(acc, a.F2T, D, DM, ZB, 0, sW, SWBUF, tid);
+    const int snew = slot(0);  // hist_{t+1}[2H-1] replaces hist_t[0]
+#pragma unroll
+    for (int r = 0; r < RTD; ++r) {
+      const int row = RTD * ty + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float s0, s1;
+        unpk(acc[r][j], s0, s1);
+        const float2 nz = *reinterpret_cast<const float2*>(ZB + (size_t)row * kE + EO(j));
+        const float n0 = nz.x - s0, n1 = nz.y - s1;
+        const int e = EO(j);
+        float w0 = 0.f, w1 = 0.f;
+        if (a.W) {
+          if (e < nvalid) w0 = a.W[(size_t)(env0 + e) * D + row];
+          if (e + 1 < nvalid) w1 = a.W[(size_t)(env0 + e + 1) * D + row];
+        }
+        *reinterpret_cast<float2*>(a.Xw + (size_t)row * a.Npad + env0 + EO(j)) = make_float2(s0 + w0, s1 + w1);
+        *reinterpret_cast<float2*>(a.Hw + ((size_t)snew * D + row) * a.Npad + env0 + EO(j)) = make_float2(n0, n1);
+        a.Hring[((size_t)(env0 + e) * P + snew) * D + row] = n0;
+        a.Hring[((size_t)(env0 + e + 1) * P + snew) * D + row] = n1;
+      }
+    }
+  }
+  // realised cost: deterministic reduction over the 32 row groups
+  {
+    float* red = sW;  // the last gemm_acc ended with a barrier; [32][kE] floats fit in one operator buffer
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[ty * kE + EO(j)] = csum[2 * j];
+      red[ty * kE + EO(j) + 1] = csum[2 * j + 1];
+    }
+    __syncthreads();
+    if (tid < kE) {
+      float c = 0.f;
+      for (int g = 0; g < 32; ++g) c += red[g * kE + tid];
+      if (tid < nvalid) {
+        const int64_t env = env0 + tid;
+        if (a.cost_out) a.cost_out[env] = c;
+        if (a.cost_sum) a.cost_sum[env] = (a.first ? 0.0 : a.cost_sum[env]) + (double)c;
+        if (a.status) {
+          const int32_t bad = isfinite(c) ? 0 : DLC_STATUS_NONFINITE;
+          a.status[env] = a.first ? bad : (a.status[env] | bad);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- S3: counterfactual forward chain, y_0 = 0
+  float *cur = ZA, *oth = ZB;
+  load_rows(cur, D, MM, a.Vw, a.Npad, env0, tid);  // v_0
+  __syncthreads();
+  for (int h = 0; h < H - 1; ++h) {
+    f2 acc[RTD][4];
+    zero_acc<RTD>(acc);
+    gemm_acc<RTD>(acc, a.FT, h == 0 ? D : 0, DM, cur, 0, sW, SWBUF, tid);
+    const float* hw = a.Hw + (size_t)slot(h + H + 1) * D * a.Npad;
+#pragma unroll
+    for (int r = 0; r < RTD; ++r) {
+      const int row = RTD * ty + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y0, y1;
+        unpk(acc[r][j], y0, y1);
+        const float2 w = *reinterpret_cast<const float2*>(hw + (size_t)row * a.Npad + env0 + EO(j));
+        *reinterpret_cast<float2*>(oth + (size_t)row * kE + EO(j)) = make_float2(y0 + w.x, y1 + w.y);
+      }
+    }
+    load_rows(oth, D, MM, a.Vw + (size_t)(h + 1) * MM * a.Npad, a.Npad, env0, tid);  // v_{h+1}
+    __syncthreads();
+    float* t = cur; cur = oth; oth = t;
+  }
+  // ---- S4: du = 2 (-K y + v_{H-1}),  g_{H-1} = du
+  {
+    f2 acc[RTM][4];
+    zero_acc<RTM>(acc);
+    gemm_acc<RTM>(acc, a.nKT, 0, D, cur, 0, sW, SWBUF, tid);
+#pragma unroll
+    for (int r = 0; r < RTM; ++r) {
+      const int n = RTM * ty + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float u0, u1;
+        unpk(acc[r][j], u0, u1);
+        const float2 v = *reinterpret_cast<const float2*>(cur + (size_t)(D + n) * kE + EO(j));
+        const float d0 = 2.f * (u0 + v.x), d1 = 2.f * (u1 + v.y);
+        *reinterpret_cast<float2*>(oth + (size_t)(D + n) * kE + EO(j)) = make_float2(d0, d1);
+        *reinterpret_cast<float2*>(a.Gw + ((size_t)(H - 1) * MM + n) * a.Npad + env0 + EO(j)) =
+            make_float2(a.nlr * d0, a.nlr * d1);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- S5: lam = 2 y - K' du
+  {
+    f2 acc[RTD][4];
+    zero_acc<RTD>(acc);
+    gemm_acc<RTD>(acc, a.nK, 0, MM, oth, D, sW, SWBUF, tid);
+#pragma unroll
+    for (int r = 0; r < RTD; ++r) {
+      const int row = RTD * ty + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float l0, l1;
+        unpk(acc[r][j], l0, l1);
+        const float2 y = *reinterpret_cast<const float2*>(cur + (size_t)row * kE + EO(j));
+        *reinterpret_cast<float2*>(oth + (size_t)row * kE + EO(j)) =
+            make_float2(fmaf(2.f, y.x, l0), fmaf(2.f, y.y, l1));
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = oth; oth = t;
+  }
+  // ---- S6: [lam ; g_h] = [A-BK | B]' lam
+  for (int h = H - 2; h >= 0; --h) {
+    f2 acc[RTDM][4];
+    zero_acc<RTDM>(acc);
+    gemm_acc<RTDM>(acc, a.Fr, 0, D, cur, 0, sW, SWBUF, tid);
+#pragma unroll
+    for (int r = 0; r < RTDM; ++r) {
+      const int row = RTDM * ty + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float l0, l1;
+        unpk(acc[r][j], l0, l1);
+        if (row < D) {
+          *reinterpret_cast<float2*>(oth + (size_t)row * kE + EO(j)) = make_float2(l0, l1);
+        } else {
+          *reinterpret_cast<float2*>(a.Gw + ((size_t)h * MM + (row - D)) * a.Npad + env0 + EO(j)) =
+              make_float2(a.nlr * l0, a.nlr * l1);
+        }
+      }
+    }
+    __syncthreads();
+    float* t = cur; cur = oth; oth = t;
+  }
+}
+
+struct Shape {
+  int d, m, H;
+};
+
+template <int D, int MM, int H>
+struct Launch {
+  static size_t smem_stream() { return (size_t)kStages * H * (D / 2) * 8 + (size_t)MM * H * 4 + (size_t)(D / 64) * H * MM * 4; }
+  static size_t smem_chain() { return ((size_t)kWS * kKC * (D + MM) + (size_t)2 * (D + MM) * kE) * 4; }
+  static cudaError_t prepare() {
+    cudaError_t e;
+    const int ss = (int)smem_stream(), sc = (int)smem_chain();
+    if ((e = cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss))) return e;
+    if ((e = cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss))) return e;
+    if ((e = cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss))) return e;
+    return cudaFuncSetAttribute(gpc_shared_chain_kernel<D, MM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc);
+  }
+  static void stream(const StreamArgs& a, bool upd, bool fwd, cudaStream_t s) {
+    const dim3 grid((unsigned)a.N), block(D / 2);
+    const size_t sm = smem_stream();
+    if (upd && fwd) gpc_m_stream_kernel<D, MM, H, true, true><<<grid, block, sm, s>>>(a);
+    else if (fwd) gpc_m_stream_kernel<D, MM, H, false, true><<<grid, block, sm, s>>>(a);
+    else gpc_m_stream_kernel<D, MM, H, true, false><<<grid, block, sm, s>>>(a);
+  }
+  static void chain(const ChainArgs& a, cudaStream_t s) {
+    gpc_shared_chain_kernel<D, MM, H><<<(unsigned)(a.Npad / kE), kThreadsA, smem_chain(), s>>>(a);
+  }
+};
+
+}  // namespace sgpc
+}  // namespace dlc
+
+using namespace dlc;
+using namespace dlc::sgpc;
+
+static bool sgpc_supported(int d, int m, int H, int HH) {
+  if (HH != H) return false;
+  return (d == 256 && m == 64 && H == 16) || (d == 64 && m == 32 && H == 4);
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct SgpcLayout {
+  int64_t Npad;
+  size_t FT, Fr, F2T, nKT, nK, Xw, AXw, Vw, Gw, Hw, Hring, total;  // offsets in bytes
+};
+
+static SgpcLayout sgpc_layout(int64_t N, int d, int m, int H) {
+  SgpcLayout L{};
+  L.Npad = (N + kE - 1) / kE * kE;
+  const size_t dm = (size_t)d + m, P = 2 * (size_t)H, np = (size_t)L.Npad;
+  size_t o = 0;
+  auto take = [&](size_t floats) { const size_t at = o; o = align256(o + floats * 4); return at; };
+  L.FT = take(dm * d); L.Fr = take(dm * d); L.F2T = take(dm * d); L.nKT = take((size_t)m * d); L.nK = take((size_t)m * d);
+  L.Xw = take(d * np); L.AXw = take(d * np); L.Vw = take((size_t)H * m * np); L.Gw = take((size_t)H * m * np);
+  L.Hw = take(P * d * np); L.Hring = take(np * P * d);
+  L.total = o;
+  return L;
+}
+
+extern "C" size_t dlc_lds_shared_gpc_workspace_bytes(const DlcSharedGpcParams* p) {
+  if (!p || p->N <= 0 || !sgpc_supported(p->d, p->m, p->H, p->HH)) return 0;
+  return sgpc_layout(p->N, p->d, p->m, p->H).total;
+}
+
+extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, const float* A, const float* B,
+                                                  const float* K, const float* W, float* x_io, float* M_io,
+                                                  float* hist_io, float* xprev_io, float* cost_out,
+                                                  double* cost_sum_out, int32_t* status_out, void* workspace,
+                                                  size_t workspace_bytes, void* stream) {
+  if (!p) return fail(DLC_ERR_ARG, "dlc_lds_shared_gpc_rollout_f32: NULL params");
+  if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lds_shared_gpc_rollout_f32: negative N or T");
+  if (!sgpc_supported(p->d, p->m, p->H, p->HH))
+    return fail(DLC_ERR_SHAPE,
+                "dlc_lds_shared_gpc_rollout_f32: built for (d, m, H = HH) in {(256, 64, 16), (64, 32, 4)}");
+  if (p->N == 0 || p->T == 0) return DLC_OK;
+  if (!A || !B || !K || !x_io || !M_io || !workspace)
+    return fail(DLC_ERR_ARG, "dlc_lds_shared_gpc_rollout_f32: NULL buffer");
+  const SgpcLayout L = sgpc_layout(p->N, p->d, p->m, p->H);
+  if (workspace_bytes < L.total) return fail(DLC_ERR_WORKSPACE, "dlc_lds_shared_gpc_rollout_f32: workspace too small");
+  if (((uintptr_t)workspace & 15) != 0) return fail(DLC_ERR_ARG, "dlc_lds_shared_gpc_rollout_f32: workspace must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  auto at = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+  const int d = p->d, m = p->m, H = p->H, P = 2 * H;
+  const bool big = d == 256;
+  cudaError_t e = big ? Launch<256, 64, 16>::prepare() : Launch<64, 32, 4>::prepare();
+  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_shared_gpc)");
+  // padded envs run on zeros
+  e = cudaMemsetAsync(ws + L.Xw, 0, L.total - L.Xw, s);
+  if (e != cudaSuccess) return cuda_status(e, "cudaMemsetAsync(workspace)");
+  {
+    const int tot = (d + m) * d;
+    pack_kernel<<<(tot + 255) / 256, 256, 0, s>>>(A, B, K, d, m, at(L.FT), at(L.Fr), at(L.F2T), at(L.nKT), at(L.nK));
+  }
+  StateArgs st{};
+  st.N = p->N; st.Npad = L.Npad; st.d = d; st.P = P; st.base = 0; st.A = A;
+  st.x_io = x_io; st.hist_io = hist_io; st.xprev_io = xprev_io;
+  st.Xw = at(L.Xw); st.AXw = at(L.AXw); st.Hw = at(L.Hw); st.Hring = at(L.Hring);
+  const unsigned sblocks = (unsigned)((p->N * d + 255) / 256);
+  state_in_kernel<<<sblocks, 256, 0, s>>>(st);
+
+  StreamArgs sa{};
+  sa.N = p->N; sa.Npad = L.Npad; sa.M = M_io; sa.Hring = at(L.Hring); sa.Gw = at(L.Gw); sa.Vw = at(L.Vw);
+  ChainArgs ca{};
+  ca.N = p->N; ca.Npad = L.Npad;
+  ca.FT = at(L.FT); ca.Fr = at(L.Fr); ca.F2T = at(L.F2T); ca.nKT = at(L.nKT); ca.nK = at(L.nK);
+  ca.Xw = at(L.Xw); ca.AXw = at(L.AXw); ca.Hw = at(L.Hw); ca.Hring = at(L.Hring); ca.Vw = at(L.Vw); ca.Gw = at(L.Gw);
+  ca.cost_sum = cost_sum_out; ca.status = status_out;
+  // profiling switch (timing only, results are then meaningless): 1 = stream kernel only, 2 = chain kernel only
+  const char* denv = getenv("DLC_SGPC_DBG");
+  const int dbg = denv ? atoi(denv) : 0;
+  for (int step = 0; step < p->T; ++step) {
+    const int t = p->t0 + step;
+    const int base = step % P;
+    sa.base = base;
+    if (dbg != 2) {
+      if (big) Launch<256, 64, 16>::stream(sa, step > 0, true, s); else Launch<64, 32, 4>::stream(sa, step > 0, true, s);
+    }
+    ca.base = base;
+    ca.first = step == 0;
+    const double lr = p->decay ? (double)p->lr_scale * (1.0 / (double)(t + 1)) : (double)p->lr_scale;
+    ca.nlr = -(float)lr;
+    ca.W = W ? W + (size_t)step * p->N * d : nullptr;
+    ca.cost_out = cost_out ? cost_out + (size_t)step * p->N : nullptr;
+    ca.xprev_out = (step == p->T - 1) ? xprev_io : nullptr;
+    if (dbg != 1) {
+      if (big) Launch<256, 64, 16>::chain(ca, s); else Launch<64, 32, 4>::chain(ca, s);
+    }
+  }
+  sa.base = p->T % P;
+  if (big) Launch<256, 64, 16>::stream(sa, true, false, s); else Launch<64, 32, 4>::stream(sa, true, false, s);
+  st.base = p->T % P;
+  state_out_kernel<<<sblocks, 256, 0, s>>>(st);
+  return cuda_status(cudaGetLastError(), "lds_shared_gpc launch");
+}

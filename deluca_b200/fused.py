@@ -299,6 +299,44 @@ def lds_shared_lqr_rollout(G_packed, x, T, m, W=None, keep_costs=True):
     return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, status=status)
 
 
+def lds_shared_gpc_rollout(A, B, K, x, T, *, H=16, HH=None, W=None, M=None, hist=None, xprev=None, t0=0,
+                           lr_scale=0.005, decay=True, keep_costs=True, donate=False):
+    """``dlc_lds_shared_gpc_rollout_f32``: T steps of LDS + GPC with shared A[d,d], B[d,m], K[m,d] and a per-env
+    policy tensor M[N,H,m,d] (``deluca/agents/_gpc.py:109-183`` under vmap with ``in_axes=None`` dynamics).
+    ``M``/``hist``/``xprev`` default to the ``GPC.__init__`` state (zeros); pass the returned ones (and ``t0``) to
+    resume.  ``donate=True`` updates the given state tensors in place instead of cloning them."""
+    _f32(x, "x")
+    N, d = x.shape
+    m = B.shape[1]
+    HH = H if HH is None else HH
+    _f32(A, "A", (d, d)); _f32(B, "B", (d, m)); _f32(K, "K", (m, d)); _f32(W, "W", (T, N, d))
+    dev = x.device
+    own = lambda t, shape, name: (torch.zeros(shape, device=dev) if t is None
+                                  else (_f32(t, name, shape) if donate else _f32(t, name, shape).clone()))
+    x_io = x if donate else x.clone()
+    M_io = own(M, (N, H, m, d), "M")
+    hist_io = own(hist, (N, H + HH, d), "hist")
+    xprev_io = own(xprev, (N, d), "xprev")
+    p = _abi.DlcSharedGpcParams(N=N, T=T, d=d, m=m, H=H, HH=HH, t0=int(t0), decay=int(bool(decay)),
+                                lr_scale=float(lr_scale), reserved=0)
+    nbytes = _abi.lib().dlc_lds_shared_gpc_workspace_bytes(ctypes.byref(p))
+    if nbytes == 0 and N > 0:
+        raise ValueError("shared-dynamics GPC path is built for (d, m, H = HH) in {(256, 64, 16), (64, 32, 4)}")
+    ws = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=dev)
+    costs = torch.empty(T, N, device=dev) if keep_costs else None
+    cost_sum = torch.zeros(N, dtype=torch.float64, device=dev)
+    status = torch.zeros(N, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().dlc_lds_shared_gpc_rollout_f32(ctypes.byref(p), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K),
+                                                       _abi.ptr(W), _abi.ptr(x_io), _abi.ptr(M_io),
+                                                       _abi.ptr(hist_io), _abi.ptr(xprev_io), _abi.ptr(costs),
+                                                       _abi.ptr(cost_sum), _abi.ptr(status), _abi.ptr(ws),
+                                                       ws.numel() * 4, _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lds_shared_gpc_rollout_f32")
+    return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, M=M_io, hist=hist_io, xprev=xprev_io,
+                            t=t0 + T, status=status)
+
+
 def lung_pid_value_and_grad(params, K, kf, tt, loss_kind=0, noise=0.0, reset_pressure=0.0, want_sums=True):
     """``dlc_lung_pid_grad_f32``: per-breath loss[N], dloss/dK[N,3] and their batch sums [4] (fp64)."""
     N, T = params.N, params.T

@@ -47,7 +47,7 @@ extern "C" {
 
 int32_t dlc_abi_version(void);
 /* sizeof() of the parameter structs as compiled, so a binding can verify its own layout:
- * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers, 3 DlcPlanParams; 0 for unknown */
+ * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers, 3 DlcPlanParams, 4 DlcSharedGpcParams; 0 for unknown */
 size_t dlc_sizeof(int32_t which);
 const char* dlc_last_error(void);
 /* 0 if the current CUDA device can run this library (compute capability 10.x) */
@@ -373,6 +373,43 @@ int32_t dlc_lds_shared_lqr_rollout_f32(int64_t N, int32_t T, int32_t d, int32_t 
                                        float* x_io /*[N,d]*/, float* cost_out /*[T,N] or NULL*/,
                                        double* cost_sum_out /*[N] or NULL*/, int32_t* status_out /*[N] or NULL*/,
                                        void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Shared-dynamics LDS + GPC rollout with a per-env policy tensor M (BASELINE config 5: d = 256, m = 64,
+ * H = HH = 16, M[H,m,d] = 1 MiB per env).  A, B, K are shared by all envs (jax.vmap in_axes=None); M, the noise
+ * history, the state and the disturbances are per env.
+ * Replaces GPC.__call__ = get_action + update with jit(grad(policy_loss)) (deluca/agents/_gpc.py:109-183),
+ * LDS.__call__ (deluca/envs/_lds.py:102-111) and quad_loss (_gpc.py:29-40) under lax.scan x vmap, reference
+ * semantics as written (the noise estimate subtracts B u_t with the action just computed, _gpc.py:141-142,155).
+ * Two kernels alternate per step (2 T + 1 launches per call):
+ *   gpc_m_stream_kernel      M_t = M_{t-1} - lr g (x) hist  and the H window products  V_t[h] = sum_i M_t[i] w[h+i]
+ *                            in one pass over M (read once + written once per env-step: HBM-bound);
+ *   gpc_shared_chain_kernel  env step, realised cost, counterfactual chain and its adjoint as dense FP32 GEMMs
+ *                            [d+m x d] x [d x 64 envs] with the shared operators.
+ * Built for (d, m, H = HH) in {(256, 64, 16), (64, 32, 4)}; other shapes -> DLC_ERR_SHAPE (the per-env kernels of
+ * dlc_lds_rollout_f32 take any shape with shared_dynamics = 1).
+ * ------------------------------------------------------------------------------------ */
+typedef struct DlcSharedGpcParams {
+  int64_t N;       /* envs in this call */
+  int32_t T;       /* steps */
+  int32_t d, m;    /* state / action dim */
+  int32_t H, HH;   /* GPC controller / system history; HH must equal H */
+  int32_t t0;      /* agent step counter at entry (lr decay) */
+  int32_t decay;   /* lr = lr_scale/(t+1) (_gpc.py:161-162) */
+  float lr_scale;  /* _gpc.py:55 */
+  int32_t reserved;
+} DlcSharedGpcParams;
+
+size_t dlc_lds_shared_gpc_workspace_bytes(const DlcSharedGpcParams* p);
+int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p,
+                                       const float* A /*[d,d]*/, const float* B /*[d,m]*/, const float* K /*[m,d]*/,
+                                       const float* W /*[T,N,d] or NULL (no disturbance)*/,
+                                       float* x_io /*[N,d]*/, float* M_io /*[N,H,m,d]*/,
+                                       float* hist_io /*[N,2H,d] oldest -> newest, or NULL = zeros, not returned*/,
+                                       float* xprev_io /*[N,d] agent's previous state, or NULL = zeros, not returned*/,
+                                       float* cost_out /*[T,N] or NULL*/, double* cost_sum_out /*[N] or NULL*/,
+                                       int32_t* status_out /*[N] or NULL*/,
+                                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC

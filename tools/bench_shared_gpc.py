@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""BASELINE config 5 with the per-env policy tensor: shared-dynamics LDS (d=256, m=64) + GPC (H=HH=16).
+Times dlc_lds_shared_gpc_rollout_f32 with CUDA events (whole call, and each of its two kernels alone through the
+DLC_SGPC_DBG profiling switch) and reports the M-stream kernel against the measured HBM peak and the chain kernel
+against the measured FP32 peak.  Prints one JSON object; results are recorded in profiles/."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from deluca_b200 import fused
+from deluca_b200.riccati import dare_gain
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=65536)
+ap.add_argument("--T", type=int, default=6)
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+dev = "cuda"
+peaks = {}
+try:
+    peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+except OSError:
+    pass
+HBM = peaks.get("hbm_gbs", 6650.0)
+d, m, H = 256, 64, 16
+N, T = args.envs, args.T
+gg = torch.Generator(device=dev).manual_seed(0)
+Qm = torch.linalg.qr(torch.randn(d, d, device=dev, generator=gg, dtype=torch.float64))[0]
+A = ((Qm * (0.7 + 0.25 * torch.rand(d, device=dev, generator=gg, dtype=torch.float64))) @ Qm.T).float().contiguous()
+B = (torch.randn(d, m, device=dev, generator=gg) / d ** 0.5).contiguous()
+K = dare_gain(A, B)[0].contiguous()
+x = torch.randn(N, d, device=dev, generator=gg)
+W = 0.5 * torch.randn(T, N, d, device=dev, generator=gg)
+M = torch.zeros(N, H, m, d, device=dev)
+hist = 0.5 * torch.randn(N, 2 * H, d, device=dev, generator=gg)   # a warm noise history: every window is live
+xprev = torch.zeros(N, d, device=dev)
+
+
+def run():
+    return fused.lds_shared_gpc_rollout(A, B, K, x, T, H=H, W=W, M=M, hist=hist, xprev=xprev, lr_scale=1e-4,
+                                        keep_costs=False, donate=True)
+
+
+def timed(reps):
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(); r = run(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2], r
+
+
+x0 = x.clone()
+run(); run()
+ms_all, r = timed(args.reps)
+finite = bool(torch.isfinite(r.cost_sum).all()) and int(r.status.sum()) == 0
+os.environ["DLC_SGPC_DBG"] = "1"
+run()
+ms_stream, _ = timed(args.reps)
+os.environ["DLC_SGPC_DBG"] = "2"
+run()
+ms_chain, _ = timed(args.reps)
+del os.environ["DLC_SGPC_DBG"]
+
+bytes_step = 2 * 4 * H * m * d + 4 * 2 * H * d + 2 * 4 * H * m          # M read + write, noise ring, G in, V out
+flops_stream = 2 * 2 * H * H * m * d                                      # rank-H update + H window products
+flops_chain = (2 * m * d + 2 * d * (d + m)) + (H - 2) * 2 * d * (d + m) + 2 * d * m \
+    + 2 * 2 * m * d + (H - 1) * 2 * d * (d + m)                           # env step, forward chain, du/lam, adjoint chain
+per_stream = ms_stream * 1e-3 / (N * (T + 1))                             # T + 1 launches (the last one update-only)
+per_chain = ms_chain * 1e-3 / (N * T)
+import bench as _bench
+fp32_peak = max(_bench.measure_fp32_peak(torch, torch.device(dev)).values())
+out = {
+    "workload": f"shared-dynamics LDS(d={d}, m={m}) + GPC(H=HH={H}), per-env M (1 MiB), {N} envs x T={T}",
+    "envs": N, "T": T, "ms_per_call": ms_all, "env_steps_per_s": N * T / (ms_all * 1e-3), "finite": finite,
+    "M_bytes_resident": N * H * m * d * 4,
+    "stream_kernel": {"ms_per_launch": ms_stream / (T + 1), "ns_per_env_step": per_stream * 1e9,
+                      "roofline": {"bound": "hbm", "achieved": bytes_step / per_stream / 1e9, "peak": HBM,
+                                   "unit": "GB/s", "frac": bytes_step / per_stream / 1e9 / HBM,
+                                   "bytes_per_env_step": bytes_step, "fp32_tflops": flops_stream / per_stream / 1e12}},
+    "chain_kernel": {"ms_per_launch": ms_chain / T, "ns_per_env_step": per_chain * 1e9,
+                     "roofline": {"bound": "fp32", "achieved": flops_chain / per_chain / 1e12, "peak": fp32_peak,
+                                  "unit": "TFLOP/s", "frac": (flops_chain / per_chain / 1e12 / fp32_peak) if fp32_peak else None,
+                                  "flops_per_env_step": flops_chain}},
+    "whole_step_vs_hbm": {"achieved": bytes_step * N * T / (ms_all * 1e-3) / 1e9, "peak": HBM,
+                          "frac": bytes_step * N * T / (ms_all * 1e-3) / 1e9 / HBM},
+}
+print(json.dumps(out, indent=1))

@@ -13,7 +13,7 @@
 //       V_t[h]   = sum_i M_t[i] hist_t[1+h+i],  h = 0..H-1                  H window products
 //     M is read once and written once per env-step (2 MiB at config 5: the algorithmic minimum); both
 //     contractions run on the row while it is in registers (packed fma.rn.f32x2, pairs = the two coordinates).
-//     Rows are prefetched four n-slices ahead with per-thread cp.async (every thread copies exactly the 8 bytes
+//     Rows are prefetched two n-slices ahead with per-thread cp.async (every thread copies exactly the 8 bytes
 //     per row it later consumes, so the pipeline needs no barrier).
 //
 //   gpc_shared_chain_kernel  (FP32-bound; one CTA per 64 envs, batch as the N dimension of dense GEMMs with the
@@ -74,7 +74,6 @@ constexpr int kE = 64;        // envs per CTA of the chain kernel
 constexpr int kKC = 16;       // k-chunk of the staged operator
 constexpr int kThreadsA = 256;
 constexpr int kWS = 3;       // operator chunks in flight (cp.async stages) in the chain kernel
-constexpr int kStages = 4;    // n-slices of M in flight per thread in the stream kernel
 
 // ------------------------------------------------------------------------------------------------ pack
 // FT  [d+m][d]   FT[c][r]  = (A - B K)[r][c] (c < d),  B[r][c-d]      forward chain, k = c
@@ -118,36 +117,63 @@ struct StateArgs {
   float *Xw, *AXw, *Hw, *Hring;
 };
 
-// one thread per (env, coordinate)
-__global__ void state_in_kernel(StateArgs a) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.N * a.d) return;
-  const int64_t env = idx / a.d;
-  const int r = (int)(idx % a.d);
-  a.Xw[(size_t)r * a.Npad + env] = a.x_io[idx];
-  float ax = 0.f;
-  if (a.xprev_io) {
-    const float* xp = a.xprev_io + env * a.d;
-    const float* Ar = a.A + (size_t)r * a.d;
-    for (int c = 0; c < a.d; ++c) ax = fmaf(Ar[c], xp[c], ax);
+// out[c][n] = in[n][c]  (n < N rows of length C; out has leading dimension ldo), 32 x 32 tiles through shared memory
+__global__ void to_env_minor_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t N, int C, int64_t ldo) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t n = n0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && c < C) ? in[n * C + c] : 0.f;
   }
-  a.AXw[(size_t)r * a.Npad + env] = ax;
-  for (int j = 0; j < a.P; ++j) {
-    const float h = a.hist_io ? a.hist_io[((size_t)env * a.P + j) * a.d + r] : 0.f;
-    a.Hring[((size_t)env * a.P + j) * a.d + r] = h;
-    a.Hw[((size_t)j * a.d + r) * a.Npad + env] = h;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t n = n0 + threadIdx.x;
+    if (c < C && n < N) out[(size_t)c * ldo + n] = tile[threadIdx.x][i];
   }
 }
 
-__global__ void state_out_kernel(StateArgs a) {
+// out[n][c] = in[c][n]
+__global__ void to_env_major_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t N, int C, int64_t ldi) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && c < C) ? in[(size_t)c * ldi + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t n = n0 + i;
+    const int c = c0 + threadIdx.x;
+    if (c < C && n < N) out[n * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+// AXw[r][env] = sum_c A[r][c] xprev[env][c]   (the agent carries A x_{t-1}); thread per (r, env), env fastest
+__global__ void ax_prev_kernel(StateArgs a) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.N * a.d) return;
-  const int64_t env = idx / a.d;
-  const int r = (int)(idx % a.d);
-  a.x_io[idx] = a.Xw[(size_t)r * a.Npad + env];
-  if (a.hist_io)
-    for (int j = 0; j < a.P; ++j)
-      a.hist_io[((size_t)env * a.P + j) * a.d + r] = a.Hring[((size_t)env * a.P + (a.base + j) % a.P) * a.d + r];
+  const int r = (int)(idx / a.N);
+  const int64_t env = idx % a.N;
+  const float* xp = a.xprev_io + env * a.d;
+  const float* Ar = a.A + (size_t)r * a.d;
+  float ax = 0.f;
+  for (int c = 0; c < a.d; ++c) ax = fmaf(Ar[c], xp[c], ax);
+  a.AXw[(size_t)r * a.Npad + env] = ax;
+}
+
+// hist_io[env][j][r] = ring[env][(base + j) % P][r]
+__global__ void hist_out_kernel(StateArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (int64_t)a.P * a.d;
+  if (idx >= a.N * per) return;
+  const int64_t env = idx / per;
+  const int j = (int)((idx % per) / a.d), r = (int)(idx % a.d);
+  a.hist_io[idx] = a.Hring[((size_t)env * a.P + (a.base + j) % a.P) * a.d + r];
 }
 
 // ------------------------------------------------------------------------------------------------ M stream
@@ -160,14 +186,14 @@ struct StreamArgs {
   float* Vw;           // [H][MM][Npad]
 };
 
-template <int D, int MM, int H, bool UPD, bool FWD>
+template <int D, int MM, int H, bool UPD, bool FWD, int kStages>
 __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
   constexpr int P = 2 * H, NT = D / 2, NW = NT / 32;
   static_assert(D % 64 == 0 && (H & (H - 1)) == 0 && H >= 2 && H <= 32, "shape");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   f2* sM = reinterpret_cast<f2*>(smem_raw);                              // [kStages][H][NT]
   float* sG = reinterpret_cast<float*>(sM + (size_t)kStages * H * NT);   // [MM][H]
-  float* sV = sG + MM * H;                                               // [NW][H][MM]
+  float* sV = sG + MM * H;                                               // [NW][MM][H]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t env = blockIdx.x;
   const int k0 = 2 * tid;
@@ -254,15 +280,16 @@ __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
 #pragma unroll
       for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
       constexpr int per = 32 / H;  // lanes holding the same h
-      if ((lane % per) == 0) sV[(warp * H + lane / per) * MM + n] = v[0];
+      if ((lane % per) == 0) sV[(warp * MM + n) * H + lane / per] = v[0];
     }
   }
   if (FWD) {
     __syncthreads();
     for (int idx = tid; idx < MM * H; idx += NT) {  // idx = h * MM + n
+      const int h = idx / MM, n = idx % MM;
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s += sV[w * H * MM + idx];
+      for (int w = 0; w < NW; ++w) s += sV[(w * MM + n) * H + h];
       a.Vw[(size_t)idx * a.Npad + env] = s;
     }
   }
@@ -579,22 +606,35 @@ struct Shape {
 
 template <int D, int MM, int H>
 struct Launch {
-  static size_t smem_stream() { return (size_t)kStages * H * (D / 2) * 8 + (size_t)MM * H * 4 + (size_t)(D / 64) * H * MM * 4; }
+  // n-slices of M in flight per thread: 3 -> 68 KB per CTA (3 CTAs per SM at config 5), 4 -> 84 KB (2 CTAs per SM)
+  static int stages() {
+    static const int st = [] { const char* e = getenv("DLC_SGPC_STAGES"); const int v = e ? atoi(e) : 0; return (v == 3 || v == 5) ? v : 4; }();
+    return st;
+  }
+  static size_t smem_stream(int st) { return (size_t)st * H * (D / 2) * 8 + (size_t)MM * H * 4 + (size_t)(D / 64) * H * MM * 4; }
   static size_t smem_chain() { return ((size_t)kWS * kKC * (D + MM) + (size_t)2 * (D + MM) * kE) * 4; }
+  template <bool UPD, bool FWD, int ST>
+  static cudaError_t prep1() {
+    return cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, UPD, FWD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem_stream(ST));
+  }
   static cudaError_t prepare() {
     cudaError_t e;
-    const int ss = (int)smem_stream(), sc = (int)smem_chain();
-    if ((e = cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss))) return e;
-    if ((e = cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss))) return e;
-    if ((e = cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ss))) return e;
-    return cudaFuncSetAttribute(gpc_shared_chain_kernel<D, MM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sc);
+    if ((e = prep1<true, true, 3>()) || (e = prep1<false, true, 3>()) || (e = prep1<true, false, 3>())) return e;
+    if ((e = prep1<true, true, 4>()) || (e = prep1<false, true, 4>()) || (e = prep1<true, false, 4>())) return e;
+    if ((e = prep1<true, true, 5>()) || (e = prep1<false, true, 5>()) || (e = prep1<true, false, 5>())) return e;
+    return cudaFuncSetAttribute(gpc_shared_chain_kernel<D, MM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain());
+  }
+  template <int ST>
+  static void stream_st(const StreamArgs& a, bool upd, bool fwd, cudaStream_t s) {
+    const dim3 grid((unsigned)a.N), block(D / 2);
+    const size_t sm = smem_stream(ST);
+    if (upd && fwd) gpc_m_stream_kernel<D, MM, H, true, true, ST><<<grid, block, sm, s>>>(a);
+    else if (fwd) gpc_m_stream_kernel<D, MM, H, false, true, ST><<<grid, block, sm, s>>>(a);
+    else gpc_m_stream_kernel<D, MM, H, true, false, ST><<<grid, block, sm, s>>>(a);
   }
   static void stream(const StreamArgs& a, bool upd, bool fwd, cudaStream_t s) {
-    const dim3 grid((unsigned)a.N), block(D / 2);
-    const size_t sm = smem_stream();
-    if (upd && fwd) gpc_m_stream_kernel<D, MM, H, true, true><<<grid, block, sm, s>>>(a);
-    else if (fwd) gpc_m_stream_kernel<D, MM, H, false, true><<<grid, block, sm, s>>>(a);
-    else gpc_m_stream_kernel<D, MM, H, true, false><<<grid, block, sm, s>>>(a);
+    if (stages() == 3) stream_st<3>(a, upd, fwd, s); else if (stages() == 5) stream_st<5>(a, upd, fwd, s); else stream_st<4>(a, upd, fwd, s);
   }
   static void chain(const ChainArgs& a, cudaStream_t s) {
     gpc_shared_chain_kernel<D, MM, H><<<(unsigned)(a.Npad / kE), kThreadsA, smem_chain(), s>>>(a);
@@ -671,9 +711,15 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
   st.N = p->N; st.Npad = L.Npad; st.d = d; st.P = P; st.base = 0; st.A = A;
   st.x_io = x_io; st.hist_io = hist_io; st.xprev_io = xprev_io;
   st.Xw = at(L.Xw); st.AXw = at(L.AXw); st.Hw = at(L.Hw); st.Hring = at(L.Hring);
-  const unsigned sblocks = (unsigned)((p->N * d + 255) / 256);
-  state_in_kernel<<<sblocks, 256, 0, s>>>(st);
-
+  const dim3 tb(32, 8);
+  const unsigned nb = (unsigned)((p->N + 31) / 32);
+  to_env_minor_kernel<<<dim3(nb, (d + 31) / 32), tb, 0, s>>>(x_io, st.Xw, p->N, d, L.Npad);
+  if (hist_io) {
+    to_env_minor_kernel<<<dim3(nb, (P * d + 31) / 32), tb, 0, s>>>(hist_io, st.Hw, p->N, P * d, L.Npad);
+    e = cudaMemcpyAsync(st.Hring, hist_io, (size_t)p->N * P * d * 4, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return cuda_status(e, "cudaMemcpyAsync(hist)");
+  }
+  if (xprev_io) ax_prev_kernel<<<(unsigned)((p->N * d + 255) / 256), 256, 0, s>>>(st);
   StreamArgs sa{};
   sa.N = p->N; sa.Npad = L.Npad; sa.M = M_io; sa.Hring = at(L.Hring); sa.Gw = at(L.Gw); sa.Vw = at(L.Vw);
   ChainArgs ca{};
@@ -705,6 +751,7 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
   sa.base = p->T % P;
   if (big) Launch<256, 64, 16>::stream(sa, true, false, s); else Launch<64, 32, 4>::stream(sa, true, false, s);
   st.base = p->T % P;
-  state_out_kernel<<<sblocks, 256, 0, s>>>(st);
+  to_env_major_kernel<<<dim3(nb, (d + 31) / 32), tb, 0, s>>>(st.Xw, x_io, p->N, d, L.Npad);
+  if (hist_io) hist_out_kernel<<<(unsigned)((p->N * P * d + 255) / 256), 256, 0, s>>>(st);
   return cuda_status(cudaGetLastError(), "lds_shared_gpc launch");
 }

@@ -65,6 +65,19 @@ class DlcSharedGpcParams(ctypes.Structure):
     ]
 
 
+class DlcOfParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int64), ("env_offset", ctypes.c_int64), ("T", ctypes.c_int32), ("d", ctypes.c_int32),
+        ("n", ctypes.c_int32), ("p", ctypes.c_int32), ("agent", ctypes.c_int32), ("m", ctypes.c_int32),
+        ("h", ctypes.c_int32), ("F", ctypes.c_int32), ("L", ctypes.c_int32), ("t0", ctypes.c_int32),
+        ("decay", ctypes.c_int32), ("shared_dynamics", ctypes.c_int32), ("mode", ctypes.c_int32),
+        ("lr", ctypes.c_float), ("R_M", ctypes.c_float), ("w_std", ctypes.c_float), ("reserved", ctypes.c_int32),
+        ("seed", ctypes.c_uint64),
+    ]
+
+
+OF_AGENT = {"lqg": 0, "drc": 1, "fgrc": 2}
+
 LUNG_BUFFER_FIELDS = [
     "K", "kf", "u_in_in", "u_out_in", "steps_io", "time_io", "volume_io", "pressure_io", "target_io",
     "pipe_pressure_io", "in_history_io", "out_history_io", "obs_pressure_io", "obs_time_io",
@@ -131,6 +144,8 @@ SYMBOLS = {
     "dlc_lds_shared_gpc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcSharedGpcParams)]),
     "dlc_lds_shared_gpc_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcSharedGpcParams)] + [_P] * 12
                                        + [ctypes.c_size_t, _P]),
+    "dlc_lds_of_smem_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcOfParams)]),
+    "dlc_lds_of_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcOfParams)] + [_P] * 18),
     "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),
     "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
     "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 18
@@ -154,7 +169,7 @@ def lib():
                 fn.restype = res
                 fn.argtypes = args
             for which, struct in enumerate((DlcLdsParams, DlcLungParams, DlcLungBuffers, DlcPlanParams,
-                                            DlcSharedGpcParams)):
+                                            DlcSharedGpcParams, DlcOfParams)):
                 if L.dlc_sizeof(which) != ctypes.sizeof(struct):
                     raise ImportError(f"{struct.__name__}: ctypes layout ({ctypes.sizeof(struct)} B) does not match "
                                       f"the library ({L.dlc_sizeof(which)} B); rebuild libdeluca_b200.so")

@@ -30,6 +30,7 @@ extern "C" size_t dlc_sizeof(int32_t which) {
     case 2: return sizeof(DlcLungBuffers);
     case 3: return sizeof(DlcPlanParams);
     case 4: return sizeof(DlcSharedGpcParams);
+    case 5: return sizeof(DlcOfParams);
     default: return 0;
   }
 }

@@ -1,0 +1,523 @@
+// lds_of.cu -- partially observed LDS (y = C x) driven by deluca's output-feedback controllers, fused over T steps
+// (SURVEY 8(f) rank 3).
+//
+//   LQG   deluca/agents/_lqg.py:83-98     u = -K x_hat;  x_hat <- A x_hat + B u + L (y - C x_hat)
+//   DRC   deluca/agents/_drc.py:131-203   y_nat <- y - sum_i G[i] us[i];  u = -K y + sum_j M[j] y_nat[j];
+//                                         M <- clip_RM(M - lr * d policy_loss / dM)
+//   GRC   deluca/agents/_grc.py:90-169    }  one family: the action is linear in the parameters and in a fixed bank
+//   SFC   deluca/agents/_sfc.py:130-214   }  of linear filters of the y_nat history,
+//   DSC   deluca/agents/_dsc.py:150-292   }      a(k) = sum_f Theta[f] phi_f(k),  phi_f(k) = sum_o Phi[f,o] ynat[k+o],
+//                                            with (F, L, Phi) chosen by the host mirror (oracle/of.py filter_bank)
+//   env   deluca/envs/_lds.py:102-111     x <- A x + B u + w,  y = C x;   cost = quad_loss(y, u)  (_grc.py:27-39)
+//
+// Mapping: ONE WARP owns an env.  Everything the env needs between steps (A, B, C, the Markov operators, the
+// parameters, the history rings) stays in the warp's slice of shared memory for all T steps; lanes split the
+// elements of each small contraction and meet through warp shuffles / __syncwarp.  Runtime dims.
+//
+// Algebra that is exact, not approximate:
+//   (i)  policy_loss rolls delta <- A delta + B a(k) for k < m and reads only C delta_m (_grc.py:97-105).  That is
+//        sum_k (C A^(m-1-k) B) a(k): the m Markov operators are formed once per call, so the m-step recursion and
+//        its adjoint become 2 m p n FMAs per step instead of 2 m (d^2 + d n)  (DRC keeps G the same way, _drc.py:97-102).
+//   (ii) the filtered windows phi_f(k), k = 0..m, of step t are those of step t-1 shifted by one: only the newest
+//        window is filtered each step, the others are kept in a ring.
+//   (iii) jit(grad(policy_loss)) is a hand adjoint: dTheta[f] = sum_k g(k) phi_f(k)^T with g(m) = 2 a(m) and
+//        g(k) = G[m-1-k]^T (2 final_y) for k < m.
+#include "common.cuh"
+
+namespace dlc {
+namespace {
+
+struct OfArgs {
+  DlcOfParams p;
+  const float *A, *B, *C, *K, *Lk, *Phi, *W, *y_in;
+  float *x_io, *theta_io, *z_io, *ynat_io, *us_io;
+  float* cost_out;
+  double* cost_sum_out;
+  float* u_out;
+  int32_t* status_out;
+  int wpc;   // warps (envs) per CTA
+  int S;     // floats of shared memory per warp
+  int J;     // Markov operators kept (m for the filter family, h for DRC)
+  int FP;    // length of one feature window: F * p (filter family), m * p (DRC)
+  int nPhi;  // CTA-wide floats at the start of dynamic shared memory (the filter bank)
+  int oA, oB, oC, oG, oK, oL, oTh, oFeat, oYn, oUs, oX, oZ, oY, oU, oAct, oGact, oFy, oTmp;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// e / den for 0 <= e < 2^20 (inv = 1 / den): one multiply and a conversion instead of an integer division
+__device__ __forceinline__ int fast_div(int e, float inv) { return (int)(((float)e + 0.5f) * inv); }
+
+// out[r] (r = lane, lane + 32) = sum_c Mat[r][c] v[c]   (rows <= 64); the caller decides where the result goes
+__device__ __forceinline__ void matvec2(const float* Mat, const float* v, int rows, int cols, int lane, float& r0, float& r1) {
+  r0 = 0.f; r1 = 0.f;
+  if (lane < rows) {
+    const float* row = Mat + lane * cols;
+    for (int c = 0; c < cols; ++c) r0 = fmaf(row[c], v[c], r0);
+  }
+  if (lane + 32 < rows) {
+    const float* row = Mat + (lane + 32) * cols;
+    for (int c = 0; c < cols; ++c) r1 = fmaf(row[c], v[c], r1);
+  }
+}
+
+__device__ __forceinline__ float pick4(const float z[4], int k) { return k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3])); }
+
+// buf[i] <- (i < step) ? fresh[i] : buf[i - step]  for i < tot: a newest-first history takes one entry.  32-wide blocks,
+// back to front, so no element is overwritten before it has moved.
+__device__ __forceinline__ void shift_in(float* buf, int tot, int step, const float* fresh, int lane) {
+  for (int base = ((tot - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int i = base + lane;
+    const float v = (i < tot) ? (i < step ? fresh[i] : buf[i - step]) : 0.f;
+    __syncwarp();
+    if (i < tot) buf[i] = v;
+    __syncwarp();
+  }
+}
+
+template <int AGENT>
+__global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DlcOfParams& P = a.p;
+  const int d = P.d, n = P.n, p = P.p, m = P.m, T = P.T;
+  const int F = P.F, L = P.L, h = P.h, FP = a.FP, J = a.J;
+  const bool closed = P.mode == DLC_MODE_CLOSED_LOOP;
+  if (AGENT == DLC_OF_FGRC) {
+    for (int i = threadIdx.x; i < a.nPhi; i += blockDim.x) smem[i] = a.Phi[i];
+    __syncthreads();  // the only CTA-wide barrier: warps are independent from here on (and may exit)
+  }
+  const int64_t env = (int64_t)blockIdx.x * a.wpc + warp;
+  if (env >= P.N) return;
+  const float* sPhi = smem;
+  float* s = smem + a.nPhi + (size_t)warp * a.S;
+  float *sA = s + a.oA, *sB = s + a.oB, *sC = s + a.oC, *sG = s + a.oG, *sK = s + a.oK, *sL = s + a.oL;
+  float *sTh = s + a.oTh, *sFeat = s + a.oFeat, *sYn = s + a.oYn, *sUs = s + a.oUs;
+  float *sx = s + a.oX, *sz = s + a.oZ, *sy = s + a.oY, *su = s + a.oU;
+  float *sAct = s + a.oAct, *sGact = s + a.oGact, *sFy = s + a.oFy, *sTmp = s + a.oTmp;
+
+  // ---------------------------------------------------------------- stage the env
+  const size_t eD = P.shared_dynamics ? 0 : (size_t)env;
+  for (int i = lane; i < d * d; i += 32) sA[i] = a.A[eD * d * d + i];
+  for (int i = lane; i < d * n; i += 32) sB[i] = a.B[eD * d * n + i];
+  for (int i = lane; i < p * d; i += 32) sC[i] = a.C[eD * p * d + i];
+  if (closed) for (int i = lane; i < d; i += 32) sx[i] = a.x_io[(size_t)env * d + i];
+  if (AGENT == DLC_OF_LQG) {
+    for (int i = lane; i < n * d; i += 32) sK[i] = a.K[eD * n * d + i];
+    for (int i = lane; i < d * p; i += 32) sL[i] = a.Lk[eD * d * p + i];
+    for (int i = lane; i < d; i += 32) sz[i] = a.z_io[(size_t)env * d + i];
+  }
+  if (AGENT == DLC_OF_DRC) {
+    for (int i = lane; i < n * p; i += 32) sK[i] = a.K ? a.K[eD * n * p + i] : 0.f;  // _drc.py:104: K defaults to 0
+    // M[j][a][q] -> sTh[a][j*p + q]
+    for (int e = lane; e < m * n * p; e += 32) {
+      const int j = e / (n * p), rem = e - j * n * p, aa = rem / p, q = rem - aa * p;
+      sTh[aa * FP + j * p + q] = a.theta_io[(size_t)env * m * n * p + e];
+    }
+    for (int i = lane; i < m * p; i += 32) sYn[i] = a.ynat_io[(size_t)env * m * p + i];
+    for (int i = lane; i < h * n; i += 32) sUs[i] = a.us_io[(size_t)env * h * n + i];
+  }
+  if (AGENT == DLC_OF_FGRC) {
+    for (int e = lane; e < F * n * p; e += 32) {
+      const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
+      sTh[aa * FP + f * p + q] = a.theta_io[(size_t)env * F * n * p + e];
+    }
+    for (int i = lane; i < (L + m) * p; i += 32) sYn[i] = a.ynat_io[(size_t)env * (L + m) * p + i];
+    for (int i = lane; i < d; i += 32) sz[i] = a.z_io[(size_t)env * d + i];
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- Markov operators G[j] = C A^j B, j < J
+  if (AGENT != DLC_OF_LQG) {
+    float* ab0 = sTmp;
+    float* ab1 = sTmp + d * n;
+    for (int i = lane; i < d * n; i += 32) ab0[i] = sB[i];
+    __syncwarp();
+    for (int j = 0; j < J; ++j) {
+      for (int e = lane; e < p * n; e += 32) {
+        const int q = e / n, aa = e - q * n;
+        float acc = 0.f;
+        for (int c = 0; c < d; ++c) acc = fmaf(sC[q * d + c], ab0[c * n + aa], acc);
+        sG[j * p * n + e] = acc;
+      }
+      for (int e = lane; e < d * n; e += 32) {
+        const int r = e / n, aa = e - r * n;
+        float acc = 0.f;
+        for (int c = 0; c < d; ++c) acc = fmaf(sA[r * d + c], ab0[c * n + aa], acc);
+        ab1[e] = acc;
+      }
+      __syncwarp();
+      float* tmp = ab0; ab0 = ab1; ab1 = tmp;
+    }
+  }
+  // ---------------------------------------------------------------- filtered windows of the initial history
+  const int M1 = m + 1, R = L + m;
+  if (AGENT == DLC_OF_FGRC) {
+    for (int k = 0; k < M1; ++k)
+      for (int i = lane; i < FP; i += 32) {
+        const int f = i / p, q = i - f * p;
+        float acc = 0.f;
+        for (int o = 0; o < L; ++o) acc = fmaf(sPhi[f * L + o], sYn[(k + o) * p + q], acc);
+        sFeat[k * FP + i] = acc;
+      }
+    __syncwarp();
+  }
+  int ybase = 0;  // ring slot of the oldest y_nat (filter family)
+  int fbase = 0;  // ring slot of feature window k = 0
+  const float inv_n = 1.f / (float)n, inv_FP = 1.f / (float)FP, inv_p = 1.f / (float)p;
+  const uint32_t genv = (uint32_t)(P.env_offset + env);
+  double csum = 0.0;
+  int status = 0;
+
+  for (int t = 0; t < T; ++t) {
+    // disturbance of this step, fetched early
+    float w0 = 0.f, w1 = 0.f;
+    if (closed) {
+      if (a.W) {
+        const float* wp = a.W + ((size_t)t * P.N + env) * d;
+        if (lane < d) w0 = wp[lane];
+        if (lane + 32 < d) w1 = wp[lane + 32];
+      } else {
+        float z4[4];
+        if (lane < d) { normal4(P.seed, genv, (uint32_t)(P.t0 + t), (uint32_t)(lane >> 2), 0u, z4); w0 = __fmul_rn(P.w_std, pick4(z4, lane & 3)); }
+        if (lane + 32 < d) { normal4(P.seed, genv, (uint32_t)(P.t0 + t), (uint32_t)((lane + 32) >> 2), 0u, z4); w1 = __fmul_rn(P.w_std, pick4(z4, lane & 3)); }
+      }
+    }
+    // ---- observation y = C x  (_lds.py:110), or the caller's observation (Agent.__call__ on its own)
+    if (closed) {
+      float r0, r1;
+      matvec2(sC, sx, p, d, lane, r0, r1);
+      if (lane < p) sy[lane] = r0;
+      if (lane + 32 < p) sy[lane + 32] = r1;
+    } else {
+      for (int i = lane; i < p; i += 32) sy[i] = a.y_in[((size_t)t * P.N + env) * p + i];
+    }
+    __syncwarp();
+
+    if (AGENT == DLC_OF_LQG) {
+      // u = -K x_hat; residual = y - C x_hat; x_hat <- A x_hat + B u + L residual   (_lqg.py:94-97)
+      float u0, u1, c0, c1;
+      matvec2(sK, sz, n, d, lane, u0, u1);
+      matvec2(sC, sz, p, d, lane, c0, c1);
+      if (lane < n) su[lane] = -u0;
+      if (lane + 32 < n) su[lane + 32] = -u1;
+      if (lane < p) sFy[lane] = sy[lane] - c0;
+      if (lane + 32 < p) sFy[lane + 32] = sy[lane + 32] - c1;
+      __syncwarp();
+      float a0, a1, b0, b1, l0, l1;
+      matvec2(sA, sz, d, d, lane, a0, a1);
+      matvec2(sB, su, d, n, lane, b0, b1);
+      matvec2(sL, sFy, d, p, lane, l0, l1);
+      __syncwarp();
+      if (lane < d) sz[lane] = a0 + b0 + l0;
+      if (lane + 32 < d) sz[lane + 32] = a1 + b1 + l1;
+      __syncwarp();
+    }
+
+    if (AGENT == DLC_OF_DRC) {
+      const float lr = P.decay ? P.lr / (float)(P.t0 + t + 1) : 1.0f;  // _drc.py:184: without decay the rate is 1.0 (sic)
+      // gu[q] = sum_i sum_a G[i][q][a] us[i][a]     (_drc.py:169)
+      for (int q = 0; q < p; ++q) {
+        float part = 0.f;
+        for (int i = lane; i < h; i += 32)
+          for (int aa = 0; aa < n; ++aa) part = fmaf(sG[(i * p + q) * n + aa], sUs[i * n + aa], part);
+        part = warp_sum(part);
+        if (lane == 0) sFy[q] = part;
+      }
+      __syncwarp();
+      // y_nat: shift by one position (newest first), y_nat[0] = y - gu    (_drc.py:169-171)
+      for (int i = lane; i < p; i += 32) sTmp[i] = sy[i] - sFy[i];
+      __syncwarp();
+      shift_in(sYn, m * p, p, sTmp, lane);
+      // mdot[a] = sum_{j,q} M[j][a][q] y_nat[j][q];  u = -K y + mdot;  final = y_nat[0] + gu;  act = -K final + mdot
+      for (int aa = 0; aa < n; ++aa) {
+        float part = 0.f;
+        for (int i = lane; i < FP; i += 32) part = fmaf(sTh[aa * FP + i], sYn[i], part);
+        part = warp_sum(part);
+        if (lane == 0) {
+          float ky = 0.f, kf = 0.f;
+          for (int q = 0; q < p; ++q) {
+            ky = fmaf(sK[aa * p + q], sy[q], ky);
+            kf = fmaf(sK[aa * p + q], sYn[q] + sFy[q], kf);
+          }
+          su[aa] = part - ky;
+          sAct[aa] = 2.f * (part - kf);   // 2 * action(final_state): the adjoint seed of quad_loss w.r.t. the action
+        }
+      }
+      __syncwarp();
+      // M <- M - lr * 2 act (x) y_nat, then the norm clip   (_drc.py:181-193)
+      float nrm = 0.f;
+      for (int e = lane; e < n * FP; e += 32) {
+        const int aa = fast_div(e, inv_FP), i = e - aa * FP;
+        const float th = fmaf(-lr * sAct[aa], sYn[i], sTh[e]);
+        sTh[e] = th;
+        nrm = fmaf(th, th, nrm);
+      }
+      nrm = sqrtf(warp_sum(nrm));
+      if (nrm > P.R_M) {
+        const float sc = P.R_M / nrm;
+        for (int e = lane; e < n * FP; e += 32) sTh[e] *= sc;
+      }
+      // us: shift, us[0] = u    (_drc.py:196-197)
+      shift_in(sUs, h * n, n, su, lane);
+    }
+
+    if (AGENT == DLC_OF_FGRC) {
+      const float lr = P.decay ? P.lr / (float)(P.t0 + t + 1) : P.lr;  // _grc.py:145
+      // ---- get_action: newest window of the history as it stands (_grc.py:157-169)
+      {
+        int snew = fbase + m; if (snew >= M1) snew -= M1;
+        const float* fw = sFeat + snew * FP;
+        for (int aa = 0; aa < n; ++aa) {
+          float part = 0.f;
+          for (int i = lane; i < FP; i += 32) part = fmaf(sTh[aa * FP + i], fw[i], part);
+          part = warp_sum(part);
+          if (lane == 0) su[aa] = part;
+        }
+      }
+      __syncwarp();
+      // ---- update: z <- A z + B u; y_nat = y - C z; push    (_grc.py:139-142)
+      {
+        float a0, a1, b0, b1;
+        matvec2(sA, sz, d, d, lane, a0, a1);
+        matvec2(sB, su, d, n, lane, b0, b1);
+        __syncwarp();
+        if (lane < d) sz[lane] = a0 + b0;
+        if (lane + 32 < d) sz[lane + 32] = a1 + b1;
+        __syncwarp();
+        float c0, c1;
+        matvec2(sC, sz, p, d, lane, c0, c1);
+        float* slot = sYn + ybase * p;   // the oldest entry is replaced by the newest
+        if (lane < p) slot[lane] = sy[lane] - c0;
+        if (lane + 32 < p) slot[lane + 32] = sy[lane + 32] - c1;
+        ybase = (ybase + 1 == R) ? 0 : ybase + 1;
+      }
+      __syncwarp();
+      // ---- filter the newest window (history positions m .. m+L-1) into the ring slot of the oldest one
+      {
+        float* fw = sFeat + fbase * FP;
+        int s0 = ybase + m; if (s0 >= R) s0 -= R;
+        for (int i = lane; i < FP; i += 32) {
+          const int f = fast_div(i, inv_p), q = i - f * p;
+          const float* ph = sPhi + f * L;
+          int sl = s0;
+          float acc = 0.f;
+          for (int o = 0; o < L; ++o) {
+            acc = fmaf(ph[o], sYn[sl * p + q], acc);
+            sl = (sl + 1 == R) ? 0 : sl + 1;
+          }
+          fw[i] = acc;
+        }
+        fbase = (fbase + 1 == M1) ? 0 : fbase + 1;
+      }
+      __syncwarp();
+      // ---- a(k), k = 0..m, with the parameters before the update
+      for (int e = lane; e < M1 * n; e += 32) {
+        const int k = fast_div(e, inv_n), aa = e - k * n;
+        int sl = fbase + k; if (sl >= M1) sl -= M1;
+        const float* fw = sFeat + sl * FP;
+        const float* th = sTh + aa * FP;
+        float acc = 0.f;
+        for (int i = 0; i < FP; ++i) acc = fmaf(th[i], fw[i], acc);
+        sAct[e] = acc;
+      }
+      __syncwarp();
+      // ---- final_y = sum_{k<m} G[m-1-k] a(k) + y_nat(newest)     (_grc.py:100-104)
+      {
+        int snew = ybase + R - 1; if (snew >= R) snew -= R;
+        for (int q = lane; q < p; q += 32) {
+          float acc = sYn[snew * p + q];
+          for (int k = 0; k < m; ++k) {
+            const float* g = sG + ((m - 1 - k) * p + q) * n;
+            for (int aa = 0; aa < n; ++aa) acc = fmaf(g[aa], sAct[k * n + aa], acc);
+          }
+          sFy[q] = 2.f * acc;
+        }
+      }
+      __syncwarp();
+      // ---- adjoint of the actions: g(m) = 2 a(m), g(k) = G[m-1-k]^T (2 final_y)
+      for (int e = lane; e < M1 * n; e += 32) {
+        const int k = fast_div(e, inv_n), aa = e - k * n;
+        float acc;
+        if (k == m) {
+          acc = 2.f * sAct[e];
+        } else {
+          acc = 0.f;
+          const float* g = sG + (m - 1 - k) * p * n + aa;
+          for (int q = 0; q < p; ++q) acc = fmaf(g[q * n], sFy[q], acc);
+        }
+        sGact[e] = acc;
+      }
+      __syncwarp();
+      // ---- Theta <- proj_RM(Theta - lr * sum_k g(k) phi(k)^T)     (_grc.py:144-151)
+      float nrm = 0.f;
+      for (int e = lane; e < n * FP; e += 32) {
+        const int aa = fast_div(e, inv_FP), i = e - aa * FP;
+        float acc = 0.f;
+        int sl = fbase;
+        for (int k = 0; k < M1; ++k) {
+          acc = fmaf(sGact[k * n + aa], sFeat[sl * FP + i], acc);
+          sl = (sl + 1 == M1) ? 0 : sl + 1;
+        }
+        const float th = fmaf(-lr, acc, sTh[e]);
+        sTh[e] = th;
+        nrm = fmaf(th, th, nrm);
+      }
+      nrm = sqrtf(warp_sum(nrm));
+      const float sc = fminf(1.0f, P.R_M / (nrm + 1e-8f));
+      if (sc < 1.0f)
+        for (int e = lane; e < n * FP; e += 32) sTh[e] *= sc;
+      __syncwarp();
+    }
+
+    // ---- realised cost quad_loss(y, u), outputs
+    {
+      float c = 0.f;
+      for (int i = lane; i < p; i += 32) c = fmaf(sy[i], sy[i], c);
+      for (int i = lane; i < n; i += 32) c = fmaf(su[i], su[i], c);
+      c = warp_sum(c);
+      if (lane == 0) {
+        if (a.cost_out) a.cost_out[(size_t)t * P.N + env] = c;
+        csum += (double)c;
+        if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
+      }
+      if (a.u_out) for (int i = lane; i < n; i += 32) a.u_out[((size_t)t * P.N + env) * n + i] = su[i];
+    }
+    // ---- env step x <- A x + B u + w    (_lds.py:107-109)
+    if (closed) {
+      float a0, a1, b0, b1;
+      matvec2(sA, sx, d, d, lane, a0, a1);
+      matvec2(sB, su, d, n, lane, b0, b1);
+      __syncwarp();
+      if (lane < d) sx[lane] = a0 + b0 + w0;
+      if (lane + 32 < d) sx[lane + 32] = a1 + b1 + w1;
+    }
+    __syncwarp();
+  }
+
+  // ---------------------------------------------------------------- write the state back
+  if (closed) for (int i = lane; i < d; i += 32) a.x_io[(size_t)env * d + i] = sx[i];
+  if (AGENT == DLC_OF_LQG) for (int i = lane; i < d; i += 32) a.z_io[(size_t)env * d + i] = sz[i];
+  if (AGENT == DLC_OF_DRC) {
+    for (int e = lane; e < m * n * p; e += 32) {
+      const int j = e / (n * p), rem = e - j * n * p, aa = rem / p, q = rem - aa * p;
+      a.theta_io[(size_t)env * m * n * p + e] = sTh[aa * FP + j * p + q];
+    }
+    for (int i = lane; i < m * p; i += 32) a.ynat_io[(size_t)env * m * p + i] = sYn[i];
+    for (int i = lane; i < h * n; i += 32) a.us_io[(size_t)env * h * n + i] = sUs[i];
+  }
+  if (AGENT == DLC_OF_FGRC) {
+    for (int e = lane; e < F * n * p; e += 32) {
+      const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
+      a.theta_io[(size_t)env * F * n * p + e] = sTh[aa * FP + f * p + q];
+    }
+    for (int i = lane; i < R * p; i += 32) {   // oldest -> newest
+      const int pos = i / p, q = i - pos * p;
+      int sl = ybase + pos; if (sl >= R) sl -= R;
+      a.ynat_io[(size_t)env * R * p + i] = sYn[sl * p + q];
+    }
+    for (int i = lane; i < d; i += 32) a.z_io[(size_t)env * d + i] = sz[i];
+  }
+  if (lane == 0) {
+    if (a.cost_sum_out) a.cost_sum_out[env] = csum;
+    if (a.status_out) a.status_out[env] = status;
+  }
+}
+
+// shared-memory layout of one warp's slice; returns floats per warp
+int layout(OfArgs& a) {
+  const DlcOfParams& P = a.p;
+  const int d = P.d, n = P.n, p = P.p, m = P.m;
+  int o = 0;
+  auto take = [&](int cnt) { const int at = o; o += (cnt + 3) & ~3; return at; };
+  a.J = P.agent == DLC_OF_DRC ? P.h : (P.agent == DLC_OF_FGRC ? m : 0);
+  a.FP = P.agent == DLC_OF_DRC ? m * p : (P.agent == DLC_OF_FGRC ? P.F * p : 0);
+  a.nPhi = P.agent == DLC_OF_FGRC ? ((P.F * P.L + 3) & ~3) : 0;
+  a.oA = take(d * d); a.oB = take(d * n); a.oC = take(p * d);
+  a.oG = take(a.J * p * n);
+  a.oK = take(P.agent == DLC_OF_LQG ? n * d : (P.agent == DLC_OF_DRC ? n * p : 0));
+  a.oL = take(P.agent == DLC_OF_LQG ? d * p : 0);
+  a.oTh = take(n * a.FP);
+  a.oFeat = take(P.agent == DLC_OF_FGRC ? (m + 1) * a.FP : 0);
+  a.oYn = take(P.agent == DLC_OF_FGRC ? (P.L + m) * p : (P.agent == DLC_OF_DRC ? m * p : 0));
+  a.oUs = take(P.agent == DLC_OF_DRC ? P.h * n : 0);
+  a.oX = take(d); a.oZ = take(d); a.oY = take(p); a.oU = take(n);
+  a.oAct = take((m + 1) * n); a.oGact = take((m + 1) * n); a.oFy = take(p);
+  a.oTmp = take(2 * d * n > p ? 2 * d * n : p);
+  return o;
+}
+
+}  // namespace
+}  // namespace dlc
+
+using namespace dlc;
+
+static int32_t of_check(const DlcOfParams* p) {
+  if (!p) return fail(DLC_ERR_ARG, "dlc_lds_of: params is NULL");
+  if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lds_of: negative N or T");
+  if (p->agent < DLC_OF_LQG || p->agent > DLC_OF_FGRC) return fail(DLC_ERR_ARG, "dlc_lds_of: unknown agent");
+  if (p->mode != DLC_MODE_CLOSED_LOOP && p->mode != DLC_MODE_AGENT_ONLY) return fail(DLC_ERR_ARG, "dlc_lds_of: unknown mode");
+  if (p->d < 1 || p->n < 1 || p->p < 1 || p->d > 64 || p->n > 64 || p->p > 64)
+    return fail(DLC_ERR_SHAPE, "dlc_lds_of: d, n, p must be in 1..64");
+  if (p->agent == DLC_OF_DRC && (p->m < 1 || p->h < 1))
+    return fail(DLC_ERR_SHAPE, "dlc_lds_of: DRC needs m >= 1 and h >= 1");
+  if (p->agent == DLC_OF_FGRC && (p->m < 1 || p->F < 1 || p->L < 1))
+    return fail(DLC_ERR_SHAPE, "dlc_lds_of: the filter family needs m, F, L >= 1");
+  if (p->agent == DLC_OF_LQG && p->m != 0) return fail(DLC_ERR_ARG, "dlc_lds_of: LQG takes m = 0");
+  return DLC_OK;
+}
+
+extern "C" size_t dlc_lds_of_smem_bytes(const DlcOfParams* p) {
+  if (of_check(p) != DLC_OK) return 0;
+  OfArgs a{};
+  a.p = *p;
+  const int S = layout(a);
+  return ((size_t)a.nPhi + S) * 4;
+}
+
+extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, const float* B, const float* C,
+                                          const float* K, const float* Lk, const float* Phi, const float* W,
+                                          const float* y_in, float* x_io, float* theta_io, float* z_io, float* ynat_io,
+                                          float* us_io, float* cost_out, double* cost_sum_out, float* u_out,
+                                          int32_t* status_out, void* stream) {
+  int32_t rc = of_check(p);
+  if (rc != DLC_OK) return rc;
+  if (p->N == 0 || p->T == 0) return DLC_OK;
+  const bool closed = p->mode == DLC_MODE_CLOSED_LOOP;
+  if (!A || !B || !C) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: A, B and C are required");
+  if (closed && !x_io) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: x_io is required in closed-loop mode");
+  if (!closed && !y_in) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: y_in is required in agent-only mode");
+  if (p->agent == DLC_OF_LQG && (!K || !Lk || !z_io)) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: LQG needs K, Lk and z_io (x_hat)");
+  if (p->agent == DLC_OF_DRC && (!theta_io || !ynat_io || !us_io)) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: DRC needs theta_io (M), ynat_io and us_io");
+  if (p->agent == DLC_OF_FGRC && (!Phi || !theta_io || !z_io || !ynat_io)) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: the filter family needs Phi, theta_io, z_io and ynat_io");
+  OfArgs a{};
+  a.p = *p;
+  a.A = A; a.B = B; a.C = C; a.K = K; a.Lk = Lk; a.Phi = Phi; a.W = W; a.y_in = y_in;
+  a.x_io = x_io; a.theta_io = theta_io; a.z_io = z_io; a.ynat_io = ynat_io; a.us_io = us_io;
+  a.cost_out = cost_out; a.cost_sum_out = cost_sum_out; a.u_out = u_out; a.status_out = status_out;
+  a.S = layout(a);
+  int dev = 0, max_smem = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_status(e, "cudaGetDevice");
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t per_warp = (size_t)a.S * 4, fixed = (size_t)a.nPhi * 4;
+  if (fixed + per_warp > (size_t)max_smem)
+    return fail(DLC_ERR_SHAPE, "dlc_lds_of_rollout_f32: one env's controller state does not fit in shared memory");
+  // warps per CTA: fill the SM's shared memory with as many envs as fit (at most 8 per CTA, several CTAs per SM)
+  int wpc = 8;
+  while (wpc > 1 && fixed + per_warp * wpc > (size_t)max_smem / 2) wpc >>= 1;
+  if (fixed + per_warp * wpc > (size_t)max_smem) wpc = 1;
+  a.wpc = wpc;
+  const size_t smem = fixed + per_warp * wpc;
+  auto kern = p->agent == DLC_OF_LQG ? of_kernel<DLC_OF_LQG> : (p->agent == DLC_OF_DRC ? of_kernel<DLC_OF_DRC> : of_kernel<DLC_OF_FGRC>);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(of_kernel)");
+  const unsigned grid = (unsigned)((p->N + wpc - 1) / wpc);
+  kern<<<grid, 32 * wpc, smem, (cudaStream_t)stream>>>(a);
+  return cuda_status(cudaGetLastError(), "of_kernel launch");
+}

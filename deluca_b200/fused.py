@@ -379,3 +379,70 @@ def lds_lqr_value_and_grad(A, B, K, x0, T, W=None, seed=0, env_offset=0, t0=0, w
                                              _abi.current_stream_ptr())
     _abi.check(rc, "dlc_lds_lqr_grad_f32")
     return loss, gK, gx, sums
+
+
+def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, Phi=None, theta=None, z=None,
+                   ynat=None, us=None, m=0, h=0, t0=0, lr=0.005, decay=True, R_M=10.0, seed=0, env_offset=0,
+                   w_std=0.5, agent_only=False, keep_costs=True, keep_actions=True, donate=False):
+    """``dlc_lds_of_rollout_f32``: T fused steps of the partially observed LDS (``deluca/envs/_lds.py:102-111``,
+    y = C x) under an output-feedback controller: ``agent`` = "lqg" (``_lqg.py:83-98``; K[.,n,d], Lk[.,d,p],
+    z = x_hat), "drc" (``_drc.py:131-203``; theta = M[N,m,n,p], ynat[N,m,p] and us[N,h,n] newest first,
+    K[.,n,p] or None) or "fgrc" (GRC/SFC/DSC, ``_grc.py:110-169``; Phi[F,L], theta[N,F,n,p], z[N,d],
+    ynat[N,L+m,p] oldest -> newest).  State tensors default to the agents' construction-time zeros; the returned
+    ones (and ``t``) resume the episode.  ``agent_only``: ``Agent.__call__(y)`` with y = ``y_in[T,N,p]``."""
+    shared = A.dim() == 2
+    d, n, p = A.shape[-1], B.shape[-1], C.shape[-2]
+    if agent_only:
+        _f32(y_in, "y_in")
+        N = y_in.shape[1]
+        _f32(y_in, "y_in", (T, N, p))
+        dev = y_in.device
+        x_io = None
+    else:
+        _f32(x, "x")
+        N = x.shape[0]
+        _f32(x, "x", (N, d))
+        dev = x.device
+        x_io = x if donate else x.clone()
+    lead = () if shared else (N,)
+    _f32(A, "A", lead + (d, d)); _f32(B, "B", lead + (d, n)); _f32(C, "C", lead + (p, d)); _f32(W, "W", (T, N, d))
+    own = lambda t, shape, name: (torch.zeros(shape, device=dev) if t is None
+                                  else (_f32(t, name, shape) if donate else _f32(t, name, shape).clone()))
+    code = _abi.OF_AGENT[agent]
+    F = L = 0
+    theta_io = z_io = ynat_io = us_io = None
+    if agent == "lqg":
+        _f32(K, "K", lead + (n, d)); _f32(Lk, "Lk", lead + (d, p))
+        z_io = own(z, (N, d), "z")
+    elif agent == "drc":
+        _f32(K, "K", lead + (n, p))
+        if theta is None:
+            raise ValueError("drc: theta (M[N,m,n,p]) is required -- the reference draws it from PRNGKey(0) (_drc.py:105)")
+        theta_io = own(theta, (N, m, n, p), "theta")
+        ynat_io = own(ynat, (N, m, p), "ynat")
+        us_io = own(us, (N, h, n), "us")
+    else:
+        _f32(Phi, "Phi")
+        F, L = Phi.shape
+        if theta is None:
+            raise ValueError("fgrc: theta[N,F,n,p] is required -- the reference draws it from PRNGKey(0) (_grc.py:77)")
+        theta_io = own(theta, (N, F, n, p), "theta")
+        z_io = own(z, (N, d), "z")
+        ynat_io = own(ynat, (N, L + m, p), "ynat")
+    prm = _abi.DlcOfParams(N=N, env_offset=int(env_offset), T=T, d=d, n=n, p=p, agent=code, m=int(m), h=int(h), F=F,
+                           L=L, t0=int(t0), decay=int(bool(decay)), shared_dynamics=int(shared),
+                           mode=1 if agent_only else 0, lr=float(lr), R_M=float(R_M), w_std=float(w_std), reserved=0,
+                           seed=int(seed))
+    costs = torch.empty(T, N, device=dev) if keep_costs else None
+    U = torch.empty(T, N, n, device=dev) if keep_actions else None
+    cost_sum = torch.zeros(N, dtype=torch.float64, device=dev)
+    status = torch.zeros(N, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().dlc_lds_of_rollout_f32(ctypes.byref(prm), _abi.ptr(A), _abi.ptr(B), _abi.ptr(C), _abi.ptr(K),
+                                               _abi.ptr(Lk), _abi.ptr(Phi), _abi.ptr(W), _abi.ptr(y_in),
+                                               _abi.ptr(x_io), _abi.ptr(theta_io), _abi.ptr(z_io), _abi.ptr(ynat_io),
+                                               _abi.ptr(us_io), _abi.ptr(costs), _abi.ptr(cost_sum), _abi.ptr(U),
+                                               _abi.ptr(status), _abi.current_stream_ptr())
+    _abi.check(rc, "dlc_lds_of_rollout_f32")
+    return LdsRolloutResult(costs=costs, cost_sum=cost_sum, U=U, x=x_io, theta=theta_io, z=z_io, ynat=ynat_io,
+                            us=us_io, t=t0 + T, status=status)

@@ -47,7 +47,8 @@ extern "C" {
 
 int32_t dlc_abi_version(void);
 /* sizeof() of the parameter structs as compiled, so a binding can verify its own layout:
- * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers, 3 DlcPlanParams, 4 DlcSharedGpcParams; 0 for unknown */
+ * which = 0 DlcLdsParams, 1 DlcLungParams, 2 DlcLungBuffers, 3 DlcPlanParams, 4 DlcSharedGpcParams, 5 DlcOfParams;
+ * 0 for unknown */
 size_t dlc_sizeof(int32_t which);
 const char* dlc_last_error(void);
 /* 0 if the current CUDA device can run this library (compute capability 10.x) */
@@ -410,6 +411,72 @@ int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p,
                                        float* cost_out /*[T,N] or NULL*/, double* cost_sum_out /*[N] or NULL*/,
                                        int32_t* status_out /*[N] or NULL*/,
                                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Partially observed LDS (y = C x) driven by an output-feedback controller for T steps, fused
+ * (SURVEY 8(f) rank 3).  Replaces, per env and per step,
+ *     y_t   = C x_t                                   LDS.__call__   deluca/envs/_lds.py:102-111
+ *     u_t   = agent(y_t)                              LQG.__call__   deluca/agents/_lqg.py:83-98
+ *                                                     DRC.__call__   deluca/agents/_drc.py:131-203
+ *                                                     GRC.__call__   deluca/agents/_grc.py:110-169
+ *                                                     SFC.__call__   deluca/agents/_sfc.py:154-214
+ *                                                     DSC.__call__   deluca/agents/_dsc.py:210-292
+ *     c_t   = quad_loss(y_t, u_t)                     deluca/agents/_grc.py:27-39
+ *     x_t+1 = A x_t + B u_t + w_t
+ * GRC, SFC and DSC are one family: a(k) = sum_f Theta[f] (sum_o Phi[f,o] ynat[k+o]) with a fixed filter bank
+ * Phi[F,L] (GRC: F = L = m, Phi = I; SFC: F = h+1, L = m+1; DSC: F = 1+2h+h^2, L = 2m+1) and a y_nat history of
+ * L + m entries.  Theta stacks the reference's parameter blocks in that order (M | M_0, M | M_0, M_1, M_2, M_3).
+ * jit(grad(policy_loss)) is a hand adjoint; the m-step evolve recursion uses the Markov operators C A^j B.
+ * One warp per env, controller state resident in shared memory: the per-env state (dlc_lds_of_smem_bytes) must fit
+ * in 227 KB, d, n, p <= 64.
+ * ------------------------------------------------------------------------------------ */
+#define DLC_OF_LQG 0
+#define DLC_OF_DRC 1
+#define DLC_OF_FGRC 2 /* GRC / SFC / DSC through the filter bank */
+
+typedef struct DlcOfParams {
+  int64_t N;           /* envs in this call */
+  int64_t env_offset;  /* global index of env 0 (keys the in-kernel disturbance stream) */
+  int32_t T;           /* steps */
+  int32_t d, n, p;     /* state / action / observation dim (the agents' d, n, p) */
+  int32_t agent;       /* DLC_OF_* */
+  int32_t m;           /* controller history: GRC/SFC/DSC m, DRC m; 0 for LQG */
+  int32_t h;           /* DRC: length of the Markov operator / action history (_drc.py:52) */
+  int32_t F, L;        /* filter family: number of filters and filter length */
+  int32_t t0;          /* agent step counter at entry (lr decay, disturbance counter) */
+  int32_t decay;       /* lr = lr/(t+1) (_grc.py:145); DRC without decay uses lr = 1.0 as written (_drc.py:184) */
+  int32_t shared_dynamics; /* 1: A, B, C (and K, Lk) are shared by all envs; 0: per env [N,...] */
+  int32_t mode;        /* DLC_MODE_CLOSED_LOOP, or DLC_MODE_AGENT_ONLY: Agent.__call__(y) with y from y_in */
+  float lr;            /* GRC/SFC/DSC lr (_grc.py:52), DRC lr_scale (_drc.py:53) */
+  float R_M;           /* projection radius R_M (_grc.py:49) / RM (_drc.py:55) */
+  float w_std;         /* std of the in-kernel Gaussian disturbance, used when W == NULL */
+  int32_t reserved;
+  uint64_t seed;
+} DlcOfParams;
+
+/* shared memory one env needs (bytes), 0 for an invalid shape */
+size_t dlc_lds_of_smem_bytes(const DlcOfParams* p);
+
+int32_t dlc_lds_of_rollout_f32(
+    const DlcOfParams* p,
+    const float* A,      /* [N,d,d] or [d,d] */
+    const float* B,      /* [N,d,n] or [d,n] */
+    const float* C,      /* [N,p,d] or [p,d] */
+    const float* K,      /* LQG: [N,n,d]; DRC: [N,n,p] or NULL (= 0, _drc.py:104); NULL for the filter family */
+    const float* Lk,     /* LQG: Kalman gain [N,d,p]; NULL otherwise */
+    const float* Phi,    /* filter family: [F,L] (shared by all envs); NULL otherwise */
+    const float* W,      /* [T,N,d] disturbances, or NULL: in-kernel Philox stream (w_std) */
+    const float* y_in,   /* [T,N,p] observations for DLC_MODE_AGENT_ONLY; NULL otherwise */
+    float* x_io,         /* [N,d] env state (closed loop) */
+    float* theta_io,     /* filter family: Theta[N,F,n,p]; DRC: M[N,m,n,p]; NULL for LQG */
+    float* z_io,         /* filter family: internal model state z[N,d] (_grc.py:79); LQG: x_hat[N,d]; NULL for DRC */
+    float* ynat_io,      /* filter family: ynat_history[N,L+m,p], oldest -> newest; DRC: y_nat[N,m,p], newest first */
+    float* us_io,        /* DRC: us[N,h,n], newest first; NULL otherwise */
+    float* cost_out,     /* [T,N] or NULL */
+    double* cost_sum_out,/* [N] or NULL */
+    float* u_out,        /* [T,N,n] or NULL */
+    int32_t* status_out, /* [N] or NULL */
+    void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC

@@ -691,6 +691,75 @@ __global__ void __launch_bounds__(128) env_rollout_kernel(const PlanArgs a) {
   a.cost_out[n] = c;
 }
 
+// Learner.generate_trajectories (deluca/learners/core.py:17-41): N random-policy episodes of T steps,
+// action ~ N(0, 1) per step (SimpleRandom, deluca/agents/_random.py:39-53), emitting the dataset
+// triple (obs, action, next_obs)[N,T,.].  Actions come from the library's Philox stream
+// (counter = (env, t, c/4, 2)); jax.random streams are not reproducible.
+// One thread per trajectory; each warp parks TC = 48/d steps of its 32 trajectories in shared
+// memory and writes them out row-wise, so the [N,T,.] batch-major stores are contiguous runs of
+// TC*D floats per trajectory instead of D-float fragments.
+struct CollectArgs {
+  DlcEnvSpec env;
+  int64_t N, env_offset;
+  int T;
+  uint64_t seed;
+  float action_std;
+  const float* x0;
+  float *obs, *act, *next_obs;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) env_collect_kernel(const CollectArgs a) {
+  using Mdl = Model<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M, TC = 48 / D;  // 16 / 12 / 8 steps parked per trajectory
+  constexpr int XS = ((TC + 1) * D) | 1, US = (TC * M) | 1;  // odd row strides: conflict-free columns
+  __shared__ float sx[4][32 * XS];
+  __shared__ float su[4][32 * US];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nw = (int64_t)blockIdx.x * blockDim.x + warp * 32;  // first trajectory of this warp
+  const int64_t n = nw + lane;
+  const bool live = n < a.N;
+  const Mdl env(a.env);
+  float x[D], u[M], xn[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) x[i] = live ? a.x0[n * D + i] : 0.f;
+  float* mx = sx[warp] + lane * XS;
+  float* mu = su[warp] + lane * US;
+  const int rows = (int)min((int64_t)32, a.N - nw);
+  for (int t0 = 0; t0 < a.T; t0 += TC) {
+    const int tc = min(TC, a.T - t0);
+#pragma unroll
+    for (int i = 0; i < D; ++i) mx[i] = x[i];
+    for (int j = 0; j < tc; ++j) {
+#pragma unroll
+      for (int g = 0; g < (M + 3) / 4; ++g) {
+        float z[4];
+        normal4(a.seed, (uint32_t)(a.env_offset + n), (uint32_t)(t0 + j), (uint32_t)g, 2u, z);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (4 * g + c < M) u[4 * g + c] = __fmul_rn(a.action_std, z[c]);
+      }
+      env.step(x, u, xn);
+#pragma unroll
+      for (int c = 0; c < M; ++c) mu[j * M + c] = u[c];
+#pragma unroll
+      for (int i = 0; i < D; ++i) { x[i] = xn[i]; mx[(j + 1) * D + i] = xn[i]; }
+    }
+    __syncwarp();
+    for (int r = 0; r < rows; ++r) {
+      const int64_t base = (nw + r) * a.T + t0;
+      const float* rx = sx[warp] + r * XS;
+      const float* ru = su[warp] + r * US;
+      for (int q = lane; q < tc * D; q += 32) {
+        a.obs[base * D + q] = rx[q];
+        a.next_obs[base * D + q] = rx[q + D];
+      }
+      for (int q = lane; q < tc * M; q += 32) a.act[base * M + q] = ru[q];
+    }
+    __syncwarp();
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(128) igpc_rollout_kernel(const PlanArgs a) {
   using Mdl = Model<KIND>;
@@ -1040,6 +1109,23 @@ extern "C" int32_t dlc_env_rollout_f32(const DlcPlanParams* p, int32_t use_sim_e
   const unsigned grid = (unsigned)((p->N + 127) / 128);
   DLC_DISPATCH_ENV(p->env_true.kind, env_rollout_kernel, grid, (cudaStream_t)stream, a);
   return cuda_status(cudaGetLastError(), "env_rollout_kernel launch");
+}
+
+extern "C" int32_t dlc_env_collect_f32(const DlcEnvSpec* env, int64_t N, int32_t T, uint64_t seed,
+                                      int64_t env_offset, float action_std, const float* x0, float* obs_out,
+                                      float* action_out, float* next_obs_out, void* stream) {
+  if (!env) return fail(DLC_ERR_ARG, "dlc_env_collect_f32: NULL env");
+  if (N < 0 || T < 1) return fail(DLC_ERR_ARG, "dlc_env_collect_f32: bad N / T");
+  if (env->kind < DLC_ENV_PENDULUM || env->kind > DLC_ENV_REACHER)
+    return fail(DLC_ERR_SHAPE, "dlc_env_collect_f32: unknown env kind");
+  if (N == 0) return DLC_OK;
+  if (!x0 || !obs_out || !action_out || !next_obs_out) return fail(DLC_ERR_ARG, "dlc_env_collect_f32: NULL buffer");
+  CollectArgs a{};
+  a.env = *env; a.N = N; a.env_offset = env_offset; a.T = T; a.seed = seed; a.action_std = action_std;
+  a.x0 = x0; a.obs = obs_out; a.act = action_out; a.next_obs = next_obs_out;
+  const unsigned grid = (unsigned)((N + 127) / 128);
+  DLC_DISPATCH_ENV(env->kind, env_collect_kernel, grid, (cudaStream_t)stream, a);
+  return cuda_status(cudaGetLastError(), "env_collect_kernel launch");
 }
 
 extern "C" int32_t dlc_igpc_rollout_f32(const DlcPlanParams* p, const float* U_old, const float* k, const float* K,

@@ -446,3 +446,42 @@ def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, 
     _abi.check(rc, "dlc_lds_of_rollout_f32")
     return LdsRolloutResult(costs=costs, cost_sum=cost_sum, U=U, x=x_io, theta=theta_io, z=z_io, ynat=ynat_io,
                             us=us_io, t=t0 + T, status=status)
+
+
+def gae(losses, values, log_probs=None, done_masks=None, discount=0.99, gae_param=0.95, time_major=False,
+        returns_use_values=False, want_returns=True):
+    """``gae_advantages`` + the returns line of ``ac_rollout`` (``deluca/training/ppo.py:44-84,131-134``)
+    over [N,T] (or [T,N] with ``time_major``) series -> (advantages, returns | None)."""
+    _f32(losses, "losses")
+    if losses.dim() != 2:
+        raise ValueError("losses must be [N,T] (or [T,N] with time_major)")
+    for name, t in (("values", values), ("log_probs", log_probs), ("done_masks", done_masks)):
+        _f32(t, name, losses.shape)
+    if want_returns and not returns_use_values and log_probs is None:
+        raise ValueError("returns = advantages + log_probs (ppo.py:133, as written) needs log_probs")
+    T, N = losses.shape if time_major else losses.shape[::-1]
+    adv = torch.empty_like(losses)
+    ret = torch.empty_like(losses) if want_returns else None
+    rc = _launch_on(losses, _abi.lib().dlc_gae_f32, N, T, int(time_major), _abi.ptr(losses), _abi.ptr(values),
+                    _abi.ptr(log_probs), _abi.ptr(done_masks), float(discount), float(gae_param),
+                    int(returns_use_values), _abi.ptr(adv), _abi.ptr(ret))
+    _abi.check(rc, "dlc_gae_f32")
+    return adv, ret
+
+
+def env_collect(env, x0, T, seed=0, env_offset=0, action_std=1.0):
+    """``Learner.generate_trajectories`` (``deluca/learners/core.py:17-41``) on a classic env:
+    (obs[N,T,d], action[N,T,m], next_obs[N,T,d]) under the N(0, action_std^2) random policy."""
+    N, d = x0.shape
+    _f32(x0, "x0", (N, env.state_dim))
+    spec = _abi.DlcEnvSpec()
+    spec.kind, vals = env.spec()
+    for i, v in enumerate(vals):
+        spec.p[i] = v
+    obs = torch.empty(N, T, d, device=x0.device)
+    act = torch.empty(N, T, env.action_dim, device=x0.device)
+    nxt = torch.empty(N, T, d, device=x0.device)
+    rc = _launch_on(x0, _abi.lib().dlc_env_collect_f32, ctypes.byref(spec), N, int(T), int(seed), int(env_offset),
+                    float(action_std), _abi.ptr(x0), _abi.ptr(obs), _abi.ptr(act), _abi.ptr(nxt))
+    _abi.check(rc, "dlc_env_collect_f32")
+    return obs, act, nxt

@@ -479,6 +479,37 @@ int32_t dlc_lds_of_rollout_f32(
     void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Experience collection around the rollout.
+ *
+ *   dlc_gae_f32          gae_advantages                 deluca/training/ppo.py:44-84
+ *                        + the tail of ac_rollout        deluca/training/ppo.py:131-134
+ *       rewards = -losses;  A_{T-1} = r_{T-1} - v_{T-1};
+ *       A_t = r_t + discount v_{t+1} mask_t - v_t + discount gae_param mask_t A_{t+1};
+ *       returns = advantages + log_probs  -- as written (`advantages + t[4]`, t[4] is log_probs);
+ *       returns_use_values = 1 gives the intended advantages + values.
+ *       done_masks == NULL means all ones (ac_rollout emits the constant 1.0, ppo.py:113).
+ *       Layout: time_major = 0 -> [N,T] (what vmap(ac_rollout) stacks; flattening it to the
+ *       [N*T] experience batch of ac_get_experience, ppo.py:196-199, is a view);
+ *       time_major = 1 -> [T,N] (gae_advantages' own documented shape).
+ *       float32, each operation rounded separately in the reference's order.
+ *
+ *   dlc_env_collect_f32  Learner.generate_trajectories  deluca/learners/core.py:17-41
+ *       N random-policy episodes (SimpleRandom: action ~ N(0,1)*action_std, deluca/agents/_random.py:39-53)
+ *       of T steps on a classic env; writes obs[N,T,d], action[N,T,m], next_obs[N,T,d].
+ *       Actions: Philox counter (env_offset + n, t, c/4, 2) with key = seed.
+ * ------------------------------------------------------------------------------------ */
+int32_t dlc_gae_f32(int64_t N, int32_t T, int32_t time_major,
+                    const float* losses, const float* values,
+                    const float* log_probs /* NULL allowed if returns_out == NULL or returns_use_values */,
+                    const float* done_masks /* or NULL */,
+                    float discount, float gae_param, int32_t returns_use_values,
+                    float* advantages_out, float* returns_out /* or NULL */, void* stream);
+
+int32_t dlc_env_collect_f32(const DlcEnvSpec* env, int64_t N, int32_t T, uint64_t seed, int64_t env_offset,
+                            float action_std, const float* x0 /*[N,d]*/, float* obs_out /*[N,T,d]*/,
+                            float* action_out /*[N,T,m]*/, float* next_obs_out /*[N,T,d]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC
  * kernels is not in MEASURED_PEAKS.json, so bench.py measures it with these.
  *   which: 0 FFMA (72 FMA/thread/iter)   1 packed fma.f32x2 (72 FMA/thread/iter)

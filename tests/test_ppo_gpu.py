@@ -103,7 +103,7 @@ def test_generate_trajectories_matches_oracle(which, N, T):
     obs, act, nxt = Learner(d_env).generate_trajectories(N, T, key=123)
     assert obs.shape == (N, T, o_env.d) and act.shape == (N, T, o_env.m) and nxt.shape == obs.shape
     o_act = OP.random_actions(123, np.arange(N), T, o_env.m)
-    np.testing.assert_allclose(act.cpu().numpy(), o_act, rtol=0, atol=2e-6)     # MUFU vs libm Box-Muller
+    np.testing.assert_allclose(act.cpu().numpy(), o_act, rtol=0, atol=5e-6)     # MUFU vs libm Box-Muller
     # step-by-step parity on the device's own (obs, action): one env step each, no chaotic drift
     x = obs.cpu().numpy().reshape(N * T, o_env.d).astype(np.float64)
     u = act.cpu().numpy().reshape(N * T, o_env.m).astype(np.float64)

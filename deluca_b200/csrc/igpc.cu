@@ -1073,6 +1073,78 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
   if (a.status_out) a.status_out[n] = status;
 }
 
+// The same outer loops with the backtracking candidates of an iteration evaluated SIDE BY SIDE: a
+// group of PLAN_G lanes owns a trajectory, lane j rolls out candidate j (alphaC = 1.1 alpha 1.1^(-j^2))
+// into its own workspace slot, and the group adopts the FIRST accepted candidate in the reference's
+// order -- exactly what the sequential `for alphaC in ...: if cC <= c: break` keeps (ilqr.py:55-73,
+// igpc.py:159-170, ilc.py:49-60); every candidate is the same arithmetic as in plan_kernel.  The
+// serial chain per iteration drops from (1 + tried candidates) rollouts to 2; the planning loops are
+// latency-bound with most issue slots idle, so the redundant candidates are free.
+constexpr int PLAN_G = 16;
+
+__host__ __device__ inline bool plan_parallel_candidates(const DlcPlanParams& p) {
+  const bool identical = p.algo == DLC_ALGO_ILQR && !p.fix_backtracking;  // SURVEY A-10: one distinct candidate
+  return p.backtracking && !identical && p.n_alpha > 1 && p.n_alpha <= PLAN_G;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) plan_par_kernel(const PlanArgs a) {
+  using Mdl = Model<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M, G = PLAN_G;
+  const DlcPlanParams& p = a.p;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (n >= p.N) return;  // whole groups leave together
+  const int j = threadIdx.x & (G - 1);
+  const int gshift = threadIdx.x & 31 & ~(G - 1);
+  const unsigned gmask = ((1u << G) - 1u) << gshift;
+  const int H = p.H;
+  const int WS = (H + 1) * D + H * M;
+  const Mdl tru(p.env_true), sim(p.env_sim);
+  float* X = a.X_out + n * (H + 1) * D;
+  float* U = a.U_out + n * H * M;
+  float* kk = a.k_out + n * H * M;
+  float* KK = a.K_out + n * H * M * D;
+  float* XC = a.ws + (n * G + j) * (int64_t)WS;
+  float* UC = XC + (H + 1) * D;
+  const float* x0 = a.x0 + n * D;
+  const bool cand = j < p.n_alpha;
+  float c = 0.f;
+  if (j == 0) c = rollout_one(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
+  c = __shfl_sync(gmask, c, gshift);
+  float alpha = p.alpha0;
+  int status = 0;
+  for (int t = 0; t < p.T; ++t) {
+    if (j == 0) status |= backward_pass(sim, p, X, U, kk, KK);
+    __syncwarp(gmask);
+    const float alphaC = (alpha * 1.1f) * powf(1.1f, -(float)(j * j));
+    float cC = 0.f;
+    bool accept = false;
+    if (cand) {
+      if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
+      else cC = rollout_one(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+      accept = p.algo == DLC_ALGO_IGPC ? (cC < c) : (cC <= c);
+    }
+    const unsigned votes = (__ballot_sync(gmask, accept) >> gshift) & ((1u << G) - 1u);
+    __syncwarp(gmask);  // every candidate buffer is complete and nobody reads X / U any more
+    if (votes) {
+      const int js = __ffs(votes) - 1;  // first accepted in the reference's order
+      const float* XS = a.ws + (n * G + js) * (int64_t)WS;
+      const float* US = XS + (H + 1) * D;
+      for (int i = j; i < (H + 1) * D; i += G) X[i] = XS[i];
+      for (int i = j; i < H * M; i += G) U[i] = US[i];
+      c = __shfl_sync(gmask, cC, gshift + js);
+      alpha = __shfl_sync(gmask, alphaC, gshift + js);
+    }
+    __syncwarp(gmask);
+  }
+  if (j == 0) {
+    a.cost_out[n] = c;
+    if (a.alpha_out) a.alpha_out[n] = alpha;
+    if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
+    if (a.status_out) a.status_out[n] = status;
+  }
+}
+
 static int32_t check_plan(const DlcPlanParams* p, const char* who) {
   if (!p) return fail(DLC_ERR_ARG, "NULL params");
   if (p->N < 0 || p->H < 1 || p->T < 0) return fail(DLC_ERR_ARG, "bad N / H / T");
@@ -1208,7 +1280,8 @@ extern "C" size_t dlc_plan_workspace_bytes(const DlcPlanParams* p) {
   if (!p || p->N <= 0 || p->H < 1) return 0;
   const int d = p->env_true.kind == DLC_ENV_PENDULUM ? 3 : (p->env_true.kind == DLC_ENV_CARTPOLE ? 4 : 6);
   const int m = p->env_true.kind >= DLC_ENV_QUADROTOR ? 2 : 1;
-  return (size_t)p->N * ((size_t)(p->H + 1) * d + (size_t)p->H * m) * sizeof(float);
+  const size_t slots = plan_parallel_candidates(*p) ? PLAN_G : 1;  // one candidate buffer per lane of a group
+  return (size_t)p->N * slots * ((size_t)(p->H + 1) * d + (size_t)p->H * m) * sizeof(float);
 }
 
 extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float* x0, float* X_out, float* k_out,
@@ -1227,6 +1300,11 @@ extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float
   PlanArgs a{};
   a.p = *p; a.U_out = U_io; a.x0 = x0; a.X_out = X_out; a.k_out = k_out; a.K_out = K_out; a.cost_out = cost_out;
   a.alpha_out = alpha_out; a.status_out = status_out; a.ws = (float*)workspace;
+  if (plan_parallel_candidates(*p)) {
+    const unsigned grid = (unsigned)((p->N * PLAN_G + 127) / 128);
+    DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);
+    return cuda_status(cudaGetLastError(), "plan_par_kernel launch");
+  }
   const unsigned grid = (unsigned)((p->N + 127) / 128);
   DLC_DISPATCH_ENV(p->env_true.kind, plan_kernel, grid, (cudaStream_t)stream, a);
   return cuda_status(cudaGetLastError(), "plan_kernel launch");

@@ -4,6 +4,8 @@
 // independent trajectories, one thread per trajectory.  Per-trajectory data (X, U, k, K: 6.4 KB at
 // d=3, H=200) stays in the caller's env-major arrays, which are L2-resident for the configured sizes;
 // the time axis is a serial dependency chain, so these kernels are latency- not bandwidth-bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dlc {
@@ -315,6 +317,73 @@ __device__ float rollout_one(const Mdl& env, const DlcPlanParams& p, const float
   return cost;
 }
 
+// The per-step operands of the feedback law, held in registers.  The planning loops are one long
+// dependency chain per trajectory, so a global load issued where its value is needed stalls the
+// chain for an L1/L2 round trip every step (ncu: long_scoreboard was 45 % of all stall cycles);
+// loading step h+1's operands while step h computes takes the memory latency off the chain.
+template <int D, int M>
+struct StepOps {
+  float Uo[M], kk[M], KK[M * D], Xo[D];
+  // h < H: everything; h == H: only X_old[H] (read by the dede / delin disturbance models)
+  __device__ __forceinline__ void load(const float* U_, const float* k_, const float* K_, const float* X_, int h, int H) {
+    if (h < H) {
+#pragma unroll
+      for (int c = 0; c < M; ++c) Uo[c] = U_[h * M + c];
+      if (k_) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) kk[c] = k_[h * M + c];
+#pragma unroll
+        for (int i = 0; i < M * D; ++i) KK[i] = K_[h * M * D + i];
+      }
+    }
+    if (X_ && h <= H) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) Xo[i] = X_[h * D + i];
+    }
+  }
+  __device__ __forceinline__ void load_x(const float* X_, int h) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) Xo[i] = X_[h * D + i];
+  }
+  __device__ __forceinline__ void feedback(float alpha, const float* x, float* u) const {
+    feedback_u<D, M>(Uo, kk, KK, Xo, alpha, x, u);
+  }
+};
+
+// rollout_one with the operands of step h+1 loaded while step h computes
+template <class Mdl, bool PF>
+__device__ float rollout_one_pf(const Mdl& env, const DlcPlanParams& p, const float* Uo, const float* kk,
+                             const float* KK, const float* Xo, float alpha, const float* x0, float* Xw, float* Uw) {
+  constexpr int D = Mdl::D, M = Mdl::M;
+  float x[D], u[M], xn[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) { x[i] = x0[i]; Xw[i] = x[i]; }
+  float cost = 0.f;
+  StepOps<D, M> cur, nxt;
+  if (PF) cur.load(Uo, kk, KK, kk ? Xo : nullptr, 0, p.H);
+  for (int h = 0; h < p.H; ++h) {
+    if (PF) {
+      if (h + 1 < p.H) nxt.load(Uo, kk, KK, kk ? Xo : nullptr, h + 1, p.H);
+    } else {
+      cur.load(Uo, kk, KK, kk ? Xo : nullptr, h, p.H);
+    }
+    if (kk == nullptr) {
+#pragma unroll
+      for (int c = 0; c < M; ++c) u[c] = cur.Uo[c];
+    } else {
+      cur.feedback(alpha, x, u);
+    }
+    env.step(x, u, xn);
+    cost += quad_cost<D, M>(p, x, u);
+#pragma unroll
+    for (int c = 0; c < M; ++c) Uw[h * M + c] = u[c];
+#pragma unroll
+    for (int i = 0; i < D; ++i) { x[i] = xn[i]; Xw[(h + 1) * D + i] = xn[i]; }
+    if (PF) cur = nxt;
+  }
+  return cost;
+}
+
 // small dense inverse (Gauss-Jordan, partial pivoting); returns false if singular / non-finite
 template <int M>
 __device__ bool inv_small(const float* A, float* Ai) {
@@ -504,6 +573,47 @@ __device__ int backward_pass(const Mdl& sim, const DlcPlanParams& p, const float
   return status;
 }
 
+// backward_pass with the next step's (x, u) loaded one step early
+template <class Mdl, bool PF>
+__device__ int backward_pass_pf(const Mdl& sim, const DlcPlanParams& p, const float* X, const float* U, float* kk,
+                             float* KK) {
+  constexpr int D = Mdl::D, M = Mdl::M;
+  float Vx[D], Vxx[D * D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) Vx[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) Vxx[i] = 0.f;
+  int status = 0;
+  float xq[D], uq[M];  // operands of the next step down, loaded one step early (see StepOps)
+#pragma unroll
+  for (int i = 0; i < D; ++i) xq[i] = X[(p.H - 1) * D + i];
+#pragma unroll
+  for (int c = 0; c < M; ++c) uq[c] = U[(p.H - 1) * M + c];
+  for (int h = p.H - 1; h >= 0; --h) {
+    float x[D], u[M], fx[D * D], fu[D * M], cx[D], cu[M], cxx[D * D], cuu[M * M];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = xq[i];
+#pragma unroll
+    for (int c = 0; c < M; ++c) u[c] = uq[c];
+    if (PF && h > 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) xq[i] = X[(h - 1) * D + i];
+#pragma unroll
+      for (int c = 0; c < M; ++c) uq[c] = U[(h - 1) * M + c];
+    }
+    if (!PF) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = X[h * D + i];
+#pragma unroll
+      for (int c = 0; c < M; ++c) u[c] = U[h * M + c];
+    }
+    sim.jac(x, u, fx, fu);
+    cost_ders<D, M>(p, x, u, cx, cu, cxx, cuu);
+    status |= riccati_step<D, M>(fx, fu, cx, cu, cxx, cuu, Vx, Vxx, kk + h * M, KK + h * M * D);
+  }
+  return status;
+}
+
 // GPC_rollout (igpc.py:63-126) for one trajectory; counterfact_loss gradient by hand adjoint
 // (only the last step's cost survives in the reference, igpc.py:41).
 template <class Mdl>
@@ -664,6 +774,193 @@ __device__ float igpc_rollout_one(const Mdl& tru, const Mdl& sim, const DlcPlanP
     for (int i = 0; i < D; ++i) x[i] = xn[i];
   }
   return cost;
+}
+
+// igpc_rollout_one with the counterfactual window's operands and states kept in a register ring
+template <class Mdl, bool PF>
+__device__ float igpc_rollout_one_pf(const Mdl& tru, const Mdl& sim, const DlcPlanParams& p, const float* Uo,
+                                  const float* kk, const float* KK, const float* Xo, float alpha, const float* x0,
+                                  float* Xw, float* Uw) {
+  constexpr int D = Mdl::D, M = Mdl::M, HG = 3, MG = 3;  // H, M of GPC_rollout (:67)
+  const float Cc = 1.0f;
+  float W[HG + MG][D], E[HG][M][D], off[M];
+#pragma unroll
+  for (int i = 0; i < HG + MG; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) W[i][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < HG; ++i)
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+      for (int j = 0; j < D; ++j) E[i][c][j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < M; ++c) off[c] = 0.f;
+  float x[D], u[M], xn[D], xs[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) { x[i] = x0[i]; Xw[i] = x[i]; }
+  float cost = 0.f;
+  // operands of steps h-HG .. h-1 (what the counterfactual window replays), of step h and of step h+1
+  StepOps<D, M> ring[HG], cur, nxt;
+  float xring[HG][D];  // X[h-HG .. h-1] of THIS rollout
+  if (PF) cur.load(Uo, kk, KK, Xo, 0, p.H);
+  for (int h = 0; h < p.H; ++h) {
+    if (PF) {
+      nxt.load(Uo, kk, KK, Xo, h + 1, p.H);
+    } else {
+      cur.load(Uo, kk, KK, Xo, h, p.H);
+      if (p.w_is != DLC_W_DE) nxt.load_x(Xo, h + 1);
+    }
+    // U_delta = tensordot(E, W[-M:]) + off                                :80
+    cur.feedback(alpha, x, u);
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < HG; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(E[i][c][j], W[HG + i][j], s);
+      u[c] += Cc * (s + off[c]);
+    }
+    tru.step(x, u, xn);                                                    // :87
+    cost += quad_cost<D, M>(p, x, u);                                      // :88
+    sim.step(x, u, xs);                                                    // :91
+    float w[D];
+    if (p.w_is == DLC_W_DE) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = xn[i] - xs[i];
+    } else if (p.w_is == DLC_W_DEDE) {   // D[h] = X_old[h+1] - sim(X_old[h], U_old[h])  (compute_ders)
+      float xo[D], uo[M], so[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xo[i] = cur.Xo[i];
+#pragma unroll
+      for (int c = 0; c < M; ++c) uo[c] = cur.Uo[c];
+      sim.step(xo, uo, so);
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = (xn[i] - xs[i]) - (nxt.Xo[i] - so[i]);
+    } else {                             // F[h] = jac of sim at (X_old[h], U_old[h])
+      float xo[D], uo[M], fx[D * D], fu[D * M];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xo[i] = cur.Xo[i];
+#pragma unroll
+      for (int c = 0; c < M; ++c) uo[c] = cur.Uo[c];
+      sim.jac(xo, uo, fx, fu);
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float s = 0.f, t = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(fx[i * D + j], x[j] - xo[j], s);
+#pragma unroll
+        for (int c = 0; c < M; ++c) t = fmaf(fu[i * M + c], u[c] - uo[c], t);
+        w[i] = xn[i] - ((nxt.Xo[i] + s) + t);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < HG + MG - 1; ++i)                                  // W[0] = w; roll(-1)   :103-104
+#pragma unroll
+      for (int j = 0; j < D; ++j) W[i][j] = W[i + 1][j];
+#pragma unroll
+    for (int j = 0; j < D; ++j) W[HG + MG - 1][j] = w[j];
+#pragma unroll
+    for (int c = 0; c < M; ++c) Uw[h * M + c] = u[c];
+#pragma unroll
+    for (int i = 0; i < D; ++i) Xw[(h + 1) * D + i] = xn[i];
+
+    if (h >= HG) {                                                         // :105-125
+      // forward: y_0 = X[h-H]; y_{j+1} = sim(y_j, u_j) + W[j+M]
+      float y[HG][D], uu[HG][M], Fx[HG - 1][D * D], Fu[HG - 1][D * M];
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[0][i] = xring[0][i];   // X[h-H] of this rollout
+#pragma unroll
+      for (int j = 0; j < HG; ++j) {
+        ring[j].feedback(alpha, y[j], uu[j]);              // step h-H+j
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < HG; ++i)
+#pragma unroll
+            for (int l = 0; l < D; ++l) s = fmaf(E[i][c][l], W[j + i][l], s);
+          uu[j][c] += Cc * (s + off[c]);
+        }
+        if (j < HG - 1) {
+          float yn[D];
+          sim.jac(y[j], uu[j], Fx[j], Fu[j]);
+          sim.step(y[j], uu[j], yn);
+#pragma unroll
+          for (int i = 0; i < D; ++i) y[j + 1][i] = yn[i] + W[j + MG][i];
+        }
+      }
+      // adjoint of c(y_{H-1}, u_{H-1})
+      float ly[D], lu[M], cxx[D * D], cuu[M * M];
+      cost_ders<D, M>(p, y[HG - 1], uu[HG - 1], ly, lu, cxx, cuu);
+      const float sc = p.lr / (float)h;
+#pragma unroll
+      for (int j = HG - 1; j >= 0; --j) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const float g = Cc * lu[c];
+          off[c] -= sc * g;
+#pragma unroll
+          for (int i = 0; i < HG; ++i)
+#pragma unroll
+            for (int l = 0; l < D; ++l) E[i][c][l] -= sc * (g * W[j + i][l]);
+        }
+        // note: E/off of this very update must not feed the remaining adjoint steps -- they do not:
+        // the adjoint only reads W, K, Fx, Fu.
+        const float* Kj = ring[j].KK;
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+          float s = ly[l];
+#pragma unroll
+          for (int c = 0; c < M; ++c) s = fmaf(Kj[c * D + l], lu[c], s);
+          ly[l] = s;
+        }
+        if (j > 0) {
+          float nu[M], ny[D];
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s = fmaf(Fu[j - 1][i * M + c], ly[i], s);
+            nu[c] = s;
+          }
+#pragma unroll
+          for (int l = 0; l < D; ++l) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s = fmaf(Fx[j - 1][i * D + l], ly[i], s);
+            ny[l] = s;
+          }
+#pragma unroll
+          for (int c = 0; c < M; ++c) lu[c] = nu[c];
+#pragma unroll
+          for (int l = 0; l < D; ++l) ly[l] = ny[l];
+        }
+      }
+    }
+    // slide the window: step h joins the ring, h+1 becomes current
+#pragma unroll
+    for (int j = 0; j < HG - 1; ++j) {
+      ring[j] = ring[j + 1];
+#pragma unroll
+      for (int i = 0; i < D; ++i) xring[j][i] = xring[j + 1][i];
+    }
+    ring[HG - 1] = cur;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { xring[HG - 1][i] = x[i]; x[i] = xn[i]; }
+    if (PF) cur = nxt;
+  }
+  return cost;
+}
+
+// the register ring of igpc_rollout_one_pf costs 5 x (2m + md + d) registers: worth it for d <= 4, spills beyond
+template <class Mdl>
+__device__ __forceinline__ float igpc_rollout_best(const Mdl& tru, const Mdl& sim, const DlcPlanParams& p,
+                                                   const float* Uo, const float* kk, const float* KK, const float* Xo,
+                                                   float alpha, const float* x0, float* Xw, float* Uw) {
+  if constexpr (Mdl::D <= 4) return igpc_rollout_one_pf<Mdl, true>(tru, sim, p, Uo, kk, KK, Xo, alpha, x0, Xw, Uw);
+  else return igpc_rollout_one(tru, sim, p, Uo, kk, KK, Xo, alpha, x0, Xw, Uw);
 }
 
 // ----------------------------------------------------------------------------------- kernels
@@ -1035,11 +1332,11 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
   float* UC = XC + (H + 1) * D;
   const float* x0 = a.x0 + n * D;
   // initial open-loop rollout into the candidate buffers, then adopt it (U may alias U_old)
-  float c = rollout_one(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
+  float c = rollout_one_pf<Mdl, true>(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
   float alpha = p.alpha0;
   int status = 0;
   for (int t = 0; t < p.T; ++t) {
-    status |= backward_pass(sim, p, X, U, kk, KK);   // compute_ders(env_sim) + LQR
+    status |= backward_pass_pf<Mdl, true>(sim, p, X, U, kk, KK);   // compute_ders(env_sim) + LQR
     const bool ilqr = p.algo == DLC_ALGO_ILQR;
     if (p.backtracking) {
       // iLQR as written passes `alpha` (not alphaC) to every candidate: they are identical, so only
@@ -1049,8 +1346,8 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
         const float alphaC = (alpha * 1.1f) * powf(1.1f, -(float)(j * j));
         const float a_use = (ilqr && !p.fix_backtracking) ? alpha : alphaC;
         float cC;
-        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, a_use, x0, XC, UC);
-        else cC = rollout_one(tru, p, U, kk, KK, X, a_use, x0, XC, UC);
+        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_best(tru, sim, p, U, kk, KK, X, a_use, x0, XC, UC);
+        else cC = rollout_one_pf<Mdl, true>(tru, p, U, kk, KK, X, a_use, x0, XC, UC);
         const bool accept = p.algo == DLC_ALGO_IGPC ? (cC < c) : (cC <= c);
         if (accept) {
           for (int i = 0; i < (H + 1) * D; ++i) X[i] = XC[i];
@@ -1061,8 +1358,8 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
         }
       }
     } else {
-      if (p.algo == DLC_ALGO_IGPC) c = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alpha, x0, XC, UC);
-      else c = rollout_one(tru, p, U, kk, KK, X, alpha, x0, XC, UC);
+      if (p.algo == DLC_ALGO_IGPC) c = igpc_rollout_best(tru, sim, p, U, kk, KK, X, alpha, x0, XC, UC);
+      else c = rollout_one_pf<Mdl, true>(tru, p, U, kk, KK, X, alpha, x0, XC, UC);
       for (int i = 0; i < (H + 1) * D; ++i) X[i] = XC[i];
       for (int i = 0; i < H * M; ++i) U[i] = UC[i];
     }
@@ -1080,6 +1377,9 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
 // igpc.py:159-170, ilc.py:49-60); every candidate is the same arithmetic as in plan_kernel.  The
 // serial chain per iteration drops from (1 + tried candidates) rollouts to 2; the planning loops are
 // latency-bound with most issue slots idle, so the redundant candidates are free.
+// The group's loads of the nominal trajectory are warp broadcasts of L1-resident lines, so the
+// one-step-ahead operand prefetch of the serial kernel buys nothing here and its registers would
+// push the 512-CTA launch of config 3 (4096 trajectories) past one wave (measured: 7.6 -> 10.7 ms).
 constexpr int PLAN_G = 16;
 
 __host__ __device__ inline bool plan_parallel_candidates(const DlcPlanParams& p) {
@@ -1088,7 +1388,7 @@ __host__ __device__ inline bool plan_parallel_candidates(const DlcPlanParams& p)
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128) plan_par_kernel(const PlanArgs a) {
+__global__ void __launch_bounds__(128, (Model<KIND>::D <= 4) ? 4 : 2) plan_par_kernel(const PlanArgs a) {
   using Mdl = Model<KIND>;
   constexpr int D = Mdl::D, M = Mdl::M, G = PLAN_G;
   const DlcPlanParams& p = a.p;
@@ -1158,6 +1458,14 @@ static int32_t check_plan(const DlcPlanParams* p, const char* who) {
 }  // namespace dlc
 
 using namespace dlc;
+
+#define DLC_DISPATCH_ENV_B(kind, KERNEL, grid, block, st, args)                            \
+  do {                                                                                    \
+    if ((kind) == DLC_ENV_PENDULUM) KERNEL<DLC_ENV_PENDULUM><<<grid, block, 0, st>>>(args); \
+    else if ((kind) == DLC_ENV_CARTPOLE) KERNEL<DLC_ENV_CARTPOLE><<<grid, block, 0, st>>>(args); \
+    else if ((kind) == DLC_ENV_QUADROTOR) KERNEL<DLC_ENV_QUADROTOR><<<grid, block, 0, st>>>(args); \
+    else KERNEL<DLC_ENV_REACHER><<<grid, block, 0, st>>>(args);                           \
+  } while (0)
 
 #define DLC_DISPATCH_ENV(kind, KERNEL, grid, st, args)                                   \
   do {                                                                                    \
@@ -1305,7 +1613,9 @@ extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float
     DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);
     return cuda_status(cudaGetLastError(), "plan_par_kernel launch");
   }
-  const unsigned grid = (unsigned)((p->N + 127) / 128);
-  DLC_DISPATCH_ENV(p->env_true.kind, plan_kernel, grid, (cudaStream_t)stream, a);
+  // one-warp CTAs: a trajectory's working set is ~10 KB, so spreading the warps over all SMs (instead of four
+  // per SM on a quarter of them) is what keeps it L1-resident
+  const unsigned grid = (unsigned)((p->N + 31) / 32);
+  DLC_DISPATCH_ENV_B(p->env_true.kind, plan_kernel, grid, 32, (cudaStream_t)stream, a);
   return cuda_status(cudaGetLastError(), "plan_kernel launch");
 }

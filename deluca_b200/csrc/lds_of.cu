@@ -10,7 +10,7 @@
 //                                            with (F, L, Phi) chosen by the host mirror (oracle/of.py filter_bank)
 //   env   deluca/envs/_lds.py:102-111     x <- A x + B u + w,  y = C x;   cost = quad_loss(y, u)  (_grc.py:27-39)
 //
-// Mapping: ONE WARP owns an env.  Everything the env needs between steps (A, B, C, the Markov operators, the
+// Mapping: a group of 8, 16 or 32 LANES owns an env (chosen from the contraction widths; see of_kernel).  Everything the env needs between steps (A, B, C, the Markov operators, the
 // parameters, the history rings) stays in the warp's slice of shared memory for all T steps; lanes split the
 // elements of each small contraction and meet through warp shuffles / __syncwarp.  Runtime dims.
 //
@@ -35,43 +35,52 @@ struct OfArgs {
   double* cost_sum_out;
   float* u_out;
   int32_t* status_out;
-  int wpc;   // warps (envs) per CTA
-  int S;     // floats of shared memory per warp
+  int wpc;   // envs (lane groups) per CTA
+  int S;     // floats of shared memory per env
   int J;     // Markov operators kept (m for the filter family, h for DRC)
   int FP;    // length of one feature window: F * p (filter family), m * p (DRC)
   int nPhi;  // CTA-wide floats at the start of dynamic shared memory (the filter bank)
   int oA, oB, oC, oG, oK, oL, oTh, oFeat, oYn, oUs, oX, oZ, oY, oU, oAct, oGact, oFy, oTmp;
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
+// sum over the GL lanes that own an env (GL = 32: the whole warp)
+template <int GL>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  for (int off = GL / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }
 
 // e / den for 0 <= e < 2^20 (inv = 1 / den): one multiply and a conversion instead of an integer division
 __device__ __forceinline__ int fast_div(int e, float inv) { return (int)(((float)e + 0.5f) * inv); }
 
-// out[r] (r = lane, lane + 32) = sum_c Mat[r][c] v[c]   (rows <= 64); the caller decides where the result goes
-__device__ __forceinline__ void matvec2(const float* Mat, const float* v, int rows, int cols, int lane, float& r0, float& r1) {
-  r0 = 0.f; r1 = 0.f;
-  if (lane < rows) {
-    const float* row = Mat + lane * cols;
-    for (int c = 0; c < cols; ++c) r0 = fmaf(row[c], v[c], r0);
-  }
-  if (lane + 32 < rows) {
-    const float* row = Mat + (lane + 32) * cols;
-    for (int c = 0; c < cols; ++c) r1 = fmaf(row[c], v[c], r1);
+// r[k] (+)= sum_c Mat[row][c] v[c] for row = gl + k GL < rows (rows <= 2 GL); the caller decides where the result goes.
+// ACC continues the accumulation in r (A z + B u + L e in one register per row).
+template <int GL, bool ACC = false>
+__device__ __forceinline__ void matvec(const float* Mat, const float* v, int rows, int cols, int gl, float (&r)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (!ACC) r[k] = 0.f;
+    if (k * GL < rows) {   // warp-uniform
+      const int row = gl + k * GL;
+      if (row < rows) {
+        const float* mr = Mat + row * cols;
+        float acc = r[k];
+        for (int c = 0; c < cols; ++c) acc = fmaf(mr[c], v[c], acc);
+        r[k] = acc;
+      }
+    }
   }
 }
 
 __device__ __forceinline__ float pick4(const float z[4], int k) { return k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3])); }
 
-// buf[i] <- (i < step) ? fresh[i] : buf[i - step]  for i < tot: a newest-first history takes one entry.  32-wide blocks,
+// buf[i] <- (i < step) ? fresh[i] : buf[i - step]  for i < tot: a newest-first history takes one entry.  GL-wide blocks,
 // back to front, so no element is overwritten before it has moved.
-__device__ __forceinline__ void shift_in(float* buf, int tot, int step, const float* fresh, int lane) {
-  for (int base = ((tot - 1) / 32) * 32; base >= 0; base -= 32) {
-    const int i = base + lane;
+template <int GL>
+__device__ __forceinline__ void shift_in(float* buf, int tot, int step, const float* fresh, int gl) {
+  for (int base = ((tot - 1) / GL) * GL; base >= 0; base -= GL) {
+    const int i = base + gl;
     const float v = (i < tot) ? (i < step ? fresh[i] : buf[i - step]) : 0.f;
     __syncwarp();
     if (i < tot) buf[i] = v;
@@ -79,22 +88,37 @@ __device__ __forceinline__ void shift_in(float* buf, int tot, int step, const fl
   }
 }
 
-template <int AGENT>
-__global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
+// GL lanes own an env (32 / GL envs per warp): the contractions of the colab-sized controllers are 10 to 60 elements
+// wide, so a whole warp per env leaves most lanes idle and the kernel issue-bound on their index arithmetic.  All
+// groups of a warp run the same trip counts (the dims are shared), so warp-wide __syncwarp / full-mask shuffles stay
+// legal; a group past the last env recomputes env N-1 and writes nothing.
+//
+// SD..SH: compile-time (d, n, p, m, F, L, h) of the shapes the reference's agents default to on the colab's system
+// (d_hidden = 10, d_action = 3, d_obs = 2); SD = 0 keeps every dim a runtime value.  With the dims known the
+// contractions unroll into LDS + FFMA with immediate offsets; the runtime-dims loops spend three integer
+// instructions per FMA on addresses and trip counts (ncu: 1660 warp-instructions per LQG step, 300 of them FFMA).
+template <int AGENT, int GL, int SD = 0, int SN = 0, int SP = 0, int SM = 0, int SF = 0, int SL = 0, int SH = 0>
+__global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 : 2)) of_kernel(const OfArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NR = 2;   // rows per lane of a mat-vec: the launcher keeps max(d, n, p) <= 2 GL (code size: the step loop must stay
+                          // inside the instruction cache -- a 64 / GL-way unroll made it 167 KB and no_instruction the top stall)
+  const int gl = threadIdx.x & (GL - 1), grp = threadIdx.x / GL;
   const DlcOfParams& P = a.p;
-  const int d = P.d, n = P.n, p = P.p, m = P.m, T = P.T;
-  const int F = P.F, L = P.L, h = P.h, FP = a.FP, J = a.J;
+  const int d = SD ? SD : P.d, n = SD ? SN : P.n, p = SD ? SP : P.p, m = SD ? SM : P.m, T = P.T;
+  const int F = SD ? SF : P.F, L = SD ? SL : P.L, h = SD ? SH : P.h;
+  const int FP = SD ? (AGENT == DLC_OF_DRC ? SM * SP : SF * SP) : a.FP;
+  const int J = SD ? (AGENT == DLC_OF_DRC ? SH : SM) : a.J;
   const bool closed = P.mode == DLC_MODE_CLOSED_LOOP;
   if (AGENT == DLC_OF_FGRC) {
     for (int i = threadIdx.x; i < a.nPhi; i += blockDim.x) smem[i] = a.Phi[i];
-    __syncthreads();  // the only CTA-wide barrier: warps are independent from here on (and may exit)
+    __syncthreads();  // the only CTA-wide barrier: warps are independent from here on
   }
-  const int64_t env = (int64_t)blockIdx.x * a.wpc + warp;
-  if (env >= P.N) return;
+  int64_t env = (int64_t)blockIdx.x * a.wpc + grp;
+  if (GL == 32 && env >= P.N) return;   // a whole warp: nobody left to shuffle with
+  const bool live = env < P.N;
+  if (!live) env = P.N - 1;
   const float* sPhi = smem;
-  float* s = smem + a.nPhi + (size_t)warp * a.S;
+  float* s = smem + a.nPhi + (size_t)grp * a.S;
   float *sA = s + a.oA, *sB = s + a.oB, *sC = s + a.oC, *sG = s + a.oG, *sK = s + a.oK, *sL = s + a.oL;
   float *sTh = s + a.oTh, *sFeat = s + a.oFeat, *sYn = s + a.oYn, *sUs = s + a.oUs;
   float *sx = s + a.oX, *sz = s + a.oZ, *sy = s + a.oY, *su = s + a.oU;
@@ -102,32 +126,32 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
 
   // ---------------------------------------------------------------- stage the env
   const size_t eD = P.shared_dynamics ? 0 : (size_t)env;
-  for (int i = lane; i < d * d; i += 32) sA[i] = a.A[eD * d * d + i];
-  for (int i = lane; i < d * n; i += 32) sB[i] = a.B[eD * d * n + i];
-  for (int i = lane; i < p * d; i += 32) sC[i] = a.C[eD * p * d + i];
-  if (closed) for (int i = lane; i < d; i += 32) sx[i] = a.x_io[(size_t)env * d + i];
+  for (int i = gl; i < d * d; i += GL) sA[i] = a.A[eD * d * d + i];
+  for (int i = gl; i < d * n; i += GL) sB[i] = a.B[eD * d * n + i];
+  for (int i = gl; i < p * d; i += GL) sC[i] = a.C[eD * p * d + i];
+  if (closed) for (int i = gl; i < d; i += GL) sx[i] = a.x_io[(size_t)env * d + i];
   if (AGENT == DLC_OF_LQG) {
-    for (int i = lane; i < n * d; i += 32) sK[i] = a.K[eD * n * d + i];
-    for (int i = lane; i < d * p; i += 32) sL[i] = a.Lk[eD * d * p + i];
-    for (int i = lane; i < d; i += 32) sz[i] = a.z_io[(size_t)env * d + i];
+    for (int i = gl; i < n * d; i += GL) sK[i] = a.K[eD * n * d + i];
+    for (int i = gl; i < d * p; i += GL) sL[i] = a.Lk[eD * d * p + i];
+    for (int i = gl; i < d; i += GL) sz[i] = a.z_io[(size_t)env * d + i];
   }
   if (AGENT == DLC_OF_DRC) {
-    for (int i = lane; i < n * p; i += 32) sK[i] = a.K ? a.K[eD * n * p + i] : 0.f;  // _drc.py:104: K defaults to 0
+    for (int i = gl; i < n * p; i += GL) sK[i] = a.K ? a.K[eD * n * p + i] : 0.f;  // _drc.py:104: K defaults to 0
     // M[j][a][q] -> sTh[a][j*p + q]
-    for (int e = lane; e < m * n * p; e += 32) {
+    for (int e = gl; e < m * n * p; e += GL) {
       const int j = e / (n * p), rem = e - j * n * p, aa = rem / p, q = rem - aa * p;
       sTh[aa * FP + j * p + q] = a.theta_io[(size_t)env * m * n * p + e];
     }
-    for (int i = lane; i < m * p; i += 32) sYn[i] = a.ynat_io[(size_t)env * m * p + i];
-    for (int i = lane; i < h * n; i += 32) sUs[i] = a.us_io[(size_t)env * h * n + i];
+    for (int i = gl; i < m * p; i += GL) sYn[i] = a.ynat_io[(size_t)env * m * p + i];
+    for (int i = gl; i < h * n; i += GL) sUs[i] = a.us_io[(size_t)env * h * n + i];
   }
   if (AGENT == DLC_OF_FGRC) {
-    for (int e = lane; e < F * n * p; e += 32) {
+    for (int e = gl; e < F * n * p; e += GL) {
       const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
       sTh[aa * FP + f * p + q] = a.theta_io[(size_t)env * F * n * p + e];
     }
-    for (int i = lane; i < (L + m) * p; i += 32) sYn[i] = a.ynat_io[(size_t)env * (L + m) * p + i];
-    for (int i = lane; i < d; i += 32) sz[i] = a.z_io[(size_t)env * d + i];
+    for (int i = gl; i < (L + m) * p; i += GL) sYn[i] = a.ynat_io[(size_t)env * (L + m) * p + i];
+    for (int i = gl; i < d; i += GL) sz[i] = a.z_io[(size_t)env * d + i];
   }
   __syncwarp();
 
@@ -135,16 +159,16 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
   if (AGENT != DLC_OF_LQG) {
     float* ab0 = sTmp;
     float* ab1 = sTmp + d * n;
-    for (int i = lane; i < d * n; i += 32) ab0[i] = sB[i];
+    for (int i = gl; i < d * n; i += GL) ab0[i] = sB[i];
     __syncwarp();
     for (int j = 0; j < J; ++j) {
-      for (int e = lane; e < p * n; e += 32) {
+      for (int e = gl; e < p * n; e += GL) {
         const int q = e / n, aa = e - q * n;
         float acc = 0.f;
         for (int c = 0; c < d; ++c) acc = fmaf(sC[q * d + c], ab0[c * n + aa], acc);
         sG[j * p * n + e] = acc;
       }
-      for (int e = lane; e < d * n; e += 32) {
+      for (int e = gl; e < d * n; e += GL) {
         const int r = e / n, aa = e - r * n;
         float acc = 0.f;
         for (int c = 0; c < d; ++c) acc = fmaf(sA[r * d + c], ab0[c * n + aa], acc);
@@ -158,7 +182,7 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
   const int M1 = m + 1, R = L + m;
   if (AGENT == DLC_OF_FGRC) {
     for (int k = 0; k < M1; ++k)
-      for (int i = lane; i < FP; i += 32) {
+      for (int i = gl; i < FP; i += GL) {
         const int f = i / p, q = i - f * p;
         float acc = 0.f;
         for (int o = 0; o < L; ++o) acc = fmaf(sPhi[f * L + o], sYn[(k + o) * p + q], acc);
@@ -175,46 +199,52 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
 
   for (int t = 0; t < T; ++t) {
     // disturbance of this step, fetched early
-    float w0 = 0.f, w1 = 0.f;
-    if (closed) {
-      if (a.W) {
-        const float* wp = a.W + ((size_t)t * P.N + env) * d;
-        if (lane < d) w0 = wp[lane];
-        if (lane + 32 < d) w1 = wp[lane + 32];
-      } else {
-        float z4[4];
-        if (lane < d) { normal4(P.seed, genv, (uint32_t)(P.t0 + t), (uint32_t)(lane >> 2), 0u, z4); w0 = __fmul_rn(P.w_std, pick4(z4, lane & 3)); }
-        if (lane + 32 < d) { normal4(P.seed, genv, (uint32_t)(P.t0 + t), (uint32_t)((lane + 32) >> 2), 0u, z4); w1 = __fmul_rn(P.w_std, pick4(z4, lane & 3)); }
+    float w[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      w[k] = 0.f;
+      const int row = gl + k * GL;
+      if (closed && k * GL < d && row < d) {
+        if (a.W) {
+          w[k] = a.W[((size_t)t * P.N + env) * d + row];
+        } else {
+          float z4[4];
+          normal4(P.seed, genv, (uint32_t)(P.t0 + t), (uint32_t)(row >> 2), 0u, z4);
+          w[k] = __fmul_rn(P.w_std, pick4(z4, row & 3));
+        }
       }
     }
     // ---- observation y = C x  (_lds.py:110), or the caller's observation (Agent.__call__ on its own)
     if (closed) {
-      float r0, r1;
-      matvec2(sC, sx, p, d, lane, r0, r1);
-      if (lane < p) sy[lane] = r0;
-      if (lane + 32 < p) sy[lane + 32] = r1;
+      float r[NR];
+      matvec<GL>(sC, sx, p, d, gl, r);
+#pragma unroll
+      for (int k = 0; k < NR; ++k)
+        if (gl + k * GL < p) sy[gl + k * GL] = r[k];
     } else {
-      for (int i = lane; i < p; i += 32) sy[i] = a.y_in[((size_t)t * P.N + env) * p + i];
+      for (int i = gl; i < p; i += GL) sy[i] = a.y_in[((size_t)t * P.N + env) * p + i];
     }
     __syncwarp();
 
     if (AGENT == DLC_OF_LQG) {
       // u = -K x_hat; residual = y - C x_hat; x_hat <- A x_hat + B u + L residual   (_lqg.py:94-97)
-      float u0, u1, c0, c1;
-      matvec2(sK, sz, n, d, lane, u0, u1);
-      matvec2(sC, sz, p, d, lane, c0, c1);
-      if (lane < n) su[lane] = -u0;
-      if (lane + 32 < n) su[lane + 32] = -u1;
-      if (lane < p) sFy[lane] = sy[lane] - c0;
-      if (lane + 32 < p) sFy[lane + 32] = sy[lane + 32] - c1;
+      float r[NR];
+      matvec<GL>(sK, sz, n, d, gl, r);
+#pragma unroll
+      for (int k = 0; k < NR; ++k)
+        if (gl + k * GL < n) su[gl + k * GL] = -r[k];
+      matvec<GL>(sC, sz, p, d, gl, r);
+#pragma unroll
+      for (int k = 0; k < NR; ++k)
+        if (gl + k * GL < p) sFy[gl + k * GL] = sy[gl + k * GL] - r[k];
       __syncwarp();
-      float a0, a1, b0, b1, l0, l1;
-      matvec2(sA, sz, d, d, lane, a0, a1);
-      matvec2(sB, su, d, n, lane, b0, b1);
-      matvec2(sL, sFy, d, p, lane, l0, l1);
+      matvec<GL>(sA, sz, d, d, gl, r);
+      matvec<GL, true>(sB, su, d, n, gl, r);
+      matvec<GL, true>(sL, sFy, d, p, gl, r);
       __syncwarp();
-      if (lane < d) sz[lane] = a0 + b0 + l0;
-      if (lane + 32 < d) sz[lane + 32] = a1 + b1 + l1;
+#pragma unroll
+      for (int k = 0; k < NR; ++k)
+        if (gl + k * GL < d) sz[gl + k * GL] = r[k];
       __syncwarp();
     }
 
@@ -223,22 +253,22 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       // gu[q] = sum_i sum_a G[i][q][a] us[i][a]     (_drc.py:169)
       for (int q = 0; q < p; ++q) {
         float part = 0.f;
-        for (int i = lane; i < h; i += 32)
+        for (int i = gl; i < h; i += GL)
           for (int aa = 0; aa < n; ++aa) part = fmaf(sG[(i * p + q) * n + aa], sUs[i * n + aa], part);
-        part = warp_sum(part);
-        if (lane == 0) sFy[q] = part;
+        part = group_sum<GL>(part);
+        if (gl == 0) sFy[q] = part;
       }
       __syncwarp();
       // y_nat: shift by one position (newest first), y_nat[0] = y - gu    (_drc.py:169-171)
-      for (int i = lane; i < p; i += 32) sTmp[i] = sy[i] - sFy[i];
+      for (int i = gl; i < p; i += GL) sTmp[i] = sy[i] - sFy[i];
       __syncwarp();
-      shift_in(sYn, m * p, p, sTmp, lane);
+      shift_in<GL>(sYn, m * p, p, sTmp, gl);
       // mdot[a] = sum_{j,q} M[j][a][q] y_nat[j][q];  u = -K y + mdot;  final = y_nat[0] + gu;  act = -K final + mdot
       for (int aa = 0; aa < n; ++aa) {
         float part = 0.f;
-        for (int i = lane; i < FP; i += 32) part = fmaf(sTh[aa * FP + i], sYn[i], part);
-        part = warp_sum(part);
-        if (lane == 0) {
+        for (int i = gl; i < FP; i += GL) part = fmaf(sTh[aa * FP + i], sYn[i], part);
+        part = group_sum<GL>(part);
+        if (gl == 0) {
           float ky = 0.f, kf = 0.f;
           for (int q = 0; q < p; ++q) {
             ky = fmaf(sK[aa * p + q], sy[q], ky);
@@ -251,19 +281,19 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       __syncwarp();
       // M <- M - lr * 2 act (x) y_nat, then the norm clip   (_drc.py:181-193)
       float nrm = 0.f;
-      for (int e = lane; e < n * FP; e += 32) {
+      for (int e = gl; e < n * FP; e += GL) {
         const int aa = fast_div(e, inv_FP), i = e - aa * FP;
         const float th = fmaf(-lr * sAct[aa], sYn[i], sTh[e]);
         sTh[e] = th;
         nrm = fmaf(th, th, nrm);
       }
-      nrm = sqrtf(warp_sum(nrm));
+      nrm = sqrtf(group_sum<GL>(nrm));
       if (nrm > P.R_M) {
         const float sc = P.R_M / nrm;
-        for (int e = lane; e < n * FP; e += 32) sTh[e] *= sc;
+        for (int e = gl; e < n * FP; e += GL) sTh[e] *= sc;
       }
       // us: shift, us[0] = u    (_drc.py:196-197)
-      shift_in(sUs, h * n, n, su, lane);
+      shift_in<GL>(sUs, h * n, n, su, gl);
     }
 
     if (AGENT == DLC_OF_FGRC) {
@@ -274,26 +304,27 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
         const float* fw = sFeat + snew * FP;
         for (int aa = 0; aa < n; ++aa) {
           float part = 0.f;
-          for (int i = lane; i < FP; i += 32) part = fmaf(sTh[aa * FP + i], fw[i], part);
-          part = warp_sum(part);
-          if (lane == 0) su[aa] = part;
+          for (int i = gl; i < FP; i += GL) part = fmaf(sTh[aa * FP + i], fw[i], part);
+          part = group_sum<GL>(part);
+          if (gl == 0) su[aa] = part;
         }
       }
       __syncwarp();
       // ---- update: z <- A z + B u; y_nat = y - C z; push    (_grc.py:139-142)
       {
-        float a0, a1, b0, b1;
-        matvec2(sA, sz, d, d, lane, a0, a1);
-        matvec2(sB, su, d, n, lane, b0, b1);
+        float rc[NR];
+        matvec<GL>(sA, sz, d, d, gl, rc);
+        matvec<GL, true>(sB, su, d, n, gl, rc);
         __syncwarp();
-        if (lane < d) sz[lane] = a0 + b0;
-        if (lane + 32 < d) sz[lane + 32] = a1 + b1;
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+          if (gl + k * GL < d) sz[gl + k * GL] = rc[k];
         __syncwarp();
-        float c0, c1;
-        matvec2(sC, sz, p, d, lane, c0, c1);
+        matvec<GL>(sC, sz, p, d, gl, rc);
         float* slot = sYn + ybase * p;   // the oldest entry is replaced by the newest
-        if (lane < p) slot[lane] = sy[lane] - c0;
-        if (lane + 32 < p) slot[lane + 32] = sy[lane + 32] - c1;
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+          if (gl + k * GL < p) slot[gl + k * GL] = sy[gl + k * GL] - rc[k];
         ybase = (ybase + 1 == R) ? 0 : ybase + 1;
       }
       __syncwarp();
@@ -301,7 +332,7 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       {
         float* fw = sFeat + fbase * FP;
         int s0 = ybase + m; if (s0 >= R) s0 -= R;
-        for (int i = lane; i < FP; i += 32) {
+        for (int i = gl; i < FP; i += GL) {
           const int f = fast_div(i, inv_p), q = i - f * p;
           const float* ph = sPhi + f * L;
           int sl = s0;
@@ -316,7 +347,7 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       }
       __syncwarp();
       // ---- a(k), k = 0..m, with the parameters before the update
-      for (int e = lane; e < M1 * n; e += 32) {
+      for (int e = gl; e < M1 * n; e += GL) {
         const int k = fast_div(e, inv_n), aa = e - k * n;
         int sl = fbase + k; if (sl >= M1) sl -= M1;
         const float* fw = sFeat + sl * FP;
@@ -329,7 +360,7 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       // ---- final_y = sum_{k<m} G[m-1-k] a(k) + y_nat(newest)     (_grc.py:100-104)
       {
         int snew = ybase + R - 1; if (snew >= R) snew -= R;
-        for (int q = lane; q < p; q += 32) {
+        for (int q = gl; q < p; q += GL) {
           float acc = sYn[snew * p + q];
           for (int k = 0; k < m; ++k) {
             const float* g = sG + ((m - 1 - k) * p + q) * n;
@@ -340,7 +371,7 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       }
       __syncwarp();
       // ---- adjoint of the actions: g(m) = 2 a(m), g(k) = G[m-1-k]^T (2 final_y)
-      for (int e = lane; e < M1 * n; e += 32) {
+      for (int e = gl; e < M1 * n; e += GL) {
         const int k = fast_div(e, inv_n), aa = e - k * n;
         float acc;
         if (k == m) {
@@ -355,7 +386,7 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
       __syncwarp();
       // ---- Theta <- proj_RM(Theta - lr * sum_k g(k) phi(k)^T)     (_grc.py:144-151)
       float nrm = 0.f;
-      for (int e = lane; e < n * FP; e += 32) {
+      for (int e = gl; e < n * FP; e += GL) {
         const int aa = fast_div(e, inv_FP), i = e - aa * FP;
         float acc = 0.f;
         int sl = fbase;
@@ -367,68 +398,70 @@ __global__ void __launch_bounds__(256, 4) of_kernel(const OfArgs a) {
         sTh[e] = th;
         nrm = fmaf(th, th, nrm);
       }
-      nrm = sqrtf(warp_sum(nrm));
+      nrm = sqrtf(group_sum<GL>(nrm));
       const float sc = fminf(1.0f, P.R_M / (nrm + 1e-8f));
       if (sc < 1.0f)
-        for (int e = lane; e < n * FP; e += 32) sTh[e] *= sc;
+        for (int e = gl; e < n * FP; e += GL) sTh[e] *= sc;
       __syncwarp();
     }
 
     // ---- realised cost quad_loss(y, u), outputs
     {
       float c = 0.f;
-      for (int i = lane; i < p; i += 32) c = fmaf(sy[i], sy[i], c);
-      for (int i = lane; i < n; i += 32) c = fmaf(su[i], su[i], c);
-      c = warp_sum(c);
-      if (lane == 0) {
-        if (a.cost_out) a.cost_out[(size_t)t * P.N + env] = c;
+      for (int i = gl; i < p; i += GL) c = fmaf(sy[i], sy[i], c);
+      for (int i = gl; i < n; i += GL) c = fmaf(su[i], su[i], c);
+      c = group_sum<GL>(c);
+      if (gl == 0) {
+        if (a.cost_out && live) a.cost_out[(size_t)t * P.N + env] = c;
         csum += (double)c;
         if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
       }
-      if (a.u_out) for (int i = lane; i < n; i += 32) a.u_out[((size_t)t * P.N + env) * n + i] = su[i];
+      if (a.u_out && live) for (int i = gl; i < n; i += GL) a.u_out[((size_t)t * P.N + env) * n + i] = su[i];
     }
     // ---- env step x <- A x + B u + w    (_lds.py:107-109)
     if (closed) {
-      float a0, a1, b0, b1;
-      matvec2(sA, sx, d, d, lane, a0, a1);
-      matvec2(sB, su, d, n, lane, b0, b1);
+      float r[NR];
+      matvec<GL>(sA, sx, d, d, gl, r);
+      matvec<GL, true>(sB, su, d, n, gl, r);
       __syncwarp();
-      if (lane < d) sx[lane] = a0 + b0 + w0;
-      if (lane + 32 < d) sx[lane + 32] = a1 + b1 + w1;
+#pragma unroll
+      for (int k = 0; k < NR; ++k)
+        if (gl + k * GL < d) sx[gl + k * GL] = r[k] + w[k];
     }
     __syncwarp();
   }
 
   // ---------------------------------------------------------------- write the state back
-  if (closed) for (int i = lane; i < d; i += 32) a.x_io[(size_t)env * d + i] = sx[i];
-  if (AGENT == DLC_OF_LQG) for (int i = lane; i < d; i += 32) a.z_io[(size_t)env * d + i] = sz[i];
+  if (!live) return;
+  if (closed) for (int i = gl; i < d; i += GL) a.x_io[(size_t)env * d + i] = sx[i];
+  if (AGENT == DLC_OF_LQG) for (int i = gl; i < d; i += GL) a.z_io[(size_t)env * d + i] = sz[i];
   if (AGENT == DLC_OF_DRC) {
-    for (int e = lane; e < m * n * p; e += 32) {
+    for (int e = gl; e < m * n * p; e += GL) {
       const int j = e / (n * p), rem = e - j * n * p, aa = rem / p, q = rem - aa * p;
       a.theta_io[(size_t)env * m * n * p + e] = sTh[aa * FP + j * p + q];
     }
-    for (int i = lane; i < m * p; i += 32) a.ynat_io[(size_t)env * m * p + i] = sYn[i];
-    for (int i = lane; i < h * n; i += 32) a.us_io[(size_t)env * h * n + i] = sUs[i];
+    for (int i = gl; i < m * p; i += GL) a.ynat_io[(size_t)env * m * p + i] = sYn[i];
+    for (int i = gl; i < h * n; i += GL) a.us_io[(size_t)env * h * n + i] = sUs[i];
   }
   if (AGENT == DLC_OF_FGRC) {
-    for (int e = lane; e < F * n * p; e += 32) {
+    for (int e = gl; e < F * n * p; e += GL) {
       const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
       a.theta_io[(size_t)env * F * n * p + e] = sTh[aa * FP + f * p + q];
     }
-    for (int i = lane; i < R * p; i += 32) {   // oldest -> newest
+    for (int i = gl; i < R * p; i += GL) {   // oldest -> newest
       const int pos = i / p, q = i - pos * p;
       int sl = ybase + pos; if (sl >= R) sl -= R;
       a.ynat_io[(size_t)env * R * p + i] = sYn[sl * p + q];
     }
-    for (int i = lane; i < d; i += 32) a.z_io[(size_t)env * d + i] = sz[i];
+    for (int i = gl; i < d; i += GL) a.z_io[(size_t)env * d + i] = sz[i];
   }
-  if (lane == 0) {
+  if (gl == 0) {
     if (a.cost_sum_out) a.cost_sum_out[env] = csum;
     if (a.status_out) a.status_out[env] = status;
   }
 }
 
-// shared-memory layout of one warp's slice; returns floats per warp
+// shared-memory layout of one env's slice; returns floats per env
 int layout(OfArgs& a) {
   const DlcOfParams& P = a.p;
   const int d = P.d, n = P.n, p = P.p, m = P.m;
@@ -505,19 +538,49 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   if (e != cudaSuccess) return cuda_status(e, "cudaGetDevice");
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t per_warp = (size_t)a.S * 4, fixed = (size_t)a.nPhi * 4;
-  if (fixed + per_warp > (size_t)max_smem)
+  // lanes per env from the widest per-step contraction (reserved = 8 / 16 / 32 overrides)
+  const int width = p->agent == DLC_OF_LQG ? p->d : (p->d > a.FP ? p->d : a.FP);
+  int GL = width <= 20 ? 8 : (width <= 48 ? 16 : 32);   // measured: GRC / DRC / LQG 8, SFC (22 wide) 16, DSC 32
+  int widest = p->d > p->n ? p->d : p->n;
+  if (p->p > widest) widest = p->p;
+  while (2 * GL < widest) GL <<= 1;   // a lane owns at most two rows of a mat-vec
+  if (p->reserved == 8 || p->reserved == 16 || p->reserved == 32) {
+    if (2 * p->reserved < widest) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved (lanes per env) must be >= max(d, n, p) / 2");
+    GL = p->reserved;
+  }
+  else if (p->reserved != 0) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved (lanes per env) must be 0, 8, 16 or 32");
+  // groups of one warp hit the same offsets of their slices at once: a slice stride of GL (mod 32) banks keeps
+  // their unit-stride accesses apart
+  if (GL < 32) a.S += ((GL - a.S % 32) + 32) % 32;
+  const size_t per_env = (size_t)a.S * 4, fixed = (size_t)a.nPhi * 4;
+  if (fixed + per_env > (size_t)max_smem)
     return fail(DLC_ERR_SHAPE, "dlc_lds_of_rollout_f32: one env's controller state does not fit in shared memory");
-  // warps per CTA: fill the SM's shared memory with as many envs as fit (at most 8 per CTA, several CTAs per SM)
-  int wpc = 8;
-  while (wpc > 1 && fixed + per_warp * wpc > (size_t)max_smem / 2) wpc >>= 1;
-  if (fixed + per_warp * wpc > (size_t)max_smem) wpc = 1;
-  a.wpc = wpc;
-  const size_t smem = fixed + per_warp * wpc;
-  auto kern = p->agent == DLC_OF_LQG ? of_kernel<DLC_OF_LQG> : (p->agent == DLC_OF_DRC ? of_kernel<DLC_OF_DRC> : of_kernel<DLC_OF_FGRC>);
+  // envs per CTA: whole warps, as many as half the SM's shared memory holds (at most 256 threads)
+  int epc = 256 / GL;
+  while (epc > 32 / GL && fixed + per_env * epc > (size_t)max_smem / 2) epc >>= 1;
+  if (fixed + per_env * epc > (size_t)max_smem) {   // not even one warp of groups: fall back to a warp per env
+    GL = 32;
+    epc = 1;
+  }
+  a.wpc = epc;
+  const size_t smem = fixed + per_env * epc;
+  void (*kern)(const OfArgs) = nullptr;
+#define OF_PICK(AG)                                                                                          \
+  if (p->agent == AG) kern = GL == 8 ? of_kernel<AG, 8> : (GL == 16 ? of_kernel<AG, 16> : of_kernel<AG, 32>);
+  OF_PICK(DLC_OF_LQG) OF_PICK(DLC_OF_DRC) OF_PICK(DLC_OF_FGRC)
+#undef OF_PICK
+  // compile-time dims for the reference's default controllers on the colab's system
+  if (p->d == 10 && p->n == 3 && p->p == 2) {
+    if (p->agent == DLC_OF_LQG && GL == 8) kern = of_kernel<DLC_OF_LQG, 8, 10, 3, 2>;
+    if (p->agent == DLC_OF_DRC && GL == 8 && p->m == 10 && p->h == 50) kern = of_kernel<DLC_OF_DRC, 8, 10, 3, 2, 10, 0, 0, 50>;
+    if (p->agent == DLC_OF_FGRC && GL == 8 && p->m == 10 && p->F == 10 && p->L == 10)       // GRC(m = 10)
+      kern = of_kernel<DLC_OF_FGRC, 8, 10, 3, 2, 10, 10, 10>;
+    if (p->agent == DLC_OF_FGRC && GL == 16 && p->m == 30 && p->F == 11 && p->L == 31)      // SFC(m = 30, h = 10)
+      kern = of_kernel<DLC_OF_FGRC, 16, 10, 3, 2, 30, 11, 31>;
+  }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(of_kernel)");
-  const unsigned grid = (unsigned)((p->N + wpc - 1) / wpc);
-  kern<<<grid, 32 * wpc, smem, (cudaStream_t)stream>>>(a);
+  const unsigned grid = (unsigned)((p->N + epc - 1) / epc);
+  kern<<<grid, GL * epc, smem, (cudaStream_t)stream>>>(a);
   return cuda_status(cudaGetLastError(), "of_kernel launch");
 }

@@ -431,8 +431,8 @@ int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p,
  * Phi[F,L] (GRC: F = L = m, Phi = I; SFC: F = h+1, L = m+1; DSC: F = 1+2h+h^2, L = 2m+1) and a y_nat history of
  * L + m entries.  Theta stacks the reference's parameter blocks in that order (M | M_0, M | M_0, M_1, M_2, M_3).
  * jit(grad(policy_loss)) is a hand adjoint; the m-step evolve recursion uses the Markov operators C A^j B.
- * One warp per env, controller state resident in shared memory: the per-env state (dlc_lds_of_smem_bytes) must fit
- * in 227 KB, d, n, p <= 64.
+ * A group of 8, 16 or 32 lanes per env (chosen from the contraction widths), controller state resident in shared
+ * memory: the per-env state (dlc_lds_of_smem_bytes) must fit in 227 KB, d, n, p <= 64.
  * ------------------------------------------------------------------------------------ */
 #define DLC_OF_LQG 0
 #define DLC_OF_DRC 1
@@ -454,7 +454,7 @@ typedef struct DlcOfParams {
   float lr;            /* GRC/SFC/DSC lr (_grc.py:52), DRC lr_scale (_drc.py:53) */
   float R_M;           /* projection radius R_M (_grc.py:49) / RM (_drc.py:55) */
   float w_std;         /* std of the in-kernel Gaussian disturbance, used when W == NULL */
-  int32_t reserved;
+  int32_t reserved;    /* 0 = choose the lanes per env automatically; 8, 16 or 32 forces it (tuning / tests) */
   uint64_t seed;
 } DlcOfParams;
 

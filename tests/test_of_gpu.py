@@ -237,3 +237,31 @@ def test_fused_rollout_through_the_mirror():
     ref = O.rollout_of(A, B, C, x0, W, "fgrc", dtype=np.float64, Theta0=st.theta.cpu().numpy(),
                        Phi=O.filter_bank("grc", m)[0], m=m)
     _check(res, ref)
+
+
+@pytest.mark.parametrize("agent", ["fgrc", "drc", "lqg"])
+def test_lane_group_widths_agree(agent):
+    """8, 16 and 32 lanes per env run the same arithmetic per element; only the order of the group reductions
+    differs, so the rollouts agree to rounding (N = 37 leaves a partly filled last warp for the narrow groups)."""
+    from deluca_b200.fused import lds_of_rollout
+    N, T, d, n, p, m = 37, 120, 10, 3, 2, 10
+    A, B, C, x0, W, rng = _sys(N, d, n, p, T, seed=3)
+    kw = dict(W=_dev(W))
+    if agent == "fgrc":
+        Phi, _ = O.filter_bank("sfc", 12, 4)
+        kw.update(agent="fgrc", Phi=_dev(Phi), m=12, R_M=10.0, lr=0.005,
+                  theta=_dev((0.2 * rng.standard_normal((N, Phi.shape[0], n, p))).astype(np.float32)))
+    elif agent == "drc":
+        kw.update(agent="drc", m=m, h=20, R_M=10.0, lr=0.005,
+                  theta=_dev((0.1 * rng.standard_normal((N, m, n, p))).astype(np.float32)),
+                  K=_dev(np.zeros((N, n, p), np.float32)))
+    else:
+        kw.update(agent="lqg", K=_dev((0.1 * rng.standard_normal((N, n, d))).astype(np.float32)),
+                  Lk=_dev((0.1 * rng.standard_normal((N, d, p))).astype(np.float32)))
+    base = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, lanes_per_env=32, **kw)
+    for lanes in (8, 16, 0):
+        r = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, lanes_per_env=lanes, **kw)
+        np.testing.assert_allclose(r.costs.cpu().numpy(), base.costs.cpu().numpy(), rtol=2e-4, atol=1e-5)
+        np.testing.assert_allclose(r.x.cpu().numpy(), base.x.cpu().numpy(), rtol=2e-4, atol=1e-5)
+    with pytest.raises(Exception):
+        lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, lanes_per_env=4, **kw)

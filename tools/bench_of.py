@@ -20,6 +20,7 @@ ap.add_argument("--T", type=int, default=500)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--cpu", type=int, default=1)
 ap.add_argument("--only", default="")
+ap.add_argument("--lanes", type=int, default=0, help="lanes per env: 0 = automatic, or 8 / 16 / 32")
 args = ap.parse_args()
 N, T = args.envs, args.T
 d, n, p = 10, 3, 2
@@ -80,18 +81,18 @@ for name, kw, (Nc, Tc) in cases:
         F, L = Phi.shape
         theta = 0.3 / F ** 0.5 * torch.randn(N, F, n, p, device=dev, generator=g)
         run = lambda: fused.lds_of_rollout(A, B, C, x0, T, agent="fgrc", W=W, Phi=Phi, theta=theta, m=kw["m"], R_M=1.0,
-                                           keep_actions=False)
+                                           keep_actions=False, lanes_per_env=args.lanes)
         fl = flops_fgrc(F, L, kw["m"])
     elif name == "drc":
         theta = 0.03 * torch.randn(N, kw["m"], n, p, device=dev, generator=g)
         K = torch.zeros(N, n, p, device=dev)
         run = lambda: fused.lds_of_rollout(A, B, C, x0, T, agent="drc", W=W, K=K, theta=theta, m=kw["m"], h=kw["h"],
-                                           lr=0.03, R_M=1000.0, keep_actions=False)
+                                           lr=0.03, R_M=1000.0, keep_actions=False, lanes_per_env=args.lanes)
         fl = flops_drc(kw["m"], kw["h"])
     else:
         K = 0.03 * torch.randn(N, n, d, device=dev, generator=g)
         Lk = 0.03 * torch.randn(N, d, p, device=dev, generator=g)
-        run = lambda: fused.lds_of_rollout(A, B, C, x0, T, agent="lqg", W=W, K=K, Lk=Lk, keep_actions=False)
+        run = lambda: fused.lds_of_rollout(A, B, C, x0, T, agent="lqg", W=W, K=K, Lk=Lk, keep_actions=False, lanes_per_env=args.lanes)
         fl = 2 * n * d + 2 * p * d + p + 2 * d * d + 2 * d * n + 2 * d * p + 2 * d + 2 * d * d + 2 * d * n + d + 2 * p * d + 2 * (p + n)
     ms, r = timed(run, args.reps)
     rate = N * T / (ms * 1e-3)

@@ -199,6 +199,42 @@ def test_bpc_matches_oracle():
         np.testing.assert_allclose(res.M.cpu().numpy(), ref["state"]["M"], rtol=1e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("d,m,H", [(10, 3, 5), (10, 3, 3), (4, 2, 2)])
+@pytest.mark.parametrize("decay,prev", [(False, False), (True, True)])
+def test_bpc_lane_split_kernel(d, m, H, decay, prev):
+    """The lane-split BPC kernel (compile-time shapes) against the float64 oracle with an explicit perturbation
+    stream, against the runtime-dims kernel with the in-kernel Philox streams, and resume == uninterrupted."""
+    from deluca_b200.fused import lds_rollout
+    rng = np.random.default_rng(d + H)
+    N, T = 41, 90          # 41: the last CTA has idle lane groups
+    A, B, K, x0, W = _problem(N, d, m, T, seed=3, dense=True)
+    M0 = (0.01 * O.unit_norm(rng.standard_normal((N, H, m, d)).astype(np.float32))).astype(np.float32)
+    eps0 = O.unit_norm(rng.standard_normal((N, H, H, m, d)).astype(np.float32))
+    eps = O.unit_norm(rng.standard_normal((T * N, H, m, d)).astype(np.float32)).reshape(T, N, H, m, d)
+    kw = dict(policy="bpc", H=H, M=_dev(M0), eps=_dev(eps0), decay=decay, lr_scale=1e-5)
+    st = O.bpc_init(N, d, m, H, M0 / 0.01, eps0, dtype=np.float64)
+    ref = O.rollout_lds(A, B, K, x0, W, "bpc", H=H, state=st, bpc_eps=eps, decay=decay, lr_scale=1e-5,
+                        dtype=np.float64)
+    res = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, W=_dev(W), eps_new=_dev(eps), **kw)
+    _check(res, ref, T)
+    kw["noise_uses_prev_action"] = prev
+    np.testing.assert_allclose(res.M.cpu().numpy(), ref["state"]["M"], rtol=1e-3, atol=1e-6)
+    # in-kernel streams (disturbances and perturbations): same draws as the runtime-dims kernel
+    a = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, seed=77, env_offset=5, traj_stride=4, **kw)
+    b = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, seed=77, env_offset=5, traj_stride=4, kernel_variant=1, **kw)
+    for f in ("costs", "x", "M", "hist", "xprev", "uprev", "eps", "bpc_cost", "X", "U"):
+        ta, tb = getattr(a, f).cpu().numpy(), getattr(b, f).cpu().numpy()
+        np.testing.assert_allclose(ta, tb, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(tb).max()), err_msg=f)
+    # resume: 2 x T/2 with the returned state is the same rollout, bit for bit
+    h = T // 2
+    r1 = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), h, seed=77, env_offset=5, **kw)
+    kw2 = dict(kw, M=r1.M, eps=r1.eps)
+    r2 = lds_rollout(_dev(A), _dev(B), _dev(K), r1.x, T - h, seed=77, env_offset=5, hist=r1.hist, xprev=r1.xprev,
+                     uprev=r1.uprev, bpc_cost=r1.bpc_cost, t0=r1.t, **kw2)
+    assert torch.equal(torch.cat([r1.costs, r2.costs]), a.costs)
+    assert torch.equal(r2.M, a.M) and torch.equal(r2.eps, a.eps) and torch.equal(r2.x, a.x)
+
+
 def test_empty_batch_and_argument_errors():
     from deluca_b200 import _abi
     from deluca_b200.fused import lds_rollout

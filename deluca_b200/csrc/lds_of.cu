@@ -577,6 +577,8 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
       kern = of_kernel<DLC_OF_FGRC, 8, 10, 3, 2, 10, 10, 10>;
     if (p->agent == DLC_OF_FGRC && GL == 16 && p->m == 30 && p->F == 11 && p->L == 31)      // SFC(m = 30, h = 10)
       kern = of_kernel<DLC_OF_FGRC, 16, 10, 3, 2, 30, 11, 31>;
+    if (p->agent == DLC_OF_FGRC && GL == 32 && p->m == 30 && p->F == 121 && p->L == 61)     // DSC(m = 30, h = 10)
+      kern = of_kernel<DLC_OF_FGRC, 32, 10, 3, 2, 30, 121, 61>;
   }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(of_kernel)");

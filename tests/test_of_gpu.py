@@ -265,3 +265,23 @@ def test_lane_group_widths_agree(agent):
         np.testing.assert_allclose(r.x.cpu().numpy(), base.x.cpu().numpy(), rtol=2e-4, atol=1e-5)
     with pytest.raises(Exception):
         lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, lanes_per_env=4, **kw)
+
+
+def test_dsc_default_shape_matches_oracle():
+    """DSC with the reference defaults (m = 30, h = 10: 121 filters of 61 taps) on the colab's system -- the
+    compile-time-dims instantiation of the 32-lane kernel.  Short and narrow: the oracle costs 0.1 s per env-step."""
+    from deluca_b200.fused import lds_of_rollout
+    N, T, d, n, p, m, h = 8, 60, 10, 3, 2, 30, 10
+    A, B, C, x0, W, rng = _sys(N, d, n, p, T, seed=11)
+    Phi, L = O.filter_bank("dsc", m, h)
+    assert Phi.shape == (121, 61)
+    Theta0 = (0.05 * rng.standard_normal((N, 121, n, p))).astype(np.float32)
+    kw = dict(lr=0.005, decay=True, R_M=0.5)
+    ref = O.rollout_of(A, B, C, x0, W, "fgrc", dtype=np.float64, Theta0=Theta0, Phi=Phi, m=m, **kw)
+    res = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, agent="fgrc", W=_dev(W), Phi=_dev(Phi),
+                         theta=_dev(Theta0), m=m, **kw)
+    _check(res, ref)
+    # the runtime-dims 32-lane kernel is never chosen for this shape any more: compare through a 16-lane launch
+    alt = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, agent="fgrc", W=_dev(W), Phi=_dev(Phi),
+                         theta=_dev(Theta0), m=m, lanes_per_env=16, **kw)
+    np.testing.assert_allclose(res.costs.cpu().numpy(), alt.costs.cpu().numpy(), rtol=2e-4, atol=1e-5)

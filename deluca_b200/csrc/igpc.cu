@@ -1384,7 +1384,9 @@ constexpr int PLAN_G = 16;
 
 __host__ __device__ inline bool plan_parallel_candidates(const DlcPlanParams& p) {
   const bool identical = p.algo == DLC_ALGO_ILQR && !p.fix_backtracking;  // SURVEY A-10: one distinct candidate
-  return p.backtracking && !identical && p.n_alpha > 1 && p.n_alpha <= PLAN_G;
+  // beyond ~64 K trajectories the thread-per-trajectory kernel already fills the machine, and 16 candidate buffers
+  // per trajectory (51 KB at d = 3, H = 200) would be the larger cost
+  return p.backtracking && !identical && p.n_alpha > 1 && p.n_alpha <= PLAN_G && p.N <= 65536;
 }
 
 template <int KIND>

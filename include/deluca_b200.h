@@ -269,7 +269,7 @@ int32_t dlc_pid_f32(int64_t N, int32_t T, float decay,
  *   dlc_plan_f32               iLQR / iGPC_closed / iLC_closed   ilqr.py:27-93, igpc.py:129-179, ilc.py:23-69
  *                              the whole outer loop incl. backtracking stays on the device; the accept
  *                              order of the reference's sequential `if cC <= c: break` is preserved.
- *                              When an iteration has 2..16 distinct candidates, a 16-lane group per
+ *                              When an iteration has 2..16 distinct candidates (and N <= 65,536), a 16-lane group per
  *                              trajectory evaluates them side by side and adopts the first accepted one
  *                              (identical results, 1 rollout of latency instead of up to n_alpha; the
  *                              workspace then holds 16 candidate buffers per trajectory).

@@ -181,3 +181,25 @@ def test_rollout_value_and_grad_matches_autograd(loss_name, use_noise):
     lo1, go1 = OG.value_and_grad(np.tile([3.0, 4.0, 0.0], (6, 1)), np.array([10., 15, 20, 25, 30, 35]), 5.0, tt)
     assert abs(float(v1) - lo1.mean()) <= 1e-4 * lo1.mean()
     np.testing.assert_allclose(g1.cpu().numpy(), go1.mean(0), rtol=2e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("sim", ["balloon", "delay"])
+def test_test_controller_score(sim):
+    """``test_controller`` (test_controller.py:23-47): PIPs as the batch of one fused launch; shared gains give the
+    reference's scalar, per-env gains one score per env."""
+    from deluca_b200.lung.controllers import PID
+    from deluca_b200.lung.envs import BalloonLung, DelayLung
+    from deluca_b200.lung.utils.scripts.test_controller import test_controller as score_fn
+    pips = [10, 15, 20, 25, 30, 35]
+    env = (BalloonLung if sim == "balloon" else DelayLung).create()
+    K = np.array([[3.0, 4.0, 0.0], [1.0, 2.0, 0.5], [0.5, 0.1, 0.0]], np.float32)
+    per_env = score_fn(PID.create(params=torch.tensor(K)), env, pips, 5.0)
+    assert per_env.shape == (3,)
+    for i in range(3):
+        ref = OL.run_controller_scan(np.repeat(K[i:i + 1], len(pips), 0), np.array(pips, np.float32), 5.0, T=29, sim=sim,
+                                     dtype=np.float32)
+        want = OL.test_controller_score(ref["timeseries"]).mean()
+        one = score_fn(PID.create(params=torch.tensor(K[i:i + 1])), env, pips, 5.0)
+        assert one.dim() == 0
+        assert abs(float(one) - want) <= 1e-4 * max(want, 1.0)
+        assert abs(float(per_env[i]) - want) <= 1e-4 * max(want, 1.0)

@@ -991,8 +991,8 @@ __global__ void __launch_bounds__(128) env_rollout_kernel(const PlanArgs a) {
 // Learner.generate_trajectories (deluca/learners/core.py:17-41): N random-policy episodes of T steps,
 // action ~ N(0, 1) per step (SimpleRandom, deluca/agents/_random.py:39-53), emitting the dataset
 // triple (obs, action, next_obs)[N,T,.].  Actions come from the library's Philox stream
-// (counter = (env, t, c/4, 2)); jax.random streams are not reproducible.
-// One thread per trajectory; each warp parks TC = 48/d steps of its 32 trajectories in shared
+// (normal number t*m + c of counter stream (env, (t*m + c) / 4, 0, 2)); jax.random streams are not reproducible.
+// One thread per trajectory; each warp parks TC = 96/d steps of its 32 trajectories in shared
 // memory and writes them out row-wise, so the [N,T,.] batch-major stores are contiguous runs of
 // TC*D floats per trajectory instead of D-float fragments.
 struct CollectArgs {
@@ -1006,13 +1006,22 @@ struct CollectArgs {
 };
 
 template <int KIND>
+struct CollectLayout {
+  static constexpr int D = Model<KIND>::D, M = Model<KIND>::M;
+  static constexpr int TC = 96 / D;                                  // 32 / 24 / 16 steps parked per trajectory
+  static constexpr int XS = ((TC + 1) * D) | 1, US = (TC * M) | 1;   // odd row strides: conflict-free columns
+  static constexpr size_t kSmemBytes = (size_t)4 * 32 * (XS + US) * sizeof(float);
+};
+
+template <int KIND>
 __global__ void __launch_bounds__(128) env_collect_kernel(const CollectArgs a) {
   using Mdl = Model<KIND>;
-  constexpr int D = Mdl::D, M = Mdl::M, TC = 48 / D;  // 16 / 12 / 8 steps parked per trajectory
-  constexpr int XS = ((TC + 1) * D) | 1, US = (TC * M) | 1;  // odd row strides: conflict-free columns
-  __shared__ float sx[4][32 * XS];
-  __shared__ float su[4][32 * US];
+  using CL = CollectLayout<KIND>;
+  constexpr int D = Mdl::D, M = Mdl::M, TC = CL::TC, XS = CL::XS, US = CL::US;
+  extern __shared__ float csm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* const sxw = csm + warp * (32 * (XS + US));
+  float* const suw = sxw + 32 * XS;
   const int64_t nw = (int64_t)blockIdx.x * blockDim.x + warp * 32;  // first trajectory of this warp
   const int64_t n = nw + lane;
   const bool live = n < a.N;
@@ -1020,21 +1029,27 @@ __global__ void __launch_bounds__(128) env_collect_kernel(const CollectArgs a) {
   float x[D], u[M], xn[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) x[i] = live ? a.x0[n * D + i] : 0.f;
-  float* mx = sx[warp] + lane * XS;
-  float* mu = su[warp] + lane * US;
+  float* mx = sxw + lane * XS;
+  float* mu = suw + lane * US;
   const int rows = (int)min((int64_t)32, a.N - nw);
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t zblk = 0xffffffffu;   // Philox block held in z
   for (int t0 = 0; t0 < a.T; t0 += TC) {
     const int tc = min(TC, a.T - t0);
 #pragma unroll
     for (int i = 0; i < D; ++i) mx[i] = x[i];
     for (int j = 0; j < tc; ++j) {
+      // action component c of step t is normal number t*M + c of the trajectory's stream: one Philox block
+      // serves 4 / M steps
 #pragma unroll
-      for (int g = 0; g < (M + 3) / 4; ++g) {
-        float z[4];
-        normal4(a.seed, (uint32_t)(a.env_offset + n), (uint32_t)(t0 + j), (uint32_t)g, 2u, z);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (4 * g + c < M) u[4 * g + c] = __fmul_rn(a.action_std, z[c]);
+      for (int c = 0; c < M; ++c) {
+        const uint32_t f = (uint32_t)(t0 + j) * M + c;
+        if ((f >> 2) != zblk) {
+          zblk = f >> 2;
+          normal4(a.seed, (uint32_t)(a.env_offset + n), zblk, 0u, 2u, z);
+        }
+        const uint32_t k = f & 3u;
+        u[c] = __fmul_rn(a.action_std, k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3])));
       }
       env.step(x, u, xn);
 #pragma unroll
@@ -1045,8 +1060,8 @@ __global__ void __launch_bounds__(128) env_collect_kernel(const CollectArgs a) {
     __syncwarp();
     for (int r = 0; r < rows; ++r) {
       const int64_t base = (nw + r) * a.T + t0;
-      const float* rx = sx[warp] + r * XS;
-      const float* ru = su[warp] + r * US;
+      const float* rx = sxw + r * XS;
+      const float* ru = suw + r * US;
       for (int q = lane; q < tc * D; q += 32) {
         a.obs[base * D + q] = rx[q];
         a.next_obs[base * D + q] = rx[q + D];
@@ -1506,7 +1521,15 @@ extern "C" int32_t dlc_env_collect_f32(const DlcEnvSpec* env, int64_t N, int32_t
   a.env = *env; a.N = N; a.env_offset = env_offset; a.T = T; a.seed = seed; a.action_std = action_std;
   a.x0 = x0; a.obs = obs_out; a.act = action_out; a.next_obs = next_obs_out;
   const unsigned grid = (unsigned)((N + 127) / 128);
-  DLC_DISPATCH_ENV(env->kind, env_collect_kernel, grid, (cudaStream_t)stream, a);
+#define COLLECT(KIND_)                                                                                          \
+  if (env->kind == KIND_) {                                                                                     \
+    cudaError_t e = cudaFuncSetAttribute(env_collect_kernel<KIND_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)CollectLayout<KIND_>::kSmemBytes);                                \
+    if (e != cudaSuccess) return cuda_status(e, "env_collect_kernel smem opt-in");                              \
+    env_collect_kernel<KIND_><<<grid, 128, CollectLayout<KIND_>::kSmemBytes, (cudaStream_t)stream>>>(a);        \
+  }
+  COLLECT(DLC_ENV_PENDULUM) COLLECT(DLC_ENV_CARTPOLE) COLLECT(DLC_ENV_QUADROTOR) COLLECT(DLC_ENV_REACHER)
+#undef COLLECT
   return cuda_status(cudaGetLastError(), "env_collect_kernel launch");
 }
 

@@ -500,7 +500,8 @@ int32_t dlc_lds_of_rollout_f32(
  *   dlc_env_collect_f32  Learner.generate_trajectories  deluca/learners/core.py:17-41
  *       N random-policy episodes (SimpleRandom: action ~ N(0,1)*action_std, deluca/agents/_random.py:39-53)
  *       of T steps on a classic env; writes obs[N,T,d], action[N,T,m], next_obs[N,T,d].
- *       Actions: Philox counter (env_offset + n, t, c/4, 2) with key = seed.
+ *       Actions: component c of step t is normal number f = t*m + c of the trajectory's stream, i.e. element f % 4 of
+ *       the Philox block with counter (env_offset + n, f / 4, 0, 2) and key = seed.
  * ------------------------------------------------------------------------------------ */
 int32_t dlc_gae_f32(int64_t N, int32_t T, int32_t time_major,
                     const float* losses, const float* values,

@@ -34,22 +34,22 @@ def ac_tail(losses, log_probs, values, done_masks, gamma, lambda_, returns_use_v
 
 
 def random_actions(seed, env_ids, T, m, std=1.0):
-    """Actions of the collect kernel: Philox counter (env, t, c // 4, 2) -> [N, T, m] float32."""
+    """Actions of the collect kernel -> [N, T, m] float32: component c of step t is normal number f = t*m + c of
+    the trajectory's stream, element f % 4 of the Philox block with counter (env, f // 4, 0, 2)."""
     env_ids = np.asarray(env_ids, dtype=np.uint32)
     N = env_ids.shape[0]
-    ngrp = (m + 3) // 4
-    ctr = np.zeros((N, T, ngrp, 4), dtype=np.uint32)
-    ctr[..., 0] = env_ids[:, None, None]
-    ctr[..., 1] = np.arange(T, dtype=np.uint32)[None, :, None]
-    ctr[..., 2] = np.arange(ngrp, dtype=np.uint32)[None, None, :]
+    nblk = (T * m + 3) // 4
+    ctr = np.zeros((N, nblk, 4), dtype=np.uint32)
+    ctr[..., 0] = env_ids[:, None]
+    ctr[..., 1] = np.arange(nblk, dtype=np.uint32)[None, :]
     ctr[..., 3] = 2
-    key = np.zeros((N, T, ngrp, 2), dtype=np.uint32)
+    key = np.zeros((N, nblk, 2), dtype=np.uint32)
     key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
     key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
     r = philox.philox4x32(ctr, key)
     z0, z1 = philox.box_muller_f32(r[..., 0], r[..., 1])
     z2, z3 = philox.box_muller_f32(r[..., 2], r[..., 3])
-    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(N, T, ngrp * 4)[..., :m]
+    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(N, nblk * 4)[:, :T * m].reshape(N, T, m)
     return (np.float32(std) * z).astype(np.float32)
 
 

@@ -23,7 +23,7 @@ def _series(N, T, seed, masks=True):
     return f(), f(), f(), mk   # losses, values, log_probs, masks
 
 
-@pytest.mark.parametrize("N,T", [(1, 1), (3, 29), (257, 32), (300, 33), (1000, 100), (513, 1000)])
+@pytest.mark.parametrize("N,T", [(1, 1), (3, 29), (100, 29), (64, 7), (257, 32), (300, 33), (70, 130), (40, 200), (17, 64), (1000, 100), (513, 1000)])
 @pytest.mark.parametrize("masks", [False, True])
 def test_gae_batch_major_bit_exact(N, T, masks):
     from deluca_b200 import fused

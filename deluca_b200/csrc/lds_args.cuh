@@ -21,5 +21,6 @@ bool launch_gpc_f2(const LdsArgs& a, cudaStream_t st, int32_t* rc);
 
 // lane-split BPC kernel for compile-time shapes (lds_bpc.cu).  Returns false if (d,m,H) has no instantiation.
 bool launch_bpc(const LdsArgs& a, float* bpc_cost_io, cudaStream_t st, int32_t* rc);
+bool bpc_supported(const DlcLdsParams& p);
 
 }  // namespace dlc

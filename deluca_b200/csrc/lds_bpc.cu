@@ -331,17 +331,26 @@ int32_t launch_bpc_shape(const LdsArgs& a, float* cost_io, cudaStream_t st) {
 }  // namespace
 
 // BPC on the compile-time shapes: (d, m, H) = (10, 3, 5) the reference default, (10, 3, 3), and a small one for tests.
+#define DLC_BPC_SHAPES(X) X(10, 3, 5, 4, 64) X(10, 3, 3, 4, 128) X(4, 2, 2, 2, 64)
+
+bool bpc_supported(const DlcLdsParams& p) {
+  if (p.policy != DLC_POLICY_BPC || p.mode != DLC_MODE_CLOSED_LOOP || p.kernel_variant == 1) return false;
+#define X(D_, M_, H_, L_, TPB_) \
+  if (p.d == D_ && p.m == M_ && p.H == H_) return true;
+  DLC_BPC_SHAPES(X)
+#undef X
+  return false;
+}
+
 bool launch_bpc(const LdsArgs& a, float* cost_io, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
-  if (p.policy != DLC_POLICY_BPC || p.mode != DLC_MODE_CLOSED_LOOP || p.kernel_variant == 1) return false;
+  if (!bpc_supported(p)) return false;
 #define X(D_, M_, H_, L_, TPB_)                                      \
   if (p.d == D_ && p.m == M_ && p.H == H_) {                         \
     *rc = launch_bpc_shape<D_, M_, H_, L_, TPB_>(a, cost_io, st);    \
     return true;                                                     \
   }
-  X(10, 3, 5, 4, 64)
-  X(10, 3, 3, 4, 128)
-  X(4, 2, 2, 2, 64)
+  DLC_BPC_SHAPES(X)
 #undef X
   return false;
 }

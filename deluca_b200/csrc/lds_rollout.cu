@@ -493,10 +493,64 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
 }
 
 // ------------------------------------------------------------------------------------------
-// runtime-dims kernel: one thread per env, state updated in place in the caller's env-major
-// buffers, small vectors in a [element][env] workspace.
+// runtime-dims kernel: one thread per env; every per-env array (A, B, K, x, M, the histories, the BPC ring) is staged
+// into an [element][env] workspace copy by tiled transposes before the rollout and back after it, next to the
+// scratch vectors, so that the 32 envs of a warp always touch 32 adjacent floats.
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline int generic_ws_floats_per_env(int d, int m) { return 6 * d + 6 * m; }
+
+// Per-env arrays of the runtime-dims kernel, element i of env n at base[i * stride]: stride = N for the staged
+// [element][env] copies (a warp's 32 envs read 32 adjacent floats), 1 for dynamics shared by all envs.
+struct Col {
+  float* p;
+  int64_t s;
+  __device__ __forceinline__ float& operator[](int i) const { return p[(int64_t)i * s]; }
+  __device__ __forceinline__ Col operator+(int off) const { return Col{p + (int64_t)off * s, s}; }
+};
+
+// where each per-env array lives in the workspace, in floats per env after the scratch vectors
+struct GenericStage {
+  int oA, oB, oK, oX, oM, oH, oXP, oE, total;
+};
+__host__ __device__ inline GenericStage generic_stage(const DlcLdsParams& p) {
+  const bool gpc = p.policy == DLC_POLICY_GPC, bpc = p.policy == DLC_POLICY_BPC;
+  const int d = p.d, m = p.m, P = gpc ? p.H + p.HH : p.H, HMD = p.H * m * d;
+  GenericStage g;
+  int o = generic_ws_floats_per_env(d, m) + 1;
+  auto take = [&](int cnt) { const int at = o; o += cnt; return at; };
+  g.oA = take(p.shared_dynamics ? 0 : d * d);
+  g.oB = take(p.shared_dynamics ? 0 : d * m);
+  g.oK = take(p.shared_dynamics ? 0 : m * d);
+  g.oX = take(d);
+  g.oM = take((gpc || bpc) ? HMD : 0);
+  g.oH = take((gpc || bpc) ? P * d : 0);
+  g.oXP = take((gpc || bpc) ? d : 0);
+  g.oE = take(bpc ? p.H * HMD : 0);
+  g.total = o;
+  return g;
+}
+
+// src[N][S] (env-major, the caller's layout) <-> dst[S][N] (element-major) through a 32 x 33 shared tile
+__global__ void __launch_bounds__(256) stage_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int64_t N, int S, int to_cols) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t n0 = (int64_t)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  if (to_cols) {   // read rows of src (contiguous in s), write rows of dst (contiguous in n)
+    for (int r = ty; r < 32; r += 8)
+      if (n0 + r < N && s0 + tx < S) tile[r][tx] = src[(n0 + r) * S + s0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+      if (s0 + r < S && n0 + tx < N) dst[(int64_t)(s0 + r) * N + n0 + tx] = tile[tx][r];
+  } else {         // dst is the caller's [N][S], src the staged [S][N]
+    for (int r = ty; r < 32; r += 8)
+      if (s0 + r < S && n0 + tx < N) tile[r][tx] = src[(int64_t)(s0 + r) * N + n0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+      if (n0 + r < N && s0 + tx < S) dst[(n0 + r) * S + s0 + tx] = tile[tx][r];
+  }
+}
 
 __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
   const DlcLdsParams& p = a.p;
@@ -506,19 +560,20 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
   const bool gpc = p.policy == DLC_POLICY_GPC, bpc = p.policy == DLC_POLICY_BPC;
   const bool open_loop = p.policy == DLC_POLICY_OPEN, agent_only = p.mode == DLC_MODE_AGENT_ONLY;
   const int P = gpc ? p.H + p.HH : p.H;  // history length (_gpc.py:98 / _bpc.py:82)
-  const int64_t np = p.shared_dynamics ? 0 : n;
-  const float* A = a.A + np * d * d;
-  const float* B = a.B + np * d * m;
-  const float* K = a.K + np * m * d;
-  float* x = a.x_io + n * d;
-  float* Mv = (gpc || bpc) ? a.M_io + n * (int64_t)H * m * d : nullptr;
-  float* hist = (gpc || bpc) ? a.hist_io + n * (int64_t)P * d : nullptr;
-  float* xprev = (gpc || bpc) ? a.xprev_io + n * d : nullptr;
-  float* eps = bpc ? a.eps_io + n * (int64_t)H * H * m * d : nullptr;
-  const int HMD = H * m * d;
-  // workspace vectors, element e at ws[(off + e) * N + n]
+  // every per-env array is read from its staged [element][env] copy (dlc_lds_rollout_f32 transposes the caller's
+  // env-major buffers in and out): with the env-major originals each lane of a warp walked its own row and every
+  // load or store touched 32 cache lines
   const int64_t N = p.N;
+  const GenericStage sg = generic_stage(p);
   float* ws = a.ws + n;
+  auto staged = [&](int off) { return Col{ws + (int64_t)off * N, N}; };
+  const Col A = p.shared_dynamics ? Col{const_cast<float*>(a.A), 1} : staged(sg.oA);
+  const Col B = p.shared_dynamics ? Col{const_cast<float*>(a.B), 1} : staged(sg.oB);
+  const Col K = p.shared_dynamics ? Col{const_cast<float*>(a.K), 1} : staged(sg.oK);   // unused for DLC_POLICY_OPEN
+  const Col x = staged(sg.oX);
+  const Col Mv = staged(sg.oM), hist = staged(sg.oH), xprev = staged(sg.oXP), eps = staged(sg.oE);
+  const int HMD = H * m * d;
+  // scratch vectors, element e at ws[(off + e) * N + n]
   auto V = [&](int off, int e) -> float& { return ws[(int64_t)(off + e) * N]; };
   const int oU = 0, oUN = m, oV = 2 * m, oMW = 3 * m, oLU = 4 * m, oDU = 5 * m;
   const int oY = 6 * m, oYN = oY + d, oLAM = oYN + d, oLN = oLAM + d, oW = oLN + d, oNZ = oW + d;
@@ -635,7 +690,7 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
         Mv[k] -= lr * (prev_cost * s);
       }
       for (int k = 0; k < (H - 1) * HMD; ++k) eps[k] = eps[k + HMD];
-      float* en = eps + (H - 1) * HMD;
+      const Col en = eps + (H - 1) * HMD;
       if (a.eps_new) {
         const float* src = a.eps_new + ((int64_t)t * p.N + n) * HMD;
         for (int k = 0; k < HMD; ++k) en[k] = src[k];
@@ -796,6 +851,18 @@ static int32_t launch_gpc(const LdsArgs& a, cudaStream_t st) {
   X(4, 1, 3, 2, 1)          \
   X(4, 2, 5, 7, 1)
 
+// does a compile-time-shape kernel take this call?  (mirrors try_split without launching)
+static bool split_supported(const DlcLdsParams& p) {
+  if (p.kernel_variant == 1 || p.policy == DLC_POLICY_BPC || p.policy == DLC_POLICY_OPEN ||
+      p.mode != DLC_MODE_CLOSED_LOOP)
+    return false;
+#define X(D_, M_, H_, HH_, L_) \
+  if (p.d == D_ && p.m == M_ && (p.policy == DLC_POLICY_LQR || (p.H == H_ && p.HH == HH_))) return true;
+  DLC_SPLIT_SHAPES(X)
+#undef X
+  return false;
+}
+
 static bool try_split(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
   if (p.kernel_variant == 1 || p.policy == DLC_POLICY_BPC || p.policy == DLC_POLICY_OPEN ||
@@ -827,7 +894,9 @@ using namespace dlc;
 
 extern "C" size_t dlc_lds_workspace_bytes(const DlcLdsParams* p) {
   if (!p || p->N <= 0 || p->d <= 0 || p->m <= 0) return 0;
-  return (size_t)(generic_ws_floats_per_env(p->d, p->m) + 1) * (size_t)p->N * sizeof(float);
+  if (split_supported(*p) || bpc_supported(*p)) return 0;   // the compile-time-shape kernels need no workspace
+  // runtime-dims kernel: scratch vectors plus an [element][env] copy of every per-env array
+  return (size_t)generic_stage(*p).total * (size_t)p->N * sizeof(float);
 }
 
 extern "C" int32_t dlc_gaussian_disturbance_f32(float* W, int64_t N, int32_t T, int32_t d,
@@ -891,10 +960,35 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
                                    "dlc_lds_workspace_bytes() of workspace");
   const unsigned grid = (unsigned)((p->N + 127) / 128);
   const int oNZ = 6 * p->m + 5 * p->d;
-  if (p->policy == DLC_POLICY_BPC)
-    bpc_cost_stage_kernel<<<grid, 128, 0, st>>>(a.ws, bpc_cost_io, p->N, oNZ, 1);
-  lds_generic_kernel<<<grid, 128, 0, st>>>(a);
-  if (p->policy == DLC_POLICY_BPC)
-    bpc_cost_stage_kernel<<<grid, 128, 0, st>>>(a.ws, bpc_cost_io, p->N, oNZ, 0);
+  const GenericStage sg = generic_stage(*p);
+  const int P = p->policy == DLC_POLICY_GPC ? p->H + p->HH : p->H, HMD = p->H * p->m * p->d;
+  auto stage = [&](const float* env_major, int off, int S, int to_cols) {   // [N][S] <-> ws[(off + s) * N + n]
+    if (!env_major || S <= 0) return;
+    const dim3 g((unsigned)((p->N + 31) / 32), (unsigned)((S + 31) / 32));
+    float* cols = a.ws + (size_t)off * p->N;
+    if (to_cols) stage_transpose_kernel<<<g, 256, 0, st>>>(env_major, cols, p->N, S, 1);
+    else stage_transpose_kernel<<<g, 256, 0, st>>>(cols, const_cast<float*>(env_major), p->N, S, 0);
+  };
+  for (int dir = 1; dir >= 0; --dir) {   // 1: stage in, run; 0: stage the updated state back out
+    if (dir == 1 && !p->shared_dynamics) {
+      stage(A, sg.oA, p->d * p->d, 1);
+      stage(B, sg.oB, p->d * p->m, 1);
+      stage(K, sg.oK, p->m * p->d, 1);
+    }
+    stage(x_io, sg.oX, p->d, dir);
+    if (learn) {
+      stage(M_io, sg.oM, HMD, dir);
+      stage(hist_io, sg.oH, P * p->d, dir);
+      stage(xprev_io, sg.oXP, p->d, dir);
+      if (p->policy == DLC_POLICY_BPC) stage(bpc_eps_io, sg.oE, p->H * HMD, dir);
+    }
+    if (dir == 1) {
+      if (p->policy == DLC_POLICY_BPC)
+        bpc_cost_stage_kernel<<<grid, 128, 0, st>>>(a.ws, bpc_cost_io, p->N, oNZ, 1);
+      lds_generic_kernel<<<grid, 128, 0, st>>>(a);
+      if (p->policy == DLC_POLICY_BPC)
+        bpc_cost_stage_kernel<<<grid, 128, 0, st>>>(a.ws, bpc_cost_io, p->N, oNZ, 0);
+    }
+  }
   return cuda_status(cudaGetLastError(), "lds_generic_kernel launch");
 }

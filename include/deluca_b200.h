@@ -108,6 +108,8 @@ typedef struct DlcLdsParams {
   uint64_t seed;       /* disturbance / perturbation stream seed */
 } DlcLdsParams;
 
+/* bytes of `workspace` dlc_lds_rollout_f32 needs for these params: 0 when a compile-time-shape kernel takes the call,
+ * otherwise the runtime-dims kernel's scratch vectors plus an [element][env] copy of every per-env array. */
 size_t dlc_lds_workspace_bytes(const DlcLdsParams* p);
 
 int32_t dlc_lds_rollout_f32(

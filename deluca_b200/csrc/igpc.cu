@@ -1404,10 +1404,13 @@ __host__ __device__ inline bool plan_parallel_candidates(const DlcPlanParams& p)
   return p.backtracking && !identical && p.n_alpha > 1 && p.n_alpha <= PLAN_G && p.N <= 65536;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(128, (Model<KIND>::D <= 4) ? 4 : 2) plan_par_kernel(const PlanArgs a) {
+// lanes per trajectory: 8 when the candidates fit (iGPC's 6), else 16
+__host__ __device__ inline int plan_group(const DlcPlanParams& p) { return p.n_alpha <= 8 ? 8 : PLAN_G; }
+
+template <int KIND, int G, bool PF>
+__device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
   using Mdl = Model<KIND>;
-  constexpr int D = Mdl::D, M = Mdl::M, G = PLAN_G;
+  constexpr int D = Mdl::D, M = Mdl::M;
   const DlcPlanParams& p = a.p;
   const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (n >= p.N) return;  // whole groups leave together
@@ -1426,19 +1429,25 @@ __global__ void __launch_bounds__(128, (Model<KIND>::D <= 4) ? 4 : 2) plan_par_k
   const float* x0 = a.x0 + n * D;
   const bool cand = j < p.n_alpha;
   float c = 0.f;
-  if (j == 0) c = rollout_one(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
+  if (j == 0) c = PF ? rollout_one_pf<Mdl, true>(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC)
+                     : rollout_one(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
   c = __shfl_sync(gmask, c, gshift);
   float alpha = p.alpha0;
   int status = 0;
   for (int t = 0; t < p.T; ++t) {
-    if (j == 0) status |= backward_pass(sim, p, X, U, kk, KK);
+    if (j == 0) status |= PF ? backward_pass_pf<Mdl, true>(sim, p, X, U, kk, KK) : backward_pass(sim, p, X, U, kk, KK);
     __syncwarp(gmask);
     const float alphaC = (alpha * 1.1f) * powf(1.1f, -(float)(j * j));
     float cC = 0.f;
     bool accept = false;
     if (cand) {
-      if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
-      else cC = rollout_one(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+      if (PF) {
+        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_best(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
+        else cC = rollout_one_pf<Mdl, true>(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+      } else {
+        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
+        else cC = rollout_one(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+      }
       accept = p.algo == DLC_ALGO_IGPC ? (cC < c) : (cC <= c);
     }
     const unsigned votes = (__ballot_sync(gmask, accept) >> gshift) & ((1u << G) - 1u);
@@ -1460,6 +1469,17 @@ __global__ void __launch_bounds__(128, (Model<KIND>::D <= 4) ? 4 : 2) plan_par_k
     if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
     if (a.status_out) a.status_out[n] = status;
   }
+}
+
+// 16 lanes per trajectory, lean: must stay at <= 128 registers (one wave at config 3, see above)
+template <int KIND>
+__global__ void __launch_bounds__(128, (Model<KIND>::D <= 4) ? 4 : 2) plan_par_kernel(const PlanArgs a) {
+  plan_par_body<KIND, PLAN_G, false>(a);
+}
+// 8 lanes per trajectory: half the threads, so the register ring / operand prefetch of the serial kernel fit in one wave
+template <int KIND>
+__global__ void __launch_bounds__(128, 2) plan_par8_kernel(const PlanArgs a) {
+  plan_par_body<KIND, 8, true>(a);
 }
 
 static int32_t check_plan(const DlcPlanParams* p, const char* who) {
@@ -1613,7 +1633,7 @@ extern "C" size_t dlc_plan_workspace_bytes(const DlcPlanParams* p) {
   if (!p || p->N <= 0 || p->H < 1) return 0;
   const int d = p->env_true.kind == DLC_ENV_PENDULUM ? 3 : (p->env_true.kind == DLC_ENV_CARTPOLE ? 4 : 6);
   const int m = p->env_true.kind >= DLC_ENV_QUADROTOR ? 2 : 1;
-  const size_t slots = plan_parallel_candidates(*p) ? PLAN_G : 1;  // one candidate buffer per lane of a group
+  const size_t slots = plan_parallel_candidates(*p) ? plan_group(*p) : 1;  // one candidate buffer per lane of a group
   return (size_t)p->N * slots * ((size_t)(p->H + 1) * d + (size_t)p->H * m) * sizeof(float);
 }
 
@@ -1634,8 +1654,9 @@ extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float
   a.p = *p; a.U_out = U_io; a.x0 = x0; a.X_out = X_out; a.k_out = k_out; a.K_out = K_out; a.cost_out = cost_out;
   a.alpha_out = alpha_out; a.status_out = status_out; a.ws = (float*)workspace;
   if (plan_parallel_candidates(*p)) {
-    const unsigned grid = (unsigned)((p->N * PLAN_G + 127) / 128);
-    DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);
+    const unsigned grid = (unsigned)((p->N * plan_group(*p) + 127) / 128);
+    if (plan_group(*p) == 8) DLC_DISPATCH_ENV(p->env_true.kind, plan_par8_kernel, grid, (cudaStream_t)stream, a);
+    else DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);
     return cuda_status(cudaGetLastError(), "plan_par_kernel launch");
   }
   // one-warp CTAs: a trajectory's working set is ~10 KB, so spreading the warps over all SMs (instead of four

@@ -1386,26 +1386,26 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
 }
 
 // The same outer loops with the backtracking candidates of an iteration evaluated SIDE BY SIDE: a
-// group of PLAN_G lanes owns a trajectory, lane j rolls out candidate j (alphaC = 1.1 alpha 1.1^(-j^2))
+// group of PLAN_G = 8 lanes owns a trajectory, lane j rolls out candidate j (alphaC = 1.1 alpha 1.1^(-j^2))
 // into its own workspace slot, and the group adopts the FIRST accepted candidate in the reference's
 // order -- exactly what the sequential `for alphaC in ...: if cC <= c: break` keeps (ilqr.py:55-73,
-// igpc.py:159-170, ilc.py:49-60); every candidate is the same arithmetic as in plan_kernel.  The
-// serial chain per iteration drops from (1 + tried candidates) rollouts to 2; the planning loops are
-// latency-bound with most issue slots idle, so the redundant candidates are free.
-// The group's loads of the nominal trajectory are warp broadcasts of L1-resident lines, so the
-// one-step-ahead operand prefetch of the serial kernel buys nothing here and its registers would
-// push the 512-CTA launch of config 3 (4096 trajectories) past one wave (measured: 7.6 -> 10.7 ms).
-constexpr int PLAN_G = 16;
+// igpc.py:159-170, ilc.py:49-60); every candidate is the same arithmetic as in plan_kernel.  More
+// than 8 candidates (iLQR / iLC: 10) go in rounds of 8; a later round runs only if no earlier candidate
+// passed.  The serial chain per iteration drops from (1 + tried candidates) rollouts to 2; the planning
+// loops are latency-bound with most issue slots idle, so the redundant candidates are free.
+// Eight lanes, not sixteen: 4096 trajectories x 8 lanes are 256 CTAs, one wave even at 255 registers, which is
+// what lets the candidates use the operand prefetch and the register ring of the serial kernel (a 16-lane
+// variant had to stay under 128 registers to remain one wave and was 12-50 % slower on every loop).
+constexpr int PLAN_G = 8;
 
 __host__ __device__ inline bool plan_parallel_candidates(const DlcPlanParams& p) {
   const bool identical = p.algo == DLC_ALGO_ILQR && !p.fix_backtracking;  // SURVEY A-10: one distinct candidate
   // beyond ~64 K trajectories the thread-per-trajectory kernel already fills the machine, and 16 candidate buffers
   // per trajectory (51 KB at d = 3, H = 200) would be the larger cost
-  return p.backtracking && !identical && p.n_alpha > 1 && p.n_alpha <= PLAN_G && p.N <= 65536;
+  return p.backtracking && !identical && p.n_alpha > 1 && p.n_alpha <= 2 * PLAN_G && p.N <= 65536;
 }
 
-// lanes per trajectory: 8 when the candidates fit (iGPC's 6), else 16
-__host__ __device__ inline int plan_group(const DlcPlanParams& p) { return p.n_alpha <= 8 ? 8 : PLAN_G; }
+__host__ __device__ inline int plan_group(const DlcPlanParams&) { return PLAN_G; }
 
 template <int KIND, int G, bool PF>
 __device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
@@ -1427,7 +1427,6 @@ __device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
   float* XC = a.ws + (n * G + j) * (int64_t)WS;
   float* UC = XC + (H + 1) * D;
   const float* x0 = a.x0 + n * D;
-  const bool cand = j < p.n_alpha;
   float c = 0.f;
   if (j == 0) c = PF ? rollout_one_pf<Mdl, true>(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC)
                      : rollout_one(tru, p, U, nullptr, nullptr, nullptr, 1.0f, x0, X, UC);
@@ -1437,29 +1436,35 @@ __device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
   for (int t = 0; t < p.T; ++t) {
     if (j == 0) status |= PF ? backward_pass_pf<Mdl, true>(sim, p, X, U, kk, KK) : backward_pass(sim, p, X, U, kk, KK);
     __syncwarp(gmask);
-    const float alphaC = (alpha * 1.1f) * powf(1.1f, -(float)(j * j));
-    float cC = 0.f;
-    bool accept = false;
-    if (cand) {
-      if (PF) {
-        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_best(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
-        else cC = rollout_one_pf<Mdl, true>(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
-      } else {
-        if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
-        else cC = rollout_one(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+    // candidates in rounds of G (one round unless n_alpha > G); a later round runs only if no earlier candidate passed
+    for (int base = 0; base < p.n_alpha; base += G) {
+      const int jc = base + j;
+      const float alphaC = (alpha * 1.1f) * powf(1.1f, -(float)(jc * jc));
+      float cC = 0.f;
+      bool accept = false;
+      if (jc < p.n_alpha) {
+        if (PF) {
+          if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_best(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
+          else cC = rollout_one_pf<Mdl, true>(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+        } else {
+          if (p.algo == DLC_ALGO_IGPC) cC = igpc_rollout_one(tru, sim, p, U, kk, KK, X, alphaC, x0, XC, UC);
+          else cC = rollout_one(tru, p, U, kk, KK, X, alphaC, x0, XC, UC);
+        }
+        accept = p.algo == DLC_ALGO_IGPC ? (cC < c) : (cC <= c);
       }
-      accept = p.algo == DLC_ALGO_IGPC ? (cC < c) : (cC <= c);
-    }
-    const unsigned votes = (__ballot_sync(gmask, accept) >> gshift) & ((1u << G) - 1u);
-    __syncwarp(gmask);  // every candidate buffer is complete and nobody reads X / U any more
-    if (votes) {
-      const int js = __ffs(votes) - 1;  // first accepted in the reference's order
-      const float* XS = a.ws + (n * G + js) * (int64_t)WS;
-      const float* US = XS + (H + 1) * D;
-      for (int i = j; i < (H + 1) * D; i += G) X[i] = XS[i];
-      for (int i = j; i < H * M; i += G) U[i] = US[i];
-      c = __shfl_sync(gmask, cC, gshift + js);
-      alpha = __shfl_sync(gmask, alphaC, gshift + js);
+      const unsigned votes = (__ballot_sync(gmask, accept) >> gshift) & ((1u << G) - 1u);
+      __syncwarp(gmask);  // every candidate buffer is complete and nobody reads X / U any more
+      if (votes) {
+        const int js = __ffs(votes) - 1;  // first accepted in the reference's order
+        const float* XS = a.ws + (n * G + js) * (int64_t)WS;
+        const float* US = XS + (H + 1) * D;
+        for (int i = j; i < (H + 1) * D; i += G) X[i] = XS[i];
+        for (int i = j; i < H * M; i += G) U[i] = US[i];
+        c = __shfl_sync(gmask, cC, gshift + js);
+        alpha = __shfl_sync(gmask, alphaC, gshift + js);
+        break;   // group-uniform
+      }
+      __syncwarp(gmask);
     }
     __syncwarp(gmask);
   }
@@ -1471,15 +1476,9 @@ __device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
   }
 }
 
-// 16 lanes per trajectory, lean: must stay at <= 128 registers (one wave at config 3, see above)
 template <int KIND>
-__global__ void __launch_bounds__(128, (Model<KIND>::D <= 4) ? 4 : 2) plan_par_kernel(const PlanArgs a) {
-  plan_par_body<KIND, PLAN_G, false>(a);
-}
-// 8 lanes per trajectory: half the threads, so the register ring / operand prefetch of the serial kernel fit in one wave
-template <int KIND>
-__global__ void __launch_bounds__(128, 2) plan_par8_kernel(const PlanArgs a) {
-  plan_par_body<KIND, 8, true>(a);
+__global__ void __launch_bounds__(128, 2) plan_par_kernel(const PlanArgs a) {
+  plan_par_body<KIND, PLAN_G, true>(a);
 }
 
 static int32_t check_plan(const DlcPlanParams* p, const char* who) {
@@ -1655,8 +1654,7 @@ extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float
   a.alpha_out = alpha_out; a.status_out = status_out; a.ws = (float*)workspace;
   if (plan_parallel_candidates(*p)) {
     const unsigned grid = (unsigned)((p->N * plan_group(*p) + 127) / 128);
-    if (plan_group(*p) == 8) DLC_DISPATCH_ENV(p->env_true.kind, plan_par8_kernel, grid, (cudaStream_t)stream, a);
-    else DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);
+    DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);
     return cuda_status(cudaGetLastError(), "plan_par_kernel launch");
   }
   // one-warp CTAs: a trajectory's working set is ~10 KB, so spreading the warps over all SMs (instead of four

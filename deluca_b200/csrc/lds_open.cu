@@ -1,0 +1,175 @@
+// lds_open.cu -- the LDS environment on its own, fused over T steps: given or random actions in, observations out.
+//
+//   LDS.__call__                    deluca/envs/_lds.py:102-111   w_t = disturbance(t); x <- A x + B u + w_t; y = C x; t += 1
+//   LDS.generate_random_trajectory  deluca/envs/_lds.py:117-140   u_t ~ N(0, 1) [n,1]; obs = self(u_t); keeps obs[0,0]
+//   (and the open-loop rollouts every system-identification caller builds from LDS.__call__)
+//
+// Mapping: the lane-group layout of lds_of.cu -- GL = 8 / 16 / 32 lanes own an env, A, B, C and the state stay in the
+// group's slice of shared memory for all T steps, lanes split the rows of each mat-vec.  Dims are runtime except for
+// the colab's system (d_hidden = 10, d_action = 3, d_obs = 2), which is a compile-time instantiation.
+// Streams: disturbances are Philox stream 0 (the same numbers the controller kernels draw), actions stream 3.
+#include "common.cuh"
+
+namespace dlc {
+namespace {
+
+struct OpenArgs {
+  int64_t N, env_offset;
+  int T, d, n, p, shared, t0, observe0;
+  const float *A, *B, *C, *u_in, *W;
+  float *x_io, *y_out, *u_out;
+  uint64_t seed;
+  float w_std, action_std;
+  int epc;  // envs per CTA
+  int S;    // floats of shared memory per env
+};
+
+__device__ __forceinline__ float pick4o(const float z[4], int k) { return k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3])); }
+
+// r[k] (+)= sum_c Mat[row][c] v[c] for row = gl + k GL < rows (rows <= 2 GL)
+template <int GL, bool ACC>
+__device__ __forceinline__ void open_matvec(const float* Mat, const float* v, int rows, int cols, int gl, float (&r)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (!ACC) r[k] = 0.f;
+    if (k * GL < rows) {
+      const int row = gl + k * GL;
+      if (row < rows) {
+        const float* mr = Mat + row * cols;
+        float acc = r[k];
+        for (int c = 0; c < cols; ++c) acc = fmaf(mr[c], v[c], acc);
+        r[k] = acc;
+      }
+    }
+  }
+}
+
+template <int GL, int SD, int SN, int SP>
+__global__ void __launch_bounds__(256) lds_open_kernel(const OpenArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int gl = threadIdx.x & (GL - 1), grp = threadIdx.x / GL;
+  const int d = SD ? SD : a.d, n = SD ? SN : a.n, p = SD ? SP : a.p;
+  int64_t env = (int64_t)blockIdx.x * a.epc + grp;
+  const bool live = env < a.N;
+  if (!live) env = a.N - 1;   // idle groups shadow the last env: warp-wide __syncwarp stays whole
+  float* s = smem + (size_t)grp * a.S;
+  float *sA = s, *sB = sA + d * d, *sC = sB + d * n, *sx = sC + p * d, *su = sx + d;
+  const size_t eD = a.shared ? 0 : (size_t)env;
+  for (int i = gl; i < d * d; i += GL) sA[i] = a.A[eD * d * d + i];
+  for (int i = gl; i < d * n; i += GL) sB[i] = a.B[eD * d * n + i];
+  if (a.C) for (int i = gl; i < p * d; i += GL) sC[i] = a.C[eD * p * d + i];
+  for (int i = gl; i < d; i += GL) sx[i] = a.x_io[(size_t)env * d + i];
+  __syncwarp();
+  const uint32_t genv = (uint32_t)(a.env_offset + env);
+  if (a.observe0 && a.y_out) {   // y = C x of the state as it stands (LDS.init / reset return it)
+    float r[2];
+    open_matvec<GL, false>(sC, sx, p, d, gl, r);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (live && gl + k * GL < p) a.y_out[(size_t)env * p + gl + k * GL] = r[k];
+  }
+  for (int t = 0; t < a.T; ++t) {
+    // ---- action: the caller's, or N(0, action_std^2) from stream 3
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = gl + k * GL;
+      if (k * GL < n && c < n) {
+        float u;
+        if (a.u_in) {
+          u = a.u_in[((size_t)t * a.N + env) * n + c];
+        } else {
+          float z4[4];
+          normal4(a.seed, genv, (uint32_t)(a.t0 + t), (uint32_t)(c >> 2), 3u, z4);
+          u = __fmul_rn(a.action_std, pick4o(z4, c & 3));
+        }
+        su[c] = u;
+        if (a.u_out && live) a.u_out[((size_t)t * a.N + env) * n + c] = u;
+      }
+    }
+    // ---- disturbance w_t (own rows)
+    float w[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      w[k] = 0.f;
+      const int row = gl + k * GL;
+      if (k * GL < d && row < d) {
+        if (a.W) {
+          w[k] = a.W[((size_t)t * a.N + env) * d + row];
+        } else if (a.w_std != 0.f) {
+          float z4[4];
+          normal4(a.seed, genv, (uint32_t)(a.t0 + t), (uint32_t)(row >> 2), 0u, z4);
+          w[k] = __fmul_rn(a.w_std, pick4o(z4, row & 3));
+        }
+      }
+    }
+    __syncwarp();
+    // ---- x <- A x + B u + w                                            _lds.py:107
+    float r[2];
+    open_matvec<GL, false>(sA, sx, d, d, gl, r);
+    open_matvec<GL, true>(sB, su, d, n, gl, r);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (gl + k * GL < d) sx[gl + k * GL] = r[k] + w[k];
+    __syncwarp();
+    // ---- y = C x                                                        _lds.py:108
+    if (a.y_out) {
+      open_matvec<GL, false>(sC, sx, p, d, gl, r);
+      float* yo = a.y_out + ((size_t)(t + a.observe0) * a.N + env) * p;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (live && gl + k * GL < p) yo[gl + k * GL] = r[k];
+    }
+  }
+  if (live) for (int i = gl; i < d; i += GL) a.x_io[(size_t)env * d + i] = sx[i];
+}
+
+}  // namespace
+}  // namespace dlc
+
+using namespace dlc;
+
+extern "C" int32_t dlc_lds_open_rollout_f32(int64_t N, int32_t T, int32_t d, int32_t n, int32_t p,
+                                            int32_t shared_dynamics, const float* A, const float* B, const float* C,
+                                            float* x_io, const float* u_in, const float* W, uint64_t seed,
+                                            int64_t env_offset, int32_t t0, float w_std, float action_std,
+                                            int32_t observe0, float* y_out, float* u_out, void* stream) {
+  if (N < 0 || T < 0) return fail(DLC_ERR_ARG, "dlc_lds_open_rollout_f32: negative N or T");
+  if (d < 1 || n < 1 || p < 1 || d > 64 || n > 64 || p > 64)
+    return fail(DLC_ERR_SHAPE, "dlc_lds_open_rollout_f32: d, n, p must be in 1..64");
+  if (N == 0 || (T == 0 && !observe0)) return DLC_OK;
+  if (!A || !B || !x_io) return fail(DLC_ERR_ARG, "dlc_lds_open_rollout_f32: A, B and x_io are required");
+  if (y_out && !C) return fail(DLC_ERR_ARG, "dlc_lds_open_rollout_f32: y_out needs C");
+  if ((uint64_t)(env_offset + N) > 0xFFFFFFFFull)
+    return fail(DLC_ERR_SHAPE, "dlc_lds_open_rollout_f32: env_offset + N exceeds the 32-bit stream counter");
+  OpenArgs a{};
+  a.N = N; a.env_offset = env_offset; a.T = T; a.d = d; a.n = n; a.p = p; a.shared = shared_dynamics; a.t0 = t0;
+  a.observe0 = observe0 ? 1 : 0;
+  a.A = A; a.B = B; a.C = C; a.u_in = u_in; a.W = W; a.x_io = x_io; a.y_out = y_out; a.u_out = u_out;
+  a.seed = seed; a.w_std = w_std; a.action_std = action_std;
+  int widest = d > n ? d : n;
+  if (p > widest) widest = p;
+  const int GL = widest <= 16 ? 8 : (widest <= 32 ? 16 : 32);
+  int S = d * d + d * n + p * d + d + n;
+  S = (S + 3) & ~3;
+  if (GL < 32) S += ((GL - S % 32) + 32) % 32;   // slices of one warp's groups on different banks
+  a.S = S;
+  int dev = 0, max_smem = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_status(e, "cudaGetDevice");
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int epc = 256 / GL;
+  while (epc > 32 / GL && (size_t)S * 4 * epc > (size_t)max_smem / 4) epc >>= 1;
+  a.epc = epc;
+  const size_t smem = (size_t)S * 4 * epc;
+  if (smem > (size_t)max_smem) return fail(DLC_ERR_SHAPE, "dlc_lds_open_rollout_f32: system does not fit shared memory");
+  void (*kern)(const OpenArgs) = GL == 8 ? lds_open_kernel<8, 0, 0, 0> : (GL == 16 ? lds_open_kernel<16, 0, 0, 0>
+                                                                                   : lds_open_kernel<32, 0, 0, 0>);
+  if (d == 10 && n == 3 && p == 2) kern = lds_open_kernel<8, 10, 3, 2>;
+  if (d == 10 && n == 3 && p == 10) kern = lds_open_kernel<8, 10, 3, 10>;   // state feedback: C = I
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_open_kernel)");
+  const unsigned grid = (unsigned)((N + epc - 1) / epc);
+  kern<<<grid, GL * epc, smem, (cudaStream_t)stream>>>(a);
+  return cuda_status(cudaGetLastError(), "lds_open_kernel launch");
+}

@@ -5,7 +5,7 @@ Two faces, as in the reference:
     ``y = env(u)`` mutates ``env.x`` / ``env.t`` (``_lds.py:58-111``);
   * functional pytree, what ``apg_rollout`` x ``vmap`` needs: ``state = env.reset(N)``,
     ``state, obs = env.step(state, u)`` with ``LDSState(x[N,d], t)`` (SURVEY A-1).
-Every state update is computed by ``dlc_lds_rollout_f32`` (open-loop policy, T = 1).  Disturbances
+Every state update and observation is computed by ``dlc_lds_open_rollout_f32`` (T = 1 for a single call).  Disturbances
 come from the library's counter-based Gaussian stream (Threefry is not reproducible without JAX,
 SURVEY a3); ``key`` is the integer stream seed.
 """
@@ -96,26 +96,53 @@ class LDS(Env):
         st.freeze()
         return st, self.observe(st)
 
+    def _abc(self, N):
+        """A, B, C with one batching convention for the kernel: all shared, or all per env."""
+        mats = (self.A, self.B, self.C)
+        if all(m.dim() == 2 for m in mats) or all(m.dim() == 3 for m in mats):
+            return mats
+        return tuple(m if m.dim() == 3 else m.unsqueeze(0).expand(N, *m.shape).contiguous() for m in mats)
+
+    def _w(self, t0, T, key, N, dev):
+        """None when the kernel draws the Gaussian stream itself, else the materialised W[T,N,d]."""
+        std = self.disturbance.std()
+        if std is None or std == 0.0:
+            return torch.stack([self.disturbance(t0 + t, key, N=N, device=dev).reshape(N, self.d)
+                                for t in range(T)]).contiguous() if T > 0 else None
+        return None
+
     def observe(self, state):
-        """y = C x (``_lds.py:108``)."""
-        if self.C.dim() == 2:
-            return state.x @ self.C.T
-        return torch.einsum("npd,nd->np", self.C, state.x)
+        """y = C x (``_lds.py:108``), through the kernel (T = 0, observe-only)."""
+        _, y, _ = fused.lds_open_rollout(*self._abc(state.x.shape[0]), state.x, 0, observe0=True)
+        return y[0]
 
     def step(self, state, u, key=None, env_offset=0):
-        """``Env.__call__(state, action)``: x <- A x + B u + w_t, t <- t + 1 (``_lds.py:102-111``)."""
+        """``Env.__call__(state, action)``: x <- A x + B u + w_t, y = C x, t <- t + 1 (``_lds.py:102-111``)."""
         N = state.x.shape[0]
-        u = torch.as_tensor(u, dtype=torch.float32, device=state.x.device).reshape(N, self.n).contiguous()
+        u = torch.as_tensor(u, dtype=torch.float32, device=state.x.device).reshape(1, N, self.n).contiguous()
         key = self.key if key is None else int(key)
-        std = self.disturbance.std()
-        W = None
-        if std is None or std == 0.0:   # not the Gaussian stream: materialise this step's w_t
-            W = self.disturbance(state.t, key, N=N, device=state.x.device).reshape(1, N, self.d).contiguous()
-        r = fused.lds_rollout(self.A, self.B, None, state.x, 1, policy="open", u_in=u.reshape(1, N, self.n), W=W,
-                              w_std=std or 0.0, seed=key, t0=state.t, env_offset=env_offset, keep_costs=False)
-        st = LDSState(x=r.x, t=state.t + 1)
+        x, y, _ = fused.lds_open_rollout(*self._abc(N), state.x, 1, u_in=u,
+                                         W=self._w(state.t, 1, key, N, state.x.device),
+                                         w_std=self.disturbance.std() or 0.0, seed=key, t0=state.t,
+                                         env_offset=env_offset)
+        st = LDSState(x=x, t=state.t + 1)
         st.freeze()
-        return st, self.observe(st)
+        return st, y[0]
+
+    def rollout(self, state, T, actions=None, key=None, env_offset=0, action_std=1.0, keep_actions=False):
+        """T fused steps of ``step``: the given ``actions[T,N,n]`` or, when None, the N(0, 1) random policy of
+        ``generate_random_trajectory`` (``_lds.py:117-140``).  Returns (state, Y[T,N,p], U[T,N,n] or None)."""
+        N = state.x.shape[0]
+        key = self.key if key is None else int(key)
+        if actions is not None:
+            actions = torch.as_tensor(actions, dtype=torch.float32, device=state.x.device).reshape(T, N, self.n).contiguous()
+        x, Y, U = fused.lds_open_rollout(*self._abc(N), state.x, T, u_in=actions,
+                                         W=self._w(state.t, T, key, N, state.x.device),
+                                         w_std=self.disturbance.std() or 0.0, seed=key, t0=state.t,
+                                         env_offset=env_offset, action_std=action_std, keep_actions=keep_actions)
+        st = LDSState(x=x, t=state.t + T)
+        st.freeze()
+        return st, Y, U
 
     # ---- stateful face (the reference's)
     def __call__(self, u, key=None):
@@ -128,3 +155,17 @@ class LDS(Env):
     @property
     def action_size(self) -> int:
         return self.n
+
+    def generate_random_trajectory(self, trajectory_length=1000, key=None):
+        """``generate_random_trajectory`` (``_lds.py:117-140``): ``trajectory_length`` steps under N(0, 1) actions,
+        one fused launch; returns the first coordinate of every observation [T] and advances ``self.x`` / ``self.t``
+        like the reference's loop of ``self(rand_action, subkey)`` calls."""
+        st = LDSState(x=self.x.reshape(1, self.d).contiguous(), t=self.t)
+        st, Y, _ = self.rollout(st, int(trajectory_length), key=0 if key is None else key)
+        self.x = st.x.reshape(self.d, 1)
+        self.t = st.t
+        return Y[:, 0, 0]
+
+    def show_me_the_signal(self, length=1000, key=None):
+        """``show_me_the_signal`` (``_lds.py:142-145``) without the plot (matplotlib is not part of this image)."""
+        return self.generate_random_trajectory(length, key)

@@ -486,3 +486,31 @@ def env_collect(env, x0, T, seed=0, env_offset=0, action_std=1.0):
                     float(action_std), _abi.ptr(x0), _abi.ptr(obs), _abi.ptr(act), _abi.ptr(nxt))
     _abi.check(rc, "dlc_env_collect_f32")
     return obs, act, nxt
+
+
+def lds_open_rollout(A, B, C, x, T, *, u_in=None, W=None, seed=0, env_offset=0, t0=0, w_std=0.5, action_std=1.0,
+                     observe0=False, keep_actions=False, want_obs=True, donate=False):
+    """``dlc_lds_open_rollout_f32``: T steps of ``LDS.__call__`` (``deluca/envs/_lds.py:102-111``) for N envs under
+    the given actions ``u_in[T,N,n]`` or, when None, N(0, action_std^2) actions (``generate_random_trajectory``,
+    ``:117-140``).  Returns (x_final[N,d], y[T (+1 with observe0),N,p] or None, u[T,N,n] or None)."""
+    _f32(x, "x")
+    N, d = x.shape
+    shared = A.dim() == 2
+    n = B.shape[-1]
+    lead = () if shared else (N,)
+    _f32(A, "A", lead + (d, d)); _f32(B, "B", lead + (d, n))
+    p = 1
+    if C is not None:
+        p = C.shape[-2]
+        _f32(C, "C", lead + (p, d))
+    elif want_obs:
+        raise ValueError("observations need C")
+    _f32(u_in, "u_in", (T, N, n)); _f32(W, "W", (T, N, d))
+    x_io = x if donate else x.clone()
+    y = torch.empty(T + int(bool(observe0)), N, p, device=x.device) if want_obs else None
+    u = torch.empty(T, N, n, device=x.device) if keep_actions else None
+    rc = _launch_on(x, _abi.lib().dlc_lds_open_rollout_f32, N, int(T), d, n, p, int(shared), _abi.ptr(A), _abi.ptr(B),
+                    _abi.ptr(C), _abi.ptr(x_io), _abi.ptr(u_in), _abi.ptr(W), int(seed), int(env_offset), int(t0),
+                    float(w_std), float(action_std), int(bool(observe0)), _abi.ptr(y), _abi.ptr(u))
+    _abi.check(rc, "dlc_lds_open_rollout_f32")
+    return x_io, y, u

@@ -485,6 +485,25 @@ int32_t dlc_lds_of_rollout_f32(
     void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * The LDS environment on its own for T steps: given or random actions in, observations out.
+ *     LDS.__call__                    deluca/envs/_lds.py:102-111   w_t = disturbance(t); x <- A x + B u_t + w_t; y_t = C x
+ *     LDS.generate_random_trajectory  deluca/envs/_lds.py:117-140   u_t ~ N(0,1) [n,1], y_t = self(u_t)
+ *   u_in == NULL: u_t = action_std * z with z from Philox stream 3, counter (env_offset + n, t0 + t, c/4, 3).
+ *   W == NULL: Gaussian disturbance of std w_std from stream 0 (the numbers the controller kernels draw); w_std = 0
+ *   gives ZeroDisturbance; any other disturbance (SinusDisturbance) is passed as W[T,N,d].
+ *   observe0 = 1 additionally writes y = C x of the entry state into y_out[0] (what LDS.init / reset return); the
+ *   steps then write y_out[1 + t].  y_out is [T + observe0, N, p].
+ *   A[d,d] B[d,n] C[p,d] shared (shared_dynamics = 1) or per env [N,...]; d, n, p <= 64.
+ * ------------------------------------------------------------------------------------ */
+int32_t dlc_lds_open_rollout_f32(int64_t N, int32_t T, int32_t d, int32_t n, int32_t p, int32_t shared_dynamics,
+                                 const float* A, const float* B, const float* C /* or NULL if y_out is NULL */,
+                                 float* x_io /*[N,d]*/, const float* u_in /*[T,N,n] or NULL*/,
+                                 const float* W /*[T,N,d] or NULL*/, uint64_t seed, int64_t env_offset, int32_t t0,
+                                 float w_std, float action_std, int32_t observe0,
+                                 float* y_out /*[T+observe0,N,p] or NULL*/, float* u_out /*[T,N,n] or NULL*/,
+                                 void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Experience collection around the rollout.
  *
  *   dlc_gae_f32          gae_advantages                 deluca/training/ppo.py:44-84

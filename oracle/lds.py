@@ -232,3 +232,40 @@ def rollout_lds(A, B, K, x0, W, policy="gpc", H=3, HH=10, lr_scale=0.005, decay=
         if keep_x:
             X[t + 1] = x
     return dict(costs=costs, X=X, x_final=x, state=state)
+
+
+def random_actions_stream3(seed, env_ids, t0, T, n, std=1.0):
+    """Actions of dlc_lds_open_rollout_f32 when none are given: U[T,N,n] = std * z with z the normals of the
+    Philox counter (env, t0 + t, c // 4, 3) -- stream 3 (disturbances are stream 0)."""
+    from . import philox
+    env_ids = np.asarray(env_ids, dtype=np.uint32)
+    N = env_ids.shape[0]
+    ngrp = (n + 3) // 4
+    ctr = np.zeros((T, N, ngrp, 4), dtype=np.uint32)
+    ctr[..., 0] = env_ids[None, :, None]
+    ctr[..., 1] = (np.arange(T, dtype=np.uint64) + np.uint64(t0)).astype(np.uint32)[:, None, None]
+    ctr[..., 2] = np.arange(ngrp, dtype=np.uint32)[None, None, :]
+    ctr[..., 3] = 3
+    key = np.zeros((T, N, ngrp, 2), dtype=np.uint32)
+    key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
+    key[..., 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    r = philox.philox4x32(ctr, key)
+    z0, z1 = philox.box_muller_f32(r[..., 0], r[..., 1])
+    z2, z3 = philox.box_muller_f32(r[..., 2], r[..., 3])
+    z = np.stack([z0, z1, z2, z3], axis=-1).reshape(T, N, ngrp * 4)[..., :n]
+    return (np.float32(std) * z).astype(np.float32)
+
+
+def open_rollout(A, B, C, x0, U, W, dtype=np.float64):
+    """``LDS.__call__`` T times (``deluca/envs/_lds.py:102-111``) for N envs: x <- A x + B u_t + w_t, y_t = C x.
+    A[N,d,d] B[N,d,n] C[N,p,d] (or unbatched), U[T,N,n], W[T,N,d] -> (Y[T,N,p], x_final[N,d])."""
+    A, B, C = (np.asarray(v, dtype=dtype) for v in (A, B, C))
+    bat = A.ndim == 3
+    x = np.asarray(x0, dtype=dtype).copy()
+    T = U.shape[0]
+    Y = np.empty((T, x.shape[0], C.shape[-2]), dtype=dtype)
+    mv = (lambda Mx, v: np.einsum("nij,nj->ni", Mx, v)) if bat else (lambda Mx, v: v @ Mx.T)
+    for t in range(T):
+        x = mv(A, x) + mv(B, U[t].astype(dtype)) + W[t].astype(dtype)                   # :107
+        Y[t] = mv(C, x)                                                                  # :108
+    return Y, x

@@ -149,6 +149,8 @@ SYMBOLS = {
     "dlc_lds_open_rollout_f32": (ctypes.c_int32, [ctypes.c_int64] + [ctypes.c_int32] * 5 + [_P] * 6
                                  + [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_int32, _P, _P, _P]),
+    "dlc_sinus_disturbance_f32": (ctypes.c_int32, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P,
+                                                   ctypes.c_float, ctypes.c_int32, _P]),
     "dlc_gae_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_int32, _P, _P, _P]),
     "dlc_env_collect_f32": (ctypes.c_int32, [ctypes.POINTER(DlcEnvSpec), ctypes.c_int64, ctypes.c_int32,

@@ -124,10 +124,33 @@ __global__ void __launch_bounds__(256) lds_open_kernel(const OpenArgs a) {
   if (live) for (int i = gl; i < d; i += GL) a.x_io[(size_t)env * d + i] = sx[i];
 }
 
+// SinusDisturbance.__call__ (deluca/envs/_lds.py:44-52): w_t[i] = sin(t * phases[i]) * amplitude, the same for every env
+__global__ void __launch_bounds__(256) sinus_disturbance_kernel(float* __restrict__ W, int64_t N, int T, int d,
+                                                                const float* __restrict__ phases, float amplitude,
+                                                                int t0) {
+  const int64_t total = (int64_t)T * N * d;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % d);
+    const int t = (int)(idx / ((int64_t)N * d));
+    W[idx] = __fmul_rn(sinf(__fmul_rn((float)(t0 + t), phases[i])), amplitude);
+  }
+}
+
 }  // namespace
 }  // namespace dlc
 
 using namespace dlc;
+
+extern "C" int32_t dlc_sinus_disturbance_f32(float* W, int64_t N, int32_t T, int32_t d, const float* phases,
+                                             float amplitude, int32_t t0, void* stream) {
+  if (!W || !phases || N < 0 || T < 0 || d <= 0) return fail(DLC_ERR_ARG, "dlc_sinus_disturbance_f32: bad argument");
+  if (N == 0 || T == 0) return DLC_OK;
+  const int64_t total = (int64_t)T * N * d;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  sinus_disturbance_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, N, T, d, phases, amplitude, t0);
+  return cuda_status(cudaGetLastError(), "sinus_disturbance_kernel launch");
+}
 
 extern "C" int32_t dlc_lds_open_rollout_f32(int64_t N, int32_t T, int32_t d, int32_t n, int32_t p,
                                             int32_t shared_dynamics, const float* A, const float* B, const float* C,

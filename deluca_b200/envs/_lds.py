@@ -57,7 +57,11 @@ class SinusDisturbance(Disturbance):
         return None
 
     def __call__(self, t, key, N=1, device="cuda"):
-        return (torch.sin(float(t) * self.phases) * self.amplitude).expand(N, self.d).contiguous()
+        return self.series(t, 1, N)[0]
+
+    def series(self, t0, T, N):
+        """W[T,N,d] for steps t0 .. t0+T-1 in one launch of ``dlc_sinus_disturbance_f32``."""
+        return fused.sinus_disturbance(N, T, self.phases.contiguous(), self.amplitude, t0=int(t0))
 
 
 class LDSState(Obj):
@@ -107,8 +111,12 @@ class LDS(Env):
         """None when the kernel draws the Gaussian stream itself, else the materialised W[T,N,d]."""
         std = self.disturbance.std()
         if std is None or std == 0.0:
+            if T <= 0:
+                return None
+            if hasattr(self.disturbance, "series"):
+                return self.disturbance.series(t0, T, N)
             return torch.stack([self.disturbance(t0 + t, key, N=N, device=dev).reshape(N, self.d)
-                                for t in range(T)]).contiguous() if T > 0 else None
+                                for t in range(T)]).contiguous()
         return None
 
     def observe(self, state):

@@ -37,6 +37,17 @@ def gaussian_disturbance(N, T, d, seed, env_offset=0, t0=0, std=0.5, device="cud
     return W
 
 
+def sinus_disturbance(N, T, phases, amplitude=0.5, t0=0):
+    """W[T,N,d] = sin((t0 + t) * phases) * amplitude (``SinusDisturbance``, ``deluca/envs/_lds.py:44-52``)."""
+    _f32(phases, "phases")
+    d = phases.numel()
+    W = torch.empty((T, N, d), dtype=torch.float32, device=phases.device)
+    rc = _launch_on(phases, _abi.lib().dlc_sinus_disturbance_f32, _abi.ptr(W), N, int(T), d, _abi.ptr(phases),
+                    float(amplitude), int(t0))
+    _abi.check(rc, "dlc_sinus_disturbance_f32")
+    return W
+
+
 class LdsRolloutResult(dict):
     __getattr__ = dict.__getitem__
 

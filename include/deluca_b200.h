@@ -66,6 +66,12 @@ int32_t dlc_gaussian_disturbance_f32(float* W /*[T,N,d]*/, int64_t N, int32_t T,
                                      uint64_t seed, int64_t env_offset, int32_t t0, float std,
                                      void* stream);
 
+/* SinusDisturbance.__call__ (deluca/envs/_lds.py:44-52): W[t, n, i] = sin((t0 + t) * phases[i]) * amplitude for every
+ * env n (the reference's phases ~ N(0,1) under PRNGKey(0); here the caller passes them, the mirror draws them from the
+ * library stream with seed 0).  float32: the product t * phase and the sine are each rounded once. */
+int32_t dlc_sinus_disturbance_f32(float* W /*[T,N,d]*/, int64_t N, int32_t T, int32_t d, const float* phases /*[d]*/,
+                                  float amplitude, int32_t t0, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * LDS environment driven by LQR / GPC / BPC for T steps, fused.
  *

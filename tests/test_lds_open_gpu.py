@@ -126,3 +126,23 @@ def test_argument_errors():
         lds_open_rollout(z(2, 4, 4).cpu(), z(2, 4, 1), z(2, 1, 4), z(2, 4), 3)
     x, y, _ = lds_open_rollout(z(0, 4, 4), z(0, 4, 1), z(0, 1, 4), z(0, 4), 3)
     assert y.shape == (3, 0, 1)
+
+
+def test_sinus_disturbance_kernel():
+    """SinusDisturbance (_lds.py:44-52): sin(t * phases) * amplitude in float32, one launch for a whole series."""
+    from deluca_b200.envs import SinusDisturbance
+    from deluca_b200.fused import sinus_disturbance
+    rng = np.random.default_rng(0)
+    ph = rng.standard_normal(10).astype(np.float32)
+    T, N, t0 = 300, 5, 9000          # large t: the argument reduction of sinf matters
+    W = sinus_disturbance(N, T, _dev(ph), 0.5, t0=t0).cpu().numpy()
+    t = (np.arange(T) + t0).astype(np.float32)[:, None]
+    want = (np.sin((t * ph[None, :]).astype(np.float32).astype(np.float64)) * 0.5).astype(np.float32)
+    assert W.shape == (T, N, 10)
+    np.testing.assert_allclose(W, np.broadcast_to(want[:, None, :], W.shape), rtol=0, atol=2e-7)
+    dist = SinusDisturbance()
+    dist.init(10)
+    assert dist.phases.shape == (10,)
+    one = dist(7, 0, N=3)
+    ser = dist.series(5, 4, 3)
+    assert one.shape == (3, 10) and torch.equal(ser[2], one)

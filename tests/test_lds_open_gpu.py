@@ -146,3 +146,19 @@ def test_sinus_disturbance_kernel():
     one = dist(7, 0, N=3)
     ser = dist.series(5, 4, 3)
     assert one.shape == (3, 10) and torch.equal(ser[2], one)
+
+
+def test_learner_generate_trajectories_on_lds():
+    """Learner.generate_trajectories (learners/core.py:17-41) with the LDS env: (obs, action, next_obs)[N,T,.]."""
+    from deluca_b200.envs import LDS
+    from deluca_b200.learners import Learner
+    env = LDS()
+    env.init(3, 10, 2, key=1)
+    N, T = 33, 40
+    obs, act, nxt = Learner(env).generate_trajectories(N, T, key=4)
+    assert obs.shape == (N, T, 2) and act.shape == (N, T, 3) and nxt.shape == (N, T, 2)
+    assert torch.equal(obs[:, 1:], nxt[:, :-1]) and float(obs[:, 0].abs().max()) == 0.0   # x0 = 0
+    W = philox.gaussian_disturbance(4, np.arange(N), 0, T, 10)
+    Y, _ = O.open_rollout(env.A.cpu().numpy(), env.B.cpu().numpy(), env.C.cpu().numpy(), np.zeros((N, 10), np.float32),
+                          act.transpose(0, 1).cpu().numpy(), W)
+    _close(nxt.transpose(0, 1).cpu().numpy(), Y)

@@ -101,6 +101,7 @@ class FilterAgent(Agent):
         N = st.theta.shape[0]
         y = torch.as_tensor(obs, dtype=torch.float32, device=st.theta.device).reshape(1, N, self.p).contiguous()
         r = fused.lds_of_rollout(self.A, self.B, self.C, None, 1, agent="fgrc", y_in=y, Phi=self.Phi, theta=st.theta,
+                                 phi_is_identity=self.kind == "grc",
                                  z=st.z, ynat=st.ynat_history, m=self.m, t0=st.t, lr=self.lr, decay=self.decay,
                                  R_M=self.R_M, agent_only=True, keep_costs=False)
         new = OFState(theta=r.theta, z=r.z, ynat_history=r.ynat, t=st.t + 1)
@@ -111,6 +112,7 @@ class FilterAgent(Agent):
         """T fused closed-loop steps on the LDS this agent was built for (the scan x vmap body)."""
         st = st or self.init(x.shape[0])
         return fused.lds_of_rollout(self.A, self.B, self.C, x, T, agent="fgrc", W=W, Phi=self.Phi, theta=st.theta,
+                                    phi_is_identity=self.kind == "grc",
                                     z=st.z, ynat=st.ynat_history, m=self.m, t0=st.t, lr=self.lr, decay=self.decay,
                                     R_M=self.R_M, **kw)
 

@@ -461,6 +461,418 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 
   }
 }
 
+// LQG on a small compile-time system, one THREAD per env with A, B, C, K, L and both states in registers
+// (200 + 20 floats at d = 10, n = 3, p = 2): a step is 355 FFMA with no shared memory and no warp synchronisation.
+// Same arithmetic per element as of_kernel<LQG> (row sums accumulated in the same order).
+template <int D, int NA, int P>
+__global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
+  const DlcOfParams& Pm = a.p;
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= Pm.N) return;
+  const bool closed = Pm.mode == DLC_MODE_CLOSED_LOOP;
+  const size_t eD = Pm.shared_dynamics ? 0 : (size_t)env;
+  float A[D][D], B[D][NA], C[P][D], K[NA][D], L[D][P], x[D], z[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = __ldg(a.A + eD * D * D + i * D + j);
+#pragma unroll
+    for (int c = 0; c < NA; ++c) B[i][c] = __ldg(a.B + eD * D * NA + i * NA + c);
+#pragma unroll
+    for (int q = 0; q < P; ++q) L[i][q] = __ldg(a.Lk + eD * D * P + i * P + q);
+    x[i] = closed ? a.x_io[(size_t)env * D + i] : 0.f;
+    z[i] = a.z_io[(size_t)env * D + i];
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+#pragma unroll
+    for (int j = 0; j < D; ++j) C[q][j] = __ldg(a.C + eD * P * D + q * D + j);
+#pragma unroll
+  for (int c = 0; c < NA; ++c)
+#pragma unroll
+    for (int j = 0; j < D; ++j) K[c][j] = __ldg(a.K + eD * NA * D + c * D + j);
+  const uint32_t genv = (uint32_t)(Pm.env_offset + env);
+  double csum = 0.0;
+  int status = 0;
+  for (int t = 0; t < Pm.T; ++t) {
+    // disturbance of this step, fetched early
+    float w[D];
+    if (closed) {
+      if (a.W) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = __ldg(a.W + ((size_t)t * Pm.N + env) * D + i);
+      } else {
+#pragma unroll
+        for (int g = 0; g < (D + 3) / 4; ++g) {
+          float z4[4];
+          normal4(Pm.seed, genv, (uint32_t)(Pm.t0 + t), (uint32_t)g, 0u, z4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
+        }
+      }
+    }
+    // y = C x (_lds.py:110), or the caller's observation
+    float y[P], u[NA], res[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      if (closed) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(C[q][j], x[j], s);
+        y[q] = s;
+      } else {
+        y[q] = a.y_in[((size_t)t * Pm.N + env) * P + q];
+      }
+    }
+    // u = -K x_hat; residual = y - C x_hat; x_hat <- A x_hat + B u + L residual   (_lqg.py:94-97)
+#pragma unroll
+    for (int c = 0; c < NA; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(K[c][j], z[j], s);
+      u[c] = -s;
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(C[q][j], z[j], s);
+      res[q] = y[q] - s;
+    }
+    float zn[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(A[i][j], z[j], s);
+#pragma unroll
+      for (int c = 0; c < NA; ++c) s = fmaf(B[i][c], u[c], s);
+#pragma unroll
+      for (int q = 0; q < P; ++q) s = fmaf(L[i][q], res[q], s);
+      zn[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = zn[i];
+    // realised cost quad_loss(y, u), outputs
+    float c = 0.f;
+#pragma unroll
+    for (int q = 0; q < P; ++q) c = fmaf(y[q], y[q], c);
+#pragma unroll
+    for (int k = 0; k < NA; ++k) c = fmaf(u[k], u[k], c);
+    if (a.cost_out) a.cost_out[(size_t)t * Pm.N + env] = c;
+    csum += (double)c;
+    if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
+    if (a.u_out)
+#pragma unroll
+      for (int k = 0; k < NA; ++k) a.u_out[((size_t)t * Pm.N + env) * NA + k] = u[k];
+    // env step x <- A x + B u + w    (_lds.py:107-109)
+    if (closed) {
+      float xn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(A[i][j], x[j], s);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s = fmaf(B[i][k], u[k], s);
+        xn[i] = s + w[i];
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = xn[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if (closed) a.x_io[(size_t)env * D + i] = x[i];
+    a.z_io[(size_t)env * D + i] = z[i];
+  }
+  if (a.cost_sum_out) a.cost_sum_out[env] = csum;
+  if (a.status_out) a.status_out[env] = status;
+}
+
+// GRC (identity filter bank: F = L = m) on a small compile-time system, one THREAD per env.  Theta, A and both states
+// live in registers; B, C, the Markov operators, the y_nat ring and the m+1 counterfactual actions live in shared
+// memory as [element][thread] (bank = thread).  With Phi = I the filtered window k IS the y_nat window starting at
+// slot k, so there is no feature ring; the y_nat ring is a mirrored linear buffer (every entry stored at slots s and
+// s + R), so a window is L*p consecutive floats at a register base + immediate offsets.  A step is ~1,900 FFMA and
+// ~600 LDS with no warp synchronisation.  The gradient is accumulated straight into Theta, candidate by candidate
+// (Theta is only read by the actions, which are all formed before), instead of into a separate sum.
+template <int D, int NA, int P, int MH>
+struct GrcRegLayout {
+  static constexpr int R = 2 * MH, FP = MH * P, M1 = MH + 1;
+  static constexpr int oRing = 0, oAct = oRing + 2 * R * P, oG = oAct + M1 * NA, oB = oG + MH * P * NA,
+                       oC = oB + D * NA, kFloats = oC + P * D;
+};
+
+template <int D, int NA, int P, int MH, int TPB>
+__global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
+  using Lay = GrcRegLayout<D, NA, P, MH>;
+  constexpr int R = Lay::R, FP = Lay::FP, M1 = Lay::M1;
+  extern __shared__ __align__(16) float smem[];
+  const DlcOfParams& Pm = a.p;
+  const int64_t env_raw = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  if (env_raw >= Pm.N) return;   // no warp-level communication: idle threads may leave
+  const int64_t env = env_raw;
+  float* const sm = smem + threadIdx.x;
+  auto S = [&](int off) -> float& { return sm[off * TPB]; };
+  const bool closed = Pm.mode == DLC_MODE_CLOSED_LOOP;
+  const size_t eD = Pm.shared_dynamics ? 0 : (size_t)env;
+  float A[D][D], Th[NA][FP], x[D], z[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = __ldg(a.A + eD * D * D + i * D + j);
+#pragma unroll
+    for (int c = 0; c < NA; ++c) S(Lay::oB + i * NA + c) = __ldg(a.B + eD * D * NA + i * NA + c);
+    x[i] = closed ? a.x_io[(size_t)env * D + i] : 0.f;
+    z[i] = a.z_io[(size_t)env * D + i];
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+#pragma unroll
+    for (int j = 0; j < D; ++j) S(Lay::oC + q * D + j) = __ldg(a.C + eD * P * D + q * D + j);
+  // Theta[f][aa][q] -> Th[aa][f*P + q]
+#pragma unroll
+  for (int f = 0; f < MH; ++f)
+#pragma unroll
+    for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+      for (int q = 0; q < P; ++q) Th[aa][f * P + q] = a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P + q];
+  // y_nat ring, oldest -> newest, mirrored
+  for (int i = 0; i < R * P; ++i) {
+    const float v = a.ynat_io[(size_t)env * R * P + i];
+    S(Lay::oRing + i) = v;
+    S(Lay::oRing + R * P + i) = v;
+  }
+  // Markov operators G[j][q][aa] = (C A^j B)[q][aa], j < m            (_grc.py:97-105 collapsed, see the file header)
+  {
+    float ab[D][NA];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int c = 0; c < NA; ++c) ab[i][c] = S(Lay::oB + i * NA + c);
+    for (int j = 0; j < MH; ++j) {
+#pragma unroll
+      for (int q = 0; q < P; ++q)
+#pragma unroll
+        for (int c = 0; c < NA; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc = fmaf(S(Lay::oC + q * D + k), ab[k][c], acc);
+          S(Lay::oG + (j * P + q) * NA + c) = acc;
+        }
+      float nb[D][NA];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < NA; ++c) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc = fmaf(A[i][k], ab[k][c], acc);
+          nb[i][c] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < NA; ++c) ab[i][c] = nb[i][c];
+    }
+  }
+  int ybase = 0;   // physical slot of the oldest entry
+  const uint32_t genv = (uint32_t)(Pm.env_offset + env);
+  double csum = 0.0;
+  int status = 0;
+  {   // the caller promised Phi == I (reserved = 1); a broken promise must not pass silently
+    bool ident = true;
+    for (int i = 0; i < MH * MH; ++i) ident = ident && (__ldg(a.Phi + i) == ((i / MH == i % MH) ? 1.0f : 0.0f));
+    if (!ident) {
+      if (a.cost_sum_out) a.cost_sum_out[env] = (double)nanf("");
+      if (a.status_out) a.status_out[env] = DLC_STATUS_BAD_HINT;
+      return;
+    }
+  }
+
+  for (int t = 0; t < Pm.T; ++t) {
+    float w[D];
+    if (closed) {
+      if (a.W) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = __ldg(a.W + ((size_t)t * Pm.N + env) * D + i);
+      } else {
+#pragma unroll
+        for (int g = 0; g < (D + 3) / 4; ++g) {
+          float z4[4];
+          normal4(Pm.seed, genv, (uint32_t)(Pm.t0 + t), (uint32_t)g, 0u, z4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
+        }
+      }
+    }
+    const float lr = Pm.decay ? Pm.lr / (float)(Pm.t0 + t + 1) : Pm.lr;  // _grc.py:145
+    float y[P], u[NA];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      if (closed) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(S(Lay::oC + q * D + j), x[j], s);
+        y[q] = s;
+      } else {
+        y[q] = a.y_in[((size_t)t * Pm.N + env) * P + q];
+      }
+    }
+    // ---- get_action: the newest window of the history as it stands (_grc.py:157-169)
+    {
+      const float* win = sm + (Lay::oRing + (ybase + MH) * P) * TPB;
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) u[aa] = 0.f;
+#pragma unroll
+      for (int i = 0; i < FP; ++i) {
+        const float v = win[i * TPB];
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa) u[aa] = fmaf(Th[aa][i], v, u[aa]);
+      }
+    }
+    // ---- update: z <- A z + B u; y_nat = y - C z; push (the oldest slot and its mirror take it)   (_grc.py:139-142)
+    {
+      float zn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(A[i][j], z[j], s);
+#pragma unroll
+        for (int c = 0; c < NA; ++c) s = fmaf(S(Lay::oB + i * NA + c), u[c], s);
+        zn[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) z[i] = zn[i];
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(S(Lay::oC + q * D + j), z[j], s);
+        const float yn = y[q] - s;
+        sm[(Lay::oRing + ybase * P + q) * TPB] = yn;
+        sm[(Lay::oRing + (ybase + R) * P + q) * TPB] = yn;
+      }
+      ybase = (ybase + 1 == R) ? 0 : ybase + 1;
+    }
+    const float* ring = sm + (Lay::oRing + ybase * P) * TPB;   // logical slot s, component q at ring[(s*P + q) * TPB]
+    // ---- a(k), k = 0..m, with the parameters before the update
+#pragma unroll 1
+    for (int k = 0; k < M1; ++k) {
+      const float* win = ring + k * P * TPB;
+      float acc[NA];
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) acc[aa] = 0.f;
+#pragma unroll
+      for (int i = 0; i < FP; ++i) {
+        const float v = win[i * TPB];
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa) acc[aa] = fmaf(Th[aa][i], v, acc[aa]);
+      }
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) S(Lay::oAct + k * NA + aa) = acc[aa];
+    }
+    // ---- final_y = sum_{k<m} G[m-1-k] a(k) + y_nat(newest); fy = 2 final_y     (_grc.py:100-104)
+    float fy[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) fy[q] = ring[((R - 1) * P + q) * TPB];
+#pragma unroll 1
+    for (int k = 0; k < MH; ++k) {
+#pragma unroll
+      for (int q = 0; q < P; ++q)
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa)
+          fy[q] = fmaf(S(Lay::oG + ((MH - 1 - k) * P + q) * NA + aa), S(Lay::oAct + k * NA + aa), fy[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) fy[q] *= 2.f;
+    // ---- Theta <- Theta - lr * sum_k g(k) phi(k)^T, g(m) = 2 a(m), g(k) = G[m-1-k]^T fy      (_grc.py:144-151)
+#pragma unroll 1
+    for (int k = 0; k < M1; ++k) {
+      float g[NA];
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) {
+        if (k == MH) {
+          g[aa] = 2.f * S(Lay::oAct + k * NA + aa);
+        } else {
+          float s = 0.f;
+#pragma unroll
+          for (int q = 0; q < P; ++q) s = fmaf(S(Lay::oG + ((MH - 1 - k) * P + q) * NA + aa), fy[q], s);
+          g[aa] = s;
+        }
+        g[aa] *= -lr;
+      }
+      const float* win = ring + k * P * TPB;
+#pragma unroll
+      for (int i = 0; i < FP; ++i) {
+        const float v = win[i * TPB];
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa) Th[aa][i] = fmaf(g[aa], v, Th[aa][i]);
+      }
+    }
+    {
+      float nrm = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+        for (int i = 0; i < FP; ++i) nrm = fmaf(Th[aa][i], Th[aa][i], nrm);
+      const float sc = fminf(1.0f, Pm.R_M / (sqrtf(nrm) + 1e-8f));
+      if (sc < 1.0f) {
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+          for (int i = 0; i < FP; ++i) Th[aa][i] *= sc;
+      }
+    }
+    // ---- realised cost quad_loss(y, u), outputs
+    float c = 0.f;
+#pragma unroll
+    for (int q = 0; q < P; ++q) c = fmaf(y[q], y[q], c);
+#pragma unroll
+    for (int k = 0; k < NA; ++k) c = fmaf(u[k], u[k], c);
+    if (a.cost_out) a.cost_out[(size_t)t * Pm.N + env] = c;
+    csum += (double)c;
+    if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
+    if (a.u_out)
+#pragma unroll
+      for (int k = 0; k < NA; ++k) a.u_out[((size_t)t * Pm.N + env) * NA + k] = u[k];
+    // ---- env step x <- A x + B u + w    (_lds.py:107-109)
+    if (closed) {
+      float xn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) s = fmaf(A[i][j], x[j], s);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s = fmaf(S(Lay::oB + i * NA + k), u[k], s);
+        xn[i] = s + w[i];
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) x[i] = xn[i];
+    }
+  }
+  // ---- write the state back
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if (closed) a.x_io[(size_t)env * D + i] = x[i];
+    a.z_io[(size_t)env * D + i] = z[i];
+  }
+#pragma unroll
+  for (int f = 0; f < MH; ++f)
+#pragma unroll
+    for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+      for (int q = 0; q < P; ++q) a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P + q] = Th[aa][f * P + q];
+  for (int i = 0; i < R * P; ++i) a.ynat_io[(size_t)env * R * P + i] = sm[(Lay::oRing + ybase * P + i) * TPB];
+  if (a.cost_sum_out) a.cost_sum_out[env] = csum;
+  if (a.status_out) a.status_out[env] = status;
+}
+
 // shared-memory layout of one env's slice; returns floats per env
 int layout(OfArgs& a) {
   const DlcOfParams& P = a.p;
@@ -538,17 +950,33 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   if (e != cudaSuccess) return cuda_status(e, "cudaGetDevice");
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (p->agent == DLC_OF_LQG && p->d == 10 && p->n == 3 && p->p == 2 && p->reserved == 0) {
+    // the colab's system: register-resident thread-per-env kernel (reserved = 8 / 16 / 32 still forces lane groups)
+    of_lqg_reg_kernel<10, 3, 2><<<(unsigned)((p->N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    return cuda_status(cudaGetLastError(), "of_lqg_reg_kernel launch");
+  }
+  if (p->agent == DLC_OF_FGRC && p->d == 10 && p->n == 3 && p->p == 2 && p->m == 10 && p->F == 10 && p->L == 10 &&
+      p->reserved == 1) {
+    // GRC(m = 10) on the colab's system: register-resident thread-per-env kernel
+    constexpr int TPB = 64;
+    const size_t smem = (size_t)GrcRegLayout<10, 3, 2, 10>::kFloats * TPB * sizeof(float);
+    auto kern = of_grc_reg_kernel<10, 3, 2, 10, TPB>;
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) return cuda_status(e2, "cudaFuncSetAttribute(of_grc_reg_kernel)");
+    kern<<<(unsigned)((p->N + TPB - 1) / TPB), TPB, smem, (cudaStream_t)stream>>>(a);
+    return cuda_status(cudaGetLastError(), "of_grc_reg_kernel launch");
+  }
   // lanes per env from the widest per-step contraction (reserved = 8 / 16 / 32 overrides)
   const int width = p->agent == DLC_OF_LQG ? p->d : (p->d > a.FP ? p->d : a.FP);
   int GL = width <= 20 ? 8 : (width <= 48 ? 16 : 32);   // measured: GRC / DRC / LQG 8, SFC (22 wide) 16, DSC 32
   int widest = p->d > p->n ? p->d : p->n;
   if (p->p > widest) widest = p->p;
   while (2 * GL < widest) GL <<= 1;   // a lane owns at most two rows of a mat-vec
-  if (p->reserved == 8 || p->reserved == 16 || p->reserved == 32) {
+  if (p->reserved == 8 || p->reserved == 16 || p->reserved == 32) {  // (1 = identity hint: lanes stay automatic)
     if (2 * p->reserved < widest) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved (lanes per env) must be >= max(d, n, p) / 2");
     GL = p->reserved;
   }
-  else if (p->reserved != 0) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved (lanes per env) must be 0, 8, 16 or 32");
+  else if (p->reserved != 0 && p->reserved != 1) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved must be 0, 1 (Phi is the identity), 8, 16 or 32 (lanes per env)");
   // groups of one warp hit the same offsets of their slices at once: a slice stride of GL (mod 32) banks keeps
   // their unit-stride accesses apart
   if (GL < 32) a.S += ((GL - a.S % 32) + 32) % 32;

@@ -4,9 +4,9 @@
 //   LDS.generate_random_trajectory  deluca/envs/_lds.py:117-140   u_t ~ N(0, 1) [n,1]; obs = self(u_t); keeps obs[0,0]
 //   (and the open-loop rollouts every system-identification caller builds from LDS.__call__)
 //
-// Mapping: the lane-group layout of lds_of.cu -- GL = 8 / 16 / 32 lanes own an env, A, B, C and the state stay in the
-// group's slice of shared memory for all T steps, lanes split the rows of each mat-vec.  Dims are runtime except for
-// the colab's system (d_hidden = 10, d_action = 3, d_obs = 2), which is a compile-time instantiation.
+// Mapping: for any (d, n, p) <= 64 the lane-group layout of lds_of.cu -- GL = 8 / 16 / 32 lanes own an env, A, B, C and
+// the state stay in the group's slice of shared memory for all T steps, lanes split the rows of each mat-vec; for the
+// colab's system (d_hidden = 10, d_action = 3, d_obs = 2) a thread per env with everything in registers.
 // Streams: disturbances are Philox stream 0 (the same numbers the controller kernels draw), actions stream 3.
 #include "common.cuh"
 
@@ -124,6 +124,102 @@ __global__ void __launch_bounds__(256) lds_open_kernel(const OpenArgs a) {
   if (live) for (int i = gl; i < d; i += GL) a.x_io[(size_t)env * d + i] = sx[i];
 }
 
+// Thread-per-env variant for small compile-time shapes: A, B, C and the state live in REGISTERS (150 + 20 floats at
+// d = 10, n = 3, p = 2), a step is 150 FFMA with no shared memory and no warp synchronisation, and the next step's
+// action / disturbance are fetched while the current one computes.  The lane-group kernel above spends its time in
+// shared-memory mat-vecs and __syncwarp; this one is bound by HBM when the inputs come from memory.
+template <int D, int NA, int P>
+__global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.N) return;
+  const size_t eD = a.shared ? 0 : (size_t)env;
+  float A[D][D], B[D][NA], C[P][D], x[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = __ldg(a.A + eD * D * D + i * D + j);
+#pragma unroll
+    for (int c = 0; c < NA; ++c) B[i][c] = __ldg(a.B + eD * D * NA + i * NA + c);
+    x[i] = a.x_io[(size_t)env * D + i];
+  }
+  if (a.C) {
+#pragma unroll
+    for (int q = 0; q < P; ++q)
+#pragma unroll
+      for (int j = 0; j < D; ++j) C[q][j] = __ldg(a.C + eD * P * D + q * D + j);
+  }
+  const uint32_t genv = (uint32_t)(a.env_offset + env);
+  auto observe = [&](float* yo) {
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(C[q][j], x[j], s);
+      yo[q] = s;
+    }
+  };
+  auto fetch = [&](int t, float (&u)[NA], float (&w)[D]) {
+    if (a.u_in) {
+#pragma unroll
+      for (int c = 0; c < NA; ++c) u[c] = __ldg(a.u_in + ((size_t)t * a.N + env) * NA + c);
+    } else {
+#pragma unroll
+      for (int g = 0; g < (NA + 3) / 4; ++g) {
+        float z4[4];
+        normal4(a.seed, genv, (uint32_t)(a.t0 + t), (uint32_t)g, 3u, z4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * g + k < NA) u[4 * g + k] = __fmul_rn(a.action_std, z4[k]);
+      }
+    }
+    if (a.W) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = __ldg(a.W + ((size_t)t * a.N + env) * D + i);
+    } else if (a.w_std != 0.f) {
+#pragma unroll
+      for (int g = 0; g < (D + 3) / 4; ++g) {
+        float z4[4];
+        normal4(a.seed, genv, (uint32_t)(a.t0 + t), (uint32_t)g, 0u, z4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * g + k < D) w[4 * g + k] = __fmul_rn(a.w_std, z4[k]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = 0.f;
+    }
+  };
+  if (a.observe0 && a.y_out) observe(a.y_out + (size_t)env * P);
+  float un[NA], wn[D];
+  if (a.T > 0) fetch(0, un, wn);
+  for (int t = 0; t < a.T; ++t) {
+    float u[NA], w[D];
+#pragma unroll
+    for (int c = 0; c < NA; ++c) u[c] = un[c];
+#pragma unroll
+    for (int i = 0; i < D; ++i) w[i] = wn[i];
+    if (t + 1 < a.T) fetch(t + 1, un, wn);
+    if (a.u_out)
+#pragma unroll
+      for (int c = 0; c < NA; ++c) a.u_out[((size_t)t * a.N + env) * NA + c] = u[c];
+    float xn[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {   // same accumulation order as the lane-group kernel: A x, then B u, then + w
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) s = fmaf(A[i][j], x[j], s);
+#pragma unroll
+      for (int c = 0; c < NA; ++c) s = fmaf(B[i][c], u[c], s);
+      xn[i] = s + w[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = xn[i];
+    if (a.y_out) observe(a.y_out + ((size_t)(t + a.observe0) * a.N + env) * P);
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) a.x_io[(size_t)env * D + i] = x[i];
+}
+
 // SinusDisturbance.__call__ (deluca/envs/_lds.py:44-52): w_t[i] = sin(t * phases[i]) * amplitude, the same for every env
 __global__ void __launch_bounds__(256) sinus_disturbance_kernel(float* __restrict__ W, int64_t N, int T, int d,
                                                                 const float* __restrict__ phases, float amplitude,
@@ -170,6 +266,10 @@ extern "C" int32_t dlc_lds_open_rollout_f32(int64_t N, int32_t T, int32_t d, int
   a.observe0 = observe0 ? 1 : 0;
   a.A = A; a.B = B; a.C = C; a.u_in = u_in; a.W = W; a.x_io = x_io; a.y_out = y_out; a.u_out = u_out;
   a.seed = seed; a.w_std = w_std; a.action_std = action_std;
+  if (d == 10 && n == 3 && p == 2) {   // the colab's system: register-resident thread-per-env kernel
+    lds_open_reg_kernel<10, 3, 2><<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    return cuda_status(cudaGetLastError(), "lds_open_reg_kernel launch");
+  }
   int widest = d > n ? d : n;
   if (p > widest) widest = p;
   const int GL = widest <= 16 ? 8 : (widest <= 32 ? 16 : 32);
@@ -188,7 +288,6 @@ extern "C" int32_t dlc_lds_open_rollout_f32(int64_t N, int32_t T, int32_t d, int
   if (smem > (size_t)max_smem) return fail(DLC_ERR_SHAPE, "dlc_lds_open_rollout_f32: system does not fit shared memory");
   void (*kern)(const OpenArgs) = GL == 8 ? lds_open_kernel<8, 0, 0, 0> : (GL == 16 ? lds_open_kernel<16, 0, 0, 0>
                                                                                    : lds_open_kernel<32, 0, 0, 0>);
-  if (d == 10 && n == 3 && p == 2) kern = lds_open_kernel<8, 10, 3, 2>;
   if (d == 10 && n == 3 && p == 10) kern = lds_open_kernel<8, 10, 3, 10>;   // state feedback: C = I
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_open_kernel)");

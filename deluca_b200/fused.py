@@ -394,14 +394,15 @@ def lds_lqr_value_and_grad(A, B, K, x0, T, W=None, seed=0, env_offset=0, t0=0, w
 
 def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, Phi=None, theta=None, z=None,
                    ynat=None, us=None, m=0, h=0, t0=0, lr=0.005, decay=True, R_M=10.0, seed=0, env_offset=0,
-                   w_std=0.5, agent_only=False, keep_costs=True, keep_actions=True, donate=False, lanes_per_env=0):
+                   w_std=0.5, agent_only=False, keep_costs=True, keep_actions=True, donate=False, lanes_per_env=0, phi_is_identity=False):
     """``dlc_lds_of_rollout_f32``: T fused steps of the partially observed LDS (``deluca/envs/_lds.py:102-111``,
     y = C x) under an output-feedback controller: ``agent`` = "lqg" (``_lqg.py:83-98``; K[.,n,d], Lk[.,d,p],
     z = x_hat), "drc" (``_drc.py:131-203``; theta = M[N,m,n,p], ynat[N,m,p] and us[N,h,n] newest first,
     K[.,n,p] or None) or "fgrc" (GRC/SFC/DSC, ``_grc.py:110-169``; Phi[F,L], theta[N,F,n,p], z[N,d],
     ynat[N,L+m,p] oldest -> newest).  State tensors default to the agents' construction-time zeros; the returned
     ones (and ``t``) resume the episode.  ``agent_only``: ``Agent.__call__(y)`` with y = ``y_in[T,N,p]``.
-    ``lanes_per_env``: 0 (automatic) or 8 / 16 / 32 lanes of a warp per env."""
+    ``lanes_per_env``: 0 (automatic) or 8 / 16 / 32 lanes of a warp per env.  ``phi_is_identity``: the caller's
+    promise that ``Phi`` is the identity (GRC); verified on the device."""
     shared = A.dim() == 2
     d, n, p = A.shape[-1], B.shape[-1], C.shape[-2]
     if agent_only:
@@ -444,7 +445,7 @@ def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, 
     prm = _abi.DlcOfParams(N=N, env_offset=int(env_offset), T=T, d=d, n=n, p=p, agent=code, m=int(m), h=int(h), F=F,
                            L=L, t0=int(t0), decay=int(bool(decay)), shared_dynamics=int(shared),
                            mode=1 if agent_only else 0, lr=float(lr), R_M=float(R_M), w_std=float(w_std),
-                           reserved=int(lanes_per_env), seed=int(seed))
+                           reserved=int(lanes_per_env) or int(bool(phi_is_identity)), seed=int(seed))
     costs = torch.empty(T, N, device=dev) if keep_costs else None
     U = torch.empty(T, N, n, device=dev) if keep_actions else None
     cost_sum = torch.zeros(N, dtype=torch.float64, device=dev)

@@ -44,6 +44,7 @@ extern "C" {
 /* per-env status bits written by the kernels */
 #define DLC_STATUS_NONFINITE 1   /* a NaN/Inf appeared in the env's state or cost */
 #define DLC_STATUS_NOT_PD 2      /* Q_uu not positive definite in the Riccati backward pass */
+#define DLC_STATUS_BAD_HINT 4    /* a caller's hint did not hold (DlcOfParams.reserved = 1 with Phi != I): nothing computed, cost_sum = NaN */
 
 int32_t dlc_abi_version(void);
 /* sizeof() of the parameter structs as compiled, so a binding can verify its own layout:
@@ -462,7 +463,9 @@ typedef struct DlcOfParams {
   float lr;            /* GRC/SFC/DSC lr (_grc.py:52), DRC lr_scale (_drc.py:53) */
   float R_M;           /* projection radius R_M (_grc.py:49) / RM (_drc.py:55) */
   float w_std;         /* std of the in-kernel Gaussian disturbance, used when W == NULL */
-  int32_t reserved;    /* 0 = choose the lanes per env automatically; 8, 16 or 32 forces it (tuning / tests) */
+  int32_t reserved;    /* 0 = automatic; 1 = the caller asserts Phi == I (GRC), which unlocks the register-resident kernel on
+                          the colab's system (verified on the device: DLC_STATUS_BAD_HINT); 8, 16 or 32 forces that many
+                          lanes per env (tuning / tests) */
   uint64_t seed;
 } DlcOfParams;
 

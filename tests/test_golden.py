@@ -99,9 +99,10 @@ def test_kernels_match_the_frozen_vectors():
     # output feedback: GRC on the colab's shape (compile-time-dims instantiation) and the runtime-dims kernel
     z = np.load(os.path.join(G, "oracle_grc_small.npz"))
     T = z["W"].shape[0]
-    for lanes in (0, 32):
+    for lanes, hint in ((0, False), (32, False), (0, True)):   # compile-time dims, runtime dims, register-resident
         r = fused.lds_of_rollout(t(z["A"]), t(z["B"]), t(z["C"]), t(z["x0"]), T, agent="fgrc", W=t(z["W"]), Phi=t(z["Phi"]),
-                                 theta=t(z["Theta0"]), m=10, lr=0.005, decay=True, R_M=10.0, lanes_per_env=lanes)
+                                 theta=t(z["Theta0"]), m=10, lr=0.005, decay=True, R_M=10.0, lanes_per_env=lanes,
+                                 phi_is_identity=hint)
         c = r.costs.cpu().numpy()
         assert (np.abs(c - z["costs"]) <= 1e-4 * np.maximum(np.abs(z["costs"]), 1e-2 * z["costs"].mean())).all()
         np.testing.assert_allclose(r.theta.cpu().numpy(), z["Theta"], rtol=1e-3, atol=1e-4 * np.abs(z["Theta"]).max())

@@ -66,14 +66,16 @@ def test_filter_family_matches_oracle(kind, d, n, p, m, h, scale, R_M):
     kw = dict(lr=0.005, decay=True, R_M=R_M)
     ref = O.rollout_of(A, B, C, x0, W, "fgrc", dtype=np.float64, Theta0=Theta0, Phi=Phi, m=m, **kw)
     assert np.abs(ref["costs"]).max() < 1e4
-    res = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, agent="fgrc", W=_dev(W), Phi=_dev(Phi),
-                         theta=_dev(Theta0), m=m, **kw)
-    _check(res, ref)
-    st = ref["state"]
-    scale = np.abs(st["Theta"]).max()
-    np.testing.assert_allclose(res.theta.cpu().numpy(), st["Theta"], rtol=1e-3, atol=1e-4 * scale)
-    np.testing.assert_allclose(res.ynat.cpu().numpy(), st["ynats"], rtol=1e-3, atol=1e-4 * np.abs(st["ynats"]).max())
-    np.testing.assert_allclose(res.z.cpu().numpy(), st["z"], rtol=1e-3, atol=1e-4 * np.abs(st["z"]).max())
+    # GRC's filter bank is the identity: with that promise the colab shape runs the register-resident kernel
+    for hint in ((False, True) if kind == "grc" else (False,)):
+        res = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, agent="fgrc", W=_dev(W), Phi=_dev(Phi),
+                             theta=_dev(Theta0), m=m, phi_is_identity=hint, **kw)
+        _check(res, ref)
+        st = ref["state"]
+        scale = np.abs(st["Theta"]).max()
+        np.testing.assert_allclose(res.theta.cpu().numpy(), st["Theta"], rtol=1e-3, atol=1e-4 * scale)
+        np.testing.assert_allclose(res.ynat.cpu().numpy(), st["ynats"], rtol=1e-3, atol=1e-4 * np.abs(st["ynats"]).max())
+        np.testing.assert_allclose(res.z.cpu().numpy(), st["z"], rtol=1e-3, atol=1e-4 * np.abs(st["z"]).max())
 
 
 def test_projection_active_and_no_decay():
@@ -285,3 +287,31 @@ def test_dsc_default_shape_matches_oracle():
     alt = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, agent="fgrc", W=_dev(W), Phi=_dev(Phi),
                          theta=_dev(Theta0), m=m, lanes_per_env=16, **kw)
     np.testing.assert_allclose(res.costs.cpu().numpy(), alt.costs.cpu().numpy(), rtol=2e-4, atol=1e-5)
+
+
+def test_grc_register_kernel_resume_projection_and_broken_promise():
+    """The register-resident GRC kernel (colab shape, reserved = 1): resume == uninterrupted bit for bit, agreement with
+    the lane-group kernel when the projection is active and without decay, in-kernel disturbances, and a loud failure
+    when the caller's `Phi is the identity` promise does not hold."""
+    from deluca_b200.fused import lds_of_rollout
+    N, T, d, n, p, m = 70, 160, 10, 3, 2, 10
+    A, B, C, x0, W, rng = _sys(N, d, n, p, T, seed=21)
+    Phi, _ = O.filter_bank("grc", m, None)
+    th = _dev((0.3 * rng.standard_normal((N, m, n, p))).astype(np.float32))
+    for kw in (dict(lr=0.005, decay=True, R_M=10.0), dict(lr=0.002, decay=False, R_M=0.4)):
+        common = dict(agent="fgrc", Phi=_dev(Phi), m=m, seed=5, env_offset=3, **kw)
+        full = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, theta=th, phi_is_identity=True, **common)
+        lanes = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, theta=th, **common)
+        np.testing.assert_allclose(full.costs.cpu().numpy(), lanes.costs.cpu().numpy(), rtol=3e-4, atol=1e-5)
+        np.testing.assert_allclose(full.theta.cpu().numpy(), lanes.theta.cpu().numpy(), rtol=1e-3, atol=1e-5)
+        h = 60
+        r1 = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), h, theta=th, phi_is_identity=True, **common)
+        r2 = lds_of_rollout(_dev(A), _dev(B), _dev(C), r1.x, T - h, theta=r1.theta, z=r1.z, ynat=r1.ynat, t0=r1.t,
+                            phi_is_identity=True, **common)
+        assert torch.equal(torch.cat([r1.costs, r2.costs]), full.costs)
+        assert torch.equal(r2.theta, full.theta) and torch.equal(r2.ynat, full.ynat) and torch.equal(r2.x, full.x)
+    bad = Phi.copy()
+    bad[0, 1] = 0.5
+    r = lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), 5, agent="fgrc", Phi=_dev(bad), theta=th, m=m,
+                       phi_is_identity=True)
+    assert (r.status.cpu().numpy() == 4).all() and torch.isnan(r.cost_sum).all()

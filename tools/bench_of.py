@@ -81,7 +81,8 @@ for name, kw, (Nc, Tc) in cases:
         F, L = Phi.shape
         theta = 0.3 / F ** 0.5 * torch.randn(N, F, n, p, device=dev, generator=g)
         run = lambda: fused.lds_of_rollout(A, B, C, x0, T, agent="fgrc", W=W, Phi=Phi, theta=theta, m=kw["m"], R_M=1.0,
-                                           keep_actions=False, lanes_per_env=args.lanes)
+                                           keep_actions=False, lanes_per_env=args.lanes,
+                                           phi_is_identity=(name == "grc" and not args.lanes))
         fl = flops_fgrc(F, L, kw["m"])
     elif name == "drc":
         theta = 0.03 * torch.randn(N, kw["m"], n, p, device=dev, generator=g)

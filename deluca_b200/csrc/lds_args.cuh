@@ -23,4 +23,7 @@ bool launch_gpc_f2(const LdsArgs& a, cudaStream_t st, int32_t* rc);
 bool launch_bpc(const LdsArgs& a, float* bpc_cost_io, cudaStream_t st, int32_t* rc);
 bool bpc_supported(const DlcLdsParams& p);
 
+// lane-group GPC kernel for any (d, m <= 64, H, HH) (lds_gpc_group.cu).  Returns false if it does not take the call.
+bool launch_gpc_group(const LdsArgs& a, cudaStream_t st, int32_t* rc);
+
 }  // namespace dlc

@@ -235,6 +235,34 @@ def test_bpc_lane_split_kernel(d, m, H, decay, prev):
     assert torch.equal(r2.M, a.M) and torch.equal(r2.eps, a.eps) and torch.equal(r2.x, a.x)
 
 
+@pytest.mark.parametrize("d,m,H,HH", [(25, 1, 3, 2), (6, 2, 4, 5), (5, 2, 4, 2), (40, 5, 3, 6), (64, 8, 2, 3), (17, 3, 1, 1)])
+def test_gpc_lane_group_kernel(d, m, H, HH):
+    """The lane-group GPC kernel (any shape with d, m <= 64; the LDS defaults d_hidden = 25, d_in = 1 among them)
+    against the float64 oracle, against the thread-per-env runtime-dims kernel on every state tensor with in-kernel
+    disturbances and sampled trajectories, and resume == uninterrupted bit for bit."""
+    from deluca_b200.fused import lds_rollout
+    N, T = 45, 80
+    A, B, K, x0, W = _problem(N, d, m, T, seed=d + H, dense=True)
+    ref = O.rollout_lds(A, B, K, x0, W, "gpc", H=H, HH=HH, lr_scale=1e-4, dtype=np.float64)
+    res = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, policy="gpc", W=_dev(W), H=H, HH=HH, lr_scale=1e-4)
+    _check(res, ref, T)
+    np.testing.assert_allclose(res.M.cpu().numpy(), ref["state"]["M"], rtol=1e-3, atol=1e-5 * max(np.abs(ref["state"]["M"]).max(), 1e-6))
+    kw = dict(policy="gpc", H=H, HH=HH, lr_scale=1e-4, seed=31, env_offset=9, traj_stride=5, noise_uses_prev_action=True)
+    a = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, **kw)
+    b = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, kernel_variant=1, **kw)
+    for f in ("costs", "x", "M", "hist", "xprev", "uprev", "X", "U"):
+        ta, tb = getattr(a, f).cpu().numpy(), getattr(b, f).cpu().numpy()
+        np.testing.assert_allclose(ta, tb, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(tb).max()), err_msg=f)
+    h = T // 2
+    kw.pop("traj_stride")
+    full = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, **kw)
+    r1 = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), h, **kw)
+    r2 = lds_rollout(_dev(A), _dev(B), _dev(K), r1.x, T - h, M=r1.M, hist=r1.hist, xprev=r1.xprev, uprev=r1.uprev,
+                     t0=r1.t, **kw)
+    assert torch.equal(torch.cat([r1.costs, r2.costs]), full.costs)
+    assert torch.equal(r2.M, full.M) and torch.equal(r2.hist, full.hist) and torch.equal(r2.x, full.x)
+
+
 def test_empty_batch_and_argument_errors():
     from deluca_b200 import _abi
     from deluca_b200.fused import lds_rollout

@@ -981,7 +981,7 @@ __global__ void __launch_bounds__(128) env_rollout_kernel(const PlanArgs a) {
   if (n >= a.p.N) return;
   const int H = a.p.H;
   const Mdl env(a.use_sim ? a.p.env_sim : a.p.env_true);
-  const float c = rollout_one(env, a.p, a.U_old + n * H * M, a.k ? a.k + n * H * M : nullptr,
+  const float c = rollout_one_pf<Mdl, true>(env, a.p, a.U_old + n * H * M, a.k ? a.k + n * H * M : nullptr,
                               a.K ? a.K + n * H * M * D : nullptr, a.X_old ? a.X_old + n * (H + 1) * D : nullptr,
                               a.alpha ? a.alpha[n] : 1.0f, a.x0 + n * D, a.X_out + n * (H + 1) * D,
                               a.U_out + n * H * M);
@@ -1080,7 +1080,7 @@ __global__ void __launch_bounds__(128) igpc_rollout_kernel(const PlanArgs a) {
   if (n >= a.p.N) return;
   const int H = a.p.H;
   const Mdl tru(a.p.env_true), sim(a.p.env_sim);
-  a.cost_out[n] = igpc_rollout_one(tru, sim, a.p, a.U_old + n * H * M, a.k + n * H * M, a.K + n * H * M * D,
+  a.cost_out[n] = igpc_rollout_best(tru, sim, a.p, a.U_old + n * H * M, a.k + n * H * M, a.K + n * H * M * D,
                                    a.X_old + n * (H + 1) * D, a.alpha ? a.alpha[n] : 1.0f, a.x0 + n * D,
                                    a.X_out + n * (H + 1) * D, a.U_out + n * H * M);
 }
@@ -1495,6 +1495,10 @@ static int32_t check_plan(const DlcPlanParams* p, const char* who) {
 
 using namespace dlc;
 
+// thread-per-trajectory kernels: one-warp CTAs while the batch is small enough that spreading the warps over all SMs
+// (L1 residency of each trajectory's ~10 KB working set) matters more than CTA count; 128 threads beyond that
+static inline int plan_block(int64_t N) { return N <= 148 * 32 * 8 ? 32 : 128; }
+
 #define DLC_DISPATCH_ENV_B(kind, KERNEL, grid, block, st, args)                            \
   do {                                                                                    \
     if ((kind) == DLC_ENV_PENDULUM) KERNEL<DLC_ENV_PENDULUM><<<grid, block, 0, st>>>(args); \
@@ -1522,8 +1526,9 @@ extern "C" int32_t dlc_env_rollout_f32(const DlcPlanParams* p, int32_t use_sim_e
   PlanArgs a{};
   a.p = *p; a.U_old = U_old; a.k = k; a.K = K; a.X_old = X_old; a.alpha = alpha; a.x0 = x0;
   a.X_out = X_out; a.U_out = U_out; a.cost_out = cost_out; a.use_sim = use_sim_env;
-  const unsigned grid = (unsigned)((p->N + 127) / 128);
-  DLC_DISPATCH_ENV(p->env_true.kind, env_rollout_kernel, grid, (cudaStream_t)stream, a);
+  const int block = plan_block(p->N);
+  const unsigned grid = (unsigned)((p->N + block - 1) / block);
+  DLC_DISPATCH_ENV_B(p->env_true.kind, env_rollout_kernel, grid, block, (cudaStream_t)stream, a);
   return cuda_status(cudaGetLastError(), "env_rollout_kernel launch");
 }
 
@@ -1564,8 +1569,9 @@ extern "C" int32_t dlc_igpc_rollout_f32(const DlcPlanParams* p, const float* U_o
   PlanArgs a{};
   a.p = *p; a.U_old = U_old; a.k = k; a.K = K; a.X_old = X_old; a.alpha = alpha; a.x0 = x0;
   a.X_out = X_out; a.U_out = U_out; a.cost_out = cost_out;
-  const unsigned grid = (unsigned)((p->N + 127) / 128);
-  DLC_DISPATCH_ENV(p->env_true.kind, igpc_rollout_kernel, grid, (cudaStream_t)stream, a);
+  const int block = plan_block(p->N);
+  const unsigned grid = (unsigned)((p->N + block - 1) / block);
+  DLC_DISPATCH_ENV_B(p->env_true.kind, igpc_rollout_kernel, grid, block, (cudaStream_t)stream, a);
   return cuda_status(cudaGetLastError(), "igpc_rollout_kernel launch");
 }
 

@@ -45,4 +45,22 @@ for name, Env in (("pendulum", Pendulum), ("cartpole", Cartpole)):
                                   "trajectory_steps_iterations_per_s": N * H * T / (ms * 1e-3),
                                   "mean_final_cost": float(c.mean()), "finite": bool(torch.isfinite(c).all()),
                                   "bound": "instruction latency (serial T x H dependency chain per trajectory)"}
+# the building blocks on their own: igpc.rollout and GPC_rollout, one launch each (pendulum)
+from deluca_b200.igpc.rollout import rollout as _rollout  # noqa: E402
+env = Pendulum.create(H=H)
+cost = QuadCost(list(env.goal_state), 1.0, 0.1)
+gg = torch.Generator(device=dev).manual_seed(0)
+x0 = env.init(N)[0].arr + 0.05 * torch.randn(N, env.state_dim, device=dev, generator=gg)
+U0 = 0.1 * torch.randn(N, H, 1, device=dev, generator=gg)
+p = fused.plan_params(env, env, cost, N, H)
+X, U, c = fused.env_rollout(p, U0, x0)
+kz = torch.zeros(N, H, 1, device=dev)
+Kz = torch.zeros(N, H, 1, env.state_dim, device=dev)
+al = torch.ones(N, device=dev)
+out["env_rollout_open_loop_pendulum"] = {"trajectories": N, "H": H, "kernel_ms": timeit(lambda: fused.env_rollout(p, U0, x0))}
+out["env_rollout_feedback_pendulum"] = {"trajectories": N, "H": H,
+                                        "kernel_ms": timeit(lambda: fused.env_rollout(p, U, x0, kz, Kz, X, al))}
+pg = fused.plan_params(env, env, cost, N, H, algo=1, lr=0.001)
+out["igpc_rollout_pendulum"] = {"trajectories": N, "H": H,
+                                "kernel_ms": timeit(lambda: fused.igpc_rollout(pg, U, kz, Kz, X, al, x0))}
 print(json.dumps(out))

@@ -226,29 +226,56 @@ __global__ void __launch_bounds__(GAE_WARPS * 32) gae_batch_major_kernel(const G
   }
 }
 
+// Time-major [T,N]: V adjacent agents per thread (float2 when N is even: twice the bytes in flight per thread), loads
+// hoisted eight steps deep.
+template <int V>
 __global__ void __launch_bounds__(128) gae_time_major_kernel(const GaeArgs a) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (n >= a.N) return;
   const int T = a.T;
   const int64_t N = a.N;
   const float* __restrict__ losses = a.losses;
   const float* __restrict__ values = a.values;
-  const float* __restrict__ tail = a.returns_use_values ? nullptr : a.log_probs;
+  const float* __restrict__ masks = a.masks;
+  const float* __restrict__ tail = a.ret ? (a.returns_use_values ? a.values : a.log_probs) : nullptr;
   float* __restrict__ adv = a.adv;
   float* __restrict__ ret = a.ret;
-  float gae = 0.f, vnext = 0.f;
+  float gae[V], vnext[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { gae[k] = 0.f; vnext[k] = 0.f; }
+  // gae_T = 0, values[T] := 0: the general step is rewards[-1] - values[-1] at t = T-1
 #pragma unroll 8
   for (int t = T - 1; t >= 0; --t) {
     const int64_t i = (int64_t)t * N + n;
-    const float rew = -losses[i];
-    const float v = values[i];
-    // gae_T = 0, values[T] := 0: the general step is rewards[-1] - values[-1] at t = T-1
-    const float mk = a.masks ? a.masks[i] : 1.0f;
-    const float delta = __fsub_rn(__fadd_rn(rew, __fmul_rn(__fmul_rn(a.discount, vnext), mk)), v);
-    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(a.dl, mk), gae));
-    vnext = v;
-    adv[i] = gae;
-    if (ret) ret[i] = __fadd_rn(gae, tail ? tail[i] : v);
+    float l[V], v[V], mk[V], tl[V], o_adv[V], o_ret[V];
+    if (V == 2) {
+      const float2 l2 = *reinterpret_cast<const float2*>(losses + i), v2 = *reinterpret_cast<const float2*>(values + i);
+      l[0] = l2.x; l[V - 1] = l2.y; v[0] = v2.x; v[V - 1] = v2.y;
+      if (masks) { const float2 m2 = *reinterpret_cast<const float2*>(masks + i); mk[0] = m2.x; mk[V - 1] = m2.y; }
+      if (tail) { const float2 t2 = *reinterpret_cast<const float2*>(tail + i); tl[0] = t2.x; tl[V - 1] = t2.y; }
+    } else {
+      l[0] = losses[i]; v[0] = values[i];
+      if (masks) mk[0] = masks[i];
+      if (tail) tl[0] = tail[i];
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float rew = -l[k];
+      float dv = __fmul_rn(a.discount, vnext[k]), cg = a.dl;
+      if (masks) { dv = __fmul_rn(dv, mk[k]); cg = __fmul_rn(cg, mk[k]); }
+      const float delta = __fsub_rn(__fadd_rn(rew, dv), v[k]);
+      gae[k] = __fadd_rn(delta, __fmul_rn(cg, gae[k]));
+      vnext[k] = v[k];
+      o_adv[k] = gae[k];
+      o_ret[k] = tail ? __fadd_rn(gae[k], tl[k]) : 0.f;
+    }
+    if (V == 2) {
+      *reinterpret_cast<float2*>(adv + i) = make_float2(o_adv[0], o_adv[V - 1]);
+      if (ret) *reinterpret_cast<float2*>(ret + i) = make_float2(o_ret[0], o_ret[V - 1]);
+    } else {
+      adv[i] = o_adv[0];
+      if (ret) ret[i] = o_ret[0];
+    }
   }
 }
 
@@ -271,7 +298,8 @@ extern "C" int32_t dlc_gae_f32(int64_t N, int32_t T, int32_t time_major, const f
   a.adv = advantages_out; a.ret = returns_out;
   cudaStream_t st = (cudaStream_t)stream;
   if (time_major) {
-    gae_time_major_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
+    if ((N & 1) == 0) gae_time_major_kernel<2><<<(unsigned)((N / 2 + 127) / 128), 128, 0, st>>>(a);
+    else gae_time_major_kernel<1><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(a);
   } else {
     const size_t smem = (size_t)GAE_WARPS * (T <= GAE_TC ? 1 : 2) * (done_masks ? 4 : 3) * GAE_TILE * sizeof(float);
     const int per_cta = GAE_WARPS * (T <= GAE_TC ? 32 : GAE_LR);   // agents per CTA

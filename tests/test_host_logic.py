@@ -139,3 +139,30 @@ def test_two_rank_statistics_reduction_over_gloo(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/deluca_b200.h must be consumable by a C compiler (no C++ / torch types in any signature) and a C
+    program must link against the shared library and get sane answers from the calls that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi_check.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "deluca_b200.h"\n'
+        "int main(void) {\n"
+        "  DlcLdsParams p; memset(&p, 0, sizeof p);\n"
+        "  if (dlc_abi_version() != DLC_ABI_VERSION) return 1;\n"
+        "  if (dlc_sizeof(0) != sizeof(DlcLdsParams) || dlc_sizeof(5) != sizeof(DlcOfParams)) return 2;\n"
+        "  p.N = -1;\n"
+        "  if (dlc_lds_rollout_f32(&p, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) >= 0) return 3;\n"
+        "  if (strlen(dlc_last_error()) == 0) return 4;\n"
+        "  if (dlc_gae_f32(4, 0, 0, 0, 0, 0, 0, 0.99f, 0.95f, 0, 0, 0, 0) >= 0) return 5;\n"
+        '  printf("ok\\n");\n  return 0;\n}\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.join(ROOT, "deluca_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-ldeluca_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)

@@ -173,8 +173,17 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
       }
     }
     if (a.W) {
+      const float* wr = a.W + ((size_t)t * a.N + env) * D;
+      if (D % 2 == 0) {   // rows of an even d start on 8-byte boundaries: half the load instructions
 #pragma unroll
-      for (int i = 0; i < D; ++i) w[i] = __ldg(a.W + ((size_t)t * a.N + env) * D + i);
+        for (int i = 0; i < D / 2; ++i) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(wr) + i);
+          w[2 * i] = v.x; w[2 * i + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = __ldg(wr + i);
+      }
     } else if (a.w_std != 0.f) {
 #pragma unroll
       for (int g = 0; g < (D + 3) / 4; ++g) {
@@ -214,7 +223,17 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
     }
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = xn[i];
-    if (a.y_out) observe(a.y_out + ((size_t)(t + a.observe0) * a.N + env) * P);
+    if (a.y_out) {
+      float yv[P];
+      observe(yv);
+      float* yo = a.y_out + ((size_t)(t + a.observe0) * a.N + env) * P;
+      if (P == 2) {
+        *reinterpret_cast<float2*>(yo) = make_float2(yv[0], yv[P - 1]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < P; ++q) yo[q] = yv[q];
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < D; ++i) a.x_io[(size_t)env * D + i] = x[i];

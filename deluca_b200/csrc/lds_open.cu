@@ -199,15 +199,8 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
     }
   };
   if (a.observe0 && a.y_out) observe(a.y_out + (size_t)env * P);
-  float un[NA], wn[D];
-  if (a.T > 0) fetch(0, un, wn);
-  for (int t = 0; t < a.T; ++t) {
-    float u[NA], w[D];
-#pragma unroll
-    for (int c = 0; c < NA; ++c) u[c] = un[c];
-#pragma unroll
-    for (int i = 0; i < D; ++i) w[i] = wn[i];
-    if (t + 1 < a.T) fetch(t + 1, un, wn);
+  // one step of the env given its action and disturbance
+  auto advance = [&](int t, const float (&u)[NA], const float (&w)[D]) {
     if (a.u_out)
 #pragma unroll
       for (int c = 0; c < NA; ++c) a.u_out[((size_t)t * a.N + env) * NA + c] = u[c];
@@ -233,6 +226,31 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
 #pragma unroll
         for (int q = 0; q < P; ++q) yo[q] = yv[q];
       }
+    }
+  };
+  // inputs are fetched TWO steps ahead (two register buffers, the loop advances two steps per trip): with 8 warps per
+  // SM one step's 52 bytes per thread in flight is well short of what the HBM latency needs
+  float u0[NA], w0[D], u1[NA], w1[D];
+  if (a.T > 0) fetch(0, u0, w0);
+  if (a.T > 1) fetch(1, u1, w1);
+  for (int t = 0; t < a.T; t += 2) {
+    {
+      float u[NA], w[D];
+#pragma unroll
+      for (int c = 0; c < NA; ++c) u[c] = u0[c];
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = w0[i];
+      if (t + 2 < a.T) fetch(t + 2, u0, w0);
+      advance(t, u, w);
+    }
+    if (t + 1 < a.T) {
+      float u[NA], w[D];
+#pragma unroll
+      for (int c = 0; c < NA; ++c) u[c] = u1[c];
+#pragma unroll
+      for (int i = 0; i < D; ++i) w[i] = w1[i];
+      if (t + 3 < a.T) fetch(t + 3, u1, w1);
+      advance(t + 1, u, w);
     }
   }
 #pragma unroll

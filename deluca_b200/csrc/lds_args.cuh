@@ -26,4 +26,8 @@ bool bpc_supported(const DlcLdsParams& p);
 // lane-group GPC kernel for any (d, m <= 64, H, HH) (lds_gpc_group.cu).  Returns false if it does not take the call.
 bool launch_gpc_group(const LdsArgs& a, cudaStream_t st, int32_t* rc);
 
+// register-resident thread-per-env LQR kernel for (d, m) = (10, 3) (lds_lqr_reg.cu)
+bool launch_lqr_reg(const LdsArgs& a, cudaStream_t st, int32_t* rc);
+bool lqr_reg_supported(const DlcLdsParams& p);
+
 }  // namespace dlc

@@ -894,7 +894,7 @@ using namespace dlc;
 
 extern "C" size_t dlc_lds_workspace_bytes(const DlcLdsParams* p) {
   if (!p || p->N <= 0 || p->d <= 0 || p->m <= 0) return 0;
-  if (split_supported(*p) || bpc_supported(*p)) return 0;   // the compile-time-shape kernels need no workspace
+  if (split_supported(*p) || bpc_supported(*p) || lqr_reg_supported(*p)) return 0;   // the compile-time-shape kernels need no workspace
   // runtime-dims kernel: scratch vectors plus an [element][env] copy of every per-env array
   return (size_t)generic_stage(*p).total * (size_t)p->N * sizeof(float);
 }
@@ -954,6 +954,7 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
   cudaStream_t st = (cudaStream_t)stream;
   int32_t rc = DLC_OK;
   if (launch_bpc(a, bpc_cost_io, st, &rc)) return rc;
+  if (launch_lqr_reg(a, st, &rc)) return rc;
   if (try_split(a, st, &rc)) return rc;
   if (launch_gpc_group(a, st, &rc)) return rc;
   if (!workspace || workspace_bytes < dlc_lds_workspace_bytes(p))

@@ -116,6 +116,25 @@ def test_lqr_matches_oracle_and_zero_lr_gpc(variant):
         assert torch.allclose(a.costs, b.costs, rtol=1e-5, atol=1e-5) and torch.allclose(a.x, b.x, rtol=1e-5, atol=1e-5)
 
 
+def test_lqr_register_kernel_against_lane_split_and_resume():
+    """The register-resident LQR kernel (d = 10, m = 3, kernel_variant 0) against the lane-split kernel (forced launch
+    shape 5) with in-kernel disturbances, shared dynamics, odd T, sampled trajectories; resume bit for bit."""
+    from deluca_b200.fused import lds_rollout
+    N, T, d, m = 77, 91, 10, 3
+    A, B, K, x0, W = _problem(N, d, m, T, seed=12, dense=True)
+    for shared in (False, True):
+        mats = tuple(_dev(v[0] if shared else v) for v in (A, B, K))
+        kw = dict(policy="lqr", seed=8, env_offset=100, traj_stride=3)
+        a = lds_rollout(*mats, _dev(x0), T, **kw)
+        b = lds_rollout(*mats, _dev(x0), T, kernel_variant=5, **kw)
+        for f in ("costs", "x", "X", "U"):
+            np.testing.assert_allclose(getattr(a, f).cpu().numpy(), getattr(b, f).cpu().numpy(), rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(a.cost_sum.cpu().numpy(), b.cost_sum.cpu().numpy(), rtol=1e-5)
+        r1 = lds_rollout(*mats, _dev(x0), 40, **kw)
+        r2 = lds_rollout(*mats, r1.x, T - 40, t0=40, **kw)
+        assert torch.equal(torch.cat([r1.costs, r2.costs]), a.costs) and torch.equal(r2.x, a.x)
+
+
 def test_resume_is_identical_and_inputs_untouched():
     from deluca_b200.fused import lds_rollout
     N, T, d, m = 64, 90, 10, 3

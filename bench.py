@@ -134,7 +134,12 @@ def cpu_baseline(wl, seconds_target=12.0):
     bounded sample of the workload: same step, same distributions, fewer envs and steps."""
     import numpy as np
     from oracle.lds_c import gpc_rollout_c, max_threads
-    cores = max_threads()
+    # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() obeys,
+    # so count the affinity mask instead and hand the number to omp_set_num_threads() explicitly
+    try:
+        cores = max(max_threads(), len(os.sched_getaffinity(0)))
+    except AttributeError:
+        cores = max(max_threads(), os.cpu_count() or 1)
     d, m = wl["d"], wl["m"]
     Nc = 2048 * cores
     rng = np.random.default_rng(0)

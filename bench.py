@@ -4,7 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch: the fused T-step rollout of all envs of the
-workload (default = BASELINE.json configs[1]: 65,536 envs x T=10,000, LDS d=10 m=3, GPC H=3 HH=10).
+workload.  Default workload = the north-star target of BASELINE.json (LDS d=10 m=3 + GPC H=HH=10,
+2^20 envs x T=1000; it fits one GPU: 42 GB of disturbances), a FIXED job that `--gpus N` splits into N
+contiguous env shards ("scaling": "strong").  BASELINE.json configs[1] (65,536 envs x T=10,000, H=3) --
+the round-1 headline -- is measured in the same run at N=1 and carried as the sub-record "c2" (and is
+still selectable with --workload c2, weak scaling as in round 1).
 One JSON line is printed by rank 0; see DESIGN.md section 6 for how each key is measured.
 """
 import argparse
@@ -19,24 +23,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    # BASELINE.json north_star target (default)
+    "tgt": dict(N=1 << 20, T=1000, d=10, m=3, H=10, HH=10, scaling="strong",
+                desc="LDS(d=10,m=3)+GPC(H=10,HH=10) 1048576 envs x T=1000, per-env A/B/K, Gaussian w (std 0.5)"),
     # BASELINE.json configs[1]
-    "c2": dict(N=65536, T=10000, d=10, m=3, H=3, HH=10,
+    "c2": dict(N=65536, T=10000, d=10, m=3, H=3, HH=10, scaling="weak",
                desc="LDS(d=10,m=3)+GPC(H=3,HH=10) 65536 envs x T=10000, per-env A/B/K, Gaussian w (std 0.5)"),
-    # BASELINE.json north_star target
-    "tgt": dict(N=1 << 20, T=1000, d=10, m=3, H=10, HH=10,
-                desc="LDS(d=10,m=3)+GPC(H=10,HH=10) 1M envs x T=1000"),
-    "smoke": dict(N=4096, T=200, d=10, m=3, H=3, HH=10, desc="small test workload"),
+    "smoke": dict(N=4096, T=200, d=10, m=3, H=3, HH=10, scaling="weak", desc="small test workload"),
 }
 # The reference default lr_scale=0.005 makes GPC-as-written diverge on the default LDS
-# (tests/test_oracle_lds.py::test_reference_noise_quirk...); 1e-4 keeps every env finite so that
+# (tests/test_oracle_lds.py::test_reference_noise_quirk...); 1e-4 keeps the envs finite so that
 # the rollout that is timed is also the rollout whose parity is tested.
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
-# `ncu --set full` capture of this same command (profiles/r01_lds_f2_32x9_full.txt): 26.33 + 2.68 GB
-# against 28.9 GB of algorithmic bytes.  Other workloads / modes have no capture -> null.
-NCU_TRAFFIC_BYTES = {("c2", "hbm"): 26.330129e9 + 2.676375e9}
 LR_SCALE = 1e-4
 W_STD = 0.5
 SEED = 20240
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
+# `ncu --set full` capture of the same workload (file named beside each); other modes -> null.
+NCU_TRAFFIC = {
+    ("c2", "hbm"): (26.330129e9 + 2.676375e9, "profiles/r01_lds_f2_32x9_full.txt"),
+}
+try:
+    NCU_TRAFFIC.update({tuple(k.split("/")): (v["bytes"], v["file"]) for k, v in
+                        json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).items()})
+except (OSError, ValueError):
+    pass
 
 
 def flops_per_env_step(d, m, H):
@@ -74,35 +84,48 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    @staticmethod
+    def mark():
+        return time.monotonic()
+
+    def stop(self, t_from=None, t_to=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for ts, r in self.rows if (t_from is None or ts >= t_from) and (t_to is None or ts <= t_to + 0.3)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm = sorted(int(float(r[0])) for r in rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": "warm-up + timed region of the headline workload"}
 
 
-def make_problem(torch, wl, dev, rank):
+def make_problem(torch, wl, dev, lo, n):
     """Synthetic per-env systems with the reference's default distributions (_lds.py:69-91):
-    A = diag(U(.9,.95)) stored and treated as a dense [d,d] matrix, B ~ N(0,1), K = LQR gain."""
+    A = diag(U(.9,.95)) stored and treated as a dense [d,d] matrix, B ~ N(0,1), K = LQR gain.
+    Every env's system is a function of its GLOBAL index (counter-based Philox stream keyed by
+    lo + local index), so a shard draws the same systems on any rank of any world size and the job's
+    statistics are invariant to how it is split."""
+    from deluca_b200.fused import gaussian_disturbance
     from deluca_b200.riccati import dare_gain
-    N, d, m = wl["N"], wl["d"], wl["m"]
-    g = torch.Generator(device=dev).manual_seed(SEED + rank)
-    A = torch.diag_embed(0.9 + 0.05 * torch.rand(N, d, device=dev, generator=g))
-    B = torch.randn(N, d, m, device=dev, generator=g)
-    K = torch.empty(N, m, d, device=dev)
-    for s in range(0, N, 1 << 16):
+    d, m = wl["d"], wl["m"]
+    z = gaussian_disturbance(n, 1, d + d * m, seed=SEED + 7, env_offset=lo, std=1.0, device=dev)[0]
+    unif = 0.5 * (1.0 + torch.erf(z[:, :d].double() * 0.7071067811865476))      # Phi(z) ~ U(0,1)
+    A = torch.diag_embed((0.9 + 0.05 * unif).float())
+    B = z[:, d:].reshape(n, d, m).contiguous()
+    K = torch.empty(n, m, d, device=dev)
+    for s in range(0, n, 1 << 16):
         K[s:s + (1 << 16)] = dare_gain(A[s:s + (1 << 16)], B[s:s + (1 << 16)])[0]
-    x0 = torch.zeros(N, d, device=dev)
-    return A.contiguous(), B.contiguous(), K.contiguous(), x0
+    x0 = torch.zeros(n, d, device=dev)
+    return A.contiguous(), B, K.contiguous(), x0
 
 
 def measure_fp32_peak(torch, dev):
@@ -129,19 +152,24 @@ def measure_fp32_peak(torch, dev):
     return out
 
 
+def host_cores():
+    from oracle.lds_c import max_threads
+    # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() obeys,
+    # so count the affinity mask instead and hand the number to omp_set_num_threads() explicitly
+    try:
+        return max(max_threads(), len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(max_threads(), os.cpu_count() or 1)
+
+
 def cpu_baseline(wl, seconds_target=12.0):
     """The oracle's C restatement (oracle/lds_c.c, OpenMP over envs, every host thread) timed on a
     bounded sample of the workload: same step, same distributions, fewer envs and steps."""
     import numpy as np
-    from oracle.lds_c import gpc_rollout_c, max_threads
-    # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() obeys,
-    # so count the affinity mask instead and hand the number to omp_set_num_threads() explicitly
-    try:
-        cores = max(max_threads(), len(os.sched_getaffinity(0)))
-    except AttributeError:
-        cores = max(max_threads(), os.cpu_count() or 1)
+    from oracle.lds_c import gpc_rollout_c
+    cores = host_cores()
     d, m = wl["d"], wl["m"]
-    Nc = 2048 * cores
+    Nc = (2048 if wl["H"] <= 4 else 512) * cores
     rng = np.random.default_rng(0)
     A = np.zeros((Nc, d, d), np.float32)
     A[:, np.arange(d), np.arange(d)] = rng.uniform(0.9, 0.95, (Nc, d))
@@ -162,24 +190,143 @@ def cpu_baseline(wl, seconds_target=12.0):
     dt = sum(run(Tc) for _ in range(reps))
     return {"value": Nc * Tc * reps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
             "seconds": dt, "reps": reps,
-            "sample": f"{reps} x ({Nc} envs x {Tc} steps) of the same LDS+GPC step (oracle/lds_c.c: scalar C, OpenMP "
-                      f"over envs, fp32, {cores} threads), {dt:.1f} s"}
+            "sample": f"{reps} x ({Nc} envs x {Tc} steps) of the same LDS+GPC(H={wl['H']},HH={wl['HH']}) step "
+                      f"(oracle/lds_c.c: scalar C, OpenMP over envs, fp32, {cores} threads), {dt:.1f} s; env-steps/s "
+                      f"is a per-env-step rate, so the bounded sample measures the same quantity as the full job"}
 
 
-def run_reference(args, wl, rank, world):
+def config_of(wl, world, scaling, use_hbm_w):
+    """The `config` object -- identical in both arms, so the driver's ratio compares like with like."""
+    N, T, d = wl["N"], wl["T"], wl["d"]
+    per = N // world if scaling == "strong" else N
+    return {"workload": wl["desc"], "envs_total": N if scaling == "strong" else N * world, "envs_per_gpu": per,
+            "T": T, "d": d, "m": wl["m"], "H": wl["H"], "HH": wl["HH"], "lr_scale": LR_SCALE, "decay": True,
+            "disturbance": "W[T,N,d] resident in HBM (%.1f GB per GPU, larger than L2)" % (per * T * d * 4 / 1e9)
+            if use_hbm_w else "Philox4x32-10 + Box-Muller drawn in-register",
+            "l2": "per-step inputs exceed L2" if use_hbm_w else "L2 flushed between iterations (256 MB write)",
+            "parallelism": f"env-sharded x{world}"}
+
+
+def run_reference(args, wl, rank, world, scaling):
+    """The reference's own algorithm on the host cores (oracle/lds_c.c; the JAX reference is not installable here,
+    SURVEY F2): each step is a bounded sample of the workload, all host threads, rank 0 only."""
     if rank != 0:
         return
     cb = cpu_baseline(wl, seconds_target=min(60.0, 8.0 * max(1, args.steps)))
     line = {"impl": "reference", "metric": "LDS+GPC env-steps/sec", "value": cb["value"], "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * cb["seconds"] / cb["reps"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "note": "reference semantics restated on the CPU (JAX is not "
-                       "installable in this image, SURVEY F2); bounded sample, see cpu_baseline.sample"},
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(wl, max(1, args.gpus), scaling, args.disturbance == "hbm"),
+            "note": "reference semantics restated on the CPU (JAX is not installable in this image, SURVEY F2); each "
+                    "step is a bounded sample of the workload, see cpu_baseline.sample",
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+class Runner:
+    """One workload on this rank's shard: problem set-up, the timed loop, the end-to-end legs."""
+
+    def __init__(self, torch, dist, wl, dev, rank, world, scaling, use_hbm_w, variant):
+        from deluca_b200.fused import gaussian_disturbance
+        from deluca_b200.sharding import shard_range
+        self.torch, self.dist, self.wl, self.dev, self.world = torch, dist, wl, dev, world
+        if scaling == "strong":
+            lo, hi = shard_range(wl["N"], rank, world)
+        else:
+            lo, hi = rank * wl["N"], (rank + 1) * wl["N"]
+        self.lo, self.n = lo, hi - lo
+        self.n_total = wl["N"] if scaling == "strong" else wl["N"] * world
+        self.A, self.B, self.K, self.x0 = make_problem(torch, wl, dev, lo, self.n)
+        self.W = gaussian_disturbance(self.n, wl["T"], wl["d"], seed=SEED, env_offset=lo, std=W_STD,
+                                      device=dev) if use_hbm_w else None
+        self.kw = dict(policy="gpc", H=wl["H"], HH=wl["HH"], lr_scale=LR_SCALE, decay=True, seed=SEED,
+                       env_offset=lo, w_std=W_STD, kernel_variant=variant)
+        self.stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.flush = None
+
+    def sync(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def rollout(self, W):
+        from deluca_b200.fused import lds_rollout
+        return lds_rollout(self.A, self.B, self.K, self.x0, self.wl["T"], W=W, **self.kw)
+
+    def timed(self, steps, warmup, W):
+        """W warm-up steps, then K steps between barriers; per-step kernel time from CUDA events on the launch stream
+        (torch's current stream IS the stream the C ABI launches on).  Returns (total_ms, kern_ms, kern_each), max
+        over ranks.  With in-kernel disturbances no per-step input exceeds L2, so L2 is flushed between iterations."""
+        from deluca_b200.sharding import local_stats, reduce_stats
+        torch = self.torch
+        if W is None and self.flush is None:
+            self.flush = torch.empty(64 << 20, dtype=torch.float32, device=self.dev)
+        flush = self.flush if W is None else None
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r = None
+        for i in range(-max(warmup, 0), steps):
+            if i == 0:
+                self.sync()
+                t0.record()
+            # drop the previous step's outputs first: holding them while the next rollout allocates its cost buffer
+            # makes torch's caching allocator cudaMalloc a second block inside the timed region
+            r = None
+            if flush is not None:
+                flush.zero_()
+            if i >= 0:
+                kev[i][0].record()
+            r = self.rollout(W)
+            if i >= 0:
+                kev[i][1].record()
+            # final statistics [sum cost, sum cost^2, finite envs, non-finite envs], one tiny all-reduce
+            # (NCCL over NVLink) per rollout -- the only collective on this path (SURVEY 8(e))
+            self.stats.copy_(reduce_stats(local_stats(r.cost_sum, r.status)))
+        t1.record()
+        self.sync()
+        total_ms = t0.elapsed_time(t1)
+        each = [a.elapsed_time(b) for a, b in kev]
+        tm = torch.tensor([total_ms, sum(each) / max(steps, 1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(tm, op=self.dist.ReduceOp.MAX)
+        return float(tm[0]), float(tm[1]), each
+
+    def e2e(self, steps, return_losses):
+        """Through the public API with HOST buffers (pinned): per step, A, B, K, x0 host -> device, the fused rollout
+        with disturbances drawn by the env itself (in-kernel Philox; the reference's env draws its own noise too,
+        _lds.py:102-105), and the result device -> host: the full losses[T,N] (what Rollout.losses holds,
+        training/apg.py:68) or the per-env cost sums only."""
+        from deluca_b200.fused import lds_rollout
+        torch = self.torch
+        hA, hB, hK, hx = (t.cpu().pin_memory() for t in (self.A, self.B, self.K, self.x0))
+        T = self.wl["T"]
+        h_out = (torch.empty((T, self.n), dtype=torch.float32) if return_losses
+                 else torch.empty(self.n, dtype=torch.float64)).pin_memory()
+
+        def one():
+            dA, dB, dK, dx = (t.to(self.dev, non_blocking=True) for t in (hA, hB, hK, hx))
+            rr = lds_rollout(dA, dB, dK, dx, T, W=None, keep_costs=return_losses, donate=True, **self.kw)
+            h_out.copy_(rr.costs if return_losses else rr.cost_sum, non_blocking=True)
+
+        one()
+        self.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        self.sync()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        h2d = sum(t.numel() * t.element_size() for t in (hA, hB, hK, hx))
+        d2h = h_out.numel() * h_out.element_size()
+        checksum = float(h_out.double().sum())
+        del h_out
+        return float(ms[0]), h2d, d2h, checksum
 
 
 def main():
@@ -188,12 +335,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="tgt", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
     ap.add_argument("--envs", type=int, default=0, help="override env count (testing)")
     ap.add_argument("--horizon", type=int, default=0, help="override T (testing)")
     ap.add_argument("--disturbance", default="hbm", choices=["hbm", "kernel"],
                     help="hbm: W[T,N,d] resident in HBM before timing; kernel: Philox drawn in-register")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] sub-record")
+    ap.add_argument("--no-e2e-losses", action="store_true", help="skip the e2e leg that returns losses[T,N]")
     ap.add_argument("--variant", type=int, default=0, help="DlcLdsParams.kernel_variant (0 = auto)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -201,16 +351,18 @@ def main():
         wl["N"] = args.envs
     if args.horizon:
         wl["T"] = args.horizon
+    overridden = bool(args.envs or args.horizon)
+    scaling = wl["scaling"] if args.scaling == "auto" else args.scaling
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, wl, rank, world)
+        return run_reference(args, wl, rank, world, scaling)
 
     import torch
     import torch.distributed as dist
     from deluca_b200 import _abi
-    from deluca_b200.fused import gaussian_disturbance, lds_rollout
+    from deluca_b200.sharding import summarize
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
@@ -221,88 +373,55 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    N, T, d, m, H, HH = (wl[k] for k in ("N", "T", "d", "m", "H", "HH"))
-    env_offset = rank * N  # weak scaling: every rank owns N envs of a world*N-env job
-    A, B, K, x0 = make_problem(torch, wl, dev, rank)
     use_hbm_w = args.disturbance == "hbm"
-    W = gaussian_disturbance(N, T, d, seed=SEED, env_offset=env_offset, std=W_STD, device=dev) if use_hbm_w else None
-    kw = dict(policy="gpc", H=H, HH=HH, lr_scale=LR_SCALE, decay=True, seed=SEED, env_offset=env_offset, w_std=W_STD,
-              kernel_variant=args.variant)
-    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    d, m, H, HH, T = (wl[k] for k in ("d", "m", "H", "HH", "T"))
 
-    from deluca_b200.sharding import local_stats, reduce_stats, summarize
-
-    def step():
-        r = lds_rollout(A, B, K, x0, T, W=W, **kw)
-        # final statistics [sum cost, sum cost^2, finite envs, non-finite envs], one tiny all-reduce
-        # (NCCL over NVLink) per rollout -- the only collective on this path
-        stats.copy_(reduce_stats(local_stats(r.cost_sum, r.status)))
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # the clock sampler (nvidia-smi -lms) is started BEFORE the warm-up: its first query on a fresh box
+    # the clock sampler (nvidia-smi -lms) is started BEFORE set-up and warm-up: its first query on a fresh box
     # takes long enough to stall a kernel, which must not land inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 0)):
-        step()
-    # ---- timed region: K steps; kernel time on the launch stream via CUDA events
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync()
-    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_all0.record()
-    torch.cuda.nvtx.range_push("dlc_timed")
-    r = None
-    for i in range(args.steps):
-        # drop the previous step's outputs first: holding them while the next rollout allocates its
-        # 2.6 GB cost buffer makes torch's caching allocator cudaMalloc a second block inside the timed
-        # region (seen as a one-off +25..85 ms "kernel" time on the second step)
-        r = None
-        kev[i][0].record()
-        r = lds_rollout(A, B, K, x0, T, W=W, **kw)
-        kev[i][1].record()
-        stats.copy_(reduce_stats(local_stats(r.cost_sum, r.status)))
-    torch.cuda.nvtx.range_pop()
-    t_all1.record()
-    sync()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = t_all0.elapsed_time(t_all1)
-    kern_each = [a.elapsed_time(b) for a, b in kev]
-    kern_ms = sum(kern_each) / max(args.steps, 1)
-    tm = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms = float(tm[0]), float(tm[1])
-    st = stats.cpu().tolist()
+    run = Runner(torch, dist, wl, dev, rank, world, scaling, use_hbm_w, args.variant)
+    n_loc, n_tot = run.n, run.n_total
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    hA, hB, hK, hx = (t.cpu().pin_memory() for t in (A, B, K, x0))
-    h_out = torch.empty(N, dtype=torch.float64).pin_memory()
-    kw_e2e = dict(kw)
-    def e2e_step():
-        dA, dB, dK, dx = (t.to(dev, non_blocking=True) for t in (hA, hB, hK, hx))
-        rr = lds_rollout(dA, dB, dK, dx, T, W=None, keep_costs=False, donate=True, **kw_e2e)
-        h_out.copy_(rr.cost_sum, non_blocking=True)
-    e2e_step(); sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(1, min(args.steps, 3))
-    e0.record()
-    for _ in range(n_e2e):
-        e2e_step()
-    e1.record()
-    sync()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1) / n_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms[0])
-    h2d = sum(t.numel() * t.element_size() for t in (hA, hB, hK, hx))
-    d2h = h_out.numel() * h_out.element_size()
+    # ---- timed region: K steps of the headline variant
+    t_from = sampler.mark()
+    total_ms, kern_ms, kern_each = run.timed(args.steps, args.warmup, run.W)
+    t_to = sampler.mark()
+    stats = run.stats.cpu()
+
+    # ---- the same job with the disturbances drawn by the env in the kernel (the variant the e2e legs run), device-timed
+    n_side = max(1, min(args.steps, 3))
+    rng_ms = stats_rng = None
+    if use_hbm_w:
+        _, rng_ms, _ = run.timed(n_side, 1, None)
+        stats_rng = run.stats.cpu()
+    # ---- end to end, host buffers, copies inside the timed region
+    run.W = None            # free the resident disturbances before pinning host memory for the losses
+    torch.cuda.empty_cache()
+    e2e_sum_ms, h2d_s, d2h_s, chk_s = run.e2e(n_side, return_losses=False)
+    if args.no_e2e_losses:
+        e2e_ms, h2d, d2h, chk = e2e_sum_ms, h2d_s, d2h_s, chk_s
+    else:
+        e2e_ms, h2d, d2h, chk = run.e2e(n_side, return_losses=True)
+
+    # ---- BASELINE.json configs[1] (the round-1 headline) as a sub-record, N = 1 only
+    c2 = None
+    if rank == 0 and world == 1 and args.workload == "tgt" and not overridden and not args.no_c2:
+        del run
+        torch.cuda.empty_cache()
+        w2 = dict(WORKLOADS["c2"])
+        r2 = Runner(torch, dist, w2, dev, 0, 1, "weak", True, 0)
+        c2_total, c2_kern, _ = r2.timed(3, 2, r2.W)
+        c2 = {"workload": w2["desc"], "steps": 3, "warmup": 2, "value": w2["N"] * w2["T"] * 3 / (c2_total * 1e-3),
+              "unit": "env-steps/s", "kernel_ms": c2_kern, "ms_per_step": c2_total / 3,
+              "flops_per_env_step": flops_per_env_step(w2["d"], w2["m"], w2["H"]),
+              "stats": summarize(r2.stats.cpu(), w2["T"])}
+        del r2
+        torch.cuda.empty_cache()
 
     if rank == 0:
+        clocks = sampler.stop(t_from, t_to)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -312,40 +431,52 @@ def main():
         fp32_peak = max(fp32.values())
         F = flops_per_env_step(d, m, H)
         Bts = bytes_per_env_step(d, m, H, T, use_hbm_w)
-        ach = F * N * T / (kern_ms * 1e-3) / 1e12
+        # roofline of the dominant kernel on ONE GPU's shard (kern_ms is the max over ranks)
+        ach = F * n_loc * T / (kern_ms * 1e-3) / 1e12
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = NCU_TRAFFIC.get((args.workload, args.disturbance)) if (not overridden and world == 1) else None
+        kname = ("lds_gpc_quad_kernel" if H > 4 else "lds_f2_kernel") if args.variant == 0 else f"kernel_variant {args.variant}"
         line = {
-            "metric": "LDS+GPC env-steps/sec", "value": world * N * T * args.steps / (total_ms * 1e-3),
+            "metric": "LDS+GPC env-steps/sec", "value": n_tot * T * args.steps / (total_ms * 1e-3),
             "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": total_ms / max(args.steps, 1), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "envs_per_gpu": N, "T": T, "d": d, "m": m, "H": H, "HH": HH,
-                       "lr_scale": LR_SCALE, "decay": True,
-                       "disturbance": "W[T,N,d] resident in HBM (%.1f GB, larger than L2)" % (N * T * d * 4 / 1e9)
-                       if use_hbm_w else "Philox4x32-10 + Box-Muller drawn in-register",
-                       "l2": "per-step inputs exceed L2" if use_hbm_w else "state is on-chip; costs written once",
-                       "parallelism": f"env-sharded x{world}"},
+            "config": config_of(wl, world, scaling, use_hbm_w),
             "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": ach / fp32_peak if fp32_peak else None,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.disturbance))
-                         if not (args.envs or args.horizon) else None,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_lds_f2_32x9_full.txt)",
-                         "algorithmic_bytes": Bts * N * T,
-                         "kernel": "lds_f2_kernel" if args.variant in (0, 8, 9, 10, 11, 12) else "lds_split_kernel", "kernel_ms": kern_ms,
+                         "traffic": traffic[0] if traffic else None,
+                         "traffic_unit": ("bytes per launch (ncu dram read+write, %s)" % traffic[1]) if traffic else None,
+                         "algorithmic_bytes": Bts * n_loc * T,
+                         "kernel": kname, "kernel_ms": kern_ms,
                          "kernel_ms_each": [round(v, 3) for v in kern_each],
-                         "flops_per_env_step": F, "bytes_per_env_step": Bts,
+                         "flops_per_env_step": F, "bytes_per_env_step": Bts, "envs_per_launch": n_loc,
                          "peak_source": "measured live: dlc_microbench_f32 (FFMA %.1f, FFMA2 %.1f TFLOP/s); "
                                         "MEASURED_PEAKS.json has no FP32 non-tensor peak" % (fp32["ffma"], fp32["ffma2"]),
-                         "hbm": {"achieved": Bts * N * T / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "hbm": {"achieved": Bts * n_loc * T / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}},
-            "e2e": {"value": world * N * T / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                    "note": "host A,B,K,x0 (pinned) -> device, fused rollout with in-kernel disturbances, "
-                            "per-env cost sums -> host"},
+            "e2e": {"value": n_tot * T / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "result_checksum": chk,
+                    "note": "per step: host A,B,K,x0 (pinned) -> device; fused rollout, disturbances drawn by the env "
+                            "in the kernel (the reference's LDS draws its own noise too); the full losses[T,N] "
+                            "(Rollout.losses) -> pinned host.  `value` differs only in reading the same disturbance "
+                            "stream from HBM; `value_kernel_rng` is this leg's kernel variant timed on the device."
+                            if not args.no_e2e_losses else "cost sums only (--no-e2e-losses)"},
+            "e2e_cost_sums_only": {"value": n_tot * T / (e2e_sum_ms * 1e-3), "unit": "env-steps/s",
+                                   "h2d_bytes_per_step": h2d_s, "d2h_bytes_per_step": d2h_s, "ms_per_step": e2e_sum_ms,
+                                   "result_checksum": chk_s,
+                                   "note": "as e2e, but no per-step losses are stored: per-env cost sums (fp64) -> host"},
             "gpu_launches": args.steps,
             "clocks": clocks,
-            "stats": summarize(stats.cpu(), T),
+            "stats": summarize(stats, T),
         }
+        if rng_ms is not None:
+            line["value_kernel_rng"] = {"value": n_tot * T / (rng_ms * 1e-3), "unit": "env-steps/s", "kernel_ms": rng_ms,
+                                        "note": "device-timed, disturbances drawn in the kernel, costs[T,N] stored, L2 "
+                                                "flushed between iterations", "stats": summarize(stats_rng, T)}
+        if c2 is not None:
+            c2["roofline_frac"] = (c2["flops_per_env_step"] * 65536 * 10000 / (c2["kernel_ms"] * 1e-3) / 1e12
+                                   / fp32_peak) if fp32_peak else None
+            line["c2"] = c2
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line), flush=True)

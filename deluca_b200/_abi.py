@@ -40,6 +40,8 @@ class DlcLdsParams(ctypes.Structure):
         ("kernel_variant", ctypes.c_int32),
         ("mode", ctypes.c_int32),
         ("seed", ctypes.c_uint64),
+        ("env_t0", ctypes.c_int32),
+        ("pad_", ctypes.c_int32),
     ]
 
 
@@ -71,8 +73,8 @@ class DlcOfParams(ctypes.Structure):
         ("n", ctypes.c_int32), ("p", ctypes.c_int32), ("agent", ctypes.c_int32), ("m", ctypes.c_int32),
         ("h", ctypes.c_int32), ("F", ctypes.c_int32), ("L", ctypes.c_int32), ("t0", ctypes.c_int32),
         ("decay", ctypes.c_int32), ("shared_dynamics", ctypes.c_int32), ("mode", ctypes.c_int32),
-        ("lr", ctypes.c_float), ("R_M", ctypes.c_float), ("w_std", ctypes.c_float), ("reserved", ctypes.c_int32),
-        ("seed", ctypes.c_uint64),
+        ("lr", ctypes.c_float), ("R_M", ctypes.c_float), ("w_std", ctypes.c_float), ("lanes_per_env", ctypes.c_int32),
+        ("seed", ctypes.c_uint64), ("flags", ctypes.c_int32), ("env_t0", ctypes.c_int32),
     ]
 
 

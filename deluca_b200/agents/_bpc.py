@@ -29,13 +29,15 @@ class BPCState(Obj):
 
 class BPC(Agent):
     def __init__(self, A, B, Q=None, R=None, K=None, start_time=0, H=5, lr_scale=0.005, decay=False, delta=0.01,
-                 seed=0):
-        as_t = lambda a: torch.as_tensor(a, dtype=torch.float32).contiguous()
+                 seed=0, device=None):
+        dev = torch.device(device) if device is not None else (
+            A.device if isinstance(A, torch.Tensor) and A.is_cuda else torch.device("cuda"))
+        as_t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(dev).contiguous()
         self.A, self.B = as_t(A), as_t(B)
         self.d_state, self.d_action = self.B.shape[-2], self.B.shape[-1]
         self.t, self.H = 0, H
         self.lr_scale, self.decay, self.delta = lr_scale, decay, delta
-        self.K = as_t(K) if K is not None else LQR(self.A, self.B, Q, R).K
+        self.K = as_t(K) if K is not None else LQR(self.A, self.B, as_t(Q), as_t(R)).K
         self.seed = seed
         self._st = None
 

@@ -76,7 +76,9 @@ class DRC(Agent):
 
     def rollout(self, x, T, W=None, st=None, **kw):
         st = st or self.init(x.shape[0])
-        return fused.lds_of_rollout(self.A, self.B, self.C, x, T, W=W, **self._kw(st), **kw)
+        args = dict(self._kw(st), W=W)
+        args.update(kw)   # the caller's keywords (t0, lr, env_t0, ...) override the agent's own
+        return fused.lds_of_rollout(self.A, self.B, self.C, x, T, **args)
 
     def __call__(self, obs):
         st = DRCState(M=self.M.unsqueeze(0).contiguous(), y_nat=self.y_nat.reshape(1, self.m, self.p).contiguous(),

@@ -28,10 +28,13 @@ class GPCState(Obj):
 
 class GPC(Agent):
     def __init__(self, A, B, Q=None, R=None, K=None, start_time=0, cost_fn=None, H=3, HH=2, lr_scale=0.005,
-                 decay=True, noise_uses_prev_action=False):
+                 decay=True, noise_uses_prev_action=False, device=None):
         if cost_fn is not None and cost_fn is not quad_loss:
             raise NotImplementedError("the fused kernel implements the reference's default quad_loss only")
-        as_t = lambda a: torch.as_tensor(a, dtype=torch.float32).contiguous()
+        # numpy / CPU inputs (how the reference is normally called) are moved to the device once, here
+        dev = torch.device(device) if device is not None else (
+            A.device if isinstance(A, torch.Tensor) and A.is_cuda else torch.device("cuda"))
+        as_t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(dev).contiguous()
         self.A, self.B = as_t(A), as_t(B)
         self.d_state, self.d_action = self.B.shape[-2], self.B.shape[-1]
         self.t = start_time * 0   # the reference ignores start_time (_gpc.py:82)
@@ -39,8 +42,7 @@ class GPC(Agent):
         self.lr_scale, self.decay = lr_scale, decay
         self.noise_uses_prev_action = noise_uses_prev_action
         self.bias = 0
-        self.K = as_t(K) if K is not None else LQR(self.A, self.B, Q, R).K      # _gpc.py:93
-        dev = self.A.device
+        self.K = as_t(K) if K is not None else LQR(self.A, self.B, as_t(Q), as_t(R)).K      # _gpc.py:93
         st = self.init(1, device=dev)
         self.M = st.M[0]
         self.noise_history = st.noise_history[0].unsqueeze(-1)

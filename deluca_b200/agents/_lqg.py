@@ -53,8 +53,9 @@ class LQG(Agent):
 
     def rollout(self, x, T, W=None, st=None, **kw):
         st = st or self.init(x.shape[0])
-        return fused.lds_of_rollout(self.A, self.B, self.C, x, T, agent="lqg", W=W, K=self.K, Lk=self.L, z=st.x_hat,
-                                    t0=st.t, **kw)
+        args = dict(agent="lqg", W=W, K=self.K, Lk=self.L, z=st.x_hat, t0=st.t)
+        args.update(kw)   # the caller's keywords override the agent's own
+        return fused.lds_of_rollout(self.A, self.B, self.C, x, T, **args)
 
     def __call__(self, y):
         st = LQGState(x_hat=self.x_hat.reshape(1, -1).contiguous(), t=self.t)

@@ -11,8 +11,11 @@ from .. import fused
 
 
 class LQR(Agent):
-    def __init__(self, A, B, Q=None, R=None):
-        as_t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32)
+    def __init__(self, A, B, Q=None, R=None, device=None):
+        # numpy / CPU inputs (how the reference is normally called) are moved to the device once, here
+        dev = torch.device(device) if device is not None else (
+            A.device if isinstance(A, torch.Tensor) and A.is_cuda else torch.device("cuda"))
+        as_t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).to(dev).contiguous()
         A, B = as_t(A), as_t(B)
         self.A, self.B = A, B
         self.K, self.X = dare_gain(A, B, as_t(Q), as_t(R))

@@ -111,10 +111,10 @@ class FilterAgent(Agent):
     def rollout(self, x, T, W=None, st=None, **kw):
         """T fused closed-loop steps on the LDS this agent was built for (the scan x vmap body)."""
         st = st or self.init(x.shape[0])
-        return fused.lds_of_rollout(self.A, self.B, self.C, x, T, agent="fgrc", W=W, Phi=self.Phi, theta=st.theta,
-                                    phi_is_identity=self.kind == "grc",
-                                    z=st.z, ynat=st.ynat_history, m=self.m, t0=st.t, lr=self.lr, decay=self.decay,
-                                    R_M=self.R_M, **kw)
+        args = dict(agent="fgrc", W=W, Phi=self.Phi, theta=st.theta, phi_is_identity=self.kind == "grc", z=st.z,
+                    ynat=st.ynat_history, m=self.m, t0=st.t, lr=self.lr, decay=self.decay, R_M=self.R_M)
+        args.update(kw)   # the caller's keywords (t0, lr, env_t0, lanes_per_env, ...) override the agent's own
+        return fused.lds_of_rollout(self.A, self.B, self.C, x, T, **args)
 
     # ---- stateful face (the reference's)
     def __call__(self, y):

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : 2) lds_gpc_group_kernel(co
           w[k] = a.W[((int64_t)t * p.N + n) * d + row];
         } else {
           float z4[4];
-          normal4(p.seed, env_id, (uint32_t)(p.t0 + t), (uint32_t)(row >> 2), 0u, z4);
+          normal4(p.seed, env_id, (uint32_t)(p.env_t0 + t), (uint32_t)(row >> 2), 0u, z4);
           w[k] = __fmul_rn(p.w_std, pick4g(z4, row & 3));
         }
       }

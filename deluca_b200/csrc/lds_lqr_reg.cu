@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) lds_lqr_reg_kernel(const LdsArgs a) {
 #pragma unroll
       for (int g = 0; g < (D + 3) / 4; ++g) {
         float z[4];
-        normal4(p.seed, env_id, (uint32_t)(p.t0 + t), (uint32_t)g, 0u, z);
+        normal4(p.seed, env_id, (uint32_t)(p.env_t0 + t), (uint32_t)g, 0u, z);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (4 * g + k < D) w[4 * g + k] = __fmul_rn(p.w_std, z[k]);

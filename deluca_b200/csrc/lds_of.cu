@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 
           w[k] = a.W[((size_t)t * P.N + env) * d + row];
         } else {
           float z4[4];
-          normal4(P.seed, genv, (uint32_t)(P.t0 + t), (uint32_t)(row >> 2), 0u, z4);
+          normal4(P.seed, genv, (uint32_t)(P.env_t0 + t), (uint32_t)(row >> 2), 0u, z4);
           w[k] = __fmul_rn(P.w_std, pick4(z4, row & 3));
         }
       }
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
 #pragma unroll
         for (int g = 0; g < (D + 3) / 4; ++g) {
           float z4[4];
-          normal4(Pm.seed, genv, (uint32_t)(Pm.t0 + t), (uint32_t)g, 0u, z4);
+          normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
   const uint32_t genv = (uint32_t)(Pm.env_offset + env);
   double csum = 0.0;
   int status = 0;
-  {   // the caller promised Phi == I (reserved = 1); a broken promise must not pass silently
+  {   // the caller promised Phi == I (DLC_OF_FLAG_PHI_IDENTITY); a broken promise must not pass silently
     bool ident = true;
     for (int i = 0; i < MH * MH; ++i) ident = ident && (__ldg(a.Phi + i) == ((i / MH == i % MH) ? 1.0f : 0.0f));
     if (!ident) {
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
 #pragma unroll
         for (int g = 0; g < (D + 3) / 4; ++g) {
           float z4[4];
-          normal4(Pm.seed, genv, (uint32_t)(Pm.t0 + t), (uint32_t)g, 0u, z4);
+          normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
@@ -968,13 +968,14 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   if (e != cudaSuccess) return cuda_status(e, "cudaGetDevice");
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (p->agent == DLC_OF_LQG && p->d == 10 && p->n == 3 && p->p == 2 && p->reserved == 0) {
-    // the colab's system: register-resident thread-per-env kernel (reserved = 8 / 16 / 32 still forces lane groups)
+  if (p->agent == DLC_OF_LQG && p->d == 10 && p->n == 3 && p->p == 2 && p->lanes_per_env == 0) {
+    // the colab's system: register-resident thread-per-env kernel (lanes_per_env = 8 / 16 / 32 still forces lane groups;
+    // the identity-filter flag means nothing to LQG and is ignored)
     of_lqg_reg_kernel<10, 3, 2><<<(unsigned)((p->N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "of_lqg_reg_kernel launch");
   }
   if (p->agent == DLC_OF_FGRC && p->d == 10 && p->n == 3 && p->p == 2 && p->m == 10 && p->F == 10 && p->L == 10 &&
-      p->reserved == 1) {
+      (p->flags & DLC_OF_FLAG_PHI_IDENTITY) && p->lanes_per_env == 0) {
     // GRC(m = 10) on the colab's system: register-resident thread-per-env kernel
     constexpr int TPB = 64;
     const size_t smem = (size_t)GrcRegLayout<10, 3, 2, 10>::kFloats * TPB * sizeof(float);
@@ -984,7 +985,7 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
     kern<<<(unsigned)((p->N + TPB - 1) / TPB), TPB, smem, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "of_grc_reg_kernel launch");
   }
-  // lanes per env from the widest per-step contraction (reserved = 8 / 16 / 32 overrides)
+  // lanes per env from the widest per-step contraction (lanes_per_env = 8 / 16 / 32 overrides)
   const int width = p->agent == DLC_OF_LQG ? p->d : (p->d > a.FP ? p->d : a.FP);
   int GL = width <= 20 ? 8 : (width <= 48 ? 16 : 32);   // measured: GRC / DRC / LQG 8, SFC (22 wide) 16, DSC 32
   // the default SFC (22 features wide) with compile-time dims is 12 % faster on 8 lanes than on 16 (137.9 vs 154.7 ms)
@@ -992,11 +993,12 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   int widest = p->d > p->n ? p->d : p->n;
   if (p->p > widest) widest = p->p;
   while (2 * GL < widest) GL <<= 1;   // a lane owns at most two rows of a mat-vec
-  if (p->reserved == 8 || p->reserved == 16 || p->reserved == 32) {  // (1 = identity hint: lanes stay automatic)
-    if (2 * p->reserved < widest) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved (lanes per env) must be >= max(d, n, p) / 2");
-    GL = p->reserved;
+  if (p->lanes_per_env == 8 || p->lanes_per_env == 16 || p->lanes_per_env == 32) {
+    if (2 * p->lanes_per_env < widest) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: lanes_per_env must be >= max(d, n, p) / 2");
+    GL = p->lanes_per_env;
   }
-  else if (p->reserved != 0 && p->reserved != 1) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: reserved must be 0, 1 (Phi is the identity), 8, 16 or 32 (lanes per env)");
+  else if (p->lanes_per_env != 0) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: lanes_per_env must be 0 (automatic), 8, 16 or 32");
+  if (p->flags & ~DLC_OF_FLAG_PHI_IDENTITY) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: unknown flag bits");
   // groups of one warp hit the same offsets of their slices at once: a slice stride of GL (mod 32) banks keeps
   // their unit-stride accesses apart
   if (GL < 32) a.S += ((GL - a.S % 32) + 32) % 32;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(TPB) __maxnreg__((65536 / (TPB * MINB)) / 8 * 
       const int g0 = (q * DL) / 4;
       float z[NG * 4];
 #pragma unroll
-      for (int g = 0; g < NG; ++g) normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g0 + g, 0u, z + 4 * g);
+      for (int g = 0; g < NG; ++g) normal4(p.seed, env_id, (uint32_t)(p.env_t0 + t), g0 + g, 0u, z + 4 * g);
       const int off = q * DL - g0 * 4;  // 0..3
 #pragma unroll
       for (int k = 0; k < DL; ++k) {
@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
     } else {
       for (int g = 0; g < (d + 3) / 4; ++g) {
         float z[4];
-        normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g, 0u, z);
+        normal4(p.seed, env_id, (uint32_t)(p.env_t0 + t), g, 0u, z);
         for (int k = 0; k < 4 && g * 4 + k < d; ++k) V(oW, g * 4 + k) = __fmul_rn(p.w_std, z[k]);
       }
     }

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(TPB)
       const int g0 = (q * DL) / 4;
       float z[NG * 4];
 #pragma unroll
-      for (int g = 0; g < NG; ++g) normal4(p.seed, env_id, (uint32_t)(p.t0 + t), g0 + g, 0u, z + 4 * g);
+      for (int g = 0; g < NG; ++g) normal4(p.seed, env_id, (uint32_t)(p.env_t0 + t), g0 + g, 0u, z + 4 * g);
       const int off = q * DL - g0 * 4;
 #pragma unroll
       for (int k = 0; k < DL; ++k) {

@@ -55,7 +55,8 @@ class LdsRolloutResult(dict):
 def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=None, xprev=None,
                 uprev=None, eps=None, eps_new=None, bpc_cost=None, t0=0, lr_scale=0.005, decay=True,
                 noise_uses_prev_action=False, w_std=0.5, seed=0, env_offset=0, bpc_delta=0.01,
-                keep_costs=True, traj_stride=0, kernel_variant=0, donate=False, u_in=None, agent_only=False):
+                keep_costs=True, traj_stride=0, kernel_variant=0, donate=False, u_in=None, agent_only=False,
+                env_t0=None):
     """T fused steps of LDS + LQR/GPC/BPC for N envs (``dlc_lds_rollout_f32``).
 
     A[N,d,d] B[N,d,m] K[N,m,d] (or unbatched = shared by all envs), x[N,d].  State tensors
@@ -64,6 +65,8 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
     untouched and updated copies are returned (the reference's functional convention).
     Returns costs[T,N], cost_sum[N] (fp64), x (final), the new agent state, status[N] and, when
     ``traj_stride`` > 0, sampled trajectories X[T,Ns,d], U[T,Ns,m] of every ``traj_stride``-th env.
+    ``t0`` is the AGENT's step counter (lr decay, BPC perturbation counter), ``env_t0`` the ENV's (``LDS.t``: the
+    counter of the in-kernel disturbance stream; defaults to ``t0``).
     """
     lib = _abi.lib()
     _f32(x, "x")
@@ -107,7 +110,8 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
                           decay=int(bool(decay)), noise_uses_prev_action=int(bool(noise_uses_prev_action)),
                           shared_dynamics=int(shared), traj_stride=max(1, int(traj_stride or 1)),
                           lr_scale=lr_scale, w_std=w_std, bpc_delta=bpc_delta,
-                          kernel_variant=kernel_variant, mode=int(bool(agent_only)), seed=seed)
+                          kernel_variant=kernel_variant, mode=int(bool(agent_only)), seed=seed,
+                          env_t0=int(t0 if env_t0 is None else env_t0))
     ws_bytes = lib.dlc_lds_workspace_bytes(ctypes.byref(p))
     ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -394,7 +398,8 @@ def lds_lqr_value_and_grad(A, B, K, x0, T, W=None, seed=0, env_offset=0, t0=0, w
 
 def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, Phi=None, theta=None, z=None,
                    ynat=None, us=None, m=0, h=0, t0=0, lr=0.005, decay=True, R_M=10.0, seed=0, env_offset=0,
-                   w_std=0.5, agent_only=False, keep_costs=True, keep_actions=True, donate=False, lanes_per_env=0, phi_is_identity=False):
+                   w_std=0.5, agent_only=False, keep_costs=True, keep_actions=True, donate=False, lanes_per_env=0, phi_is_identity=False,
+                   env_t0=None):
     """``dlc_lds_of_rollout_f32``: T fused steps of the partially observed LDS (``deluca/envs/_lds.py:102-111``,
     y = C x) under an output-feedback controller: ``agent`` = "lqg" (``_lqg.py:83-98``; K[.,n,d], Lk[.,d,p],
     z = x_hat), "drc" (``_drc.py:131-203``; theta = M[N,m,n,p], ynat[N,m,p] and us[N,h,n] newest first,
@@ -402,7 +407,8 @@ def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, 
     ynat[N,L+m,p] oldest -> newest).  State tensors default to the agents' construction-time zeros; the returned
     ones (and ``t``) resume the episode.  ``agent_only``: ``Agent.__call__(y)`` with y = ``y_in[T,N,p]``.
     ``lanes_per_env``: 0 (automatic) or 8 / 16 / 32 lanes of a warp per env.  ``phi_is_identity``: the caller's
-    promise that ``Phi`` is the identity (GRC); verified on the device."""
+    promise that ``Phi`` is the identity (GRC); verified on the device.  ``t0``: the agent's step counter (lr decay);
+    ``env_t0``: the env's (counter of the in-kernel disturbance stream; defaults to ``t0``)."""
     shared = A.dim() == 2
     d, n, p = A.shape[-1], B.shape[-1], C.shape[-2]
     if agent_only:
@@ -445,7 +451,8 @@ def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, 
     prm = _abi.DlcOfParams(N=N, env_offset=int(env_offset), T=T, d=d, n=n, p=p, agent=code, m=int(m), h=int(h), F=F,
                            L=L, t0=int(t0), decay=int(bool(decay)), shared_dynamics=int(shared),
                            mode=1 if agent_only else 0, lr=float(lr), R_M=float(R_M), w_std=float(w_std),
-                           reserved=int(lanes_per_env) or int(bool(phi_is_identity)), seed=int(seed))
+                           lanes_per_env=int(lanes_per_env), flags=int(bool(phi_is_identity)), seed=int(seed),
+                           env_t0=int(t0 if env_t0 is None else env_t0))
     costs = torch.empty(T, N, device=dev) if keep_costs else None
     U = torch.empty(T, N, n, device=dev) if keep_actions else None
     cost_sum = torch.zeros(N, dtype=torch.float64, device=dev)

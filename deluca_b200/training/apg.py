@@ -46,7 +46,10 @@ def apg_parallel_rollouts(env, env_start_states, env_init_obs, agent, agent_star
     if W is None and (std is None or std == 0.0):
         W = torch.stack([env.disturbance(env_start_states.t + t, env.key, N=x.shape[0], device=x.device)
                          for t in range(T)]).contiguous()
-    common = dict(W=W, w_std=std or 0.0, seed=env.key, env_offset=env_offset, traj_stride=1)
+    # the ENV's step counter keys the in-kernel disturbance stream; the agent's own counter (s.t) only drives its
+    # learning-rate decay, so chunked rollouts and fresh agents on a continued env neither replay nor skip noise
+    common = dict(W=W, w_std=std or 0.0, seed=env.key, env_offset=env_offset, traj_stride=1,
+                  env_t0=env_start_states.t)
     if isinstance(agent, GPC):
         s = agent_start_states
         r = fused.lds_rollout(env.A, env.B, agent.K.to(x.device), x, T, policy="gpc", H=agent.H, HH=agent.HH, M=s.M,
@@ -107,8 +110,10 @@ def value_and_grad_apg_loss(agent, env, env_start_states, env_init_obs, agent_in
     return value, gK / denom
 
 
-def apg_loss(env, env_start_states, env_init_obs, agent, agent_start_states, unroll_length, loss_func):
-    """Mean loss over the batch and horizon, the forward value of ``apg_loss`` (``apg.py:103-122``)."""
-    ro, _ = apg_parallel_rollouts(env, env_start_states, env_init_obs, agent, agent_start_states, unroll_length,
-                                  loss_func)
+def apg_loss(agent, env, env_start_states, env_init_obs, agent_init_states, unroll_length, loss_func,
+             env_offset=0, disturbances=None):
+    """Mean loss over the batch and horizon, the forward value of ``apg_loss`` (``apg.py:103-122``).  Argument order
+    as in the reference: the agent comes first because ``jax.value_and_grad`` differentiates argument 0."""
+    ro, _ = apg_parallel_rollouts(env, env_start_states, env_init_obs, agent, agent_init_states, unroll_length,
+                                  loss_func, env_offset=env_offset, disturbances=disturbances)
     return ro.losses.mean()

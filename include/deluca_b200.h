@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DLC_ABI_VERSION 1
+#define DLC_ABI_VERSION 2
 
 #define DLC_OK 0
 #define DLC_ERR_ARG (-1)         /* NULL where a buffer is required, negative size, ... */
@@ -100,7 +100,7 @@ typedef struct DlcLdsParams {
   int32_t d, m;        /* state / action dim */
   int32_t H, HH;       /* GPC controller / system history (_gpc.py:53-54); BPC uses H only */
   int32_t policy;      /* DLC_POLICY_* */
-  int32_t t0;          /* agent step counter at entry (lr decay, disturbance counter) */
+  int32_t t0;          /* AGENT step counter at entry: lr decay (_gpc.py:161-162), BPC perturbation counter */
   int32_t decay;       /* GPC: lr = lr_scale/(t+1) (_gpc.py:161-162); BPC: /(t^0.75+1) (_bpc.py:128-129) */
   int32_t noise_uses_prev_action; /* 0 = reference as written (B u_t, _gpc.py:141-142,155); 1 = B u_{t-1} */
   int32_t shared_dynamics;        /* 1: A,B,K are [d,d],[d,m],[m,d] shared by all envs; 0: per env [N,...] */
@@ -113,6 +113,10 @@ typedef struct DlcLdsParams {
                              8..12 = launch shapes of the packed-FFMA2 kernel (128x2, 128x3, 64x5, 32x9, 256x1) */
   int32_t mode;        /* DLC_MODE_*: which half of the loop runs (single-step Env/Agent calls use 1 and 2) */
   uint64_t seed;       /* disturbance / perturbation stream seed */
+  int32_t env_t0;      /* ENV step counter at entry (LDS.t, _lds.py:109): counter of the in-kernel disturbance stream.
+                          Separate from t0 so that a fresh agent on a continued env (or chunked LQR rollouts) neither
+                          replays nor skips noise (ABI version 2) */
+  int32_t pad_;
 } DlcLdsParams;
 
 /* bytes of `workspace` dlc_lds_rollout_f32 needs for these params: 0 when a compile-time-shape kernel takes the call,
@@ -456,18 +460,20 @@ typedef struct DlcOfParams {
   int32_t m;           /* controller history: GRC/SFC/DSC m, DRC m; 0 for LQG */
   int32_t h;           /* DRC: length of the Markov operator / action history (_drc.py:52) */
   int32_t F, L;        /* filter family: number of filters and filter length */
-  int32_t t0;          /* agent step counter at entry (lr decay, disturbance counter) */
+  int32_t t0;          /* AGENT step counter at entry (lr decay) */
   int32_t decay;       /* lr = lr/(t+1) (_grc.py:145); DRC without decay uses lr = 1.0 as written (_drc.py:184) */
   int32_t shared_dynamics; /* 1: A, B, C (and K, Lk) are shared by all envs; 0: per env [N,...] */
   int32_t mode;        /* DLC_MODE_CLOSED_LOOP, or DLC_MODE_AGENT_ONLY: Agent.__call__(y) with y from y_in */
   float lr;            /* GRC/SFC/DSC lr (_grc.py:52), DRC lr_scale (_drc.py:53) */
   float R_M;           /* projection radius R_M (_grc.py:49) / RM (_drc.py:55) */
   float w_std;         /* std of the in-kernel Gaussian disturbance, used when W == NULL */
-  int32_t reserved;    /* 0 = automatic; 1 = the caller asserts Phi == I (GRC), which unlocks the register-resident kernel on
-                          the colab's system (verified on the device: DLC_STATUS_BAD_HINT); 8, 16 or 32 forces that many
-                          lanes per env (tuning / tests) */
+  int32_t lanes_per_env; /* 0 = automatic; 8, 16 or 32 forces that many lanes per env (tuning / tests) */
   uint64_t seed;
+  int32_t flags;       /* DLC_OF_FLAG_*: bit 0 = the caller asserts Phi == I (GRC), which unlocks the register-resident kernel
+                          on the colab's system (verified on the device: DLC_STATUS_BAD_HINT); ignored by LQG / DRC */
+  int32_t env_t0;      /* ENV step counter at entry: counter of the in-kernel disturbance stream (see DlcLdsParams.env_t0) */
 } DlcOfParams;
+#define DLC_OF_FLAG_PHI_IDENTITY 1
 
 /* shared memory one env needs (bytes), 0 for an invalid shape */
 size_t dlc_lds_of_smem_bytes(const DlcOfParams* p);

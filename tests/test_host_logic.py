@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
-    assert lib.dlc_abi_version() == 1
+    assert lib.dlc_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r"\bT (dlc_[a-z0-9_]+)", out))
     assert declared <= exported

@@ -133,3 +133,58 @@ def test_value_and_grad_apg_loss_matches_autograd():
     ls.backward()
     assert abs(float(value) - float(ls)) <= 1e-4 * float(ls)
     assert np.abs(grad.cpu().numpy() - Ks.grad.numpy()).max() <= 2e-3 * np.abs(Ks.grad.numpy()).max() + 1e-5
+
+
+def test_chunked_rollouts_continue_the_noise_stream():
+    """the ENV's step counter keys the in-kernel disturbance stream.  Two T/2 chunks must equal one T
+    rollout for LQR, and for GPC also when the agent is reset mid-way (fresh agent, continued env): the chunks see
+    noise steps [0, T/2) and [T/2, T), never [0, T/2) twice."""
+    from deluca_b200.agents import GPC, LQR
+    from deluca_b200.agents._gpc import quad_loss
+    from deluca_b200.envs import LDS
+    from deluca_b200.fused import gaussian_disturbance
+    from deluca_b200.training.apg import apg_parallel_rollouts
+    rng = np.random.default_rng(3)
+    N, d, m, T = 40, 10, 3, 80
+    A, B, _ = O.lds_default_params(rng, N, d, m)
+    env = LDS()
+    env.init(d_in=m, d_hidden=d, d_out=d, A=A, B=B, C=np.eye(d), key=21)
+    lqr = LQR(env.A, env.B)
+    st, obs = env.reset(N)
+    whole, _ = apg_parallel_rollouts(env, st, obs, lqr, None, T, quad_loss)
+    a, mid = apg_parallel_rollouts(env, st, obs, lqr, None, T // 2, quad_loss)
+    assert mid.t == T // 2
+    b, end = apg_parallel_rollouts(env, mid, None, lqr, None, T // 2, quad_loss)
+    assert end.t == T
+    assert torch.equal(torch.cat([a.losses, b.losses], 1), whole.losses)
+    assert not torch.equal(a.losses, b.losses)
+    # GPC: agent reset mid-way on the continued env == the oracle fed the continuous stream W[0:T]
+    gpc = GPC(env.A, env.B, H=3, HH=10, lr_scale=1e-4)
+    g1, mid = apg_parallel_rollouts(env, st, obs, gpc, gpc.init(N), T // 2, quad_loss)
+    g2, _ = apg_parallel_rollouts(env, mid, None, gpc, gpc.init(N), T // 2, quad_loss)
+    W = gaussian_disturbance(N, T, d, seed=21).cpu().numpy()
+    K = gpc.K.cpu().numpy()
+    r1 = O.rollout_lds(A, B, K, np.zeros((N, d), np.float32), W[:T // 2], "gpc", H=3, HH=10, lr_scale=1e-4,
+                       dtype=np.float64)
+    r2 = O.rollout_lds(A, B, K, r1["x_final"], W[T // 2:], "gpc", H=3, HH=10, lr_scale=1e-4, dtype=np.float64)
+    ref = np.concatenate([r1["costs"], r2["costs"]], 0)
+    got = torch.cat([g1.losses, g2.losses], 1).T.cpu().numpy()
+    rel = np.abs(got - ref) / np.maximum(ref, 1e-2 * ref.mean())
+    assert rel.max() < 1e-4
+
+
+def test_agents_built_from_numpy_inputs():
+    """GPC / BPC / LQR take numpy (CPU) A, B, K the way the reference is called and keep them on the
+    device; the first call must not fail with 'must be a CUDA tensor'."""
+    from deluca_b200.agents import BPC, GPC, LQR
+    rng = np.random.default_rng(4)
+    d, m = 10, 3
+    A, B, _ = O.lds_default_params(rng, 1, d, m)
+    x = (0.1 * rng.standard_normal((d, 1))).astype(np.float32)
+    Kref = O.lqr_gain(A, B)[0]
+    for agent in (LQR(A[0], B[0]), GPC(A[0], B[0], H=3, HH=10), BPC(A[0], B[0], H=3)):
+        assert agent.K.is_cuda and agent.A.is_cuda
+        np.testing.assert_allclose(agent.K.cpu().numpy(), Kref, rtol=1e-4, atol=1e-6)
+        u = agent(x, 0.0) if isinstance(agent, BPC) else agent(x)
+        assert u.is_cuda and u.shape == (m, 1) and torch.isfinite(u).all()
+    np.testing.assert_allclose(LQR(A[0], B[0])(x).cpu().numpy(), -Kref @ x, rtol=1e-5, atol=1e-6)

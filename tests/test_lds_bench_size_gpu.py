@@ -106,6 +106,12 @@ def test_full_size_checksum_and_subset(name, other_variant):
     cs = r.cost_sum.clone()
     status_ok = int((r.status == 0).sum())
     xf = r.x.clone()
+    bad = torch.nonzero(r.status != 0).flatten()[:16]
+    if bad.numel():
+        # GPC-as-written diverges on a few systems even at lr_scale = 1e-4 (tests/test_oracle_lds.py); that must be
+        # the algorithm's behaviour, not the kernel's: the float64 oracle blows up on the same envs
+        bc, _ = _oracle(bench, wl, A[bad], B[bad], K[bad], x0[bad], W[:, bad].contiguous())
+        assert (~np.isfinite(bc.sum(0)) | (np.abs(bc).max(0) > 1e30)).all(), "kernel-only divergence"
     del r
     torch.cuda.empty_cache()
     # an independent kernel (scalar lane-split layout, other summation order) on the same job, in-kernel stream
@@ -116,6 +122,6 @@ def test_full_size_checksum_and_subset(name, other_variant):
     assert float(rel.max()) < RTOL, f"per-env episode cost, kernel vs kernel: {float(rel.max()):.3e}"
     tot_a, tot_b = float(cs[ok].sum()), float(r2.cost_sum[ok].sum())
     assert abs(tot_a - tot_b) <= 1e-6 * abs(tot_a), "all-env checksum"
-    exf = ((r2.x - xf).abs().amax(1) / xf.abs().mean())[ok]
+    exf = ((r2.x - xf).abs().amax(1) / xf[ok].abs().mean())[ok]
     assert float(exf.max()) < RTOL
     print(f"{name}: full size {N} x {T}: checksum {tot_a:.9e} vs {tot_b:.9e}; finite envs {status_ok}")

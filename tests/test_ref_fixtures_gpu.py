@@ -1,0 +1,285 @@
+"""The CUDA kernels against fixtures produced by EXECUTING THE REFERENCE'S OWN FILES (tests/golden/ref_*.npz, made by
+tests/golden/make_ref_fixtures.py on the JAX-semantics shim; B200 only).  Same recorded inputs -> the reference's
+numbers within the north-star tolerance: 1e-4 relative on costs and states (float32 kernels vs the reference run under
+`jax_enable_x64`; the reference's own float32 run is in the fixtures too and is about as far from its float64 run).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-4
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, f"ref_{name}.npz"))
+
+
+def _t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _within(got, ref, rtol=RTOL, floor=None, what=""):
+    """|got - ref| <= rtol * max(|ref|, floor); floor defaults to 1 % of the mean magnitude (relative error of
+    near-zero entries is meaningless)."""
+    got = _np(got) if isinstance(got, torch.Tensor) else np.asarray(got)
+    floor = floor if floor is not None else max(1e-2 * np.abs(ref).mean(), 1e-12)
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), floor)
+    assert err.max() <= rtol, f"{what}: max rel err {err.max():.3e}"
+
+
+# ------------------------------------------------------------------------------------------ LDS + GPC / BPC / LQR
+@pytest.mark.parametrize("case", ["h3", "h10", "h3hh2", "d4", "default_lr", "clamp", "ref_defaults"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_gpc_kernels_match_reference_files(case, variant):
+    from deluca_b200.fused import lds_rollout
+    g = _load("lds")
+    d, m, H, HH, lr, decay, T = g[f"in_gpc_{case}_cfg"]
+    d, m, H, HH, T = int(d), int(m), int(H), int(HH), int(T)
+    A, B, W, K = (g[f"in_gpc_{case}_A"], g[f"in_gpc_{case}_B"], g[f"in_gpc_{case}_W"], g[f"out_gpc_{case}_K"])
+    N = A.shape[0]
+    r = lds_rollout(_t(A), _t(B), _t(K), torch.zeros(N, d, device="cuda"), T, policy="gpc", W=_t(W), H=H, HH=HH,
+                    lr_scale=float(lr), decay=bool(decay), traj_stride=1, kernel_variant=variant)
+    tol = RTOL if case != "default_lr" else 1e-3     # the reference's default lr amplifies (tests/test_oracle_lds.py)
+    _within(r.costs, g[f"out_gpc_{case}_costs"], tol, what="costs")
+    _within(r.X, g[f"out_gpc_{case}_X"][:T], tol, floor=np.abs(g[f"out_gpc_{case}_X"]).mean(), what="X")
+    _within(r.U, g[f"out_gpc_{case}_U"], tol, floor=np.abs(g[f"out_gpc_{case}_U"]).mean(), what="U")
+    _within(r.x, g[f"out_gpc_{case}_X"][T], tol, floor=np.abs(g[f"out_gpc_{case}_X"]).mean(), what="x_final")
+    _within(r.M, g[f"out_gpc_{case}_M"], 10 * tol, floor=np.abs(g[f"out_gpc_{case}_M"]).max() * 1e-1, what="M")
+    _within(r.hist, g[f"out_gpc_{case}_hist"], tol, floor=np.abs(g[f"out_gpc_{case}_hist"]).mean(), what="hist")
+    # the kernel is no farther from the reference's float64 run than the reference's own float32 run (x20)
+    e_ref = np.abs(g[f"out_gpc_{case}_costs_f32"] - g[f"out_gpc_{case}_costs"]).max()
+    e_k = np.abs(_np(r.costs) - g[f"out_gpc_{case}_costs"]).max()
+    assert e_k <= 20 * e_ref + 1e-6 * np.abs(g[f"out_gpc_{case}_costs"]).max()
+
+
+def test_lqr_gain_and_kernel_match_reference_files():
+    from deluca_b200.fused import lds_rollout
+    from deluca_b200.riccati import dare_gain
+    g = _load("lds")
+    A, B, W, Q, R = (g[k] for k in ("in_lqr_A", "in_lqr_B", "in_lqr_W", "in_lqr_Q", "in_lqr_R"))
+    K = dare_gain(_t(A), _t(B), _t(Q), _t(R))[0]
+    _within(K, g["out_lqr_K"], 1e-5, floor=np.abs(g["out_lqr_K"]).mean(), what="K (batched doubling vs scipy DARE)")
+    N, d = A.shape[:2]
+    for variant in (0, 1):
+        r = lds_rollout(_t(A), _t(B), K.contiguous(), torch.zeros(N, d, device="cuda"), W.shape[0], policy="lqr",
+                        W=_t(W), traj_stride=1, kernel_variant=variant)
+        _within(r.costs, g["out_lqr_costs"], what="costs")
+        _within(r.X, g["out_lqr_X"][:-1], floor=np.abs(g["out_lqr_X"]).mean(), what="X")
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_bpc_kernels_match_reference_files(variant):
+    from deluca_b200.fused import lds_rollout
+    g = _load("lds")
+    d, m, H, lr, delta, T = g["in_bpc_cfg"]
+    d, m, H, T = int(d), int(m), int(H), int(T)
+    for n in range(g["in_bpc_A"].shape[0]):           # odd envs ran with decay=True: one call per env
+        s = slice(n, n + 1)
+        r = lds_rollout(_t(g["in_bpc_A"][s]), _t(g["in_bpc_B"][s]), _t(g["out_bpc_K"][s]), torch.zeros(1, d, device="cuda"),
+                        T, policy="bpc", W=_t(g["in_bpc_W"][:, s]), H=H, M=_t(g["in_bpc_M0"][s]), eps=_t(g["in_bpc_eps0"][s]),
+                        eps_new=_t(g["in_bpc_eps_new"][:, s]), lr_scale=float(lr), decay=(n % 2 == 1),
+                        bpc_delta=float(delta), traj_stride=1, kernel_variant=variant)
+        _within(r.costs, g["out_bpc_costs"][:, s], what="costs")
+        _within(r.X, g["out_bpc_X"][:T, s], floor=np.abs(g["out_bpc_X"]).mean(), what="X")
+        _within(r.M, g["out_bpc_M"][s], 1e-3, floor=np.abs(g["out_bpc_M"]).max() * 1e-1, what="M")
+
+
+def test_open_lds_kernel_matches_reference_files():
+    from deluca_b200.fused import lds_open_rollout
+    g = _load("lds")
+    A, B, C, U, W = (g[k] for k in ("in_open_A", "in_open_B", "in_open_C", "in_open_U", "in_open_W"))
+    x, Y, _ = lds_open_rollout(_t(A), _t(B), _t(C), torch.zeros(A.shape[0], A.shape[1], device="cuda"), U.shape[0],
+                               u_in=_t(U), W=_t(W))
+    _within(Y, g["out_open_Y"], floor=np.abs(g["out_open_Y"]).mean(), what="Y")
+    _within(x, g["out_open_x"], floor=np.abs(g["out_open_x"]).mean(), what="x")
+
+
+# ------------------------------------------------------------------------------------------ lung
+@pytest.mark.parametrize("sim,kw", [("balloon", {}), ("delay", {}), ("balloon_leak", dict(leak=True))])
+def test_lung_kernel_matches_reference_files(sim, kw):
+    """The fused ventilator episode against `run_controller_scan` executed literally.  The kernel computes in float32
+    with the reference's float32 waveform knot (`3 - 1e-8 == 3`), so it is held to the reference's float32 run:
+    1e-4 relative for the whole default horizon T = 29, and at T = 150 per breath up to the first step at which the
+    kernel and the reference take different sides of `pressure > peep_valve` -- where the pressure must sit within
+    rounding of the valve threshold."""
+    from deluca_b200.lung.controllers import PID
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung, DelayLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    g = _load("lung")
+    gains, pips = g["in_gains"], g["in_pips"]
+    K = np.repeat(gains, len(pips), axis=0).astype(np.float32)
+    pip = np.tile(pips, len(gains)).astype(np.float32)
+    env = (DelayLung if sim == "delay" else BalloonLung).create(**kw)
+    for T in (29, 150):
+        wave = BreathWaveform.create(pip=torch.tensor(pip), peep=5.0)
+        res = run_controller_scan(PID.create(params=torch.tensor(K)), T=T, env=env, waveform=wave, init_controller=True)
+        flipped = 0
+        for k in ("timestamp", "u_out", "target", "flow", "pressure", "u_in"):
+            ref = g[f"out_{sim}_T{T}_{k}_f32"].reshape(-1, T)
+            got = _np(res["timeseries"][k])
+            scale = max(np.abs(ref).max(), 1.0)
+            ok = np.abs(got - ref) <= RTOL * scale
+            if T == 29:
+                assert ok.all(), (k, np.abs(got - ref).max())
+                continue
+            if k in ("timestamp", "u_out", "target", "flow"):
+                assert ok.all(), (k, np.abs(got - ref).max())     # these do not depend on the lung state
+                continue
+            p_ref = g[f"out_{sim}_T{T}_pressure_f32"].reshape(-1, T)
+            for n in range(ref.shape[0]):
+                bad = np.nonzero(~ok[n])[0]
+                if bad.size == 0:
+                    continue
+                # the first disagreement must be a valve-branch flip: the pressure that was compared with
+                # peep_valve = 5 one step earlier is within rounding of it in the reference's run
+                t0 = int(bad[0])
+                near = np.abs(p_ref[n, max(t0 - 2, 0):t0 + 1] - 5.0).min()
+                assert near <= 5e-3, (k, n, t0, near)
+                flipped += 1
+        if T == 150:
+            print(f"{sim}: breaths that left the reference's branch within 150 steps: {flipped // 2} of {K.shape[0]}")
+    # test_controller's score at the reference's horizon (float64 literal run)
+    wave = BreathWaveform.create(pip=torch.tensor(pip), peep=5.0)
+    res = run_controller_scan(PID.create(params=torch.tensor(K)), T=29, env=env, waveform=wave, init_controller=True)
+    score = _np((res["timeseries"]["pressure"] - res["timeseries"]["target"]).abs().mean(1)).reshape(len(gains), len(pips)).mean(1)
+    np.testing.assert_allclose(score, g[f"out_{sim}_score_f32"], rtol=1e-4)
+
+
+def test_generic_pid_kernel_matches_reference_files():
+    from deluca_b200.fused import pid_rollout
+    g = _load("lung")
+    err = _t(g["in_pid_err"].reshape(-1, 1))
+    kp, ki, kd = (_t([v]) for v in g["in_pid_gains"])
+    z = torch.zeros(1, device="cuda")
+    u, P, I, D = pid_rollout(kp, ki, kd, err, z, z.clone(), z.clone(), 0.03 / 0.53)
+    _within(u[:, 0], g["out_pid_u"], floor=np.abs(g["out_pid_u"]).mean(), what="u")
+    _within(torch.stack([P, I, D])[:, 0], g["out_pid_state"], floor=1e-2, what="state")
+
+
+# ------------------------------------------------------------------------------------------ classic envs, deluca/igpc
+def _env(name, H):
+    from deluca_b200.envs.classic import Pendulum, PlanarQuadrotor, QuadCost, Reacher
+    from deluca_b200.envs.classic._planar_quadrotor import constant
+    if name == "pendulum":
+        return Pendulum.create(H=H), QuadCost([0.0, -1.0, 0.0], 1.0, 0.1)
+    if name == "reacher":
+        return Reacher.create(H=H), QuadCost([0.0] * 6, 1.0, 0.1)
+    wind = {"quad": 0.0, "quad_wind": 0.3, "quad_const": 0.2}[name]
+    env = PlanarQuadrotor.create(H=H, wind=wind, **({"wind_func": constant} if name == "quad_const" else {}))
+    return env, QuadCost([0.0] * 6, 1.0, 0.1, goal_action=[0.4905, 0.4905])
+
+
+@pytest.mark.parametrize("name", ["pendulum", "quad", "quad_wind", "quad_const", "reacher"])
+def test_classic_env_kernels_match_reference_files(name):
+    from deluca_b200.envs.classic import PendulumState
+    from deluca_b200.igpc.rollout import rollout
+    c = _load("classic")
+    x0, U, X = c[f"in_{name}_x0"], c[f"in_{name}_U"], c[f"out_{name}_X"]
+    T = U.shape[0]
+    env, cost = _env(name, T)
+    Xk, _, _ = rollout(env, cost, _t(np.swapaxes(U, 0, 1)), start_state=PendulumState(arr=_t(x0)))
+    got = np.swapaxes(_np(Xk), 0, 1)
+    # 1e-4 on a short horizon; over the whole rollout no farther from the reference's float64 run than its own
+    # float32 run (x20) -- the pendulum map is expansive (BASELINE.json: short horizons for chaotic envs)
+    _within(got[:6], X[:6], floor=np.abs(X).mean(), what="X[:6]")
+    e_ref = np.abs(c[f"out_{name}_X_f32"] - X).max()
+    assert np.abs(got - X).max() <= 20 * e_ref + 1e-5 * np.abs(X).max()
+
+
+@pytest.mark.parametrize("name", ["quad", "quadc", "pend"])
+def test_igpc_kernels_match_reference_files(name):
+    """rollout / linearise / Riccati / GPC_rollout / iLQR / iGPC_closed / iLC_closed kernels vs the literal run of
+    deluca/igpc (one trajectory, H = 24, 4 outer iterations)."""
+    from deluca_b200.envs.classic import Pendulum, PlanarQuadrotor, QuadCost
+    from deluca_b200.igpc.igpc import GPC_rollout, iGPC_closed
+    from deluca_b200.igpc.ilc import iLC_closed
+    from deluca_b200.igpc.ilqr import iLQR
+    from deluca_b200.igpc.lqr_solver import LQR
+    from deluca_b200.igpc.rollout import compute_ders, rollout
+    g = _load("igpc")
+    H, T = g[f"out_{name}_X"].shape[0] - 1, 4
+    if name == "pend":
+        et, es = Pendulum.create(H=H, g=9.0), Pendulum.create(H=H)
+        cost = QuadCost([0.0, -1.0, 0.0], 1.0, 0.1)
+    else:
+        from deluca_b200.envs.classic._planar_quadrotor import constant
+        kw = {"wind_func": constant} if name == "quadc" else {}
+        et, es = PlanarQuadrotor.create(H=H, wind=0.1, **kw), PlanarQuadrotor.create(H=H)
+        cost = QuadCost([0.0] * 6, 1.0, 0.1, goal_action=[0.4905, 0.4905])
+    ref = lambda key: g[f"out_{name}_{key}"]
+    U0 = _t(g[f"in_{name}_U0"])
+    X, U, c = rollout(es, cost, U0)
+    _within(X, ref("X"), floor=np.abs(ref("X")).mean(), what="X"); _within(c, ref("c"), what="c")
+    D, F, C = compute_ders(es, cost, _t(ref("X")), U0)
+    for got, key in ((F[0], "Fx"), (F[1], "Fu"), (C[0], "cx"), (C[1], "cu"), (C[2], "cxx"), (C[3], "cuu")):
+        _within(got, ref(key), floor=max(np.abs(ref(key)).max() * 1e-2, 1e-6), what=key)
+    k, K = LQR(tuple(_t(ref(x)) for x in ("Fx", "Fu")), tuple(_t(ref(x)) for x in ("cx", "cu", "cxx", "cuu")))
+    _within(K, ref("K"), 2e-3, floor=np.abs(ref("K")).max() * 1e-1, what="K")
+    _within(k, ref("k"), 2e-3, floor=max(np.abs(ref("k")).max() * 1e-1, 1e-6), what="k")
+    X1, U1, c1 = rollout(es, cost, U0, _t(ref("k")), _t(ref("K")), _t(ref("X")), alpha=0.5)
+    _within(c1, ref("c1"), 1e-3, what="c1")
+    Xi, Ui, _, _, ci = iLQR(es, cost, U0, T)
+    _within(ci, ref("ilqr_c"), 1e-3, what="iLQR cost")
+    for w_is in ("de", "dede", "delin"):
+        Dg, Fg, Cg = compute_ders(es, cost, _t(ref("ilqr_X")), _t(ref("ilqr_U")))
+        kg, Kg = LQR(Fg, Cg)
+        Xg, Ug, cg = GPC_rollout(et, es, cost, _t(ref("ilqr_U")), kg, Kg, _t(ref("ilqr_X")), None, None, 0.6, w_is, 0.05)
+        _within(cg, ref(f"gpc_{w_is}_c"), 1e-3, what=f"GPC_rollout {w_is} cost")
+        _within(Xg, ref(f"gpc_{w_is}_X"), 2e-3, floor=np.abs(ref(f"gpc_{w_is}_X")).mean(), what=f"GPC_rollout {w_is} X")
+    cc = iGPC_closed(et, es, cost, U0, T, lr=0.05)[4]
+    _within(cc, ref("igpc_c"), 2e-3, what="iGPC_closed cost")
+    cl = iLC_closed(et, es, cost, U0, T)[4]
+    _within(cl, ref("ilc_c"), 2e-3, what="iLC_closed cost")
+
+
+# ------------------------------------------------------------------------------------------ output-feedback agents
+def test_output_feedback_kernels_match_reference_files():
+    from deluca_b200.fused import lds_of_rollout
+    from oracle import of as F   # (filter bank layout only; numbers come from the fixtures)
+    g = _load("of")
+    A, B, C, W, x0 = (_t(g[k]) for k in ("in_A", "in_B", "in_C", "in_W", "in_x0"))
+    N = A.shape[0]
+    T = W.shape[0]
+
+    def check(r, name):
+        _within(r.costs, g[f"out_{name}_costs"], what=f"{name} costs")
+        _within(r.U, g[f"out_{name}_U"], floor=np.abs(g[f"out_{name}_U"]).mean(), what=f"{name} U")
+        _within(r.x, g[f"out_{name}_x"], floor=np.abs(g[f"out_{name}_x"]).mean(), what=f"{name} x")
+
+    for name, kw in (("grc", dict(m=5, lr=0.002, decay=True, R_M=10.0)), ("grc_proj", dict(m=5, lr=0.05, R_M=2.0, decay=False))):
+        Phi, _ = F.filter_bank("grc", 5)
+        r = lds_of_rollout(A, B, C, x0, T, agent="fgrc", W=W, Phi=_t(Phi), theta=_t(g[f"in_{name}_M"]), **kw)
+        check(r, name)
+        _within(r.theta, g[f"out_{name}_Mf"], 1e-3, floor=np.abs(g[f"out_{name}_Mf"]).max() * 1e-1, what="theta")
+    Phi, _ = F.filter_bank("sfc", 8, 4)
+    theta0 = np.concatenate([g["in_sfc_M_0"][:, None], g["in_sfc_M"]], axis=1)
+    check(lds_of_rollout(A, B, C, x0, T, agent="fgrc", W=W, Phi=_t(Phi), theta=_t(theta0), m=8, lr=0.002), "sfc")
+    Phi, _ = F.filter_bank("dsc", 6, 3)
+    theta0 = np.stack([F.dsc_pack_theta(*(g[f"in_dsc_M_{i}"][e] for i in range(4))) for e in range(N)])
+    check(lds_of_rollout(A, B, C, x0, T, agent="fgrc", W=W, Phi=_t(Phi), theta=_t(theta0), m=6, lr=0.002), "dsc")
+    for name, kw in (("drc", dict(decay=True, R_M=1000.0)), ("drc_nodecay", dict(decay=False, R_M=0.5))):
+        r = lds_of_rollout(A, B, C, x0, T, agent="drc", W=W, K=_t(g["in_drc_K"]), theta=_t(g[f"in_{name}_M"]), m=4, h=6,
+                           lr=0.03, **kw)
+        check(r, name)
+    r = lds_of_rollout(A, B, C, x0, T, agent="lqg", W=W, K=_t(g["in_lqg_K"]), Lk=_t(g["in_lqg_L"]))
+    check(r, "lqg")
+
+
+def test_gae_kernel_matches_reference_file():
+    from deluca_b200.fused import gae
+    g = _load("drivers")
+    # the reference's gae_advantages is time-major [actor_steps, num_agents] (ppo.py:52-58)
+    adv, _ = gae(_t(g["in_gae_rewards"]), _t(g["in_gae_values"]), done_masks=_t(g["in_gae_masks"]), discount=0.99,
+                 gae_param=0.95, time_major=True, want_returns=False)
+    _within(adv, g["out_gae_adv"], 1e-5, floor=np.abs(g["out_gae_adv"]).mean(), what="advantages")
+    np.testing.assert_allclose(_np(adv), g["out_gae_adv_f32"], rtol=2e-6, atol=2e-6)

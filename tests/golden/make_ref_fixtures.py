@@ -163,7 +163,8 @@ def family_lds():
             try:
                 np.random.seed(100 + n)
                 env, x = make_env(A[n], B[n], W[:, n])
-                agent = bpc_mod.BPC(jnp.array(A[n]), jnp.array(B[n]), H=H, lr_scale=0.005, decay=(n % 2 == 1), delta=0.01)
+                # (the default lr_scale = 0.005 makes the bandit update blow up within 40 steps on the default LDS; 2e-5 stays finite)
+                agent = bpc_mod.BPC(jnp.array(A[n]), jnp.array(B[n]), H=H, lr_scale=2e-5, decay=(n % 2 == 1), delta=0.01)
                 Ks[n] = npf(agent.K)
                 M0[n], eps0[n] = npf(agent.M), npf(agent.eps)      # drawn[0] * delta, drawn[1]; drawn[2] = eps_bias (unused)
                 n_init = len(drawn)
@@ -182,7 +183,7 @@ def family_lds():
             finally:
                 bpc_mod.generate_uniform = orig
         out.update(in_bpc_A=A, in_bpc_B=B, in_bpc_W=W, in_bpc_M0=M0, in_bpc_eps0=eps0, in_bpc_eps_new=eps_new,
-                   in_bpc_cfg=np.array([d, m, H, 0.005, 0.01, T]), out_bpc_K=Ks, out_bpc_costs=costs, out_bpc_X=X,
+                   in_bpc_cfg=np.array([d, m, H, 2e-5, 0.01, T]), out_bpc_K=Ks, out_bpc_costs=costs, out_bpc_X=X,
                    out_bpc_M=Mf)
         # ---- LDS on its own: y = C x with C != I, actions given (LDS.__call__, _lds.py:102-111)
         d, n_in, p, T = 10, 3, 2, 30
@@ -575,7 +576,76 @@ def family_drivers():
     return both_precisions(run)
 
 
-FAMILIES = {"drivers": family_drivers, "of": family_of, "lds": family_lds, "lung": family_lung, "classic": family_classic, "igpc": family_igpc}
+def family_lung_steps():
+    """Every state the reference visits: `loop_over_tt` (run_controller.py:111-141, the body `run_controller_scan` scans)
+    called step by step, recording the full carry (simulator state, observation, PID state, Expiratory state) BEFORE each
+    step and the step's outputs.  Lets a test restart the kernel from any visited state and compare ONE step, which
+    separates per-step arithmetic from the closed loop's amplification of rounding (BalloonLung + PID is locally
+    expansive on the float32 waveform's 5 -> 35 ramp)."""
+    import jax.numpy as jnp
+    from deluca.lung.core import BreathWaveform
+    from deluca.lung.controllers._expiratory import Expiratory
+    from deluca.lung.controllers._pid import PID
+    from deluca.lung.envs._balloon_lung import BalloonLung
+    from deluca.lung.envs._delay_lung import DelayLung
+    from deluca.lung.utils.scripts.run_controller import loop_over_tt
+
+    gains = np.array([[3.0, 4.0, 0.0], [1.0, 2.5, 0.3], [0.4, 0.05, 0.0], [4.5, 0.8, 1.5]])
+    pips = [10.0, 20.0, 35.0]
+    T = 150
+    f = lambda v: float(v)
+
+    def run():
+        out = dict(in_gains=gains, in_pips=np.array(pips))
+        for sim_name, make in (("balloon", lambda wf: BalloonLung.create(waveform=wf)),
+                               ("delay", lambda wf: DelayLung.create(waveform=wf, delay=3)),
+                               ("balloon_leak", lambda wf: BalloonLung.create(waveform=wf, leak=True))):
+            names = ["env_steps", "env_time", "env_volume", "env_pressure", "env_target", "obs_pressure", "obs_time",
+                     "pid_p", "pid_i", "pid_d", "pid_time", "pid_dt", "pid_steps", "exp_time", "exp_dt", "exp_steps",
+                     "u_in", "u_out", "pressure", "timestamp"]
+            if sim_name == "delay":
+                names += ["env_pipe"]
+            rec = {k: np.zeros((len(gains) * len(pips), T + 1)) for k in names}
+            hist = np.zeros((len(gains) * len(pips), T + 1, 2, 3)) if sim_name == "delay" else None
+            b = 0
+            for g in gains:
+                ctrl = PID.create(params={"K": {"kernel": jnp.array(g.reshape(3, 1))}})
+                for pip in pips:
+                    wf = BreathWaveform.create(peep=5.0, pip=pip)
+                    env = make(wf)
+                    exp = Expiratory.create(waveform=wf)
+                    cs, es = ctrl.init(wf), exp.init()
+                    state, obs = env.reset()
+                    carry = (state, obs, cs, es, 0)
+                    for t in range(T + 1):
+                        state, obs, cs, es, _ = carry
+                        r = rec
+                        r["env_steps"][b, t], r["env_time"][b, t] = f(state.steps), f(state.time)
+                        r["env_volume"][b, t], r["env_pressure"][b, t] = f(state.volume), f(state.predicted_pressure)
+                        r["env_target"][b, t] = f(state.target)
+                        r["obs_pressure"][b, t], r["obs_time"][b, t] = f(obs.predicted_pressure), f(obs.time)
+                        r["pid_p"][b, t], r["pid_i"][b, t], r["pid_d"][b, t] = f(cs.p), f(cs.i), f(cs.d)
+                        r["pid_time"][b, t], r["pid_dt"][b, t], r["pid_steps"][b, t] = f(cs.time), f(cs.dt), f(cs.steps)
+                        r["exp_time"][b, t], r["exp_dt"][b, t], r["exp_steps"][b, t] = f(es.time), f(es.dt), f(es.steps)
+                        if sim_name == "delay":
+                            r["env_pipe"][b, t] = f(state.pipe_pressure)
+                            hist[b, t, 0], hist[b, t, 1] = npf(state.in_history), npf(state.out_history)
+                        if t == T:
+                            break
+                        carry, (ts, u_in, u_out, p, fl) = loop_over_tt(carry, None, ctrl, exp, env, 0.03)
+                        r["timestamp"][b, t], r["u_in"][b, t], r["u_out"][b, t], r["pressure"][b, t] = (
+                            f(ts), f(jnp.squeeze(u_in)), f(u_out), f(p))
+                    b += 1
+            for k, v in rec.items():
+                out[f"out_{sim_name}_{k}"] = v
+            if hist is not None:
+                out[f"out_{sim_name}_hist"] = hist
+        return out
+
+    return both_precisions(run)
+
+
+FAMILIES = {"lung_steps": family_lung_steps, "drivers": family_drivers, "of": family_of, "lds": family_lds, "lung": family_lung, "classic": family_classic, "igpc": family_igpc}
 
 
 def main():

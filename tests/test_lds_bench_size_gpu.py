@@ -119,9 +119,10 @@ def test_full_size_checksum_and_subset(name, other_variant):
     ok = (r2.status == 0) & torch.isfinite(cs)
     assert int(ok.sum()) >= status_ok - 8 and status_ok >= N - 64     # (a handful of envs may diverge: lr quirk)
     rel = ((r2.cost_sum - cs).abs() / cs.abs().clamp_min(1e-30))[ok]
-    assert float(rel.max()) < RTOL, f"per-env episode cost, kernel vs kernel: {float(rel.max()):.3e}"
+    assert float(rel.max()) < 2 * RTOL, f"per-env episode cost, kernel vs kernel: {float(rel.max()):.3e}"
     tot_a, tot_b = float(cs[ok].sum()), float(r2.cost_sum[ok].sum())
     assert abs(tot_a - tot_b) <= 1e-6 * abs(tot_a), "all-env checksum"
+    # final states: each kernel is within RTOL of the float64 truth, so two kernels are within 2 RTOL of each other
     exf = ((r2.x - xf).abs().amax(1) / xf[ok].abs().mean())[ok]
-    assert float(exf.max()) < RTOL
+    assert float(exf.max()) < 2 * RTOL
     print(f"{name}: full size {N} x {T}: checksum {tot_a:.9e} vs {tot_b:.9e}; finite envs {status_ok}")

@@ -31,6 +31,7 @@ def _within(got, ref, rtol=RTOL, floor=None, what=""):
     """|got - ref| <= rtol * max(|ref|, floor); floor defaults to 1 % of the mean magnitude (relative error of
     near-zero entries is meaningless)."""
     got = _np(got) if isinstance(got, torch.Tensor) else np.asarray(got)
+    assert np.isfinite(ref).all(), f"{what}: the fixture itself is not finite"
     floor = floor if floor is not None else max(1e-2 * np.abs(ref).mean(), 1e-12)
     err = np.abs(got - ref) / np.maximum(np.abs(ref), floor)
     assert err.max() <= rtol, f"{what}: max rel err {err.max():.3e}"
@@ -108,9 +109,11 @@ def test_open_lds_kernel_matches_reference_files():
 def test_lung_kernel_matches_reference_files(sim, kw):
     """The fused ventilator episode against `run_controller_scan` executed literally.  The kernel computes in float32
     with the reference's float32 waveform knot (`3 - 1e-8 == 3`), so it is held to the reference's float32 run:
-    1e-4 relative for the whole default horizon T = 29, and at T = 150 per breath up to the first step at which the
-    kernel and the reference take different sides of `pressure > peep_valve` -- where the pressure must sit within
-    rounding of the valve threshold."""
+    1e-4 relative for the whole default horizon T = 29 and for the first 60 steps of the long episode.  Beyond that the
+    float32 closed loop (BalloonLung + PID tracking the float32 waveform's 5 -> 35 ramp) is locally expansive -- two
+    float32 runs of the reference's own arithmetic (torch vs NumPy libm) are 2e-2 apart by step 100 without any
+    branch flip -- so the rest of the episode is bounded by that measured amplification (x20), and exact per-step
+    parity on every visited state is `test_lung_kernel_one_step_parity_on_every_visited_state`."""
     from deluca_b200.lung.controllers import PID
     from deluca_b200.lung.core import BreathWaveform
     from deluca_b200.lung.envs import BalloonLung, DelayLung
@@ -135,24 +138,83 @@ def test_lung_kernel_matches_reference_files(sim, kw):
             if k in ("timestamp", "u_out", "target", "flow"):
                 assert ok.all(), (k, np.abs(got - ref).max())     # these do not depend on the lung state
                 continue
-            p_ref = g[f"out_{sim}_T{T}_pressure_f32"].reshape(-1, T)
-            for n in range(ref.shape[0]):
-                bad = np.nonzero(~ok[n])[0]
-                if bad.size == 0:
-                    continue
-                # the first disagreement must be a valve-branch flip: the pressure that was compared with
-                # peep_valve = 5 one step earlier is within rounding of it in the reference's run
-                t0 = int(bad[0])
-                near = np.abs(p_ref[n, max(t0 - 2, 0):t0 + 1] - 5.0).min()
-                assert near <= 5e-3, (k, n, t0, near)
-                flipped += 1
-        if T == 150:
-            print(f"{sim}: breaths that left the reference's branch within 150 steps: {flipped // 2} of {K.shape[0]}")
+            assert ok[:, :60].all(), (k, np.abs(got - ref)[:, :60].max())
+            # the reference's float32 vs float64 run differ QUALITATIVELY here (SURVEY A-9), so the yardstick for the
+            # tail is float32 vs float32: the NumPy float32 oracle against the reference's torch float32 run
+            from oracle import lung as OL
+            o = OL.run_controller_scan(K, pip, 5.0, T=T, sim="delay" if sim == "delay" else "balloon", dtype=np.float32,
+                                       sim_kwargs=kw)["timeseries"][k].T
+            amp = np.maximum(np.abs(o - ref).max(axis=1, keepdims=True), RTOL * scale)
+            assert (np.abs(got - ref) <= 20 * amp).all(), (k, (np.abs(got - ref) / amp).max())
     # test_controller's score at the reference's horizon (float64 literal run)
     wave = BreathWaveform.create(pip=torch.tensor(pip), peep=5.0)
     res = run_controller_scan(PID.create(params=torch.tensor(K)), T=29, env=env, waveform=wave, init_controller=True)
     score = _np((res["timeseries"]["pressure"] - res["timeseries"]["target"]).abs().mean(1)).reshape(len(gains), len(pips)).mean(1)
     np.testing.assert_allclose(score, g[f"out_{sim}_score_f32"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("sim", ["balloon", "balloon_leak", "delay"])
+def test_lung_kernel_one_step_parity_on_every_visited_state(sim):
+    """One kernel step from EVERY state the reference visits in 150 steps of 12 breaths (1,800 restarts in one launch),
+    compared with the reference's next state: 1e-5 relative -- per-step arithmetic parity in both branches of
+    `pressure > peep_valve`, on the inhale plateau, the exhale, the float32 ramp and (DelayLung, delay = 3) both sides of
+    `time < delay`, with no closed-loop amplification in the way."""
+    from deluca_b200.lung import _launch
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung, DelayLung
+    g = _load("lung_steps")
+    gains, pips = g["in_gains"], g["in_pips"]
+    r = lambda k: g[f"out_{sim}_{k}_f32"]
+    B, T1 = r("env_time").shape
+    T = T1 - 1
+    Kb = np.repeat(gains, len(pips), axis=0)
+    pipb = np.tile(pips, len(gains))
+    flat = lambda a: _t(np.ascontiguousarray(a[:, :T]).reshape(-1))
+    K = np.repeat(Kb, T, axis=0)
+    pip = np.repeat(pipb, T)
+    env = DelayLung.create(delay=3) if sim == "delay" else BalloonLung.create(leak=(sim == "balloon_leak"))
+    wave = BreathWaveform.create(pip=torch.tensor(pip, dtype=torch.float32), peep=5.0)
+    es = dict(steps=flat(r("env_steps")), time=flat(r("env_time")), volume=flat(r("env_volume")),
+              predicted_pressure=flat(r("env_pressure")), target=flat(r("env_target")))
+    if sim == "delay":
+        h = g[f"out_{sim}_hist_f32"][:, :T]
+        es.update(pipe_pressure=flat(r("env_pipe")), in_history=_t(h[:, :, 0].reshape(-1, 3)),
+                  out_history=_t(h[:, :, 1].reshape(-1, 3)))
+    ps = dict(p=flat(r("pid_p")), i=flat(r("pid_i")), d=flat(r("pid_d")), time=flat(r("pid_time")), dt=flat(r("pid_dt")),
+              steps=torch.as_tensor(r("pid_steps")[:, :T].reshape(-1), dtype=torch.int32).cuda())
+    xs = dict(time=flat(r("exp_time")), dt=flat(r("exp_dt")),
+              steps=torch.as_tensor(r("exp_steps")[:, :T].reshape(-1), dtype=torch.int32).cuda())
+    b, out = _launch.launch(env, wave, B * T, 1, "closed_loop", "cuda", K=_t(K), env_state=es,
+                            obs=dict(predicted_pressure=flat(r("obs_pressure")), time=flat(r("obs_time"))),
+                            pid_state=ps, exp_state=xs)
+    nxt = lambda a: np.ascontiguousarray(a[:, 1:]).reshape(-1)
+
+    def chk(got, want, what, tol=1e-5):
+        got = _np(got).reshape(-1)
+        scale = max(np.abs(want).max(), 1.0)
+        assert np.isfinite(want).all() and np.abs(got - want).max() <= tol * scale, (what, np.abs(got - want).max(), scale)
+
+    chk(out["u_in"][0], np.ascontiguousarray(r("u_in")[:, :T]).reshape(-1), "u_in")
+    chk(out["u_out"][0], np.ascontiguousarray(r("u_out")[:, :T]).reshape(-1), "u_out")
+    chk(out["pressure"][0], np.ascontiguousarray(r("pressure")[:, :T]).reshape(-1), "emitted pressure")
+    chk(out["timestamp"][0], np.ascontiguousarray(r("timestamp")[:, :T]).reshape(-1), "timestamp")
+    chk(b["volume_io"], nxt(r("env_volume")), "volume")
+    chk(b["pressure_io"], nxt(r("env_pressure")), "pressure")
+    chk(b["time_io"], nxt(r("env_time")), "time")
+    chk(b["target_io"], nxt(r("env_target")), "target")
+    chk(b["pid_i_io"], nxt(r("pid_i")), "pid i")
+    chk(b["pid_d_io"], nxt(r("pid_d")), "pid d")
+    chk(b["pid_p_io"], nxt(r("pid_p")), "pid p")
+    if sim == "delay":
+        chk(b["pipe_pressure_io"], nxt(r("env_pipe")), "pipe pressure")
+        h1 = g[f"out_{sim}_hist_f32"][:, 1:]
+        chk(b["in_history_io"], h1[:, :, 0].reshape(-1), "in_history")
+    # both branches of the valve / delay switches were exercised by the visited states
+    p0 = r("env_pressure")[:, :T]
+    if sim != "delay":
+        assert (p0 > 5.0).mean() > 0.2 and (p0 <= 5.0).mean() > 0.05
+    else:
+        assert (r("env_time")[:, :T] >= 3.0).any() and (r("env_time")[:, :T] < 3.0).any()
 
 
 def test_generic_pid_kernel_matches_reference_files():
@@ -279,7 +341,8 @@ def test_gae_kernel_matches_reference_file():
     from deluca_b200.fused import gae
     g = _load("drivers")
     # the reference's gae_advantages is time-major [actor_steps, num_agents] (ppo.py:52-58)
-    adv, _ = gae(_t(g["in_gae_rewards"]), _t(g["in_gae_values"]), done_masks=_t(g["in_gae_masks"]), discount=0.99,
+    # dlc_gae_f32 takes the LOSSES and negates them itself, as ac_rollout does before the call (ppo.py:132)
+    adv, _ = gae(_t(-g["in_gae_rewards"]), _t(g["in_gae_values"]), done_masks=_t(g["in_gae_masks"]), discount=0.99,
                  gae_param=0.95, time_major=True, want_returns=False)
     _within(adv, g["out_gae_adv"], 1e-5, floor=np.abs(g["out_gae_adv"]).mean(), what="advantages")
     np.testing.assert_allclose(_np(adv), g["out_gae_adv_f32"], rtol=2e-6, atol=2e-6)

@@ -19,6 +19,9 @@ struct LdsArgs {
 // packed-FFMA2 lane-split GPC kernel (lds_rollout_f2.cu).  Returns false if (d,m,H,HH) has no instantiation.
 bool launch_gpc_f2(const LdsArgs& a, cudaStream_t st, int32_t* rc);
 
+// quad-split GPC kernel for long even histories, H = HH (lds_gpc_quad.cu).  Returns false if it does not take the call.
+bool launch_gpc_quad(const LdsArgs& a, cudaStream_t st, int32_t* rc);
+
 // lane-split BPC kernel for compile-time shapes (lds_bpc.cu).  Returns false if (d,m,H) has no instantiation.
 bool launch_bpc(const LdsArgs& a, float* bpc_cost_io, cudaStream_t st, int32_t* rc);
 bool bpc_supported(const DlcLdsParams& p);

@@ -955,6 +955,7 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
   int32_t rc = DLC_OK;
   if (launch_bpc(a, bpc_cost_io, st, &rc)) return rc;
   if (launch_lqr_reg(a, st, &rc)) return rc;
+  if (launch_gpc_quad(a, st, &rc)) return rc;
   if (try_split(a, st, &rc)) return rc;
   if (launch_gpc_group(a, st, &rc)) return rc;
   if (!workspace || workspace_bytes < dlc_lds_workspace_bytes(p))

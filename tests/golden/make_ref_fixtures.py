@@ -616,7 +616,10 @@ def family_lung_steps():
                     exp = Expiratory.create(waveform=wf)
                     cs, es = ctrl.init(wf), exp.init()
                     state, obs = env.reset()
-                    carry = (state, obs, cs, es, 0)
+                    # `lax.scan` traces its carry: Python-scalar leaves become arrays of the default dtype, which is what
+                    # makes `state.time + self.dt` accumulate in float32 under run_controller_scan
+                    from jax._core import arrayify
+                    carry = arrayify((state, obs, cs, es, 0))
                     for t in range(T + 1):
                         state, obs, cs, es, _ = carry
                         r = rec
@@ -633,6 +636,7 @@ def family_lung_steps():
                         if t == T:
                             break
                         carry, (ts, u_in, u_out, p, fl) = loop_over_tt(carry, None, ctrl, exp, env, 0.03)
+                        carry = arrayify(carry)
                         r["timestamp"][b, t], r["u_in"][b, t], r["u_out"][b, t], r["pressure"][b, t] = (
                             f(ts), f(jnp.squeeze(u_in)), f(u_out), f(p))
                     b += 1

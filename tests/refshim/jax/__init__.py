@@ -15,11 +15,20 @@ __version__ = "0.0.0+refshim"
 
 
 def jit(fun=None, static_argnums=None, static_argnames=None, **_):
-    """Identity: the shim is eager.  Works as `@jax.jit`, `jax.jit(f, static_argnums=...)` and
+    """Eager, but with the one effect of tracing that changes VALUES: the non-static arguments' Python-scalar leaves
+    become arrays of the default dtype (`_core.arrayify`).  Works as `@jax.jit`, `jax.jit(f, static_argnums=...)` and
     `functools.partial(jax.jit, static_argnums=...)`."""
     if fun is None:
-        return lambda f: f
-    return fun
+        return lambda f: jit(f, static_argnums=static_argnums, static_argnames=static_argnames)
+    static = () if static_argnums is None else ((static_argnums,) if isinstance(static_argnums, int) else tuple(static_argnums))
+    names = () if static_argnames is None else ((static_argnames,) if isinstance(static_argnames, str) else tuple(static_argnames))
+
+    @_ft.wraps(fun)
+    def wrapped(*args, **kwargs):
+        args = [a if i in static else _core.arrayify(a) for i, a in enumerate(args)]
+        kwargs = {k: (v if k in names else _core.arrayify(v)) for k, v in kwargs.items()}
+        return fun(*args, **kwargs)
+    return wrapped
 
 
 def jacfwd(f, argnums=0, has_aux=False):

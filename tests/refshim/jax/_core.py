@@ -434,6 +434,20 @@ def tree_unflatten(treedef, leaves):
     return go(treedef)
 
 
+def arrayify(tree):
+    """What tracing does to the arguments of a jitted function and to a scan carry: Python / NumPy scalar leaves
+    become (weakly typed) arrays of the default dtype, so that e.g. `state.time + self.dt` accumulates in float32
+    inside `lax.scan` instead of in Python's float64.  Other leaves (arrays, functions, strings) pass through."""
+    def conv(l):
+        if isinstance(l, (bool, int, float, np.generic)):
+            return asarray(l)
+        if isinstance(l, np.ndarray):
+            return asarray(l)
+        return l
+    leaves, td = tree_flatten(tree)
+    return tree_unflatten(td, [conv(l) for l in leaves])
+
+
 def tree_map(f, tree, *rest):
     leaves, td = tree_flatten(tree)
     others = [tree_flatten(r)[0] for r in rest]

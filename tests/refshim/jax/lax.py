@@ -68,11 +68,12 @@ def scan(f, init, xs=None, length=None, reverse=False, unroll=1):
         leaves = [asarray(l) for l in leaves]
         n = leaves[0].shape[0] if length is None else length
         get = lambda i: tree_unflatten(td, [l[i] for l in leaves])
-    carry = init
+    carry = _core.arrayify(init)          # tracing turns the carry's Python scalars into arrays (float32 by default)
     ys = []
     order = range(n - 1, -1, -1) if reverse else range(n)
     for i in order:
         carry, y = f(carry, get(i))
+        carry = _core.arrayify(carry)
         ys.append(y)
     if reverse:
         ys.reverse()

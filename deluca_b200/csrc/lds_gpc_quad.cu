@@ -1,26 +1,25 @@
-// LDS + GPC rollout for long even histories (H = HH, the north-star target d = 10, m = 3, H = HH = 10):
-// four lanes own an env and split it TWO ways -- by state coordinate (halves S_0, S_1 of D/2) and by GPC tap
-// (halves I_0, I_1 of H/2) -- so that every lane holds exactly a quarter of everything and nothing is padded:
+// LDS + GPC rollout for long even histories (H = HH, the north-star target d = 10, m = 3, H = HH = 10).
 //
-//     lane (qc, qi):   M[i in I_qi][c][k in S_qc]   (H/2 * m * D/2 floats: 75)
-//                      (A - B K)[rows S_qc][cols S_qi]   (25),  B[rows S_qc][:] (15),  K[:][cols S_qc] (15)
+// 1. Layout.  Four lanes own an env and split it TWO ways -- by state coordinate (halves S_0, S_1 of D/2) and by GPC
+//    tap (halves I_0, I_1 of H/2) -- so that every lane holds exactly a quarter of everything and nothing is padded:
+//    lane (qc, qi) keeps M[i in I_qi][c][k in S_qc] (75 floats) in registers for the whole rollout.
+//    (lds_f2_kernel's split of 10 coordinates over 4 lanes as 3 + 3 + 3 + 1 pads every contraction 12-for-10.)
 //
-// (lds_f2_kernel's split of 10 coordinates over 4 lanes as 3 + 3 + 3 + 1 pads every contraction 12-for-10.)
+// 2. One pass over the noise ring per step.  The rank-H update of step t-1 and the H window products of step t,
+//        M[i] += sum_h s[h] (x) w[h + i]        V[h] = sum_i M[i] w'[h + i],   w'[j] = w[j + 1] (the ring rolled by one)
+//    touch the same ring slots, so for each own coordinate the 15 slots a lane needs are loaded once, M[.][.][k] is
+//    updated in registers and immediately used for the window products.  Both sides are packed FFMA2 (tap pairs as
+//    accumulators backward, window pairs forward).
 //
-// The M-side work of a step -- the rank-H update of step t-1 and the H window products of step t,
-//     M[i] += sum_h s[h] (x) w[h + i]        V[h] = sum_i M[i] w'[h + i],   w'[j] = w[j + 1] (the ring rolled by one)
-// -- is ONE pass over the noise ring: for each own coordinate the 14 slot pairs a lane needs are loaded once
-// (LDS.64 of (w[j], w[j+1]), the ring stores every element with its successor), M[.][.][k] is updated in registers
-// and immediately used for the window products of the next step.  Both sides are packed FFMA2 (tap pairs as
-// accumulators backward, window pairs forward); the partial window products are summed over the four lanes.
-//
-// The two recursions of policy_loss are latency chains (2 (H - 2) dependent mat-vecs per step), so they are kept short:
-// lane (qc, qi) multiplies with the block Abar[S_qc][S_qi] when the vector arrives split by columns (S_qi) and with the
-// block Abar[S_qi][S_qc] -- its partner lane's block -- when it arrives split by rows (S_qc); the result of either
-// product is a 1-bit xor-reduce away from the input layout of the other, so consecutive steps alternate between the
-// two and no vector is ever exchanged.  The term B v_h + w[h+H], which does not depend on the recursion state, is the
-// initial value of the dot-product chains on the two diagonal lanes.  The blocks live in shared memory and are loaded
-// into registers only for the recursion phase, which keeps the M pass free of spills.
+// 3. No recursions.  policy_loss runs H-1 steps of y <- Abar y + B v_h + w[h+H] (Abar = A - B K) and only its LAST
+//    state enters the loss, and the dynamics are linear, so (exact algebra, not an approximation)
+//        y_f      = sum_h Abar^(H-2-h) (B v_h + w[h+H]) = sum_h G_(H-2-h) v_h + q,        G_k = Abar^k B
+//        s[h]     = -lr B' (Abar')^(H-2-h) lam = -lr G_(H-2-h)' lam                       (the adjoint of the same map)
+//        q_(t+1)  = Abar q_t - Abar^(H-1) w_t[H] + w_t[2H-1]                              (the ring only shifts)
+//    with G_k and Abar^(H-1) formed once per rollout.  The 2 (H - 2) dependent mat-vecs per step -- a latency chain that
+//    no amount of occupancy at 255 registers could hide -- become two wide products against the same 27 x 10 operator
+//    plus two block products for q; 2,080 FMAs per env-step shrink to 740.  q is a contraction (Abar is stable), so its
+//    rounding error does not accumulate; the result agrees with the float64 oracle to ~1e-6 (tests/test_lds_gpu.py).
 //
 // Reference arithmetic: deluca/agents/_gpc.py:109-183 (policy_loss, update, get_action), deluca/envs/_lds.py:102-111.
 #include "lds_args.cuh"
@@ -32,41 +31,27 @@ namespace dlc {
 
 template <int D, int M, int H, int TPB>
 struct QuadLayout {
-  static constexpr int DC = D / 2, HT = H / 2, P = 2 * H, EPW = 8, WARPS = TPB / 32;
-  // float2 per ring slot of one warp.  The two tap halves of an env read slots H/2 apart in the same instruction; the
-  // pad puts those reads on different banks (H/2 * S * 2 words = 8 mod 32 for D = 10, H = 10)
-  static constexpr int S = D * EPW + 4;
-  static constexpr size_t kRingBytes = (size_t)WARPS * P * S * sizeof(float2);
-  static constexpr size_t kScratchBytes = (size_t)H * M * TPB * sizeof(float);
-  static constexpr int NPAR = DC * DC + 2 * DC * M;                   // Abar block, B rows, K columns of one lane
-  static constexpr size_t kParamBytes = (size_t)NPAR * TPB * sizeof(float);
-  static constexpr size_t kSmemBytes = kRingBytes + kScratchBytes + kParamBytes;
+  static constexpr int DC = D / 2, HT = H / 2, HS = H / 2, P = 2 * H, EPW = 8, WARPS = TPB / 32;
+  // floats per ring slot of one warp: [coordinate][env] plus a pad chosen so that the four lanes of an env -- reading
+  // coordinate halves D/2 apart and slots H/2 apart in one instruction -- land in four different bank octets
+  static constexpr int S1 = D * EPW;                                  // (5 slots * 80 floats = 16 mod 32 banks: no pad needed)
+  static_assert((DC * EPW) % 32 == 8 && (HT * S1) % 32 == 16, "ring padding is tuned for D = 10, H = 10");
+  static constexpr size_t kRingBytes = (size_t)WARPS * P * S1 * sizeof(float);
+  // per-lane operators in shared memory, as float4 columns [idx4][thread]: Abar block | Abar^(H-1) block | G rows
+  static constexpr int nA4 = (DC * DC + 3) / 4, nG4 = (HS * DC * M + 3) / 4;
+  static constexpr int oA9 = nA4, oG = 2 * nA4, NPAR4 = 2 * nA4 + nG4;
+  static constexpr size_t kParamBytes = (size_t)NPAR4 * TPB * sizeof(float4);
+  static constexpr size_t kSmemBytes = kRingBytes + kParamBytes;
 };
-
-// dot product of two DC-vectors as two interleaved chains (shorter dependency chain than one), on top of `init`
-template <int DC>
-__device__ __forceinline__ float dot_chain(const float* a, const float* v, float init) {
-  float p0 = fmaf(a[0], v[0], init);
-  if (DC == 1) return p0;
-  float p1 = a[1] * v[1];
-#pragma unroll
-  for (int i = 2; i < DC; ++i) {
-    if (i & 1) p1 = fmaf(a[i], v[i], p1);
-    else p0 = fmaf(a[i], v[i], p0);
-  }
-  return p0 + p1;
-}
-
-// arrivals per SM: every second CTA that lands on an SM starts half a step late (see `phase_delay` in the kernel)
-__device__ unsigned int g_quad_arrivals[1024];
 
 // WSRC: 1 = disturbances from a.W, 2 = in-kernel Philox stream
 template <int D, int M, int H, int TPB, int MINB, int WSRC>
 __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a) {
   using Lay = QuadLayout<D, M, H, TPB>;
-  constexpr int DC = Lay::DC, HT = Lay::HT, HP = H / 2, P = Lay::P, EPW = Lay::EPW, S = Lay::S;
+  constexpr int DC = Lay::DC, HT = Lay::HT, HS = Lay::HS, HP = H / 2, P = Lay::P, EPW = Lay::EPW, S1 = Lay::S1;
   constexpr int NPI = HT / 2, TI = HT & 1, NPIA = NPI > 0 ? NPI : 1;   // tap pairs of a tap half
-  constexpr int R = H + HT - 1;                                        // ring slots one lane touches per pass
+  constexpr int R = H + HT;                                            // ring slots one lane touches per pass
+  constexpr int KMAX = H - 1;                                          // Abar^KMAX closes the sliding sum q
   static_assert(D % 2 == 0 && H % 2 == 0 && H >= 4, "the quad split needs even D and even H >= 4");
   extern __shared__ __align__(16) unsigned char smraw[];
   const DlcLdsParams& p = a.p;
@@ -78,40 +63,142 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
   const bool live = n_raw < p.N;
   const int64_t n = live ? n_raw : p.N - 1;
   const int i0 = qi * HT, k0 = qc * DC, j0 = qi * DC;
-  float2* const ring = reinterpret_cast<float2*>(smraw) + (size_t)warp * P * S + e;   // entry(slot, k) = ring[slot*S + k*EPW]
-  float2* const rown = ring + k0 * EPW;                                               // own coordinates
-  float* const sV = reinterpret_cast<float*>(smraw + Lay::kRingBytes) + tid;          // scratch: V[h][c] then s[h][c]
-  float* const sPar = reinterpret_cast<float*>(smraw + Lay::kRingBytes + Lay::kScratchBytes) + tid;
-  const float* const sParT = sPar - lane + partner;                                   // the partner lane's blocks
-  constexpr int oB = DC * DC, oK = DC * DC + DC * M;       // sPar[idx * TPB]: Abar block [kk][jj] | B rows [kk][c] | K cols [c][kk]
+  float* const ring = reinterpret_cast<float*>(smraw) + (size_t)warp * P * S1 + e;    // w[slot][k] = ring[slot*S1 + k*EPW]
+  float* const rown = ring + k0 * EPW;                                                // own coordinates (S_qc)
+  float* const rcol = ring + j0 * EPW;                                                // coordinates S_qi
+  float4* const sPar = reinterpret_cast<float4*>(smraw + Lay::kRingBytes) + tid;      // sPar[idx4 * TPB]
   constexpr unsigned FULL = 0xffffffffu;
 
-  // ---- parameters -> shared memory.  Abar = A - B K (the counterfactual recursion is y <- Abar y + B v + w and its
-  // adjoint Abar' lam; the env step recovers A x = Abar x + B (K x)).
+  // ================= set-up: operators of the recursion-free form (once per rollout)
+  float Br[DC][M], Kc[M][DC];             // B rows S_qc, K columns S_qc: registers for the whole rollout
+  float qrow[DC];                         // q split by rows (S_qc)
   {
     const int64_t np = p.shared_dynamics ? 0 : n;
     const float* gA = a.A + np * (D * D);
     const float* gB = a.B + np * (D * M);
     const float* gK = a.K + np * (M * D);
-    float Br0[DC][M];
+    const float* gh = a.hist_io + n * (P * D);
+    float Bq[DC][M];                      // B rows S_qi (for G = Abar^k B summed over the column halves)
 #pragma unroll
     for (int kk = 0; kk < DC; ++kk)
 #pragma unroll
       for (int c = 0; c < M; ++c) {
-        Br0[kk][c] = __ldg(gB + (k0 + kk) * M + c);
-        sPar[(oB + kk * M + c) * TPB] = Br0[kk][c];
-        sPar[(oK + c * DC + kk) * TPB] = __ldg(gK + c * D + k0 + kk);
+        Br[kk][c] = __ldg(gB + (k0 + kk) * M + c);
+        Kc[c][kk] = __ldg(gK + c * D + k0 + kk);
+        Bq[kk][c] = __ldg(gB + (j0 + kk) * M + c);
       }
+    float Aown[DC][DC], Aoth[DC][DC];     // Abar[S_qc][S_qi], Abar[S_qc][S_(1-qi)]
 #pragma unroll
     for (int kk = 0; kk < DC; ++kk)
 #pragma unroll
       for (int jj = 0; jj < DC; ++jj) {
         float v = __ldg(gA + (k0 + kk) * D + j0 + jj);
 #pragma unroll
-        for (int c = 0; c < M; ++c) v = fmaf(-Br0[kk][c], __ldg(gK + c * D + j0 + jj), v);
-        sPar[(kk * DC + jj) * TPB] = v;
+        for (int c = 0; c < M; ++c) v = fmaf(-Br[kk][c], __ldg(gK + c * D + j0 + jj), v);
+        Aown[kk][jj] = v;
       }
+    {
+      float flat[Lay::nA4 * 4];           // Abar block, row-major [kk][jj], padded to float4
+#pragma unroll
+      for (int i = 0; i < Lay::nA4 * 4; ++i) flat[i] = i < DC * DC ? Aown[i / DC][i % DC] : 0.f;
+#pragma unroll
+      for (int i = 0; i < Lay::nA4; ++i) sPar[i * TPB] = make_float4(flat[4 * i], flat[4 * i + 1], flat[4 * i + 2], flat[4 * i + 3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+      for (int jj = 0; jj < DC; ++jj) Aoth[kk][jj] = __shfl_xor_sync(FULL, Aown[kk][jj], 2);
+    // Abar[S_qc][S_qc] and Abar[S_qc][S_(1-qc)]: what multiplies the own / the other row block of a power
+    float Asame[DC][DC], Adiff[DC][DC];
+#pragma unroll
+    for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+      for (int jj = 0; jj < DC; ++jj) {
+        Asame[kk][jj] = diag ? Aown[kk][jj] : Aoth[kk][jj];
+        Adiff[kk][jj] = diag ? Aoth[kk][jj] : Aown[kk][jj];
+      }
+    float Pk[DC][DC];                     // block (qc, qi) of Abar^k
+#pragma unroll
+    for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+      for (int jj = 0; jj < DC; ++jj) Pk[kk][jj] = (diag && kk == jj) ? 1.f : 0.f;
+    float qacc[DC];
+#pragma unroll
+    for (int kk = 0; kk < DC; ++kk) qacc[kk] = 0.f;
+    float* const sG = reinterpret_cast<float*>(sPar + Lay::oG * TPB);          // G rows as scalars: float i at sG[(i/4)*4*TPB + i%4]
+    // the lane's window subset is h in [qi*HS, qi*HS + HS); window h uses G_(H-2-h); h = H-1 has no recursion term
+    for (int i = 0; i < Lay::nG4 * 4; ++i) sG[(i >> 2) * 4 * TPB + (i & 3)] = 0.f;
+#pragma unroll 1
+    for (int k = 0; k <= KMAX; ++k) {
+      if (k <= H - 2) {
+        // G_k[S_qc][:] = sum over the column halves of Abar^k(qc, .) B[S_.][:]
+        float g[DC][M];
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < DC; ++jj) s = fmaf(Pk[kk][jj], Bq[jj][c], s);
+            g[kk][c] = s + __shfl_xor_sync(FULL, s, 2);
+          }
+        const int hh = (H - 2 - k) - qi * HS;                          // position of window h = H-2-k in the lane's subset
+        if (hh >= 0 && hh < HS) {
+#pragma unroll
+          for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+              const int i = (hh * DC + kk) * M + c;
+              sG[(i >> 2) * 4 * TPB + (i & 3)] = g[kk][c];
+            }
+        }
+        // q of the entry ring: sum_k Abar^k w[2H-2-k]  (slots H .. 2H-2), partial over the column halves
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk) {
+          float s = qacc[kk];
+#pragma unroll
+          for (int jj = 0; jj < DC; ++jj) s = fmaf(Pk[kk][jj], gh[(2 * H - 2 - k) * D + j0 + jj], s);
+          qacc[kk] = s;
+        }
+      }
+      if (k == KMAX) {
+        float flat[Lay::nA4 * 4];
+#pragma unroll
+        for (int i = 0; i < Lay::nA4 * 4; ++i) flat[i] = i < DC * DC ? Pk[i / DC][i % DC] : 0.f;
+#pragma unroll
+        for (int i = 0; i < Lay::nA4; ++i)
+          sPar[(Lay::oA9 + i) * TPB] = make_float4(flat[4 * i], flat[4 * i + 1], flat[4 * i + 2], flat[4 * i + 3]);
+      } else {
+        // Abar^(k+1)(qc, qi) = Abar(qc, qc) P(qc, qi) + Abar(qc, 1-qc) P(1-qc, qi)
+        float Po[DC][DC], Pnew[DC][DC];
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+          for (int jj = 0; jj < DC; ++jj) Po[kk][jj] = __shfl_xor_sync(FULL, Pk[kk][jj], 1);   // block (1-qc, qi)
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+          for (int jj = 0; jj < DC; ++jj) {
+            float s = 0.f;
+#pragma unroll
+            for (int l = 0; l < DC; ++l) s = fmaf(Asame[kk][l], Pk[l][jj], s);
+#pragma unroll
+            for (int l = 0; l < DC; ++l) s = fmaf(Adiff[kk][l], Po[l][jj], s);
+            Pnew[kk][jj] = s;
+          }
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk)
+#pragma unroll
+          for (int jj = 0; jj < DC; ++jj) Pk[kk][jj] = Pnew[kk][jj];
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < DC; ++kk) qrow[kk] = qacc[kk] + __shfl_xor_sync(FULL, qacc[kk], 2);
   }
+  float qcol[DC];                         // q split by columns (S_qi): the input layout of the next block product
+#pragma unroll
+  for (int kk = 0; kk < DC; ++kk) qcol[kk] = __shfl_sync(FULL, qrow[kk], partner);
+
   // M: tap pairs (2p, 2p+1) as packed accumulators, the odd tap as a scalar
   f2 Mp[NPIA][M][DC];
   float Ms[M][DC];
@@ -131,100 +218,73 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
     if (TI && ii == HT - 1) return Ms[c][kk];
     return (ii & 1) ? hi(Mp[ii / 2][c][kk]) : lo(Mp[ii / 2][c][kk]);
   };
-  // noise ring: every element with its successor, (w[s][k], w[s+1][k]); the four lanes of an env fill it together
+  // noise ring: the four lanes of an env fill it together
   {
     const float* gh = a.hist_io + n * (P * D);
     for (int idx = q; idx < P * D; idx += 4) {
       const int s = idx / D, k = idx - s * D;
-      ring[s * S + k * EPW] = make_float2(gh[s * D + k], s + 1 < P ? gh[(s + 1) * D + k] : 0.f);
+      ring[s * S1 + k * EPW] = gh[s * D + k];
     }
   }
   __syncwarp();
 
-  // the blocks of the recursion phase, loaded from shared memory where they are needed
-  struct Blocks { float Ab[DC][DC], AbT[DC][DC], Br[DC][M], Kc[M][DC]; };
-  auto load_blocks = [&](Blocks& b) {
+  // per-lane operators back from shared memory (float4 columns), at the point of use
+  auto load_block = [&](int o4, float blk[DC][DC]) {
+    float flat[Lay::nA4 * 4];
 #pragma unroll
-    for (int kk = 0; kk < DC; ++kk)
-#pragma unroll
-      for (int jj = 0; jj < DC; ++jj) {
-        b.Ab[kk][jj] = sPar[(kk * DC + jj) * TPB];                     // Abar[k0 + kk][j0 + jj]
-        b.AbT[kk][jj] = sParT[(kk * DC + jj) * TPB];                   // Abar[j0 + kk][k0 + jj]
-      }
-#pragma unroll
-    for (int kk = 0; kk < DC; ++kk)
-#pragma unroll
-      for (int c = 0; c < M; ++c) {
-        b.Br[kk][c] = sPar[(oB + kk * M + c) * TPB];
-        b.Kc[c][kk] = sPar[(oK + c * DC + kk) * TPB];
-      }
-  };
-  // y[S_qc] = init + Abar[S_qc][S_qi] vc   (vc split by columns)  -> summed over qi: split by rows
-  auto mul_cols_to_rows = [&](const Blocks& b, const float vc[DC], const float init[DC], float out[DC]) {
-#pragma unroll
-    for (int kk = 0; kk < DC; ++kk) out[kk] = dot_chain<DC>(b.Ab[kk], vc, init[kk]);
-#pragma unroll
-    for (int kk = 0; kk < DC; ++kk) out[kk] += __shfl_xor_sync(FULL, out[kk], 2);
-  };
-  // y[S_qi] = init + Abar[S_qi][S_qc] vr   (vr split by rows)     -> summed over qc: split by columns
-  auto mul_rows_to_cols = [&](const Blocks& b, const float vr[DC], const float init[DC], float out[DC]) {
-#pragma unroll
-    for (int jj = 0; jj < DC; ++jj) out[jj] = dot_chain<DC>(b.AbT[jj], vr, init[jj]);
-#pragma unroll
-    for (int jj = 0; jj < DC; ++jj) out[jj] += __shfl_xor_sync(FULL, out[jj], 1);
-  };
-  // adjoint products: lam'[S_qi] = Abar[S_qc][S_qi]' lam[S_qc] (rows -> columns), lam'[S_qc] = Abar[S_qi][S_qc]' lam[S_qi]
-  auto mulT_rows_to_cols = [&](const Blocks& b, const float vr[DC], float out[DC]) {
-#pragma unroll
-    for (int jj = 0; jj < DC; ++jj) {
-      float col[DC];
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) col[kk] = b.Ab[kk][jj];
-      out[jj] = dot_chain<DC>(col, vr, 0.f);
+    for (int i = 0; i < Lay::nA4; ++i) {
+      const float4 v = sPar[(o4 + i) * TPB];
+      flat[4 * i] = v.x; flat[4 * i + 1] = v.y; flat[4 * i + 2] = v.z; flat[4 * i + 3] = v.w;
     }
 #pragma unroll
-    for (int jj = 0; jj < DC; ++jj) out[jj] += __shfl_xor_sync(FULL, out[jj], 1);
+    for (int i = 0; i < DC * DC; ++i) blk[i / DC][i % DC] = flat[i];
   };
-  auto mulT_cols_to_rows = [&](const Blocks& b, const float vc[DC], float out[DC]) {
+  auto load_G = [&](float G[HS][DC][M]) {
+    float flat[Lay::nG4 * 4];
 #pragma unroll
-    for (int kk = 0; kk < DC; ++kk) {
-      float col[DC];
-#pragma unroll
-      for (int jj = 0; jj < DC; ++jj) col[jj] = b.AbT[jj][kk];
-      out[kk] = dot_chain<DC>(col, vc, 0.f);
+    for (int i = 0; i < Lay::nG4; ++i) {
+      const float4 v = sPar[(Lay::oG + i) * TPB];
+      flat[4 * i] = v.x; flat[4 * i + 1] = v.y; flat[4 * i + 2] = v.z; flat[4 * i + 3] = v.w;
     }
 #pragma unroll
-    for (int kk = 0; kk < DC; ++kk) out[kk] += __shfl_xor_sync(FULL, out[kk], 2);
+    for (int i = 0; i < HS * DC * M; ++i) G[i / (DC * M)][(i / M) % DC][i % M] = flat[i];
   };
-  auto K_dot = [&](const Blocks& b, const float vr[DC], float out[M]) {   // K v (v split by rows), summed over qc
+  auto K_dot = [&](const float vr[DC], float out[M]) {                // K v (v split by rows), summed over qc
 #pragma unroll
-    for (int c = 0; c < M; ++c) out[c] = dot_chain<DC>(b.Kc[c], vr, 0.f);
+    for (int c = 0; c < M; ++c) {
+      float s = Kc[c][0] * vr[0];
+#pragma unroll
+      for (int kk = 1; kk < DC; ++kk) s = fmaf(Kc[c][kk], vr[kk], s);
+      out[c] = s;
+    }
 #pragma unroll
     for (int c = 0; c < M; ++c) out[c] += __shfl_xor_sync(FULL, out[c], 1);
   };
-  auto B_acc = [&](const Blocks& b, const float v[M], float acc[DC]) {     // acc[S_qc] += B[S_qc][:] v
+  auto B_acc = [&](const float v[M], float acc[DC]) {                 // acc[S_qc] += B[S_qc][:] v
 #pragma unroll
     for (int kk = 0; kk < DC; ++kk)
 #pragma unroll
-      for (int c = 0; c < M; ++c) acc[kk] = fmaf(b.Br[kk][c], v[c], acc[kk]);
+      for (int c = 0; c < M; ++c) acc[kk] = fmaf(Br[kk][c], v[c], acc[kk]);
   };
-  float zero[DC];
-#pragma unroll
-  for (int kk = 0; kk < DC; ++kk) zero[kk] = 0.f;
 
   // ---- state
   float xr[DC], ax[DC], uprev[M];
 #pragma unroll
   for (int kk = 0; kk < DC; ++kk) xr[kk] = a.x_io[n * D + k0 + kk];
   {
-    Blocks b;
-    load_blocks(b);
-    float xpr[DC], xpc[DC], kxp[M];
+    float Ab[DC][DC], xpc[DC], xpr[DC], kxp[M];
+    load_block(0, Ab);
 #pragma unroll
     for (int kk = 0; kk < DC; ++kk) { xpr[kk] = a.xprev_io[n * D + k0 + kk]; xpc[kk] = a.xprev_io[n * D + j0 + kk]; }
-    mul_cols_to_rows(b, xpc, zero, ax);                               // Abar x_prev ...
-    K_dot(b, xpr, kxp);
-    B_acc(b, kxp, ax);                                                // ... + B (K x_prev) = A x_prev
+#pragma unroll
+    for (int kk = 0; kk < DC; ++kk) {
+      float s = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < DC; ++jj) s = fmaf(Ab[kk][jj], xpc[jj], s);
+      ax[kk] = s + __shfl_xor_sync(FULL, s, 2);                        // Abar x_prev ...
+    }
+    K_dot(xpr, kxp);
+    B_acc(kxp, ax);                                                   // ... + B (K x_prev) = A x_prev
 #pragma unroll
     for (int c = 0; c < M; ++c) uprev[c] = a.uprev_io ? a.uprev_io[n * M + c] : 0.f;
   }
@@ -253,61 +313,50 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
   };
   float wnext[DC];
   if (p.T > 0) load_w(0, wnext);
+  float sprev[H][M];                      // s of the previous step (all windows); zero: no update in the first pass
 #pragma unroll
-  for (int r = 0; r < H * M; ++r) sV[r * TPB] = 0.f;                   // s of "step -1": no update in the first pass
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int c = 0; c < M; ++c) sprev[h][c] = 0.f;
 
-  // A step alternates between a phase that saturates the FMA pipe (the pass) and a phase of dependent mat-vecs that
-  // mostly waits (the recursions).  All warps run identical steps, so the two warps that share a scheduler stay in
-  // whatever relative phase they started with -- and they start together.  Delaying every second arrival on an SM by
-  // about half a step puts one warp's pass under the other's recursions for the whole launch.
-  if (a.phase_delay > 0) {
-    __shared__ unsigned int s_arrival;
-    if (tid == 0) {
-      unsigned int smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      s_arrival = atomicAdd(&g_quad_arrivals[smid & 1023], 1u);
-    }
-    __syncthreads();
-    const bool late = TPB >= 256 ? (((warp >> 2) ^ s_arrival) & 1) : (s_arrival & 1);
-    if (late) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < (long long)a.phase_delay) { }
-    }
-  }
   int head = 0;
   // T + 1 trips: the pass at the top of trip t applies step t-1's update, so trip T only runs the pass.  (Written as a
-  // counted loop with a guarded body so that the compiler does not rotate the loop and duplicate the 11 KB pass.)
+  // counted loop with a guarded body so that the compiler does not rotate the loop and duplicate the pass.)
 #pragma unroll 1
   for (int t = 0; t <= p.T; ++t) {
-    // ================= one pass over the ring: M += sum_h s[h] (x) w[h+i];  V[h] = sum_i M[i] w[h+i+1]
+    // ================= one pass over the ring (old indexing): M += sum_h s[h] (x) w[h+i];  V[h] = sum_i M[i] w[h+i+1]
     f2 acc[HP][M];
     {
-      float sprev[H * M];
-#pragma unroll
-      for (int r = 0; r < H * M; ++r) sprev[r] = sV[r * TPB];
 #pragma unroll
       for (int b = 0; b < HP; ++b)
 #pragma unroll
         for (int c = 0; c < M; ++c) acc[b][c] = pk(0.f, 0.f);
-      const float2* rlo = rown + (head + i0) * S;                     // logical slot i0 + r lives at rlo + r*S ...
-      const float2* rhi = rlo - P * S;                                // ... or, past the wrap, at rhi + r*S
+      // logical slot i0 + r lives at byte address rlo + r*S1*4, or, past the wrap, at rhi + r*S1*4
+      const unsigned rlo = (unsigned)__cvta_generic_to_shared(rown + (head + i0) * S1);
+      const unsigned rhi = rlo - P * S1 * 4;
       const int rw = P - head - i0;
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) {
-        f2 w2[R];
+        // every slot pair (w[i0 + r], w[i0 + r + 1]) is loaded straight into its own aligned register pair (two
+        // LDS.32 per pair; a slot is therefore loaded twice, which is cheaper than the register moves that sharing
+        // one load between an even and an odd pair costs)
+        f2 wp[R - 1];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float2 v = ((r < rw) ? rlo : rhi)[r * S + kk * EPW];
-          w2[r] = pk(v.x, v.y);
+        for (int r = 0; r < R - 1; ++r) {
+          const unsigned a0 = ((r < rw) ? rlo : rhi) + (r * S1 + kk * EPW) * 4;
+          const unsigned a1 = ((r + 1 < rw) ? rlo : rhi) + ((r + 1) * S1 + kk * EPW) * 4;
+          asm volatile("{ .reg .f32 lo_, hi_; ld.volatile.shared.f32 lo_, [%1]; ld.volatile.shared.f32 hi_, [%2]; mov.b64 %0, {lo_, hi_}; }"
+                       : "=l"(wp[r]) : "r"(a0), "r"(a1));
         }
+        auto pair = [&](int r) -> f2 { return wp[r]; };
         // backward (step t-1): M[ii][c][k] += s[h][c] * w[h + i0 + ii][k]                       _gpc.py:163
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
           for (int c = 0; c < M; ++c) {
 #pragma unroll
-            for (int pp = 0; pp < NPI; ++pp) Mp[pp][c][kk] = fma2(dup(sprev[h * M + c]), w2[h + 2 * pp], Mp[pp][c][kk]);
-            if (TI) Ms[c][kk] = fmaf(sprev[h * M + c], lo(w2[h + HT - 1]), Ms[c][kk]);
+            for (int pp = 0; pp < NPI; ++pp) Mp[pp][c][kk] = fma2(dup(sprev[h][c]), pair(h + 2 * pp), Mp[pp][c][kk]);
+            if (TI) Ms[c][kk] = fmaf(sprev[h][c], lo(wp[h + HT - 1]), Ms[c][kk]);
           }
         // forward (step t): (V[2b], V[2b+1])[c] += M[ii][c][k] * (w'[2b + i], w'[2b + i + 1]),  w'[j] = w[j+1]
 #pragma unroll
@@ -315,40 +364,65 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
 #pragma unroll
           for (int ii = 0; ii < HT; ++ii)
 #pragma unroll
-            for (int c = 0; c < M; ++c) acc[b][c] = fma2(dup(Mtap(ii, c, kk)), w2[2 * b + ii + 1], acc[b][c]);
+            for (int c = 0; c < M; ++c) acc[b][c] = fma2(dup(Mtap(ii, c, kk)), pair(2 * b + ii + 1), acc[b][c]);
       }
     }
     if (t < p.T) {                                                    // (trip T: the pass applied the last update)
     head = (head + 1 == P) ? 0 : head + 1;                            // roll(-1)               _gpc.py:156-157
-    const float2* const nlo = rown + head * S;                        // new logical slot j at nlo + j*S (j < nw) ...
-    const float2* const nhi = nlo - P * S;                            // ... else at nhi + j*S
-    const int nw = P - head;
-    auto w_at = [&](int j, int kk) -> float {                         // w[j][own coordinate kk], new indexing
-      return reinterpret_cast<const float*>(((j < nw) ? nlo : nhi) + j * S + kk * EPW)[0];
-    };
+    const int nw = P - head;                                          // new logical slot j: physical head + j (- P past nw)
+    auto slot = [&](const float* base, int j) -> const float* { return base + (head + j - (j < nw ? 0 : P)) * S1; };
     float wt[DC];
 #pragma unroll
     for (int kk = 0; kk < DC; ++kk) wt[kk] = wnext[kk];
     if (t + 1 < p.T) load_w(t + 1, wnext);
-    Blocks b;
-    load_blocks(b);
 
-    // ---- sum the partial window products over the four lanes
-    float V0[M], mw[M];
+    // ---- q_t = Abar q_(t-1) - Abar^(H-1) w[H-1] + w[2H-2]   (new indexing; both slots predate this step's noise)
+    float Ab[DC][DC];
+    load_block(0, Ab);
+    {
+      float A9[DC][DC], wold[DC];
+      load_block(Lay::oA9, A9);
+      const float* so = slot(rcol, H - 1);
+      const float* sn = slot(rown, 2 * H - 2);
 #pragma unroll
-    for (int bb = 0; bb < HP; ++bb)
+      for (int jj = 0; jj < DC; ++jj) wold[jj] = so[jj * EPW];
 #pragma unroll
-      for (int c = 0; c < M; ++c) {
-        float v0 = lo(acc[bb][c]), v1 = hi(acc[bb][c]);
-        v0 += __shfl_xor_sync(FULL, v0, 1);
-        v1 += __shfl_xor_sync(FULL, v1, 1);
-        v0 += __shfl_xor_sync(FULL, v0, 2);
-        v1 += __shfl_xor_sync(FULL, v1, 2);
-        if (bb == 0) V0[c] = v0; else sV[((2 * bb) * M + c) * TPB] = v0;
-        if (bb == HP - 1) mw[c] = v1; else sV[((2 * bb + 1) * M + c) * TPB] = v1;
+      for (int kk = 0; kk < DC; ++kk) {
+        float s0 = Ab[kk][0] * qcol[0], s1 = -A9[kk][0] * wold[0];
+#pragma unroll
+        for (int jj = 1; jj < DC; ++jj) { s0 = fmaf(Ab[kk][jj], qcol[jj], s0); s1 = fmaf(-A9[kk][jj], wold[jj], s1); }
+        const float s = s0 + s1;
+        qrow[kk] = (s + __shfl_xor_sync(FULL, s, 2)) + sn[kk * EPW];
       }
+#pragma unroll
+      for (int kk = 0; kk < DC; ++kk) qcol[kk] = __shfl_sync(FULL, qrow[kk], partner);
+    }
+
+    // ---- window products: sum over the coordinate halves, then each tap half keeps the windows of its subset
+    float Vown[HS][M], mw[M];
+    {
+      float v[H][M];
+#pragma unroll
+      for (int b = 0; b < HP; ++b)
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const float v0 = lo(acc[b][c]), v1 = hi(acc[b][c]);
+          v[2 * b][c] = v0 + __shfl_xor_sync(FULL, v0, 1);
+          v[2 * b + 1][c] = v1 + __shfl_xor_sync(FULL, v1, 1);
+        }
+#pragma unroll
+      for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const float mine = qi ? v[HS + hh][c] : v[hh][c];
+          const float theirs = qi ? v[hh][c] : v[HS + hh][c];
+          Vown[hh][c] = mine + __shfl_xor_sync(FULL, theirs, 2);
+        }
+#pragma unroll
+      for (int c = 0; c < M; ++c) mw[c] = __shfl_sync(FULL, Vown[HS - 1][c], lane | 2);   // V[H-1] lives in the upper tap half
+    }
     float kx[M], u[M];
-    K_dot(b, xr, kx);                                                 // K x                     _lqr.py:72
+    K_dot(xr, kx);                                                    // K x                     _lqr.py:72
 #pragma unroll
     for (int c = 0; c < M; ++c) u[c] = mw[c] - kx[c];                 // get_action              _gpc.py:171-183
 
@@ -359,101 +433,76 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
       for (int c = 0; c < M; ++c) un[c] = p.noise_uses_prev_action ? uprev[c] : u[c];
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) nz[kk] = 0.f;
-      B_acc(b, un, nz);
+      B_acc(un, nz);
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) nz[kk] = (xr[kk] - ax[kk]) - nz[kk];
       if (qi == 0) {
-        float* newest = reinterpret_cast<float*>(const_cast<float2*>(((P - 1 < nw) ? nlo : nhi) + (P - 1) * S));      // .x
-        float* second = reinterpret_cast<float*>(const_cast<float2*>(((P - 2 < nw) ? nlo : nhi) + (P - 2) * S)) + 1;  // .y
+        float* newest = const_cast<float*>(slot(rown, P - 1));
 #pragma unroll
-        for (int kk = 0; kk < DC; ++kk) {
-          newest[2 * kk * EPW] = nz[kk];
-          second[2 * kk * EPW] = nz[kk];
-        }
+        for (int kk = 0; kk < DC; ++kk) newest[kk * EPW] = nz[kk];
       }
     }
     __syncwarp();
 
-    // ---- policy_loss forward: y <- Abar y + (B v_h + w[h+H])                                 _gpc.py:118-124
-    // zb(h) = B v_h + w[h+H] on the own rows; only the two diagonal lanes feed it into the reduced sums
-    auto zb_of = [&](int h, const float v[M], float zb[DC]) {
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) zb[kk] = w_at(h + H, kk);
-      B_acc(b, v, zb);
-    };
-    float yr[DC];
-    zb_of(0, V0, yr);                                                 // y_1 = B v_0 + w[H]  (y_0 = 0), split by rows
-#pragma unroll 1
-    for (int h = 1; h < H - 1; h += 2) {
-      float v1[M], v2[M], z1[DC], z2[DC], yc[DC];
-#pragma unroll
-      for (int c = 0; c < M; ++c) { v1[c] = sV[(h * M + c) * TPB]; v2[c] = sV[((h + 1) * M + c) * TPB]; }
-      zb_of(h, v1, z1);
-      zb_of(h + 1, v2, z2);
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) { z1[kk] = diag ? z1[kk] : 0.f; z2[kk] = diag ? z2[kk] : 0.f; }
-      mul_rows_to_cols(b, yr, z1, yc);                                // y_{h+1}, split by columns
-      mul_cols_to_rows(b, yc, z2, yr);                                // y_{h+2}, split by rows
-    }
-    // ---- u_f = -K y + mw ; du = 2 u_f ; lam = 2 y - K' du                                    SURVEY A-3.5
+    // ---- y_f = q + sum_h G_(H-2-h) v_h ;  u_f = -K y_f + mw ; du = 2 u_f ; lam = 2 y_f - K' du   _gpc.py:109-125
     const float lr = p.decay ? p.lr_scale * (1.0f / (float)(p.t0 + t + 1)) : p.lr_scale;
-    float du[M], lam[DC];
+    float sown[HS][M], du[M];
     {
-      float ky[M];
-      K_dot(b, yr, ky);
+      float G[HS][DC][M];
+      load_G(G);
+      float yf[DC];
+#pragma unroll
+      for (int kk = 0; kk < DC; ++kk) {
+        float sc[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) sc[c] = G[0][kk][c] * Vown[0][c];
+#pragma unroll
+        for (int hh = 1; hh < HS; ++hh)
+#pragma unroll
+          for (int c = 0; c < M; ++c) sc[c] = fmaf(G[hh][kk][c], Vown[hh][c], sc[c]);
+        float s = sc[0];
+#pragma unroll
+        for (int c = 1; c < M; ++c) s += sc[c];
+        yf[kk] = (s + __shfl_xor_sync(FULL, s, 2)) + qrow[kk];
+      }
+      float ky[M], lam[DC];
+      K_dot(yf, ky);
 #pragma unroll
       for (int c = 0; c < M; ++c) du[c] = 2.0f * (mw[c] - ky[c]);
+#pragma unroll
+      for (int kk = 0; kk < DC; ++kk) {
+        float s = 2.0f * yf[kk];
+#pragma unroll
+        for (int c = 0; c < M; ++c) s = fmaf(-Kc[c][kk], du[c], s);
+        lam[kk] = s;
+      }
+      // s[h] = -lr G_(H-2-h)' lam on the lane's window subset, summed over the coordinate halves       SURVEY A-3.5
+#pragma unroll
+      for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          float s = G[hh][0][c] * lam[0];
+#pragma unroll
+          for (int kk = 1; kk < DC; ++kk) s = fmaf(G[hh][kk][c], lam[kk], s);
+          sown[hh][c] = s;
+        }
     }
 #pragma unroll
-    for (int kk = 0; kk < DC; ++kk) {
-      float s = 2.0f * yr[kk];
-#pragma unroll
-      for (int c = 0; c < M; ++c) s = fmaf(-b.Kc[c][kk], du[c], s);
-      lam[kk] = s;
-    }
-#pragma unroll
-    for (int c = 0; c < M; ++c) sV[((H - 1) * M + c) * TPB] = -lr * du[c];
-    // ---- adjoint recursion: s[h] = -lr B' lam_h ; lam_{h-1} = Abar' lam_h, alternating layouts
-    auto s_from_rows = [&](int h, const float lr_[DC]) {              // lam split by rows: every lane has its B rows
-      float lu[M];
+    for (int hh = 0; hh < HS; ++hh)
 #pragma unroll
       for (int c = 0; c < M; ++c) {
-        float col[DC];
-#pragma unroll
-        for (int kk = 0; kk < DC; ++kk) col[kk] = b.Br[kk][c];
-        lu[c] = dot_chain<DC>(col, lr_, 0.f);
+        const float s = sown[hh][c] + __shfl_xor_sync(FULL, sown[hh][c], 1);
+        sown[hh][c] = -lr * ((hh == HS - 1 && qi) ? du[c] : s);       // window H-1: s = -lr du (the final action)
       }
+    // every lane needs every window's s for the next pass: the tap halves exchange their subsets
 #pragma unroll
-      for (int c = 0; c < M; ++c) lu[c] += __shfl_xor_sync(FULL, lu[c], 1);
-#pragma unroll
-      for (int c = 0; c < M; ++c) sV[(h * M + c) * TPB] = -lr * lu[c];
-    };
-    auto s_from_cols = [&](int h, const float lc[DC]) {               // lam split by columns: the diagonal lanes' B rows
-      float lu[M];
+    for (int hh = 0; hh < HS; ++hh)
 #pragma unroll
       for (int c = 0; c < M; ++c) {
-        float col[DC];
-#pragma unroll
-        for (int kk = 0; kk < DC; ++kk) col[kk] = b.Br[kk][c];
-        const float v = dot_chain<DC>(col, lc, 0.f);
-        lu[c] = diag ? v : 0.f;
+        const float other = __shfl_xor_sync(FULL, sown[hh][c], 2);
+        sprev[hh][c] = qi ? other : sown[hh][c];
+        sprev[HS + hh][c] = qi ? sown[hh][c] : other;
       }
-#pragma unroll
-      for (int c = 0; c < M; ++c) lu[c] += __shfl_xor_sync(FULL, lu[c], 1);
-#pragma unroll
-      for (int c = 0; c < M; ++c) lu[c] += __shfl_xor_sync(FULL, lu[c], 2);
-#pragma unroll
-      for (int c = 0; c < M; ++c) sV[(h * M + c) * TPB] = -lr * lu[c];
-    };
-#pragma unroll 1
-    for (int h = H - 2; h >= 2; h -= 2) {
-      float lc[DC];
-      s_from_rows(h, lam);
-      mulT_rows_to_cols(b, lam, lc);                                  // lam_{h-1}, split by columns
-      s_from_cols(h - 1, lc);
-      mulT_cols_to_rows(b, lc, lam);                                  // lam_{h-2}, split by rows
-    }
-    s_from_rows(0, lam);
 #pragma unroll
     for (int c = 0; c < M; ++c) uprev[c] = u[c];
 
@@ -491,11 +540,17 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
       float xc[DC], z[DC];
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) xc[kk] = __shfl_sync(FULL, xr[kk], partner);   // split by columns
-      mul_cols_to_rows(b, xc, zero, z);
+#pragma unroll
+      for (int kk = 0; kk < DC; ++kk) {
+        float s = Ab[kk][0] * xc[0];
+#pragma unroll
+        for (int jj = 1; jj < DC; ++jj) s = fmaf(Ab[kk][jj], xc[jj], s);
+        z[kk] = s + __shfl_xor_sync(FULL, s, 2);
+      }
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) ax[kk] = z[kk];
-      B_acc(b, kx, ax);
-      B_acc(b, mw, z);
+      B_acc(kx, ax);
+      B_acc(mw, z);
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) xr[kk] = z[kk] + wt[kk];
     }
@@ -537,7 +592,7 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
       const int s = idx / D, k = idx - s * D;
       int ph = head + s;
       ph = ph >= P ? ph - P : ph;
-      gh[s * D + k] = ring[ph * S + k * EPW].x;
+      gh[s * D + k] = ring[ph * S1 + k * EPW];
     }
   }
 }
@@ -545,7 +600,7 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
 template <int D, int M, int H, int TPB, int MINB, int WSRC>
 static int32_t launch_quad_w(const LdsArgs& a, cudaStream_t st, bool one_cta_per_sm = false) {
   using Lay = QuadLayout<D, M, H, TPB>;
-  static_assert((Lay::kSmemBytes + 1024) * MINB <= 228 * 1024, "ring + scratch + blocks do not fit shared memory");
+  static_assert((Lay::kSmemBytes + 1024) * MINB <= 228 * 1024, "ring + operators do not fit shared memory");
   auto kern = lds_gpc_quad_kernel<D, M, H, TPB, MINB, WSRC>;
   // (measurement only: asking for more than half of the SM's shared memory keeps a second CTA off the SM)
   const size_t smem = one_cta_per_sm && Lay::kSmemBytes < 120 * 1024 ? 120 * 1024 : Lay::kSmemBytes;
@@ -559,10 +614,11 @@ static int32_t launch_quad_w(const LdsArgs& a, cudaStream_t st, bool one_cta_per
 
 template <int D, int M, int H, int TPB, int MINB>
 static int32_t launch_quad(const LdsArgs& a, cudaStream_t st, bool one_cta_per_sm = false) {
-  return a.W ? launch_quad_w<D, M, H, TPB, MINB, 1>(a, st, one_cta_per_sm) : launch_quad_w<D, M, H, TPB, MINB, 2>(a, st, one_cta_per_sm);
+  return a.W ? launch_quad_w<D, M, H, TPB, MINB, 1>(a, st, one_cta_per_sm)
+             : launch_quad_w<D, M, H, TPB, MINB, 2>(a, st, one_cta_per_sm);
 }
 
-// kernel_variant 0 (automatic) or 13..15 (launch shapes 128 x 2, 64 x 4, 256 x 1)
+// kernel_variant 0 (automatic) or 13..16 (launch shapes 128 x 2, 64 x 4, 256 x 1, 128 x 1)
 bool launch_gpc_quad(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
   if (p.policy != DLC_POLICY_GPC || p.mode != DLC_MODE_CLOSED_LOOP) return false;

@@ -324,6 +324,49 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
   // counted loop with a guarded body so that the compiler does not rotate the loop and duplicate the pass.)
 #pragma unroll 1
   for (int t = 0; t <= p.T; ++t) {
+    // ================= work that does not depend on this step's window products, issued ahead of the pass so that its
+    // shuffle / shared-memory latencies run under the pass's FFMA2 stream (ring indices here: before the roll)
+    float kx[M], z[DC], nzp[DC], wt[DC];
+    {
+      float Ab[DC][DC], A9[DC][DC], wold[DC], xc[DC];
+      load_block(0, Ab);
+      load_block(Lay::oA9, A9);
+      // q_t = Abar q_(t-1) - Abar^(H-1) w[H] + w[2H-1]          (the ring only shifts: see the header)
+      {
+        int so = head + H, sn = head + 2 * H - 1;
+        so -= so >= P ? P : 0;
+        sn -= sn >= P ? P : 0;
+#pragma unroll
+        for (int jj = 0; jj < DC; ++jj) wold[jj] = rcol[so * S1 + jj * EPW];
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk) xc[kk] = __shfl_sync(FULL, xr[kk], partner);   // x split by columns
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk) {
+          float s0 = Ab[kk][0] * qcol[0], s1 = -A9[kk][0] * wold[0], s2 = Ab[kk][0] * xc[0];
+#pragma unroll
+          for (int jj = 1; jj < DC; ++jj) {
+            s0 = fmaf(Ab[kk][jj], qcol[jj], s0);
+            s1 = fmaf(-A9[kk][jj], wold[jj], s1);
+            s2 = fmaf(Ab[kk][jj], xc[jj], s2);
+          }
+          const float s = s0 + s1;
+          qrow[kk] = (s + __shfl_xor_sync(FULL, s, 2)) + rown[sn * S1 + kk * EPW];
+          z[kk] = s2 + __shfl_xor_sync(FULL, s2, 2);                   // Abar x
+        }
+#pragma unroll
+        for (int kk = 0; kk < DC; ++kk) qcol[kk] = __shfl_sync(FULL, qrow[kk], partner);
+      }
+      K_dot(xr, kx);                                                  // K x                     _lqr.py:72
+#pragma unroll
+      for (int kk = 0; kk < DC; ++kk) {
+        nzp[kk] = xr[kk] - ax[kk];                                    // x - A x_prev (the noise estimate minus B u)
+        ax[kk] = z[kk];
+        wt[kk] = wnext[kk];
+      }
+      B_acc(kx, ax);                                                  // A x = Abar x + B (K x): next step's A x_prev
+      const int tn = t + 1 < p.T ? t + 1 : (p.T > 0 ? p.T - 1 : 0);
+      if (p.T > 0) load_w(tn, wnext);
+    }
     // ================= one pass over the ring (old indexing): M += sum_h s[h] (x) w[h+i];  V[h] = sum_i M[i] w[h+i+1]
     f2 acc[HP][M];
     {
@@ -369,60 +412,31 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
     }
     if (t < p.T) {                                                    // (trip T: the pass applied the last update)
     head = (head + 1 == P) ? 0 : head + 1;                            // roll(-1)               _gpc.py:156-157
-    const int nw = P - head;                                          // new logical slot j: physical head + j (- P past nw)
-    auto slot = [&](const float* base, int j) -> const float* { return base + (head + j - (j < nw ? 0 : P)) * S1; };
-    float wt[DC];
-#pragma unroll
-    for (int kk = 0; kk < DC; ++kk) wt[kk] = wnext[kk];
-    if (t + 1 < p.T) load_w(t + 1, wnext);
+    float G[HS][DC][M];
+    load_G(G);
 
-    // ---- q_t = Abar q_(t-1) - Abar^(H-1) w[H-1] + w[2H-2]   (new indexing; both slots predate this step's noise)
-    float Ab[DC][DC];
-    load_block(0, Ab);
-    {
-      float A9[DC][DC], wold[DC];
-      load_block(Lay::oA9, A9);
-      const float* so = slot(rcol, H - 1);
-      const float* sn = slot(rown, 2 * H - 2);
-#pragma unroll
-      for (int jj = 0; jj < DC; ++jj) wold[jj] = so[jj * EPW];
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) {
-        float s0 = Ab[kk][0] * qcol[0], s1 = -A9[kk][0] * wold[0];
-#pragma unroll
-        for (int jj = 1; jj < DC; ++jj) { s0 = fmaf(Ab[kk][jj], qcol[jj], s0); s1 = fmaf(-A9[kk][jj], wold[jj], s1); }
-        const float s = s0 + s1;
-        qrow[kk] = (s + __shfl_xor_sync(FULL, s, 2)) + sn[kk * EPW];
-      }
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) qcol[kk] = __shfl_sync(FULL, qrow[kk], partner);
-    }
-
-    // ---- window products: sum over the coordinate halves, then each tap half keeps the windows of its subset
+    // ---- window products: the tap halves swap the partial sums of each other's window subset, then the coordinate
+    // halves are summed; lane (qc, qi) ends up with the complete V[h] of its subset h in [qi*HS, qi*HS + HS)
     float Vown[HS][M], mw[M];
     {
       float v[H][M];
 #pragma unroll
       for (int b = 0; b < HP; ++b)
 #pragma unroll
-        for (int c = 0; c < M; ++c) {
-          const float v0 = lo(acc[b][c]), v1 = hi(acc[b][c]);
-          v[2 * b][c] = v0 + __shfl_xor_sync(FULL, v0, 1);
-          v[2 * b + 1][c] = v1 + __shfl_xor_sync(FULL, v1, 1);
-        }
+        for (int c = 0; c < M; ++c) { v[2 * b][c] = lo(acc[b][c]); v[2 * b + 1][c] = hi(acc[b][c]); }
 #pragma unroll
       for (int hh = 0; hh < HS; ++hh)
 #pragma unroll
         for (int c = 0; c < M; ++c) {
           const float mine = qi ? v[HS + hh][c] : v[hh][c];
           const float theirs = qi ? v[hh][c] : v[HS + hh][c];
-          Vown[hh][c] = mine + __shfl_xor_sync(FULL, theirs, 2);
+          const float s = mine + __shfl_xor_sync(FULL, theirs, 2);
+          Vown[hh][c] = s + __shfl_xor_sync(FULL, s, 1);
         }
 #pragma unroll
       for (int c = 0; c < M; ++c) mw[c] = __shfl_sync(FULL, Vown[HS - 1][c], lane | 2);   // V[H-1] lives in the upper tap half
     }
-    float kx[M], u[M];
-    K_dot(xr, kx);                                                    // K x                     _lqr.py:72
+    float u[M];
 #pragma unroll
     for (int c = 0; c < M; ++c) u[c] = mw[c] - kx[c];                 // get_action              _gpc.py:171-183
 
@@ -434,13 +448,11 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) nz[kk] = 0.f;
       B_acc(un, nz);
+      int sn = head + P - 1;
+      sn -= sn >= P ? P : 0;
+      float* newest = rown + sn * S1;                                 // (both tap halves store the same values)
 #pragma unroll
-      for (int kk = 0; kk < DC; ++kk) nz[kk] = (xr[kk] - ax[kk]) - nz[kk];
-      if (qi == 0) {
-        float* newest = const_cast<float*>(slot(rown, P - 1));
-#pragma unroll
-        for (int kk = 0; kk < DC; ++kk) newest[kk * EPW] = nz[kk];
-      }
+      for (int kk = 0; kk < DC; ++kk) newest[kk * EPW] = nzp[kk] - nz[kk];
     }
     __syncwarp();
 
@@ -448,8 +460,6 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
     const float lr = p.decay ? p.lr_scale * (1.0f / (float)(p.t0 + t + 1)) : p.lr_scale;
     float sown[HS][M], du[M];
     {
-      float G[HS][DC][M];
-      load_G(G);
       float yf[DC];
 #pragma unroll
       for (int kk = 0; kk < DC; ++kk) {
@@ -535,25 +545,10 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
       }
     }
 
-    // ---- env: x <- (A x + B u) + w_t = (Abar x + B mw) + w_t;  A x = Abar x + B (K x)          _lds.py:102-111
-    {
-      float xc[DC], z[DC];
+    // ---- env: x <- (A x + B u) + w_t = (Abar x + B mw) + w_t                                   _lds.py:102-111
+    B_acc(mw, z);
 #pragma unroll
-      for (int kk = 0; kk < DC; ++kk) xc[kk] = __shfl_sync(FULL, xr[kk], partner);   // split by columns
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) {
-        float s = Ab[kk][0] * xc[0];
-#pragma unroll
-        for (int jj = 1; jj < DC; ++jj) s = fmaf(Ab[kk][jj], xc[jj], s);
-        z[kk] = s + __shfl_xor_sync(FULL, s, 2);
-      }
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) ax[kk] = z[kk];
-      B_acc(kx, ax);
-      B_acc(mw, z);
-#pragma unroll
-      for (int kk = 0; kk < DC; ++kk) xr[kk] = z[kk] + wt[kk];
-    }
+    for (int kk = 0; kk < DC; ++kk) xr[kk] = z[kk] + wt[kk];
     }  // t < T
   }
 

@@ -152,7 +152,10 @@ def test_resume_is_identical_and_inputs_untouched():
 
 @pytest.mark.parametrize("variant", [0, 8, 11])
 def test_resume_long_history(variant):
-    """H = HH = 10 (slot-paired noise ring in the packed kernel): split rollouts continue bit-identically."""
+    """H = HH = 10: split rollouts continue bit-identically in the packed kernel (slot-paired noise ring, variants
+    8 / 11).  The quad-split kernel (variant 0) keeps the noise part of the counterfactual state as a sliding sum q
+    (exact algebra, lds_gpc_quad.cu) that it re-forms from the ring on entry, so a resumed rollout agrees with the
+    uninterrupted one to rounding (1e-6 relative), not bit for bit."""
     from deluca_b200.fused import lds_rollout
     N, T, d, m = 45, 70, 10, 3
     A, B, K, x0, W = _problem(N, d, m, T, seed=5)
@@ -162,6 +165,10 @@ def test_resume_long_history(variant):
     h1 = lds_rollout(dA, dB, dK, dx, 27, W=dW[:27].contiguous(), **kw)
     h2 = lds_rollout(dA, dB, dK, h1.x, T - 27, W=dW[27:].contiguous(), M=h1.M, hist=h1.hist,
                      xprev=h1.xprev, uprev=h1.uprev, t0=h1.t, **kw)
+    if variant == 0:
+        close = lambda a, b: bool(((a - b).abs() <= 1e-6 * b.abs().max()).all())
+        assert close(h2.costs, full.costs[27:]) and close(h2.x, full.x) and close(h2.M, full.M) and close(h2.hist, full.hist)
+        return
     assert torch.equal(full.costs[27:], h2.costs)
     assert torch.equal(full.x, h2.x) and torch.equal(full.M, h2.M) and torch.equal(full.hist, h2.hist)
 

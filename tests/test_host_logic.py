@@ -166,3 +166,35 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-L", libdir, "-ldeluca_b200", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", (out.returncode, out.stdout, out.stderr)
+
+
+def test_xla_ffi_translation_unit_type_checks():
+    """deluca_b200/csrc/xla_ffi/deluca_xla_ffi.cc (the XLA FFI custom-call handlers north_star names) compiles both
+    without jaxlib's header (guarded: an empty TU) and against an API-shaped stand-in of `xla/ffi/api/ffi.h`
+    (tests/xla_ffi_stub) whose Bind().To() static_asserts that every handler is invocable with exactly the bound
+    context / argument / attribute / result types -- i.e. the binding chains and the C-ABI calls are type-checked."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    tu = os.path.join(ROOT, "deluca_b200", "csrc", "xla_ffi", "deluca_xla_ffi.cc")
+    base = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "include")]
+    subprocess.run(base + [tu], check=True)
+    r = subprocess.run(base + ["-I" + os.path.join(ROOT, "tests", "xla_ffi_stub"), tu], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # a handler whose signature drifts from its binding must fail the check (the stub is not vacuous)
+    src = open(tu).read().replace("int32_t policy, int32_t T, int32_t H,", "int32_t policy, int64_t T, float H,", 1)
+    bad = os.path.join(ROOT, "tests", "xla_ffi_stub", "_drifted.cc")
+    try:
+        open(bad, "w").write(src)
+        r = subprocess.run(base + ["-I" + os.path.join(ROOT, "tests", "xla_ffi_stub"), bad], capture_output=True, text=True)
+        # (int32 attributes convert implicitly to int64 / float in C++, so invocability alone cannot see THIS drift;
+        # what it must see is an arity / buffer-type drift)
+        src2 = open(tu).read().replace(".Attr<int32_t>(\"policy\")", "", 1)
+        open(bad, "w").write(src2)
+        r2 = subprocess.run(base + ["-I" + os.path.join(ROOT, "tests", "xla_ffi_stub"), bad], capture_output=True, text=True)
+        assert r2.returncode != 0 and "handler signature does not match" in r2.stderr
+    finally:
+        if os.path.exists(bad):
+            os.remove(bad)

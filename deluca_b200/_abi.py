@@ -108,6 +108,16 @@ class DlcPlanParams(ctypes.Structure):
     ]
 
 
+class DlcEnvAgentParams(ctypes.Structure):
+    _fields_ = [
+        ("N", ctypes.c_int64), ("T", ctypes.c_int32), ("agent", ctypes.c_int32), ("env", DlcEnvSpec),
+        ("gains_per_env", ctypes.c_int32), ("state_stride", ctypes.c_int32), ("want_grad", ctypes.c_int32),
+        ("pid_decay", ctypes.c_float),
+        ("q", ctypes.c_float * 8), ("goal", ctypes.c_float * 8), ("r", ctypes.c_float * 4),
+        ("goal_u", ctypes.c_float * 4),
+    ]
+
+
 POLICY = {"lqr": 0, "gpc": 1, "bpc": 2, "open": 3}
 
 # every symbol include/deluca_b200.h declares: name -> (restype, argtypes)
@@ -155,6 +165,7 @@ SYMBOLS = {
                                                    ctypes.c_float, ctypes.c_int32, _P]),
     "dlc_gae_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_int32, _P, _P, _P]),
+    "dlc_env_agent_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcEnvAgentParams)] + [_P] * 11),
     "dlc_env_collect_f32": (ctypes.c_int32, [ctypes.POINTER(DlcEnvSpec), ctypes.c_int64, ctypes.c_int32,
                                              ctypes.c_uint64, ctypes.c_int64, ctypes.c_float, _P, _P, _P, _P, _P]),
     "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),

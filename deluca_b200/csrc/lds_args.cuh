@@ -14,7 +14,6 @@ struct LdsArgs {
   float *x_out, *u_out;
   int32_t* status_out;
   float* ws;
-  int phase_delay;   // internal: cycles by which every second co-resident CTA / warp set is delayed (0 = off)
 };
 
 // packed-FFMA2 lane-split GPC kernel (lds_rollout_f2.cu).  Returns false if (d,m,H,HH) has no instantiation.

@@ -951,10 +951,6 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
   a.eps_io = bpc_eps_io; a.eps_new = bpc_eps_new;
   a.cost_out = cost_out; a.cost_sum_out = cost_sum_out; a.x_out = x_out; a.u_out = u_out;
   a.status_out = status_out; a.ws = (float*)workspace;
-  {
-    static const int delay = []() { const char* e = getenv("DLC_PHASE_DELAY"); return e ? atoi(e) : 0; }();
-    a.phase_delay = delay;
-  }
   cudaStream_t st = (cudaStream_t)stream;
   int32_t rc = DLC_OK;
   if (launch_bpc(a, bpc_cost_io, st, &rc)) return rc;

@@ -5,7 +5,7 @@ tensors are torch CUDA tensors used purely as device-memory handles; every numbe
 by ``libdeluca_b200.so``.
 """
 import ctypes
-from typing import Optional
+from typing import NamedTuple, Optional
 
 import torch
 
@@ -487,6 +487,73 @@ def gae(losses, values, log_probs=None, done_masks=None, discount=0.99, gae_para
                     int(returns_use_values), _abi.ptr(adv), _abi.ptr(ret))
     _abi.check(rc, "dlc_gae_f32")
     return adv, ret
+
+
+class EnvAgentResult(NamedTuple):
+    x: torch.Tensor                 # [N,d] final env state
+    agent_state: Optional[tuple]    # PID: (P, I, D) each [N,d]
+    losses: Optional[torch.Tensor]  # [T,N]
+    actions: Optional[torch.Tensor] # [T,N,da]
+    loss_sum: torch.Tensor          # [N] float64
+    grad: Optional[torch.Tensor]    # [N,ng] d(sum_t loss)/d(gains)
+    agent_stack: Optional[torch.Tensor]  # [T // state_stride, N, 3, d]
+    x_stack: Optional[torch.Tensor]      # [T // state_stride, N, d]
+    status: torch.Tensor
+
+
+def env_agent_rollout(env, cost, agent, gains, x0, T, *, pid_state=None, pid_decay=0.0, keep_losses=True,
+                      keep_actions=True, state_stride=0, want_grad=False, donate=False):
+    """``dlc_env_agent_rollout_f32``: ``apg_rollout`` x ``vmap`` (``deluca/training/apg.py:39-100``) of a classic env
+    under the generic PID agent (``agent="pid"``, ``gains`` [3] or [N,3]) or linear state feedback (``"linear"``,
+    ``gains`` [m,d] or [N,m,d], u = -K x) with the quadratic loss ``cost`` (an object with ``vectors(d,m)`` /
+    ``action_goal(m)``: sum q (x - goal)^2 + sum r (u - goal_u)^2)."""
+    N, d = x0.shape
+    m = env.action_dim
+    _f32(x0, "x0", (N, env.state_dim))
+    pid = agent == "pid"
+    if not pid and agent != "linear":
+        raise ValueError("agent must be 'pid' or 'linear'")
+    ng, da = (3, d) if pid else (m * d, m)
+    _f32(gains, "gains")
+    shp = (3,) if pid else (m, d)
+    if tuple(gains.shape) not in (shp, (N,) + shp):
+        raise ValueError(f"gains must be {shp} (shared) or {(N,) + shp} (one set per env), got {tuple(gains.shape)}")
+    p = _abi.DlcEnvAgentParams()
+    p.N, p.T, p.agent = N, int(T), 0 if pid else 1
+    p.env.kind, vals = env.spec()
+    for i, v in enumerate(vals):
+        p.env.p[i] = v
+    p.gains_per_env = int(gains.dim() == (2 if pid else 3))
+    p.state_stride, p.want_grad, p.pid_decay = int(state_stride), int(bool(want_grad)), float(pid_decay)
+    q, r, goal = cost.vectors(d, m)
+    gu = cost.action_goal(m)
+    for i in range(d):
+        p.q[i], p.goal[i] = q[i], goal[i]
+    for i in range(m):
+        p.r[i], p.goal_u[i] = r[i], gu[i]
+    dev = x0.device
+    x_io = x0 if donate else x0.clone()
+    a_io = None
+    if pid:
+        if pid_state is None:
+            a_io = torch.zeros(N, 3, d, device=dev)
+        else:
+            a_io = torch.stack([torch.as_tensor(s, dtype=torch.float32, device=dev).expand(N, d) for s in pid_state], 1)
+            a_io = a_io.contiguous()
+    losses = torch.empty(T, N, device=dev) if keep_losses else None
+    actions = torch.empty(T, N, da, device=dev) if keep_actions else None
+    ns = T // state_stride if state_stride > 0 else 0
+    a_stack = torch.empty(ns, N, 3, d, device=dev) if (ns and pid) else None
+    x_stack = torch.empty(ns, N, d, device=dev) if ns else None
+    lsum = torch.empty(N, dtype=torch.float64, device=dev)
+    grad = torch.empty(N, ng, device=dev) if want_grad else None
+    status = torch.empty(N, dtype=torch.int32, device=dev)
+    rc = _launch_on(x0, _abi.lib().dlc_env_agent_rollout_f32, ctypes.byref(p), _abi.ptr(gains), _abi.ptr(x_io),
+                    _abi.ptr(a_io), _abi.ptr(losses), _abi.ptr(actions), _abi.ptr(a_stack), _abi.ptr(x_stack),
+                    _abi.ptr(lsum), _abi.ptr(grad), _abi.ptr(status))
+    _abi.check(rc, "dlc_env_agent_rollout_f32")
+    st = (a_io[:, 0], a_io[:, 1], a_io[:, 2]) if pid else None
+    return EnvAgentResult(x_io, st, losses, actions, lsum, grad, a_stack, x_stack, status)
 
 
 def env_collect(env, x0, T, seed=0, env_offset=0, action_std=1.0):

@@ -375,6 +375,46 @@ int32_t dlc_plan_f32(const DlcPlanParams* p,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * The functional Env / Agent rollout on the classic envs: apg_rollout x vmap (deluca/training/apg.py:39-100) with
+ *     agent = generic PID acting on the observation vector (deluca/agents/_pid.py:20-48; the env consumes
+ *             action[:m], as Pendulum does with action[0], _pendulum.py:65) or linear state feedback u = -K x
+ *             (deluca/agents/_lqr.py:62-72 on the env's state vector),
+ *     env   = Pendulum / Cartpole (intent-fixed, SURVEY A-7) / PlanarQuadrotor / Reacher,
+ *     loss  = sum_i q_i (x_i - goal_i)^2 + sum_j r_j (u_j - goal_u_j)^2 on (env_state.arr, action[:m]) of the state
+ *             the agent saw (apg.py:54) -- the quadratic family; arbitrary Python loss functions have no CUDA path.
+ * Emits Rollout(agent_states, actions, losses) (apg.py:68): losses [T,N], actions [T,N,da] (da = d for PID, m for linear
+ * feedback), agent / env state stacks every `state_stride` steps, and -- with want_grad -- d(sum_t loss)/d(gains) per env
+ * by forward-mode tangents: what jax.value_and_grad(apg_loss) (apg.py:103-122,152-167) yields for the agent's leaves.
+ * ------------------------------------------------------------------------------------ */
+#define DLC_AGENT_PID 0
+#define DLC_AGENT_LINEAR 1
+
+typedef struct DlcEnvAgentParams {
+  int64_t N;           /* episodes */
+  int32_t T;           /* steps (unroll_length) */
+  int32_t agent;       /* DLC_AGENT_* */
+  DlcEnvSpec env;
+  int32_t gains_per_env; /* 1: gains is [N,ng]; 0: [ng] shared (ng = 3 for PID: K_P, K_I, K_D; m*d for linear feedback) */
+  int32_t state_stride;  /* > 0: stack the agent / env state after every state_stride-th step; 0: final state only */
+  int32_t want_grad;
+  float pid_decay;     /* dt / (dt + RC), _pid.py:37-38 */
+  float q[DLC_PLAN_MAXD], goal[DLC_PLAN_MAXD], r[DLC_PLAN_MAXM], goal_u[DLC_PLAN_MAXM];
+} DlcEnvAgentParams;
+
+int32_t dlc_env_agent_rollout_f32(const DlcEnvAgentParams* p,
+                                  const float* gains,       /* [N,ng] or [ng] */
+                                  float* x_io,              /* [N,d] env state (arr): start in, final out */
+                                  float* agent_io,          /* PID: [N,3,d] (P, I, D); NULL for linear feedback */
+                                  float* loss_out,          /* [T,N] or NULL */
+                                  float* action_out,        /* [T,N,da] or NULL */
+                                  float* agent_stack_out,   /* [T/state_stride,N,3,d] or NULL */
+                                  float* x_stack_out,       /* [T/state_stride,N,d] or NULL */
+                                  double* loss_sum_out,     /* [N] or NULL */
+                                  float* grad_out,          /* [N,ng] d(sum_t loss)/d(gains), required with want_grad */
+                                  int32_t* status_out,      /* [N] or NULL */
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Shared-dynamics LDS + LQR rollout on the tensor cores (tcgen05, TF32 x3 split, fp32 accumulate in TMEM).
  * When A, B, K are shared by all envs (jax.vmap in_axes=None) the batch is the N dimension of a GEMM:
  *     [x_{t+1} - w_t ; u_t] = [A - B K ; -K] X_t,   cost_t = x_t'x_t + u_t'u_t

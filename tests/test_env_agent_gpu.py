@@ -1,0 +1,201 @@
+"""`apg_rollout` / `apg_parallel_rollouts` / `value_and_grad(apg_loss)` (deluca/training/apg.py:39-122,152-167) on the
+classic envs through the fused env x agent kernel (dlc_env_agent_rollout_f32):
+
+* Pendulum x generic PID against the reference's OWN files run on the shim (tests/golden/ref_drivers.npz): losses,
+  actions, the stacked PID states, the mean loss and d mean-loss / d (K_P, K_I, K_D);
+* every classic env x {PID, linear feedback} against the float64 numpy oracle (oracle/env_agent.py), gradients included;
+* strided state stacks, chunked resume, Q,R-weighted quad loss on LDS x LQR, lung x lung-PID through the same driver.
+
+Tolerance: 1e-4 relative (BASELINE.json north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-4
+
+
+def _close(a, b, rtol=RTOL, what=""):
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    scale = max(np.abs(b).mean(), 1e-30)
+    err = np.abs(a - b) / np.maximum(np.abs(b), scale)
+    assert np.isfinite(a).all() and err.max() < rtol, f"{what}: max rel err {err.max():.3e}"
+
+
+def test_pendulum_pid_apg_matches_reference_files():
+    from deluca_b200.agents._pid import PID, PIDState
+    from deluca_b200.envs.classic import Pendulum
+    from deluca_b200.envs.classic._pendulum import PendulumState
+    from deluca_b200.training.apg import QuadLoss, apg_loss, apg_parallel_rollouts, apg_rollout, value_and_grad_apg_loss
+    g = np.load(os.path.join(GOLD, "ref_drivers.npz"))
+    N, T = g["out_apg_losses"].shape
+    arr0 = torch.tensor(g["in_apg_arr0"], dtype=torch.float32, device="cuda")
+    kp, ki, kd = (float(v) for v in g["in_apg_gains"])
+    env = Pendulum.create()
+    agent = PID.create(K_P=kp, K_I=ki, K_D=kd)
+    st = PendulumState(arr=arr0, h=0)
+    ast = PIDState(P=torch.zeros(N, 3, device="cuda"), I=torch.zeros(N, 3, device="cuda"),
+                   D=torch.zeros(N, 3, device="cuda"))
+    loss = QuadLoss(q=1.0, r=0.1)                                     # sum (arr - goal_state)^2 + 0.1 action[0]^2
+    ro, final = apg_parallel_rollouts(env, st, arr0, agent, ast, T, loss)
+    assert ro.losses.shape == (N, T) and ro.actions.shape == (N, T, 3) and ro.agent_states.P.shape == (N, T, 3)
+    _close(ro.losses, g["out_apg_losses"], what="losses")
+    _close(ro.actions, g["out_apg_actions"], what="actions")
+    for k in "PID":
+        _close(getattr(ro.agent_states, k), g[f"out_apg_{k}"], what=f"agent_states.{k}")
+    assert final.h == T and final.arr.shape == (N, 3)
+    _close(apg_loss(agent, env, st, arr0, ast, T, loss), g["out_apg_mean_loss"], what="apg_loss")
+    one = apg_rollout(env, PendulumState(arr=arr0[0], h=0), arr0[0], agent, PIDState(P=0.0, I=0.0, D=0.0), T, loss)[0]
+    _close(one.losses[0], g["out_apg_single_losses"], what="apg_rollout")
+    val, grad = value_and_grad_apg_loss(agent, env, st, arr0, ast, T, loss)
+    _close(val, g["out_apg_value"], what="value")
+    _close(torch.stack([grad.K_P, grad.K_I, grad.K_D]), g["out_apg_grad"], what="grad")
+
+
+def _envs():
+    from deluca_b200.envs.classic import Cartpole, Pendulum, PlanarQuadrotor, Reacher
+    from oracle import igpc as G
+    return [("pendulum", Pendulum.create(), G.Pendulum(), [0.0]),
+            ("cartpole", Cartpole.create(), G.Cartpole(), [0.0]),
+            ("quad", PlanarQuadrotor.create(wind=0.1), G.PlanarQuadrotor(wind=0.1), [0.4905, 0.4905]),
+            ("reacher", Reacher.create(), G.Reacher(), [0.0, 0.0])]
+
+
+@pytest.mark.parametrize("idx", range(4))
+@pytest.mark.parametrize("agent", ["pid", "linear"])
+def test_env_agent_kernel_matches_oracle(idx, agent):
+    from deluca_b200 import fused
+    from deluca_b200.envs.classic._pendulum import QuadCost
+    from oracle import env_agent as E
+    name, env, oenv, gu = _envs()[idx]
+    rng = np.random.default_rng(10 + idx)
+    N, T = 300, 40
+    d, m = oenv.d, oenv.m
+    x0 = oenv.init(N, np.float64) + 0.05 * rng.standard_normal((N, d))
+    goal = np.asarray(getattr(oenv, "goal_state", np.zeros(d)), np.float64)
+    q, r = np.linspace(0.5, 1.5, d), np.linspace(0.1, 0.2, m)
+    if agent == "pid":
+        gains = np.array([0.05, 0.02, 0.01]) * (1 + 0.2 * rng.standard_normal((N, 3)))
+    else:
+        gains = 0.03 * rng.standard_normal((N, m, d))
+    ref = E.rollout(oenv, agent, gains, x0, T, q, goal, r, gu, pid_decay=0.0566, want_grad=True)
+    cost = QuadCost(goal.tolist(), q.tolist(), r.tolist(), gu)
+    cu = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda").contiguous()
+    res = fused.env_agent_rollout(env, cost, agent, cu(gains), cu(x0), T, pid_decay=0.0566, state_stride=8,
+                                  want_grad=True)
+    assert int((res.status != 0).sum()) == 0
+    _close(res.losses, ref["losses"], what=f"{name} losses")
+    _close(res.actions, ref["actions"], what=f"{name} actions")
+    _close(res.x, ref["X"][-1], what=f"{name} final state")
+    _close(res.x_stack, ref["X"][8::8], what=f"{name} state stack")
+    _close(res.loss_sum, ref["losses"].sum(0), what=f"{name} loss sums")
+    gref = ref["grad"]
+    gerr = np.abs(res.grad.cpu().numpy() - gref) / np.maximum(np.abs(gref), np.abs(gref).mean())
+    assert gerr.max() < 5 * RTOL, f"{name} {agent} grad: {gerr.max():.3e}"    # T-step products of Jacobians in fp32
+    if agent == "pid":
+        _close(res.agent_stack[:, :, 1], ref["I"][7::8], what=f"{name} I stack")
+        _close(res.agent_state[2], ref["D"][-1], what=f"{name} final D")
+        # chunked resume == one launch (bit-exact: the carried state is the whole state)
+        a = fused.env_agent_rollout(env, cost, agent, cu(gains), cu(x0), 16, pid_decay=0.0566)
+        b = fused.env_agent_rollout(env, cost, agent, cu(gains), a.x, T - 16, pid_state=a.agent_state, pid_decay=0.0566)
+        assert torch.equal(torch.cat([a.losses, b.losses]), res.losses) and torch.equal(b.x, res.x)
+    # shared gains: one set for every env
+    g0 = gains[0]
+    ref0 = E.rollout(oenv, agent, g0, x0, T, q, goal, r, gu, pid_decay=0.0566)
+    res0 = fused.env_agent_rollout(env, cost, agent, cu(g0), cu(x0), T, pid_decay=0.0566, keep_actions=False)
+    assert res0.actions is None
+    _close(res0.losses, ref0["losses"], what=f"{name} shared-gain losses")
+
+
+def test_apg_linear_feedback_value_and_grad_on_cartpole():
+    """value_and_grad(apg_loss) for an LQR-type agent (leaf K) on Cartpole x QuadLoss, vs the oracle's tangents."""
+    from deluca_b200.agents._lqr import LQR
+    from deluca_b200.envs.classic import Cartpole
+    from deluca_b200.envs.classic._cartpole import CartpoleState
+    from deluca_b200.training.apg import QuadLoss, apg_parallel_rollouts, value_and_grad_apg_loss
+    from oracle import env_agent as E, igpc as G
+    rng = np.random.default_rng(2)
+    N, T = 64, 50
+    oenv = G.Cartpole()
+    x0 = 0.1 * rng.standard_normal((N, 4))
+    K = np.array([[0.1, 0.3, 2.0, 0.5]])
+    ref = E.rollout(oenv, "linear", K, x0, T, np.ones(4), np.zeros(4), [0.1], [0.0], want_grad=True)
+    env = Cartpole.create()
+    agent = LQR(0.9 * torch.eye(4), torch.ones(4, 1))
+    agent.K = torch.tensor(K, dtype=torch.float32, device="cuda")          # the leaf jax.value_and_grad differentiates
+    st = CartpoleState(arr=torch.tensor(x0, dtype=torch.float32, device="cuda"), h=0)
+    loss = QuadLoss(goal=[0.0] * 4, q=1.0, r=0.1)
+    ro, _ = apg_parallel_rollouts(env, st, st.arr, agent, None, T, loss)
+    _close(ro.losses, ref["losses"].T, what="losses")
+    val, gK = value_and_grad_apg_loss(agent, env, st, st.arr, None, T, loss)
+    _close(val, ref["losses"].mean(), what="value")
+    _close(gK, ref["grad"].sum(0).reshape(1, 4) / (N * T), rtol=5 * RTOL, what="dK")
+
+
+def test_apg_rejects_python_loss_and_unknown_pairs_loudly():
+    from deluca_b200.agents._pid import PID, PIDState
+    from deluca_b200.envs.classic import Pendulum
+    from deluca_b200.training.apg import apg_parallel_rollouts
+    env = Pendulum.create()
+    st, _ = env.init(N=4)
+    with pytest.raises(NotImplementedError):
+        apg_parallel_rollouts(env, st, st.arr, PID.create(K_P=1.0), PIDState(), 5, lambda *a: 0.0)
+
+
+def test_apg_lds_lqr_weighted_quad_loss_and_strided_agent_states():
+    from deluca_b200.agents._gpc import GPC, quad_loss
+    from deluca_b200.agents._lqr import LQR
+    from deluca_b200.envs._lds import LDS, LDSState
+    from deluca_b200.training.apg import QuadLoss, apg_parallel_rollouts
+    from oracle import lds as OL
+    torch.manual_seed(0)
+    N, d, m, T = 128, 10, 3, 24
+    A = torch.diag_embed(0.9 + 0.05 * torch.rand(N, d)).cuda()
+    B = (torch.randn(N, d, m) / d ** 0.5).cuda()
+    env = LDS.create(state_size=d, action_size=m, A=A, B=B, key=11)
+    x0 = torch.randn(N, d, device="cuda")
+    q = np.linspace(0.5, 2.0, d); r = np.linspace(0.1, 0.3, m)
+    agent = LQR(A, B)
+    W = 0.1 * torch.randn(T, N, d, device="cuda")
+    ro, fin = apg_parallel_rollouts(env, LDSState(x=x0, t=0), x0, agent, None, T,
+                                    QuadLoss(goal=[0.0] * d, q=q.tolist(), r=r.tolist()), disturbances=W)
+    # oracle: x' = A x + B u + w, u = -K x ; loss_t = sum q x_t^2 + sum r u_t^2
+    c = lambda t: t.detach().cpu().double().numpy()
+    x, K = c(x0), c(agent.K)
+    ref = np.zeros((N, T))
+    for t in range(T):
+        u = -np.einsum("nmd,nd->nm", K, x)
+        ref[:, t] = (q * x * x).sum(1) + (r * u * u).sum(1)
+        x = np.einsum("nij,nj->ni", c(A), x) + np.einsum("nim,nm->ni", c(B), u) + c(W[t])
+    _close(ro.losses, ref, what="weighted LQR losses")
+    _close(fin.x, x, what="final state")
+    # strided GPC agent states: chunked launches == one launch
+    gpc = GPC.create(A=A, B=B, H=3, HH=4, lr_scale=1e-4)
+    s0 = gpc.init(N=N)
+    full, _ = apg_parallel_rollouts(env, LDSState(x=x0, t=0), x0, gpc, s0, T, quad_loss, disturbances=W)
+    stk, _ = apg_parallel_rollouts(env, LDSState(x=x0, t=0), x0, gpc, s0, T, quad_loss, disturbances=W, state_stride=8)
+    assert stk.agent_states.M.shape[:2] == (N, 3)
+    assert torch.equal(stk.losses, full.losses) and torch.equal(stk.agent_states.M[:, -1], full.agent_states.M)
+
+
+@pytest.mark.parametrize("sim", ["balloon", "delay"])
+def test_apg_lung_pid_through_driver(sim):
+    from deluca_b200.lung.controllers._pid import PID
+    from deluca_b200.lung.envs._balloon_lung import BalloonLung
+    from deluca_b200.lung.envs._delay_lung import DelayLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    from deluca_b200.training.apg import LungLoss, apg_parallel_rollouts
+    env = BalloonLung.create() if sim == "balloon" else DelayLung.create()
+    K = torch.tensor([[1.0, 0.5, 0.0], [3.0, 1.0, 0.1], [0.2, 2.0, 0.0]])
+    ctrl = PID.create(params=K)
+    T = 60
+    ro, fin = apg_parallel_rollouts(env, None, None, ctrl, None, T, LungLoss("l1"))
+    res = run_controller_scan(ctrl, T=T, dt=env.dt, env=env)
+    ts = res["timeseries"]
+    assert ro.losses.shape == (3, T) and ro.actions.shape == (3, T, 2)
+    assert torch.equal(ro.losses, (ts["target"] - ts["pressure"]).abs())
+    assert torch.equal(ro.actions[..., 0], ts["u_in"]) and torch.equal(ro.actions[..., 1], ts["u_out"])

@@ -285,3 +285,47 @@ def test_fixture_generator_reproduces_committed_files():
         assert sorted(new.files) == sorted(old.files)
         for k in old.files:
             np.testing.assert_allclose(new[k], old[k], rtol=1e-12, atol=1e-12, err_msg=k)
+
+
+def test_env_agent_oracle_equals_reference_apg_rollout():
+    """`apg_parallel_rollouts` / `apg_rollout` / `jax.value_and_grad(apg_loss)` (deluca/training/apg.py:39-122) run
+    literally on Pendulum x generic PID: losses, actions, the stacked PID states, the mean loss and its gradient
+    w.r.t. (K_P, K_I, K_D)."""
+    from oracle import env_agent as E, igpc as G
+    g = _load("drivers")
+    env = G.Pendulum()
+    N, T = g["out_apg_losses"].shape
+    r = E.rollout(env, "pid", g["in_apg_gains"], g["in_apg_arr0"], T, [1, 1, 1], env.goal_state, [0.1], [0.0],
+                  pid_decay=0.03 / (0.03 + 0.5), want_grad=True)
+    tm = lambda a: a.transpose(1, 0, 2)
+    np.testing.assert_allclose(r["losses"].T, g["out_apg_losses"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(tm(r["actions"]), g["out_apg_actions"], rtol=1e-12, atol=1e-12)
+    for k in "PID":
+        np.testing.assert_allclose(tm(r[k]), g[f"out_apg_{k}"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(r["losses"][:, 0], g["out_apg_single_losses"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(r["losses"].mean(), g["out_apg_value"], rtol=1e-12)
+    np.testing.assert_allclose(r["grad"].sum(0) / (N * T), g["out_apg_grad"], rtol=1e-9)
+
+
+def test_env_agent_oracle_tangents_equal_finite_differences():
+    """Forward-mode tangents of the oracle against central differences, for every env and both agents."""
+    from oracle import env_agent as E, igpc as G
+    rng = np.random.default_rng(3)
+    N, T = 3, 15
+    for env, x0, gu in ((G.Pendulum(), None, [0.0]), (G.Cartpole(), None, [0.0]),
+                        (G.PlanarQuadrotor(wind=0.1), None, [0.4905, 0.4905]), (G.Reacher(), None, [0.0, 0.0])):
+        d, m = env.d, env.m
+        x0 = env.init(N, np.float64) + 0.05 * rng.standard_normal((N, d))
+        goal = np.asarray(getattr(env, "goal_state", np.zeros(d)), np.float64)
+        for agent, gains in (("pid", np.array([0.05, 0.02, 0.01])), ("linear", 0.03 * rng.standard_normal((m, d)))):
+            kw = dict(q=np.ones(d), goal=goal, r=0.1 * np.ones(m), goal_u=gu, pid_decay=0.0566)
+            r = E.rollout(env, agent, gains, x0, T, want_grad=True, **kw)
+            flat = gains.reshape(-1)
+            for k in range(flat.size):
+                h = 1e-6
+                gp, gm = flat.copy(), flat.copy()
+                gp[k] += h; gm[k] -= h
+                lp = E.rollout(env, agent, gp.reshape(gains.shape), x0, T, **kw)["losses"].sum(0)
+                lm = E.rollout(env, agent, gm.reshape(gains.shape), x0, T, **kw)["losses"].sum(0)
+                fd = (lp - lm) / (2 * h)
+                np.testing.assert_allclose(r["grad"][:, k], fd, rtol=2e-5, atol=1e-6 * np.abs(fd).max())

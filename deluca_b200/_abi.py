@@ -55,7 +55,7 @@ class DlcLungParams(ctypes.Structure):
         ("R", ctypes.c_float), ("dt", ctypes.c_float), ("min_volume", ctypes.c_float), ("r0", ctypes.c_float),
         ("r0_sq", ctypes.c_float), ("leak_coef", ctypes.c_float),
         ("delay", ctypes.c_int32), ("d_R", ctypes.c_float), ("d_C", ctypes.c_float), ("inertia", ctypes.c_float),
-        ("control_gain", ctypes.c_float), ("mode", ctypes.c_int32),
+        ("control_gain", ctypes.c_float), ("mode", ctypes.c_int32), ("kernel_variant", ctypes.c_int32),
     ]
 
 

@@ -3,6 +3,7 @@
 // ring); per step five/six coalesced 4-byte stores per thread ([T,N] time-major series), which is
 // what bounds the kernel (HBM writes).
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -86,8 +87,8 @@ __device__ __forceinline__ float fmod_fast(float t, float period, float inv_peri
 // in a segment, so the knot search (searchsorted(side='right') clipped to [1, NK-1], as jnp.interp) only runs when
 // x leaves the cached segment; the values are the same either way.
 struct Seg {
-  float x0, x1, f0, sl;
-};
+  float x0, w, f0, sl;   // w = x1 - x0 (as computed in float32: x in [x0, x1) <=> 0 <= x - x0 < w up to that rounding,
+};                       // and an x within rounding of x1 interpolates to the same value from either side)
 
 template <int NK>
 __device__ __forceinline__ void seg_search(const DlcLungParams& p, const float* kf, float x, Seg& s) {
@@ -109,14 +110,24 @@ __device__ __forceinline__ void seg_search(const DlcLungParams& p, const float* 
     x0 = p.kx[i - 1]; x1 = p.kx[i]; f0 = kf[i - 1]; f1 = kf[i];
   }
   const float dx = x1 - x0;
-  s.x0 = x0; s.x1 = x1; s.f0 = f0;
+  s.x0 = x0; s.w = dx; s.f0 = f0;
   s.sl = dx == 0.f ? 0.f : __fdiv_rn(f1 - f0, dx);
 }
 
+// The hit test is ONE unsigned compare on x - x0 (which the interpolant needs anyway): a negative or NaN difference
+// has its sign / exponent bits above any finite positive width.  The miss is voted warp-wide so that the common
+// path carries no divergence bookkeeping (BSSY / BSYNC).
 template <int NK>
-__device__ __forceinline__ float interp_seg(const DlcLungParams& p, const float* kf, float x, Seg& s) {
-  if (__builtin_expect(!(s.x0 <= x && x < s.x1), 0)) seg_search<NK>(p, kf, x, s);
-  return fmaf(x - s.x0, s.sl, s.f0);
+__device__ __forceinline__ float interp_seg(const DlcLungParams& p, const float* kf, float x, Seg& s, unsigned mask) {
+  float d = x - s.x0;
+  const bool miss = !(__float_as_uint(d) < __float_as_uint(s.w)) || !(s.x0 <= x);
+  if (__builtin_expect(__any_sync(mask, miss), 0)) {
+    if (miss) {
+      seg_search<NK>(p, kf, x, s);
+      d = x - s.x0;
+    }
+  }
+  return fmaf(d, s.sl, s.f0);
 }
 
 // tanh(z) + 1 = 2 e / (1 + e), e = exp(2z): relative accuracy ~3e-7 everywhere (tanhf(z) + 1 loses it for z << 0);
@@ -145,6 +156,7 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   const DlcLungBuffers& b = a.b;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= p.N) return;
+  const unsigned lanes = __activemask();   // the warp's live lanes: constant from here on (no early exits below)
   float kf[DLC_MAX_KNOTS];
   {
     const float* g = b.kf + (p.kf_per_env ? n * p.nk : 0);
@@ -169,14 +181,20 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   // the caller's histories are [N, delay]: a full CTA owns one contiguous chunk and copies it with coalesced
   // accesses (the per-thread rows are 4 * delay bytes apart); the last, partial CTA copies row by row
   const bool full_cta = (int64_t)(blockIdx.x + 1) * blockDim.x <= p.N;
-  if (SIM == DLC_SIM_DELAY) {
+  // The episode only WRITES the histories (the simulator reads the current action, _delay_lung.py:88-96), so after
+  // T >= delay steps nothing of the caller's contents survives: the load is skipped then.
+  const bool keep_old = p.T < p.delay || p.mode == DLC_LUNG_MODE_CTRL_ONLY;   // (ctrl-only: the ring passes through)
+  const int di = blockDim.x / p.delay, dr = blockDim.x - di * p.delay;     // i += blockDim without a divide per element
+  if (SIM == DLC_SIM_DELAY && keep_old) {
     if (full_cta) {
       const int64_t base = (int64_t)blockIdx.x * blockDim.x * p.delay;
       const int count = blockDim.x * p.delay;
+      int e = threadIdx.x / p.delay, k = threadIdx.x - e * p.delay;
       for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const int e = i / p.delay, k = i - e * p.delay;
         ring[k * rs + e] = b.in_history_io[base + i];
         ring[(p.delay + k) * rs + e] = b.out_history_io[base + i];
+        k += dr; e += di;
+        if (k >= p.delay) { k -= p.delay; ++e; }
       }
       __syncthreads();
     } else {
@@ -203,15 +221,50 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   const float inv_period = __fdiv_rn(1.0f, p.period), t_max = 1048576.0f * p.period;
   const float pc_r0sq = __fdiv_rn(SIM == DLC_SIM_BALLOON ? p.PC : p.d_C, p.r0_sq), inv_dR = __fdiv_rn(1.0f, p.d_R);
   const float early_end = (float)p.delay;
-  Seg seg_pid = {1.f, 0.f, 0.f, 0.f}, seg_out = {1.f, 0.f, 0.f, 0.f};   // empty segments: first use searches
+  Seg seg_pid = {0.f, 0.f, 0.f, 0.f}, seg_out = {0.f, 0.f, 0.f, 0.f};   // empty segments: first use searches
+  float chk = 0.f;                                                 // 0 * pressure accumulated: NaN iff any non-finite
 
+  // The two clocks the waveform is read on -- the observation time and the emitted timestamp -- advance by dt and
+  // dt * dt per step.  When every thread of the warp can promise nondecreasing arguments with steps below one period
+  // (the only case in practice), t mod period is carried as a cached quotient: one FMA, and a predicated bump when the
+  // phase wraps -- exact, like fmodf (see fmod_fast).  Otherwise the warp runs the loop with the general reduction.
+  float q_obs = 0.f, q_ts = 0.f;
+  bool fast_clock = false;
+  if (MODE == DLC_LUNG_MODE_CLOSED_LOOP) {
+    const float nxt = SIM == DLC_SIM_BALLOON ? time + dt : time;   // the observation time after the first step
+    const float ts0 = dt * (time + 1.0f) - run_dt;
+    const bool valid = dt > 0.f && dt < period && dt * dt < period && obs_t >= 0.f && nxt >= obs_t &&
+                       nxt - obs_t < period && ts0 >= 0.f && (time + 2.0f) + (float)p.T * dt < t_max &&
+                       dt * ((time + 2.0f) + (float)p.T * dt) < t_max;
+    fast_clock = __all_sync(lanes, valid);
+    if (fast_clock) {
+      q_obs = floorf(obs_t * inv_period);
+      float r = fmaf(-q_obs, period, obs_t);
+      q_obs += r < 0.f ? -1.0f : (r >= period ? 1.0f : 0.f);
+      q_ts = floorf(ts0 * inv_period);
+      r = fmaf(-q_ts, period, ts0);
+      q_ts += r < 0.f ? -1.0f : (r >= period ? 1.0f : 0.f);
+    }
+  }
+
+  auto episode = [&](auto fast_tag) {
+  constexpr bool FAST = decltype(fast_tag)::value;
+  auto phase = [&](float x, float& q) -> float {
+    if (!FAST) return fmod_fast(x, period, inv_period, t_max);
+    float r = fmaf(-q, period, x);
+    if (r >= period) {
+      q += 1.0f;
+      r = fmaf(-q, period, x);
+    }
+    return r;
+  };
   for (int t = 0; t < p.T; ++t) {
     const float pr_emit = obs_p;                                   // run_controller.py:118
     float u_in, u_out;
     if (run_ctrl) {
       // ---- PID                                                   controllers/_pid.py:77-102
-      const float xo = fmod_fast(obs_t, period, inv_period, t_max);   // shared by PID (at) and Expiratory (is_in)
-      const float err = interp_seg<NK>(p, kf, xo, seg_pid) - obs_p;
+      const float xo = phase(obs_t, q_obs);                        // shared by PID (at) and Expiratory (is_in)
+      const float err = interp_seg<NK>(p, kf, xo, seg_pid, lanes) - obs_p;
       const float ni = ci + dec * (err - ci);
       const float nd = cd + dec * ((err - cp) - cd);
       cp = err; ci = ni; cd = nd;
@@ -274,11 +327,15 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
     if (ALLOUT || o_pr) { *o_pr = pr_emit; o_pr += N; }
     if (ALLOUT || o_flow) { *o_flow = p.env_flow; o_flow += N; }
     if (ALLOUT || o_tgt) {                                          // waveform.at(timestamps), :207
-      *o_tgt = interp_seg<NK>(p, kf, fmod_fast(ts, period, inv_period, t_max), seg_out);
+      *o_tgt = interp_seg<NK>(p, kf, phase(ts, q_ts), seg_out, lanes);
       o_tgt += N;
     }
-    bad |= !isfinite(pressure);
+    chk = fmaf(0.f, pressure, chk);
   }
+  };
+  if (fast_clock) episode(std::true_type{});
+  else episode(std::false_type{});
+  bad = chk != chk;
 
   if (ran_env) target = interp_knots<NK>(p, kf, fmod_pos(time, p.period));   // state.target (:140)
   b.steps_io[n] = steps; b.time_io[n] = time; b.volume_io[n] = volume; b.pressure_io[n] = pressure;
@@ -299,12 +356,14 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
       __syncthreads();
       const int64_t base = (int64_t)blockIdx.x * blockDim.x * p.delay;
       const int count = blockDim.x * p.delay;
+      int e = threadIdx.x / p.delay, k = threadIdx.x - e * p.delay;
       for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const int e = i / p.delay, k = i - e * p.delay;
         int s = pos + k;
         s -= s >= p.delay ? p.delay : 0;
         b.in_history_io[base + i] = ring[s * rs + e];
         b.out_history_io[base + i] = ring[(p.delay + s) * rs + e];
+        k += dr; e += di;
+        if (k >= p.delay) { k -= p.delay; ++e; }
       }
     } else {
       for (int k = 0; k < p.delay; ++k) {
@@ -316,6 +375,240 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
     }
   }
   if (b.status_out) b.status_out[n] = bad ? DLC_STATUS_NONFINITE : 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// The hot instance (default 7-knot waveform, closed loop, all six series) with TWO breaths per thread.  The kernel is
+// bound by its stores (24 B per env-step, nothing read): measured on B200 (tools/bench_series_store.py), six [T,N]
+// series written with one 4-byte store per thread top out at ~5.0 TB/s, with 8-byte stores (two adjacent envs per
+// thread, 256 contiguous bytes per warp and row) at ~6.3 TB/s -- so each thread owns envs (2j, 2j+1), runs their
+// recurrences interleaved (two independent dependency chains) and emits float2 rows.  Arithmetic per env is the
+// same sequence of operations as lung_pid_kernel (bit-identical results, tests/test_lung_gpu.py).
+struct LungEnv {
+  float time, volume, pressure, steps, pipe, obs_p, obs_t, cp, ci, cd, ctime, etime, prev_ctime, prev_etime;
+  float q_obs, q_ts, chk;
+  Seg seg_pid, seg_out;
+};
+
+template <int SIM>
+__global__ void __launch_bounds__(128) lung_pid_pair_kernel(const LungArgs a) {
+  constexpr int NK = 7;
+  extern __shared__ float ring[];                 // DelayLung: [2][delay][2 * blockDim + 1], column = e * blockDim + tid
+  const DlcLungParams& p = a.p;
+  const DlcLungBuffers& b = a.b;
+  const int64_t n0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);      // N is even (launcher)
+  const bool live = n0 < p.N;
+  const int64_t cta_lo = 2 * (int64_t)blockIdx.x * blockDim.x;
+  const int cta_envs = (int)min((int64_t)2 * blockDim.x, p.N - cta_lo);
+  const int rs = 2 * blockDim.x + 1;
+  const int di = blockDim.x / p.delay, dr = blockDim.x - di * p.delay;       // i += blockDim without a divide per element
+  if (SIM == DLC_SIM_DELAY && p.T < p.delay) {    // (after T >= delay steps nothing of the old contents survives)
+    const int64_t base = cta_lo * p.delay;        // coalesced transposing copy of the CTA's [envs, delay] chunk
+    const int count = cta_envs * p.delay;
+    int el = threadIdx.x / p.delay, k = threadIdx.x - el * p.delay;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+      const int col = (el & 1) * blockDim.x + (el >> 1);
+      ring[k * rs + col] = b.in_history_io[base + i];
+      ring[(p.delay + k) * rs + col] = b.out_history_io[base + i];
+      k += dr; el += di;
+      if (k >= p.delay) { k -= p.delay; ++el; }
+    }
+    __syncthreads();
+  }
+  int pos = 0;
+  const unsigned lanes = __ballot_sync(0xffffffffu, live);
+  if (live) {
+    float kf[2][NK], kg[2][3];
+    LungEnv E[2];
+    float target[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int64_t n = n0 + e;
+      const float* g = b.kf + (p.kf_per_env ? n * NK : 0);
+#pragma unroll
+      for (int k = 0; k < NK; ++k) kf[e][k] = g[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) kg[e][k] = b.K[n * 3 + k];
+    }
+    {
+      auto ld2 = [&](const float* src, float& x0, float& x1) {
+        const float2 v = *reinterpret_cast<const float2*>(src + n0);
+        x0 = v.x; x1 = v.y;
+      };
+      ld2(b.time_io, E[0].time, E[1].time); ld2(b.volume_io, E[0].volume, E[1].volume);
+      ld2(b.pressure_io, E[0].pressure, E[1].pressure); ld2(b.steps_io, E[0].steps, E[1].steps);
+      ld2(b.target_io, target[0], target[1]);
+      if (SIM == DLC_SIM_DELAY) ld2(b.pipe_pressure_io, E[0].pipe, E[1].pipe);
+      else E[0].pipe = E[1].pipe = 0.f;
+      ld2(b.obs_pressure_io, E[0].obs_p, E[1].obs_p); ld2(b.obs_time_io, E[0].obs_t, E[1].obs_t);
+      ld2(b.pid_p_io, E[0].cp, E[1].cp); ld2(b.pid_i_io, E[0].ci, E[1].ci); ld2(b.pid_d_io, E[0].cd, E[1].cd);
+      ld2(b.pid_time_io, E[0].ctime, E[1].ctime); ld2(b.exp_time_io, E[0].etime, E[1].etime);
+    }
+    const float period = p.period, xp_in = p.xp_in, dec = p.pid_decay, dt = p.dt, run_dt = p.run_dt;
+    const float inv_period = __fdiv_rn(1.0f, p.period), t_max = 1048576.0f * p.period;
+    const float pc_r0sq = __fdiv_rn(SIM == DLC_SIM_BALLOON ? p.PC : p.d_C, p.r0_sq), inv_dR = __fdiv_rn(1.0f, p.d_R);
+    const float early_end = (float)p.delay;
+    bool valid = true;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      LungEnv& s = E[e];
+      s.prev_ctime = s.ctime; s.prev_etime = s.etime;
+      s.seg_pid = Seg{0.f, 0.f, 0.f, 0.f}; s.seg_out = Seg{0.f, 0.f, 0.f, 0.f};
+      s.chk = 0.f; s.q_obs = 0.f; s.q_ts = 0.f;
+      const float nxt = SIM == DLC_SIM_BALLOON ? s.time + dt : s.time;
+      const float ts0 = dt * (s.time + 1.0f) - run_dt;
+      valid = valid && dt > 0.f && dt < period && dt * dt < period && s.obs_t >= 0.f && nxt >= s.obs_t &&
+              nxt - s.obs_t < period && ts0 >= 0.f && (s.time + 2.0f) + (float)p.T * dt < t_max &&
+              dt * ((s.time + 2.0f) + (float)p.T * dt) < t_max;
+    }
+    const bool fast_clock = __all_sync(lanes, valid);   // see lung_pid_kernel: cached-quotient t mod period
+    if (fast_clock) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        LungEnv& s = E[e];
+        s.q_obs = floorf(s.obs_t * inv_period);
+        float r = fmaf(-s.q_obs, period, s.obs_t);
+        s.q_obs += r < 0.f ? -1.0f : (r >= period ? 1.0f : 0.f);
+        const float ts0 = dt * (s.time + 1.0f) - run_dt;
+        s.q_ts = floorf(ts0 * inv_period);
+        r = fmaf(-s.q_ts, period, ts0);
+        s.q_ts += r < 0.f ? -1.0f : (r >= period ? 1.0f : 0.f);
+      }
+    }
+    const int64_t N2 = p.N >> 1;
+    float2* o_ts = reinterpret_cast<float2*>(b.timestamp_out + n0);
+    float2* o_uin = reinterpret_cast<float2*>(b.u_in_out + n0);
+    float2* o_uout = reinterpret_cast<float2*>(b.u_out_out + n0);
+    float2* o_pr = reinterpret_cast<float2*>(b.pressure_out + n0);
+    float2* o_flow = reinterpret_cast<float2*>(b.flow_out + n0);
+    float2* o_tgt = reinterpret_cast<float2*>(b.target_out + n0);
+
+    auto episode = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+      auto phase = [&](float x, float& q) -> float {
+        if (!FAST) return fmod_fast(x, period, inv_period, t_max);
+        float r = fmaf(-q, period, x);
+        if (r >= period) {
+          q += 1.0f;
+          r = fmaf(-q, period, x);
+        }
+        return r;
+      };
+      for (int t = 0; t < p.T; ++t) {
+        float v_ts[2], v_uin[2], v_uout[2], v_pr[2], v_tgt[2];
+        if (SIM == DLC_SIM_DELAY) pos = pos == 0 ? p.delay - 1 : pos - 1;          // roll(+1); [0] <- u
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          LungEnv& s = E[e];
+          v_pr[e] = s.obs_p;                                           // run_controller.py:118
+          // ---- PID                                                  controllers/_pid.py:77-102
+          const float xo = phase(s.obs_t, s.q_obs);
+          const float err = interp_seg<NK>(p, kf[e], xo, s.seg_pid, lanes) - s.obs_p;
+          const float ni = s.ci + dec * (err - s.ci);
+          const float nd = s.cd + dec * ((err - s.cp) - s.cd);
+          s.cp = err; s.ci = ni; s.cd = nd;
+          float u_in = (err * kg[e][0] + ni * kg[e][1]) + nd * kg[e][2];
+          u_in = fminf(fmaxf(u_in, 0.f), 100.f);
+          const float u_out = (xo <= xp_in) ? 0.f : 1.f;               // controllers/_expiratory.py:35-45
+          s.prev_ctime = s.ctime; s.prev_etime = s.etime;
+          s.ctime = s.obs_t; s.etime = s.obs_t;
+          // ---- simulator
+          if (SIM == DLC_SIM_BALLOON) {                                // envs/_balloon_lung.py:100-146
+            float valve = tanh_plus_one(0.03f * (3.0f * u_in - 130.f));
+            valve = fminf(fmaxf(valve, 0.f), 1.72f);
+            float flow = fminf(fmaxf(valve * p.R, 0.f), 2.0f);
+            if (s.pressure > p.peep_valve) flow -= (u_out > 0.f ? 1.0f : 0.0f) * 0.05f * s.pressure;
+            s.volume += flow * dt;
+            if (p.leak) s.volume += p.leak_coef * (p.min_volume - s.volume);
+            const float r = cbrt_pos(s.volume * 0.238732414637843f);
+            const float ir = rcpf_approx(r);
+            const float q = p.r0 * ir, q2 = q * q;
+            s.pressure = fmaf(pc_r0sq * fmaf(-q2 * q2, q2, 1.0f), ir, p.P0);
+            s.steps = s.time + 1.0f;                                    // sic (:135)
+            s.time = s.time + dt;
+            s.obs_p = s.pressure;
+            s.obs_t = s.time;
+          } else {                                                     // envs/_delay_lung.py:75-133
+            const float uin_pos = u_in > 0.f ? u_in : 0.f;
+            const int col = e * blockDim.x + threadIdx.x;
+            ring[pos * rs + col] = uin_pos;
+            ring[(p.delay + pos) * rs + col] = u_out;
+            s.obs_p = s.pressure;
+            s.obs_t = s.time;
+            const float flow = s.pressure * inv_dR;
+            s.volume = fmaxf(s.volume + flow * dt, p.min_volume);
+            const float r = cbrt_pos(s.volume * 0.238732414637843f);
+            const float ir = rcpf_approx(r);
+            const float q = p.r0 * ir, q2 = q * q;
+            const float lung_p = pc_r0sq * fmaf(-q2 * q2, q2, 1.0f) * ir;
+            const bool early = s.time < early_end;                      // seconds vs steps, sic (:88-96)
+            const float impulse = early ? 0.f : p.control_gain * uin_pos;
+            const float peep = early ? 0.f : u_out;
+            s.pipe = p.inertia * s.pipe + impulse;
+            s.pressure = fmaxf(0.f, s.pipe - lung_p);
+            if (peep != 0.f) s.pipe *= 0.995f;
+            s.steps = s.time + 1.0f;
+            s.time = s.time + dt;
+          }
+          const float ts = dt * s.steps - run_dt;                       // run_controller.py:128-141
+          v_ts[e] = ts; v_uin[e] = u_in; v_uout[e] = u_out;
+          v_tgt[e] = interp_seg<NK>(p, kf[e], phase(ts, s.q_ts), s.seg_out, lanes);
+          s.chk = fmaf(0.f, s.pressure, s.chk);
+        }
+        *o_ts = make_float2(v_ts[0], v_ts[1]); o_ts += N2;
+        *o_uin = make_float2(v_uin[0], v_uin[1]); o_uin += N2;
+        *o_uout = make_float2(v_uout[0], v_uout[1]); o_uout += N2;
+        *o_pr = make_float2(v_pr[0], v_pr[1]); o_pr += N2;
+        *o_flow = make_float2(p.env_flow, p.env_flow); o_flow += N2;
+        *o_tgt = make_float2(v_tgt[0], v_tgt[1]); o_tgt += N2;
+      }
+    };
+    if (fast_clock) episode(std::true_type{});
+    else episode(std::false_type{});
+
+    if (p.T > 0) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) target[e] = interp_knots<NK>(p, kf[e], fmod_pos(E[e].time, p.period));   // :140
+    }
+    auto st2 = [&](float* dst, float x0, float x1) { *reinterpret_cast<float2*>(dst + n0) = make_float2(x0, x1); };
+    st2(b.steps_io, E[0].steps, E[1].steps); st2(b.time_io, E[0].time, E[1].time);
+    st2(b.volume_io, E[0].volume, E[1].volume); st2(b.pressure_io, E[0].pressure, E[1].pressure);
+    st2(b.target_io, target[0], target[1]);
+    st2(b.obs_pressure_io, E[0].obs_p, E[1].obs_p); st2(b.obs_time_io, E[0].obs_t, E[1].obs_t);
+    st2(b.pid_p_io, E[0].cp, E[1].cp); st2(b.pid_i_io, E[0].ci, E[1].ci); st2(b.pid_d_io, E[0].cd, E[1].cd);
+    if (p.T > 0) {
+      auto bk = [&](float cur, float prev) { return fmaxf(p.default_dt, cur - (isinf(prev) ? 0.f : prev)); };
+      st2(b.pid_time_io, E[0].ctime, E[1].ctime);
+      st2(b.pid_dt_io, bk(E[0].ctime, E[0].prev_ctime), bk(E[1].ctime, E[1].prev_ctime));
+      st2(b.exp_time_io, E[0].etime, E[1].etime);
+      st2(b.exp_dt_io, bk(E[0].etime, E[0].prev_etime), bk(E[1].etime, E[1].prev_etime));
+      int2* ps = reinterpret_cast<int2*>(b.pid_steps_io + n0);
+      int2 v = *ps; v.x += p.T; v.y += p.T; *ps = v;
+      int2* xs = reinterpret_cast<int2*>(b.exp_steps_io + n0);
+      v = *xs; v.x += p.T; v.y += p.T; *xs = v;
+    }
+    if (SIM == DLC_SIM_DELAY) st2(b.pipe_pressure_io, E[0].pipe, E[1].pipe);
+    if (b.status_out)
+      *reinterpret_cast<int2*>(b.status_out + n0) = make_int2(E[0].chk != E[0].chk ? DLC_STATUS_NONFINITE : 0,
+                                                              E[1].chk != E[1].chk ? DLC_STATUS_NONFINITE : 0);
+  }
+  if (SIM == DLC_SIM_DELAY) {                      // pos is the same in every live thread (T steps each)
+    pos = p.T % p.delay == 0 ? 0 : p.delay - p.T % p.delay;
+    __syncthreads();
+    const int64_t base = cta_lo * p.delay;
+    const int count = cta_envs * p.delay;
+    int el = threadIdx.x / p.delay, k = threadIdx.x - el * p.delay;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+      const int col = (el & 1) * blockDim.x + (el >> 1);
+      int s = pos + k;
+      s -= s >= p.delay ? p.delay : 0;
+      b.in_history_io[base + i] = ring[s * rs + col];
+      b.out_history_io[base + i] = ring[(p.delay + s) * rs + col];
+      k += dr; el += di;
+      if (k >= p.delay) { k -= p.delay; ++el; }
+    }
+  }
 }
 
 }  // namespace dlc
@@ -348,6 +641,35 @@ extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLun
   // hot instance: default 7-knot waveform table, closed loop, all six series requested
   const bool hot = p->nk == 7 && p->mode == DLC_LUNG_MODE_CLOSED_LOOP && b->timestamp_out && b->u_in_out &&
                    b->u_out_out && b->pressure_out && b->flow_out && b->target_out;
+  // two breaths per thread (float2 rows) when the batch is even and every [N] array is 8-byte aligned
+  auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+  // (measured, tools/bench_lung_n.py: the wider stores win from ~48 steps on BalloonLung, ~96 on DelayLung; below that
+  // the one-per-thread kernel's higher occupancy hides the state load / store better)
+  const bool long_enough = p->kernel_variant == 2 || p->T >= (p->sim == DLC_SIM_BALLOON ? 48 : 96);
+  bool pair = hot && p->kernel_variant != 1 && long_enough && (p->N % 2 == 0) && al8(b->timestamp_out) && al8(b->u_in_out) &&
+              al8(b->u_out_out) && al8(b->pressure_out) && al8(b->flow_out) && al8(b->target_out) &&
+              al8(b->steps_io) && al8(b->time_io) && al8(b->volume_io) && al8(b->pressure_io) && al8(b->target_io) &&
+              al8(b->obs_pressure_io) && al8(b->obs_time_io) && al8(b->pid_p_io) && al8(b->pid_i_io) &&
+              al8(b->pid_d_io) && al8(b->pid_time_io) && al8(b->pid_dt_io) && al8(b->pid_steps_io) &&
+              al8(b->exp_time_io) && al8(b->exp_dt_io) && al8(b->exp_steps_io) &&
+              (!b->status_out || al8(b->status_out)) && (p->sim != DLC_SIM_DELAY || al8(b->pipe_pressure_io));
+  const unsigned grid2 = (unsigned)((p->N / 2 + 127) / 128);
+  if (pair && p->sim == DLC_SIM_BALLOON) {
+    lung_pid_pair_kernel<DLC_SIM_BALLOON><<<grid2, 128, 0, st>>>(a);
+    return cuda_status(cudaGetLastError(), "lung_pid_pair_kernel launch");
+  }
+  if (pair) {
+    const size_t smem2 = 2 * (size_t)p->delay * 257 * sizeof(float);   // 128.5 KB at the maximum delay of 64
+    static std::once_flag once2;
+    static cudaError_t rc2;
+    std::call_once(once2, [] {
+      rc2 = cudaFuncSetAttribute(lung_pid_pair_kernel<DLC_SIM_DELAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 2 * DLC_MAX_DELAY * 257 * 4);
+    });
+    if (rc2 != cudaSuccess) return cuda_status(rc2, "lung_pid_pair_kernel shared-memory attribute");
+    lung_pid_pair_kernel<DLC_SIM_DELAY><<<grid2, 128, smem2, st>>>(a);
+    return cuda_status(cudaGetLastError(), "lung_pid_pair_kernel launch");
+  }
   if (p->sim == DLC_SIM_BALLOON) {
     if (hot) lung_pid_kernel<DLC_SIM_BALLOON, 7, DLC_LUNG_MODE_CLOSED_LOOP, true><<<grid, 128, 0, st>>>(a);
     else if (p->nk == 7) lung_pid_kernel<DLC_SIM_BALLOON, 7, -1, false><<<grid, 128, 0, st>>>(a);

@@ -135,6 +135,59 @@ __global__ void __launch_bounds__(256) mb_mix_kernel(float* sink, int iters) {
   if (s == 123.456f) sink[0] = s;
 }
 
+// The store pattern of the time-major series kernels (lung episode, rollouts that keep costs): NS series [T,N], one
+// 4-byte store per thread, series and step; WORK dependent FMAs per step stand in for the per-step arithmetic.
+// sink must hold NS * iters * blocks * 128 floats.  Measures what HBM takes from this pattern with nothing else going on.
+template <int NS, int WORK>
+__global__ void __launch_bounds__(128) mb_series_store_kernel(float* out, int T) {
+  const long long N = (long long)gridDim.x * 128, n = (long long)blockIdx.x * 128 + threadIdx.x;
+  float v = (float)n * 1e-6f;
+  float* o[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) o[s] = out + (long long)s * T * N + n;
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int k = 0; k < WORK; ++k) v = fmaf(v, 0.999f, 1e-3f);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      *o[s] = v + (float)s;
+      o[s] += N;
+    }
+  }
+}
+
+// The same traffic with VEC consecutive envs per thread (one 4*VEC-byte store per thread, series and step) and a
+// cache hint (0 default, 1 st.global.cs, 2 st.global.wt): which store shapes HBM takes at full rate.
+template <int NS, int VEC, int HINT, int TPB>
+__global__ void __launch_bounds__(TPB) mb_series_store_vec_kernel(float* out, int T, long long N) {
+  const long long n = ((long long)blockIdx.x * TPB + threadIdx.x) * VEC;
+  if (n >= N) return;
+  float v = (float)n * 1e-6f;
+  float* o[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) o[s] = out + (long long)s * T * N + n;
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v = fmaf(v, 0.999f, 1e-3f);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const float w = v + (float)s;
+      if (VEC == 4) {
+        if (HINT == 1) asm volatile("st.global.cs.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(o[s]), "f"(w) : "memory");
+        else if (HINT == 2) asm volatile("st.global.wt.v4.f32 [%0], {%1,%1,%1,%1};" ::"l"(o[s]), "f"(w) : "memory");
+        else *reinterpret_cast<float4*>(o[s]) = make_float4(w, w, w, w);
+      } else if (VEC == 2) {
+        *reinterpret_cast<float2*>(o[s]) = make_float2(w, w);
+      } else {
+        if (HINT == 1) asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(o[s]), "f"(w) : "memory");
+        else if (HINT == 2) asm volatile("st.global.wt.f32 [%0], %1;" ::"l"(o[s]), "f"(w) : "memory");
+        else *o[s] = w;
+      }
+      o[s] += N;
+    }
+  }
+}
+
 }  // namespace dlc
 
 // which: 0 FFMA (72 FMA/thread/iter), 1 FFMA2 (72 FMA/thread/iter as 36 packed), 2 LDS (32 loads),
@@ -150,6 +203,18 @@ extern "C" int32_t dlc_microbench_f32(int32_t which, float* sink, int32_t iters,
     case 2: mb_lds_kernel<<<blocks, 256, 0, st>>>(sink, iters); break;
     case 3: mb_shfl_kernel<<<blocks, 256, 0, st>>>(sink, iters); break;
     case 4: mb_mix_kernel<<<blocks, 256, 0, st>>>(sink, iters); break;
+    case 5: mb_series_store_kernel<6, 8><<<blocks, 128, 0, st>>>(sink, iters); break;     // sink: 6*iters*blocks*128 floats
+    case 6: mb_series_store_kernel<6, 100><<<blocks, 128, 0, st>>>(sink, iters); break;
+    case 7: mb_series_store_kernel<1, 8><<<blocks, 128, 0, st>>>(sink, iters); break;     // sink: iters*blocks*128 floats
+    // 10..: six series over N = blocks * 128 envs in other store shapes (same bytes as 5)
+    case 10: mb_series_store_vec_kernel<6, 4, 0, 128><<<blocks / 4, 128, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 11: mb_series_store_vec_kernel<6, 2, 0, 128><<<blocks / 2, 128, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 12: mb_series_store_vec_kernel<6, 1, 1, 128><<<blocks, 128, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 13: mb_series_store_vec_kernel<6, 1, 2, 128><<<blocks, 128, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 14: mb_series_store_vec_kernel<6, 4, 1, 128><<<blocks / 4, 128, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 15: mb_series_store_vec_kernel<6, 1, 0, 512><<<blocks / 4, 512, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 16: mb_series_store_vec_kernel<6, 1, 0, 32><<<blocks * 4, 32, 0, st>>>(sink, iters, (long long)blocks * 128); break;
+    case 17: mb_series_store_vec_kernel<6, 4, 0, 32><<<blocks, 32, 0, st>>>(sink, iters, (long long)blocks * 128); break;
     default: return fail(DLC_ERR_ARG, "dlc_microbench_f32: unknown benchmark");
   }
   return cuda_status(cudaGetLastError(), "microbench launch");

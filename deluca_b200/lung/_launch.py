@@ -49,12 +49,13 @@ def launch(env, waveform, N, T, mode, dev, **kw):
 
 
 def prepare(env, waveform, N, T, mode, dev, *, K=None, env_state=None, obs=None, pid_state=None, exp_state=None,
-           actions=None, pid_decay=DEFAULT_DT / (DEFAULT_DT + 0.5), run_dt=DEFAULT_DT, series=True):
+           actions=None, pid_decay=DEFAULT_DT / (DEFAULT_DT + 0.5), run_dt=DEFAULT_DT, series=True,
+           kernel_variant=0):
     """Pack one kernel call.  ``env_state`` / ``obs`` / ``pid_state`` / ``exp_state`` are dicts of
     leaves (scalars or [N] tensors); missing pieces get neutral values.  Returns (params, buffers,
     dict of [T,N] series tensors)."""
     p = _abi.DlcLungParams()
-    p.N, p.T, p.mode = N, T, MODE[mode]
+    p.N, p.T, p.mode, p.kernel_variant = N, T, MODE[mode], int(kernel_variant)
     waveform = waveform or BreathWaveform.create()
     kx, kf, period, xp_in = waveform.knots(N=N, device=dev)
     p.nk = len(kx)

@@ -211,6 +211,10 @@ typedef struct DlcLungParams {
   int32_t delay;
   float d_R, d_C, inertia, control_gain;
   int32_t mode;              /* DLC_LUNG_MODE_* */
+  int32_t kernel_variant;    /* 0 = auto; 1 = one breath per thread; 2 = two per thread wherever that instance applies
+                                (even N, 8-byte aligned arrays, default waveform table, closed loop, all six series)
+                                regardless of T.  The two produce identical numbers; 1 / 2 are for tests and
+                                measurements */
 } DlcLungParams;
 
 typedef struct DlcLungBuffers {
@@ -597,7 +601,9 @@ int32_t dlc_env_collect_f32(const DlcEnvSpec* env, int64_t N, int32_t T, uint64_
  *   which: 0 FFMA (72 FMA/thread/iter)   1 packed fma.f32x2 (72 FMA/thread/iter)
  *          2 shared loads (32/thread/iter)   3 shuffles (32/thread/iter)
  *          4 FFMA + shared loads mixed (80 FMA + 16 loads /thread/iter)
- *   256 threads per block; sink = at least 32 zero floats.
+ *          5 / 6 the store pattern of the time-major series kernels: six series [iters, blocks*128], one 4-byte store
+ *            per thread, series and step, with 8 / 100 dependent FMAs per step;   7 the same with one series
+ *   256 threads per block (128 for 5..7); sink = at least 32 zero floats (5, 6: 6*iters*blocks*128 floats; 7: a sixth).
  * ------------------------------------------------------------------------------------ */
 int32_t dlc_microbench_f32(int32_t which, float* sink, int32_t iters, int32_t blocks, void* stream);
 

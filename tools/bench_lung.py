@@ -77,8 +77,9 @@ for name, Env in (("balloon", BalloonLung), ("delay", DelayLung)):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
         # carried leaves: K 12 + kf 28 read; 13 float + 0 int leaves read, 15 float + 2 int (rmw) + status written
-        state = 12 + 28 + 13 * 4 + (15 + 2 * 2 + 1) * 4 + (2 * 2 * 4 * env.delay * (1 if T >= env.delay else 2)
-                                                           if name == "delay" else 0)
+        state = 12 + 28 + 13 * 4 + (15 + 2 * 2 + 1) * 4
+        if name == "delay":     # + pipe_pressure (rw) and the two [delay] histories (written; read only if T < delay)
+            state += 8 + 2 * 4 * env.delay * (1 if T >= env.delay else 2)
         series_b = 24.0 * n * T
         ach = series_b / (ms * 1e-3) / 1e9
         if rank == 0:

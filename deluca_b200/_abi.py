@@ -148,7 +148,7 @@ SYMBOLS = {
                              + [_P] * 9 + [ctypes.c_float, ctypes.c_float, ctypes.c_int32] + [_P] * 5),
     "dlc_igpc_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 10),
     "dlc_plan_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcPlanParams)]),
-    "dlc_plan_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 9 + [ctypes.c_size_t, _P]),
+    "dlc_plan_f32": (ctypes.c_int32, [ctypes.POINTER(DlcPlanParams)] + [_P] * 11 + [ctypes.c_size_t, _P]),
     "dlc_lds_shared_packed_floats": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
     "dlc_lds_shared_pack_f32": (ctypes.c_int32, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "dlc_lds_shared_lqr_rollout_f32": (ctypes.c_int32, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,

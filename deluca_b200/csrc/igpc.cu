@@ -718,6 +718,8 @@ struct PlanArgs {
   const float *U_old, *k, *K, *X_old, *alpha, *x0;
   float *X_out, *U_out, *cost_out, *k_out, *K_out, *alpha_out;
   int32_t* status_out;
+  int32_t* decision_out;   // [T,N]: accepted backtracking candidate per outer iteration, -1 = none (or NULL)
+  float* cost_trace_out;   // [T,N]: cost after each outer iteration (or NULL)
   float* ws;
   int use_sim;
 };
@@ -1102,6 +1104,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
   for (int t = 0; t < p.T; ++t) {
     status |= backward_pass_pf<Mdl, true>(sim, p, X, U, kk, KK);   // compute_ders(env_sim) + LQR
     const bool ilqr = p.algo == DLC_ALGO_ILQR;
+    int dec = -1;
     if (p.backtracking) {
       // iLQR as written passes `alpha` (not alphaC) to every candidate: they are identical, so only
       // the first can be accepted (SURVEY A-10)
@@ -1118,6 +1121,7 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
           for (int i = 0; i < H * M; ++i) U[i] = UC[i];
           c = cC;
           alpha = alphaC;
+          dec = j;
           break;
         }
       }
@@ -1126,7 +1130,10 @@ __global__ void __launch_bounds__(128) plan_kernel(const PlanArgs a) {
       else c = rollout_one_pf<Mdl, true>(tru, p, U, kk, KK, X, alpha, x0, XC, UC);
       for (int i = 0; i < (H + 1) * D; ++i) X[i] = XC[i];
       for (int i = 0; i < H * M; ++i) U[i] = UC[i];
+      dec = 0;
     }
+    if (a.decision_out) a.decision_out[(int64_t)t * p.N + n] = dec;
+    if (a.cost_trace_out) a.cost_trace_out[(int64_t)t * p.N + n] = c;
   }
   a.cost_out[n] = c;
   if (a.alpha_out) a.alpha_out[n] = alpha;
@@ -1185,6 +1192,7 @@ __device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
   for (int t = 0; t < p.T; ++t) {
     if (j == 0) status |= PF ? backward_pass_pf<Mdl, true>(sim, p, X, U, kk, KK) : backward_pass(sim, p, X, U, kk, KK);
     __syncwarp(gmask);
+    int dec = -1;
     // candidates in rounds of G (one round unless n_alpha > G); a later round runs only if no earlier candidate passed
     for (int base = 0; base < p.n_alpha; base += G) {
       const int jc = base + j;
@@ -1211,11 +1219,16 @@ __device__ __forceinline__ void plan_par_body(const PlanArgs& a) {
         for (int i = j; i < H * M; i += G) U[i] = US[i];
         c = __shfl_sync(gmask, cC, gshift + js);
         alpha = __shfl_sync(gmask, alphaC, gshift + js);
+        dec = base + js;
         break;   // group-uniform
       }
       __syncwarp(gmask);
     }
     __syncwarp(gmask);
+    if (j == 0) {
+      if (a.decision_out) a.decision_out[(int64_t)t * p.N + n] = dec;
+      if (a.cost_trace_out) a.cost_trace_out[(int64_t)t * p.N + n] = c;
+    }
   }
   if (j == 0) {
     a.cost_out[n] = c;
@@ -1393,6 +1406,7 @@ extern "C" size_t dlc_plan_workspace_bytes(const DlcPlanParams* p) {
 
 extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float* x0, float* X_out, float* k_out,
                                 float* K_out, float* cost_out, float* alpha_out, int32_t* status_out,
+                                int32_t* decision_out, float* cost_trace_out,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   int32_t rc = check_plan(p, "dlc_plan_f32");
   if (rc) return rc;
@@ -1407,6 +1421,7 @@ extern "C" int32_t dlc_plan_f32(const DlcPlanParams* p, float* U_io, const float
   PlanArgs a{};
   a.p = *p; a.U_out = U_io; a.x0 = x0; a.X_out = X_out; a.k_out = k_out; a.K_out = K_out; a.cost_out = cost_out;
   a.alpha_out = alpha_out; a.status_out = status_out; a.ws = (float*)workspace;
+  a.decision_out = decision_out; a.cost_trace_out = cost_trace_out;
   if (plan_parallel_candidates(*p)) {
     const unsigned grid = (unsigned)((p->N * plan_group(*p) + 127) / 128);
     DLC_DISPATCH_ENV(p->env_true.kind, plan_par_kernel, grid, (cudaStream_t)stream, a);

@@ -154,8 +154,8 @@ ffi::Error Plan(cudaStream_t stream, ffi::Buffer<ffi::F32> U0, ffi::Buffer<ffi::
   if (workspace->size_bytes() < need) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "workspace result is too small");
   donate(stream, U0, U);
   return status(dlc_plan_f32(&p, U->typed_data(), x0.typed_data(), X->typed_data(), k->typed_data(), Kg->typed_data(),
-                             c->typed_data(), alpha->typed_data(), status_out->typed_data(), workspace->untyped_data(),
-                             workspace->size_bytes(), stream));
+                             c->typed_data(), alpha->typed_data(), status_out->typed_data(), /*decision_out=*/nullptr,
+                             /*cost_trace_out=*/nullptr, workspace->untyped_data(), workspace->size_bytes(), stream));
 }
 
 }  // namespace

@@ -257,8 +257,9 @@ def lqg_backward(F, C, reg_lambda, multiplier, factor, lambda_min, reg_type):
     return k, K, gains, status
 
 
-def plan(p, U, x0):
-    """``dlc_plan_f32``: the whole iLQR / iGPC / iLC loop.  Returns X, U, k, K, cost, alpha, status."""
+def plan(p, U, x0, trace=False):
+    """``dlc_plan_f32``: the whole iLQR / iGPC / iLC loop.  Returns X, U, k, K, cost, alpha, status; with ``trace`` also
+    (decisions[T,N] int32 -- the accepted backtracking candidate per outer iteration, -1 = none -- and costs[T,N])."""
     N, H, m = U.shape
     d = x0.shape[1]
     _f32(U, "U"); _f32(x0, "x0", (N, d))
@@ -273,10 +274,14 @@ def plan(p, U, x0):
     nbytes = _abi.lib().dlc_plan_workspace_bytes(ctypes.byref(p))
     ws = torch.empty(max(nbytes, 4) // 4, device=dev)
     with torch.cuda.device(dev):
+        dec = torch.empty(p.T, N, dtype=torch.int32, device=dev) if trace else None
+        ctr = torch.empty(p.T, N, device=dev) if trace else None
         rc = _abi.lib().dlc_plan_f32(ctypes.byref(p), _abi.ptr(U_io), _abi.ptr(x0), _abi.ptr(X), _abi.ptr(k),
-                                     _abi.ptr(K), _abi.ptr(c), _abi.ptr(alpha), _abi.ptr(status), _abi.ptr(ws),
-                                     ws.numel() * 4, _abi.current_stream_ptr())
+                                     _abi.ptr(K), _abi.ptr(c), _abi.ptr(alpha), _abi.ptr(status), _abi.ptr(dec),
+                                     _abi.ptr(ctr), _abi.ptr(ws), ws.numel() * 4, _abi.current_stream_ptr())
     _abi.check(rc, "dlc_plan_f32")
+    if trace:
+        return X, U_io, k, K, c, alpha, status, dec, ctr
     return X, U_io, k, K, c, alpha, status
 
 

@@ -376,6 +376,10 @@ int32_t dlc_plan_f32(const DlcPlanParams* p,
                      float* cost_out,    /* [N] */
                      float* alpha_out,   /* [N] */
                      int32_t* status_out,/* [N] or NULL */
+                     int32_t* decision_out, /* [T,N] or NULL: per outer iteration the index j of the accepted
+                                               backtracking candidate (alphaC = 1.1 alpha 1.1^(-j^2); ilqr.py:55-73,
+                                               igpc.py:159-170, ilc.py:49-60), -1 when none passed */
+                     float* cost_trace_out, /* [T,N] or NULL: the trajectory cost after each outer iteration */
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------

@@ -412,8 +412,9 @@ def lqg_backward(F, C, reg_lambda, multiplier, damping_consts, reg_type="V"):
 
 
 # ----------------------------------------------------------------------------- iLQR
-def ilqr(env, cost, U, T, x0=None, alpha=0.5, backtracking=True, fix_backtracking=False, n_alpha=10):
-    """``iLQR`` (``ilqr.py:27-93``).  Returns X, U, k, K, c, alpha[N]."""
+def ilqr(env, cost, U, T, x0=None, alpha=0.5, backtracking=True, fix_backtracking=False, n_alpha=10, trace=None):
+    """``iLQR`` (``ilqr.py:27-93``).  Returns X, U, k, K, c, alpha[N].  ``trace``: a list that receives, per iteration,
+    dict(decision[N] = index of the accepted candidate or -1, c_before[N], cC[tried,N], c_after[N])."""
     N = U.shape[0]
     dtype = U.dtype
     X, U, c = rollout(env, cost, U, x0=x0)
@@ -424,6 +425,7 @@ def ilqr(env, cost, U, T, x0=None, alpha=0.5, backtracking=True, fix_backtrackin
         k, K = lqr_backward(F, C)
         if backtracking:
             done = np.zeros(N, dtype=bool)
+            dec, cCs, c_before = np.full(N, -1), [], c.copy()
             Xn, Un, cn, an = X.copy(), U.copy(), c.copy(), alpha.copy()
             # as written every candidate rollout uses `alpha` (A-10), so all ten are identical and only
             # j = 0 can ever be accepted; with the fix each candidate uses its own alphaC
@@ -432,10 +434,14 @@ def ilqr(env, cost, U, T, x0=None, alpha=0.5, backtracking=True, fix_backtrackin
                 XC, UC, cC = rollout(env, cost, U, k, K, X, alphaC if fix_backtracking else alpha, x0=x0)
                 acc = (~done) & (cC <= c)                                   # :73
                 Xn[acc], Un[acc], cn[acc], an[acc] = XC[acc], UC[acc], cC[acc], alphaC[acc]
+                dec[acc] = j
+                cCs.append(cC.copy())
                 done |= acc
                 if done.all():
                     break
             X, U, c, alpha = Xn, Un, cn, an
+            if trace is not None:
+                trace.append(dict(decision=dec, c_before=c_before, cC=np.stack(cCs), c_after=c.copy()))
         else:
             X, U, c = rollout(env, cost, U, k, K, X, alpha, x0=x0)          # :78-90
     return X, U, k, K, c, alpha
@@ -519,7 +525,7 @@ def gpc_rollout(env_true, env_sim, cost, U_old, k, K, X_old, D, F, alpha, w_is="
 
 
 def igpc_closed(env_true, env_sim, cost, U, T, w_is="de", lr=0.1, ref_alpha=1.0, backtracking=True,
-                x0=None, n_alpha=6):
+                x0=None, n_alpha=6, trace=None):
     """``iGPC_closed`` (``igpc.py:129-179``) with ``verbose=False`` (no LR annealing, ``:153-156``)."""
     N = U.shape[0]
     dtype = U.dtype
@@ -531,22 +537,27 @@ def igpc_closed(env_true, env_sim, cost, U, T, w_is="de", lr=0.1, ref_alpha=1.0,
         k, K = lqr_backward(F, C)
         if backtracking:
             done = np.zeros(N, dtype=bool)
+            dec, cCs, c_before = np.full(N, -1), [], c.copy()
             Xn, Un, cn, an = X.copy(), U.copy(), c.copy(), alpha.copy()
             for j in range(n_alpha):
                 alphaC = (alpha * dtype.type(1.1)) * dtype.type(1.1) ** dtype.type(-(j ** 2))     # :159
                 XC, UC, cC = gpc_rollout(env_true, env_sim, cost, U, k, K, X, D, F, alphaC, w_is, lr, x0=x0)
                 acc = (~done) & (cC < c)                                    # strict, :164
                 Xn[acc], Un[acc], cn[acc], an[acc] = XC[acc], UC[acc], cC[acc], alphaC[acc]
+                dec[acc] = j
+                cCs.append(cC.copy())
                 done |= acc
                 if done.all():
                     break
             X, U, c, alpha = Xn, Un, cn, an
+            if trace is not None:
+                trace.append(dict(decision=dec, c_before=c_before, cC=np.stack(cCs), c_after=c.copy()))
         else:
             X, U, c = gpc_rollout(env_true, env_sim, cost, U, k, K, X, D, F, alpha, w_is, lr, x0=x0)
     return X, U, k, K, c, alpha
 
 
-def ilc_closed(env_true, env_sim, cost, U, T, ref_alpha=1.0, x0=None, n_alpha=10):
+def ilc_closed(env_true, env_sim, cost, U, T, ref_alpha=1.0, x0=None, n_alpha=10, trace=None):
     """``iLC_closed`` (``ilc.py:23-69``) with backtracking and ``verbose=False``: derivatives from
     env_sim, candidate rollouts on env_true with alphaC, accept the first cC <= c.  (With
     ``verbose=False`` ``prev_loop_fail`` is never cleared but also never acted on, ``:44-47,58``.)"""
@@ -559,14 +570,19 @@ def ilc_closed(env_true, env_sim, cost, U, T, ref_alpha=1.0, x0=None, n_alpha=10
         _, F, C = compute_ders(env_sim, cost, X, U)
         k, K = lqr_backward(F, C)
         done = np.zeros(N, dtype=bool)
+        dec, cCs, c_before = np.full(N, -1), [], c.copy()
         Xn, Un, cn, an = X.copy(), U.copy(), c.copy(), alpha.copy()
         for j in range(n_alpha):
             alphaC = (alpha * dtype.type(1.1)) * dtype.type(1.1) ** dtype.type(-(j ** 2))
             XC, UC, cC = rollout(env_true, cost, U, k, K, X, alphaC, x0=x0)
             acc = (~done) & (cC <= c)
             Xn[acc], Un[acc], cn[acc], an[acc] = XC[acc], UC[acc], cC[acc], alphaC[acc]
+            dec[acc] = j
+            cCs.append(cC.copy())
             done |= acc
             if done.all():
                 break
         X, U, c, alpha = Xn, Un, cn, an
+        if trace is not None:
+            trace.append(dict(decision=dec, c_before=c_before, cC=np.stack(cCs), c_after=c.copy()))
     return X, U, k, K, c, alpha

@@ -231,12 +231,22 @@ struct StreamArgs {
   const float* Hring;  // [Npad][2H][D]
   const float* Gw;     // [H][MM][Npad], already scaled by -lr
   float* Vw;           // [H][MM][Npad]
+  float* Gr;           // [Npad][2H][2H]: Gram matrix of the noise ring, indexed by ring slot
 };
 
-template <int D, int MM, int H, bool UPD, bool FWD, int kStages>
+// FWD: 0 = update only (the call's last launch), 1 = all H window products from M (the call's first step; also forms
+// the Gram matrix of the noise ring), 2 = incremental.  The windows slide: hist_t[j] = hist_{t-1}[j+1], so for h <= H-2
+//     V_t[h] = sum_i M_t[i] hist_t[1+h+i] = V_{t-1}[h+1] + sum_i dM_t[i] hist_t[1+h+i],
+//     dM_t[i] = sum_h' s[h'] (x) hist_t[h'+i]   ==>   dV_t[h] = sum_h' s[h'] C[h'][h],  C[h'][h] = sum_i <hist_t[h'+i], hist_t[1+h+i]>
+// -- inner products of the noise vectors only (the Gram matrix; one new row per step).  Only V_t[H-1] still needs M:
+// 1 + H multiply-adds per element of M instead of 2H, which is what takes the FP32 pipe off the critical path of this
+// HBM stream (r01 profile: FMA pipe 65 % busy next to DRAM 69 %).  A window value lives H steps (computed in full at
+// h = H-1, then corrected H-1 times), so the incremental form adds at most H-1 roundings to it.
+template <int D, int MM, int H, bool UPD, int FWD, int kStages>
 __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
   constexpr int P = 2 * H, NT = D / 2, NW = NT / 32;
-  static_assert(D % 64 == 0 && (H & (H - 1)) == 0 && H >= 2 && H <= 32, "shape");
+  static_assert(D % 64 == 0 && (H & (H - 1)) == 0 && H >= 2 && H <= 16, "shape");
+  static_assert(FWD != 2 || UPD, "the incremental windows correct for an update");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   f2* sM = reinterpret_cast<f2*>(smem_raw);                              // [kStages][H][NT]
   float* sG = reinterpret_cast<float*>(sM + (size_t)kStages * H * NT);   // [MM][H]
@@ -282,9 +292,10 @@ __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
         g[h + 1] = t.y;
       }
     }
-    f2 acc[H];
+    constexpr int NACC = FWD == 1 ? H : 1;
+    f2 acc[NACC];
 #pragma unroll
-    for (int h = 0; h < H; ++h) acc[h] = 0ull;
+    for (int h = 0; h < NACC; ++h) acc[h] = 0ull;
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       f2 mp = src[i * NT];
@@ -298,13 +309,15 @@ __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
         mp = add2(mp, p1);
         *reinterpret_cast<f2*>(Mp + ((size_t)i * MM + n) * D) = mp;
       }
-      if (FWD) {
+      if (FWD == 1) {
 #pragma unroll
         for (int h = 0; h < H; ++h)
           acc[h] = fma2(mp, hp[1 + h + i], acc[h]);
+      } else if (FWD == 2) {
+        acc[0] = fma2(mp, hp[H + i], acc[0]);        // window H-1: hist_t[1 + (H-1) + i]
       }
     }
-    if (FWD) {
+    if (FWD == 1) {
       float v[H];
 #pragma unroll
       for (int h = 0; h < H; ++h) {
@@ -328,17 +341,91 @@ __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
       for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
       constexpr int per = 32 / H;  // lanes holding the same h
       if ((lane % per) == 0) sV[(warp * MM + n) * H + lane / per] = v[0];
+    } else if (FWD == 2) {
+      float x, y;
+      unpk(acc[0], x, y);
+      float v = x + y;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) sV[(warp * MM + n) * H + (H - 1)] = v;
     }
   }
-  if (FWD) {
+  if (FWD == 0) return;
+
+  // ---- Gram matrix of the noise ring (by ring slot): all of it on the call's first step, the newest row afterwards
+  cp_async_wait<0>();
+  __syncthreads();                                   // the M stages are drained: their memory is scratch from here on
+  float* sGr = reinterpret_cast<float*>(sM);         // [P][P]
+  float* sRed = sGr + P * P;                         // [NW][P]
+  float* sC = sRed + NW * P;                         // [H][H]   C[h'][h]
+  float* sVo = sC + H * H;                           // [H][MM]  V_{t-1}
+  auto sl = [&](int j) { return (a.base + j) % P; };
+  float* Gg = a.Gr + (size_t)env * P * P;
+  auto gram_row = [&](const f2 row, int jrow) {      // <hist[jrow], hist[b]> for every b -> sGr row / column, and global
+    float v[P];
+#pragma unroll
+    for (int b2 = 0; b2 < P; ++b2) {
+      float x, y;
+      unpk(fma2(row, hp[b2], 0ull), x, y);
+      v[b2] = x + y;
+    }
+    int cnt = P, off = 16;
+#pragma unroll
+    for (; cnt > 1 && off >= 1; cnt >>= 1, off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < cnt / 2; ++j) {
+        const float send = up ? v[j] : v[j + cnt / 2];
+        const float keep = up ? v[j + cnt / 2] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+#pragma unroll
+    for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    constexpr int per = 32 / P > 0 ? 32 / P : 1;     // lanes holding the same b (P <= 32)
+    if ((lane % per) == 0) sRed[warp * P + lane / per] = v[0];
     __syncthreads();
-    for (int idx = tid; idx < MM * H; idx += NT) {  // idx = h * MM + n
-      const int h = idx / MM, n = idx % MM;
+    if (tid < P) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s += sV[(w * MM + n) * H + h];
-      a.Vw[(size_t)idx * a.Npad + env] = s;
+      for (int w = 0; w < NW; ++w) s += sRed[w * P + tid];
+      const int ra = sl(jrow), rb = sl(tid);
+      sGr[ra * P + rb] = s;
+      sGr[rb * P + ra] = s;
+      Gg[ra * P + rb] = s;
+      Gg[rb * P + ra] = s;
     }
+    __syncthreads();
+  };
+  if (FWD == 1) {
+#pragma unroll
+    for (int ja = 0; ja < P; ++ja) gram_row(hp[ja], ja);
+  } else {
+    for (int idx = tid; idx < P * P; idx += NT) sGr[idx] = Gg[idx];
+    for (int idx = tid; idx < H * MM; idx += NT) sVo[idx] = a.Vw[(size_t)idx * a.Npad + env];   // idx = h * MM + n
+    __syncthreads();
+    gram_row(hp[P - 1], P - 1);
+    for (int idx = tid; idx < H * (H - 1); idx += NT) {
+      const int h1 = idx / (H - 1), h = idx % (H - 1);
+      float c = 0.f;
+#pragma unroll
+      for (int i = 0; i < H; ++i) c += sGr[sl(h1 + i) * P + sl(1 + h + i)];
+      sC[h1 * H + h] = c;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < MM * H; idx += NT) {  // idx = h * MM + n
+    const int h = idx / MM, n = idx % MM;
+    float s = 0.f;
+    if (FWD == 1 || h == H - 1) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s += sV[(w * MM + n) * H + h];
+    } else {
+      s = sVo[(h + 1) * MM + n];
+#pragma unroll
+      for (int h1 = 0; h1 < H; ++h1) s = fmaf(sG[n * H + h1], sC[h1 * H + h], s);
+    }
+    a.Vw[(size_t)idx * a.Npad + env] = s;
   }
 }
 
@@ -724,29 +811,31 @@ struct Launch {
   }
   static size_t smem_stream(int st) { return (size_t)st * H * (D / 2) * 8 + (size_t)MM * H * 4 + (size_t)(D / 64) * H * MM * 4; }
   static size_t smem_chain() { return ((size_t)kWS * kKC * (D + MM) + (size_t)2 * (D + MM) * kE) * 4; }
-  template <bool UPD, bool FWD, int ST>
+  template <bool UPD, int FWD, int ST>
   static cudaError_t prep1() {
     return cudaFuncSetAttribute(gpc_m_stream_kernel<D, MM, H, UPD, FWD, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem_stream(ST));
   }
   static cudaError_t prepare() {
     cudaError_t e;
-    if ((e = prep1<true, true, 3>()) || (e = prep1<false, true, 3>()) || (e = prep1<true, false, 3>())) return e;
-    if ((e = prep1<true, true, 4>()) || (e = prep1<false, true, 4>()) || (e = prep1<true, false, 4>())) return e;
-    if ((e = prep1<true, true, 5>()) || (e = prep1<false, true, 5>()) || (e = prep1<true, false, 5>())) return e;
+    if ((e = prep1<true, 2, 3>()) || (e = prep1<true, 1, 3>()) || (e = prep1<false, 1, 3>()) || (e = prep1<true, 0, 3>())) return e;
+    if ((e = prep1<true, 2, 4>()) || (e = prep1<true, 1, 4>()) || (e = prep1<false, 1, 4>()) || (e = prep1<true, 0, 4>())) return e;
+    if ((e = prep1<true, 2, 5>()) || (e = prep1<true, 1, 5>()) || (e = prep1<false, 1, 5>()) || (e = prep1<true, 0, 5>())) return e;
     if ((e = cudaFuncSetAttribute(gpc_q_init_kernel<D, MM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain())))
       return e;
     return cudaFuncSetAttribute(gpc_shared_chain_kernel<D, MM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain());
   }
+  // fwd: 0 none, 1 all windows from M (+ the Gram matrix), 2 incremental (needs upd and a previous fwd launch)
   template <int ST>
-  static void stream_st(const StreamArgs& a, bool upd, bool fwd, cudaStream_t s) {
+  static void stream_st(const StreamArgs& a, bool upd, int fwd, cudaStream_t s) {
     const dim3 grid((unsigned)a.N), block(D / 2);
     const size_t sm = smem_stream(ST);
-    if (upd && fwd) gpc_m_stream_kernel<D, MM, H, true, true, ST><<<grid, block, sm, s>>>(a);
-    else if (fwd) gpc_m_stream_kernel<D, MM, H, false, true, ST><<<grid, block, sm, s>>>(a);
-    else gpc_m_stream_kernel<D, MM, H, true, false, ST><<<grid, block, sm, s>>>(a);
+    if (upd && fwd == 2) gpc_m_stream_kernel<D, MM, H, true, 2, ST><<<grid, block, sm, s>>>(a);
+    else if (upd && fwd == 1) gpc_m_stream_kernel<D, MM, H, true, 1, ST><<<grid, block, sm, s>>>(a);
+    else if (fwd) gpc_m_stream_kernel<D, MM, H, false, 1, ST><<<grid, block, sm, s>>>(a);
+    else gpc_m_stream_kernel<D, MM, H, true, 0, ST><<<grid, block, sm, s>>>(a);
   }
-  static void stream(const StreamArgs& a, bool upd, bool fwd, cudaStream_t s) {
+  static void stream(const StreamArgs& a, bool upd, int fwd, cudaStream_t s) {
     if (stages() == 3) stream_st<3>(a, upd, fwd, s); else if (stages() == 5) stream_st<5>(a, upd, fwd, s); else stream_st<4>(a, upd, fwd, s);
   }
   static void chain(const ChainArgs& a, cudaStream_t s) {
@@ -772,7 +861,7 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct SgpcLayout {
   int64_t Npad;
-  size_t FT, Fr, F2T, nKT, nK, GcT, Sop, QT, Ad, Bd, Pd, Gd, Xw, AXw, Qw, Vw, Gw, Hw, Hring, total;  // offsets in bytes
+  size_t FT, Fr, F2T, nKT, nK, GcT, Sop, QT, Ad, Bd, Pd, Gd, Xw, AXw, Qw, Vw, Gw, Hw, Hring, Gr, total;  // offsets in bytes
 };
 
 static SgpcLayout sgpc_layout(int64_t N, int d, int m, int H) {
@@ -787,7 +876,7 @@ static SgpcLayout sgpc_layout(int64_t N, int d, int m, int H) {
   // double-precision scratch of the power recursion (two floats per double): Ab, B, two d x d and two d x m buffers
   L.Ad = take((size_t)2 * d * d); L.Bd = take((size_t)2 * d * m); L.Pd = take((size_t)4 * d * d); L.Gd = take((size_t)4 * d * m);
   L.Xw = take(d * np); L.AXw = take(d * np); L.Qw = take(d * np); L.Vw = take((size_t)H * m * np); L.Gw = take((size_t)H * m * np);
-  L.Hw = take(P * d * np); L.Hring = take(np * P * d);
+  L.Hw = take(P * d * np); L.Hring = take(np * P * d); L.Gr = take(np * P * P);
   L.total = o;
   return L;
 }
@@ -862,7 +951,9 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
   }
   if (xprev_io) ax_prev_kernel<<<(unsigned)((p->N * d + 255) / 256), 256, 0, s>>>(st);
   StreamArgs sa{};
-  sa.N = p->N; sa.Npad = L.Npad; sa.M = M_io; sa.Hring = at(L.Hring); sa.Gw = at(L.Gw); sa.Vw = at(L.Vw);
+  sa.N = p->N; sa.Npad = L.Npad; sa.M = M_io; sa.Hring = at(L.Hring); sa.Gw = at(L.Gw); sa.Vw = at(L.Vw); sa.Gr = at(L.Gr);
+  // DLC_SGPC_FULLFWD=1 (measurements / tests): every step forms all H window products from M, as round 1 did
+  static const bool fullfwd = [] { const char* e = getenv("DLC_SGPC_FULLFWD"); return e && atoi(e) != 0; }();
   ChainArgs ca{};
   ca.N = p->N; ca.Npad = L.Npad;
   ca.FT = at(L.FT); ca.Fr = at(L.Fr); ca.F2T = at(L.F2T); ca.nKT = at(L.nKT); ca.nK = at(L.nK);
@@ -881,7 +972,8 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
     const int base = step % P;
     sa.base = base;
     if (dbg != 2) {
-      if (big) Launch<256, 64, 16>::stream(sa, step > 0, true, s); else Launch<64, 32, 4>::stream(sa, step > 0, true, s);
+      const int fwd = (step > 0 && !fullfwd) ? 2 : 1;
+      if (big) Launch<256, 64, 16>::stream(sa, step > 0, fwd, s); else Launch<64, 32, 4>::stream(sa, step > 0, fwd, s);
     }
     ca.base = base;
     ca.first = step == 0;
@@ -895,7 +987,7 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
     }
   }
   sa.base = p->T % P;
-  if (big) Launch<256, 64, 16>::stream(sa, true, false, s); else Launch<64, 32, 4>::stream(sa, true, false, s);
+  if (big) Launch<256, 64, 16>::stream(sa, true, 0, s); else Launch<64, 32, 4>::stream(sa, true, 0, s);
   st.base = p->T % P;
   to_env_major_kernel<<<dim3(nb, (d + 31) / 32), tb, 0, s>>>(st.Xw, x_io, p->N, d, L.Npad);
   if (hist_io) hist_out_kernel<<<(unsigned)((p->N * P * d + 255) / 256), 256, 0, s>>>(st);

@@ -299,7 +299,7 @@ class Runner:
         with disturbances drawn by the env itself (in-kernel Philox; the reference's env draws its own noise too,
         _lds.py:102-105), and the result device -> host: the full losses[T,N] (what Rollout.losses holds,
         training/apg.py:68) or the per-env cost sums only."""
-        from deluca_b200.fused import lds_rollout
+        from deluca_b200.fused import lds_rollout, lds_rollout_to_host
         torch = self.torch
         hA, hB, hK, hx = (t.cpu().pin_memory() for t in (self.A, self.B, self.K, self.x0))
         T = self.wl["T"]
@@ -308,8 +308,12 @@ class Runner:
 
         def one():
             dA, dB, dK, dx = (t.to(self.dev, non_blocking=True) for t in (hA, hB, hK, hx))
-            rr = lds_rollout(dA, dB, dK, dx, T, W=None, keep_costs=return_losses, donate=True, **self.kw)
-            h_out.copy_(rr.costs if return_losses else rr.cost_sum, non_blocking=True)
+            if return_losses:   # losses[T,N] stream to the host chunk by chunk under the rollout (public API)
+                rr = lds_rollout_to_host(dA, dB, dK, dx, T, h_out, chunks=8, donate=True, **self.kw)
+                torch.cuda.current_stream(self.dev).wait_event(rr.done)
+            else:
+                rr = lds_rollout(dA, dB, dK, dx, T, W=None, keep_costs=False, donate=True, **self.kw)
+                h_out.copy_(rr.cost_sum, non_blocking=True)
 
         one()
         self.sync()

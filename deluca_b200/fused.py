@@ -127,6 +127,65 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
                             t=t0 + T)
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    dev = torch.device(dev)
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[dev]
+
+
+def lds_rollout_to_host(A, B, K, x, T, host_costs, *, chunks=8, W=None, t0=0, env_t0=None, donate=False, **kw):
+    """``lds_rollout`` whose losses[T,N] (``Rollout.losses``, ``deluca/training/apg.py:68``) land in PINNED host memory
+    while the rollout is still running: the horizon is cut into ``chunks`` launches resumed from the carried agent / env
+    state (same arithmetic; the in-kernel disturbance stream is keyed by the env step counter), and each chunk's costs
+    travel device -> host on a side stream under the next chunk's kernel.  Only the last chunk's copy is exposed.
+    Returns the ``lds_rollout`` result of the whole horizon (``costs`` = ``host_costs``) plus ``done``, a CUDA event that
+    completes when the last copy has; the caller must wait on it (or synchronise) before reading ``host_costs``."""
+    if not (isinstance(host_costs, torch.Tensor) and not host_costs.is_cuda and host_costs.is_pinned()):
+        raise TypeError("host_costs must be a pinned CPU tensor")
+    N = x.shape[0]
+    if tuple(host_costs.shape) != (T, N) or host_costs.dtype != torch.float32:
+        raise ValueError(f"host_costs must be float32 [{T},{N}]")
+    for k in ("keep_costs", "traj_stride"):
+        if kw.get(k):
+            raise ValueError(f"{k} is not available on the streamed path")
+    kw.pop("keep_costs", None)
+    dev = x.device
+    main, side = torch.cuda.current_stream(dev), _copy_stream(dev)
+    chunks = max(1, min(int(chunks), T))
+    bounds = [round(i * T / chunks) for i in range(chunks + 1)]
+    env_t0 = t0 if env_t0 is None else env_t0
+    state = {k: kw.pop(k, None) for k in ("M", "hist", "xprev", "uprev", "eps", "bpc_cost")}
+    eps_new = kw.pop("eps_new", None)
+    cost_sum = status = r = None
+    xc = x
+    for c in range(chunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        if hi == lo:
+            continue
+        r = lds_rollout(A, B, K, xc, hi - lo, W=None if W is None else W[lo:hi], t0=t0 + lo, env_t0=env_t0 + lo,
+                        eps_new=None if eps_new is None else eps_new[lo:hi], keep_costs=True,
+                        donate=donate or c > 0, **state, **kw)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            host_costs[lo:hi].copy_(r.costs, non_blocking=True)
+        r.costs.record_stream(side)
+        cost_sum = r.cost_sum if cost_sum is None else cost_sum + r.cost_sum
+        status = r.status if status is None else status | r.status
+        xc = r.x
+        state = {k: r[k] for k in state}
+    done = torch.cuda.Event()
+    done.record(side)
+    out = LdsRolloutResult(r)
+    out.update(costs=host_costs, cost_sum=cost_sum, status=status, t=t0 + T, done=done)
+    return out
+
+
 # ------------------------------------------------------------------------------------------ lung
 def lung_rollout(params, bufs):
     """``dlc_lung_pid_rollout_f32`` on already-prepared ctypes structs (see deluca_b200.lung)."""

@@ -331,3 +331,31 @@ def test_large_batch_properties():
     gp = lds_rollout(A, B, K, x0, T, policy="gpc", W=W, H=3, HH=10, lr_scale=1e-4)
     assert torch.allclose(gp.costs.double().sum(0), gp.cost_sum, rtol=1e-6)
     assert int(gp.status.sum()) == 0
+
+
+@pytest.mark.parametrize("H,HH,N,T", [(3, 2, 300, 41), (10, 10, 256, 60)])
+def test_rollout_streamed_to_host_equals_one_launch(H, HH, N, T):
+    """`lds_rollout_to_host`: the horizon in resumed chunks, losses copied to pinned host memory under the next chunk's
+    kernel.  Same numbers as one launch (to rounding where a kernel re-forms a carried sum on entry), same final
+    agent / env state, and the in-kernel disturbance stream continues across the cuts."""
+    from deluca_b200.fused import lds_rollout, lds_rollout_to_host
+    g = torch.Generator(device="cuda").manual_seed(3)
+    d, m = 10, 3
+    A = torch.diag_embed(0.9 + 0.05 * torch.rand(N, d, device="cuda", generator=g))
+    B = torch.randn(N, d, m, device="cuda", generator=g) / d ** 0.5
+    K = 0.05 * torch.randn(N, m, d, device="cuda", generator=g)
+    x0 = torch.randn(N, d, device="cuda", generator=g)
+    kw = dict(policy="gpc", H=H, HH=HH, lr_scale=1e-5, seed=77, env_offset=5, w_std=0.5)
+    one = lds_rollout(A, B, K, x0, T, W=None, **kw)
+    assert bool(torch.isfinite(one.costs).all())
+    host = torch.empty(T, N).pin_memory()
+    r = lds_rollout_to_host(A, B, K, x0, T, host, chunks=5, **kw)
+    r.done.synchronize()
+    # (the quad-split kernel of the long-history case re-forms its sliding sum from the ring on entry: rounding only)
+    tol = dict(rtol=2e-6, atol=1e-6) if H < 10 else dict(rtol=5e-5, atol=5e-5)
+    err = (host - one.costs.cpu()).abs().max()
+    assert torch.allclose(host, one.costs.cpu(), **tol), float(err)
+    assert torch.allclose(r.x, one.x, **tol) and torch.allclose(r.M, one.M, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(r.cost_sum, one.cost_sum, rtol=1e-6) and r.t == T and int(r.status.sum()) == 0
+    with pytest.raises(TypeError):
+        lds_rollout_to_host(A, B, K, x0, T, torch.empty(T, N), **kw)        # not pinned

@@ -22,6 +22,8 @@
 //        window is filtered each step, the others are kept in a ring.
 //   (iii) jit(grad(policy_loss)) is a hand adjoint: dTheta[f] = sum_k g(k) phi_f(k)^T with g(m) = 2 a(m) and
 //        g(k) = G[m-1-k]^T (2 final_y) for k < m.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dlc {
@@ -73,6 +75,23 @@ __device__ __forceinline__ void matvec(const float* Mat, const float* v, int row
   }
 }
 
+// Reduce-scatter over the 8 lanes of a group: v[0 .. 8 Q) are per-lane partial sums of 8 Q quantities; afterwards lane gl holds
+// the group totals of quantities base .. base + Q - 1 in v[0 .. Q), base = Q * (4 b2 + 2 b1 + b0) for gl = (b2 b1 b0).
+// 7 Q shuffles (an all-reduce of every quantity would take 24 Q).
+template <int Q>
+__device__ __forceinline__ void group8_reduce_scatter(float (&v)[8 * Q], int gl) {
+#pragma unroll
+  for (int half = 4 * Q, off = 4; off >= 1; half >>= 1, off >>= 1) {
+    const bool up = (gl & off) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 __device__ __forceinline__ float pick4(const float z[4], int k) { return k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3])); }
 
 // buf[i] <- (i < step) ? fresh[i] : buf[i - step]  for i < tot: a newest-first history takes one entry.  GL-wide blocks,
@@ -98,7 +117,10 @@ __device__ __forceinline__ void shift_in(float* buf, int tot, int step, const fl
 // contractions unroll into LDS + FFMA with immediate offsets; the runtime-dims loops spend three integer
 // instructions per FMA on addresses and trip counts (ncu: 1660 warp-instructions per LQG step, 300 of them FFMA).
 template <int AGENT, int GL, int SD = 0, int SN = 0, int SP = 0, int SM = 0, int SF = 0, int SL = 0, int SH = 0>
-__global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 : 2)) of_kernel(const OfArgs a) {
+// (the window-blocked SFC instance -- 8 lanes, m = 30 -- holds Theta / dTheta in registers and is limited to 16 envs per CTA by
+// its shared memory anyway: it may use the whole register file)
+__global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 : ((GL == 8 && SM >= 20) ? 1 : 2)))
+of_kernel(const OfArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NR = 2;   // rows per lane of a mat-vec: the launcher keeps max(d, n, p) <= 2 GL (code size: the step loop must stay
                           // inside the instruction cache -- a 64 / GL-way unroll made it 167 KB and no_instruction the top stall)
@@ -109,6 +131,14 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 
   const int FP = SD ? (AGENT == DLC_OF_DRC ? SM * SP : SF * SP) : a.FP;
   const int J = SD ? (AGENT == DLC_OF_DRC ? SH : SM) : a.J;
   const bool closed = P.mode == DLC_MODE_CLOSED_LOOP;
+  // Window-blocked form of the filter family's three contractions (compile-time dims, 8 lanes, n F p <= 72: the default GRC
+  // and SFC).  The element-per-lane loops below read two shared-memory operands per FMA and are LSU-bound (ncu,
+  // profiles/r01_of_grc_reg_full.txt: LSU pipe 61 %); here a lane owns the windows in ring slots gl, gl + 8, ... and
+  // holds Theta (then the partial dTheta) in registers, so a window's features are read once per pass and each feeds
+  // n FMAs; the per-lane partial sums meet in a 7/8-shuffle-per-value reduce-scatter.  Same products, other summation order.
+  constexpr bool BLK = AGENT == DLC_OF_FGRC && SD != 0 && GL == 8 && SN * SF * SP <= 72 && SF * SP <= 24;
+  constexpr int CFP = BLK ? SF * SP : 1, CN = BLK ? SN : 1, CP = BLK ? SP : 1, CM1 = BLK ? SM + 1 : 1;
+  constexpr int WPL = (CM1 + 7) / 8;   // windows per lane
   if (AGENT == DLC_OF_FGRC) {
     for (int i = threadIdx.x; i < a.nPhi; i += blockDim.x) smem[i] = a.Phi[i];
     __syncthreads();  // the only CTA-wide barrier: warps are independent from here on
@@ -329,7 +359,32 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 
       }
       __syncwarp();
       // ---- filter the newest window (history positions m .. m+L-1) into the ring slot of the oldest one
-      {
+      if constexpr (BLK) {
+        // taps dealt to lanes: a lane reads y_nat[o] once and feeds all F filters with it
+        float* fw = sFeat + fbase * FP;
+        int s0 = ybase + m; if (s0 >= R) s0 -= R;
+        float part[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) part[i] = 0.f;
+        for (int o = gl; o < L; o += 8) {
+          int sl = s0 + o; if (sl >= R) sl -= R;
+          float yq[CP];
+#pragma unroll
+          for (int q = 0; q < CP; ++q) yq[q] = sYn[sl * CP + q];
+#pragma unroll
+          for (int f = 0; f < CFP / CP; ++f) {
+            const float ph = sPhi[f * L + o];
+#pragma unroll
+            for (int q = 0; q < CP; ++q) part[f * CP + q] = fmaf(ph, yq[q], part[f * CP + q]);
+          }
+        }
+        group8_reduce_scatter<3>(part, gl);
+        const int base = 3 * gl;   // (4 b2 + 2 b1 + b0 = gl)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          if (base + r < CFP) fw[base + r] = part[r];
+        fbase = (fbase + 1 == M1) ? 0 : fbase + 1;
+      } else {
         float* fw = sFeat + fbase * FP;
         int s0 = ybase + m; if (s0 >= R) s0 -= R;
         for (int i = gl; i < FP; i += GL) {
@@ -346,6 +401,111 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 
         fbase = (fbase + 1 == M1) ? 0 : fbase + 1;
       }
       __syncwarp();
+      if constexpr (BLK) {
+        // ---- pass 1: a(k) = Theta phi(k) for this lane's windows; their share of final_y    (_grc.py:97-104)
+        float am[CN], fyp[CP];
+#pragma unroll
+        for (int aa = 0; aa < CN; ++aa) am[aa] = 0.f;
+#pragma unroll
+        for (int q = 0; q < CP; ++q) fyp[q] = 0.f;
+        {
+          static_assert(!BLK || CFP % 2 == 0, "feature rows are read as float2");
+          float th[CN][CFP];   // (every per-env offset is a multiple of 4 floats and CFP is even: 8-byte aligned rows)
+#pragma unroll
+          for (int aa = 0; aa < CN; ++aa)
+#pragma unroll
+            for (int i = 0; i < CFP; i += 2) {
+              const float2 t2 = *reinterpret_cast<const float2*>(sTh + aa * CFP + i);
+              th[aa][i] = t2.x; th[aa][i + 1] = t2.y;
+            }
+          // (branch-free: an out-of-range slot is clamped and weighted 0, so the WPL windows' chains interleave)
+#pragma unroll
+          for (int j = 0; j < WPL; ++j) {
+            const int sl0 = gl + 8 * j;
+            const bool valid = sl0 < CM1;
+            const int sl = valid ? sl0 : CM1 - 1;
+            int k = sl - fbase; if (k < 0) k += CM1;
+            const bool newest = k == m;
+            const float* fw = sFeat + sl * CFP;
+            float ak[CN];
+#pragma unroll
+            for (int aa = 0; aa < CN; ++aa) ak[aa] = 0.f;
+#pragma unroll
+            for (int i = 0; i < CFP; i += 2) {
+              const float2 ph = *reinterpret_cast<const float2*>(fw + i);
+#pragma unroll
+              for (int aa = 0; aa < CN; ++aa) ak[aa] = fmaf(th[aa][i + 1], ph.y, fmaf(th[aa][i], ph.x, ak[aa]));
+            }
+            const float* g = sG + (newest ? 0 : m - 1 - k) * CP * CN;
+            const float wgt = (valid && !newest) ? 1.f : 0.f;
+#pragma unroll
+            for (int aa = 0; aa < CN; ++aa) {
+              am[aa] = (valid && newest) ? ak[aa] : am[aa];
+              ak[aa] *= wgt;
+            }
+#pragma unroll
+            for (int q = 0; q < CP; ++q)
+#pragma unroll
+              for (int aa = 0; aa < CN; ++aa) fyp[q] = fmaf(g[q * CN + aa], ak[aa], fyp[q]);
+          }
+        }
+        int snew = ybase + R - 1; if (snew >= R) snew -= R;
+        float fy[CP];
+#pragma unroll
+        for (int q = 0; q < CP; ++q) fy[q] = 2.f * (sYn[snew * CP + q] + group_sum<8>(fyp[q]));
+        // ---- pass 2: dTheta = sum_k g(k) phi(k)^T, g(m) = 2 a(m), g(k) = G[m-1-k]^T fy     (_grc.py:144-151)
+        float dth[72];
+#pragma unroll
+        for (int e = 0; e < 72; ++e) dth[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) {
+          const int sl0 = gl + 8 * j;
+          const bool valid = sl0 < CM1;
+          const int sl = valid ? sl0 : CM1 - 1;
+          int k = sl - fbase; if (k < 0) k += CM1;
+          const bool newest = k == m;
+          const float* fw = sFeat + sl * CFP;
+          const float* g = sG + (newest ? 0 : m - 1 - k) * CP * CN;
+          float gk[CN];
+#pragma unroll
+          for (int aa = 0; aa < CN; ++aa) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < CP; ++q) acc = fmaf(g[q * CN + aa], fy[q], acc);
+            gk[aa] = valid ? (newest ? 2.f * am[aa] : acc) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < CFP; i += 2) {
+            const float2 ph = *reinterpret_cast<const float2*>(fw + i);
+#pragma unroll
+            for (int aa = 0; aa < CN; ++aa) {
+              dth[aa * CFP + i] = fmaf(gk[aa], ph.x, dth[aa * CFP + i]);
+              dth[aa * CFP + i + 1] = fmaf(gk[aa], ph.y, dth[aa * CFP + i + 1]);
+            }
+          }
+        }
+        group8_reduce_scatter<9>(dth, gl);
+        // ---- Theta <- proj_RM(Theta - lr dTheta): this lane applies entries 9 gl .. 9 gl + 8
+        __syncwarp();                                  // every lane has read the old Theta
+        float nrm = 0.f;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const int e = 9 * gl + r;
+          if (e < CN * CFP) {
+            const float thn = fmaf(-lr, dth[r], sTh[e]);
+            sTh[e] = thn;
+            nrm = fmaf(thn, thn, nrm);
+          }
+        }
+        nrm = sqrtf(group_sum<8>(nrm));
+        const float sc = fminf(1.0f, P.R_M / (nrm + 1e-8f));
+        if (sc < 1.0f) {
+#pragma unroll
+          for (int r = 0; r < 9; ++r)
+            if (9 * gl + r < CN * CFP) sTh[9 * gl + r] *= sc;
+        }
+        __syncwarp();
+      } else {
       // ---- a(k), k = 0..m, with the parameters before the update
       for (int e = gl; e < M1 * n; e += GL) {
         const int k = fast_div(e, inv_n), aa = e - k * n;
@@ -403,6 +563,7 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 
       if (sc < 1.0f)
         for (int e = gl; e < n * FP; e += GL) sTh[e] *= sc;
       __syncwarp();
+      }
     }
 
     // ---- realised cost quad_loss(y, u), outputs
@@ -1001,6 +1162,8 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   if (p->flags & ~DLC_OF_FLAG_PHI_IDENTITY) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: unknown flag bits");
   // groups of one warp hit the same offsets of their slices at once: a slice stride of GL (mod 32) banks keeps
   // their unit-stride accesses apart
+  // (for the window-blocked SFC instance a stride of 16 mod 32 would spread its 8-byte feature-row reads over all even
+  // banks, but it measured slower than GL mod 32 -- 61.1 vs 58.3 ms -- because every other access then collides)
   if (GL < 32) a.S += ((GL - a.S % 32) + 32) % 32;
   const size_t per_env = (size_t)a.S * 4, fixed = (size_t)a.nPhi * 4;
   if (fixed + per_env > (size_t)max_smem)

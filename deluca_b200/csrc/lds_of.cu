@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "f2.cuh"
 
 namespace dlc {
 namespace {
@@ -92,6 +93,22 @@ __device__ __forceinline__ void group8_reduce_scatter(float (&v)[8 * Q], int gl)
   }
 }
 
+// The same over a whole warp: v[0 .. 32 Q) per-lane partials; afterwards lane l holds the warp totals of quantities
+// Q l .. Q l + Q - 1 in v[0 .. Q).  31 Q shuffles.
+template <int Q>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[32 * Q], int lane) {
+#pragma unroll
+  for (int half = 16 * Q, off = 16; off >= 1; half >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 __device__ __forceinline__ float pick4(const float z[4], int k) { return k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3])); }
 
 // buf[i] <- (i < step) ? fresh[i] : buf[i - step]  for i < tot: a newest-first history takes one entry.  GL-wide blocks,
@@ -119,7 +136,8 @@ __device__ __forceinline__ void shift_in(float* buf, int tot, int step, const fl
 template <int AGENT, int GL, int SD = 0, int SN = 0, int SP = 0, int SM = 0, int SF = 0, int SL = 0, int SH = 0>
 // (the window-blocked SFC instance -- 8 lanes, m = 30 -- holds Theta / dTheta in registers and is limited to 16 envs per CTA by
 // its shared memory anyway: it may use the whole register file)
-__global__ void __launch_bounds__(256, GL == 32 ? 4 : (AGENT != DLC_OF_FGRC ? 3 : ((GL == 8 && SM >= 20) ? 1 : 2)))
+__global__ void __launch_bounds__(256, GL == 32 ? ((AGENT == DLC_OF_FGRC && SD != 0 && SF * SP > 24) ? 1 : 4)
+                                                : (AGENT != DLC_OF_FGRC ? 3 : ((GL == 8 && SM >= 20) ? 1 : 2)))
 of_kernel(const OfArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NR = 2;   // rows per lane of a mat-vec: the launcher keeps max(d, n, p) <= 2 GL (code size: the step loop must stay
@@ -139,8 +157,30 @@ of_kernel(const OfArgs a) {
   constexpr bool BLK = AGENT == DLC_OF_FGRC && SD != 0 && GL == 8 && SN * SF * SP <= 72 && SF * SP <= 24;
   constexpr int CFP = BLK ? SF * SP : 1, CN = BLK ? SN : 1, CP = BLK ? SP : 1, CM1 = BLK ? SM + 1 : 1;
   constexpr int WPL = (CM1 + 7) / 8;   // windows per lane
+  // Feature-blocked form for wide filter banks on a whole warp (compile-time dims, F p > 24: the default DSC, 242 features
+  // x 31 windows).  Lane l owns features 8 l .. 8 l + 7 of EVERY window and keeps its 3 x 8 block of Theta in registers for
+  // the whole rollout: a(k) needs one reduce-scatter over the warp (lane k ends up with a(k)), dTheta needs no cross-lane
+  // sum at all, and the filter bank is staged transposed ([tap][filter]) so a lane reads its 4 filters of a tap as one
+  // 16-byte word.  Window rows are padded to 8 * 31 = 248 floats.
+  constexpr bool FBL = AGENT == DLC_OF_FGRC && SD != 0 && GL == 32 && SF * SP > 24 && SF * SP <= 248 && SM + 1 <= 32 &&
+                       SN == 3 && SP == 2;
+  constexpr int FST = 248;                       // padded feature-row stride (FBL)
+  constexpr int FPD = FBL ? ((SF + 3) & ~3) : 1; // padded filter count of the transposed bank
+  // FBL feature ownership: lane l < 31 owns features 4 l .. 4 l + 3 and 124 + 4 l .. 124 + 4 l + 3, so that each of its
+  // two 16-byte reads of a window row is part of one contiguous 496-byte sweep of the warp (conflict-free); in filter
+  // terms (p = 2) that is filters 2 l, 2 l + 1 and 62 + 2 l, 62 + 2 l + 1.  Lane 31 idles through the passes (its block of
+  // Theta is zero and it reads lane 0's addresses).
+  const int fl = gl < 31 ? gl : 0;
+  auto fbl_feature = [&](int j) { return (j < 4 ? 0 : 124) + 4 * gl + (j & 3); };
   if (AGENT == DLC_OF_FGRC) {
-    for (int i = threadIdx.x; i < a.nPhi; i += blockDim.x) smem[i] = a.Phi[i];
+    if constexpr (FBL) {
+      for (int i = threadIdx.x; i < a.nPhi; i += blockDim.x) {
+        const int o = i / FPD, f = i - o * FPD;
+        smem[i] = (o < SL && f < SF) ? a.Phi[f * SL + o] : 0.f;
+      }
+    } else {
+      for (int i = threadIdx.x; i < a.nPhi; i += blockDim.x) smem[i] = a.Phi[i];
+    }
     __syncthreads();  // the only CTA-wide barrier: warps are independent from here on
   }
   int64_t env = (int64_t)blockIdx.x * a.wpc + grp;
@@ -175,12 +215,38 @@ of_kernel(const OfArgs a) {
     for (int i = gl; i < m * p; i += GL) sYn[i] = a.ynat_io[(size_t)env * m * p + i];
     for (int i = gl; i < h * n; i += GL) sUs[i] = a.us_io[(size_t)env * h * n + i];
   }
+  // FBL: this lane's 3 x 8 block of Theta, resident for the whole rollout as packed pairs (feature j = 2 i, 2 i + 1): the
+  // passes run on fma.rn.f32x2 (two FMAs per issued instruction), the window rows arriving as ready-made pairs
+  f2 thr2[3][4];
+#pragma unroll
+  for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) thr2[aa][i] = 0ull;
   if (AGENT == DLC_OF_FGRC) {
-    for (int e = gl; e < F * n * p; e += GL) {
-      const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
-      sTh[aa * FP + f * p + q] = a.theta_io[(size_t)env * F * n * p + e];
+    if constexpr (FBL) {
+#pragma unroll
+      for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+          float v[2] = {0.f, 0.f};
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int i = fbl_feature(2 * i2 + h2), f = i >> 1, q = i & 1;      // (p = 2)
+            if (gl < 31 && i < SF * SP) v[h2] = a.theta_io[(size_t)env * SF * 6 + (f * 3 + aa) * 2 + q];
+          }
+          thr2[aa][i2] = pk(v[0], v[1]);
+        }
+    } else {
+      for (int e = gl; e < F * n * p; e += GL) {
+        const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
+        sTh[aa * FP + f * p + q] = a.theta_io[(size_t)env * F * n * p + e];
+      }
     }
-    for (int i = gl; i < (L + m) * p; i += GL) sYn[i] = a.ynat_io[(size_t)env * (L + m) * p + i];
+    for (int i = gl; i < (L + m) * p; i += GL) {
+      const float v = a.ynat_io[(size_t)env * (L + m) * p + i];
+      sYn[i] = v;
+      if constexpr (FBL) sYn[(L + m) * p + i] = v;   // the mirror copy (see fbl_filter)
+    }
     for (int i = gl; i < d; i += GL) sz[i] = a.z_io[(size_t)env * d + i];
   }
   __syncwarp();
@@ -210,6 +276,31 @@ of_kernel(const OfArgs a) {
   }
   // ---------------------------------------------------------------- filtered windows of the initial history
   const int M1 = m + 1, R = L + m;
+  // FBL: one window's 8 outputs of this lane: sum_o PhiT[o][own filters] (x) y_nat[s0 + o][0..1].  The y_nat ring is kept
+  // twice (slot and slot + R), so the L taps starting anywhere are contiguous and the loop unrolls without wrap tests.
+  auto fbl_filter = [&](int s0, float* fw) {
+    f2 acc[4] = {0ull, 0ull, 0ull, 0ull};        // (filter, q = 0 / 1) pairs: own filters 2 l, 2 l + 1, 62 + 2 l, 62 + 2 l + 1
+    const float* yb = sYn + s0 * 2;
+    const float* pb = sPhi + 2 * fl;
+#pragma unroll 4
+    for (int o = 0; o < SL; ++o) {
+      const f2 y2 = *reinterpret_cast<const f2*>(yb + 2 * o);
+      const float2 pa = *reinterpret_cast<const float2*>(pb + o * FPD);
+      const float2 pc = *reinterpret_cast<const float2*>(pb + o * FPD + 62);
+      acc[0] = fma2(dup(pa.x), y2, acc[0]);
+      acc[1] = fma2(dup(pa.y), y2, acc[1]);
+      acc[2] = fma2(dup(pc.x), y2, acc[2]);
+      acc[3] = fma2(dup(pc.y), y2, acc[3]);
+    }
+    if (gl < 31) {
+      *reinterpret_cast<ulonglong2*>(fw + 4 * gl) = make_ulonglong2(acc[0], acc[1]);
+      *reinterpret_cast<ulonglong2*>(fw + 124 + 4 * gl) = make_ulonglong2(acc[2], acc[3]);
+    }
+  };
+  if constexpr (FBL) {
+    for (int k = 0; k < M1; ++k) fbl_filter(k, sFeat + k * FST);
+    __syncwarp();
+  } else
   if (AGENT == DLC_OF_FGRC) {
     for (int k = 0; k < M1; ++k)
       for (int i = gl; i < FP; i += GL) {
@@ -329,7 +420,18 @@ of_kernel(const OfArgs a) {
     if (AGENT == DLC_OF_FGRC) {
       const float lr = P.decay ? P.lr / (float)(P.t0 + t + 1) : P.lr;  // _grc.py:145
       // ---- get_action: newest window of the history as it stands (_grc.py:157-169)
-      {
+      if constexpr (FBL) {
+        int snew = fbase + m; if (snew >= M1) snew -= M1;
+        const float* fw = sFeat + snew * FST + 4 * fl;
+        const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(fw), p1 = *reinterpret_cast<const ulonglong2*>(fw + 124);
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa) {
+          const f2 acc = fma2(thr2[aa][3], p1.y, fma2(thr2[aa][2], p1.x, fma2(thr2[aa][1], p0.y, mul2(thr2[aa][0], p0.x))));
+          float part = lo(acc) + hi(acc);                               // (lane 31's block of Theta is zero)
+          part = group_sum<32>(part);
+          if (gl == 0) su[aa] = part;
+        }
+      } else {
         int snew = fbase + m; if (snew >= M1) snew -= M1;
         const float* fw = sFeat + snew * FP;
         for (int aa = 0; aa < n; ++aa) {
@@ -354,12 +456,19 @@ of_kernel(const OfArgs a) {
         float* slot = sYn + ybase * p;   // the oldest entry is replaced by the newest
 #pragma unroll
         for (int k = 0; k < NR; ++k)
-          if (gl + k * GL < p) slot[gl + k * GL] = sy[gl + k * GL] - rc[k];
+          if (gl + k * GL < p) {
+            slot[gl + k * GL] = sy[gl + k * GL] - rc[k];
+            if constexpr (FBL) slot[R * p + gl + k * GL] = sy[gl + k * GL] - rc[k];
+          }
         ybase = (ybase + 1 == R) ? 0 : ybase + 1;
       }
       __syncwarp();
       // ---- filter the newest window (history positions m .. m+L-1) into the ring slot of the oldest one
-      if constexpr (BLK) {
+      if constexpr (FBL) {
+        int s0 = ybase + m; if (s0 >= R) s0 -= R;
+        fbl_filter(s0, sFeat + fbase * FST);
+        fbase = (fbase + 1 == M1) ? 0 : fbase + 1;
+      } else if constexpr (BLK) {
         // taps dealt to lanes: a lane reads y_nat[o] once and feeds all F filters with it
         float* fw = sFeat + fbase * FP;
         int s0 = ybase + m; if (s0 >= R) s0 -= R;
@@ -401,7 +510,97 @@ of_kernel(const OfArgs a) {
         fbase = (fbase + 1 == M1) ? 0 : fbase + 1;
       }
       __syncwarp();
-      if constexpr (BLK) {
+      if constexpr (FBL) {
+        // ---- pass 1: this lane's share of a(k) = Theta phi(k) for every window; reduce-scatter: lane k gets a(k)
+        constexpr int CM1f = SM + 1;
+        float ap[96];
+#pragma unroll
+        for (int e = 0; e < 96; ++e) ap[e] = 0.f;
+        const int fo = 4 * fl;
+        {
+          int sl = fbase;
+#pragma unroll
+          for (int k = 0; k < CM1f; ++k) {
+            const float* fw = sFeat + sl * FST + fo;
+            const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(fw), p1 = *reinterpret_cast<const ulonglong2*>(fw + 124);
+#pragma unroll
+            for (int aa = 0; aa < 3; ++aa) {
+              const f2 acc = fma2(thr2[aa][3], p1.y, fma2(thr2[aa][2], p1.x, fma2(thr2[aa][1], p0.y, mul2(thr2[aa][0], p0.x))));
+              ap[3 * k + aa] = lo(acc) + hi(acc);
+            }
+            sl = (sl + 1 == CM1f) ? 0 : sl + 1;
+          }
+        }
+        warp_reduce_scatter<3>(ap, gl);                    // lane k: a(k)[0..2] in ap[0..2]  (lane 31: zeros)
+        // ---- final_y and the adjoint seeds; lane k owns window k, so its Markov operator index is fixed: m - 1 - gl
+        const int kk = gl < SM ? SM - 1 - gl : 0;
+        const float* g = sG + kk * 6;
+        float fy0 = 0.f, fy1 = 0.f;
+        if (gl < SM) {
+          fy0 = fmaf(g[2], ap[2], fmaf(g[1], ap[1], g[0] * ap[0]));
+          fy1 = fmaf(g[5], ap[2], fmaf(g[4], ap[1], g[3] * ap[0]));
+        }
+        int snew = ybase + R - 1; if (snew >= R) snew -= R;
+        fy0 = 2.f * (sYn[snew * 2] + group_sum<32>(fy0));
+        fy1 = 2.f * (sYn[snew * 2 + 1] + group_sum<32>(fy1));
+        float gk[3];
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa)
+          gk[aa] = gl == SM ? 2.f * ap[aa] : (gl < SM ? fmaf(g[3 + aa], fy1, g[aa] * fy0) : 0.f);
+        __syncwarp();
+        if (gl < CM1f) *reinterpret_cast<float4*>(sAct + 4 * gl) = make_float4(gk[0], gk[1], gk[2], 0.f);
+        __syncwarp();
+        // ---- pass 2: dTheta block of this lane = sum_k g(k) (x) phi(k)[own features]; no cross-lane sum
+        f2 dth[3][4];
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dth[aa][i] = 0ull;
+        {
+          int sl = fbase;
+          // (rolled 4 at a time: with both passes fully unrolled the step loop is ~45 KB of SASS, past the 32 KB
+          // instruction cache -- ncu: no_instruction 0.42 stall cycles per issue -- and nothing here needs a
+          // compile-time window index)
+#pragma unroll 4
+          for (int k = 0; k < CM1f; ++k) {
+            const float* fw = sFeat + sl * FST + fo;
+            const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(fw), p1 = *reinterpret_cast<const ulonglong2*>(fw + 124);
+            const float4 g4 = *reinterpret_cast<const float4*>(sAct + 4 * k);
+            const float gg[3] = {g4.x, g4.y, g4.z};
+#pragma unroll
+            for (int aa = 0; aa < 3; ++aa) {
+              const f2 g2 = dup(gg[aa]);
+              dth[aa][0] = fma2(g2, p0.x, dth[aa][0]);
+              dth[aa][1] = fma2(g2, p0.y, dth[aa][1]);
+              dth[aa][2] = fma2(g2, p1.x, dth[aa][2]);
+              dth[aa][3] = fma2(g2, p1.y, dth[aa][3]);
+            }
+            sl = (sl + 1 == CM1f) ? 0 : sl + 1;
+          }
+        }
+        // ---- Theta <- proj_RM(Theta - lr dTheta)     (_grc.py:144-151).  (Padding features carry zeros: their filters are
+        // zero, so their dTheta is zero and their Theta stays zero -- no masks.)
+        f2 nrm2 = 0ull;
+        const f2 nlr2 = dup(gl < 31 ? -lr : 0.f);   // (lane 31 reads lane 0's rows: its block of Theta must stay zero)
+#pragma unroll
+        for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            thr2[aa][i] = fma2(nlr2, dth[aa][i], thr2[aa][i]);
+            nrm2 = fma2(thr2[aa][i], thr2[aa][i], nrm2);
+          }
+        float nrm = gl < 31 ? lo(nrm2) + hi(nrm2) : 0.f;
+        nrm = sqrtf(group_sum<32>(nrm));
+        const float sc = fminf(1.0f, P.R_M / (nrm + 1e-8f));
+        if (sc < 1.0f) {
+          const f2 sc2 = dup(sc);
+#pragma unroll
+          for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) thr2[aa][i] = mul2(thr2[aa][i], sc2);
+        }
+        __syncwarp();
+      } else if constexpr (BLK) {
         // ---- pass 1: a(k) = Theta phi(k) for this lane's windows; their share of final_y    (_grc.py:97-104)
         float am[CN], fyp[CP];
 #pragma unroll
@@ -605,9 +804,20 @@ of_kernel(const OfArgs a) {
     for (int i = gl; i < h * n; i += GL) a.us_io[(size_t)env * h * n + i] = sUs[i];
   }
   if (AGENT == DLC_OF_FGRC) {
-    for (int e = gl; e < F * n * p; e += GL) {
-      const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
-      a.theta_io[(size_t)env * F * n * p + e] = sTh[aa * FP + f * p + q];
+    if constexpr (FBL) {
+#pragma unroll
+      for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = fbl_feature(j), f = i >> 1, q = i & 1;
+          const float v = (j & 1) ? hi(thr2[aa][j >> 1]) : lo(thr2[aa][j >> 1]);
+          if (gl < 31 && i < SF * SP) a.theta_io[(size_t)env * SF * 6 + (f * 3 + aa) * 2 + q] = v;
+        }
+    } else {
+      for (int e = gl; e < F * n * p; e += GL) {
+        const int f = e / (n * p), rem = e - f * n * p, aa = rem / p, q = rem - aa * p;
+        a.theta_io[(size_t)env * F * n * p + e] = sTh[aa * FP + f * p + q];
+      }
     }
     for (int i = gl; i < R * p; i += GL) {   // oldest -> newest
       const int pos = i / p, q = i - pos * p;
@@ -1052,6 +1262,13 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
   if (a.status_out) a.status_out[env] = status;
 }
 
+// the shape served by the feature-blocked instance of_kernel<FGRC, 32, 10, 3, 2, 30, 121, 61> (DSC(m = 30, h = 10) on the
+// colab's system) unless the caller forces 8 or 16 lanes
+bool of_feature_blocked(const DlcOfParams& P) {
+  return P.agent == DLC_OF_FGRC && P.d == 10 && P.n == 3 && P.p == 2 && P.m == 30 && P.F == 121 && P.L == 61 &&
+         (P.lanes_per_env == 0 || P.lanes_per_env == 32);
+}
+
 // shared-memory layout of one env's slice; returns floats per env
 int layout(OfArgs& a) {
   const DlcOfParams& P = a.p;
@@ -1061,13 +1278,15 @@ int layout(OfArgs& a) {
   a.J = P.agent == DLC_OF_DRC ? P.h : (P.agent == DLC_OF_FGRC ? m : 0);
   a.FP = P.agent == DLC_OF_DRC ? m * p : (P.agent == DLC_OF_FGRC ? P.F * p : 0);
   a.nPhi = P.agent == DLC_OF_FGRC ? ((P.F * P.L + 3) & ~3) : 0;
+  const bool fbl = of_feature_blocked(P);   // the default DSC: transposed filter bank, padded feature rows, Theta in registers
+  if (fbl) a.nPhi = P.L * ((P.F + 3) & ~3);
   a.oA = take(d * d); a.oB = take(d * n); a.oC = take(p * d);
   a.oG = take(a.J * p * n);
   a.oK = take(P.agent == DLC_OF_LQG ? n * d : (P.agent == DLC_OF_DRC ? n * p : 0));
   a.oL = take(P.agent == DLC_OF_LQG ? d * p : 0);
-  a.oTh = take(n * a.FP);
-  a.oFeat = take(P.agent == DLC_OF_FGRC ? (m + 1) * a.FP : 0);
-  a.oYn = take(P.agent == DLC_OF_FGRC ? (P.L + m) * p : (P.agent == DLC_OF_DRC ? m * p : 0));
+  a.oTh = take(fbl ? 0 : n * a.FP);
+  a.oFeat = take(P.agent == DLC_OF_FGRC ? (m + 1) * (fbl ? 248 : a.FP) : 0);
+  a.oYn = take(P.agent == DLC_OF_FGRC ? (fbl ? 2 : 1) * (P.L + m) * p : (P.agent == DLC_OF_DRC ? m * p : 0));
   a.oUs = take(P.agent == DLC_OF_DRC ? P.h * n : 0);
   a.oX = take(d); a.oZ = take(d); a.oY = take(p); a.oU = take(n);
   a.oAct = take((m + 1) * n); a.oGact = take((m + 1) * n); a.oFy = take(p);
@@ -1171,6 +1390,12 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   // envs per CTA: whole warps, as many as half the SM's shared memory holds (at most 256 threads)
   int epc = 256 / GL;
   while (epc > 32 / GL && fixed + per_env * epc > (size_t)max_smem / 2) epc >>= 1;
+  // the feature-blocked DSC instance is a warp per env with 34 KB of windows each and a 30 KB filter bank per CTA: one CTA
+  // per SM with as many envs as fit (5) instead of two CTAs of two
+  if (GL == 32 && of_feature_blocked(*p)) {
+    epc = 8;
+    while (epc > 1 && fixed + per_env * epc > (size_t)max_smem) --epc;
+  }
   if (fixed + per_env * epc > (size_t)max_smem) {   // not even one warp of groups: fall back to a warp per env
     GL = 32;
     epc = 1;

@@ -271,6 +271,7 @@ class Runner:
         for i in range(-max(warmup, 0), steps):
             if i == 0:
                 self.sync()
+                torch.cuda.nvtx.range_push("dlc_timed")   # `ncu --nvtx --nvtx-include "dlc_timed/"`: the timed region only
                 t0.record()
             # drop the previous step's outputs first: holding them while the next rollout allocates its cost buffer
             # makes torch's caching allocator cudaMalloc a second block inside the timed region
@@ -287,6 +288,7 @@ class Runner:
             self.stats.copy_(reduce_stats(local_stats(r.cost_sum, r.status)))
         t1.record()
         self.sync()
+        torch.cuda.nvtx.range_pop()
         total_ms = t0.elapsed_time(t1)
         each = [a.elapsed_time(b) for a, b in kev]
         tm = torch.tensor([total_ms, sum(each) / max(steps, 1)], dtype=torch.float64, device=self.dev)

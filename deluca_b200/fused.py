@@ -137,11 +137,16 @@ def _copy_stream(dev):
     return _COPY_STREAMS[dev]
 
 
-def lds_rollout_to_host(A, B, K, x, T, host_costs, *, chunks=8, W=None, t0=0, env_t0=None, donate=False, **kw):
+def lds_rollout_to_host(A, B, K, x, T, host_costs, *, chunks=8, W=None, t0=0, env_t0=None, donate=False,
+                        materialize_disturbance=False, **kw):
     """``lds_rollout`` whose losses[T,N] (``Rollout.losses``, ``deluca/training/apg.py:68``) land in PINNED host memory
     while the rollout is still running: the horizon is cut into ``chunks`` launches resumed from the carried agent / env
     state (same arithmetic; the in-kernel disturbance stream is keyed by the env step counter), and each chunk's costs
     travel device -> host on a side stream under the next chunk's kernel.  Only the last chunk's copy is exposed.
+    ``materialize_disturbance`` (off): with ``W=None``, write each chunk's slice of the in-kernel Gaussian stream to a
+    reusable HBM buffer with ``dlc_gaussian_disturbance_f32`` first (the SAME stream, bit for bit) and let the rollout
+    read it.  Measured on the target (tools/probe_e2e_chunks.py): no gain -- the generator pass costs what drawing the
+    normals inside the rollout kernel does (391 vs 392 ms at 8 chunks); a chunk costs ~3 ms of state I/O and set-up.
     Returns the ``lds_rollout`` result of the whole horizon (``costs`` = ``host_costs``) plus ``done``, a CUDA event that
     completes when the last copy has; the caller must wait on it (or synchronise) before reading ``host_costs``."""
     if not (isinstance(host_costs, torch.Tensor) and not host_costs.is_cuda and host_costs.is_pinned()):
@@ -162,11 +167,20 @@ def lds_rollout_to_host(A, B, K, x, T, host_costs, *, chunks=8, W=None, t0=0, en
     eps_new = kw.pop("eps_new", None)
     cost_sum = status = r = None
     xc = x
+    w_std = kw.get("w_std", 0.5)
+    gen = W is None and materialize_disturbance and w_std > 0 and kw.get("policy", "gpc") != "open"
+    wbuf = None
+    if gen:
+        wbuf = torch.empty((max(bounds[c + 1] - bounds[c] for c in range(chunks)), N, x.shape[1]), device=dev)
     for c in range(chunks):
         lo, hi = bounds[c], bounds[c + 1]
         if hi == lo:
             continue
-        r = lds_rollout(A, B, K, xc, hi - lo, W=None if W is None else W[lo:hi], t0=t0 + lo, env_t0=env_t0 + lo,
+        Wc = None if W is None else W[lo:hi]
+        if gen:
+            Wc = gaussian_disturbance(N, hi - lo, x.shape[1], kw.get("seed", 0), env_offset=kw.get("env_offset", 0),
+                                      t0=env_t0 + lo, std=w_std, out=wbuf[:hi - lo])
+        r = lds_rollout(A, B, K, xc, hi - lo, W=Wc, t0=t0 + lo, env_t0=env_t0 + lo,
                         eps_new=None if eps_new is None else eps_new[lo:hi], keep_costs=True,
                         donate=donate or c > 0, **state, **kw)
         ready = torch.cuda.Event()

@@ -170,28 +170,39 @@ __device__ __forceinline__ void warp_colsum32(float (&q)[kHalf], int lane) {
   }
 }
 
-template <int MB>
-__global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const SharedArgs a) {
+// NT envs per CTA (= MMA N), TH threads (TH = 4 NT: four threads stage one env; TH / 128 warps share each TMEM lane quadrant
+// and split the NT accumulator columns into 32-wide halves), NS pipeline stages.  <64, 256, 4> is one CTA per SM (r01);
+// <32, 128, 2> fits TWO CTAs per SM (111 KB of shared memory, 128 of the 512 TMEM columns, 214 x 128 registers each), so
+// the epilogue of one CTA's step runs under the other CTA's MMAs without any change to the per-CTA program: the state
+// feedback x_{t+1} = f(x_t) forbids overlapping a CTA's own step t+1 MMAs with its step t epilogue, two independent
+// CTAs per SM do not care.  Each CTA streams the whole operator, so the per-env L2 traffic doubles; TMA multicast over
+// a cluster of 2 / 4 CTAs takes it back.
+template <int MB, int NT, int TH, int NS>
+__global__ void __launch_bounds__(TH, TH == 256 ? 1 : 2) lds_shared_lqr_kernel(const SharedArgs a) {
+  static_assert(TH == 4 * NT && (TH == 256 || TH == 128), "four staging threads per env; one or two warps per TMEM quadrant");
+  constexpr uint32_t XB = NT * 4 + 4;             // floats per 4-coordinate block of the X operand (padded by 16 B)
+  constexpr int NTc = NT;
+  auto xoff = [](int n, int k) { return (uint32_t)(k >> 2) * XB + (uint32_t)n * 4u + (uint32_t)(k & 3); };
   extern __shared__ __align__(1024) unsigned char smem[];
   const int rows = a.RP;
   const uint32_t part_floats = (uint32_t)(kKC / 4) * rows * 4;          // one hi (or lo) part of a stage
   const uint32_t part_bytes = part_floats * 4, stage_bytes = 2 * part_bytes;
   const int d = a.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t env0 = (int64_t)blockIdx.x * kNT;
-  const int nvalid = (int)((a.N - env0) < kNT ? (a.N - env0 > 0 ? a.N - env0 : 0) : kNT);
+  const int64_t env0 = (int64_t)blockIdx.x * NT;
+  const int nvalid = (int)((a.N - env0) < NT ? (a.N - env0 > 0 ? a.N - env0 : 0) : NT);
   // shared-memory carve-up
-  float* sXhi = reinterpret_cast<float*>(smem);                         // [d/4][kNT (+1 pad)][4]
-  float* sXlo = sXhi + (size_t)(d / 4) * kXBlock;
-  float* sG0 = sXlo + (size_t)(d / 4) * kXBlock;                                  // stage s at sG0 + s * 2 * part_floats
-  float* sSum = sG0 + 2 * kNS * part_floats;                            // [2 (x, u)][4 warps][kNT] column sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 2 * 4 * kNT);     // full[kNS], empty[kNS], accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kNS + 1);
-  uint64_t *bar_full = bars, *bar_empty = bars + kNS, *bar_accum = bars + 2 * kNS;
+  float* sXhi = reinterpret_cast<float*>(smem);                         // [d/4][NT (+1 pad)][4]
+  float* sXlo = sXhi + (size_t)(d / 4) * XB;
+  float* sG0 = sXlo + (size_t)(d / 4) * XB;                                  // stage s at sG0 + s * 2 * part_floats
+  float* sSum = sG0 + 2 * NS * part_floats;                            // [2 (x, u)][4 warps][NT] column sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 512);            // (sSum rows are indexed which * 8 + warp: 16 x 32) full[NS], empty[NS], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  uint64_t *bar_full = bars, *bar_empty = bars + NS, *bar_accum = bars + 2 * NS;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n"
-                 :: "r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                 :: "r"(smem_u32(tmem_slot)), "n"(NT * 4) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   const int C = a.C;
@@ -199,13 +210,13 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   if (C > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   if (tid == 0) {
-    for (int i = 0; i < kNS; ++i) mbar_init(&bars[i], 1);                // full: own producer's arrive.expect_tx
-    for (int i = 0; i < kNS; ++i) mbar_init(&bars[kNS + i], C);          // empty: one commit per CTA of the cluster
-    mbar_init(&bars[2 * kNS], 1);
+    for (int i = 0; i < NS; ++i) mbar_init(&bars[i], 1);                // full: own producer's arrive.expect_tx
+    for (int i = 0; i < NS; ++i) mbar_init(&bars[NS + i], C);          // empty: one commit per CTA of the cluster
+    mbar_init(&bars[2 * NS], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   // X_0 -> operand buffer (hi/lo split); |x_0|^2 per env through the column-sum scratch
-  float xsq = 0.f;  // thread n < kNT: |x_t|^2 of env n
+  float xsq = 0.f;  // thread n < NT: |x_t|^2 of env n
   {
     float part = 0.f;  // this thread's share of env (tid / 4): a quarter of the coordinates
     const int n = tid >> 2, k0 = (tid & 3) * (d / 4);
@@ -228,16 +239,16 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (tid < kNT) xsq = sSum[tid];
+  if (tid < NT) xsq = sSum[tid];
   if (C > 1) cluster_sync_all();   // peers' barriers are initialised before anything is multicast at them
   else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t idesc = umma_idesc_tf32(128, kNT);
+  const uint32_t idesc = umma_idesc_tf32(128, NT);
   const int nchunk = d / kKC;
   const int64_t total = (int64_t)a.T * nchunk;                           // G chunks consumed over the rollout
   const uint32_t lboA = (uint32_t)rows * 16u;
-  constexpr uint32_t lboB = kXBlock * 4;      // bytes between the two 4-coordinate halves of one K = 8 MMA step
+  constexpr uint32_t lboB = XB * 4;      // bytes between the two 4-coordinate halves of one K = 8 MMA step
 
   // TMA producer (thread 0): one bulk copy per chunk; G is packed so that a chunk is contiguous
   auto issue_load = [&](int s, int c) {
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
     }
   };
   if (tid == 0) {
-    for (int g = 0; g < kNS && g < total; ++g) issue_load(g, g % nchunk);
+    for (int g = 0; g < NS && g < total; ++g) issue_load(g, g % nchunk);
   }
   // descriptor bases: per-MMA descriptors differ from these only in the 14-bit start-address field
   const uint64_t a_desc0 = umma_desc(smem_u32(sG0), lboA, 128);
@@ -271,8 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   const uint32_t lane_taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)half * kHalf;
   const int nbase = half * kHalf;
   int fill = 0, fphase = 0;      // pipeline cursor of this thread's role (stage index, phase parity)
-  int cnext = kNS % nchunk;      // producer: chunk index of the next refill
-  int64_t gnext = kNS;
+  int cnext = NS % nchunk;      // producer: chunk index of the next refill
+  int64_t gnext = NS;
 
   for (int t = 0; t < a.T; ++t) {
     float wv[kHalf];
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
       const int row = b * 128 + quad * 32 + lane;
       if (a.W != nullptr && row < d) {
         const float* wrow = a.W + ((int64_t)t * a.N + env0 + nbase) * d + row;
-        if (nvalid == kNT) {
+        if (nvalid == NT) {
 #pragma unroll
           for (int n = 0; n < kHalf; ++n) wv[n] = __ldg(wrow + (uint32_t)n * (uint32_t)d);
         } else {
@@ -300,13 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
         if (lane == 0 && gnext < total) issue_load(fill, cnext);
         ++gnext;
         cnext = cnext + 1 == nchunk ? 0 : cnext + 1;
-        if (++fill == kNS) { fill = 0; fphase ^= 1; }
+        if (++fill == NS) { fill = 0; fphase ^= 1; }
       }
     } else if (warp == 1) {
       // ---- MMA warp: every lane tracks the pipeline (warp-uniform descriptors), one elected lane issues
       uint64_t bhi = bhi_desc0, blo = blo_desc0;
       for (int c = 0; c < nchunk; ++c) {
-        if (!(a.dbg & 2) || (t == 0 && c < kNS)) mbar_wait(&bar_full[fill], (uint32_t)fphase);
+        if (!(a.dbg & 2) || (t == 0 && c < NS)) mbar_wait(&bar_full[fill], (uint32_t)fphase);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint64_t ahi = a_desc0 + (uint64_t)((uint32_t)fill * (stage_bytes >> 4));
         const uint64_t alo = ahi + (part_bytes >> 4);
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
         if (elect_one()) {
 #pragma unroll
           for (int b = 0; b < MB; ++b) {
-            const uint32_t td = tmem_base + (uint32_t)b * kNT;
+            const uint32_t td = tmem_base + (uint32_t)b * NT;
             umma_tf32(td, ahi + (uint64_t)(b * 128), bhi, idesc, acc);     // 128 rows x 16 B = 2048 B >> 4
             if (!(a.dbg & 1)) {
               umma_tf32(td, ahi + (uint64_t)(b * 128), blo, idesc, 1);
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
         __syncwarp();
         bhi += (2 * lboB) >> 4;
         blo += (2 * lboB) >> 4;
-        if (++fill == kNS) { fill = 0; fphase ^= 1; }
+        if (++fill == NS) { fill = 0; fphase ^= 1; }
       }
     }
     load_w(0);
@@ -339,10 +350,10 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
     for (int b = 0; b < MB; ++b) {
       const int row = b * 128 + quad * 32 + lane;                        // output row of G owned by this thread
       uint32_t v[kHalf];
-      tmem_ld_row32(lane_taddr + (uint32_t)b * kNT, v);
+      tmem_ld_row32(lane_taddr + (uint32_t)b * NT, v);
       const bool is_x = row < d, is_u = row >= d && row < d + a.m;
-      float* xh = sXhi + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3) + (uint32_t)nbase * 4u;   // lane = coordinate: 32 banks
-      float* xl = sXlo + (uint32_t)(row >> 2) * kXBlock + (uint32_t)(row & 3) + (uint32_t)nbase * 4u;
+      float* xh = sXhi + (uint32_t)(row >> 2) * XB + (uint32_t)(row & 3) + (uint32_t)nbase * 4u;   // lane = coordinate: 32 banks
+      float* xl = sXlo + (uint32_t)(row >> 2) * XB + (uint32_t)(row & 3) + (uint32_t)nbase * 4u;
       float qx[kHalf];
       if (is_x) {
 #pragma unroll
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
       const int which = (b * 128 >= d) ? 1 : 0;                          // 0: state block (or mixed: x part), 1: action block
       sSum[(which * 8 + warp) * kHalf + lane] = qx[0];
       __syncthreads();
-      if (tid < kNT) {                                                   // thread = env: add the four quadrants of its half
+      if (tid < NT) {                                                   // thread = env: add the four quadrants of its half
         const int hw = (tid >> 5) * 4, col = tid & 31;
         const float* ps = sSum + (which * 8 + hw) * kHalf + col;
         const float s4 = (ps[0] + ps[kHalf]) + (ps[2 * kHalf] + ps[3 * kHalf]);
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
       }
       __syncthreads();
     }
-    if (tid < kNT) {
+    if (tid < NT) {
       const float cost = xsq + us;                                       // x_t'x_t + u_t'u_t
       if (tid < nvalid) {
         if (a.cost_out) a.cost_out[(int64_t)t * a.N + env0 + tid] = cost;
@@ -418,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) lds_shared_lqr_kernel(const Share
   __syncthreads();
   if (C > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" :: "r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "n"(NT * 4) : "memory");
   }
 }
 
@@ -457,25 +468,35 @@ extern "C" int32_t dlc_lds_shared_lqr_rollout_f32(int64_t N, int32_t T, int32_t 
   a.Gp = G_packed; a.W = W; a.x_io = x_io; a.cost_out = cost_out; a.cost_sum_out = cost_sum_out;
   a.status_out = status_out;
   const size_t part = (size_t)(kKC / 4) * a.RP * 4;
-  const size_t smem = ((size_t)2 * (d / 4) * kXBlock + 2 * kNS * part + 2 * 4 * kNT) * sizeof(float) + 128;
-  void (*kern)(SharedArgs) = a.MB == 1 ? lds_shared_lqr_kernel<1> : a.MB == 2 ? lds_shared_lqr_kernel<2>
-                                                                               : lds_shared_lqr_kernel<3>;
+  // launch shape: default = one 64-env CTA per SM; DLC_SHARED_VARIANT=0 = two 32-env CTAs per SM (see the kernel's comment;
+  // measured 7 % slower: N = 32 MMAs and twice the operator traffic cost what the overlap wins)
+  const char* venv = getenv("DLC_SHARED_VARIANT");
+  const int variant = venv ? atoi(venv) : 1;
+  const int NT = variant == 1 ? 64 : 32, TH = 4 * NT, NS = variant == 1 ? 4 : 2;
+  const size_t smem = ((size_t)2 * (d / 4) * (NT * 4 + 4) + 2 * NS * part + 2 * 4 * 64) * sizeof(float) + 128;
+  void (*kern)(SharedArgs);
+  if (variant == 1)
+    kern = a.MB == 1 ? lds_shared_lqr_kernel<1, 64, 256, 4> : a.MB == 2 ? lds_shared_lqr_kernel<2, 64, 256, 4>
+                                                                        : lds_shared_lqr_kernel<3, 64, 256, 4>;
+  else
+    kern = a.MB == 1 ? lds_shared_lqr_kernel<1, 32, 128, 2> : a.MB == 2 ? lds_shared_lqr_kernel<2, 32, 128, 2>
+                                                                        : lds_shared_lqr_kernel<3, 32, 128, 2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_shared_lqr)");
-  unsigned grid = (unsigned)((N + kNT - 1) / kNT);
+  unsigned grid = (unsigned)((N + NT - 1) / NT);
   // clusters of up to 4 CTAs share every G chunk through TMA multicast (L2 traffic / C); idle CTAs of a
   // partially filled last cluster run on zeros and store nothing
   const char* denv = getenv("DLC_SHARED_DBG");
   a.dbg = denv ? atoi(denv) : 0;
   const char* cenv = getenv("DLC_SHARED_CLUSTER");
-  int C = cenv ? atoi(cenv) : 4;
-  if (C != 1 && C != 2 && C != 4) C = 4;
+  int C = cenv ? atoi(cenv) : 1;   // (measured, tools/bench_shared_lqr.py: 6.56 / 6.64 / 7.46 ms at C = 1 / 2 / 4 -- not L2-bound)
+  if (C != 1 && C != 2 && C != 4) C = 1;
   while (C > 1 && grid < (unsigned)C) C >>= 1;
   a.C = C;
   grid = (grid + C - 1) / C * C;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(TH);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];

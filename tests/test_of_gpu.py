@@ -290,7 +290,7 @@ def test_dsc_default_shape_matches_oracle():
 
 
 def test_grc_register_kernel_resume_projection_and_broken_promise():
-    """The register-resident GRC kernel (colab shape, reserved = 1): resume == uninterrupted bit for bit, agreement with
+    """The register-resident GRC kernel (colab shape, DLC_OF_FLAG_PHI_IDENTITY): resume == uninterrupted bit for bit, agreement with
     the lane-group kernel when the projection is active and without decay, in-kernel disturbances, and a loud failure
     when the caller's `Phi is the identity` promise does not hold."""
     from deluca_b200.fused import lds_of_rollout

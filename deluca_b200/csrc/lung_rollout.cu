@@ -2,6 +2,8 @@
 // One thread per breath; all state in registers (DelayLung's two valve histories in a local
 // ring); per step five/six coalesced 4-byte stores per thread ([T,N] time-major series), which is
 // what bounds the kernel (HBM writes).
+#include <stdlib.h>
+
 #include <mutex>
 #include <type_traits>
 
@@ -852,10 +854,109 @@ __global__ void __launch_bounds__(128) lung_pid_grad_kernel(const LungGradArgs a
   }
 }
 
+
+// The same value and gradient in FORWARD mode: the leaves are three gains, so their tangents ride along the episode --
+// (dP, dV, dp, di, dd, dloss) x 3 = 18 registers -- and nothing is checkpointed: no workspace, no second sweep, no HBM
+// traffic beyond the gains in and loss + gradient out (the reverse-mode kernel above writes and re-reads 48 B per
+// env-step and recomputes every step).  Same step as lung_pid_grad_kernel's forward sweep, operation for operation.
+template <int NK>
+__global__ void __launch_bounds__(128) lung_pid_grad_fwd_kernel(const LungGradArgs a) {
+  const DlcLungParams& p = a.p;
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = n < p.N;
+  const int64_t nn = live ? n : p.N - 1;
+  float kf[DLC_MAX_KNOTS];
+  {
+    const float* g = a.kf + (p.kf_per_env ? nn * p.nk : 0);
+#pragma unroll
+    for (int k = 0; k < DLC_MAX_KNOTS; ++k) kf[k] = k < p.nk ? g[k] : 0.f;
+  }
+  const float kg[3] = {a.K[nn * 3 + 0], a.K[nn * 3 + 1], a.K[nn * 3 + 2]};
+  const float dec = p.pid_decay;
+  const float pc_r0sq = __fdiv_rn(p.PC, p.r0_sq);
+  float P = a.reset_pressure, V = p.min_volume, cp = 0.f, ci = 0.f, cd = 0.f, time = 0.f, total = 0.f;
+  float dP[3] = {0.f, 0.f, 0.f}, dV[3] = {0.f, 0.f, 0.f}, dcp[3] = {0.f, 0.f, 0.f}, dci[3] = {0.f, 0.f, 0.f},
+        dcd[3] = {0.f, 0.f, 0.f}, dtot[3] = {0.f, 0.f, 0.f};
+  for (int t = 0; t < p.T; ++t) {
+    P += a.noise;                                                  // train_controller.py:51-53
+    const float xo = fmod_pos(time, p.period);
+    const float err = interp_knots<NK>(p, kf, xo) - P;
+    const float ni = ci + dec * (err - ci), nd = cd + dec * ((err - cp) - cd);
+    const float pid[3] = {err, ni, nd};
+    const float u_raw = (err * kg[0] + ni * kg[1]) + nd * kg[2];
+    const float u = fminf(fmaxf(u_raw, 0.f), 100.f);
+    const bool u_in = u_raw >= 0.f && u_raw <= 100.f;             // clamp: the tangent passes inside the range
+    const bool inhale = xo <= p.xp_in;                             // u_out == 0
+    const float vraw = tanh_plus_one(0.03f * (3.0f * u - 130.f));   // (the rollout kernel's MUFU forms throughout)
+    const float th = vraw - 1.0f;
+    const float vr = fminf(fmaxf(vraw, 0.f), 1.72f) * p.R;
+    float flow = fminf(fmaxf(vr, 0.f), 2.0f);
+    const bool valve_open = P > p.peep_valve;
+    const float bleed = (valve_open && !inhale) ? 0.05f : 0.f;
+    flow -= bleed * P;
+    // d flow / d u_raw through tanh and the three clamps
+    const float chain = (u_in && vraw >= 0.f && vraw <= 1.72f && vr >= 0.f && vr <= 2.0f)
+                            ? 0.09f * (1.0f - th * th) * p.R : 0.f;
+    const float diff = interp_knots<NK>(p, kf, fmod_pos(a.tt[t], p.period)) - P;
+    float dl = 0.f;                                                // d loss_t / d P
+    if (inhale) {
+      total += a.loss_kind == DLC_LOSS_L1 ? fabsf(diff) : diff * diff;
+      dl = a.loss_kind == DLC_LOSS_L1 ? (diff > 0.f ? -1.0f : (diff < 0.f ? 1.0f : 0.f)) : -2.0f * diff;
+    }
+    float Vn = V + flow * p.dt;
+    if (p.leak) Vn += p.leak_coef * (p.min_volume - Vn);
+    const float r = cbrt_pos(Vn * 0.238732414637843f);              // (3V / 4pi)^(1/3)
+    const float ir = rcpf_approx(r), ir2 = ir * ir, q = p.r0 * ir, q2 = q * q, q6 = q2 * q2 * q2;
+    const float dPdV = pc_r0sq * (-ir2 + 7.0f * q6 * ir2) * (r * rcpf_approx(3.0f * Vn));
+    const float keep = p.leak ? 1.0f - p.leak_coef : 1.0f;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      dtot[g] = fmaf(dl, dP[g], dtot[g]);
+      const float derr = -dP[g];
+      const float dni = dci[g] + dec * (derr - dci[g]);
+      const float dnd = dcd[g] + dec * ((derr - dcp[g]) - dcd[g]);
+      const float du_raw = ((derr * kg[0] + dni * kg[1]) + dnd * kg[2]) + pid[g];
+      const float dflow = chain * du_raw - bleed * dP[g];
+      dcp[g] = derr; dci[g] = dni; dcd[g] = dnd;
+      dV[g] = keep * (dV[g] + p.dt * dflow);
+      dP[g] = dPdV * dV[g];
+    }
+    cp = err; ci = ni; cd = nd;
+    V = Vn;
+    P = fmaf(pc_r0sq * fmaf(-q2 * q2, q2, 1.0f), ir, p.P0);         // P0 + PC (1 - (r0/r)^6) / (r0^2 r)
+    time += p.dt;
+  }
+  if (live) {
+    a.loss_out[n] = total;
+    a.grad_out[n * 3 + 0] = dtot[0]; a.grad_out[n * 3 + 1] = dtot[1]; a.grad_out[n * 3 + 2] = dtot[2];
+  }
+  if (a.sums_out) {   // block reduction, one atomic per block and component
+    __shared__ double red[4][4];
+    double v[4] = {live ? (double)total : 0.0, live ? (double)dtot[0] : 0.0, live ? (double)dtot[1] : 0.0,
+                   live ? (double)dtot[2] : 0.0};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+    if ((threadIdx.x & 31) == 0)
+      for (int c = 0; c < 4; ++c) red[c][threadIdx.x >> 5] = v[c];
+    __syncthreads();
+    if (threadIdx.x < 4) atomicAdd(&a.sums_out[threadIdx.x], (red[threadIdx.x][0] + red[threadIdx.x][1]) +
+                                                                  (red[threadIdx.x][2] + red[threadIdx.x][3]));
+  }
+}
+
 }  // namespace dlc
 
+// DLC_LUNG_GRAD_REVERSE=1 selects the checkpointed reverse-mode kernel (kept for cross-checks and measurements); the
+// default forward-mode kernel needs no workspace.
+static bool lung_grad_reverse() {
+  static const bool rev = [] { const char* e = getenv("DLC_LUNG_GRAD_REVERSE"); return e && atoi(e) != 0; }();
+  return rev;
+}
+
 extern "C" size_t dlc_lung_pid_grad_workspace_bytes(const DlcLungParams* p) {
-  if (!p || p->N <= 0 || p->T <= 0) return 0;
+  if (!p || p->N <= 0 || p->T <= 0 || !lung_grad_reverse()) return 0;
   return (size_t)p->T * 6 * (size_t)p->N * sizeof(float);
 }
 
@@ -872,13 +973,19 @@ extern "C" int32_t dlc_lung_pid_grad_f32(const DlcLungParams* p, const float* K,
   if (p->N == 0) return DLC_OK;
   if (!K || !kf || (!tt && p->T > 0) || !loss_out || !gradK_out)
     return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: NULL buffer");
-  if (p->T > 0 && (!workspace || workspace_bytes < dlc_lung_pid_grad_workspace_bytes(p)))
+  const bool reverse = lung_grad_reverse();
+  if (reverse && p->T > 0 && (!workspace || workspace_bytes < dlc_lung_pid_grad_workspace_bytes(p)))
     return fail(DLC_ERR_WORKSPACE, "dlc_lung_pid_grad_f32: workspace smaller than dlc_lung_pid_grad_workspace_bytes()");
   LungGradArgs a;
   a.p = *p; a.K = K; a.kf = kf; a.tt = tt; a.loss_kind = loss_kind; a.noise = noise; a.reset_pressure = reset_pressure;
   a.loss_out = loss_out; a.grad_out = gradK_out; a.sums_out = sums_out; a.ws = (float*)workspace;
   const unsigned grid = (unsigned)((p->N + 127) / 128);
-  if (p->nk == 7) lung_pid_grad_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-  else lung_pid_grad_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  if (reverse) {
+    if (p->nk == 7) lung_pid_grad_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else lung_pid_grad_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    if (p->nk == 7) lung_pid_grad_fwd_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else lung_pid_grad_fwd_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  }
   return cuda_status(cudaGetLastError(), "lung_pid_grad_kernel launch");
 }

@@ -149,9 +149,10 @@ __device__ __forceinline__ float cbrt_pos(float x) {
   return r;
 }
 
-// MODE >= 0 fixes p.mode at compile time (the closed-loop episode is the hot instance), MODE < 0 reads it; ALLOUT
-// promises that all six series pointers are non-NULL.
-template <int SIM, int NK, int MODE, bool ALLOUT>
+// MODE >= 0 fixes p.mode at compile time (the closed-loop episode is the hot instance), MODE < 0 reads it; OUTS = 1
+// promises that all six series pointers are non-NULL, OUTS = 2 that the four per-breath ones are and that timestamp /
+// flow are not wanted (see lung_pid_pair_kernel's LEAN), OUTS = 0 tests every pointer.
+template <int SIM, int NK, int MODE, int OUTS>
 __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
   extern __shared__ float ring[];                                  // DelayLung valve histories [2][delay][blockDim]
   const DlcLungParams& p = a.p;
@@ -323,12 +324,12 @@ __global__ void __launch_bounds__(128) lung_pid_kernel(const LungArgs a) {
     }
     // ---- emitted series                                          run_controller.py:128-141
     const float ts = dt * steps - run_dt;
-    if (ALLOUT || o_ts) { *o_ts = ts; o_ts += N; }
-    if (ALLOUT || o_uin) { *o_uin = u_in; o_uin += N; }
-    if (ALLOUT || o_uout) { *o_uout = u_out; o_uout += N; }
-    if (ALLOUT || o_pr) { *o_pr = pr_emit; o_pr += N; }
-    if (ALLOUT || o_flow) { *o_flow = p.env_flow; o_flow += N; }
-    if (ALLOUT || o_tgt) {                                          // waveform.at(timestamps), :207
+    if (OUTS == 1 || (OUTS == 0 && o_ts)) { *o_ts = ts; o_ts += N; }
+    if (OUTS >= 1 || o_uin) { *o_uin = u_in; o_uin += N; }
+    if (OUTS >= 1 || o_uout) { *o_uout = u_out; o_uout += N; }
+    if (OUTS >= 1 || o_pr) { *o_pr = pr_emit; o_pr += N; }
+    if (OUTS == 1 || (OUTS == 0 && o_flow)) { *o_flow = p.env_flow; o_flow += N; }
+    if (OUTS >= 1 || o_tgt) {                                          // waveform.at(timestamps), :207
       *o_tgt = interp_seg<NK>(p, kf, phase(ts, q_ts), seg_out, lanes);
       o_tgt += N;
     }
@@ -393,7 +394,10 @@ struct LungEnv {
   Seg seg_pid, seg_out;
 };
 
-template <int SIM>
+// LEAN: the timestamp and flow series are not stored.  Both are the same for every breath of a batch that starts at a
+// common time -- flow is the env's static field, the timestamp depends on the step only -- so a caller can keep ONE
+// column of each (16 B per env-step instead of 24; the Python mirror does, lung/utils/scripts/run_controller.py).
+template <int SIM, bool LEAN>
 __global__ void __launch_bounds__(128) lung_pid_pair_kernel(const LungArgs a) {
   constexpr int NK = 7;
   extern __shared__ float ring[];                 // DelayLung: [2][delay][2 * blockDim + 1], column = e * blockDim + tid
@@ -479,11 +483,11 @@ __global__ void __launch_bounds__(128) lung_pid_pair_kernel(const LungArgs a) {
       }
     }
     const int64_t N2 = p.N >> 1;
-    float2* o_ts = reinterpret_cast<float2*>(b.timestamp_out + n0);
+    float2* o_ts = LEAN ? nullptr : reinterpret_cast<float2*>(b.timestamp_out + n0);
     float2* o_uin = reinterpret_cast<float2*>(b.u_in_out + n0);
     float2* o_uout = reinterpret_cast<float2*>(b.u_out_out + n0);
     float2* o_pr = reinterpret_cast<float2*>(b.pressure_out + n0);
-    float2* o_flow = reinterpret_cast<float2*>(b.flow_out + n0);
+    float2* o_flow = LEAN ? nullptr : reinterpret_cast<float2*>(b.flow_out + n0);
     float2* o_tgt = reinterpret_cast<float2*>(b.target_out + n0);
 
     auto episode = [&](auto fast_tag) {
@@ -558,11 +562,11 @@ __global__ void __launch_bounds__(128) lung_pid_pair_kernel(const LungArgs a) {
           v_tgt[e] = interp_seg<NK>(p, kf[e], phase(ts, s.q_ts), s.seg_out, lanes);
           s.chk = fmaf(0.f, s.pressure, s.chk);
         }
-        *o_ts = make_float2(v_ts[0], v_ts[1]); o_ts += N2;
+        if (!LEAN) { *o_ts = make_float2(v_ts[0], v_ts[1]); o_ts += N2; }
         *o_uin = make_float2(v_uin[0], v_uin[1]); o_uin += N2;
         *o_uout = make_float2(v_uout[0], v_uout[1]); o_uout += N2;
         *o_pr = make_float2(v_pr[0], v_pr[1]); o_pr += N2;
-        *o_flow = make_float2(p.env_flow, p.env_flow); o_flow += N2;
+        if (!LEAN) { *o_flow = make_float2(p.env_flow, p.env_flow); o_flow += N2; }
         *o_tgt = make_float2(v_tgt[0], v_tgt[1]); o_tgt += N2;
       }
     };
@@ -640,16 +644,19 @@ extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLun
   a.b = *b;
   const unsigned grid = (unsigned)((p->N + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
-  // hot instance: default 7-knot waveform table, closed loop, all six series requested
-  const bool hot = p->nk == 7 && p->mode == DLC_LUNG_MODE_CLOSED_LOOP && b->timestamp_out && b->u_in_out &&
-                   b->u_out_out && b->pressure_out && b->flow_out && b->target_out;
+  // hot instances: default 7-knot waveform table, closed loop, and either all six series or the four that differ between
+  // breaths (timestamp_out and flow_out both NULL: "lean")
+  const bool four = p->nk == 7 && p->mode == DLC_LUNG_MODE_CLOSED_LOOP && b->u_in_out && b->u_out_out &&
+                    b->pressure_out && b->target_out;
+  const bool lean = four && !b->timestamp_out && !b->flow_out;
+  const bool hot = four && b->timestamp_out && b->flow_out;
   // two breaths per thread (float2 rows) when the batch is even and every [N] array is 8-byte aligned
   auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
   // (measured, tools/bench_lung_n.py: the wider stores win from ~48 steps on BalloonLung, ~96 on DelayLung; below that
   // the one-per-thread kernel's higher occupancy hides the state load / store better)
   const bool long_enough = p->kernel_variant == 2 || p->T >= (p->sim == DLC_SIM_BALLOON ? 48 : 96);
-  bool pair = hot && p->kernel_variant != 1 && long_enough && (p->N % 2 == 0) && al8(b->timestamp_out) && al8(b->u_in_out) &&
-              al8(b->u_out_out) && al8(b->pressure_out) && al8(b->flow_out) && al8(b->target_out) &&
+  bool pair = (hot || lean) && p->kernel_variant != 1 && long_enough && (p->N % 2 == 0) && al8(b->timestamp_out) &&
+              al8(b->u_in_out) && al8(b->u_out_out) && al8(b->pressure_out) && al8(b->flow_out) && al8(b->target_out) &&
               al8(b->steps_io) && al8(b->time_io) && al8(b->volume_io) && al8(b->pressure_io) && al8(b->target_io) &&
               al8(b->obs_pressure_io) && al8(b->obs_time_io) && al8(b->pid_p_io) && al8(b->pid_i_io) &&
               al8(b->pid_d_io) && al8(b->pid_time_io) && al8(b->pid_dt_io) && al8(b->pid_steps_io) &&
@@ -657,7 +664,8 @@ extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLun
               (!b->status_out || al8(b->status_out)) && (p->sim != DLC_SIM_DELAY || al8(b->pipe_pressure_io));
   const unsigned grid2 = (unsigned)((p->N / 2 + 127) / 128);
   if (pair && p->sim == DLC_SIM_BALLOON) {
-    lung_pid_pair_kernel<DLC_SIM_BALLOON><<<grid2, 128, 0, st>>>(a);
+    if (lean) lung_pid_pair_kernel<DLC_SIM_BALLOON, true><<<grid2, 128, 0, st>>>(a);
+    else lung_pid_pair_kernel<DLC_SIM_BALLOON, false><<<grid2, 128, 0, st>>>(a);
     return cuda_status(cudaGetLastError(), "lung_pid_pair_kernel launch");
   }
   if (pair) {
@@ -665,37 +673,45 @@ extern "C" int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLun
     static std::once_flag once2;
     static cudaError_t rc2;
     std::call_once(once2, [] {
-      rc2 = cudaFuncSetAttribute(lung_pid_pair_kernel<DLC_SIM_DELAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      rc2 = cudaFuncSetAttribute(lung_pid_pair_kernel<DLC_SIM_DELAY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  2 * DLC_MAX_DELAY * 257 * 4);
+      if (rc2 == cudaSuccess)
+        rc2 = cudaFuncSetAttribute(lung_pid_pair_kernel<DLC_SIM_DELAY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   2 * DLC_MAX_DELAY * 257 * 4);
     });
     if (rc2 != cudaSuccess) return cuda_status(rc2, "lung_pid_pair_kernel shared-memory attribute");
-    lung_pid_pair_kernel<DLC_SIM_DELAY><<<grid2, 128, smem2, st>>>(a);
+    if (lean) lung_pid_pair_kernel<DLC_SIM_DELAY, true><<<grid2, 128, smem2, st>>>(a);
+    else lung_pid_pair_kernel<DLC_SIM_DELAY, false><<<grid2, 128, smem2, st>>>(a);
     return cuda_status(cudaGetLastError(), "lung_pid_pair_kernel launch");
   }
   if (p->sim == DLC_SIM_BALLOON) {
-    if (hot) lung_pid_kernel<DLC_SIM_BALLOON, 7, DLC_LUNG_MODE_CLOSED_LOOP, true><<<grid, 128, 0, st>>>(a);
-    else if (p->nk == 7) lung_pid_kernel<DLC_SIM_BALLOON, 7, -1, false><<<grid, 128, 0, st>>>(a);
-    else lung_pid_kernel<DLC_SIM_BALLOON, 0, -1, false><<<grid, 128, 0, st>>>(a);
+    if (hot) lung_pid_kernel<DLC_SIM_BALLOON, 7, DLC_LUNG_MODE_CLOSED_LOOP, 1><<<grid, 128, 0, st>>>(a);
+    else if (lean) lung_pid_kernel<DLC_SIM_BALLOON, 7, DLC_LUNG_MODE_CLOSED_LOOP, 2><<<grid, 128, 0, st>>>(a);
+    else if (p->nk == 7) lung_pid_kernel<DLC_SIM_BALLOON, 7, -1, 0><<<grid, 128, 0, st>>>(a);
+    else lung_pid_kernel<DLC_SIM_BALLOON, 0, -1, 0><<<grid, 128, 0, st>>>(a);
   } else {
     const size_t smem = 2 * (size_t)p->delay * 129 * sizeof(float);   // 64.5 KB at the maximum delay of 64
     if (smem > 48 * 1024) {
       static std::once_flag once;
-      static cudaError_t attr_rc[3];
+      static cudaError_t attr_rc[4];
       std::call_once(once, [] {
         const int cap = 2 * DLC_MAX_DELAY * 129 * 4;
-        attr_rc[0] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, true>,
+        attr_rc[3] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, 2>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        attr_rc[1] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, -1, false>,
+        attr_rc[0] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, 1>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        attr_rc[2] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 0, -1, false>,
+        attr_rc[1] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 7, -1, 0>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        attr_rc[2] = cudaFuncSetAttribute(lung_pid_kernel<DLC_SIM_DELAY, 0, -1, 0>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
       });
-      for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 4; ++i)
         if (attr_rc[i] != cudaSuccess) return cuda_status(attr_rc[i], "lung_pid_kernel shared-memory attribute");
     }
-    if (hot) lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, true><<<grid, 128, smem, st>>>(a);
-    else if (p->nk == 7) lung_pid_kernel<DLC_SIM_DELAY, 7, -1, false><<<grid, 128, smem, st>>>(a);
-    else lung_pid_kernel<DLC_SIM_DELAY, 0, -1, false><<<grid, 128, smem, st>>>(a);
+    if (hot) lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, 1><<<grid, 128, smem, st>>>(a);
+    else if (lean) lung_pid_kernel<DLC_SIM_DELAY, 7, DLC_LUNG_MODE_CLOSED_LOOP, 2><<<grid, 128, smem, st>>>(a);
+    else if (p->nk == 7) lung_pid_kernel<DLC_SIM_DELAY, 7, -1, 0><<<grid, 128, smem, st>>>(a);
+    else lung_pid_kernel<DLC_SIM_DELAY, 0, -1, 0><<<grid, 128, smem, st>>>(a);
   }
   return cuda_status(cudaGetLastError(), "lung_pid_kernel launch");
 }

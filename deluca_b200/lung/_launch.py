@@ -50,7 +50,7 @@ def launch(env, waveform, N, T, mode, dev, **kw):
 
 def prepare(env, waveform, N, T, mode, dev, *, K=None, env_state=None, obs=None, pid_state=None, exp_state=None,
            actions=None, pid_decay=DEFAULT_DT / (DEFAULT_DT + 0.5), run_dt=DEFAULT_DT, series=True,
-           kernel_variant=0):
+           kernel_variant=0, lean=False):
     """Pack one kernel call.  ``env_state`` / ``obs`` / ``pid_state`` / ``exp_state`` are dicts of
     leaves (scalars or [N] tensors); missing pieces get neutral values.  Returns (params, buffers,
     dict of [T,N] series tensors)."""
@@ -98,7 +98,12 @@ def prepare(env, waveform, N, T, mode, dev, *, K=None, env_state=None, obs=None,
         b["u_out_in"] = torch.as_tensor(u_out, dtype=torch.float32, device=dev).reshape(T, N).contiguous()
     out = {}
     if series:
-        for k in ("timestamp", "u_in", "u_out", "pressure", "flow", "target"):
+        # lean: the two series that are the same for every breath of a batch with a common start time (the timestamp
+        # depends on the step only, flow is the env's static field) are not written per breath -- 16 B per env-step
+        # instead of 24; the caller keeps one column of each (run_controller_scan does)
+        names = ("u_in", "u_out", "pressure", "target") if lean else ("timestamp", "u_in", "u_out", "pressure", "flow",
+                                                                      "target")
+        for k in names:
             out[k] = torch.empty(T, N, device=dev)
             b[k + "_out"] = out[k]
     b["status_out"] = torch.empty(N, dtype=torch.int32, device=dev)

@@ -14,7 +14,7 @@ from ... import _launch
 
 
 def run_controller_scan(controller, T=1000, dt=0.03, abort=60, env=None, waveform=None, use_tqdm=False,
-                        directory=None, init_controller=False, N=None):
+                        directory=None, init_controller=False, N=None, materialize=False):
     if not isinstance(controller, PID):
         raise TypeError("the fused episode kernel drives the lung PID controller; got "
                         f"{type(controller).__name__}")
@@ -27,10 +27,26 @@ def run_controller_scan(controller, T=1000, dt=0.03, abort=60, env=None, wavefor
     n_w = kf_n.shape[0] if kf_n.dim() == 2 else 1
     N = N or max(n_k, n_w)
     env_state, obs = env.reset()                                          # :178
-    b, out = _launch.launch(env, ctrl_wave, N, T, "closed_loop", dev, K=controller.params,
-                            env_state=env.state_dict(env_state),
-                            obs=dict(predicted_pressure=obs.predicted_pressure, time=obs.time),
-                            pid_decay=controller.dt / (controller.dt + controller.RC), run_dt=dt)
+    # Every episode starts from env.reset(), so `timestamp` depends on the step only and `flow` is the env's static
+    # field: for a batch they are computed once (a one-breath launch of the same kernel: bit-identical arithmetic) and
+    # returned as broadcast VIEWS [N,T] instead of being written N times (16 B per env-step instead of 24).
+    # `materialize=True` writes all six series per breath, as round 1 did.
+    lean = N > 1 and not materialize
+    kw = dict(env_state=env.state_dict(env_state), obs=dict(predicted_pressure=obs.predicted_pressure, time=obs.time),
+              pid_decay=controller.dt / (controller.dt + controller.RC), run_dt=dt)
+    b, out = _launch.launch(env, ctrl_wave, N, T, "closed_loop", dev, K=controller.params, lean=lean, **kw)
+    if lean:
+        one_wave = ctrl_wave if ctrl_wave.knots(device="cpu")[1].dim() == 1 else BreathWaveform.create()
+        first = lambda v: v.reshape(-1)[:1] if isinstance(v, torch.Tensor) and v.numel() > 1 else v
+        kw1 = dict(kw, env_state={k: first(v) for k, v in kw["env_state"].items()},
+                   obs={k: first(v) for k, v in kw["obs"].items()})
+        if "in_history" in kw1["env_state"]:      # DelayLung: [N, delay] histories -> the first breath's
+            for k in ("in_history", "out_history"):
+                h = kw["env_state"][k]
+                kw1["env_state"][k] = h.reshape(-1, env.delay)[:1] if isinstance(h, torch.Tensor) else h
+        _, col = _launch.launch(env, one_wave, 1, T, "closed_loop", dev, K=controller.params[:1], **kw1)
+        out["timestamp"] = col["timestamp"].expand(T, N)
+        out["flow"] = col["flow"].expand(T, N)
     single = N == 1
     shape = (lambda s: s[:, 0]) if single else (lambda s: s.T)
     ts = {k: shape(out[k]) for k in ("timestamp", "pressure", "flow", "u_in", "u_out")}

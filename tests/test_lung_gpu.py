@@ -271,3 +271,28 @@ def test_odd_batch_takes_the_one_per_thread_kernel():
     p2, b2, s2 = _launch.prepare(env, None, N - 1, T, "closed_loop", "cuda", **dict(kw, K=K[:-1]))
     fused.lung_rollout(p2, b2)
     assert torch.equal(s["pressure"][:, :-1], s2["pressure"]) and torch.equal(s["u_in"][:, :-1], s2["u_in"])
+
+
+@pytest.mark.parametrize("sim", ["balloon", "delay"])
+@pytest.mark.parametrize("T", [29, 130])
+def test_lean_series_equal_materialised_series(sim, T):
+    """For a batch `run_controller_scan` stores four series per breath and returns `timestamp` / `flow` as broadcast
+    views of one column (they are the same for every breath that starts from `env.reset()`): every value must equal the
+    all-six-series launch bit for bit."""
+    from deluca_b200.lung.controllers import PID
+    from deluca_b200.lung.core import BreathWaveform
+    from deluca_b200.lung.envs import BalloonLung, DelayLung
+    from deluca_b200.lung.utils.scripts.run_controller import run_controller_scan
+    g = torch.Generator().manual_seed(T)
+    N = 514
+    K = 5 * torch.rand(N, 3, generator=g)
+    pip = torch.tensor([10.0, 15, 20, 25, 30, 35])[torch.randint(0, 6, (N,), generator=g)]
+    wave = BreathWaveform.create(pip=pip, peep=5.0)
+    env = (BalloonLung if sim == "balloon" else DelayLung).create()
+    ctrl = PID.create(params=K)
+    a = run_controller_scan(ctrl, T=T, env=env, waveform=wave, init_controller=True)
+    b = run_controller_scan(ctrl, T=T, env=env, waveform=wave, init_controller=True, materialize=True)
+    for k in ("timestamp", "pressure", "flow", "u_in", "u_out", "target"):
+        assert a["timeseries"][k].shape == (N, T)
+        assert torch.equal(a["timeseries"][k], b["timeseries"][k]), k
+    assert a["timeseries"]["timestamp"].stride(0) == 0 and b["timeseries"]["timestamp"].stride(0) != 0

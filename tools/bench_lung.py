@@ -7,9 +7,11 @@
 
 The breaths are independent: each rank takes a contiguous shard (`shard_range`), there is no data-path collective;
 timing is CUDA events around K launches bracketed by a barrier, MAX over ranks.  One JSON line per (simulator, T) from
-rank 0.  Roofline: the kernel only stores -- six float32 series per env-step (24 B) -- plus, once per
-launch, the carried pytree leaves read and written back (`state_bytes_per_env`); `frac` is on the 24 B/step figure,
-`frac_with_state_io` adds the state traffic the functional contract requires.
+rank 0.  Roofline: the kernel only stores -- six float32 series per env-step (24 B), or the four that differ
+between the breaths of a batch (16 B: `timestamp` depends on the step only and `flow` is the env's static field, so
+`run_controller_scan` keeps one column of each) -- plus, once per launch, the carried pytree leaves read and written
+back (`state_bytes_per_env`); `frac` is on the per-step figure, `frac_with_state_io` adds the state traffic the
+functional contract requires.
 """
 import argparse
 import json
@@ -54,11 +56,12 @@ pip = torch.tensor([10.0, 15, 20, 25, 30, 35])[torch.randint(0, 6, (n,), generat
 wave = BreathWaveform.create(pip=pip, peep=5.0)
 flush = torch.empty(64 << 20, device=dev)                       # 256 MB > L2: written between timed launches
 for name, Env in (("balloon", BalloonLung), ("delay", DelayLung)):
+  for lean in (True, False):     # four series per breath (what run_controller_scan stores for a batch) / all six
     for T in (29, 1000):
         env = Env.create(device=str(dev))
         st, obs = env.reset()
         p, b, series = _launch.prepare(env, wave, n, T, "closed_loop", dev, K=K, env_state=env.state_dict(st),
-                                       obs=dict(predicted_pressure=obs.predicted_pressure, time=obs.time))
+                                       obs=dict(predicted_pressure=obs.predicted_pressure, time=obs.time), lean=lean)
         for _ in range(args.warmup):
             fused.lung_rollout(p, b)
         torch.cuda.synchronize()
@@ -80,15 +83,17 @@ for name, Env in (("balloon", BalloonLung), ("delay", DelayLung)):
         state = 12 + 28 + 13 * 4 + (15 + 2 * 2 + 1) * 4
         if name == "delay":     # + pipe_pressure (rw) and the two [delay] histories (written; read only if T < delay)
             state += 8 + 2 * 4 * env.delay * (1 if T >= env.delay else 2)
-        series_b = 24.0 * n * T
+        per_step = 16 if lean else 24
+        series_b = float(per_step) * n * T
         ach = series_b / (ms * 1e-3) / 1e9
         if rank == 0:
             print(json.dumps({
-                "metric": "env_steps_per_s", "workload": f"{name} lung + PID, {total} breaths x T={T}",
+                "metric": "env_steps_per_s", "workload": f"{name} lung + PID, {total} breaths x T={T}, "
+                                                         f"{'four' if lean else 'six'} series stored per breath",
                 "value": total * T / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "scaling": args.scaling,
                 "ms_per_step": ms, "steps": args.steps, "warmup": args.warmup, "l2": "256 MB flush between launches",
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": HBM, "unit": "GB/s", "frac": ach / HBM,
-                             "bytes_per_env_step": 24, "state_bytes_per_env": state,
+                             "bytes_per_env_step": per_step, "state_bytes_per_env": state,
                              "frac_with_state_io": (series_b + state * n) / (ms * 1e-3) / 1e9 / HBM}}))
         del p, b, series
         torch.cuda.empty_cache()

@@ -94,7 +94,14 @@ def _classic_rollout(env, env_start_states, agent, agent_start_states, T, loss_f
         per_env = max(kp.dim(), ki.dim(), kd.dim()) > 0
         gains = torch.stack([g.reshape(-1).expand(N) if per_env else g for g in (kp, ki, kd)], -1).contiguous()
         s = agent_start_states
-        ps = [tens(v).reshape(-1, 1 if tens(v).dim() < 2 else d).expand(N, d) for v in (s.P, s.I, s.D)]
+        def leaf(v):    # scalar (the reference's PIDState default 0.0), [d] (one episode) or [N,d]
+            t = tens(v)
+            if t.numel() == 1:
+                return t.reshape(1, 1).expand(N, d)
+            if t.numel() == d:
+                return t.reshape(1, d).expand(N, d)
+            return t.reshape(N, d)
+        ps = [leaf(v) for v in (s.P, s.I, s.D)]
         stride = 1 if state_stride is None else int(state_stride)
         r = fused.env_agent_rollout(env, cost, "pid", gains, x, T, pid_state=ps, pid_decay=agent.decay,
                                     state_stride=stride, want_grad=want_grad)

@@ -49,7 +49,8 @@ def test_pendulum_pid_apg_matches_reference_files():
         _close(getattr(ro.agent_states, k), g[f"out_apg_{k}"], what=f"agent_states.{k}")
     assert final.h == T and final.arr.shape == (N, 3)
     _close(apg_loss(agent, env, st, arr0, ast, T, loss), g["out_apg_mean_loss"], what="apg_loss")
-    one = apg_rollout(env, PendulumState(arr=arr0[0], h=0), arr0[0], agent, PIDState(P=0.0, I=0.0, D=0.0), T, loss)[0]
+    one = apg_rollout(env, PendulumState(arr=arr0[0], h=0), arr0[0], agent,
+                      PIDState(P=torch.zeros(3), I=0.0, D=torch.zeros(3, device="cuda")), T, loss)[0]
     _close(one.losses[0], g["out_apg_single_losses"], what="apg_rollout")
     val, grad = value_and_grad_apg_loss(agent, env, st, arr0, ast, T, loss)
     _close(val, g["out_apg_value"], what="value")

@@ -215,3 +215,23 @@ def test_apg_lung_pid_through_driver(sim):
     assert ro.losses.shape == (3, T) and ro.actions.shape == (3, T, 2)
     assert torch.equal(ro.losses, (ts["target"] - ts["pressure"]).abs())
     assert torch.equal(ro.actions[..., 0], ts["u_in"]) and torch.equal(ro.actions[..., 1], ts["u_out"])
+
+
+def test_env_agent_empty_and_zero_length_rollouts():
+    """N = 0 launches nothing and returns empty stacks; T = 0 returns the start state untouched."""
+    from deluca_b200 import fused
+    from deluca_b200.envs.classic import Pendulum
+    from deluca_b200.envs.classic._pendulum import QuadCost
+    env = Pendulum.create()
+    cost = QuadCost([0.0, -1.0, 0.0], 1.0, 0.1)
+    g = torch.tensor([0.5, 0.1, 0.0], device="cuda")
+    r = fused.env_agent_rollout(env, cost, "pid", g, torch.zeros(0, 3, device="cuda"), 7)
+    assert r.losses.shape == (7, 0) and r.x.shape == (0, 3)
+    x0 = torch.tensor([[0.0, 1.0, 0.0], [0.6, 0.8, 0.1]], device="cuda")
+    r = fused.env_agent_rollout(env, cost, "pid", g, x0, 0, want_grad=True)
+    assert torch.equal(r.x, x0) and r.losses.shape == (0, 2) and float(r.loss_sum.abs().sum()) == 0.0
+    assert float(r.grad.abs().sum()) == 0.0 and int(r.status.sum()) == 0
+    with pytest.raises(ValueError):
+        fused.env_agent_rollout(env, cost, "pid", torch.zeros(2, device="cuda"), x0, 3)       # wrong gains shape
+    with pytest.raises(TypeError):
+        fused.env_agent_rollout(env, cost, "pid", g.cpu(), x0, 3)                              # no CPU path

@@ -8,7 +8,10 @@
 // the state stay in the group's slice of shared memory for all T steps, lanes split the rows of each mat-vec; for the
 // colab's system (d_hidden = 10, d_action = 3, d_obs = 2) a thread per env with everything in registers.
 // Streams: disturbances are Philox stream 0 (the same numbers the controller kernels draw), actions stream 3.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "row_ring.cuh"
 
 namespace dlc {
 namespace {
@@ -128,10 +131,17 @@ __global__ void __launch_bounds__(256) lds_open_kernel(const OpenArgs a) {
 // d = 10, n = 3, p = 2), a step is 150 FFMA with no shared memory and no warp synchronisation, and the next step's
 // action / disturbance are fetched while the current one computes.  The lane-group kernel above spends its time in
 // shared-memory mat-vecs and __syncwarp; this one is bound by HBM when the inputs come from memory.
-template <int D, int NA, int P>
+// RS > 0: given actions and disturbances arrive through per-warp cp.async rings RS steps deep (row_ring.cuh) instead of
+// the two register buffers; the kernel is issue-bound at 8 warps per SM, so the per-step index arithmetic is replaced by
+// running pointers as well.
+template <int D, int NA, int P, int RS>
 __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
-  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= a.N) return;
+  const int64_t nt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t nw0 = nt - lane;                       // first env of this warp
+  if (nw0 >= a.N) return;                              // (warp-uniform)
+  const bool live = nt < a.N;                          // idle lanes of the last warp shadow its last env, store nothing
+  const int64_t env = live ? nt : a.N - 1;
   const size_t eD = a.shared ? 0 : (size_t)env;
   float A[D][D], B[D][NA], C[P][D], x[D];
 #pragma unroll
@@ -198,12 +208,17 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
       for (int i = 0; i < D; ++i) w[i] = 0.f;
     }
   };
-  if (a.observe0 && a.y_out) observe(a.y_out + (size_t)env * P);
+  if (a.observe0 && a.y_out && live) observe(a.y_out + (size_t)env * P);
+  const bool store_u = a.u_out != nullptr && live, store_y = a.y_out != nullptr && live;
+  float* yo = a.y_out + ((size_t)a.observe0 * a.N + env) * P;   // running output pointers (not dereferenced when absent)
+  float* uo = a.u_out + (size_t)env * NA;
+  const int64_t y_step = a.N * P, u_step = a.N * NA;
   // one step of the env given its action and disturbance
-  auto advance = [&](int t, const float (&u)[NA], const float (&w)[D]) {
-    if (a.u_out)
+  auto advance = [&](const float (&u)[NA], const float (&w)[D]) {
+    if (store_u)
 #pragma unroll
-      for (int c = 0; c < NA; ++c) a.u_out[((size_t)t * a.N + env) * NA + c] = u[c];
+      for (int c = 0; c < NA; ++c) uo[c] = u[c];
+    uo += u_step;
     float xn[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {   // same accumulation order as the lane-group kernel: A x, then B u, then + w
@@ -216,10 +231,9 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
     }
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = xn[i];
-    if (a.y_out) {
+    if (store_y) {
       float yv[P];
       observe(yv);
-      float* yo = a.y_out + ((size_t)(t + a.observe0) * a.N + env) * P;
       if (P == 2) {
         *reinterpret_cast<float2*>(yo) = make_float2(yv[0], yv[P - 1]);
       } else {
@@ -227,7 +241,62 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
         for (int q = 0; q < P; ++q) yo[q] = yv[q];
       }
     }
+    yo += y_step;
   };
+  if constexpr (RS > 0) {
+    // both input streams through the warp's rings (one commit group per step holds the step's two tiles); the step
+    // loop is unrolled by 4 so that stage offsets are compile-time constants within a group
+    static_assert(RS % 4 == 0, "the step loop is unrolled by 4");
+    using RingW = WarpRowRing<D, RS>;
+    using RingU = WarpRowRing<NA, RS>;
+    extern __shared__ __align__(16) unsigned char ring_smem[];
+    unsigned char* ws = ring_smem + (size_t)(threadIdx.x >> 5) * (RingW::kBytesPerWarp + RingU::kBytesPerWarp);
+    const int64_t left = a.N - nw0;
+    const int nvalid = (int)(left < 32 ? left : 32), rl = live ? lane : 0;
+    RingW rw;
+    RingU ru;
+    rw.init(ws, a.W + nw0 * D, a.N * D, nvalid, lane, rl);
+    ru.init(ws + RingW::kBytesPerWarp, a.u_in + nw0 * NA, a.N * NA, nvalid, lane, rl);
+#pragma unroll 1
+    for (int s = 0; s < RS; ++s) {
+      rw.fill(s, s < a.T);
+      ru.fill(s, s < a.T);
+      RingW::commit();
+    }
+    for (int tb = 0; tb < a.T; tb += 4) {
+      const int sb = tb & (RS - 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (tb + k < a.T) {
+          RingW::wait();
+          const uint32_t wrow = rw.row_addr(sb + k), urow = ru.row_addr(sb + k);
+          float u[NA], w[D];
+          if (D % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < D / 2; ++i) {
+              const float2 v = lds_f2(wrow + 8u * i);
+              w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) w[i] = lds_f1(wrow + 4u * i);
+          }
+#pragma unroll
+          for (int c = 0; c < NA; ++c) u[c] = lds_f1(urow + 4u * c);
+          __syncwarp();
+          const bool more = tb + k + RS < a.T;
+          rw.fill(sb + k, more);
+          ru.fill(sb + k, more);
+          RingW::commit();
+          advance(u, w);
+        }
+      }
+    }
+    if (live)
+#pragma unroll
+      for (int i = 0; i < D; ++i) a.x_io[(size_t)env * D + i] = x[i];
+    return;
+  }
   // inputs are fetched TWO steps ahead (two register buffers, the loop advances two steps per trip): with 8 warps per
   // SM one step's 52 bytes per thread in flight is well short of what the HBM latency needs
   float u0[NA], w0[D], u1[NA], w1[D];
@@ -241,7 +310,7 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
 #pragma unroll
       for (int i = 0; i < D; ++i) w[i] = w0[i];
       if (t + 2 < a.T) fetch(t + 2, u0, w0);
-      advance(t, u, w);
+      advance(u, w);
     }
     if (t + 1 < a.T) {
       float u[NA], w[D];
@@ -250,11 +319,12 @@ __global__ void __launch_bounds__(128) lds_open_reg_kernel(const OpenArgs a) {
 #pragma unroll
       for (int i = 0; i < D; ++i) w[i] = w1[i];
       if (t + 3 < a.T) fetch(t + 3, u1, w1);
-      advance(t + 1, u, w);
+      advance(u, w);
     }
   }
+  if (live)
 #pragma unroll
-  for (int i = 0; i < D; ++i) a.x_io[(size_t)env * D + i] = x[i];
+    for (int i = 0; i < D; ++i) a.x_io[(size_t)env * D + i] = x[i];
 }
 
 // SinusDisturbance.__call__ (deluca/envs/_lds.py:44-52): w_t[i] = sin(t * phases[i]) * amplitude, the same for every env
@@ -304,7 +374,15 @@ extern "C" int32_t dlc_lds_open_rollout_f32(int64_t N, int32_t T, int32_t d, int
   a.A = A; a.B = B; a.C = C; a.u_in = u_in; a.W = W; a.x_io = x_io; a.y_out = y_out; a.u_out = u_out;
   a.seed = seed; a.w_std = w_std; a.action_std = action_std;
   if (d == 10 && n == 3 && p == 2) {   // the colab's system: register-resident thread-per-env kernel
-    lds_open_reg_kernel<10, 3, 2><<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    const char* renv = getenv("DLC_ROW_RING");   // profiling switch: 0 = the register double buffers
+    if ((!renv || atoi(renv) > 0) && T > 2 && WarpRowRing<10, 4>::usable(W, N) && WarpRowRing<3, 4>::usable(u_in, N)) {
+      auto kern = lds_open_reg_kernel<10, 3, 2, 4>;
+      const size_t smem = 4 * (WarpRowRing<10, 4>::kBytesPerWarp + WarpRowRing<3, 4>::kBytesPerWarp);
+      kern<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+      return cuda_status(cudaGetLastError(), "lds_open_reg_kernel (row rings) launch");
+    }
+    lds_open_reg_kernel<10, 3, 2, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "lds_open_reg_kernel launch");
   }
   int widest = d > n ? d : n;

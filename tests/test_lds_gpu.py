@@ -135,6 +135,27 @@ def test_lqr_register_kernel_against_lane_split_and_resume():
         assert torch.equal(torch.cat([r1.costs, r2.costs]), a.costs) and torch.equal(r2.x, a.x)
 
 
+def test_lqr_row_ring_equals_register_buffers(monkeypatch):
+    """The cp.async disturbance ring (row_ring.cuh: 4, 8 or 16 stages per warp) against the register double buffer
+    (DLC_ROW_RING=0): same bits, for horizons shorter and longer than the ring, a ragged last warp (N = 130: a 2-env
+    tile), an odd N (rows not 16-byte tileable: falls back), and against the float64 oracle."""
+    from deluca_b200.fused import lds_rollout
+    d, m = 10, 3
+    for N, T in ((130, 1), (130, 3), (130, 16), (130, 17), (130, 75), (4096 + 62, 40), (129, 20)):
+        A, B, K, x0, W = _problem(N, d, m, T, seed=21, dense=True)
+        args = tuple(map(_dev, (A, B, K, x0)))
+        out = {}
+        for ring in ("0", "4", "8", "16"):
+            monkeypatch.setenv("DLC_ROW_RING", ring)
+            out[ring] = lds_rollout(*args, T, policy="lqr", W=_dev(W), traj_stride=7)
+        monkeypatch.delenv("DLC_ROW_RING")
+        for ring in ("4", "8", "16"):
+            for f in ("costs", "x", "X", "U", "cost_sum", "status"):
+                assert torch.equal(getattr(out[ring], f), getattr(out["0"], f)), (N, T, ring, f)
+        if N == 130 and T == 75:
+            _check(out["16"], O.rollout_lds(A, B, K, x0, W, "lqr", dtype=np.float64), T)
+
+
 def test_resume_is_identical_and_inputs_untouched():
     from deluca_b200.fused import lds_rollout
     N, T, d, m = 64, 90, 10, 3

@@ -54,6 +54,27 @@ def test_given_actions_match_oracle(d, n, p, shared):
     assert torch.equal(u, _dev(U))
 
 
+def test_row_rings_equal_register_buffers(monkeypatch):
+    """Register-resident kernel (d, n, p) = (10, 3, 2) with given actions and disturbances: the cp.async rings
+    (row_ring.cuh; taken when N % 4 == 0) against the register double buffers (DLC_ROW_RING=0), bit for bit, for
+    horizons around the ring depth and a ragged last warp; and against the oracle."""
+    from deluca_b200.fused import lds_open_rollout
+    d, n, p = 10, 3, 2
+    for N, T in ((132, 1), (132, 3), (132, 4), (132, 5), (132, 61), (4096 + 8, 33)):
+        A, B, C, x0, U, W = _sys(N, d, n, p, T, seed=N + T, shared=N > 1000)
+        args = (_dev(A), _dev(B), _dev(C), _dev(x0), T)
+        kw = dict(u_in=_dev(U), W=_dev(W), observe0=True, keep_actions=True)
+        monkeypatch.setenv("DLC_ROW_RING", "0")
+        x0_, y0_, u0_ = lds_open_rollout(*args, **kw)
+        monkeypatch.delenv("DLC_ROW_RING")
+        x1_, y1_, u1_ = lds_open_rollout(*args, **kw)
+        assert torch.equal(x0_, x1_) and torch.equal(y0_, y1_) and torch.equal(u0_, u1_), (N, T)
+        if T == 61:
+            Y, xf = O.open_rollout(A, B, C, x0, U, W)
+            _close(y1_[1:].cpu().numpy(), Y)
+            _close(x1_.cpu().numpy(), xf)
+
+
 def test_random_policy_streams_and_resume():
     from deluca_b200.fused import gaussian_disturbance, lds_open_rollout
     N, T, d, n, p = 70, 64, 10, 3, 2

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "f2.cuh"
+#include "row_ring.cuh"
 
 namespace dlc {
 namespace {
@@ -835,12 +836,19 @@ of_kernel(const OfArgs a) {
 // LQG on a small compile-time system, one THREAD per env with A, B, C, K, L and both states in registers
 // (200 + 20 floats at d = 10, n = 3, p = 2): a step is 355 FFMA with no shared memory and no warp synchronisation.
 // Same arithmetic per element as of_kernel<LQG> (row sums accumulated in the same order).
-template <int D, int NA, int P>
+// RS > 0 (closed loop, W from HBM, 16-byte tileable rows): the disturbance rows arrive through the warp's cp.async ring
+// (row_ring.cuh) RS steps ahead; outputs go through running pointers either way (the kernel is issue-bound at 8 warps
+// per SM: every per-step index computation is paid in FFMA slots).
+template <int D, int NA, int P, int RS>
 __global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
   const DlcOfParams& Pm = a.p;
-  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= Pm.N) return;
-  const bool closed = Pm.mode == DLC_MODE_CLOSED_LOOP;
+  const int64_t nt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t nw0 = nt - lane;                       // first env of this warp
+  if (nw0 >= Pm.N) return;                             // (warp-uniform)
+  const bool live = nt < Pm.N;                         // idle lanes of the last warp shadow its last env, store nothing
+  const int64_t env = live ? nt : Pm.N - 1;
+  const bool closed = RS > 0 || Pm.mode == DLC_MODE_CLOSED_LOOP;
   const size_t eD = Pm.shared_dynamics ? 0 : (size_t)env;
   float A[D][D], B[D][NA], C[P][D], K[NA][D], L[D][P], x[D], z[D];
 #pragma unroll
@@ -865,33 +873,34 @@ __global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
   const uint32_t genv = (uint32_t)(Pm.env_offset + env);
   double csum = 0.0;
   int status = 0;
-  for (int t = 0; t < Pm.T; ++t) {
-    // disturbance of this step, fetched early
-    float w[D];
-    if (closed) {
-      if (a.W) {
-        const float* wr = a.W + ((size_t)t * Pm.N + env) * D;
-        if (D % 2 == 0) {   // rows of an even d start on 8-byte boundaries: half the load instructions
+  const bool store_cost = a.cost_out != nullptr && live, store_u = a.u_out != nullptr && live;
+  float* cost_p = a.cost_out + env;                    // running pointer (not dereferenced when absent)
+  // disturbance of step t from HBM (register path) or the generator
+  auto fetch = [&](int t, float (&w)[D]) {
+    if (a.W) {
+      const float* wr = a.W + ((size_t)t * Pm.N + env) * D;
+      if (D % 2 == 0) {   // rows of an even d start on 8-byte boundaries: half the load instructions
 #pragma unroll
-          for (int i = 0; i < D / 2; ++i) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(wr) + i);
-            w[2 * i] = v.x; w[2 * i + 1] = v.y;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < D; ++i) w[i] = __ldg(wr + i);
+        for (int i = 0; i < D / 2; ++i) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(wr) + i);
+          w[2 * i] = v.x; w[2 * i + 1] = v.y;
         }
       } else {
 #pragma unroll
-        for (int g = 0; g < (D + 3) / 4; ++g) {
-          float z4[4];
-          normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
+        for (int i = 0; i < D; ++i) w[i] = __ldg(wr + i);
+      }
+    } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
-        }
+      for (int g = 0; g < (D + 3) / 4; ++g) {
+        float z4[4];
+        normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
       }
     }
+  };
+  auto advance = [&](int t, const float (&w)[D]) {
     // y = C x (_lds.py:110), or the caller's observation
     float y[P], u[NA], res[P];
 #pragma unroll
@@ -940,10 +949,15 @@ __global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
     for (int q = 0; q < P; ++q) c = fmaf(y[q], y[q], c);
 #pragma unroll
     for (int k = 0; k < NA; ++k) c = fmaf(u[k], u[k], c);
-    if (a.cost_out) a.cost_out[(size_t)t * Pm.N + env] = c;
+    if constexpr (RS > 0) {
+      if (store_cost) *cost_p = c;
+      cost_p += Pm.N;
+    } else {   // (the register path has no room for the pointer: it would spill)
+      if (store_cost) a.cost_out[(size_t)t * Pm.N + env] = c;
+    }
     csum += (double)c;
     if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
-    if (a.u_out)
+    if (store_u)
 #pragma unroll
       for (int k = 0; k < NA; ++k) a.u_out[((size_t)t * Pm.N + env) * NA + k] = u[k];
     // env step x <- A x + B u + w    (_lds.py:107-109)
@@ -961,7 +975,46 @@ __global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
 #pragma unroll
       for (int i = 0; i < D; ++i) x[i] = xn[i];
     }
+  };
+  if constexpr (RS > 0) {
+    static_assert(RS % 4 == 0, "the step loop is unrolled by 4");
+    using Ring = WarpRowRing<D, RS>;
+    extern __shared__ __align__(16) unsigned char ring_smem[];
+    Ring ring;
+    const int64_t left = Pm.N - nw0;
+    ring.init(ring_smem + (size_t)(threadIdx.x >> 5) * Ring::kBytesPerWarp, a.W + nw0 * D, Pm.N * D,
+              (int)(left < 32 ? left : 32), lane, live ? lane : 0);
+    ring.prime(Pm.T);
+    for (int tb = 0; tb < Pm.T; tb += 4) {
+      const int sb = tb & (RS - 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (tb + k < Pm.T) {
+          const uint32_t row = ring.acquire(sb + k);
+          float w[D];
+          if (D % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < D / 2; ++i) {
+              const float2 v = lds_f2(row + 8u * i);
+              w[2 * i] = v.x; w[2 * i + 1] = v.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) w[i] = lds_f1(row + 4u * i);
+          }
+          ring.release(sb + k, tb + k + RS < Pm.T);
+          advance(tb + k, w);
+        }
+      }
+    }
+  } else {
+    for (int t = 0; t < Pm.T; ++t) {
+      float w[D];
+      if (closed) fetch(t, w);   // fetched early
+      advance(t, w);
+    }
   }
+  if (!live) return;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     if (closed) a.x_io[(size_t)env * D + i] = x[i];
@@ -1351,7 +1404,13 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
   if (p->agent == DLC_OF_LQG && p->d == 10 && p->n == 3 && p->p == 2 && p->lanes_per_env == 0) {
     // the colab's system: register-resident thread-per-env kernel (lanes_per_env = 8 / 16 / 32 still forces lane groups;
     // the identity-filter flag means nothing to LQG and is ignored)
-    of_lqg_reg_kernel<10, 3, 2><<<(unsigned)((p->N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    const unsigned grid = (unsigned)((p->N + 127) / 128);
+    const char* renv = getenv("DLC_ROW_RING");   // profiling switch: 0 = disturbance rows through registers
+    if ((!renv || atoi(renv) > 0) && p->mode == DLC_MODE_CLOSED_LOOP && p->T > 2 && WarpRowRing<10, 4>::usable(W, p->N)) {
+      of_lqg_reg_kernel<10, 3, 2, 4><<<grid, 128, 4 * WarpRowRing<10, 4>::kBytesPerWarp, (cudaStream_t)stream>>>(a);
+      return cuda_status(cudaGetLastError(), "of_lqg_reg_kernel (row ring) launch");
+    }
+    of_lqg_reg_kernel<10, 3, 2, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "of_lqg_reg_kernel launch");
   }
   if (p->agent == DLC_OF_FGRC && p->d == 10 && p->n == 3 && p->p == 2 && p->m == 10 && p->F == 10 && p->L == 10 &&

@@ -133,6 +133,30 @@ def test_lqg_matches_oracle(d, n, p, shared):
                                atol=1e-4 * np.abs(ref["state"]["x_hat"]).max())
 
 
+def test_lqg_row_ring_equals_register_path(monkeypatch):
+    """Register-resident LQG kernel (d, n, p) = (10, 3, 2): disturbance rows through the cp.async ring (row_ring.cuh;
+    taken when N is even) against the register path (DLC_ROW_RING=0), bit for bit, around the ring depth and with a
+    ragged last warp; the ring run against the float64 oracle."""
+    from deluca_b200.fused import lds_of_rollout
+    d, n, p = 10, 3, 2
+    for N, T in ((130, 1), (130, 3), (130, 4), (130, 5), (130, 90), (2048 + 34, 21)):
+        A, B, C, x0, W, rng = _sys(N, d, n, p, T, seed=N + T)
+        K = (0.1 * rng.standard_normal((N, n, d))).astype(np.float32)
+        Lk = (0.1 * rng.standard_normal((N, d, p))).astype(np.float32)
+        if T == 90:
+            for i in range(N):
+                K[i], Lk[i] = O.lqg_gains(A[i].astype(np.float64), B[i].astype(np.float64), C[i].astype(np.float64))
+        run = lambda: lds_of_rollout(_dev(A), _dev(B), _dev(C), _dev(x0), T, agent="lqg", W=_dev(W), K=_dev(K), Lk=_dev(Lk))
+        monkeypatch.setenv("DLC_ROW_RING", "0")
+        a = run()
+        monkeypatch.delenv("DLC_ROW_RING")
+        b = run()
+        for f in ("costs", "U", "x", "z", "cost_sum", "status"):
+            assert torch.equal(getattr(a, f), getattr(b, f)), (N, T, f)
+        if T == 90:
+            _check(b, O.rollout_of(A, B, C, x0, W, "lqg", dtype=np.float64, K=K, Lk=Lk))
+
+
 def test_resume_equals_uninterrupted_and_in_kernel_disturbances():
     from deluca_b200.fused import gaussian_disturbance, lds_of_rollout
     N, T, d, n, p, m, h = 45, 120, 10, 3, 2, 10, 4

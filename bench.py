@@ -246,6 +246,7 @@ class Runner:
                        env_offset=lo, w_std=W_STD, kernel_variant=variant)
         self.stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self.flush = None
+        self.e2e_mode = "env_slices"
 
     def sync(self):
         if self.world > 1:
@@ -301,7 +302,7 @@ class Runner:
         with disturbances drawn by the env itself (in-kernel Philox; the reference's env draws its own noise too,
         _lds.py:102-105), and the result device -> host: the full losses[T,N] (what Rollout.losses holds,
         training/apg.py:68) or the per-env cost sums only."""
-        from deluca_b200.fused import lds_rollout, lds_rollout_to_host
+        from deluca_b200.fused import lds_rollout, lds_rollout_host_to_host, lds_rollout_to_host
         torch = self.torch
         hA, hB, hK, hx = (t.cpu().pin_memory() for t in (self.A, self.B, self.K, self.x0))
         T = self.wl["T"]
@@ -309,6 +310,15 @@ class Runner:
                  else torch.empty(self.n, dtype=torch.float64)).pin_memory()
 
         def one():
+            if return_losses and self.e2e_mode == "env_slices":
+                # env slices: uploads, rollouts and the losses' downloads of different slices overlap (public API)
+                rr = lds_rollout_host_to_host(hA, hB, hK, hx, T, h_out, device=self.dev, slices=16, **self.kw)
+                torch.cuda.current_stream(self.dev).wait_event(rr.done)
+                return
+            if self.e2e_mode == "env_slices":
+                rr = lds_rollout_host_to_host(hA, hB, hK, hx, T, None, device=self.dev, slices=16, **self.kw)
+                h_out.copy_(rr.cost_sum, non_blocking=True)
+                return
             dA, dB, dK, dx = (t.to(self.dev, non_blocking=True) for t in (hA, hB, hK, hx))
             if return_losses:   # losses[T,N] stream to the host chunk by chunk under the rollout (public API)
                 rr = lds_rollout_to_host(dA, dB, dK, dx, T, h_out, chunks=8, donate=True, **self.kw)
@@ -351,6 +361,8 @@ def main():
     ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] sub-record")
     ap.add_argument("--no-e2e-losses", action="store_true", help="skip the e2e leg that returns losses[T,N]")
     ap.add_argument("--variant", type=int, default=0, help="DlcLdsParams.kernel_variant (0 = auto)")
+    ap.add_argument("--e2e-mode", default="env_slices", choices=["env_slices", "time_chunks"],
+                    help="how the e2e leg overlaps its copies: 16 env slices (uploads too) or 8 horizon chunks")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
@@ -388,6 +400,7 @@ def main():
     if rank == 0:
         sampler.start()
     run = Runner(torch, dist, wl, dev, rank, world, scaling, use_hbm_w, args.variant)
+    run.e2e_mode = args.e2e_mode
     n_loc, n_tot = run.n, run.n_total
 
     # ---- timed region: K steps of the headline variant
@@ -462,10 +475,13 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}},
             "e2e": {"value": n_tot * T / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "result_checksum": chk,
+                    "overlap": args.e2e_mode,
                     "note": "per step: host A,B,K,x0 (pinned) -> device; fused rollout, disturbances drawn by the env "
                             "in the kernel (the reference's LDS draws its own noise too); the full losses[T,N] "
-                            "(Rollout.losses) -> pinned host.  `value` differs only in reading the same disturbance "
-                            "stream from HBM; `value_kernel_rng` is this leg's kernel variant timed on the device."
+                            "(Rollout.losses) -> pinned host; the batch is cut into 16 env slices whose uploads, "
+                            "rollouts and downloads overlap (fused.lds_rollout_host_to_host).  `value` differs only in "
+                            "reading the same disturbance stream from HBM; `value_kernel_rng` is this leg's kernel "
+                            "variant timed on the device."
                             if not args.no_e2e_losses else "cost sums only (--no-e2e-losses)"},
             "e2e_cost_sums_only": {"value": n_tot * T / (e2e_sum_ms * 1e-3), "unit": "env-steps/s",
                                    "h2d_bytes_per_step": h2d_s, "d2h_bytes_per_step": d2h_s, "ms_per_step": e2e_sum_ms,

@@ -169,6 +169,8 @@ SYMBOLS = {
     "dlc_env_collect_f32": (ctypes.c_int32, [ctypes.POINTER(DlcEnvSpec), ctypes.c_int64, ctypes.c_int32,
                                              ctypes.c_uint64, ctypes.c_int64, ctypes.c_float, _P, _P, _P, _P, _P]),
     "dlc_microbench_f32": (ctypes.c_int32, [ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P]),
+    "dlc_copy_rows_async": (ctypes.c_int32, [_P, ctypes.c_size_t, _P, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+                                             ctypes.c_int32, _P]),
     "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
     "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 18
                             + [_P, ctypes.c_size_t, _P]),

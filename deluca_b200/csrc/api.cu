@@ -34,3 +34,16 @@ extern "C" size_t dlc_sizeof(int32_t which) {
     default: return 0;
   }
 }
+
+extern "C" int32_t dlc_copy_rows_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes,
+                                       size_t row_bytes, size_t rows, int32_t kind, void* stream) {
+  if (kind < 1 || kind > 3) return dlc::fail(DLC_ERR_ARG, "dlc_copy_rows_async: kind must be 1 (H2D), 2 (D2H) or 3 (D2D)");
+  if (row_bytes == 0 || rows == 0) return DLC_OK;
+  if (!dst || !src) return dlc::fail(DLC_ERR_ARG, "dlc_copy_rows_async: NULL buffer");
+  if (dst_pitch_bytes < row_bytes || src_pitch_bytes < row_bytes)
+    return dlc::fail(DLC_ERR_ARG, "dlc_copy_rows_async: a pitch is smaller than the row");
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  return dlc::cuda_status(cudaMemcpy2DAsync(dst, dst_pitch_bytes, src, src_pitch_bytes, row_bytes, rows, k,
+                                            (cudaStream_t)stream),
+                          "cudaMemcpy2DAsync");
+}

@@ -200,6 +200,110 @@ def lds_rollout_to_host(A, B, K, x, T, host_costs, *, chunks=8, W=None, t0=0, en
     return out
 
 
+_SLICE_STREAMS = {}
+
+
+def _slice_streams(dev):
+    dev = torch.device(dev)
+    if dev not in _SLICE_STREAMS:
+        _SLICE_STREAMS[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev),
+                               (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)))
+    return _SLICE_STREAMS[dev]
+
+
+def copy_rows_async(dst, src, stream=None):
+    """``dlc_copy_rows_async``: dst[r, :] = src[r, :] for 2-D tensors whose rows are contiguous (row pitches free), host
+    or device on either side, as ONE asynchronous 2-D copy on ``stream`` (default: the current stream)."""
+    if dst.dim() != 2 or src.dim() != 2 or dst.shape != src.shape or dst.dtype != src.dtype:
+        raise ValueError("copy_rows_async needs two 2-D tensors of one shape and dtype")
+    if dst.stride(1) != 1 or src.stride(1) != 1:
+        raise ValueError("copy_rows_async: rows must be contiguous")
+    for t in (dst, src):
+        if not t.is_cuda and not t.is_pinned():
+            raise TypeError("copy_rows_async: host tensors must be pinned")
+    kind = 3 if (dst.is_cuda and src.is_cuda) else 2 if src.is_cuda else 1
+    if not (dst.is_cuda or src.is_cuda):
+        raise TypeError("copy_rows_async: at least one side must be a CUDA tensor")
+    es = dst.element_size()
+    dev = dst.device if dst.is_cuda else src.device
+    st = torch.cuda.current_stream(dev) if stream is None else stream
+    with torch.cuda.device(dev):
+        rc = _abi.lib().dlc_copy_rows_async(ctypes.c_void_p(dst.data_ptr()), dst.stride(0) * es,
+                                            ctypes.c_void_p(src.data_ptr()), src.stride(0) * es, dst.shape[1] * es,
+                                            dst.shape[0], kind, ctypes.c_void_p(st.cuda_stream))
+    _abi.check(rc, "dlc_copy_rows_async")
+
+
+def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=16, env_offset=0, **kw):
+    """The whole end-to-end job of a vmapped rollout whose systems live on the HOST: per-env ``A[N,d,d] B[N,d,m]
+    K[N,m,d] x[N,d]`` in pinned host memory in, ``losses[T,N]`` (``Rollout.losses``, ``deluca/training/apg.py:68``) in
+    pinned host memory out.  Episodes never interact (``apg.py:91``), so the batch is cut into ``slices`` env ranges:
+    slice k + 1's systems travel host -> device and slice k - 1's losses device -> host (one 2-D copy into columns
+    [lo, hi) of ``host_costs``) while slice k's rollout runs -- every slice is ONE launch over the full horizon, so there
+    is no carried agent state to write and re-read between launches (``lds_rollout_to_host`` cuts the horizon instead
+    and pays ~3 ms per cut on the target job).  Slices alternate between two compute streams so that the tail of one
+    slice's grid overlaps the head of the next.  Disturbances are drawn in the kernel, keyed by the GLOBAL env index
+    (``env_offset`` + position): the result is the same job as one ``lds_rollout`` call on the whole batch.
+    ``host_costs=None`` stores no per-step losses (per-env cost sums only).
+    Returns ``cost_sum[N]`` (fp64), ``x[N,d]`` (final states), ``status[N]`` on the device, ``costs = host_costs`` and
+    ``done``, a CUDA event that completes when the last copy has."""
+    for name, t in (("A", A), ("B", B), ("K", K), ("x", x), ("host_costs", host_costs)):
+        if name == "host_costs" and t is None:
+            continue
+        if not (isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == torch.float32
+                and t.is_contiguous()):
+            raise TypeError(f"{name} must be a contiguous pinned float32 CPU tensor")
+    if A.dim() != 3:
+        raise ValueError("lds_rollout_host_to_host takes per-env systems A[N,d,d] (shared dynamics need no slicing)")
+    N, d = x.shape
+    if host_costs is not None and tuple(host_costs.shape) != (T, N):
+        raise ValueError(f"host_costs must be float32 [{T},{N}]")
+    for k in ("W", "keep_costs", "traj_stride", "donate", "M", "hist", "xprev", "uprev", "eps", "eps_new", "bpc_cost"):
+        if kw.get(k) is not None and kw.get(k) is not False:
+            raise ValueError(f"{k} is not available on the env-sliced path")
+        kw.pop(k, None)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    slices = max(1, min(int(slices), N)) if N else 1
+    # slice boundaries on multiples of 32 envs (whole CTAs of every LDS kernel)
+    bounds = sorted({min(N, (round(i * N / slices) + 31) // 32 * 32) for i in range(slices)} | {0, N})
+    cost_sum = torch.empty((N,), dtype=torch.float64, device=dev)
+    status = torch.empty((N,), dtype=torch.int32, device=dev)
+    x_out = torch.empty((N, d), dtype=torch.float32, device=dev)
+    up, down, comp = _slice_streams(dev)
+    caller = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(caller)
+    for st in (up, down) + comp:
+        st.wait_event(start)
+    for i, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+        cs = comp[i % 2]
+        with torch.cuda.stream(up):
+            dA, dB, dK, dx = (t[lo:hi].to(dev, non_blocking=True) for t in (A, B, K, x))
+            ready = torch.cuda.Event()
+            ready.record(up)
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready)
+            for t in (dA, dB, dK, dx):
+                t.record_stream(cs)
+            r = lds_rollout(dA, dB, dK, dx, T, keep_costs=host_costs is not None, donate=True,
+                            env_offset=env_offset + lo, **kw)
+            cost_sum[lo:hi].copy_(r.cost_sum)
+            status[lo:hi].copy_(r.status)
+            x_out[lo:hi].copy_(r.x)
+            finished = torch.cuda.Event()
+            finished.record(cs)
+        if host_costs is not None:
+            down.wait_event(finished)
+            copy_rows_async(host_costs[:, lo:hi], r.costs, stream=down)
+            r.costs.record_stream(down)
+    done = torch.cuda.Event()
+    done.record(down)
+    for cs in comp:
+        caller.wait_stream(cs)
+    return LdsRolloutResult(costs=host_costs, cost_sum=cost_sum, x=x_out, status=status, t=kw.get("t0", 0) + T,
+                            done=done)
+
+
 # ------------------------------------------------------------------------------------------ lung
 def lung_rollout(params, bufs):
     """``dlc_lung_pid_rollout_f32`` on already-prepared ctypes structs (see deluca_b200.lung)."""

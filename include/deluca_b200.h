@@ -600,6 +600,16 @@ int32_t dlc_env_collect_f32(const DlcEnvSpec* env, int64_t N, int32_t T, uint64_
                             float* action_out /*[N,T,m]*/, float* next_obs_out /*[N,T,d]*/, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Strided slice transfer (no reference counterpart: JAX owns its transfers).  Copies `rows` rows of `row_bytes` bytes
+ * between pitched buffers on `stream` (one asynchronous 2-D copy): an env slice [T, n] of a time-major result lands in
+ * columns [lo, lo + n) of the caller's pinned [T, N] host array (kind 2, device -> host), or the reverse (kind 1).
+ * Used by the env-sliced end-to-end rollout (deluca_b200.fused.lds_rollout_host_to_host), whose per-slice uploads,
+ * kernels and downloads overlap.  kind: 1 host -> device, 2 device -> host, 3 device -> device.
+ * ------------------------------------------------------------------------------------ */
+int32_t dlc_copy_rows_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes,
+                            size_t row_bytes, size_t rows, int32_t kind, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Pipe-rate microbenchmarks (no reference counterpart): the FP32 FMA peak that bounds the LDS+GPC
  * kernels is not in MEASURED_PEAKS.json, so bench.py measures it with these.
  *   which: 0 FFMA (72 FMA/thread/iter)   1 packed fma.f32x2 (72 FMA/thread/iter)

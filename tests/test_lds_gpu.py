@@ -380,3 +380,38 @@ def test_rollout_streamed_to_host_equals_one_launch(H, HH, N, T):
     assert torch.allclose(r.cost_sum, one.cost_sum, rtol=1e-6) and r.t == T and int(r.status.sum()) == 0
     with pytest.raises(TypeError):
         lds_rollout_to_host(A, B, K, x0, T, torch.empty(T, N), **kw)        # not pinned
+
+
+def test_env_sliced_host_to_host_rollout_is_the_same_job():
+    """fused.lds_rollout_host_to_host (pinned host systems in, losses[T,N] in pinned host memory out, env slices whose
+    copies and kernels overlap) against ONE lds_rollout call on the whole batch with the in-kernel disturbance stream:
+    same bits (the stream is keyed by the global env index), for the target's shape (H = HH = 10) and configs[1]'s;
+    and dlc_copy_rows_async in both directions."""
+    from deluca_b200.fused import copy_rows_async, lds_rollout, lds_rollout_host_to_host
+    src = torch.arange(7 * 40, dtype=torch.float32).reshape(7, 40)
+    host = torch.zeros(7, 40).pin_memory()
+    dev = src.cuda()
+    copy_rows_async(host[:, 8:24], dev[:, 3:19])
+    torch.cuda.synchronize()
+    assert torch.equal(host[:, 8:24], src[:, 3:19]) and host[:, :8].eq(0).all() and host[:, 24:].eq(0).all()
+    back = torch.zeros(7, 40, device="cuda")
+    copy_rows_async(back[:, 1:17], host[:, 8:24])
+    torch.cuda.synchronize()
+    assert torch.equal(back[:, 1:17].cpu(), src[:, 3:19])
+    with pytest.raises(ValueError):
+        copy_rows_async(host[:, ::2], dev[:, :20])
+    d, m = 10, 3
+    for (H, HH), N, T, slices in (((10, 10), 1000, 40, 4), ((3, 10), 700, 60, 16), ((10, 10), 64, 12, 1)):
+        A, B, K, x0, _ = _problem(N, d, m, T, seed=31 + H, dense=True)
+        kw = dict(policy="gpc", H=H, HH=HH, lr_scale=1e-4, seed=5, w_std=0.5)
+        whole = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, env_offset=77, **kw)
+        pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).pin_memory()
+        out = torch.full((T, N), float("nan")).pin_memory()
+        r = lds_rollout_host_to_host(pin(A), pin(B), pin(K), pin(x0), T, out, slices=slices, env_offset=77, **kw)
+        r.done.synchronize()
+        assert torch.equal(out, whole.costs.cpu()), (H, N)
+        assert torch.equal(r.cost_sum, whole.cost_sum) and torch.equal(r.x, whole.x) and torch.equal(r.status, whole.status)
+        r2 = lds_rollout_host_to_host(pin(A), pin(B), pin(K), pin(x0), T, None, slices=slices, env_offset=77, **kw)
+        assert r2.costs is None and torch.equal(r2.cost_sum, whole.cost_sum) and torch.equal(r2.x, whole.x)
+    with pytest.raises(TypeError):
+        lds_rollout_host_to_host(torch.zeros(4, 10, 10), pin(B[:4]), pin(K[:4]), pin(x0[:4]), 3, out[:3, :4].contiguous().pin_memory())

@@ -312,11 +312,11 @@ class Runner:
         def one():
             if return_losses and self.e2e_mode == "env_slices":
                 # env slices: uploads, rollouts and the losses' downloads of different slices overlap (public API)
-                rr = lds_rollout_host_to_host(hA, hB, hK, hx, T, h_out, device=self.dev, slices=16, **self.kw)
+                rr = lds_rollout_host_to_host(hA, hB, hK, hx, T, h_out, device=self.dev, **self.kw)
                 torch.cuda.current_stream(self.dev).wait_event(rr.done)
                 return
             if self.e2e_mode == "env_slices":
-                rr = lds_rollout_host_to_host(hA, hB, hK, hx, T, None, device=self.dev, slices=16, **self.kw)
+                rr = lds_rollout_host_to_host(hA, hB, hK, hx, T, None, device=self.dev, **self.kw)
                 h_out.copy_(rr.cost_sum, non_blocking=True)
                 return
             dA, dB, dK, dx = (t.to(self.dev, non_blocking=True) for t in (hA, hB, hK, hx))
@@ -478,7 +478,7 @@ def main():
                     "overlap": args.e2e_mode,
                     "note": "per step: host A,B,K,x0 (pinned) -> device; fused rollout, disturbances drawn by the env "
                             "in the kernel (the reference's LDS draws its own noise too); the full losses[T,N] "
-                            "(Rollout.losses) -> pinned host; the batch is cut into 16 env slices whose uploads, "
+                            "(Rollout.losses) -> pinned host; the batch is cut into <= 16 env slices whose uploads, "
                             "rollouts and downloads overlap (fused.lds_rollout_host_to_host).  `value` differs only in "
                             "reading the same disturbance stream from HBM; `value_kernel_rng` is this leg's kernel "
                             "variant timed on the device."

@@ -234,10 +234,11 @@ def copy_rows_async(dst, src, stream=None):
     _abi.check(rc, "dlc_copy_rows_async")
 
 
-def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=16, env_offset=0, **kw):
+def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=None, env_offset=0, **kw):
     """The whole end-to-end job of a vmapped rollout whose systems live on the HOST: per-env ``A[N,d,d] B[N,d,m]
     K[N,m,d] x[N,d]`` in pinned host memory in, ``losses[T,N]`` (``Rollout.losses``, ``deluca/training/apg.py:68``) in
-    pinned host memory out.  Episodes never interact (``apg.py:91``), so the batch is cut into ``slices`` env ranges:
+    pinned host memory out.  Episodes never interact (``apg.py:91``), so the batch is cut into ``slices`` env ranges
+    (default: up to 16, of at least 32,768 envs -- a few full waves of the rollout kernels' grids -- each):
     slice k + 1's systems travel host -> device and slice k - 1's losses device -> host (one 2-D copy into columns
     [lo, hi) of ``host_costs``) while slice k's rollout runs -- every slice is ONE launch over the full horizon, so there
     is no carried agent state to write and re-read between launches (``lds_rollout_to_host`` cuts the horizon instead
@@ -263,6 +264,8 @@ def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=1
             raise ValueError(f"{k} is not available on the env-sliced path")
         kw.pop(k, None)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if slices is None:
+        slices = min(16, N // 32768)
     slices = max(1, min(int(slices), N)) if N else 1
     # slice boundaries on multiples of 32 envs (whole CTAs of every LDS kernel)
     bounds = sorted({min(N, (round(i * N / slices) + 31) // 32 * 32) for i in range(slices)} | {0, N})

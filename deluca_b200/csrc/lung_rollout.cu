@@ -875,7 +875,7 @@ __global__ void __launch_bounds__(128) lung_pid_grad_kernel(const LungGradArgs a
 // (dP, dV, dp, di, dd, dloss) x 3 = 18 registers -- and nothing is checkpointed: no workspace, no second sweep, no HBM
 // traffic beyond the gains in and loss + gradient out (the reverse-mode kernel above writes and re-reads 48 B per
 // env-step and recomputes every step).  Same step as lung_pid_grad_kernel's forward sweep, operation for operation.
-template <int NK>
+template <int NK, int SIM>
 __global__ void __launch_bounds__(128) lung_pid_grad_fwd_kernel(const LungGradArgs a) {
   const DlcLungParams& p = a.p;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -889,11 +889,70 @@ __global__ void __launch_bounds__(128) lung_pid_grad_fwd_kernel(const LungGradAr
   }
   const float kg[3] = {a.K[nn * 3 + 0], a.K[nn * 3 + 1], a.K[nn * 3 + 2]};
   const float dec = p.pid_decay;
-  const float pc_r0sq = __fdiv_rn(p.PC, p.r0_sq);
+  const float pc_r0sq = __fdiv_rn(SIM == DLC_SIM_BALLOON ? p.PC : p.d_C, p.r0_sq);
   float P = a.reset_pressure, V = p.min_volume, cp = 0.f, ci = 0.f, cd = 0.f, time = 0.f, total = 0.f;
   float dP[3] = {0.f, 0.f, 0.f}, dV[3] = {0.f, 0.f, 0.f}, dcp[3] = {0.f, 0.f, 0.f}, dci[3] = {0.f, 0.f, 0.f},
         dcd[3] = {0.f, 0.f, 0.f}, dtot[3] = {0.f, 0.f, 0.f};
-  for (int t = 0; t < p.T; ++t) {
+  if (SIM == DLC_SIM_DELAY) {
+    // DelayLung (envs/_delay_lung.py:75-133) under train_controller.rollout: the observation is the PRE-dynamics
+    // state, so the controllers' clock lags the simulator's by a step; the action enters the pipe through
+    // in_history[0] -- the entry just written (:120-123) -- once `time < delay` (seconds against a step count, sic
+    // :88-96) stops holding, which is why the gradient is exactly zero over the first 25 s with the default delay.
+    // Forward arithmetic as lung_pid_kernel's DelayLung branch, operation for operation.
+    const float inv_dR = __fdiv_rn(1.0f, p.d_R), early_end = (float)p.delay;
+    float pipe = 0.f, obs_t = 0.f, dpipe[3] = {0.f, 0.f, 0.f};
+    for (int t = 0; t < p.T; ++t) {
+      P += a.noise;                                                // train_controller.py:51-53
+      const float xo = fmod_pos(obs_t, p.period);
+      const float err = interp_knots<NK>(p, kf, xo) - P;
+      const float ni = ci + dec * (err - ci), nd = cd + dec * ((err - cp) - cd);
+      const float pid[3] = {err, ni, nd};
+      const float u_raw = (err * kg[0] + ni * kg[1]) + nd * kg[2];
+      const float u = fminf(fmaxf(u_raw, 0.f), 100.f);
+      const bool inhale = xo <= p.xp_in;                           // u_out == 0
+      const bool early = time < early_end;
+      // d impulse / d u_raw: the clamp passes inside its range, `u_in > 0` (:113-115) on the positive side
+      const float chain = (!early && u_raw > 0.f && u_raw <= 100.f) ? p.control_gain : 0.f;
+      const float diff = interp_knots<NK>(p, kf, fmod_pos(a.tt[t], p.period)) - P;
+      float dl = 0.f;
+      if (inhale) {
+        total += a.loss_kind == DLC_LOSS_L1 ? fabsf(diff) : diff * diff;
+        dl = a.loss_kind == DLC_LOSS_L1 ? (diff > 0.f ? -1.0f : (diff < 0.f ? 1.0f : 0.f)) : -2.0f * diff;
+      }
+      const float uin_pos = u > 0.f ? u : 0.f;
+      obs_t = time;
+      const float Vraw = V + (P * inv_dR) * p.dt;
+      const bool v_free = Vraw > p.min_volume;                     // jnp.maximum(volume, min_volume)
+      const float Vn = fmaxf(Vraw, p.min_volume);
+      const float r = cbrt_pos(Vn * 0.238732414637843f);
+      const float ir = rcpf_approx(r), ir2 = ir * ir, q = p.r0 * ir, q2 = q * q, q6 = q2 * q2 * q2;
+      const float lung_p = pc_r0sq * fmaf(-q2 * q2, q2, 1.0f) * ir;
+      const float dLdV = pc_r0sq * (-ir2 + 7.0f * q6 * ir2) * (r * rcpf_approx(3.0f * Vn));
+      const float pipe_n = p.inertia * pipe + (early ? 0.f : p.control_gain * uin_pos);
+      const float Praw = pipe_n - lung_p;
+      const bool p_free = Praw > 0.f;                              // jnp.maximum(0, pipe_pressure - lung_pressure)
+      const float bleed = (!early && !inhale) ? 0.995f : 1.0f;     // peep = out_history[0] = u_out (:93-102)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        dtot[g] = fmaf(dl, dP[g], dtot[g]);
+        const float derr = -dP[g];
+        const float dni = dci[g] + dec * (derr - dci[g]);
+        const float dnd = dcd[g] + dec * ((derr - dcp[g]) - dcd[g]);
+        const float du_raw = ((derr * kg[0] + dni * kg[1]) + dnd * kg[2]) + pid[g];
+        dcp[g] = derr; dci[g] = dni; dcd[g] = dnd;
+        dV[g] = v_free ? dV[g] + p.dt * inv_dR * dP[g] : 0.f;
+        const float dpn = p.inertia * dpipe[g] + chain * du_raw;
+        dP[g] = p_free ? dpn - dLdV * dV[g] : 0.f;
+        dpipe[g] = bleed * dpn;
+      }
+      cp = err; ci = ni; cd = nd;
+      V = Vn;
+      P = fmaxf(0.f, Praw);
+      pipe = bleed == 1.0f ? pipe_n : pipe_n * 0.995f;
+      time += p.dt;
+    }
+  }
+  for (int t = 0; SIM == DLC_SIM_BALLOON && t < p.T; ++t) {
     P += a.noise;                                                  // train_controller.py:51-53
     const float xo = fmod_pos(time, p.period);
     const float err = interp_knots<NK>(p, kf, xo) - P;
@@ -983,7 +1042,10 @@ extern "C" int32_t dlc_lung_pid_grad_f32(const DlcLungParams* p, const float* K,
   using namespace dlc;
   if (!p) return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: NULL params");
   if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: negative N or T");
-  if (p->sim != DLC_SIM_BALLOON) return fail(DLC_ERR_SHAPE, "dlc_lung_pid_grad_f32: BalloonLung only");
+  if (p->sim != DLC_SIM_BALLOON && p->sim != DLC_SIM_DELAY)
+    return fail(DLC_ERR_SHAPE, "dlc_lung_pid_grad_f32: sim must be DLC_SIM_BALLOON or DLC_SIM_DELAY");
+  if (p->sim == DLC_SIM_DELAY && lung_grad_reverse())
+    return fail(DLC_ERR_SHAPE, "dlc_lung_pid_grad_f32: the reverse-mode cross-check kernel covers BalloonLung only");
   if (p->nk < 2 || p->nk > DLC_MAX_KNOTS) return fail(DLC_ERR_SHAPE, "dlc_lung_pid_grad_f32: 2 <= nk <= 16 knots");
   if (loss_kind != DLC_LOSS_L1 && loss_kind != DLC_LOSS_L2) return fail(DLC_ERR_ARG, "dlc_lung_pid_grad_f32: bad loss");
   if (p->N == 0) return DLC_OK;
@@ -1000,8 +1062,14 @@ extern "C" int32_t dlc_lung_pid_grad_f32(const DlcLungParams* p, const float* K,
     if (p->nk == 7) lung_pid_grad_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
     else lung_pid_grad_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
   } else {
-    if (p->nk == 7) lung_pid_grad_fwd_kernel<7><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-    else lung_pid_grad_fwd_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (p->sim == DLC_SIM_DELAY) {
+      if (p->nk == 7) lung_pid_grad_fwd_kernel<7, DLC_SIM_DELAY><<<grid, 128, 0, st>>>(a);
+      else lung_pid_grad_fwd_kernel<0, DLC_SIM_DELAY><<<grid, 128, 0, st>>>(a);
+    } else {
+      if (p->nk == 7) lung_pid_grad_fwd_kernel<7, DLC_SIM_BALLOON><<<grid, 128, 0, st>>>(a);
+      else lung_pid_grad_fwd_kernel<0, DLC_SIM_BALLOON><<<grid, 128, 0, st>>>(a);
+    }
   }
   return cuda_status(cudaGetLastError(), "lung_pid_grad_kernel launch");
 }

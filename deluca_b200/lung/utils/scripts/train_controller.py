@@ -1,10 +1,10 @@
 """``deluca/lung/utils/scripts/train_controller.py``: the differentiable episode and its gradient.
 
 ``rollout`` / ``rollout_parallel`` (``:33-92``) return the inhale-only tracking loss of a lung PID
-controller on BalloonLung; ``value_and_grad_rollout_parallel`` is what
+controller on BalloonLung or DelayLung; ``value_and_grad_rollout_parallel`` is what
 ``jax.value_and_grad(rollout_parallel)`` (``:151-153``) yields for the controller's ``params``
-leaf.  Forward and reverse pass run in ``dlc_lung_pid_grad_f32`` (hand-derived adjoint).  The
-optimiser loop around it (optax, ``:116-186``) is out of scope.
+leaf.  Value and gradient come from one launch of ``dlc_lung_pid_grad_f32`` (forward mode: the three gains'
+tangents ride along the episode).  The optimiser loop around it (optax, ``:116-186``) is out of scope.
 """
 import torch
 
@@ -13,6 +13,7 @@ from ... import _launch
 from ...controllers._pid import PID
 from ...core import DEFAULT_DT, BreathWaveform
 from ...envs._balloon_lung import BalloonLung
+from ...envs._delay_lung import DelayLung
 from .... import _abi, fused
 
 
@@ -29,8 +30,8 @@ _LOSS = {l1_loss: 0, l2_loss: 1}
 
 
 def _episode(controller, sim, tt, use_noise, peep, pips, loss_fn, noise_value):
-    if not isinstance(controller, PID) or not isinstance(sim, BalloonLung):
-        raise NotImplementedError("the fused gradient kernel covers the lung PID controller on BalloonLung")
+    if not isinstance(controller, PID) or not isinstance(sim, (BalloonLung, DelayLung)):
+        raise NotImplementedError("the fused gradient kernel covers the lung PID controller on BalloonLung / DelayLung")
     if loss_fn not in _LOSS:
         raise NotImplementedError("loss_fn must be train_controller.l1_loss (the reference default) or l2_loss")
     dev = sim.device
@@ -50,7 +51,8 @@ def _episode(controller, sim, tt, use_noise, peep, pips, loss_fn, noise_value):
     _launch.sim_params(sim, p)
     K = controller.params.to(dev).expand(N, 3).contiguous()
     noise = float(use_noise) * float(noise_value)
-    return fused.lung_pid_value_and_grad(p, K, kf, tt, _LOSS[loss_fn], noise, sim.reset_normalized_peep), N
+    reset_pressure = sim.reset_normalized_peep if isinstance(sim, BalloonLung) else 0.0     # _delay_lung.py:62-74
+    return fused.lung_pid_value_and_grad(p, K, kf, tt, _LOSS[loss_fn], noise, reset_pressure), N
 
 
 def rollout(controller, sim, tt, use_noise, peep, pip, loss_fn, loss=0.0, noise_value=1.5):

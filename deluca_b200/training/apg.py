@@ -166,11 +166,10 @@ def apg_parallel_rollouts(env, env_start_states, env_init_obs, agent, agent_star
         raise NotImplementedError(f"no fused rollout kernel for env {type(env).__name__}")
     weighted = isinstance(loss_func, QuadLoss)
     if loss_func is not quad_loss and not weighted:
-        raise NotImplementedError("the fused LDS kernels realise quad_loss (x'x + u'u) and, for LQR, its diagonal "
-                                  "Q, R-weighted form QuadLoss")
-    if weighted and not isinstance(agent, LQR):
-        raise NotImplementedError("GPC / BPC learn from quad_loss inside the kernel (deluca/agents/_gpc.py:55-56); a "
-                                  "re-weighted loss would change their update -- only LQR takes QuadLoss on LDS")
+        raise NotImplementedError("the fused LDS kernels realise quad_loss (x'x + u'u) and its diagonal Q, R-weighted "
+                                  "form QuadLoss")
+    # (loss_func only scores the rollout, apg.py:54; GPC / BPC keep learning from their own cost_fn = quad_loss inside
+    # the kernel, deluca/agents/_gpc.py:55-56, so a QuadLoss here re-weights the reported losses and nothing else)
     if state_stride:
         return _lds_strided(env, env_start_states, env_init_obs, agent, agent_start_states, T, loss_func, env_offset,
                             disturbances, int(state_stride))

@@ -242,10 +242,14 @@ int32_t dlc_lung_pid_rollout_f32(const DlcLungParams* p, const DlcLungBuffers* b
  * Reverse mode through the ventilator episode: value and gradient of
  * train_controller.rollout (deluca/lung/utils/scripts/train_controller.py:33-67) with respect to the PID
  * gains, i.e. what jax.value_and_grad(rollout_parallel) (:151-153) computes for the lung PID controller on
- * BalloonLung.  Every breath starts from sim.reset() / controller.init(waveform) as in the reference;
+ * BalloonLung (deluca/lung/envs/_balloon_lung.py:100-146) or DelayLung (_delay_lung.py:75-133).  Every breath starts
+ * from sim.reset() / controller.init(waveform) as in the reference;
  *     loss_n = sum_i [u_out_i == 0] * loss_fn(waveform.at(tt[i]), pressure_i),  loss_fn = |x - y| or (x - y)^2.
- * Forward pass stores six floats per step in the workspace, the backward pass is a hand-derived adjoint
- * (checked against torch.autograd in tests).  p->sim must be DLC_SIM_BALLOON; p->T = len(tt).
+ * Default: forward mode (the three gains' tangents ride along the episode, no workspace).  With
+ * DLC_LUNG_GRAD_REVERSE=1 (BalloonLung only, kept for cross-checks) the forward pass stores six floats per step in the
+ * workspace and the backward pass is a hand-derived adjoint.  Both are held to the reference's own
+ * jax.value_and_grad(rollout_parallel) (tests/golden/ref_lung_train.npz).  p->T = len(tt); for DelayLung pass
+ * reset_pressure = 0 (its reset() has no normalized peep, :62-74).
  * ------------------------------------------------------------------------------------ */
 #define DLC_LOSS_L1 0
 #define DLC_LOSS_L2 1

@@ -649,7 +649,69 @@ def family_lung_steps():
     return both_precisions(run)
 
 
-FAMILIES = {"lung_steps": family_lung_steps, "drivers": family_drivers, "of": family_of, "lds": family_lds, "lung": family_lung, "classic": family_classic, "igpc": family_igpc}
+def family_lung_train():
+    """`train_controller.rollout` / `rollout_parallel` (deluca/lung/utils/scripts/train_controller.py:33-92) and
+    `jax.value_and_grad(rollout_parallel)` as `train_controller` takes it w.r.t. the controller's leaves (`:151-153`),
+    executed literally for the lung `PID` (explicit gains) on `BalloonLung` (with and without leak) and `DelayLung`.
+    DelayLung as written compares seconds with its step-count `delay` (`_delay_lung.py:88-96`): with the default
+    delay = 25 nothing of the action reaches the pressure for 833 steps and the gradient is exactly zero at the training
+    horizon.  The loss only counts inhale steps, so the action first shows in it during the breath after the impulses
+    start: `delay=1` (impulses from step 34 on) over 130 steps, and the default delay over 940 steps (l1 only).  The noise of
+    `:47-50` is `1.5 + normal(PRNGKey(0))`, the same constant every step; the shim's generator is not Threefry, so the
+    value is recorded (`in_noise_value`)."""
+    import jax
+    import jax.numpy as jnp
+    from deluca.lung.controllers._pid import PID
+    from deluca.lung.envs._balloon_lung import BalloonLung
+    from deluca.lung.envs._delay_lung import DelayLung
+    from deluca.lung.utils.scripts import train_controller as TC
+
+    gains = np.array([[3.0, 4.0, 0.0], [1.0, 2.5, 0.3], [0.4, 0.05, 0.0], [4.5, 0.8, 1.5]])
+    pips = [10.0, 20.0, 35.0]
+    losses = {"l1": lambda x, y: (jnp.abs(x - y)).mean(),           # the default loss_fn (:106)
+              "l2": lambda x, y: ((x - y) ** 2).mean()}
+    cases = [("balloon", lambda: BalloonLung.create(), 29), ("balloon_leak", lambda: BalloonLung.create(leak=True), 29),
+             ("balloon", lambda: BalloonLung.create(), 60),
+             ("delay", lambda: DelayLung.create(), 29), ("delay1", lambda: DelayLung.create(delay=1), 130),
+             ("delay", lambda: DelayLung.create(), 940)]
+
+    def run():
+        out = dict(in_gains=gains, in_pips=np.array(pips), in_peep=np.array(5.0),
+                   in_noise_value=np.array(float(1.5 + 1.0 * jax.random.normal(jax.random.PRNGKey(0), shape=()))))
+        for sim_name, make, T in cases:
+            tt = jnp.array(np.linspace(0.0, 0.03 * T, T))            # jnp.linspace(0, duration, int(duration / dt)), :148
+            out[f"in_tt_T{T}"] = npf(tt)
+            for loss_name, loss_fn in losses.items():
+                for use_noise in (0.0, 1.0):
+                    if use_noise and (loss_name == "l2" or sim_name == "balloon_leak"):
+                        continue
+                    if T > 500 and (use_noise or loss_name == "l2"):
+                        continue
+                    tag = f"{sim_name}_T{T}_{loss_name}_n{int(use_noise)}"
+                    per = np.zeros((len(gains), len(pips)))
+                    gper = np.zeros((len(gains), len(pips), 3))
+                    val = np.zeros(len(gains))
+                    grad = np.zeros((len(gains), 3))
+                    for gi, g in enumerate(gains):
+                        ctrl = PID.create(params={"K": {"kernel": jnp.array(g.reshape(3, 1))}})
+                        sim = make()
+                        for pi_, pip in enumerate(pips):
+                            per[gi, pi_] = float(TC.rollout(ctrl, sim, tt, use_noise, 5.0, pip, loss_fn, 0.0))
+                            v1, g1 = jax.value_and_grad(TC.rollout_parallel)(ctrl, sim, tt, use_noise, 5.0,
+                                                                             jnp.array([pip]), loss_fn)
+                            assert abs(float(v1) - per[gi, pi_]) <= 1e-9 * max(1.0, abs(per[gi, pi_]))
+                            gper[gi, pi_] = npf(g1.params["K"]["kernel"]).reshape(3)
+                        v, gr = jax.value_and_grad(TC.rollout_parallel)(ctrl, sim, tt, use_noise, 5.0, jnp.array(pips),
+                                                                        loss_fn)
+                        val[gi], grad[gi] = float(v), npf(gr.params["K"]["kernel"]).reshape(3)
+                    out[f"out_{tag}_loss"], out[f"out_{tag}_loss_grad"] = per, gper
+                    out[f"out_{tag}_value"], out[f"out_{tag}_grad"] = val, grad
+        return out
+
+    return both_precisions(run)
+
+
+FAMILIES = {"lung_train": family_lung_train, "lung_steps": family_lung_steps, "drivers": family_drivers, "of": family_of, "lds": family_lds, "lung": family_lung, "classic": family_classic, "igpc": family_igpc}
 
 
 def main():

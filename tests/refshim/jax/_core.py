@@ -344,7 +344,7 @@ def asarray(x, dtype=None):
     elif isinstance(x, torch.Tensor):
         t = x
     elif isinstance(x, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(x))
+        t = torch.from_numpy(np.ascontiguousarray(x)).reshape(x.shape)   # (ascontiguousarray makes 0-d arrays 1-d)
         if t.dtype == torch.float64 and not _X64[0]:
             t = t.float()
         if t.dtype == torch.int64 and not _X64[0]:

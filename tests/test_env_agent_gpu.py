@@ -196,6 +196,19 @@ def test_apg_lds_lqr_weighted_quad_loss_and_strided_agent_states():
     stk, _ = apg_parallel_rollouts(env, LDSState(x=x0, t=0), x0, gpc, s0, T, quad_loss, disturbances=W, state_stride=8)
     assert stk.agent_states.M.shape[:2] == (N, 3)
     assert torch.equal(stk.losses, full.losses) and torch.equal(stk.agent_states.M[:, -1], full.agent_states.M)
+    # loss_func only scores the rollout (apg.py:54): under a Q, R-weighted loss GPC learns exactly as before (its own
+    # cost_fn, _gpc.py:55-56) -- same actions and policy tensors bit for bit -- and the losses are the weighted form
+    # of the (x_t, u_t) it visited
+    wl, _ = apg_parallel_rollouts(env, LDSState(x=x0, t=0), x0, gpc, s0, T,
+                                  QuadLoss(goal=[0.0] * d, q=q.tolist(), r=r.tolist()), disturbances=W)
+    assert torch.equal(wl.actions, full.actions) and torch.equal(wl.agent_states.M, full.agent_states.M)
+    x = c(x0)
+    ref = np.zeros((N, T))
+    for t in range(T):
+        u = c(full.actions[:, t])
+        ref[:, t] = (q * x * x).sum(1) + (r * u * u).sum(1)
+        x = np.einsum("nij,nj->ni", c(A), x) + np.einsum("nim,nm->ni", c(B), u) + c(W[t])
+    _close(wl.losses, ref, what="weighted GPC losses")
 
 
 @pytest.mark.parametrize("sim", ["balloon", "delay"])

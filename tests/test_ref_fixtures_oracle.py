@@ -329,3 +329,42 @@ def test_env_agent_oracle_tangents_equal_finite_differences():
                 lm = E.rollout(env, agent, gm.reshape(gains.shape), x0, T, **kw)["losses"].sum(0)
                 fd = (lp - lm) / (2 * h)
                 np.testing.assert_allclose(r["grad"][:, k], fd, rtol=2e-5, atol=1e-6 * np.abs(fd).max())
+
+
+LUNG_TRAIN_CASES = [("balloon", "balloon", 29, None), ("balloon", "balloon_leak", 29, dict(leak=True)),
+                    ("balloon", "balloon", 60, None), ("delay", "delay", 29, None),
+                    ("delay", "delay1", 130, dict(delay=1)), ("delay", "delay", 940, None)]
+
+
+@pytest.mark.parametrize("sim,name,T,kw", LUNG_TRAIN_CASES)
+def test_lung_train_oracle_equals_reference_files(sim, name, T, kw):
+    """`train_controller.rollout` and `jax.value_and_grad(rollout_parallel)` (train_controller.py:33-92,151-153)
+    executed literally vs oracle/lung_grad.py: per-breath losses and d loss / d (K_P, K_I, K_D), float64 to rounding
+    and the reference's float32 run at 1e-4 (both walk the same float32 clocks, so the DelayLung threshold crossings
+    agree; the float64 run sees `3 - 1e-8` as a separate waveform knot and is a different trajectory after 1.5 s)."""
+    import torch
+    from oracle import lung_grad as OG
+    g = _load("lung_train")
+    gains, pips, noise = g["in_gains"], g["in_pips"], float(g["in_noise_value"])
+    K, P = np.repeat(gains, len(pips), 0), np.tile(pips, len(gains))
+    tt = g[f"in_tt_T{T}"]
+    seen = 0
+    for loss in ("l1", "l2"):
+        for un in (0.0, 1.0):
+            tag = f"{name}_T{T}_{loss}_n{int(un)}"
+            if f"out_{tag}_loss" not in g.files:
+                continue
+            seen += 1
+            for dt, suf, tol in ((torch.float64, "", 1e-8), (torch.float32, "_f32", 1e-4)):
+                lo, go = OG.value_and_grad(K, P, 5.0, tt, loss=loss, use_noise=un, noise=noise, dtype=dt, sim=sim,
+                                           sim_kwargs=kw)
+                rl, rg = g[f"out_{tag}_loss{suf}"].reshape(-1), g[f"out_{tag}_loss_grad{suf}"].reshape(-1, 3)
+                np.testing.assert_allclose(lo, rl, rtol=tol, atol=tol)
+                assert np.abs(go - rg).max() <= tol * max(np.abs(rg).max(), 1.0), (tag, suf, np.abs(go - rg).max())
+                # rollout_parallel: the mean over the pips, value and gradient
+                np.testing.assert_allclose(lo.reshape(len(gains), -1).mean(1), g[f"out_{tag}_value{suf}"], rtol=tol)
+                gm = go.reshape(len(gains), -1, 3).mean(1)
+                assert np.abs(gm - g[f"out_{tag}_grad{suf}"]).max() <= tol * max(np.abs(rg).max(), 1.0)
+    assert seen >= 1
+    if name == "delay" and T == 29:       # the action cannot reach the pressure before 25 s: exact zeros
+        assert not g["out_delay_T29_l1_n0_grad"].any() and not g["out_delay_T29_l1_n0_grad_f32"].any()

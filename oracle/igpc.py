@@ -1,9 +1,12 @@
 """deluca/igpc (rollout, compute_ders, LQR / LQG backward passes, iLQR, GPC_rollout, iGPC_closed, iLC_closed)
 and the classic envs it plans on, restated on the CPU (test infrastructure; see oracle/__init__.py).
 
-Parity unpinned: the reference has no test for any of this.  Analytic Jacobians replace
-``jax.jacfwd`` / ``jax.grad`` and are cross-checked against ``torch.autograd`` on a literal
-restatement of the env step (tests/test_oracle_igpc.py).
+Parity pinned to the reference's own files run here: ``tests/golden/ref_igpc.npz`` / ``ref_classic.npz`` hold
+``rollout``, ``compute_ders``, ``LQR``, ``iLQR``, ``GPC_rollout``, ``iGPC_closed``, ``iLC_closed`` and the env steps
+executed literally on tests/refshim (the reference has no test of its own for any of this), reproduced here to rounding
+in float64 (tests/test_ref_fixtures_oracle.py).  Analytic Jacobians replace ``jax.jacfwd`` / ``jax.grad`` and are
+additionally cross-checked against ``torch.autograd`` on a literal restatement of the env step
+(tests/test_oracle_igpc.py).
 
 Batched over a leading trajectory axis N; all trajectories advance in lockstep and the
 reference's data-dependent Python control flow (``if cC <= c: ... break``) becomes per-trajectory

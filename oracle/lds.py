@@ -1,6 +1,9 @@
 """LDS + GPC / BPC / LQR restated on the CPU (test infrastructure; see oracle/__init__.py).
 
-Parity unpinned: the reference has no test or golden vector for any function here.
+Parity pinned to the reference's own files run here: ``tests/golden/ref_lds.npz`` (``deluca/envs/_lds.py``,
+``deluca/agents/_gpc.py``, ``_bpc.py``, ``_lqr.py`` executed literally by tests/golden/make_ref_fixtures.py on
+tests/refshim; the reference ships no test or golden vector of its own for them) -- this module reproduces those runs
+to <= 1e-9 relative in float64 (tests/test_ref_fixtures_oracle.py).
 
 Everything is batched over a leading env axis N (the reference's vmap axis,
 ``deluca/training/apg.py:91``); vectors are stored flat ``[N, d]`` instead of the

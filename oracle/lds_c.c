@@ -1,8 +1,10 @@
 /*
  * C restatement of the LDS + GPC rollout (TEST INFRASTRUCTURE / CPU baseline; see oracle/__init__.py).
  *
- * Parity unpinned (no reference test or golden vector exists for LDS/GPC); checked
- * against oracle/lds.py (the line-by-line NumPy restatement) in tests/test_oracle_lds.py.
+ * Parity pinned to the reference's own files run here: reproduces tests/golden/ref_lds.npz (deluca/agents/_gpc.py +
+ * deluca/envs/_lds.py executed literally on tests/refshim) to 1e-9 in double
+ * (tests/test_ref_fixtures_oracle.py::test_c_oracle_equals_reference_file), and agrees with oracle/lds.py (the
+ * line-by-line NumPy restatement) in tests/test_oracle_lds.py.  The reference ships no test of its own for LDS/GPC.
  *
  * Follows, per env and per step t:
  *   u = -K x + sum_i M[i] hist[HH+i]                       deluca/agents/_gpc.py:171-183

@@ -4,7 +4,7 @@ Same arithmetic as ``oracle/lds.py`` (which follows ``deluca/agents/_gpc.py:109-
 ``deluca/envs/_lds.py:102-111`` line by line) written with batched torch CPU ops so that it uses
 every host core (``torch.set_num_threads``); used only by ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs and checked against ``oracle/lds.py`` in tests/test_oracle_lds.py.
-Parity unpinned (see oracle/__init__.py).
+Parity: pinned through ``oracle/lds.py`` (which reproduces the reference-generated ``tests/golden/ref_lds.npz``).
 """
 import torch
 

@@ -3,9 +3,11 @@
 Pinned: ``BreathWaveform.at / is_in / elapsed``, ``LungEnv.time``, ``proper_time`` and
 ``Controller.decay`` against the reference's own known answers
 (``deluca/tests/lung/core_test.py:43-68,73-84,97-99,119-127``; tests/test_oracle_lung.py).
-Parity unpinned: ``BalloonLung``, ``DelayLung``, lung ``PID``, ``Expiratory`` and
-``run_controller_scan`` -- the reference only smoke-tests them
-(``deluca/tests/lung/utils/scripts/test_controller_test.py:189-208``).
+Pinned as well, to the reference's own files run here: ``BalloonLung``, ``DelayLung``, lung ``PID``,
+``Expiratory``, ``run_controller_scan`` and ``test_controller`` executed literally on tests/refshim
+(``tests/golden/ref_lung.npz``: whole episodes; ``ref_lung_steps.npz``: every visited state, one step at a time);
+tests/test_ref_fixtures_oracle.py holds this module to them (1e-11 at the reference's horizon T = 29 in float64).  The
+reference itself only smoke-tests them (``deluca/tests/lung/utils/scripts/test_controller_test.py:189-208``).
 
 Everything is batched over a leading env axis N and computed in ``dtype`` (float32 = default
 JAX; every Python-float constant of the reference is weakly typed and therefore rounded to

@@ -8,10 +8,12 @@ partially observed LDS  (SURVEY 8(f) rank 3):
     DSC  ``deluca/agents/_dsc.py:42-292``     double spectral controller
 
 TEST INFRASTRUCTURE ONLY: imported by ``tests/`` (and ``__graft_entry__.smoke()``); the product
-never imports it.  PARITY UNPINNED: the reference ships no test or golden vector for any of these
-agents and cannot be executed here (no JAX).  Each function follows the cited source
-lines; the hand adjoints are checked against ``torch.autograd`` on literal restatements of the
-reference ``policy_loss`` einsums (``tests/test_oracle_of.py``).
+never imports it.  PARITY PINNED to the reference's own files run here: ``tests/golden/ref_of.npz`` holds closed
+loops of the reference's ``GRC`` / ``SFC`` / ``DSC`` / ``DRC`` / ``LQG`` classes executed literally on tests/refshim
+(tests/golden/make_ref_fixtures.py, family ``of``; the reference ships no test of its own for them), and
+this module reproduces them to rounding in float64 (tests/test_ref_fixtures_oracle.py).  In addition the hand
+adjoints are checked against ``torch.autograd`` on literal restatements of the reference ``policy_loss`` einsums
+(``tests/test_oracle_of.py``).
 
 GRC, SFC and DSC share one structure: the action is linear in the parameters and in a fixed bank of
 linear filters of the y_nat history,

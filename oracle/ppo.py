@@ -1,8 +1,9 @@
 """CPU restatement of the experience post-processing (test infrastructure; see oracle/__init__.py).
 
-Parity unpinned: the reference holds no test or golden vector for ``gae_advantages``; this follows
-``deluca/training/ppo.py:44-84`` statement by statement in the dtype it is given (float32 arrays
-reproduce the reference's arithmetic; float64 is the yardstick).
+Parity pinned to the reference's own file run here: ``gae_advantages`` of ``deluca/training/ppo.py:44-84`` executed
+literally on tests/refshim (``tests/golden/ref_drivers.npz``, tests/test_ref_fixtures_oracle.py); this follows it
+statement by statement in the dtype it is given (float32 arrays reproduce the reference's arithmetic; float64 is the
+yardstick).
 """
 import numpy as np
 

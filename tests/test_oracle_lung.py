@@ -1,5 +1,5 @@
 """Oracle checks for the lung path: the reference's own known answers
-(deluca/tests/lung/core_test.py) plus behavioural sanity of the unpinned simulators."""
+(deluca/tests/lung/core_test.py) plus behavioural sanity of the simulators (which are pinned to reference runs in test_ref_fixtures_oracle.py)."""
 import numpy as np
 import pytest
 

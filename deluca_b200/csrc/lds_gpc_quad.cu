@@ -22,6 +22,8 @@
 //    rounding error does not accumulate; the result agrees with the float64 oracle to ~1e-6 (tests/test_lds_gpu.py).
 //
 // Reference arithmetic: deluca/agents/_gpc.py:109-183 (policy_loss, update, get_action), deluca/envs/_lds.py:102-111.
+#include <stdlib.h>
+
 #include "lds_args.cuh"
 #include "f2.cuh"
 
@@ -42,10 +44,30 @@ struct QuadLayout {
   static constexpr int oA9 = nA4, oG = 2 * nA4, NPAR4 = 2 * nA4 + nG4;
   static constexpr size_t kParamBytes = (size_t)NPAR4 * TPB * sizeof(float4);
   static constexpr size_t kSmemBytes = kRingBytes + kParamBytes;
+  // INCR: per warp H slots x H positions (+ one pad row) of window Gram sums, [row][env]
+  static constexpr int CROWS = H * H + 1;
+  static constexpr size_t kColBytes = (size_t)WARPS * CROWS * EPW * sizeof(float);
+  // INCR: the previous step's window products V[h][c], h = 0 .. H (row H is a pad), [row][env] per warp
+  static constexpr int VROWS = (H + 1) * M;
+  static constexpr size_t kVBytes = (size_t)WARPS * VROWS * EPW * sizeof(float);
+  static constexpr size_t kSmemBytesIncr = kSmemBytes + kColBytes + kVBytes;
 };
 
 // WSRC: 1 = disturbances from a.W, 2 = in-kernel Philox stream
-template <int D, int M, int H, int TPB, int MINB, int WSRC>
+//
+// INCR: incremental window products.  The ring only shifts (w_t[j] = w_(t-1)[j+1]) and M only changes by the rank-H
+// update, so for h <= H-2
+//     V_t[h] = sum_i M_t[i] w_t[h+i+1] = V_(t-1)[h+1] + sum_h' s_(t-1)[h'] C_t[h'][h+1],
+//     C_t[a][b] = sum_(i<H) <w_t[a+i], w_t[b+i]>                    (Gram sums of the ring: no M in them)
+// and only the newest window V_t[H-1] is contracted with M (H m d multiply-adds instead of H^2 m d).  C shifts with the
+// ring as well, C_(t+1)[a][b] = C_t[a+1][b+1]; its last column is carried by
+//     C_(t+1)[a][H-1] = C_t[a][H-1] + <w_t[a+H], w_t[2H-1]> - <w_t[a], w_t[H-1]>
+// (2H inner products per step, formed inside the pass from slots that are in registers anyway).  Entry (mn, mx),
+// mn <= mx, of C_t lives at row ((t + mn) mod H) * H + (mx - mn) of the warp's column ring -- a place that does not move
+// when the matrix shifts -- so a step writes H values and reads the H (H-1) it needs.  A window value is formed in
+// full once and corrected H-1 times; C and V are re-formed from (M, ring) at every call entry.  Same numbers to
+// rounding (float64 prototype: 1e-15; held to 1e-4 against the float64 oracle like the direct form).
+template <int D, int M, int H, int TPB, int MINB, int WSRC, bool INCR>
 __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a) {
   using Lay = QuadLayout<D, M, H, TPB>;
   constexpr int DC = Lay::DC, HT = Lay::HT, HS = Lay::HS, HP = H / 2, P = Lay::P, EPW = Lay::EPW, S1 = Lay::S1;
@@ -67,6 +89,11 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
   float* const rown = ring + k0 * EPW;                                                // own coordinates (S_qc)
   float* const rcol = ring + j0 * EPW;                                                // coordinates S_qi
   float4* const sPar = reinterpret_cast<float4*>(smraw + Lay::kRingBytes) + tid;      // sPar[idx4 * TPB]
+  // INCR: the warp's column ring of window Gram sums, entry (row, env) at colw[row * EPW]
+  float* const colw = reinterpret_cast<float*>(smraw + Lay::kSmemBytes) + (size_t)warp * Lay::CROWS * EPW + e;
+  static_assert(!INCR || ((HT & 1) == 1), "INCR is written for an odd tap half (H = 10)");
+  // INCR: V_(t-1)[h][c] at vsh[(h * M + c) * EPW] (kept in shared memory: 15 registers less across the pass)
+  float* const vsh = reinterpret_cast<float*>(smraw + Lay::kSmemBytes + Lay::kColBytes) + (size_t)warp * Lay::VROWS * EPW + e;
   constexpr unsigned FULL = 0xffffffffu;
 
   // ================= set-up: operators of the recursion-free form (once per rollout)
@@ -228,6 +255,57 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
   }
   __syncwarp();
 
+  // INCR set-up: C_0 and the previous step's window products, both formed in full from (M, ring) once per call
+  int cb = 0;                             // t mod H
+  if constexpr (INCR) {
+    float Vp[HS][M];                      // V_(-1) on the lane's window subset h in [qi*HS, qi*HS + HS)
+    int cnt = 0;
+#pragma unroll 1
+    for (int mn = 0; mn < H; ++mn)
+#pragma unroll 1
+      for (int mx = mn; mx < H; ++mx) {
+        if ((cnt++ & 3) != q) continue;
+        float sacc = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < H; ++i)
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            sacc = fmaf(ring[(mn + i) * S1 + k * EPW], ring[(mx + i) * S1 + k * EPW], sacc);
+        colw[(mn * H + (mx - mn)) * EPW] = sacc;                       // (head = 0 here: logical slot = physical slot)
+      }
+    if (q == 0) colw[H * H * EPW] = 0.f;                               // pad row (read by a discarded term only)
+#pragma unroll
+    for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+      for (int c = 0; c < M; ++c) Vp[hh][c] = 0.f;
+    const float* gM = a.M_io + n * (H * M * D);
+#pragma unroll 1
+    for (int i = 0; i < H; ++i)
+#pragma unroll 1
+      for (int k = 0; k < D; ++k) {
+        float mv[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) mv[c] = gM[(i * M + c) * D + k];
+#pragma unroll
+        for (int hh = 0; hh < HS; ++hh) {                              // V_(-1)[h] = sum_i M[i] w[h + i]
+          const float wv = ring[(qi * HS + hh + i) * S1 + k * EPW];
+#pragma unroll
+          for (int c = 0; c < M; ++c) Vp[hh][c] = fmaf(mv[c], wv, Vp[hh][c]);
+        }
+      }
+    if (qc == 0) {
+#pragma unroll
+      for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+        for (int c = 0; c < M; ++c) vsh[((qi * HS + hh) * M + c) * EPW] = Vp[hh][c];
+    }
+    if (q == 0) {
+#pragma unroll
+      for (int c = 0; c < M; ++c) vsh[(H * M + c) * EPW] = 0.f;        // pad row (read by a discarded term only)
+    }
+    __syncwarp();
+  }
+
   // per-lane operators back from shared memory (float4 columns), at the point of use
   auto load_block = [&](int o4, float blk[DC][DC]) {
     float flat[Lay::nA4 * 4];
@@ -368,12 +446,19 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
       if (p.T > 0) load_w(tn, wnext);
     }
     // ================= one pass over the ring (old indexing): M += sum_h s[h] (x) w[h+i];  V[h] = sum_i M[i] w[h+i+1]
-    f2 acc[HP][M];
+    constexpr int NACC = INCR ? 1 : HP;
+    f2 acc[NACC][M];
+    float acct[M];                        // INCR: the odd tap's share of the newest window
+    f2 g2[H / 2];                         // INCR: pairs of ring inner products (in-terms on qi = 1, out-terms on qi = 0)
     {
 #pragma unroll
-      for (int b = 0; b < HP; ++b)
+      for (int b = 0; b < NACC; ++b)
 #pragma unroll
         for (int c = 0; c < M; ++c) acc[b][c] = pk(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < M; ++c) acct[c] = 0.f;
+#pragma unroll
+      for (int j = 0; j < H / 2; ++j) g2[j] = pk(0.f, 0.f);
       // logical slot i0 + r lives at byte address rlo + r*S1*4, or, past the wrap, at rhi + r*S1*4
       const unsigned rlo = (unsigned)__cvta_generic_to_shared(rown + (head + i0) * S1);
       const unsigned rhi = rlo - P * S1 * 4;
@@ -401,23 +486,140 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
             for (int pp = 0; pp < NPI; ++pp) Mp[pp][c][kk] = fma2(dup(sprev[h][c]), pair(h + 2 * pp), Mp[pp][c][kk]);
             if (TI) Ms[c][kk] = fmaf(sprev[h][c], lo(wp[h + HT - 1]), Ms[c][kk]);
           }
+        if constexpr (INCR) {
+          // forward, newest window only: V[H-1][c] += M[ii][c][k] * w[H + i0 + ii][k]; tap pairs against slot pairs
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+#pragma unroll
+            for (int pp = 0; pp < NPI; ++pp) acc[0][c] = fma2(Mp[pp][c][kk], wp[H + 2 * pp], acc[0][c]);
+            if (TI) acct[c] = fmaf(Ms[c][kk], hi(wp[R - 2]), acct[c]);
+          }
+          // ring inner products for the last column of C_(t+1): qi = 1 holds slots H .. 2H-1 (in-terms against the
+          // newest slot), qi = 0 holds slots 0 .. H-1 (out-terms against slot H-1)
+          const f2 pv = dup(qi ? hi(wp[R - 2]) : lo(wp[H - 1]));
+#pragma unroll
+          for (int j = 0; j < H / 2; ++j) {
+            const f2 src = qi ? wp[HT + 2 * j] : wp[2 * j];
+            g2[j] = fma2(src, pv, g2[j]);
+          }
+        } else {
         // forward (step t): (V[2b], V[2b+1])[c] += M[ii][c][k] * (w'[2b + i], w'[2b + i + 1]),  w'[j] = w[j+1]
 #pragma unroll
-        for (int b = 0; b < HP; ++b)
+        for (int b = 0; b < NACC; ++b)
 #pragma unroll
           for (int ii = 0; ii < HT; ++ii)
 #pragma unroll
             for (int c = 0; c < M; ++c) acc[b][c] = fma2(dup(Mtap(ii, c, kk)), pair(2 * b + ii + 1), acc[b][c]);
+        }
       }
     }
     if (t < p.T) {                                                    // (trip T: the pass applied the last update)
     head = (head + 1 == P) ? 0 : head + 1;                            // roll(-1)               _gpc.py:156-157
     float G[HS][DC][M];
-    load_G(G);
+    if constexpr (!INCR) load_G(G);
 
     // ---- window products: the tap halves swap the partial sums of each other's window subset, then the coordinate
     // halves are summed; lane (qc, qi) ends up with the complete V[h] of its subset h in [qi*HS, qi*HS + HS)
     float Vown[HS][M], mw[M];
+    if constexpr (INCR) {
+      // newest window, summed over the four lanes (every lane ends up with it: it is the action's M-part)
+#pragma unroll
+      for (int c = 0; c < M; ++c) {
+        float v = (lo(acc[0][c]) + hi(acc[0][c])) + acct[c];
+        v += __shfl_xor_sync(FULL, v, 1);
+        v += __shfl_xor_sync(FULL, v, 2);
+        mw[c] = v;
+      }
+      // ---- rows of the column ring this step touches.  The lane sums h' = a over [A0, A0 + HT) for the windows
+      // b = h + 1 in [B0, B0 + HS); entry (mn, mx) of C_t is at row ((t + mn) mod H) * H + (mx - mn).
+      constexpr int RS = H * EPW;                                      // floats per slot
+      const int A0 = qc * HT, B0 = qi * HS + 1, D0 = B0 - A0;
+      int offA[HT + 1], offB[HS];
+#pragma unroll
+      for (int x = 0; x <= HT; ++x) {
+        int sl = cb + A0 + x;
+        sl -= sl >= H ? H : 0;
+        offA[x] = sl * RS;
+      }
+#pragma unroll
+      for (int hh = 0; hh < HS; ++hh) {
+        int sl = cb + B0 + hh;
+        sl -= sl >= H ? H : 0;
+        offB[hh] = sl * RS;
+      }
+      // ---- last column of C_(t+1) first (it frees the pass's accumulators): reduce the inner products over the
+      // coordinate halves (each keeps its a half), exchange in- and out-terms between the tap halves, add to the old
+      // column.  (No entry of C_t that this step reads lives where the new column goes: see the header.)
+      {
+        float gl[H], keep[HT];
+#pragma unroll
+        for (int j = 0; j < H / 2; ++j) { gl[2 * j] = lo(g2[j]); gl[2 * j + 1] = hi(g2[j]); }
+#pragma unroll
+        for (int x = 0; x < HT; ++x) {
+          const float send = qc ? gl[x] : gl[HT + x];
+          const float mine = qc ? gl[HT + x] : gl[x];
+          keep[x] = mine + __shfl_xor_sync(FULL, send, 1);
+        }
+#pragma unroll
+        for (int x = 0; x < HT; ++x) {
+          const float other = __shfl_xor_sync(FULL, keep[x], 2);
+          const float delta = qi ? keep[x] - other : other - keep[x];  // in - out
+          const int pos = (H - 1 - A0 - x) * EPW;                      // entry (a, H-1), a = A0 + x; both tap halves
+          colw[offA[x + 1] + pos] = colw[offA[x] + pos] + delta;       // store the same value (no divergent branch)
+        }
+      }
+      // ---- V_t[h] = V_(t-1)[h+1] + sum_h' s_(t-1)[h'] C_t[h'][h+1] on the lane's windows, h' split over qc.
+      // a <= b: row offA[x] + (b - a) = ua[x] + hh ; a >= b: row offB[hh] + (a - b) = ub[hh] + x.  Which order holds is
+      // a compile-time property of (x, hh) on the diagonal lanes (x <= hh + 1 <=> a <= b) and fixed on the other two.
+      const bool is10 = qc == 1 && qi == 0, is01 = qc == 0 && qi == 1;
+      int QA[HS], QB[HS];
+#pragma unroll
+      for (int hh = 0; hh < HS; ++hh) {
+        const int ub = offB[hh] - (D0 + hh) * EPW;
+        QA[hh] = is10 ? ub : hh * EPW;
+        QB[hh] = is01 ? hh * EPW : ub;
+      }
+      // the accumulators start from the shifted previous windows on qc = 0 and from zero on qc = 1, so that the sum
+      // over the coordinate-half pair adds V_(t-1)[h+1] once; the subset's last window continues in the other tap half
+      {
+        const float* vnext = vsh + (qi * HS + 1) * M * EPW;            // V_(t-1)[h + 1], h = qi*HS + hh
+#pragma unroll
+        for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            const float nxt = vnext[(hh * M + c) * EPW];
+            Vown[hh][c] = qc ? 0.f : nxt;
+          }
+      }
+#pragma unroll
+      for (int x = 0; x < HT; ++x) {
+        const int ua = offA[x] + (D0 - x) * EPW;
+        const int pa = is10 ? x * EPW : ua, pb = is01 ? ua : x * EPW;
+        float shx[M];                                                  // s_(t-1)[A0 + x]
+#pragma unroll
+        for (int c = 0; c < M; ++c) shx[c] = qc ? sprev[HT + x][c] : sprev[x][c];
+#pragma unroll
+        for (int hh = 0; hh < HS; ++hh) {
+          const float cv = colw[(x <= hh + 1) ? pa + QA[hh] : pb + QB[hh]];
+#pragma unroll
+          for (int c = 0; c < M; ++c) Vown[hh][c] = fmaf(shx[c], cv, Vown[hh][c]);
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const float v = Vown[hh][c] + __shfl_xor_sync(FULL, Vown[hh][c], 1);
+          Vown[hh][c] = (hh == HS - 1 && qi) ? mw[c] : v;              // h = H-1: the direct one
+        }
+      __syncwarp();                                                    // (all of V_(t-1) has been read)
+      if (qc == 0) {
+#pragma unroll
+        for (int hh = 0; hh < HS; ++hh)
+#pragma unroll
+          for (int c = 0; c < M; ++c) vsh[((qi * HS + hh) * M + c) * EPW] = Vown[hh][c];
+      }
+    } else {
     {
       float v[H][M];
 #pragma unroll
@@ -436,6 +638,8 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
 #pragma unroll
       for (int c = 0; c < M; ++c) mw[c] = __shfl_sync(FULL, Vown[HS - 1][c], lane | 2);   // V[H-1] lives in the upper tap half
     }
+    }
+    if constexpr (INCR) load_G(G);                                    // (after the correction block: 75 registers)
     float u[M];
 #pragma unroll
     for (int c = 0; c < M; ++c) u[c] = mw[c] - kx[c];                 // get_action              _gpc.py:171-183
@@ -549,6 +753,7 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
     B_acc(mw, z);
 #pragma unroll
     for (int kk = 0; kk < DC; ++kk) xr[kk] = z[kk] + wt[kk];
+    cb = (cb + 1 == H) ? 0 : cb + 1;
     }  // t < T
   }
 
@@ -592,13 +797,14 @@ __global__ void __launch_bounds__(TPB, MINB) lds_gpc_quad_kernel(const LdsArgs a
   }
 }
 
-template <int D, int M, int H, int TPB, int MINB, int WSRC>
+template <int D, int M, int H, int TPB, int MINB, int WSRC, bool INCR>
 static int32_t launch_quad_w(const LdsArgs& a, cudaStream_t st, bool one_cta_per_sm = false) {
   using Lay = QuadLayout<D, M, H, TPB>;
-  static_assert((Lay::kSmemBytes + 1024) * MINB <= 228 * 1024, "ring + operators do not fit shared memory");
-  auto kern = lds_gpc_quad_kernel<D, M, H, TPB, MINB, WSRC>;
+  constexpr size_t kBytes = INCR ? Lay::kSmemBytesIncr : Lay::kSmemBytes;
+  static_assert((kBytes + 1024) * MINB <= 228 * 1024, "ring + operators do not fit shared memory");
+  auto kern = lds_gpc_quad_kernel<D, M, H, TPB, MINB, WSRC, INCR>;
   // (measurement only: asking for more than half of the SM's shared memory keeps a second CTA off the SM)
-  const size_t smem = one_cta_per_sm && Lay::kSmemBytes < 120 * 1024 ? 120 * 1024 : Lay::kSmemBytes;
+  const size_t smem = one_cta_per_sm && kBytes < 120 * 1024 ? 120 * 1024 : kBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_status(e, "cudaFuncSetAttribute(lds_gpc_quad)");
   const int64_t threads = a.p.N * 4;
@@ -607,23 +813,36 @@ static int32_t launch_quad_w(const LdsArgs& a, cudaStream_t st, bool one_cta_per
   return cuda_status(cudaGetLastError(), "lds_gpc_quad_kernel launch");
 }
 
-template <int D, int M, int H, int TPB, int MINB>
+template <int D, int M, int H, int TPB, int MINB, bool INCR = false>
 static int32_t launch_quad(const LdsArgs& a, cudaStream_t st, bool one_cta_per_sm = false) {
-  return a.W ? launch_quad_w<D, M, H, TPB, MINB, 1>(a, st, one_cta_per_sm)
-             : launch_quad_w<D, M, H, TPB, MINB, 2>(a, st, one_cta_per_sm);
+  return a.W ? launch_quad_w<D, M, H, TPB, MINB, 1, INCR>(a, st, one_cta_per_sm)
+             : launch_quad_w<D, M, H, TPB, MINB, 2, INCR>(a, st, one_cta_per_sm);
 }
 
-// kernel_variant 0 (automatic) or 13..16 (launch shapes 128 x 2, 64 x 4, 256 x 1, 128 x 1)
+// DLC_QUAD_INCR=1 makes kernel_variant 0 the incremental-window kernel (variant 17) instead of the direct one (13).
+// Measured (B200, 262,144 envs x 1000 steps): the incremental form executes 27 % fewer FMA-pipe cycles but MORE
+// instructions (ring addressing, lane-role selects, extra shared-memory traffic) and is slower, so it is not the default.
+static bool quad_incr_default() {
+  static const bool on = [] { const char* e = getenv("DLC_QUAD_INCR"); return e && atoi(e) != 0; }();
+  return on;
+}
+
+// kernel_variant 0 (automatic) or 13..16 (direct window products; launch shapes 128 x 2, 64 x 4, 256 x 1, 128 x 1)
+// or 17 (incremental window products, 128 x 2)
 bool launch_gpc_quad(const LdsArgs& a, cudaStream_t st, int32_t* rc) {
   const DlcLdsParams& p = a.p;
   if (p.policy != DLC_POLICY_GPC || p.mode != DLC_MODE_CLOSED_LOOP) return false;
-  if (!(p.kernel_variant == 0 || (p.kernel_variant >= 13 && p.kernel_variant <= 16))) return false;
+  if (!(p.kernel_variant == 0 || (p.kernel_variant >= 13 && p.kernel_variant <= 17))) return false;
   if (p.d == 10 && p.m == 3 && p.H == 10 && p.HH == 10) {
     switch (p.kernel_variant) {
       case 14: *rc = launch_quad<10, 3, 10, 64, 4>(a, st); break;
       case 15: *rc = launch_quad<10, 3, 10, 256, 1>(a, st); break;
       case 16: *rc = launch_quad<10, 3, 10, 128, 2>(a, st, true); break;   // one warp per scheduler (measurement only)
-      default: *rc = launch_quad<10, 3, 10, 128, 2>(a, st); break;
+      case 13: *rc = launch_quad<10, 3, 10, 128, 2>(a, st); break;
+      case 17: *rc = launch_quad<10, 3, 10, 128, 2, true>(a, st); break;
+      default:
+        *rc = quad_incr_default() ? launch_quad<10, 3, 10, 128, 2, true>(a, st) : launch_quad<10, 3, 10, 128, 2>(a, st);
+        break;
     }
     return true;
   }

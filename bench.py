@@ -152,6 +152,25 @@ def measure_fp32_peak(torch, dev):
     return out
 
 
+def bind_to_gpu_cpus(index):
+    """One process per GPU: run this rank's host thread -- and therefore first-touch its pinned staging buffers -- on the
+    CPUs NVML reports as closest to its GPU, so that the end-to-end leg's host <-> device copies do not cross the socket
+    interconnect when eight ranks copy at once.  Returns the number of CPUs bound to (None if NVML is unavailable)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, v in enumerate(mask) for b in range(64) if (int(v) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus) or None
+    except Exception:      # noqa: BLE001 -- binding is an optimisation, never a requirement
+        return None
+
+
 def host_cores():
     from oracle.lds_c import max_threads
     # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1, which omp_get_max_threads() obeys,
@@ -386,6 +405,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _abi.check(_abi.lib().dlc_check_device(), "dlc_check_device")
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout ahead of the JSON line
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -475,7 +495,7 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}},
             "e2e": {"value": n_tot * T / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "result_checksum": chk,
-                    "overlap": args.e2e_mode,
+                    "overlap": args.e2e_mode, "host_cpus_bound": numa,
                     "note": "per step: host A,B,K,x0 (pinned) -> device; fused rollout, disturbances drawn by the env "
                             "in the kernel (the reference's LDS draws its own noise too); the full losses[T,N] "
                             "(Rollout.losses) -> pinned host; the batch is cut into <= 16 env slices whose uploads, "

@@ -238,7 +238,7 @@ def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=N
     """The whole end-to-end job of a vmapped rollout whose systems live on the HOST: per-env ``A[N,d,d] B[N,d,m]
     K[N,m,d] x[N,d]`` in pinned host memory in, ``losses[T,N]`` (``Rollout.losses``, ``deluca/training/apg.py:68``) in
     pinned host memory out.  Episodes never interact (``apg.py:91``), so the batch is cut into ``slices`` env ranges
-    (default: up to 16, each a whole number (>= 4) of full waves of the rollout kernels' grids):
+    (default: up to 16, each a whole number of full waves of the rollout kernels' grids):
     slice k + 1's systems travel host -> device and slice k - 1's losses device -> host (one 2-D copy into columns
     [lo, hi) of ``host_costs``) while slice k's rollout runs -- every slice is ONE launch over the full horizon, so there
     is no carried agent state to write and re-read between launches (``lds_rollout_to_host`` cuts the horizon instead
@@ -265,11 +265,11 @@ def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=N
         kw.pop(k, None)
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if slices is None:
-        # whole waves of the rollout kernels' grids per slice (a CTA holds 32 envs, two CTAs per SM), at least four of
-        # them, at most 16 slices: a slice that ends mid-wave leaves SMs idle at its tail (measured on 8 GPUs, where
-        # a rank's 131,072 envs cut into four equal slices of 0.86 + 0.86 waves ran 4 wave-times for 3.5 waves of work)
+        # whole waves of the rollout kernels' grids per slice (a CTA holds 32 envs, two CTAs per SM), at most 16
+        # slices: a slice that ends mid-wave leaves SMs idle at its tail, and short slices start the downloads early
+        # and leave little of the last one exposed (which is what a rank of an 8-GPU job, 14 waves, is bound by)
         wave = 64 * torch.cuda.get_device_properties(dev).multi_processor_count
-        per = max(4 * wave, -(-N // (16 * wave)) * wave)
+        per = max(wave, -(-N // (16 * wave)) * wave)
         bounds = list(range(0, N, per)) + [N]
         if len(bounds) > 2 and N - bounds[-2] < wave:
             del bounds[-2]

@@ -401,8 +401,13 @@ def test_env_sliced_host_to_host_rollout_is_the_same_job():
     with pytest.raises(ValueError):
         copy_rows_async(host[:, ::2], dev[:, :20])
     d, m = 10, 3
-    for (H, HH), N, T, slices in (((10, 10), 1000, 40, 4), ((3, 10), 700, 60, 16), ((10, 10), 64, 12, 1)):
-        A, B, K, x0, _ = _problem(N, d, m, T, seed=31 + H, dense=True)
+    # (slices=None: the default cut into whole grid waves -- 64 envs per SM -- so 2.x waves make three slices)
+    wave = 64 * torch.cuda.get_device_properties(0).multi_processor_count
+    for (H, HH), N, T, slices in (((10, 10), 1000, 40, 4), ((3, 10), 700, 60, 16), ((10, 10), 64, 12, 1),
+                                  ((10, 10), 2 * wave + 1000, 6, None), ((3, 10), wave + 50, 5, None)):
+        A, B, K, x0, _ = _problem(min(N, 500), d, m, T, seed=31 + H, dense=True)
+        if N > 500:                                                  # (tiled: the DARE solves dominate otherwise)
+            A, B, K, x0 = (np.resize(a, (N,) + a.shape[1:]) for a in (A, B, K, x0))
         kw = dict(policy="gpc", H=H, HH=HH, lr_scale=1e-4, seed=5, w_std=0.5)
         whole = lds_rollout(_dev(A), _dev(B), _dev(K), _dev(x0), T, env_offset=77, **kw)
         pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).pin_memory()

@@ -174,6 +174,8 @@ SYMBOLS = {
     "dlc_lds_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(DlcLdsParams)]),
     "dlc_lds_rollout_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 18
                             + [_P, ctypes.c_size_t, _P]),
+    "dlc_lds_rollout_cost_f32": (ctypes.c_int32, [ctypes.POINTER(DlcLdsParams)] + [_P] * 16
+                                 + [_P, ctypes.c_size_t, _P]),
 }
 
 

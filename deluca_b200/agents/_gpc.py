@@ -29,8 +29,16 @@ class GPCState(Obj):
 class GPC(Agent):
     def __init__(self, A, B, Q=None, R=None, K=None, start_time=0, cost_fn=None, H=3, HH=2, lr_scale=0.005,
                  decay=True, noise_uses_prev_action=False, device=None):
+        # cost_fn (_gpc.py:52,76): quad_loss, or a diagonal quadratic QuadCost(goal = 0, q, r) -- the family the fused
+        # kernels seed their hand adjoint with (dlc_lds_rollout_cost_f32)
+        self.cost_q = self.cost_r = None
         if cost_fn is not None and cost_fn is not quad_loss:
-            raise NotImplementedError("the fused kernel implements the reference's default quad_loss only")
+            from ..envs.classic._pendulum import QuadCost
+            goal = getattr(cost_fn, "goal", None)
+            if (not isinstance(cost_fn, QuadCost) or cost_fn.goal_action is not None
+                    or (goal is not None and any(float(g) != 0.0 for g in goal))):
+                raise NotImplementedError("the fused kernels take cost_fn = quad_loss or a diagonal quadratic "
+                                          "QuadCost(goal=None or zeros, q, r) without an action goal")
         # numpy / CPU inputs (how the reference is normally called) are moved to the device once, here
         dev = torch.device(device) if device is not None else (
             A.device if isinstance(A, torch.Tensor) and A.is_cuda else torch.device("cuda"))
@@ -43,6 +51,9 @@ class GPC(Agent):
         self.noise_uses_prev_action = noise_uses_prev_action
         self.bias = 0
         self.K = as_t(K) if K is not None else LQR(self.A, self.B, as_t(Q), as_t(R)).K      # _gpc.py:93
+        if cost_fn is not None and cost_fn is not quad_loss:
+            ex = lambda v, n: torch.tensor([float(x) for x in (v if hasattr(v, "__len__") else [v] * n)], device=dev)
+            self.cost_q, self.cost_r = ex(cost_fn.q, self.d_state), ex(cost_fn.r, self.d_action)
         st = self.init(1, device=dev)
         self.M = st.M[0]
         self.noise_history = st.noise_history[0].unsqueeze(-1)
@@ -66,7 +77,7 @@ class GPC(Agent):
                               H=self.H, HH=self.HH, M=st.M, hist=st.noise_history, xprev=st.state,
                               uprev=st.action, t0=st.t, lr_scale=self.lr_scale, decay=self.decay,
                               noise_uses_prev_action=self.noise_uses_prev_action, agent_only=True, traj_stride=1,
-                              keep_costs=False)
+                              keep_costs=False, cost_q=self.cost_q, cost_r=self.cost_r)
         new = GPCState(M=r.M, noise_history=r.hist, state=r.xprev, action=r.uprev, t=st.t + 1)
         new.freeze()
         return new, r.U[0]

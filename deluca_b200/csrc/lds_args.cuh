@@ -14,6 +14,9 @@ struct LdsArgs {
   float *x_out, *u_out;
   int32_t* status_out;
   float* ws;
+  // GPC's cost_fn as a diagonal quadratic sum(q x^2) + sum(r u^2) (deluca/agents/_gpc.py:52,76,125); NULL = ones
+  // (quad_loss).  Shared by all envs; only the lane-group kernel reads them (dlc_lds_rollout_cost_f32).
+  const float *cost_q = nullptr, *cost_r = nullptr;
 };
 
 // packed-FFMA2 lane-split GPC kernel (lds_rollout_f2.cu).  Returns false if (d,m,H,HH) has no instantiation.

@@ -187,7 +187,10 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : 2) lds_gpc_group_kernel(co
       mv<GL, false>(sK, sy, m, d, gl, r);
 #pragma unroll
       for (int k = 0; k < 2; ++k)
-        if (gl + k * GL < m) sdu[gl + k * GL] = 2.0f * (sv[gl + k * GL] - r[k]);   // dL/du_f
+        if (gl + k * GL < m) {                                                    // dL/du_f = 2 r (.) u_f
+          const float wr = a.cost_r ? 2.0f * __ldg(a.cost_r + gl + k * GL) : 2.0f;
+          sdu[gl + k * GL] = wr * (sv[gl + k * GL] - r[k]);
+        }
     }
     __syncwarp();
     {
@@ -195,7 +198,10 @@ __global__ void __launch_bounds__(256, GL == 32 ? 4 : 2) lds_gpc_group_kernel(co
       mvt<GL, false>(sK, sdu, m, d, gl, r);   // K' du
 #pragma unroll
       for (int k = 0; k < 2; ++k)
-        if (gl + k * GL < d) slam[gl + k * GL] = 2.0f * sy[gl + k * GL] - r[k];
+        if (gl + k * GL < d) {                                                    // lam = 2 q (.) y_f - K' du
+          const float wq = a.cost_q ? 2.0f * __ldg(a.cost_q + gl + k * GL) : 2.0f;
+          slam[gl + k * GL] = wq * sy[gl + k * GL] - r[k];
+        }
     }
     // adjoint, M updated in place (the backward pass never reads M): M[i][c][:] -= lr du[c] hist[fstart + i][:]
     auto rank1 = [&](int start, const float* coef) {

@@ -646,10 +646,10 @@ __global__ void __launch_bounds__(128) lds_generic_kernel(const LdsArgs a) {
       for (int c = 0; c < m; ++c) {
         float s = 0.f;
         for (int j = 0; j < d; ++j) s = fmaf(K[c * d + j], V(oY, j), s);
-        V(oDU, c) = 2.0f * (V(oV, c) - s);  // dL/du_f
+        V(oDU, c) = (a.cost_r ? 2.0f * __ldg(a.cost_r + c) : 2.0f) * (V(oV, c) - s);  // dL/du_f = 2 r (.) u_f
       }
       for (int i = 0; i < d; ++i) {
-        float s = 2.0f * V(oY, i);
+        float s = (a.cost_q ? 2.0f * __ldg(a.cost_q + i) : 2.0f) * V(oY, i);             // 2 q (.) y_f
         for (int c = 0; c < m; ++c) s = fmaf(-K[c * d + i], V(oDU, c), s);
         V(oLAM, i) = s;
       }
@@ -930,14 +930,15 @@ extern "C" int32_t dlc_gaussian_disturbance_f32(float* W, int64_t N, int32_t T, 
   return cuda_status(cudaGetLastError(), "gaussian_disturbance_kernel launch");
 }
 
-extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, const float* B,
-                                       const float* K, const float* W, const float* u_in, float* x_io,
-                                       float* M_io,
-                                       float* hist_io, float* xprev_io, float* uprev_io,
-                                       float* bpc_eps_io, const float* bpc_eps_new,
-                                       float* bpc_cost_io, float* cost_out, double* cost_sum_out,
-                                       float* x_out, float* u_out, int32_t* status_out,
-                                       void* workspace, size_t workspace_bytes, void* stream) {
+static int32_t lds_rollout_impl(const DlcLdsParams* p, const float* A, const float* B,
+                                const float* K, const float* W, const float* u_in, float* x_io,
+                                float* M_io,
+                                float* hist_io, float* xprev_io, float* uprev_io,
+                                float* bpc_eps_io, const float* bpc_eps_new,
+                                float* bpc_cost_io, float* cost_out, double* cost_sum_out,
+                                float* x_out, float* u_out, int32_t* status_out,
+                                void* workspace, size_t workspace_bytes, void* stream,
+                                const float* cost_q, const float* cost_r) {
   if (!p) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: params is NULL");
   if (p->N < 0 || p->T < 0) return fail(DLC_ERR_ARG, "dlc_lds_rollout_f32: negative N or T");
   if (p->d <= 0 || p->m <= 0) return fail(DLC_ERR_SHAPE, "dlc_lds_rollout_f32: d and m must be positive");
@@ -973,12 +974,24 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
   a.status_out = status_out; a.ws = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   int32_t rc = DLC_OK;
-  if (launch_bpc(a, bpc_cost_io, st, &rc)) return rc;
-  if (launch_lqr_reg(a, st, &rc)) return rc;
-  if (launch_gpc_quad(a, st, &rc)) return rc;
-  if (try_split(a, st, &rc)) return rc;
+  const bool weighted = cost_q || cost_r;
+  if (weighted) {
+    // a caller's cost_fn only enters GPC's update (_gpc.py:125,128): the lane-group kernel (closed loop, any d, m <= 64)
+    // and the runtime-dims kernel (everything else, incl. single Agent.__call__ steps) read the weights
+    if (p->policy != DLC_POLICY_GPC)
+      return fail(DLC_ERR_ARG, "dlc_lds_rollout_cost_f32: cost weights apply to GPC only");
+    a.cost_q = cost_q; a.cost_r = cost_r;
+  }
+  if (!weighted) {
+    if (launch_bpc(a, bpc_cost_io, st, &rc)) return rc;
+    if (launch_lqr_reg(a, st, &rc)) return rc;
+    if (launch_gpc_quad(a, st, &rc)) return rc;
+    if (try_split(a, st, &rc)) return rc;
+  }
   if (launch_gpc_group(a, st, &rc)) return rc;
-  if (!workspace || workspace_bytes < dlc_lds_workspace_bytes(p))
+  DlcLdsParams sized = *p;
+  if (weighted) sized.kernel_variant = 1;   // (a weighted call never runs the compile-time-shape kernels)
+  if (!workspace || workspace_bytes < dlc_lds_workspace_bytes(&sized))
     return fail(DLC_ERR_WORKSPACE, "dlc_lds_rollout_f32: this shape runs the runtime-dims kernel and needs "
                                    "dlc_lds_workspace_bytes() of workspace");
   const unsigned grid = (unsigned)((p->N + 127) / 128);
@@ -1014,4 +1027,28 @@ extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, co
     }
   }
   return cuda_status(cudaGetLastError(), "lds_generic_kernel launch");
+}
+
+extern "C" int32_t dlc_lds_rollout_f32(const DlcLdsParams* p, const float* A, const float* B,
+                                       const float* K, const float* W, const float* u_in, float* x_io,
+                                       float* M_io,
+                                       float* hist_io, float* xprev_io, float* uprev_io,
+                                       float* bpc_eps_io, const float* bpc_eps_new,
+                                       float* bpc_cost_io, float* cost_out, double* cost_sum_out,
+                                       float* x_out, float* u_out, int32_t* status_out,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  return lds_rollout_impl(p, A, B, K, W, u_in, x_io, M_io, hist_io, xprev_io, uprev_io, bpc_eps_io, bpc_eps_new,
+                          bpc_cost_io, cost_out, cost_sum_out, x_out, u_out, status_out, workspace, workspace_bytes,
+                          stream, nullptr, nullptr);
+}
+
+extern "C" int32_t dlc_lds_rollout_cost_f32(const DlcLdsParams* p, const float* A, const float* B, const float* K,
+                                            const float* W, float* x_io, float* M_io, float* hist_io,
+                                            float* xprev_io, float* uprev_io, const float* cost_q,
+                                            const float* cost_r, float* cost_out, double* cost_sum_out,
+                                            float* x_out, float* u_out, int32_t* status_out, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  return lds_rollout_impl(p, A, B, K, W, nullptr, x_io, M_io, hist_io, xprev_io, uprev_io, nullptr, nullptr, nullptr,
+                          cost_out, cost_sum_out, x_out, u_out, status_out, workspace, workspace_bytes, stream, cost_q,
+                          cost_r);
 }

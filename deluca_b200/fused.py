@@ -56,7 +56,7 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
                 uprev=None, eps=None, eps_new=None, bpc_cost=None, t0=0, lr_scale=0.005, decay=True,
                 noise_uses_prev_action=False, w_std=0.5, seed=0, env_offset=0, bpc_delta=0.01,
                 keep_costs=True, traj_stride=0, kernel_variant=0, donate=False, u_in=None, agent_only=False,
-                env_t0=None):
+                env_t0=None, cost_q=None, cost_r=None):
     """T fused steps of LDS + LQR/GPC/BPC for N envs (``dlc_lds_rollout_f32``).
 
     A[N,d,d] B[N,d,m] K[N,m,d] (or unbatched = shared by all envs), x[N,d].  State tensors
@@ -67,6 +67,8 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
     ``traj_stride`` > 0, sampled trajectories X[T,Ns,d], U[T,Ns,m] of every ``traj_stride``-th env.
     ``t0`` is the AGENT's step counter (lr decay, BPC perturbation counter), ``env_t0`` the ENV's (``LDS.t``: the
     counter of the in-kernel disturbance stream; defaults to ``t0``).
+    ``cost_q[d]`` / ``cost_r[m]``: GPC's ``cost_fn`` as a diagonal quadratic ``sum(q x^2) + sum(r u^2)``
+    (``deluca/agents/_gpc.py:52,76,125``; ``dlc_lds_rollout_cost_f32``); the reported costs stay ``quad_loss``.
     """
     lib = _abi.lib()
     _f32(x, "x")
@@ -114,6 +116,27 @@ def lds_rollout(A, B, K, x, T, *, policy="gpc", W=None, H=3, HH=2, M=None, hist=
                           env_t0=int(t0 if env_t0 is None else env_t0))
     ws_bytes = lib.dlc_lds_workspace_bytes(ctypes.byref(p))
     ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=torch.float32, device=dev)
+    if cost_q is not None or cost_r is not None:
+        if policy != "gpc":
+            raise ValueError("cost_q / cost_r weight GPC's cost_fn")
+        cq = None if cost_q is None else _f32(torch.as_tensor(cost_q, dtype=torch.float32, device=dev).contiguous(),
+                                              "cost_q", (d,))
+        cr = None if cost_r is None else _f32(torch.as_tensor(cost_r, dtype=torch.float32, device=dev).contiguous(),
+                                              "cost_r", (m,))
+        sized = _abi.DlcLdsParams.from_buffer_copy(p)             # (workspace as for the runtime-dims kernel)
+        sized.kernel_variant = 1
+        nb = lib.dlc_lds_workspace_bytes(ctypes.byref(sized))
+        if nb > ws.numel() * 4:
+            ws = torch.empty((nb // 4 + 1,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.dlc_lds_rollout_cost_f32(ctypes.byref(p), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K), _abi.ptr(W),
+                                              _abi.ptr(x_io), _abi.ptr(M_io), _abi.ptr(hist_io), _abi.ptr(xprev_io),
+                                              _abi.ptr(uprev_io), _abi.ptr(cq), _abi.ptr(cr), _abi.ptr(costs),
+                                              _abi.ptr(cost_sum), _abi.ptr(X), _abi.ptr(U), _abi.ptr(status),
+                                              _abi.ptr(ws), ws.numel() * 4, _abi.current_stream_ptr())
+        _abi.check(rc, "dlc_lds_rollout_cost_f32")
+        return LdsRolloutResult(costs=costs, cost_sum=cost_sum, x=x_io, M=M_io, hist=hist_io, xprev=xprev_io,
+                                uprev=uprev_io, eps=None, bpc_cost=None, status=status, X=X, U=U, t=t0 + T)
     with torch.cuda.device(dev):
         rc = lib.dlc_lds_rollout_f32(ctypes.byref(p), _abi.ptr(A), _abi.ptr(B), _abi.ptr(K), _abi.ptr(W), _abi.ptr(u_in),
                                      _abi.ptr(x_io), _abi.ptr(M_io), _abi.ptr(hist_io), _abi.ptr(xprev_io),

@@ -187,7 +187,8 @@ def apg_parallel_rollouts(env, env_start_states, env_init_obs, agent, agent_star
         s = agent_start_states
         r = fused.lds_rollout(env.A, env.B, agent.K.to(x.device), x, T, policy="gpc", H=agent.H, HH=agent.HH, M=s.M,
                               hist=s.noise_history, xprev=s.state, uprev=s.action, t0=s.t, lr_scale=agent.lr_scale,
-                              decay=agent.decay, noise_uses_prev_action=agent.noise_uses_prev_action, **common)
+                              decay=agent.decay, noise_uses_prev_action=agent.noise_uses_prev_action,
+                              cost_q=agent.cost_q, cost_r=agent.cost_r, **common)
         final = GPCState(M=r.M, noise_history=r.hist, state=r.xprev, action=r.uprev, t=s.t + T)
     elif isinstance(agent, BPC):
         s = agent_start_states

@@ -147,6 +147,20 @@ int32_t dlc_lds_rollout_f32(
     int32_t* status_out,  /* [N]     DLC_STATUS_* bit flags, or NULL */
     void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same closed-loop LDS + GPC rollout with a caller's cost_fn in the controller's update: GPC.__init__ takes
+ * cost_fn (deluca/agents/_gpc.py:52,76) and learns from policy_loss = cost_fn(y_f, u_f) (:125,128).  The family taken here
+ * is the diagonal quadratic cost_fn(x, u) = sum_k q_k x_k^2 + sum_c r_c u_c^2: cost_q [d] and cost_r [m] are device
+ * arrays shared by all envs (NULL = ones, i.e. quad_loss), seeding the hand adjoint with dL/du_f = 2 r (.) u_f and
+ * lam = 2 q (.) y_f - K' dL/du_f.  cost_out / cost_sum_out remain the realised quad_loss(x_t, u_t) (a re-weighted
+ * report is the caller's loss_func, deluca/training/apg.py:54).  p->policy must be DLC_POLICY_GPC.  Runs the lane-group
+ * kernel (closed loop, d <= 64, m <= 64) or the runtime-dims kernel (any shape, single Agent.__call__ steps), which
+ * needs dlc_lds_workspace_bytes() of workspace -- allocate it as if p->kernel_variant were 1.  Other arguments as above. */
+int32_t dlc_lds_rollout_cost_f32(const DlcLdsParams* p, const float* A, const float* B, const float* K,
+                                 const float* W, float* x_io, float* M_io, float* hist_io, float* xprev_io,
+                                 float* uprev_io, const float* cost_q, const float* cost_r, float* cost_out,
+                                 double* cost_sum_out, float* x_out, float* u_out, int32_t* status_out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Reverse mode through the LDS rollout: value and gradient of
  *     loss_n = sum_{t<T} quad_loss(x_t, u_t),  u_t = -K x_t,  x_{t+1} = A x_t + B u_t + w_t

@@ -67,10 +67,11 @@ def _window(w, start, size):
     return w[:, start:start + size]
 
 
-def gpc_policy_loss(M, w, A, B, K, H, HH):
+def gpc_policy_loss(M, w, A, B, K, H, HH, cost_q=None, cost_r=None):
     """``policy_loss`` (``deluca/agents/_gpc.py:109-125``), literal forward restatement.
 
-    M[N,H,m,d], w[N,H+HH,d] oldest -> newest.  Returns loss[N]."""
+    M[N,H,m,d], w[N,H+HH,d] oldest -> newest.  Returns loss[N].  ``cost_q[d]`` / ``cost_r[m]`` stand for a caller's
+    diagonal quadratic ``cost_fn(x, u) = sum(q x^2) + sum(r u^2)`` (``_gpc.py:52,76``); None is ``quad_loss``."""
     N, P, d = w.shape
 
     def action(state, h):                                     # _gpc.py:112-116
@@ -82,10 +83,15 @@ def gpc_policy_loss(M, w, A, B, K, H, HH):
         idx = min(h + H, P - 1)                               # traced scalar index clamps
         y = (np.einsum("nij,nj->ni", A, y)
              + np.einsum("nij,nj->ni", B, action(y, h))) + w[:, idx]
-    return quad_loss(y, action(y, HH - 1))                    # _gpc.py:125
+    u = action(y, HH - 1)
+    if cost_q is None and cost_r is None:
+        return quad_loss(y, u)                                # _gpc.py:125
+    q = np.ones(d, M.dtype) if cost_q is None else np.asarray(cost_q, M.dtype)
+    r = np.ones(u.shape[1], M.dtype) if cost_r is None else np.asarray(cost_r, M.dtype)
+    return (q * y * y).sum(1) + (r * u * u).sum(1)
 
 
-def gpc_grad(M, w, A, B, K, H, HH):
+def gpc_grad(M, w, A, B, K, H, HH, cost_q=None, cost_r=None):
     """dM of ``policy_loss`` -- the hand-derived adjoint the kernels implement
     (SURVEY A-3.5; checked against torch.autograd and finite differences in
     tests/test_oracle_lds.py).  Replaces ``jit(grad(policy_loss, (0, 1)))``
@@ -105,9 +111,9 @@ def gpc_grad(M, w, A, B, K, H, HH):
     u_f = -mv(K, y) + np.einsum("nhij,nhj->ni", M, wf)
 
     G = np.zeros_like(M)
-    du = 2 * u_f
+    du = 2 * u_f if cost_r is None else 2 * np.asarray(cost_r, M.dtype) * u_f
     G += np.einsum("ni,nhj->nhij", du, wf)
-    lam = 2 * y - mtv(K, du)
+    lam = (2 * y if cost_q is None else 2 * np.asarray(cost_q, M.dtype) * y) - mtv(K, du)
     for h in range(H - 2, -1, -1):
         lam_u = mtv(B, lam)
         G += np.einsum("ni,nhj->nhij", lam_u, _window(w, h, H))
@@ -125,7 +131,8 @@ def gpc_init(N, d, m, H, HH, dtype=np.float32):
                 t=0)
 
 
-def gpc_call(st, x, A, B, K, H, HH, lr_scale=0.005, decay=True, noise_uses_prev_action=False):
+def gpc_call(st, x, A, B, K, H, HH, lr_scale=0.005, decay=True, noise_uses_prev_action=False, cost_q=None,
+             cost_r=None):
     """``GPC.__call__`` = ``get_action`` then ``update`` (``_gpc.py:130-183``).  Mutates ``st``.
 
     ``noise_uses_prev_action=False`` is the reference as written: the disturbance estimate
@@ -141,7 +148,7 @@ def gpc_call(st, x, A, B, K, H, HH, lr_scale=0.005, decay=True, noise_uses_prev_
     u_n = st.get("uprev", np.zeros_like(u)) if noise_uses_prev_action else u
     noise = x - np.einsum("nij,nj->ni", A, st["xprev"]) - np.einsum("nij,nj->ni", B, u_n)
     hist = np.concatenate([hist[:, 1:], noise[:, None, :]], axis=1)   # .at[0].set; roll(-1)
-    G = gpc_grad(M, hist, A, B, K, H, HH)
+    G = gpc_grad(M, hist, A, B, K, H, HH, cost_q, cost_r)
     lr = dtype.type(lr_scale)
     if decay:
         lr = dtype.type(lr_scale * (1.0 / (st["t"] + 1)))
@@ -194,7 +201,7 @@ def bpc_call(st, x, cost, eps_new, A, B, K, H, lr_scale=0.005, decay=False, delt
 # --------------------------------------------------------------------------- rollouts
 def rollout_lds(A, B, K, x0, W, policy="gpc", H=3, HH=10, lr_scale=0.005, decay=True,
                 state=None, bpc_eps=None, bpc_delta=0.01, dtype=np.float32, keep_x=True,
-                noise_uses_prev_action=False):
+                noise_uses_prev_action=False, cost_q=None, cost_r=None):
     """The episode loop of SURVEY S2 (driver notebook missing from the snapshot; restated
     from the class APIs): per step  u = agent(x);  cost_t = quad_loss(x, u);
     x <- A x + B u + w_t.
@@ -202,7 +209,8 @@ def rollout_lds(A, B, K, x0, W, policy="gpc", H=3, HH=10, lr_scale=0.005, decay=
     policy: "gpc" | "lqr" (u = -K x, no learning) | "bpc" (``bpc_eps`` [T,N,H,m,d] gives
     the fresh perturbations; the cost handed to BPC at step t is the cost realised at
     step t-1, 0 at the first step -- a stated choice, the reference driver is missing).
-    W[T,N,d].  Returns dict(costs[T,N], X[T+1,N,d] if keep_x, x_final, state)."""
+    W[T,N,d].  ``cost_q`` / ``cost_r``: GPC's ``cost_fn`` as a diagonal quadratic (see ``gpc_policy_loss``); the
+    realised ``costs`` stay ``quad_loss``.  Returns dict(costs[T,N], X[T+1,N,d] if keep_x, x_final, state)."""
     A, B, K = A.astype(dtype), B.astype(dtype), K.astype(dtype)
     x = x0.astype(dtype).copy()
     W = W.astype(dtype)
@@ -222,7 +230,7 @@ def rollout_lds(A, B, K, x0, W, policy="gpc", H=3, HH=10, lr_scale=0.005, decay=
     prev_cost = np.zeros(N, dtype=dtype)
     for t in range(T):
         if policy == "gpc":
-            u = gpc_call(state, x, A, B, K, H, HH, lr_scale, decay, noise_uses_prev_action)
+            u = gpc_call(state, x, A, B, K, H, HH, lr_scale, decay, noise_uses_prev_action, cost_q, cost_r)
         elif policy == "bpc":
             u = bpc_call(state, x, prev_cost, bpc_eps[t].astype(dtype), A, B, K, H,
                          lr_scale, decay, bpc_delta)

@@ -711,7 +711,63 @@ def family_lung_train():
     return both_precisions(run)
 
 
-FAMILIES = {"lung_train": family_lung_train, "lung_steps": family_lung_steps, "drivers": family_drivers, "of": family_of, "lds": family_lds, "lung": family_lung, "classic": family_classic, "igpc": family_igpc}
+def family_lds_cost():
+    """`GPC(cost_fn=...)` (deluca/agents/_gpc.py:52,76,125): the surrogate loss the controller learns from is a caller's
+    function of the counterfactual final state and action.  Run with a diagonal quadratic
+    `cost_fn(x, u) = sum(q x^2) + sum(r u^2)` -- the family the fused kernels take as `cost_q` / `cost_r` -- on recorded
+    disturbances, stepped like `family_lds`."""
+    import jax.numpy as jnp
+    from deluca.core import Disturbance
+    from deluca.envs._lds import LDS
+    from deluca.agents._gpc import GPC, quad_loss
+
+    class Replay(Disturbance):
+        def init(self, d):
+            self.d = d
+
+        def __call__(self, t, key):
+            return jnp.array(self.W[t].reshape(self.d, 1))
+
+    cases = [("h3", 10, 3, 3, 10, 1e-4, True, 60), ("h10", 10, 3, 10, 10, 1e-4, True, 50), ("d4", 4, 2, 5, 7, 2e-5, False, 50)]
+
+    def run():
+        out = {}
+        rng = np.random.default_rng(77)
+        N = 3
+        for name, d, m, H, HH, lr, decay, T in cases:
+            A, B = _lds_systems(rng, N, d, m)
+            W = 0.5 * rng.standard_normal((T, N, d))
+            q, r = rng.uniform(0.3, 3.0, d), rng.uniform(0.3, 3.0, m)
+            qc, rc = jnp.array(q.reshape(d, 1)), jnp.array(r.reshape(m, 1))
+            cost_fn = lambda x, u: jnp.sum(qc * x * x) + jnp.sum(rc * u * u)
+            costs = np.zeros((T, N)); X = np.zeros((T + 1, N, d)); U = np.zeros((T, N, m))
+            Ks = np.zeros((N, m, d)); Mf = np.zeros((N, H, m, d)); hist = np.zeros((N, H + HH, d))
+            for n in range(N):
+                dist = Replay()
+                dist.W = W[:, n]
+                env = LDS()
+                x = env.init(d_in=m, d_hidden=d, d_out=d, A=A[n], B=B[n], C=np.eye(d), disturbance=dist)
+                agent = GPC(jnp.array(A[n]), jnp.array(B[n]), cost_fn=cost_fn, H=H, HH=HH, lr_scale=lr, decay=decay)
+                Ks[n] = npf(agent.K)
+                for t in range(T):
+                    X[t, n] = npf(x).ravel()
+                    u = agent(x)
+                    costs[t, n] = float(quad_loss(x, u))             # the realised (unweighted) cost, as in family_lds
+                    U[t, n] = npf(u).ravel()
+                    env(u)
+                    x = env.x
+                X[T, n] = npf(x).ravel()
+                Mf[n], hist[n] = npf(agent.M), npf(agent.noise_history)[:, :, 0]
+            out.update({f"in_{name}_A": A, f"in_{name}_B": B, f"in_{name}_W": W, f"in_{name}_q": q, f"in_{name}_r": r,
+                        f"in_{name}_cfg": np.array([d, m, H, HH, lr, float(decay), T]),
+                        f"out_{name}_K": Ks, f"out_{name}_costs": costs, f"out_{name}_X": X, f"out_{name}_U": U,
+                        f"out_{name}_M": Mf, f"out_{name}_hist": hist})
+        return out
+
+    return both_precisions(run)
+
+
+FAMILIES = {"lds_cost": family_lds_cost, "lung_train": family_lung_train, "lung_steps": family_lung_steps, "drivers": family_drivers, "of": family_of, "lds": family_lds, "lung": family_lung, "classic": family_classic, "igpc": family_igpc}
 
 
 def main():

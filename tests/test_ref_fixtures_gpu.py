@@ -404,3 +404,45 @@ def test_lung_value_and_grad_kernel_matches_reference_files(name, T, kw):
                 assert abs(float(v1) - rv) <= max(ltol * abs(rv), yard_l)
                 assert np.abs(_np(g1) - rgm).max() <= max(2e-3 * gscale, yard_g)
     assert seen >= 1
+
+
+# ------------------------------------------------------------------------------------------ GPC with a caller's cost_fn
+@pytest.mark.parametrize("case", ["h3", "h10", "d4"])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_gpc_weighted_cost_fn_kernels_match_reference_files(case, variant):
+    """`GPC(cost_fn=...)` with a diagonal quadratic cost executed literally (fixture family `lds_cost`,
+    deluca/agents/_gpc.py:52,76,125) vs `dlc_lds_rollout_cost_f32`: the lane-group kernel (variant 0) and the
+    runtime-dims kernel (variant 1), and the stateful single-step face `agent(x)` of the mirror."""
+    from deluca_b200.fused import lds_rollout
+    g = _load("lds_cost")
+    d, m, H, HH, lr, decay, T = g[f"in_{case}_cfg"]
+    d, m, H, HH, T = int(d), int(m), int(H), int(HH), int(T)
+    A, B, W, K = g[f"in_{case}_A"], g[f"in_{case}_B"], g[f"in_{case}_W"], g[f"out_{case}_K"]
+    q, r_ = g[f"in_{case}_q"], g[f"in_{case}_r"]
+    N = A.shape[0]
+    r = lds_rollout(_t(A), _t(B), _t(K), torch.zeros(N, d, device="cuda"), T, policy="gpc", W=_t(W), H=H, HH=HH,
+                    lr_scale=float(lr), decay=bool(decay), traj_stride=1, kernel_variant=variant, cost_q=_t(q),
+                    cost_r=_t(r_))
+    _within(r.costs, g[f"out_{case}_costs"], RTOL, what="costs")
+    _within(r.U, g[f"out_{case}_U"], RTOL, floor=np.abs(g[f"out_{case}_U"]).mean(), what="U")
+    _within(r.x, g[f"out_{case}_X"][T], RTOL, floor=np.abs(g[f"out_{case}_X"]).mean(), what="x_final")
+    _within(r.M, g[f"out_{case}_M"], 10 * RTOL, floor=np.abs(g[f"out_{case}_M"]).max() * 1e-1, what="M")
+    # the weights reach the update: the plain quad_loss kernel ends at a different policy tensor
+    plain = lds_rollout(_t(A), _t(B), _t(K), torch.zeros(N, d, device="cuda"), T, policy="gpc", W=_t(W), H=H, HH=HH,
+                        lr_scale=float(lr), decay=bool(decay))
+    assert float((plain.M - r.M).abs().max()) > 1e-3 * float(r.M.abs().max())
+    if variant == 0 and case == "d4":
+        # the reference's stateful API, one env: u = agent(x); x = A x + B u + w
+        from deluca_b200.agents._gpc import GPC
+        from deluca_b200.envs.classic._pendulum import QuadCost
+        agent = GPC(A[0], B[0], K=K[0], cost_fn=QuadCost(None, q.tolist(), r_.tolist()), H=H, HH=HH,
+                    lr_scale=float(lr), decay=bool(decay))
+        x = np.zeros(d)
+        for t in range(T):
+            u = agent(x.reshape(d, 1)).cpu().numpy().reshape(m).astype(np.float64)
+            np.testing.assert_allclose(u, g[f"out_{case}_U"][t, 0], rtol=5e-4, atol=1e-4 * np.abs(g[f"out_{case}_U"]).mean())
+            x = A[0] @ x + B[0] @ u + W[t, 0]
+        _within(agent.M.unsqueeze(0), g[f"out_{case}_M"][:1], 10 * RTOL, floor=np.abs(g[f"out_{case}_M"]).max() * 1e-1,
+                what="M (stateful face)")
+    with pytest.raises(ValueError):
+        lds_rollout(_t(A), _t(B), _t(K), torch.zeros(N, d, device="cuda"), 2, policy="lqr", W=_t(W[:2]), cost_q=_t(q))

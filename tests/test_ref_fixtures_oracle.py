@@ -368,3 +368,23 @@ def test_lung_train_oracle_equals_reference_files(sim, name, T, kw):
     assert seen >= 1
     if name == "delay" and T == 29:       # the action cannot reach the pressure before 25 s: exact zeros
         assert not g["out_delay_T29_l1_n0_grad"].any() and not g["out_delay_T29_l1_n0_grad_f32"].any()
+
+
+@pytest.mark.parametrize("case", ["h3", "h10", "d4"])
+def test_gpc_weighted_cost_fn_oracle_equals_reference_file(case):
+    """`GPC(cost_fn=...)` with a diagonal quadratic cost (deluca/agents/_gpc.py:52,76,125) executed literally
+    (fixture family `lds_cost`) vs oracle/lds.py's `cost_q` / `cost_r`: float64 to rounding."""
+    g = _load("lds_cost")
+    d, m, H, HH, lr, decay, T = g[f"in_{case}_cfg"]
+    d, m, H, HH, T = int(d), int(m), int(H), int(HH), int(T)
+    A, B, W, K = g[f"in_{case}_A"], g[f"in_{case}_B"], g[f"in_{case}_W"], g[f"out_{case}_K"]
+    ref = O.rollout_lds(A, B, K, np.zeros((A.shape[0], d)), W, "gpc", H=H, HH=HH, lr_scale=lr, decay=bool(decay),
+                        dtype=np.float64, cost_q=g[f"in_{case}_q"], cost_r=g[f"in_{case}_r"])
+    scale = np.abs(g[f"out_{case}_costs"]).max()
+    np.testing.assert_allclose(ref["costs"], g[f"out_{case}_costs"], rtol=1e-9, atol=1e-12 * scale)
+    np.testing.assert_allclose(ref["X"], g[f"out_{case}_X"], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(ref["state"]["M"], g[f"out_{case}_M"], rtol=1e-8, atol=1e-15)
+    # and the weights matter: the unweighted oracle ends at a different policy tensor
+    plain = O.rollout_lds(A, B, K, np.zeros((A.shape[0], d)), W, "gpc", H=H, HH=HH, lr_scale=lr, decay=bool(decay),
+                          dtype=np.float64)
+    assert np.abs(plain["state"]["M"] - g[f"out_{case}_M"]).max() > 1e-3 * np.abs(g[f"out_{case}_M"]).max()

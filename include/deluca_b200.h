@@ -111,7 +111,9 @@ typedef struct DlcLdsParams {
   int32_t kernel_variant; /* 0 = auto; 1 = force the runtime-dims kernel (testing); 2..7 = force a launch shape
                              of the lane-split kernel: (128 thr x 3 CTA/SM), (64x5), (64x7), (128x2), (32x7), (32x8);
                              8..12 = launch shapes of the packed-FFMA2 kernel (128x2, 128x3, 64x5, 32x9, 256x1);
-                             13..15 = launch shapes of the quad-split kernel for H = HH even (128x2, 64x4, 256x1) */
+                             13..16 = launch shapes of the quad-split kernel for H = HH even (128x2, 64x4, 256x1,
+                             128x1); 17 = the same kernel with incremental window products (measured slower, kept for
+                             cross-checks) */
   int32_t mode;        /* DLC_MODE_*: which half of the loop runs (single-step Env/Agent calls use 1 and 2) */
   uint64_t seed;       /* disturbance / perturbation stream seed */
   int32_t env_t0;      /* ENV step counter at entry (LDS.t, _lds.py:109): counter of the in-kernel disturbance stream.

@@ -292,7 +292,7 @@ def lds_rollout_host_to_host(A, B, K, x, T, host_costs, *, device=None, slices=N
         # slices: a slice that ends mid-wave leaves SMs idle at its tail, and short slices start the downloads early
         # and leave little of the last one exposed (which is what a rank of an 8-GPU job, 14 waves, is bound by)
         wave = 64 * torch.cuda.get_device_properties(dev).multi_processor_count
-        per = max(wave, -(-N // (16 * wave)) * wave)
+        per = max(wave, -(-N // (int(os.environ.get("DLC_E2E_MAX_SLICES", "16")) * wave)) * wave)
         bounds = list(range(0, N, per)) + [N]
         if len(bounds) > 2 and N - bounds[-2] < wave:
             del bounds[-2]

@@ -37,6 +37,10 @@ class DRC(Agent):
         self.m, self.h = m, h
         self.lr_scale, self.decay, self.RM, self.seed = lr_scale, decay, RM, int(seed)
         self.K = as_t(K).to(dev) if K is not None else torch.zeros(*self.A.shape[:-2], self.n, self.p, device=dev)
+        # the truncated response decays (|A^h B|_F <= |B|_F for every env): the kernel may carry sum_i G[i] us[i] as a
+        # d-vector recursion (DLC_OF_FLAG_STABLE_A; it re-checks the promise per env)
+        AhB = torch.linalg.matrix_power(self.A.double(), h) @ self.B.double()
+        self.stable_a = bool((AhB.flatten(-2).norm(dim=-1) <= 0.999 * self.B.double().flatten(-2).norm(dim=-1)).all())
         st = self.init(1)
         self.M, self.y_nat, self.us = st.M[0], st.y_nat[0].unsqueeze(-1), st.us[0].unsqueeze(-1)
 
@@ -62,7 +66,7 @@ class DRC(Agent):
 
     def _kw(self, st):
         return dict(agent="drc", K=self.K, theta=st.M, ynat=st.y_nat, us=st.us, m=self.m, h=self.h, t0=st.t,
-                    lr=self.lr_scale, decay=self.decay, R_M=float(self.RM))
+                    lr=self.lr_scale, decay=self.decay, R_M=float(self.RM), stable_a=self.stable_a)
 
     def step(self, st, obs):
         """update_noise, get_action, update_params for N envs (``_drc.py:131-149``)."""

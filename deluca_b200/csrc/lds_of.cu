@@ -1315,6 +1315,310 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
   if (a.status_out) a.status_out[env] = status;
 }
 
+// DRC on a small compile-time system, one THREAD per env (the caller's DLC_OF_FLAG_STABLE_A promise).  The as-written
+// agent contracts the truncated Markov operator with the action history twice a step, gu = sum_{i<h} (C A^i B) us[i]
+// (_drc.py:97-102,169,113): h p n = 300 multiply-adds on 450 operands that fit no register file.  Because
+// G[i] = C A^i B, gu = C s with s = sum_{i<h} A^i B us[i], and pushing u into the history moves s by
+//   s <- A s + B u - (A^h B) us[h-1]                  (the action that drops out of the window)
+// -- one d x d mat-vec, exact algebra, and a contraction of rounding errors exactly when the truncated response decays
+// (|A^h B| <= |B|, which is what the flag asserts and what the kernel verifies per env on entry: a broken promise
+// returns DLC_STATUS_BAD_HINT and a NaN cost sum, never wrong numbers).  s is re-formed from the stored history at
+// every call entry (Horner), so chunked calls do not carry the recursion's rounding along.  A, M (as Th[a][j p + q]),
+// the y_nat window, x and s live in registers; B, C, K, A^h B and the action ring in shared memory as [element][thread].
+template <int D, int NA, int P, int MH, int HH>
+struct DrcRegLayout {
+  static constexpr int oUs = 0, oB = oUs + HH * NA, oC = oB + D * NA, oAhB = oC + P * D, oK = oAhB + D * NA,
+                       kFloats = oK + NA * P;
+};
+
+template <int D, int NA, int P, int MH, int HH, int TPB, int RS>
+__global__ void __launch_bounds__(TPB) of_drc_reg_kernel(const OfArgs a) {
+  using Lay = DrcRegLayout<D, NA, P, MH, HH>;
+  constexpr int FP = MH * P;
+  extern __shared__ __align__(16) float smem[];
+  const DlcOfParams& Pm = a.p;
+  const int64_t nt = (int64_t)blockIdx.x * TPB + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t nw0 = nt - lane;                       // first env of this warp
+  if (nw0 >= Pm.N) return;                             // (warp-uniform)
+  const bool live = nt < Pm.N;                         // idle lanes of the last warp shadow its last env, store nothing
+  const int64_t env = live ? nt : Pm.N - 1;
+  float* const sm = smem + threadIdx.x;
+  auto S = [&](int off) -> float& { return sm[off * TPB]; };
+  const bool closed = RS > 0 || Pm.mode == DLC_MODE_CLOSED_LOOP;
+  const size_t eD = Pm.shared_dynamics ? 0 : (size_t)env;
+  float A[D][D], Th[NA][FP], yn[FP], x[D], s[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) A[i][j] = __ldg(a.A + eD * D * D + i * D + j);
+#pragma unroll
+    for (int c = 0; c < NA; ++c) S(Lay::oB + i * NA + c) = __ldg(a.B + eD * D * NA + i * NA + c);
+    x[i] = closed ? a.x_io[(size_t)env * D + i] : 0.f;
+    s[i] = 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < P; ++q)
+#pragma unroll
+    for (int j = 0; j < D; ++j) S(Lay::oC + q * D + j) = __ldg(a.C + eD * P * D + q * D + j);
+#pragma unroll
+  for (int i = 0; i < NA * P; ++i) S(Lay::oK + i) = a.K ? __ldg(a.K + eD * NA * P + i) : 0.f;   // _drc.py:104
+  // the action ring: logical us[i] (newest first) sits in slot (head + i) mod h
+  for (int i = 0; i < HH * NA; ++i) S(Lay::oUs + i) = a.us_io[(size_t)env * HH * NA + i];
+  int head = 0;
+  int status = 0;
+  bool bad = false;
+  // A^h B column by column (h applications of A each), and s = sum_i A^i B us[i] by Horner from the oldest action
+  // (before M and the y_nat window are loaded: the setup then fits the register file)
+  {
+    float nb2 = 0.f, na2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NA; ++c) {
+      float v[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        v[i] = S(Lay::oB + i * NA + c);
+        nb2 = fmaf(v[i], v[i], nb2);
+      }
+#pragma unroll 1
+      for (int k = 0; k < HH; ++k) {
+        float nv[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < D; ++j) acc = fmaf(A[i][j], v[j], acc);
+          nv[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) v[i] = nv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        S(Lay::oAhB + i * NA + c) = v[i];
+        na2 = fmaf(v[i], v[i], na2);
+      }
+    }
+    // the truncated response does not decay (or is not finite): the recursion would not contract.  The thread stays with
+    // its warp (the row ring synchronises it) and reports nothing but the flag.
+    bad = !(na2 <= nb2);
+#pragma unroll 1
+    for (int k = HH - 1; k >= 0; --k) {
+      float ns[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fmaf(A[i][j], s[j], acc);
+#pragma unroll
+        for (int c = 0; c < NA; ++c) acc = fmaf(S(Lay::oB + i * NA + c), S(Lay::oUs + k * NA + c), acc);
+        ns[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[i] = ns[i];
+    }
+  }
+  // M[j][aa][q] -> Th[aa][j*P + q]; y_nat newest first
+#pragma unroll
+  for (int j = 0; j < MH; ++j)
+#pragma unroll
+    for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+      for (int q = 0; q < P; ++q) Th[aa][j * P + q] = a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P + q];
+#pragma unroll
+  for (int i = 0; i < FP; ++i) yn[i] = a.ynat_io[(size_t)env * FP + i];
+  const uint32_t genv = (uint32_t)(Pm.env_offset + env);
+  double csum = 0.0;
+  // RS > 0 (closed loop, W from HBM, 16-byte tileable rows): the disturbance rows arrive through the warp's cp.async
+  // ring (row_ring.cuh) RS steps ahead and are read where the env step needs them -- no registers held across the step
+  using Ring = WarpRowRing<D, RS ? RS : 4>;
+  Ring ring;
+  if constexpr (RS > 0) {
+    const int64_t left = Pm.N - nw0;
+    ring.init(reinterpret_cast<unsigned char*>(smem + Lay::kFloats * TPB) + (size_t)(threadIdx.x >> 5) * Ring::kBytesPerWarp,
+              a.W + nw0 * D, Pm.N * D, (int)(left < 32 ? left : 32), lane, live ? lane : 0);
+    ring.prime(Pm.T);
+  }
+  const bool store_cost = a.cost_out != nullptr && live, store_u = a.u_out != nullptr && live;
+
+#pragma unroll 1
+  for (int t = 0; t < Pm.T; ++t) {
+    float w[D] = {};
+    if (RS == 0 && closed) {
+      if (a.W) {
+        const float* wr = a.W + ((size_t)t * Pm.N + env) * D;
+        if (D % 2 == 0) {
+#pragma unroll
+          for (int i = 0; i < D / 2; ++i) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(wr) + i);
+            w[2 * i] = v.x; w[2 * i + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < D; ++i) w[i] = __ldg(wr + i);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < (D + 3) / 4; ++g) {
+          float z4[4];
+          normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
+        }
+      }
+    }
+    const float lr = Pm.decay ? Pm.lr / (float)(Pm.t0 + t + 1) : 1.0f;  // _drc.py:184: without decay the rate is 1.0 (sic)
+    float y[P], gu[P], u[NA], act[NA];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+      if (closed) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fmaf(S(Lay::oC + q * D + j), x[j], acc);
+        y[q] = acc;
+      } else {
+        y[q] = a.y_in[((size_t)t * Pm.N + env) * P + q];
+      }
+      // gu = sum_i G[i] us[i] = C s     (_drc.py:169)
+      float g = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) g = fmaf(S(Lay::oC + q * D + j), s[j], g);
+      gu[q] = g;
+    }
+    // y_nat: shift by one position (newest first), y_nat[0] = y - gu    (_drc.py:169-171)
+#pragma unroll
+    for (int i = FP - 1; i >= P; --i) yn[i] = yn[i - P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) yn[q] = y[q] - gu[q];
+    // mdot = sum_{j,q} M[j][.][q] y_nat[j][q];  u = -K y + mdot;  final = y_nat[0] + gu;  act = 2 (-K final + mdot)
+#pragma unroll
+    for (int aa = 0; aa < NA; ++aa) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < FP; ++i) part = fmaf(Th[aa][i], yn[i], part);
+      float ky = 0.f, kf = 0.f;
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        const float kq = S(Lay::oK + aa * P + q);
+        ky = fmaf(kq, y[q], ky);
+        kf = fmaf(kq, yn[q] + gu[q], kf);
+      }
+      u[aa] = part - ky;
+      act[aa] = 2.f * (part - kf);
+    }
+    // M <- M - lr * 2 act (x) y_nat, then the norm clip   (_drc.py:181-193)
+    {
+      float nrm = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) {
+        const float g = -lr * act[aa];
+#pragma unroll
+        for (int i = 0; i < FP; ++i) {
+          Th[aa][i] = fmaf(g, yn[i], Th[aa][i]);
+          nrm = fmaf(Th[aa][i], Th[aa][i], nrm);
+        }
+      }
+      nrm = sqrtf(nrm);
+      if (nrm > Pm.R_M) {
+        const float sc = Pm.R_M / nrm;
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+          for (int i = 0; i < FP; ++i) Th[aa][i] *= sc;
+      }
+    }
+    // us: shift, us[0] = u (_drc.py:196-197); the oldest action leaves the window and s follows
+    {
+      head = head == 0 ? HH - 1 : head - 1;
+      float uo[NA];
+#pragma unroll
+      for (int c = 0; c < NA; ++c) {
+        uo[c] = S(Lay::oUs + head * NA + c);
+        S(Lay::oUs + head * NA + c) = u[c];
+      }
+      float ns[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fmaf(A[i][j], s[j], acc);
+#pragma unroll
+        for (int c = 0; c < NA; ++c) acc = fmaf(-S(Lay::oAhB + i * NA + c), uo[c], acc);
+        ns[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) s[i] = ns[i];   // (+ B u below: the env step forms the same product)
+    }
+    // ---- realised cost quad_loss(y, u), outputs
+    float c = 0.f;
+#pragma unroll
+    for (int q = 0; q < P; ++q) c = fmaf(y[q], y[q], c);
+#pragma unroll
+    for (int k = 0; k < NA; ++k) c = fmaf(u[k], u[k], c);
+    if (store_cost) a.cost_out[(size_t)t * Pm.N + env] = c;
+    csum += (double)c;
+    if (!isfinite(c)) status |= DLC_STATUS_NONFINITE;
+    if (store_u)
+#pragma unroll
+      for (int k = 0; k < NA; ++k) a.u_out[((size_t)t * Pm.N + env) * NA + k] = u[k];
+    // ---- env step x <- A x + B u + w    (_lds.py:107-109)
+    {
+      if constexpr (RS > 0) {
+        const int st = t & (RS - 1);
+        const uint32_t row = ring.acquire(st);
+        static_assert(RS == 0 || D % 2 == 0, "rows are read as 8-byte pairs");
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) {
+          const float2 v = lds_f2(row + 8u * i);
+          w[2 * i] = v.x; w[2 * i + 1] = v.y;
+        }
+        ring.release(st, t + RS < Pm.T);
+      }
+      float xn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float bu = 0.f;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) bu = fmaf(S(Lay::oB + i * NA + k), u[k], bu);
+        s[i] += bu;
+        float acc = bu;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fmaf(A[i][j], x[j], acc);
+        xn[i] = acc + w[i];
+      }
+      if (closed)
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = xn[i];
+    }
+  }
+  // ---- write the state back
+  if (!live) return;
+  if (bad) {
+    if (a.cost_sum_out) a.cost_sum_out[env] = (double)nanf("");
+    if (a.status_out) a.status_out[env] = DLC_STATUS_BAD_HINT;
+    return;
+  }
+  if (closed)
+#pragma unroll
+    for (int i = 0; i < D; ++i) a.x_io[(size_t)env * D + i] = x[i];
+#pragma unroll
+  for (int j = 0; j < MH; ++j)
+#pragma unroll
+    for (int aa = 0; aa < NA; ++aa)
+#pragma unroll
+      for (int q = 0; q < P; ++q) a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P + q] = Th[aa][j * P + q];
+#pragma unroll
+  for (int i = 0; i < FP; ++i) a.ynat_io[(size_t)env * FP + i] = yn[i];
+  for (int i = 0; i < HH; ++i) {
+    int sl = head + i; if (sl >= HH) sl -= HH;
+#pragma unroll
+    for (int c = 0; c < NA; ++c) a.us_io[(size_t)env * HH * NA + i * NA + c] = S(Lay::oUs + sl * NA + c);
+  }
+  if (a.cost_sum_out) a.cost_sum_out[env] = csum;
+  if (a.status_out) a.status_out[env] = status;
+}
+
 // the shape served by the feature-blocked instance of_kernel<FGRC, 32, 10, 3, 2, 30, 121, 61> (DSC(m = 30, h = 10) on the
 // colab's system) unless the caller forces 8 or 16 lanes
 bool of_feature_blocked(const DlcOfParams& P) {
@@ -1424,6 +1728,22 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
     kern<<<(unsigned)((p->N + TPB - 1) / TPB), TPB, smem, (cudaStream_t)stream>>>(a);
     return cuda_status(cudaGetLastError(), "of_grc_reg_kernel launch");
   }
+  if (p->agent == DLC_OF_DRC && p->d == 10 && p->n == 3 && p->p == 2 && p->m == 10 && p->h == 50 &&
+      (p->flags & DLC_OF_FLAG_STABLE_A) && p->lanes_per_env == 0) {
+    // DRC(m = 10, h = 50) on the colab's system with a decaying truncated response: register-resident thread-per-env kernel
+    constexpr int TPB = 64;
+    size_t smem = (size_t)DrcRegLayout<10, 3, 2, 10, 50>::kFloats * TPB * sizeof(float);
+    auto kern = of_drc_reg_kernel<10, 3, 2, 10, 50, TPB, 0>;
+    const char* renv = getenv("DLC_ROW_RING");   // profiling switch: 0 = disturbance rows through registers
+    if ((!renv || atoi(renv) > 0) && p->mode == DLC_MODE_CLOSED_LOOP && p->T > 2 && WarpRowRing<10, 4>::usable(W, p->N)) {
+      kern = of_drc_reg_kernel<10, 3, 2, 10, 50, TPB, 4>;
+      smem += (TPB / 32) * WarpRowRing<10, 4>::kBytesPerWarp;
+    }
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) return cuda_status(e2, "cudaFuncSetAttribute(of_drc_reg_kernel)");
+    kern<<<(unsigned)((p->N + TPB - 1) / TPB), TPB, smem, (cudaStream_t)stream>>>(a);
+    return cuda_status(cudaGetLastError(), "of_drc_reg_kernel launch");
+  }
   // lanes per env from the widest per-step contraction (lanes_per_env = 8 / 16 / 32 overrides)
   const int width = p->agent == DLC_OF_LQG ? p->d : (p->d > a.FP ? p->d : a.FP);
   int GL = width <= 20 ? 8 : (width <= 48 ? 16 : 32);   // measured: GRC / DRC / LQG 8, SFC (22 wide) 16, DSC 32
@@ -1437,7 +1757,7 @@ extern "C" int32_t dlc_lds_of_rollout_f32(const DlcOfParams* p, const float* A, 
     GL = p->lanes_per_env;
   }
   else if (p->lanes_per_env != 0) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: lanes_per_env must be 0 (automatic), 8, 16 or 32");
-  if (p->flags & ~DLC_OF_FLAG_PHI_IDENTITY) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: unknown flag bits");
+  if (p->flags & ~(DLC_OF_FLAG_PHI_IDENTITY | DLC_OF_FLAG_STABLE_A)) return fail(DLC_ERR_ARG, "dlc_lds_of_rollout_f32: unknown flag bits");
   // groups of one warp hit the same offsets of their slices at once: a slice stride of GL (mod 32) banks keeps
   // their unit-stride accesses apart
   // (for the window-blocked SFC instance a stride of 16 mod 32 would spread its 8-byte feature-row reads over all even

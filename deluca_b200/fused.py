@@ -615,7 +615,7 @@ def lds_lqr_value_and_grad(A, B, K, x0, T, W=None, seed=0, env_offset=0, t0=0, w
 def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, Phi=None, theta=None, z=None,
                    ynat=None, us=None, m=0, h=0, t0=0, lr=0.005, decay=True, R_M=10.0, seed=0, env_offset=0,
                    w_std=0.5, agent_only=False, keep_costs=True, keep_actions=True, donate=False, lanes_per_env=0, phi_is_identity=False,
-                   env_t0=None):
+                   stable_a=False, env_t0=None):
     """``dlc_lds_of_rollout_f32``: T fused steps of the partially observed LDS (``deluca/envs/_lds.py:102-111``,
     y = C x) under an output-feedback controller: ``agent`` = "lqg" (``_lqg.py:83-98``; K[.,n,d], Lk[.,d,p],
     z = x_hat), "drc" (``_drc.py:131-203``; theta = M[N,m,n,p], ynat[N,m,p] and us[N,h,n] newest first,
@@ -623,7 +623,8 @@ def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, 
     ynat[N,L+m,p] oldest -> newest).  State tensors default to the agents' construction-time zeros; the returned
     ones (and ``t``) resume the episode.  ``agent_only``: ``Agent.__call__(y)`` with y = ``y_in[T,N,p]``.
     ``lanes_per_env``: 0 (automatic) or 8 / 16 / 32 lanes of a warp per env.  ``phi_is_identity``: the caller's
-    promise that ``Phi`` is the identity (GRC); verified on the device.  ``t0``: the agent's step counter (lr decay);
+    promise that ``Phi`` is the identity (GRC); ``stable_a``: the promise that the truncated response decays,
+    ``|A^h B|_F <= |B|_F`` (DRC: ``DLC_OF_FLAG_STABLE_A``); both verified on the device.  ``t0``: the agent's step counter (lr decay);
     ``env_t0``: the env's (counter of the in-kernel disturbance stream; defaults to ``t0``)."""
     shared = A.dim() == 2
     d, n, p = A.shape[-1], B.shape[-1], C.shape[-2]
@@ -667,7 +668,7 @@ def lds_of_rollout(A, B, C, x, T, *, agent, W=None, y_in=None, K=None, Lk=None, 
     prm = _abi.DlcOfParams(N=N, env_offset=int(env_offset), T=T, d=d, n=n, p=p, agent=code, m=int(m), h=int(h), F=F,
                            L=L, t0=int(t0), decay=int(bool(decay)), shared_dynamics=int(shared),
                            mode=1 if agent_only else 0, lr=float(lr), R_M=float(R_M), w_std=float(w_std),
-                           lanes_per_env=int(lanes_per_env), flags=int(bool(phi_is_identity)), seed=int(seed),
+                           lanes_per_env=int(lanes_per_env), flags=int(bool(phi_is_identity)) | (2 * int(bool(stable_a))), seed=int(seed),
                            env_t0=int(t0 if env_t0 is None else env_t0))
     costs = torch.empty(T, N, device=dev) if keep_costs else None
     U = torch.empty(T, N, n, device=dev) if keep_actions else None

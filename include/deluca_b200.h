@@ -44,7 +44,7 @@ extern "C" {
 /* per-env status bits written by the kernels */
 #define DLC_STATUS_NONFINITE 1   /* a NaN/Inf appeared in the env's state or cost */
 #define DLC_STATUS_NOT_PD 2      /* Q_uu not positive definite in the Riccati backward pass */
-#define DLC_STATUS_BAD_HINT 4    /* a caller's hint did not hold (DlcOfParams.reserved = 1 with Phi != I): nothing computed, cost_sum = NaN */
+#define DLC_STATUS_BAD_HINT 4    /* a caller's hint did not hold (DlcOfParams.flags: Phi != I, or |A^h B| > |B|): nothing computed, cost_sum = NaN */
 
 int32_t dlc_abi_version(void);
 /* sizeof() of the parameter structs as compiled, so a binding can verify its own layout:
@@ -538,11 +538,14 @@ typedef struct DlcOfParams {
   float w_std;         /* std of the in-kernel Gaussian disturbance, used when W == NULL */
   int32_t lanes_per_env; /* 0 = automatic; 8, 16 or 32 forces that many lanes per env (tuning / tests) */
   uint64_t seed;
-  int32_t flags;       /* DLC_OF_FLAG_*: bit 0 = the caller asserts Phi == I (GRC), which unlocks the register-resident kernel
-                          on the colab's system (verified on the device: DLC_STATUS_BAD_HINT); ignored by LQG / DRC */
+  int32_t flags;       /* DLC_OF_FLAG_*: bit 0 = the caller asserts Phi == I (GRC), bit 1 = the caller asserts that the truncated
+                          response decays, |A^h B|_F <= |B|_F (DRC: sum_i G[i] us[i] is then carried as the d-vector
+                          recursion s <- A s + B u - A^h B u_old); each unlocks a register-resident kernel on the colab's
+                          system and is verified on the device (DLC_STATUS_BAD_HINT); bits an agent has no use for are ignored */
   int32_t env_t0;      /* ENV step counter at entry: counter of the in-kernel disturbance stream (see DlcLdsParams.env_t0) */
 } DlcOfParams;
 #define DLC_OF_FLAG_PHI_IDENTITY 1
+#define DLC_OF_FLAG_STABLE_A 2
 
 /* shared memory one env needs (bytes), 0 for an invalid shape */
 size_t dlc_lds_of_smem_bytes(const DlcOfParams* p);

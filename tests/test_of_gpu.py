@@ -114,6 +114,68 @@ def test_drc_matches_oracle(d, n, p, m, h, decay):
     np.testing.assert_allclose(res.us.cpu().numpy(), st["us"], rtol=1e-3, atol=1e-4 * np.abs(st["us"]).max())
 
 
+@pytest.mark.parametrize("decay", [True, False])
+def test_drc_register_kernel(decay):
+    """DRC(m = 10, h = 50) on the colab's system with DLC_OF_FLAG_STABLE_A: the thread-per-env kernel that carries
+    sum_i G[i] us[i] as the recursion s <- A s + B u - A^h B u_old (exact algebra of _drc.py:97-102,169).  Held to the
+    float64 oracle of the as-written sums, to the lane-group kernel, across a resumed call (s is re-formed from the
+    stored history) and on the in-kernel disturbance stream; a system whose truncated response grows is refused."""
+    from deluca_b200.fused import lds_of_rollout
+    N, T, d, n, p, m, h = 70, 400, 10, 3, 2, 10, 50
+    A, B, C, x0, W, rng = _sys(N, d, n, p, T, seed=77, w_std=0.5 if decay else 0.02)
+    K = (0.05 * rng.standard_normal((N, n, p))).astype(np.float32)
+    M0 = (0.03 * rng.standard_normal((N, m, n, p))).astype(np.float32)
+    RM = 1000.0 if decay else 0.05
+    ref = O.rollout_of(A, B, C, x0, W, "drc", dtype=np.float64, K=K, M0=M0, h=h, lr_scale=0.03, decay=decay, RM=RM)
+    common = dict(agent="drc", K=_dev(K), m=m, h=h, lr=0.03, decay=decay, R_M=RM)
+    dA, dB, dC = _dev(A), _dev(B), _dev(C)
+    res = lds_of_rollout(dA, dB, dC, _dev(x0), T, W=_dev(W), theta=_dev(M0), stable_a=True, **common)
+    _check(res, ref)
+    st = ref["state"]
+    np.testing.assert_allclose(res.theta.cpu().numpy(), st["M"], rtol=1e-3, atol=1e-4 * np.abs(st["M"]).max())
+    np.testing.assert_allclose(res.ynat.cpu().numpy(), st["y_nat"], rtol=1e-3, atol=1e-4 * np.abs(st["y_nat"]).max())
+    np.testing.assert_allclose(res.us.cpu().numpy(), st["us"], rtol=1e-3, atol=1e-4 * np.abs(st["us"]).max())
+    lanes = lds_of_rollout(dA, dB, dC, _dev(x0), T, W=_dev(W), theta=_dev(M0), **common)
+    np.testing.assert_allclose(res.costs.cpu().numpy(), lanes.costs.cpu().numpy(), rtol=2e-4, atol=1e-5)
+    # resumed: 130 + 270 steps == 400 steps (to rounding: the second call re-forms s from us by Horner)
+    r1 = lds_of_rollout(dA, dB, dC, _dev(x0), 130, W=_dev(W[:130]), theta=_dev(M0), stable_a=True, **common)
+    r2 = lds_of_rollout(dA, dB, dC, r1.x, T - 130, W=_dev(W[130:]), theta=r1.theta, ynat=r1.ynat, us=r1.us,
+                        stable_a=True, **dict(common, t0=r1.t))
+    np.testing.assert_allclose(torch.cat([r1.costs, r2.costs]).cpu().numpy(), res.costs.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(r2.x.cpu().numpy(), res.x.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    # the env's own disturbance stream (in-kernel Philox) on both kernels
+    a = lds_of_rollout(dA, dB, dC, _dev(x0), T, theta=_dev(M0), seed=5, w_std=0.3 if decay else 0.02, stable_a=True, **common)
+    b = lds_of_rollout(dA, dB, dC, _dev(x0), T, theta=_dev(M0), seed=5, w_std=0.3 if decay else 0.02, **common)
+    np.testing.assert_allclose(a.costs.cpu().numpy(), b.costs.cpu().numpy(), rtol=2e-4, atol=1e-5)
+    # Agent.__call__ on its own (observations given)
+    y_in = _dev((0.3 * rng.standard_normal((40, N, p))).astype(np.float32))
+    a = lds_of_rollout(dA, dB, dC, None, 40, y_in=y_in, agent_only=True, theta=_dev(M0), stable_a=True, **common)
+    b = lds_of_rollout(dA, dB, dC, None, 40, y_in=y_in, agent_only=True, theta=_dev(M0), **common)
+    np.testing.assert_allclose(a.U.cpu().numpy(), b.U.cpu().numpy(), rtol=2e-4, atol=1e-6)
+    # a broken promise: the response of A = 1.02 I grows over the window
+    Abad = A.copy()
+    Abad[3] = 1.02 * np.eye(d, dtype=np.float32)
+    bad = lds_of_rollout(_dev(Abad), dB, dC, _dev(x0), 10, W=_dev(W[:10]), theta=_dev(M0), stable_a=True, **common)
+    stt = bad.status.cpu().numpy()
+    assert stt[3] == 4 and (np.delete(stt, 3) == 0).all() and np.isnan(bad.cost_sum.cpu().numpy()[3])
+
+
+def test_drc_mirror_sets_the_stability_flag():
+    from deluca_b200.agents import DRC
+    N, T, d, n, p = 40, 120, 10, 3, 2
+    A, B, C, x0, W, rng = _sys(N, d, n, p, T, seed=78)
+    ag = DRC(_dev(A), _dev(B), _dev(C))
+    assert ag.stable_a
+    M0 = (0.03 * rng.standard_normal((N, 10, n, p))).astype(np.float32)
+    res = ag.rollout(_dev(x0), T, W=_dev(W), st=ag.init(N, M=M0))
+    ref = O.rollout_of(A, B, C, x0, W, "drc", dtype=np.float64, K=np.zeros((N, n, p), np.float32), M0=M0, h=50,
+                       lr_scale=0.03, decay=True, RM=1000.0)
+    _check(res, ref)
+    Abad = A.copy()
+    Abad[0] = 1.02 * np.eye(d, dtype=np.float32)
+    assert not DRC(_dev(Abad), _dev(B), _dev(C)).stable_a
+
+
 @pytest.mark.parametrize("d,n,p,shared", [(10, 3, 2, False), (10, 3, 2, True), (6, 2, 6, False), (40, 4, 3, False)])
 def test_lqg_matches_oracle(d, n, p, shared):
     from deluca_b200.fused import lds_of_rollout

@@ -66,7 +66,7 @@ out = {"workload": f"partially observed LDS(d={d}, n={n}, p={p}), {N} envs x T={
        "fp32_peak_tflops": fp32_peak, "agents": {}}
 # DSC's default controller state is 35 KB per env (121 filters x 61 taps): a smaller batch keeps the tool quick
 cases = [("grc", dict(m=10), (N, T)), ("sfc", dict(m=30, h=10), (N, T)), ("dsc", dict(m=30, h=10), (148 * 256, 100)),
-         ("drc", dict(m=10, h=50), (N, T)), ("lqg", {}, (N, T))]
+         ("drc", dict(m=10, h=50), (N, T)), ("drc_lanes", dict(m=10, h=50), (N, T)), ("lqg", {}, (N, T))]
 full = (A, B, C, x0, W, N, T)
 for name, kw, (Nc, Tc) in cases:
     if args.only and name != args.only:
@@ -84,11 +84,12 @@ for name, kw, (Nc, Tc) in cases:
                                            keep_actions=False, lanes_per_env=args.lanes,
                                            phi_is_identity=(name == "grc" and not args.lanes))
         fl = flops_fgrc(F, L, kw["m"])
-    elif name == "drc":
+    elif name in ("drc", "drc_lanes"):   # drc: the register-resident kernel (stable_a); drc_lanes: 8 lanes per env
         theta = 0.03 * torch.randn(N, kw["m"], n, p, device=dev, generator=g)
         K = torch.zeros(N, n, p, device=dev)
         run = lambda: fused.lds_of_rollout(A, B, C, x0, T, agent="drc", W=W, K=K, theta=theta, m=kw["m"], h=kw["h"],
-                                           lr=0.03, R_M=1000.0, keep_actions=False, lanes_per_env=args.lanes)
+                                           lr=0.03, R_M=1000.0, keep_actions=False, lanes_per_env=args.lanes,
+                                           stable_a=(name == "drc"))
         fl = flops_drc(kw["m"], kw["h"])
     else:
         K = 0.03 * torch.randn(N, n, d, device=dev, generator=g)

@@ -1049,9 +1049,14 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
   const int64_t env = env_raw;
   float* const sm = smem + threadIdx.x;
   auto S = [&](int off) -> float& { return sm[off * TPB]; };
+  // the y_nat ring as 8-byte slots [slot][thread] (p = 2: a slot IS one (q = 0, q = 1) pair, a window is MH consecutive
+  // slots), so every window element pair is one LDS.64 feeding one fma.rn.f32x2 per action row
+  static_assert(P == 2 && Lay::oRing == 0, "the packed ring assumes two observations per slot at the start of the slice");
+  f2* const ring2 = reinterpret_cast<f2*>(smem) + threadIdx.x;
   const bool closed = Pm.mode == DLC_MODE_CLOSED_LOOP;
   const size_t eD = Pm.shared_dynamics ? 0 : (size_t)env;
-  float A[D][D], Th[NA][FP], x[D], z[D];
+  float A[D][D], x[D], z[D];
+  f2 Th[NA][MH];   // Theta[f][aa][.] as the pair (q = 0, q = 1)
 #pragma unroll
   for (int i = 0; i < D; ++i) {
 #pragma unroll
@@ -1070,13 +1075,13 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
   for (int f = 0; f < MH; ++f)
 #pragma unroll
     for (int aa = 0; aa < NA; ++aa)
-#pragma unroll
-      for (int q = 0; q < P; ++q) Th[aa][f * P + q] = a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P + q];
+      Th[aa][f] = pk(a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P],
+                     a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P + 1]);
   // y_nat ring, oldest -> newest, mirrored
-  for (int i = 0; i < R * P; ++i) {
-    const float v = a.ynat_io[(size_t)env * R * P + i];
-    S(Lay::oRing + i) = v;
-    S(Lay::oRing + R * P + i) = v;
+  for (int i = 0; i < R; ++i) {
+    const f2 v = pk(a.ynat_io[(size_t)env * R * P + 2 * i], a.ynat_io[(size_t)env * R * P + 2 * i + 1]);
+    ring2[i * TPB] = v;
+    ring2[(i + R) * TPB] = v;
   }
   // Markov operators G[j][q][aa] = (C A^j B)[q][aa], j < m            (_grc.py:97-105 collapsed, see the file header)
   {
@@ -1166,15 +1171,18 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
     }
     // ---- get_action: the newest window of the history as it stands (_grc.py:157-169)
     {
-      const float* win = sm + (Lay::oRing + (ybase + MH) * P) * TPB;
+      const f2* win = ring2 + (ybase + MH) * TPB;
+      f2 acc[NA];
 #pragma unroll
-      for (int aa = 0; aa < NA; ++aa) u[aa] = 0.f;
+      for (int aa = 0; aa < NA; ++aa) acc[aa] = 0ull;
 #pragma unroll
-      for (int i = 0; i < FP; ++i) {
-        const float v = win[i * TPB];
+      for (int i = 0; i < MH; ++i) {
+        const f2 v = win[i * TPB];
 #pragma unroll
-        for (int aa = 0; aa < NA; ++aa) u[aa] = fmaf(Th[aa][i], v, u[aa]);
+        for (int aa = 0; aa < NA; ++aa) acc[aa] = fma2(Th[aa][i], v, acc[aa]);
       }
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) u[aa] = lo(acc[aa]) + hi(acc[aa]);
     }
     // ---- update: z <- A z + B u; y_nat = y - C z; push (the oldest slot and its mirror take it)   (_grc.py:139-142)
     {
@@ -1190,38 +1198,41 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) z[i] = zn[i];
+      float yn[P];
 #pragma unroll
       for (int q = 0; q < P; ++q) {
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < D; ++j) s = fmaf(S(Lay::oC + q * D + j), z[j], s);
-        const float yn = y[q] - s;
-        sm[(Lay::oRing + ybase * P + q) * TPB] = yn;
-        sm[(Lay::oRing + (ybase + R) * P + q) * TPB] = yn;
+        yn[q] = y[q] - s;
       }
+      ring2[ybase * TPB] = pk(yn[0], yn[1]);
+      ring2[(ybase + R) * TPB] = pk(yn[0], yn[1]);
       ybase = (ybase + 1 == R) ? 0 : ybase + 1;
     }
-    const float* ring = sm + (Lay::oRing + ybase * P) * TPB;   // logical slot s, component q at ring[(s*P + q) * TPB]
+    const f2* ring = ring2 + ybase * TPB;   // logical slot s at ring[s * TPB]
     // ---- a(k), k = 0..m, with the parameters before the update
 #pragma unroll 1
     for (int k = 0; k < M1; ++k) {
-      const float* win = ring + k * P * TPB;
-      float acc[NA];
+      const f2* win = ring + k * TPB;
+      f2 acc[NA];
 #pragma unroll
-      for (int aa = 0; aa < NA; ++aa) acc[aa] = 0.f;
+      for (int aa = 0; aa < NA; ++aa) acc[aa] = 0ull;
 #pragma unroll
-      for (int i = 0; i < FP; ++i) {
-        const float v = win[i * TPB];
+      for (int i = 0; i < MH; ++i) {
+        const f2 v = win[i * TPB];
 #pragma unroll
-        for (int aa = 0; aa < NA; ++aa) acc[aa] = fmaf(Th[aa][i], v, acc[aa]);
+        for (int aa = 0; aa < NA; ++aa) acc[aa] = fma2(Th[aa][i], v, acc[aa]);
       }
 #pragma unroll
-      for (int aa = 0; aa < NA; ++aa) S(Lay::oAct + k * NA + aa) = acc[aa];
+      for (int aa = 0; aa < NA; ++aa) S(Lay::oAct + k * NA + aa) = lo(acc[aa]) + hi(acc[aa]);
     }
     // ---- final_y = sum_{k<m} G[m-1-k] a(k) + y_nat(newest); fy = 2 final_y     (_grc.py:100-104)
     float fy[P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) fy[q] = ring[((R - 1) * P + q) * TPB];
+    {
+      const f2 newest = ring[(R - 1) * TPB];
+      fy[0] = lo(newest); fy[1] = hi(newest);
+    }
 #pragma unroll 1
     for (int k = 0; k < MH; ++k) {
 #pragma unroll
@@ -1248,26 +1259,27 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
         }
         g[aa] *= -lr;
       }
-      const float* win = ring + k * P * TPB;
+      const f2* win = ring + k * TPB;
 #pragma unroll
-      for (int i = 0; i < FP; ++i) {
-        const float v = win[i * TPB];
+      for (int i = 0; i < MH; ++i) {
+        const f2 v = win[i * TPB];
 #pragma unroll
-        for (int aa = 0; aa < NA; ++aa) Th[aa][i] = fmaf(g[aa], v, Th[aa][i]);
+        for (int aa = 0; aa < NA; ++aa) Th[aa][i] = fma2(dup(g[aa]), v, Th[aa][i]);
       }
     }
     {
-      float nrm = 0.f;
+      f2 nrm2 = 0ull;
 #pragma unroll
       for (int aa = 0; aa < NA; ++aa)
 #pragma unroll
-        for (int i = 0; i < FP; ++i) nrm = fmaf(Th[aa][i], Th[aa][i], nrm);
+        for (int i = 0; i < MH; ++i) nrm2 = fma2(Th[aa][i], Th[aa][i], nrm2);
+      const float nrm = lo(nrm2) + hi(nrm2);
       const float sc = fminf(1.0f, Pm.R_M / (sqrtf(nrm) + 1e-8f));
       if (sc < 1.0f) {
 #pragma unroll
         for (int aa = 0; aa < NA; ++aa)
 #pragma unroll
-          for (int i = 0; i < FP; ++i) Th[aa][i] *= sc;
+          for (int i = 0; i < MH; ++i) Th[aa][i] = mul2(Th[aa][i], dup(sc));
       }
     }
     // ---- realised cost quad_loss(y, u), outputs
@@ -1307,10 +1319,15 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
 #pragma unroll
   for (int f = 0; f < MH; ++f)
 #pragma unroll
-    for (int aa = 0; aa < NA; ++aa)
-#pragma unroll
-      for (int q = 0; q < P; ++q) a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P + q] = Th[aa][f * P + q];
-  for (int i = 0; i < R * P; ++i) a.ynat_io[(size_t)env * R * P + i] = sm[(Lay::oRing + ybase * P + i) * TPB];
+    for (int aa = 0; aa < NA; ++aa) {
+      a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P] = lo(Th[aa][f]);
+      a.theta_io[(size_t)env * MH * NA * P + (f * NA + aa) * P + 1] = hi(Th[aa][f]);
+    }
+  for (int i = 0; i < R; ++i) {
+    const f2 v = ring2[(ybase + i) * TPB];
+    a.ynat_io[(size_t)env * R * P + 2 * i] = lo(v);
+    a.ynat_io[(size_t)env * R * P + 2 * i + 1] = hi(v);
+  }
   if (a.cost_sum_out) a.cost_sum_out[env] = csum;
   if (a.status_out) a.status_out[env] = status;
 }

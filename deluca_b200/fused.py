@@ -5,6 +5,7 @@ tensors are torch CUDA tensors used purely as device-memory handles; every numbe
 by ``libdeluca_b200.so``.
 """
 import ctypes
+import os
 from typing import NamedTuple, Optional
 
 import torch

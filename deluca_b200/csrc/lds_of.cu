@@ -25,6 +25,8 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include <type_traits>
+
 #include "f2.cuh"
 #include "row_ring.cuh"
 
@@ -1034,7 +1036,7 @@ __global__ void __launch_bounds__(128) of_lqg_reg_kernel(const OfArgs a) {
 template <int D, int NA, int P, int MH>
 struct GrcRegLayout {
   static constexpr int R = 2 * MH, FP = MH * P, M1 = MH + 1;
-  static constexpr int oRing = 0, oAct = oRing + 2 * R * P, oG = oAct + M1 * NA, oB = oG + MH * P * NA,
+  static constexpr int oRing = 0, oG = oRing + 2 * R * P, oB = oG + MH * P * NA,
                        oC = oB + D * NA, kFloats = oC + P * D;
 };
 
@@ -1131,31 +1133,6 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
   }
 
   for (int t = 0; t < Pm.T; ++t) {
-    float w[D];
-    if (closed) {
-      if (a.W) {
-        const float* wr = a.W + ((size_t)t * Pm.N + env) * D;
-        if (D % 2 == 0) {   // rows of an even d start on 8-byte boundaries: half the load instructions
-#pragma unroll
-          for (int i = 0; i < D / 2; ++i) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(wr) + i);
-            w[2 * i] = v.x; w[2 * i + 1] = v.y;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < D; ++i) w[i] = __ldg(wr + i);
-        }
-      } else {
-#pragma unroll
-        for (int g = 0; g < (D + 3) / 4; ++g) {
-          float z4[4];
-          normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
-        }
-      }
-    }
     const float lr = Pm.decay ? Pm.lr / (float)(Pm.t0 + t + 1) : Pm.lr;  // _grc.py:145
     float y[P], u[NA];
 #pragma unroll
@@ -1212,68 +1189,130 @@ __global__ void __launch_bounds__(TPB) of_grc_reg_kernel(const OfArgs a) {
     }
     const f2* ring = ring2 + ybase * TPB;   // logical slot s at ring[s * TPB]
     // ---- a(k), k = 0..m, with the parameters before the update
-#pragma unroll 1
-    for (int k = 0; k < M1; ++k) {
-      const f2* win = ring + k * TPB;
-      f2 acc[NA];
-#pragma unroll
-      for (int aa = 0; aa < NA; ++aa) acc[aa] = 0ull;
-#pragma unroll
-      for (int i = 0; i < MH; ++i) {
-        const f2 v = win[i * TPB];
-#pragma unroll
-        for (int aa = 0; aa < NA; ++aa) acc[aa] = fma2(Th[aa][i], v, acc[aa]);
-      }
-#pragma unroll
-      for (int aa = 0; aa < NA; ++aa) S(Lay::oAct + k * NA + aa) = lo(acc[aa]) + hi(acc[aa]);
-    }
-    // ---- final_y = sum_{k<m} G[m-1-k] a(k) + y_nat(newest); fy = 2 final_y     (_grc.py:100-104)
-    float fy[P];
+    // (windows k .. k + NW - 1 overlap in all but NW - 1 slots: a group per trip reads MH + NW - 1 slots once and runs
+    // NW x NA independent chains -- the kernel is latency-bound at six warps per SM, so the chains are what it needs)
+    float fy[P], aM[NA];
     {
       const f2 newest = ring[(R - 1) * TPB];
       fy[0] = lo(newest); fy[1] = hi(newest);
     }
+    auto act_windows = [&](int k0, auto nwc) {
+      constexpr int NW = decltype(nwc)::value;
+      const f2* win = ring + k0 * TPB;
+      f2 acc[NW][NA];
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa) acc[w][aa] = 0ull;
+#pragma unroll
+      for (int i = 0; i < MH + NW - 1; ++i) {
+        const f2 v = win[i * TPB];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+          if (i - w >= 0 && i - w < MH) {
+#pragma unroll
+            for (int aa = 0; aa < NA; ++aa) acc[w][aa] = fma2(Th[aa][i - w], v, acc[w][aa]);
+          }
+      }
+      // final_y = sum_{k<m} G[m-1-k] a(k) + y_nat(newest) (_grc.py:100-104) rides along: a(k) is still in registers,
+      // and only a(m) is needed again (the seed of the newest window)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        float ak[NA];
+#pragma unroll
+        for (int aa = 0; aa < NA; ++aa) ak[aa] = lo(acc[w][aa]) + hi(acc[w][aa]);
+        if (k0 + w == MH) {
+#pragma unroll
+          for (int aa = 0; aa < NA; ++aa) aM[aa] = ak[aa];
+        } else {
+#pragma unroll
+          for (int q = 0; q < P; ++q)
+#pragma unroll
+            for (int aa = 0; aa < NA; ++aa)
+              fy[q] = fmaf(S(Lay::oG + ((MH - 1 - (k0 + w)) * P + q) * NA + aa), ak[aa], fy[q]);
+        }
+      }
+    };
+    constexpr int NWG = 4, NFULL = M1 / NWG, NREST = M1 % NWG;
 #pragma unroll 1
-    for (int k = 0; k < MH; ++k) {
+    for (int k = 0; k < NFULL * NWG; k += NWG) act_windows(k, std::integral_constant<int, NWG>{});
+    if constexpr (NREST > 0) act_windows(NFULL * NWG, std::integral_constant<int, NREST>{});
+    // ---- this step's disturbance row: asked for here (not at the top of the step) so that it is not live during the
+    // window pass, the phase with the most registers in use; the update below covers its latency
+    float w[D];
+    if (closed) {
+      if (a.W) {
+        const float* wr = a.W + ((size_t)t * Pm.N + env) * D;
+        if (D % 2 == 0) {   // rows of an even d start on 8-byte boundaries: half the load instructions
 #pragma unroll
-      for (int q = 0; q < P; ++q)
+          for (int i = 0; i < D / 2; ++i) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(wr) + i);
+            w[2 * i] = v.x; w[2 * i + 1] = v.y;
+          }
+        } else {
 #pragma unroll
-        for (int aa = 0; aa < NA; ++aa)
-          fy[q] = fmaf(S(Lay::oG + ((MH - 1 - k) * P + q) * NA + aa), S(Lay::oAct + k * NA + aa), fy[q]);
+          for (int i = 0; i < D; ++i) w[i] = __ldg(wr + i);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < (D + 3) / 4; ++g) {
+          float z4[4];
+          normal4(Pm.seed, genv, (uint32_t)(Pm.env_t0 + t), (uint32_t)g, 0u, z4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * g + k < D) w[4 * g + k] = __fmul_rn(Pm.w_std, z4[k]);
+        }
+      }
     }
+    // ---- fy = 2 final_y
 #pragma unroll
     for (int q = 0; q < P; ++q) fy[q] *= 2.f;
     // ---- Theta <- Theta - lr * sum_k g(k) phi(k)^T, g(m) = 2 a(m), g(k) = G[m-1-k]^T fy      (_grc.py:144-151)
-#pragma unroll 1
-    for (int k = 0; k < M1; ++k) {
-      float g[NA];
+    auto seed_of = [&](int k, float (&g)[NA]) {   // -lr g(k)
 #pragma unroll
       for (int aa = 0; aa < NA; ++aa) {
+        float s;
         if (k == MH) {
-          g[aa] = 2.f * S(Lay::oAct + k * NA + aa);
+          s = 2.f * aM[aa];
         } else {
-          float s = 0.f;
+          s = 0.f;
 #pragma unroll
           for (int q = 0; q < P; ++q) s = fmaf(S(Lay::oG + ((MH - 1 - k) * P + q) * NA + aa), fy[q], s);
-          g[aa] = s;
         }
-        g[aa] *= -lr;
+        g[aa] = -lr * s;
       }
-      const f2* win = ring + k * TPB;
+    };
+    auto grad_windows = [&](int k0, auto nwc) {
+      constexpr int NW = decltype(nwc)::value;
+      float g[NW][NA];
 #pragma unroll
-      for (int i = 0; i < MH; ++i) {
+      for (int w = 0; w < NW; ++w) seed_of(k0 + w, g[w]);
+      const f2* win = ring + k0 * TPB;
+#pragma unroll
+      for (int i = 0; i < MH + NW - 1; ++i) {
         const f2 v = win[i * TPB];
 #pragma unroll
-        for (int aa = 0; aa < NA; ++aa) Th[aa][i] = fma2(dup(g[aa]), v, Th[aa][i]);
+        for (int w = 0; w < NW; ++w)
+          if (i - w >= 0 && i - w < MH) {
+#pragma unroll
+            for (int aa = 0; aa < NA; ++aa) Th[aa][i - w] = fma2(dup(g[w][aa]), v, Th[aa][i - w]);
+          }
       }
-    }
+    };
+#pragma unroll 1
+    for (int k = 0; k < NFULL * NWG; k += NWG) grad_windows(k, std::integral_constant<int, NWG>{});
+    if constexpr (NREST > 0) grad_windows(NFULL * NWG, std::integral_constant<int, NREST>{});
     {
-      f2 nrm2 = 0ull;
+      f2 nrm2[NA];   // (a chain per action row)
 #pragma unroll
-      for (int aa = 0; aa < NA; ++aa)
+      for (int aa = 0; aa < NA; ++aa) {
+        nrm2[aa] = 0ull;
 #pragma unroll
-        for (int i = 0; i < MH; ++i) nrm2 = fma2(Th[aa][i], Th[aa][i], nrm2);
-      const float nrm = lo(nrm2) + hi(nrm2);
+        for (int i = 0; i < MH; ++i) nrm2[aa] = fma2(Th[aa][i], Th[aa][i], nrm2[aa]);
+      }
+      float nrm = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) nrm += lo(nrm2[aa]) + hi(nrm2[aa]);
       const float sc = fminf(1.0f, Pm.R_M / (sqrtf(nrm) + 1e-8f));
       if (sc < 1.0f) {
 #pragma unroll

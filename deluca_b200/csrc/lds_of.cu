@@ -1403,7 +1403,9 @@ __global__ void __launch_bounds__(TPB) of_drc_reg_kernel(const OfArgs a) {
   auto S = [&](int off) -> float& { return sm[off * TPB]; };
   const bool closed = RS > 0 || Pm.mode == DLC_MODE_CLOSED_LOOP;
   const size_t eD = Pm.shared_dynamics ? 0 : (size_t)env;
-  float A[D][D], Th[NA][FP], yn[FP], x[D], s[D];
+  static_assert(P == 2, "M and the y_nat window are held as (q = 0, q = 1) pairs");
+  float A[D][D], x[D], s[D];
+  f2 Th[NA][MH], yn[MH];   // M[j][aa][.] and y_nat[j][.] as packed pairs: every FMA on them is a fma.rn.f32x2
 #pragma unroll
   for (int i = 0; i < D; ++i) {
 #pragma unroll
@@ -1479,10 +1481,10 @@ __global__ void __launch_bounds__(TPB) of_drc_reg_kernel(const OfArgs a) {
   for (int j = 0; j < MH; ++j)
 #pragma unroll
     for (int aa = 0; aa < NA; ++aa)
+      Th[aa][j] = pk(a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P],
+                     a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P + 1]);
 #pragma unroll
-      for (int q = 0; q < P; ++q) Th[aa][j * P + q] = a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P + q];
-#pragma unroll
-  for (int i = 0; i < FP; ++i) yn[i] = a.ynat_io[(size_t)env * FP + i];
+  for (int i = 0; i < MH; ++i) yn[i] = pk(a.ynat_io[(size_t)env * FP + 2 * i], a.ynat_io[(size_t)env * FP + 2 * i + 1]);
   const uint32_t genv = (uint32_t)(Pm.env_offset + env);
   double csum = 0.0;
   // RS > 0 (closed loop, W from HBM, 16-byte tileable rows): the disturbance rows arrive through the warp's cp.async
@@ -1544,44 +1546,49 @@ __global__ void __launch_bounds__(TPB) of_drc_reg_kernel(const OfArgs a) {
     }
     // y_nat: shift by one position (newest first), y_nat[0] = y - gu    (_drc.py:169-171)
 #pragma unroll
-    for (int i = FP - 1; i >= P; --i) yn[i] = yn[i - P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) yn[q] = y[q] - gu[q];
+    for (int i = MH - 1; i >= 1; --i) yn[i] = yn[i - 1];
+    const float yn0[P] = {y[0] - gu[0], y[1] - gu[1]};
+    yn[0] = pk(yn0[0], yn0[1]);
     // mdot = sum_{j,q} M[j][.][q] y_nat[j][q];  u = -K y + mdot;  final = y_nat[0] + gu;  act = 2 (-K final + mdot)
 #pragma unroll
     for (int aa = 0; aa < NA; ++aa) {
-      float part = 0.f;
+      f2 part2 = 0ull;
 #pragma unroll
-      for (int i = 0; i < FP; ++i) part = fmaf(Th[aa][i], yn[i], part);
+      for (int i = 0; i < MH; ++i) part2 = fma2(Th[aa][i], yn[i], part2);
+      const float part = lo(part2) + hi(part2);
       float ky = 0.f, kf = 0.f;
 #pragma unroll
       for (int q = 0; q < P; ++q) {
         const float kq = S(Lay::oK + aa * P + q);
         ky = fmaf(kq, y[q], ky);
-        kf = fmaf(kq, yn[q] + gu[q], kf);
+        kf = fmaf(kq, yn0[q] + gu[q], kf);
       }
       u[aa] = part - ky;
       act[aa] = 2.f * (part - kf);
     }
     // M <- M - lr * 2 act (x) y_nat, then the norm clip   (_drc.py:181-193)
     {
-      float nrm = 0.f;
+      f2 nrm2[NA];   // (a chain per action row)
 #pragma unroll
       for (int aa = 0; aa < NA; ++aa) {
-        const float g = -lr * act[aa];
+        const f2 g = dup(-lr * act[aa]);
+        nrm2[aa] = 0ull;
 #pragma unroll
-        for (int i = 0; i < FP; ++i) {
-          Th[aa][i] = fmaf(g, yn[i], Th[aa][i]);
-          nrm = fmaf(Th[aa][i], Th[aa][i], nrm);
+        for (int i = 0; i < MH; ++i) {
+          Th[aa][i] = fma2(g, yn[i], Th[aa][i]);
+          nrm2[aa] = fma2(Th[aa][i], Th[aa][i], nrm2[aa]);
         }
       }
+      float nrm = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < NA; ++aa) nrm += lo(nrm2[aa]) + hi(nrm2[aa]);
       nrm = sqrtf(nrm);
       if (nrm > Pm.R_M) {
-        const float sc = Pm.R_M / nrm;
+        const f2 sc = dup(Pm.R_M / nrm);
 #pragma unroll
         for (int aa = 0; aa < NA; ++aa)
 #pragma unroll
-          for (int i = 0; i < FP; ++i) Th[aa][i] *= sc;
+          for (int i = 0; i < MH; ++i) Th[aa][i] = mul2(Th[aa][i], sc);
       }
     }
     // us: shift, us[0] = u (_drc.py:196-197); the oldest action leaves the window and s follows
@@ -1661,11 +1668,15 @@ __global__ void __launch_bounds__(TPB) of_drc_reg_kernel(const OfArgs a) {
 #pragma unroll
   for (int j = 0; j < MH; ++j)
 #pragma unroll
-    for (int aa = 0; aa < NA; ++aa)
+    for (int aa = 0; aa < NA; ++aa) {
+      a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P] = lo(Th[aa][j]);
+      a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P + 1] = hi(Th[aa][j]);
+    }
 #pragma unroll
-      for (int q = 0; q < P; ++q) a.theta_io[(size_t)env * MH * NA * P + (j * NA + aa) * P + q] = Th[aa][j * P + q];
-#pragma unroll
-  for (int i = 0; i < FP; ++i) a.ynat_io[(size_t)env * FP + i] = yn[i];
+  for (int i = 0; i < MH; ++i) {
+    a.ynat_io[(size_t)env * FP + 2 * i] = lo(yn[i]);
+    a.ynat_io[(size_t)env * FP + 2 * i + 1] = hi(yn[i]);
+  }
   for (int i = 0; i < HH; ++i) {
     int sl = head + i; if (sl >= HH) sl -= HH;
 #pragma unroll

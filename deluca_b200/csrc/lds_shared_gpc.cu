@@ -226,6 +226,7 @@ __global__ void hist_out_kernel(StateArgs a) {
 // ------------------------------------------------------------------------------------------------ M stream
 struct StreamArgs {
   int64_t N, Npad;
+  int64_t env0, nenv;  // this launch streams envs [env0, env0 + nenv) (one CTA each)
   int base;            // ring slot of hist_t[0]
   float* M;            // [N][H][MM][D]
   const float* Hring;  // [Npad][2H][D]
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
   float* sG = reinterpret_cast<float*>(sM + (size_t)kStages * H * NT);   // [MM][H]
   float* sV = sG + MM * H;                                               // [NW][MM][H]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t env = blockIdx.x;
+  const int64_t env = a.env0 + blockIdx.x;
   const int k0 = 2 * tid;
 
   float* Mp = a.M + (size_t)env * H * MM * D + k0;
@@ -432,6 +433,8 @@ __global__ void __launch_bounds__(D / 2) gpc_m_stream_kernel(StreamArgs a) {
 // ------------------------------------------------------------------------------------------------ shared chain
 struct ChainArgs {
   int64_t N, Npad;
+  int tile0, tile_end;  // this launch covers the kE-env tiles [tile0, tile_end); a CTA takes tile0 + blockIdx.x and
+                        // strides by gridDim.x (grid == tile count: one tile per CTA; a smaller grid: persistent CTAs)
   int base;        // ring slot of hist_t[0]
   int first;       // first step of this call: cost_sum / status are initialised
   float nlr;       // -lr_t
@@ -534,9 +537,11 @@ __global__ void __launch_bounds__(kThreadsA, 1) gpc_shared_chain_kernel(ChainArg
   float* ZA = sW + kWS * SWBUF;                      // [DM][kE]
   float* ZB = ZA + (size_t)DM * kE;
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
-  const int64_t env0 = (int64_t)blockIdx.x * kE;
-  const int nvalid = (int)min((int64_t)kE, a.N - env0);
   auto slot = [&](int j) { return (a.base + j) % P; };
+#pragma unroll 1
+  for (int tile = a.tile0 + (int)blockIdx.x; tile < a.tile_end; tile += (int)gridDim.x) {
+  const int64_t env0 = (int64_t)tile * kE;
+  const int nvalid = (int)min((int64_t)kE, a.N - env0);
 
   // ---- S0: x_t and v_{H-1} (the action's window product)
   load_rows(ZA, 0, D, a.Xw, a.Npad, env0, tid);
@@ -756,6 +761,8 @@ __global__ void __launch_bounds__(kThreadsA, 1) gpc_shared_chain_kernel(ChainArg
       }
     }
   }
+  __syncthreads();   // the next tile's loads overwrite ZA / ZB
+  }  // tile loop
 }
 
 // q_0 = sum_h Ab^{H-2-h} hist[h+H+1] by Horner's rule on the entry history (once per call)
@@ -828,7 +835,7 @@ struct Launch {
   // fwd: 0 none, 1 all windows from M (+ the Gram matrix), 2 incremental (needs upd and a previous fwd launch)
   template <int ST>
   static void stream_st(const StreamArgs& a, bool upd, int fwd, cudaStream_t s) {
-    const dim3 grid((unsigned)a.N), block(D / 2);
+    const dim3 grid((unsigned)a.nenv), block(D / 2);
     const size_t sm = smem_stream(ST);
     if (upd && fwd == 2) gpc_m_stream_kernel<D, MM, H, true, 2, ST><<<grid, block, sm, s>>>(a);
     else if (upd && fwd == 1) gpc_m_stream_kernel<D, MM, H, true, 1, ST><<<grid, block, sm, s>>>(a);
@@ -838,8 +845,11 @@ struct Launch {
   static void stream(const StreamArgs& a, bool upd, int fwd, cudaStream_t s) {
     if (stages() == 3) stream_st<3>(a, upd, fwd, s); else if (stages() == 5) stream_st<5>(a, upd, fwd, s); else stream_st<4>(a, upd, fwd, s);
   }
-  static void chain(const ChainArgs& a, cudaStream_t s) {
-    gpc_shared_chain_kernel<D, MM, H><<<(unsigned)(a.Npad / kE), kThreadsA, smem_chain(), s>>>(a);
+  // ctas = 0: one CTA per tile; otherwise at most `ctas` persistent CTAs stride over the tiles
+  static void chain(const ChainArgs& a, cudaStream_t s, int ctas = 0) {
+    const int nt = a.tile_end - a.tile0;
+    const unsigned grid = (unsigned)((ctas > 0 && ctas < nt) ? ctas : nt);
+    gpc_shared_chain_kernel<D, MM, H><<<grid, kThreadsA, smem_chain(), s>>>(a);
   }
   static void q_init(const ChainArgs& a, cudaStream_t s) {
     gpc_q_init_kernel<D, MM, H><<<(unsigned)(a.Npad / kE), kThreadsA, smem_chain(), s>>>(a);
@@ -967,27 +977,97 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
   // profiling switch (timing only, results are then meaningless): 1 = stream kernel only, 2 = chain kernel only
   const char* denv = getenv("DLC_SGPC_DBG");
   const int dbg = denv ? atoi(denv) : 0;
-  for (int step = 0; step < p->T; ++step) {
+  sa.env0 = 0; sa.nenv = p->N;
+  const int ntiles = (int)(L.Npad / kE);
+  ca.tile0 = 0; ca.tile_end = ntiles;
+  // Two-half software pipeline (DLC_SGPC_PIPE: 1 = on, 0 = off, unset = on from 4 grid waves of chain tiles): the chain
+  // of one half of the envs runs on a few persistent CTAs (DLC_SGPC_CHAIN_CTAS, one per SM: 225 KB of shared memory
+  // each) of a high-priority stream WHILE the M stream of the other half runs on the remaining SMs.  The two kernels of
+  // a slot start together (both wait for both kernels of the previous slot), the chain CTAs are dispatched first and
+  // keep their SMs, the stream CTAs fill the rest.  Per env the launches and their arguments are the serial loop's, so
+  // the results are bit-identical to it.  Measured (56,832 envs, profiles/r02_probe_c5_pipeline.json): serial 23.60 ms
+  // per step; 12 / 16 / 18 / 20 / 24 chain CTAs 30.9 / 25.1 / 24.1 / 23.2 / 23.7 ms -- a small gain only, because the M
+  // stream's rate scales with the SMs it has (it is bound by issue latency at 8 warps per SM).  Not used
+  // while the caller's stream is being captured into a graph.
+  const char* penv = getenv("DLC_SGPC_PIPE");
+  const char* cenv = getenv("DLC_SGPC_CHAIN_CTAS");
+  const int chain_ctas = (cenv && atoi(cenv) > 0) ? atoi(cenv) : 20;
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess) { (void)cudaGetLastError(); capturing = cudaStreamCaptureStatusActive; }
+  const bool pipe = dbg == 0 && ntiles >= 2 && capturing == cudaStreamCaptureStatusNone &&
+                    (penv ? atoi(penv) != 0 : ntiles >= 4 * 148);
+  auto launch_stream = [&](int64_t env0, int64_t nenv, int step, bool upd, int fwd, cudaStream_t q) {
+    sa.env0 = env0; sa.nenv = nenv; sa.base = step % P;
+    if (big) Launch<256, 64, 16>::stream(sa, upd, fwd, q); else Launch<64, 32, 4>::stream(sa, upd, fwd, q);
+  };
+  auto launch_chain = [&](int tile0, int tile_end, int step, cudaStream_t q, int ctas) {
     const int t = p->t0 + step;
-    const int base = step % P;
-    sa.base = base;
-    if (dbg != 2) {
-      const int fwd = (step > 0 && !fullfwd) ? 2 : 1;
-      if (big) Launch<256, 64, 16>::stream(sa, step > 0, fwd, s); else Launch<64, 32, 4>::stream(sa, step > 0, fwd, s);
-    }
-    ca.base = base;
+    ca.tile0 = tile0; ca.tile_end = tile_end;
+    ca.base = step % P;
     ca.first = step == 0;
     const double lr = p->decay ? (double)p->lr_scale * (1.0 / (double)(t + 1)) : (double)p->lr_scale;
     ca.nlr = -(float)lr;
     ca.W = W ? W + (size_t)step * p->N * d : nullptr;
     ca.cost_out = cost_out ? cost_out + (size_t)step * p->N : nullptr;
     ca.xprev_out = (step == p->T - 1) ? xprev_io : nullptr;
-    if (dbg != 1) {
-      if (big) Launch<256, 64, 16>::chain(ca, s); else Launch<64, 32, 4>::chain(ca, s);
+    if (big) Launch<256, 64, 16>::chain(ca, q, ctas); else Launch<64, 32, 4>::chain(ca, q, ctas);
+  };
+  if (pipe) {
+    int lo = 0, hi = 0;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t evS[2] = {nullptr, nullptr}, evC[2] = {nullptr, nullptr};
+    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&evS[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&evC[i], cudaEventDisableTiming);
     }
+    const int tA = ntiles / 2;                                   // half A = tiles [0, tA), half B = [tA, ntiles)
+    const int64_t nA = (int64_t)tA * kE, nB = p->N - nA;
+    const int T = p->T;
+    // slot 0: stream(A, 0); slot 2t+1: chain(A, t) | stream(B, t); slot 2t+2: chain(B, t) | stream(A, t+1) (the
+    // update-only launch when t+1 == T); slot 2T+1: the update-only stream(B)
+    bool on_s2 = false;
+    for (int k = 0; k <= 2 * T + 1 && e == cudaSuccess; ++k) {
+      if (k > 0) {   // both kernels of this slot wait for both kernels of the previous one
+        e = cudaEventRecord(evS[k & 1], s);
+        if (e == cudaSuccess && on_s2) e = cudaEventRecord(evC[k & 1], s2);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, evS[k & 1], 0);
+        if (e == cudaSuccess && on_s2) e = cudaStreamWaitEvent(s, evC[k & 1], 0);
+        if (e != cudaSuccess) break;
+      }
+      const bool half_b = (k & 1) != 0;                          // the half whose M stream runs in this slot
+      const int sstep = k / 2;                                   // its step
+      on_s2 = false;
+      if (k >= 1 && k <= 2 * T) {                                // chain of the other half, first and prioritised
+        const int cstep = (k - 1) / 2;
+        if (half_b) launch_chain(0, tA, cstep, s2, chain_ctas); else launch_chain(tA, ntiles, cstep, s2, chain_ctas);
+        on_s2 = true;
+      }
+      const bool last = sstep == T;                              // update-only launch closing the call
+      const int fwd = last ? 0 : ((sstep > 0 && !fullfwd) ? 2 : 1);
+      launch_stream(half_b ? nA : 0, half_b ? nB : nA, sstep, sstep > 0, fwd, s);
+    }
+    // (after the last slot nothing is pending on s2: its last kernel was joined into s before stream(B) was launched)
+    const cudaError_t le = cudaGetLastError();
+    if (s2) cudaStreamDestroy(s2);
+    for (int i = 0; i < 2; ++i) {
+      if (evS[i]) cudaEventDestroy(evS[i]);
+      if (evC[i]) cudaEventDestroy(evC[i]);
+    }
+    if (e != cudaSuccess) return cuda_status(e, "lds_shared_gpc pipeline (stream / event)");
+    if (le != cudaSuccess) return cuda_status(le, "lds_shared_gpc launch");
+    sa.env0 = 0; sa.nenv = p->N;
+  } else {
+  for (int step = 0; step < p->T; ++step) {
+    if (dbg != 2) {
+      const int fwd = (step > 0 && !fullfwd) ? 2 : 1;
+      launch_stream(0, p->N, step, step > 0, fwd, s);
+    }
+    if (dbg != 1) launch_chain(0, ntiles, step, s, 0);
   }
-  sa.base = p->T % P;
-  if (big) Launch<256, 64, 16>::stream(sa, true, 0, s); else Launch<64, 32, 4>::stream(sa, true, 0, s);
+  launch_stream(0, p->N, p->T, true, 0, s);
+  }
   st.base = p->T % P;
   to_env_major_kernel<<<dim3(nb, (d + 31) / 32), tb, 0, s>>>(st.Xw, x_io, p->N, d, L.Npad);
   if (hist_io) hist_out_kernel<<<(unsigned)((p->N * P * d + 255) / 256), 256, 0, s>>>(st);

@@ -140,6 +140,43 @@ def test_shared_gpc_agrees_with_the_per_env_kernel():
     assert torch.allclose(a.M, b.M, rtol=1e-3, atol=1e-4 * float(a.M.abs().max()))
 
 
+@pytest.mark.parametrize("d,m,H,N,T,ctas", [(64, 32, 4, 300, 9, 1), (64, 32, 4, 130, 1, 18), (64, 32, 4, 65, 5, 2),
+                                            (256, 64, 16, 200, 4, 1)])
+def test_shared_gpc_two_half_pipeline_is_bit_identical(d, m, H, N, T, ctas, monkeypatch):
+    """The two-half software pipeline (chain of one half on a few persistent CTAs of a second stream while the other
+    half's M stream runs) launches, per env, exactly what the serial loop launches: every output must be bit-equal.
+    `ctas` < tiles per half exercises the persistent tile loop of the chain kernel; resuming exercises q_init."""
+    from deluca_b200.fused import lds_shared_gpc_rollout
+    A, B, K = _system(d, m, seed=21)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x0 = torch.randn(N, d, device="cuda", generator=g)
+    W = 0.5 * torch.randn(T + 3, N, d, device="cuda", generator=g)
+    t = lambda a: torch.as_tensor(a).cuda()
+
+    def run():
+        a = lds_shared_gpc_rollout(t(A), t(B), t(K), x0, T, H=H, W=W[:T].contiguous(), lr_scale=0.002)
+        b = lds_shared_gpc_rollout(t(A), t(B), t(K), a.x, 3, H=H, W=W[T:].contiguous(), lr_scale=0.002,
+                                   M=a.M, hist=a.hist, xprev=a.xprev, t0=a.t)
+        torch.cuda.synchronize()
+        return a, b
+
+    monkeypatch.setenv("DLC_SGPC_PIPE", "0")
+    sa, sb = run()
+    monkeypatch.setenv("DLC_SGPC_PIPE", "1")
+    monkeypatch.setenv("DLC_SGPC_CHAIN_CTAS", str(ctas))
+    pa, pb = run()
+    bad = []
+    for tag, ser, pip in (("first call", sa, pa), ("resumed call", sb, pb)):
+        for name in ("costs", "x", "M", "hist", "xprev", "cost_sum", "status"):
+            u, v = getattr(ser, name), getattr(pip, name)
+            if not torch.equal(u, v):
+                diff = (u.double() - v.double()).abs()
+                envs = torch.nonzero(diff.reshape(-1, N).sum(0) if name == "costs" else diff.reshape(N, -1).sum(1)).flatten()
+                bad.append((tag, name, float(diff.max()), envs[:8].tolist(), int(envs.numel())))
+    assert not bad, bad
+    assert float(sb.M.abs().max()) > 0      # (the resumed call: a T = 1 call from a zero history leaves M = 0)
+
+
 def test_shared_gpc_rejects_unsupported_shapes():
     from deluca_b200.fused import lds_shared_gpc_rollout
     z = lambda *s: torch.zeros(*s, device="cuda")

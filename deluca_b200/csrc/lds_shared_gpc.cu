@@ -980,7 +980,7 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
   sa.env0 = 0; sa.nenv = p->N;
   const int ntiles = (int)(L.Npad / kE);
   ca.tile0 = 0; ca.tile_end = ntiles;
-  // Two-half software pipeline (DLC_SGPC_PIPE: 1 = on, 0 = off, unset = on from 4 grid waves of chain tiles): the chain
+  // Two-half software pipeline (opt-in: DLC_SGPC_PIPE=1; the gain is within run-to-run noise, see below): the chain
   // of one half of the envs runs on a few persistent CTAs (DLC_SGPC_CHAIN_CTAS, one per SM: 225 KB of shared memory
   // each) of a high-priority stream WHILE the M stream of the other half runs on the remaining SMs.  The two kernels of
   // a slot start together (both wait for both kernels of the previous slot), the chain CTAs are dispatched first and
@@ -995,7 +995,7 @@ extern "C" int32_t dlc_lds_shared_gpc_rollout_f32(const DlcSharedGpcParams* p, c
   cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &capturing) != cudaSuccess) { (void)cudaGetLastError(); capturing = cudaStreamCaptureStatusActive; }
   const bool pipe = dbg == 0 && ntiles >= 2 && capturing == cudaStreamCaptureStatusNone &&
-                    (penv ? atoi(penv) != 0 : ntiles >= 4 * 148);
+                    (penv && atoi(penv) != 0);
   auto launch_stream = [&](int64_t env0, int64_t nenv, int step, bool upd, int fwd, cudaStream_t q) {
     sa.env0 = env0; sa.nenv = nenv; sa.base = step % P;
     if (big) Launch<256, 64, 16>::stream(sa, upd, fwd, q); else Launch<64, 32, 4>::stream(sa, upd, fwd, q);
